@@ -1,0 +1,68 @@
+/* ldb_datagen.h — C-ABI of the deterministic TPC-H-shaped table generator.
+ *
+ * Not part of the reference's runtime surface: the reference gets its tables from dbgen + COPY
+ * (tools/generate/tpch.sh, resources/sql/tpch/initialize.sql).  BASELINE.json asks for
+ * "generator-synthesised tables"; this generator produces them directly in the reference's Arrow
+ * physical column layout (src/runtime/storage/LingoDBTable.cpp:122-195) on the host
+ * (libldb_datagen_host.so) and on the device (ldb_gpu_datagen_* in libldb_gpu.so), bit-identically.
+ */
+#ifndef LDB_DATAGEN_H
+#define LDB_DATAGEN_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct LdbGenScale {
+   uint64_t seed;
+   int64_t n_orders, n_customer, n_supplier, n_part;
+   int64_t n_lineitem; /* derived: closed-form prefix of the per-order line counts */
+} LdbGenScale;
+
+/* Column buffers; NULL = skip the column.  decimal columns are 16 bytes/value. */
+typedef struct LdbGenLineitemCols {
+   int32_t* l_orderkey;
+   int32_t* l_partkey;
+   int32_t* l_suppkey;
+   uint8_t* l_quantity;      /* decimal128(12,2) */
+   uint8_t* l_extendedprice; /* decimal128(12,2) */
+   uint8_t* l_discount;      /* decimal128(12,2) */
+   uint8_t* l_tax;           /* decimal128(12,2) */
+   int32_t* l_returnflag;    /* fixed_size_binary(4) */
+   int32_t* l_linestatus;    /* fixed_size_binary(4) */
+   int32_t* l_shipdate;      /* date32 */
+   int32_t* l_commitdate;
+   int32_t* l_receiptdate;
+} LdbGenLineitemCols;
+
+typedef struct LdbGenOrdersCols {
+   int32_t* o_orderkey;
+   int32_t* o_custkey;
+   int32_t* o_orderdate; /* date32 */
+   int32_t* o_shippriority;
+} LdbGenOrdersCols;
+
+typedef struct LdbGenCustomerCols {
+   int32_t* c_custkey;
+   int32_t* c_nationkey;
+   int32_t* c_mktsegment_offsets; /* utf8 offsets, n_rows + 1 */
+   uint8_t* c_mktsegment_data;
+} LdbGenCustomerCols;
+
+typedef struct LdbGenSupplierCols {
+   int32_t* s_suppkey;
+   int32_t* s_nationkey;
+} LdbGenSupplierCols;
+
+/* host side (libldb_datagen_host.so) */
+void ldbgen_scale(double sf, uint64_t seed, LdbGenScale* out);
+int64_t ldbgen_order_first_line(const LdbGenScale* g, int64_t order_idx);
+void ldbgen_lineitem_host(const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenLineitemCols* cols);
+void ldbgen_orders_host(const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenOrdersCols* cols);
+int64_t ldbgen_customer_host(const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenCustomerCols* cols);
+void ldbgen_supplier_host(const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenSupplierCols* cols);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,521 @@
+// oracle/port/pipelines.cpp — TEST INFRASTRUCTURE ONLY (CPU oracle; never on the product path).
+//
+// Hand-restated output of the reference's SubOpToControlFlow lowering for TPC-H Q6, Q1, Q3, Q5:
+// what the JIT'd `main()` and its per-morsel functions do, calling the runtime objects (`rt::`)
+// exactly where generated code calls them (SURVEY.md §3.2–3.4).  The compiler cannot be built in
+// this container, so this file stands in for its output; value semantics come from values.h.
+//
+//   table scan loop        SubOpToControlFlow.cpp:1123-1203 (+951-983 loads)
+//   materialize (build)    :2538  → rt::GrowingBuffer::insert, tuple {next, hash, keys, values}
+//                          (layout from SpecializeSubOpPass.cpp:79-88)
+//   HashIndexedView probe  :2558-2586, chain walk :2254-2313
+//   group-by               :3065-3157 (pre-aggregation fragment lookup-or-insert), reduce :3719-3769,
+//                          merge functions :1861-1939
+//   group-join (Q3)        :2730-2839 pure lookup + :4218-4251 entry lock
+//   keyless aggregate      :1733-1781, :3966-3993 (SimpleState)
+#include "pipelines.h"
+#include "scan.h"
+
+#include <algorithm>
+#include <chrono>
+
+namespace oracle {
+namespace {
+
+constexpr bool parallelScan = true;
+
+struct HivView { // first 16 bytes of a HashIndexedView, as generated code reads them (:2573-2575)
+   struct Entry {
+      Entry* next;
+      uint64_t hashValue;
+   };
+   Entry** ht;
+   size_t mask;
+};
+// lookup in a HashIndexedView: slot load, bloom-tag check, untag (:2566-2584; LowerToLLVM.cpp:568-616)
+inline HivView::Entry* hivLookup(rt::HashIndexedView* v, uint64_t hash) {
+   auto* h = reinterpret_cast<HivView*>(v);
+   HivView::Entry* p = h->ht[hash & h->mask];
+   return rt::matchesTag(p, hash) ? rt::untag(p) : nullptr;
+}
+struct PartitionedHtView { // PreAggregationHashtable read as struct{Entry** ht; size_t mask;}[64] (:2765-2772)
+   struct P {
+      rt::PreAggregationHashtableFragment::Entry** ht;
+      size_t mask;
+   } parts[64];
+};
+inline rt::PreAggregationHashtableFragment::Entry* preAggrLookup(rt::PreAggregationHashtable* t, uint64_t hash) {
+   auto* v = reinterpret_cast<PartitionedHtView*>(t);
+   auto& p = v->parts[hash & 63];
+   if (!p.ht) return nullptr;
+   auto* e = p.ht[(hash >> 6) & p.mask];
+   return rt::matchesTag(e, hash) ? rt::untag(e) : nullptr;
+}
+
+template <class T>
+rt::ThreadLocal* threadLocalBuffers() { return rt::GrowingBuffer::createThreadLocal(sizeof(T)); }
+
+double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+} // namespace
+
+// =====================================================================================  Q6
+// select sum(l_extendedprice * l_discount) from lineitem where l_shipdate >= A and l_shipdate < B
+//   and l_discount between C and D and l_quantity < E          (resources/sql/tpch/6.sql)
+// All four predicates are column-vs-constant → pushed into the scan (Pushdown.cpp:300-405).
+// l_extendedprice * l_discount : decimal(12,2)*decimal(12,2) = decimal(24,4) → i128 (DBOps.cpp:98-107).
+Q6Result runQ6(const HostTable& lineitem, const Q6Params& p) {
+   rt::QueryContextScope scope;
+   double t0 = now();
+   struct State {
+      i128 sum;
+   };
+   auto* tl = rt::ThreadLocal::create([](uint8_t*) -> uint8_t* {
+      auto* s = (State*) rt::SimpleState::create(sizeof(State));
+      s->sum = 0;
+      return (uint8_t*) s; }, nullptr);
+   std::vector<FilterDescription> filters = {
+      {"l_shipdate", 0, FilterOp::GTE, p.shipdateGe},
+      {"l_shipdate", 0, FilterOp::LT, p.shipdateLt},
+      {"l_discount", 0, FilterOp::GTE, p.discountGe},
+      {"l_discount", 0, FilterOp::LTE, p.discountLe},
+      {"l_quantity", 0, FilterOp::LT, p.quantityLt},
+   };
+   scanTable(lineitem, {"l_extendedprice", "l_discount"}, filters, [&](rt::BatchView* b) {
+      auto* st = (State*) tl->getLocal();
+      ColReader ext(b, 0), disc(b, 1);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         i128 prod = wrapMul((i128) ext.dec64(idx), (i128) disc.dec64(idx));
+         st->sum = wrapAdd(st->sum, prod);
+      }
+   });
+   auto* merged = (State*) rt::SimpleState::merge(tl, [](uint8_t* d, uint8_t* s) { ((State*) d)->sum = wrapAdd(((State*) d)->sum, ((State*) s)->sum); });
+   Q6Result r;
+   r.revenue = merged->sum;
+   r.seconds = now() - t0;
+   return r;
+}
+
+// =====================================================================================  Q1
+// (resources/sql/tpch/1.sql) l_shipdate <= const is pushed down; group by (l_returnflag, l_linestatus)
+// through per-worker pre-aggregation fragments and the 64-partition merge.
+//   1 - l_discount              : decimal(19,0) const rescaled to scale 2 (=100) minus decimal(12,2) → decimal(21,2) i128
+//   ext * (1 - disc)            : decimal(33,4) i128
+//   … * (1 + tax)               : decimal(38,6) i128 (precision clamped to 38, scale kept; no division)
+//   sum(decimal(12,2))          : accumulates in i64 (result type = argument type, sql_analyzer.cpp:2631)
+//   avg(x) → sum(x)/count       : SimplifyAggregations.cpp:160-181 → values.h avgDec12_2
+namespace {
+struct Q1Entry {
+   void* next;
+   uint64_t hash;
+   int32_t returnflag, linestatus; // key tuple
+   int64_t sumQty, sumBase;        // value tuple (natural alignment, i128 on 16)
+   i128 sumDiscPrice, sumCharge;
+   int64_t sumDisc, count;
+};
+static_assert(sizeof(Q1Entry) == 96);
+} // namespace
+std::vector<Q1Row> runQ1(const HostTable& lineitem, const Q1Params& p, double* seconds) {
+   rt::QueryContextScope scope;
+   double t0 = now();
+   using Frag = rt::PreAggregationHashtableFragment;
+   auto* tl = rt::ThreadLocal::create([](uint8_t*) -> uint8_t* { return (uint8_t*) Frag::create(sizeof(Q1Entry), false); }, nullptr);
+   std::vector<FilterDescription> filters = {{"l_shipdate", 0, FilterOp::LTE, p.shipdateLe}};
+   scanTable(lineitem, {"l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice", "l_discount", "l_tax"}, filters, [&](rt::BatchView* b) {
+      auto* frag = (Frag*) tl->getLocal();
+      ColReader rf(b, 0), ls(b, 1), qty(b, 2), ext(b, 3), disc(b, 4), tax(b, 5);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         int32_t kRf = rf.i32(idx), kLs = ls.i32(idx);
+         int64_t q = qty.dec64(idx), e = ext.dec64(idx), d = disc.dec64(idx), t = tax.dec64(idx);
+         i128 oneMinus = wrapSub((i128) 100, (i128) d);
+         i128 discPrice = wrapMul((i128) e, oneMinus);
+         i128 onePlus = wrapAdd((i128) 100, (i128) t);
+         i128 charge = wrapMul(discPrice, onePlus);
+         HashBuilder hb;
+         hb.addInt(kRf);
+         hb.addInt(kLs);
+         uint64_t hash = hb.total;
+         // lookup-or-insert in the 1024-slot direct-mapped cache (:3073-3156)
+         auto* cached = (Q1Entry*) frag->ht[(hash >> 6) & 1023];
+         Q1Entry* en;
+         if (cached && cached->hash == hash && cached->returnflag == kRf && cached->linestatus == kLs) {
+            en = cached;
+         } else {
+            en = (Q1Entry*) frag->insert(hash);
+            en->returnflag = kRf;
+            en->linestatus = kLs;
+            en->sumQty = en->sumBase = en->sumDisc = en->count = 0;
+            en->sumDiscPrice = en->sumCharge = 0;
+         }
+         en->sumQty = wrapAdd64(en->sumQty, q);
+         en->sumBase = wrapAdd64(en->sumBase, e);
+         en->sumDiscPrice = wrapAdd(en->sumDiscPrice, discPrice);
+         en->sumCharge = wrapAdd(en->sumCharge, charge);
+         en->sumDisc = wrapAdd64(en->sumDisc, d);
+         en->count += 1;
+      }
+   });
+   constexpr size_t contentOff = offsetof(Q1Entry, returnflag);
+   auto* merged = rt::PreAggregationHashtable::merge(
+      tl,
+      [](uint8_t* a, uint8_t* b) {
+         auto* x = (Q1Entry*) (a - contentOff);
+         auto* y = (Q1Entry*) (b - contentOff);
+         return x->returnflag == y->returnflag && x->linestatus == y->linestatus;
+      },
+      [](uint8_t* a, uint8_t* b) {
+         auto* x = (Q1Entry*) (a - contentOff);
+         auto* y = (Q1Entry*) (b - contentOff);
+         x->sumQty = wrapAdd64(x->sumQty, y->sumQty);
+         x->sumBase = wrapAdd64(x->sumBase, y->sumBase);
+         x->sumDiscPrice = wrapAdd(x->sumDiscPrice, y->sumDiscPrice);
+         x->sumCharge = wrapAdd(x->sumCharge, y->sumCharge);
+         x->sumDisc = wrapAdd64(x->sumDisc, y->sumDisc);
+         x->count += y->count;
+      });
+   std::vector<Q1Row> rows;
+   rt::BufferIterator::iterate(
+      merged->createIterator(), false, [](rt::Buffer buf, void* ctx) {
+         auto& rows = *(std::vector<Q1Row>*) ctx;
+         auto** entries = (Q1Entry**) buf.ptr;
+         for (size_t i = 0; i < buf.numElements / sizeof(Q1Entry*); i++) {
+            Q1Entry* e = entries[i];
+            Q1Row r;
+            r.returnflag = e->returnflag;
+            r.linestatus = e->linestatus;
+            r.sumQty = e->sumQty;
+            r.sumBasePrice = e->sumBase;
+            r.sumDiscPrice = e->sumDiscPrice;
+            r.sumCharge = e->sumCharge;
+            r.avgQty = avgDec12_2(e->sumQty, e->count);
+            r.avgPrice = avgDec12_2(e->sumBase, e->count);
+            r.avgDisc = avgDec12_2(e->sumDisc, e->count);
+            r.count = e->count;
+            rows.push_back(r);
+         }
+      },
+      &rows);
+   std::sort(rows.begin(), rows.end(), [](const Q1Row& a, const Q1Row& b) { return a.returnflag != b.returnflag ? a.returnflag < b.returnflag : a.linestatus < b.linestatus; });
+   *seconds = now() - t0;
+   return rows;
+}
+
+// =====================================================================================  Q3
+// (resources/sql/tpch/3.sql)  customer(BUILDING) ⋈ orders(o_orderdate < D) ⋈ lineitem(l_shipdate > D),
+// group by l_orderkey (o_orderdate, o_shippriority functionally dependent → any()), top 10.
+// Plan: hash join customer→orders, then the group-join: one map entry per
+// surviving order, lineitem does a pure lookup and reduces under the entry lock.
+namespace {
+struct CustBuildTuple {
+   void* next;
+   uint64_t hash;
+   int32_t custkey;
+};
+struct Q3Entry {
+   void* next;
+   uint64_t hash;
+   int32_t orderkey; // key
+   bool marker;      // value tuple: {marker, stored left columns, aggregates, lock}
+   int64_t orderdateNs;
+   int32_t shippriority;
+   i128 revenue;
+   rt::EntryLock lock;
+};
+} // namespace
+std::vector<Q3Row> runQ3(const HostTable& customer, const HostTable& orders, const HostTable& lineitem, const Q3Params& p, double* seconds) {
+   rt::QueryContextScope scope;
+   double t0 = now();
+   // ---- pipeline 1: customer → build side (materialize + HashIndexedView::build)
+   auto* custTl = threadLocalBuffers<CustBuildTuple>();
+   scanTable(customer, {"c_custkey"}, {{"c_mktsegment", 0, FilterOp::EQ, p.segment}}, [&](rt::BatchView* b) {
+      auto* buf = (rt::GrowingBuffer*) custTl->getLocal();
+      ColReader ck(b, 0);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         auto* t = (CustBuildTuple*) buf->insert();
+         t->next = nullptr;
+         t->custkey = ck.i32(idx);
+         t->hash = hash64((uint64_t) (int64_t) t->custkey);
+      }
+   });
+   auto* custView = rt::HashIndexedView::build(rt::GrowingBuffer::merge(custTl));
+   // ---- pipeline 2: orders probe customer, insert one group per surviving order
+   using Frag = rt::PreAggregationHashtableFragment;
+   auto* mapTl = rt::ThreadLocal::create([](uint8_t*) -> uint8_t* { return (uint8_t*) Frag::create(sizeof(Q3Entry), true); }, nullptr);
+   scanTable(orders, {"o_orderkey", "o_custkey", "o_orderdate", "o_shippriority"}, {{"o_orderdate", 0, FilterOp::LT, p.date}}, [&](rt::BatchView* b) {
+      auto* frag = (Frag*) mapTl->getLocal();
+      ColReader ok(b, 0), ck(b, 1), od(b, 2), sp(b, 3);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         int32_t custkey = ck.i32(idx);
+         uint64_t h = hash64((uint64_t) (int64_t) custkey);
+         for (auto* e = hivLookup(custView, h); e; e = e->next) {
+            auto* t = (CustBuildTuple*) e;
+            if (t->custkey != custkey) continue; // single integer key: hash compare skipped (SpecializeSubOpPass.cpp:110-118)
+            int32_t orderkey = ok.i32(idx);
+            uint64_t gh = hash64((uint64_t) (int64_t) orderkey);
+            auto* cached = (Q3Entry*) frag->ht[(gh >> 6) & 1023];
+            Q3Entry* en;
+            if (cached && cached->hash == gh && cached->orderkey == orderkey) {
+               en = cached;
+            } else {
+               en = (Q3Entry*) frag->insert(gh);
+               en->orderkey = orderkey;
+               en->marker = false;
+               en->revenue = 0;
+               rt::EntryLock::initialize(&en->lock);
+            }
+            en->orderdateNs = od.dateNs(idx);
+            en->shippriority = sp.i32(idx);
+         }
+      }
+   });
+   constexpr size_t contentOff = offsetof(Q3Entry, orderkey);
+   auto* map = rt::PreAggregationHashtable::merge(
+      mapTl,
+      [](uint8_t* a, uint8_t* b) { return ((Q3Entry*) (a - contentOff))->orderkey == ((Q3Entry*) (b - contentOff))->orderkey; },
+      [](uint8_t* a, uint8_t* b) {
+         auto* x = (Q3Entry*) (a - contentOff);
+         auto* y = (Q3Entry*) (b - contentOff);
+         x->marker |= y->marker;
+         x->revenue = wrapAdd(x->revenue, y->revenue);
+      });
+   // ---- pipeline 3: lineitem pure lookup + locked reduce
+   scanTable(lineitem, {"l_orderkey", "l_extendedprice", "l_discount"}, {{"l_shipdate", 0, FilterOp::GT, p.date}}, [&](rt::BatchView* b) {
+      ColReader ok(b, 0), ext(b, 1), disc(b, 2);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         int32_t orderkey = ok.i32(idx);
+         uint64_t h = hash64((uint64_t) (int64_t) orderkey);
+         for (auto* e = preAggrLookup(map, h); e; e = e->next) {
+            auto* en = (Q3Entry*) e;
+            if (en->hash != h || en->orderkey != orderkey) continue;
+            i128 rev = wrapMul((i128) ext.dec64(idx), wrapSub((i128) 100, (i128) disc.dec64(idx)));
+            rt::EntryLock::lock(&en->lock);
+            en->marker = true;
+            en->revenue = wrapAdd(en->revenue, rev);
+            rt::EntryLock::unlock(&en->lock);
+            break;
+         }
+      }
+   });
+   // ---- pipeline 4: scan the map, keep marked groups, top-10 by (revenue desc, o_orderdate asc).
+   // The reference's order among full ties is unspecified (LIMIT without a total order); the oracle
+   // and the GPU path both break remaining ties by l_orderkey ascending.
+   std::vector<Q3Row> rows;
+   rt::BufferIterator::iterate(
+      map->createIterator(), false, [](rt::Buffer buf, void* ctx) {
+         auto& rows = *(std::vector<Q3Row>*) ctx;
+         auto** entries = (Q3Entry**) buf.ptr;
+         for (size_t i = 0; i < buf.numElements / sizeof(Q3Entry*); i++) {
+            Q3Entry* e = entries[i];
+            if (!e->marker) continue;
+            rows.push_back(Q3Row{e->orderkey, e->revenue, (int32_t) (e->orderdateNs / 86400000000000ll), e->shippriority});
+         }
+      },
+      &rows);
+   auto cmp = [](const Q3Row& a, const Q3Row& b) {
+      if (a.revenue != b.revenue) return a.revenue > b.revenue;
+      if (a.orderdate != b.orderdate) return a.orderdate < b.orderdate;
+      return a.orderkey < b.orderkey;
+   };
+   size_t k = std::min<size_t>(10, rows.size());
+   std::partial_sort(rows.begin(), rows.begin() + k, rows.end(), cmp);
+   rows.resize(k);
+   *seconds = now() - t0;
+   return rows;
+}
+
+// =====================================================================================  Q5
+// (resources/sql/tpch/5.sql) six-way join, group by n_name.  Join order (the optimizer cannot be run
+// here; any order yields the same result): region(r_name) → nation → customer → orders(date range)
+// → lineitem, with supplier⋈nation probed on the composite key (l_suppkey, c_nationkey).
+namespace {
+struct KeyTuple { // {next, hash, key}
+   void* next;
+   uint64_t hash;
+   int32_t key;
+};
+struct NationTuple {
+   void* next;
+   uint64_t hash;
+   int32_t nationkey;
+   VarLen32 name;
+};
+struct KeyPayloadTuple { // {next, hash, key, payload}
+   void* next;
+   uint64_t hash;
+   int32_t key, payload;
+};
+struct SuppTuple {
+   void* next;
+   uint64_t hash;
+   int32_t suppkey, nationkey;
+   VarLen32 name;
+};
+struct Q5Entry {
+   void* next;
+   uint64_t hash;
+   VarLen32 name; // key
+   i128 revenue;  // value
+};
+inline uint64_t hashI32(int32_t v) { return hash64((uint64_t) (int64_t) v); }
+inline uint64_t hashI32Pair(int32_t a, int32_t b) {
+   HashBuilder hb;
+   hb.addInt(a);
+   hb.addInt(b);
+   return hb.total;
+}
+} // namespace
+std::vector<Q5Row> runQ5(const HostTable& customer, const HostTable& orders, const HostTable& lineitem, const HostTable& supplier, const HostTable& nation, const HostTable& region, const Q5Params& p, double* seconds) {
+   rt::QueryContextScope scope;
+   double t0 = now();
+   // region(r_name = X)
+   auto* regTl = threadLocalBuffers<KeyTuple>();
+   scanTable(region, {"r_regionkey"}, {{"r_name", 0, FilterOp::EQ, p.regionName}}, [&](rt::BatchView* b) {
+      auto* buf = (rt::GrowingBuffer*) regTl->getLocal();
+      ColReader rk(b, 0);
+      for (int64_t i = 0; i < b->length; i++) {
+         auto* t = (KeyTuple*) buf->insert();
+         t->next = nullptr;
+         t->key = rk.i32(b->selectionVector[i]);
+         t->hash = hashI32(t->key);
+      }
+   });
+   auto* regView = rt::HashIndexedView::build(rt::GrowingBuffer::merge(regTl));
+   // nation ⋈ region
+   auto* natTl = threadLocalBuffers<NationTuple>();
+   scanTable(nation, {"n_nationkey", "n_name", "n_regionkey"}, {}, [&](rt::BatchView* b) {
+      auto* buf = (rt::GrowingBuffer*) natTl->getLocal();
+      ColReader nk(b, 0), nn(b, 1), nr(b, 2);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         int32_t regionkey = nr.i32(idx);
+         for (auto* e = hivLookup(regView, hashI32(regionkey)); e; e = e->next) {
+            if (((KeyTuple*) e)->key != regionkey) continue;
+            auto* t = (NationTuple*) buf->insert();
+            t->next = nullptr;
+            t->nationkey = nk.i32(idx);
+            t->name = nn.str(idx);
+            t->hash = hashI32(t->nationkey);
+         }
+      }
+   });
+   auto* natView = rt::HashIndexedView::build(rt::GrowingBuffer::merge(natTl));
+   // customer ⋈ nation  → {c_custkey, c_nationkey}
+   auto* custTl = threadLocalBuffers<KeyPayloadTuple>();
+   scanTable(customer, {"c_custkey", "c_nationkey"}, {}, [&](rt::BatchView* b) {
+      auto* buf = (rt::GrowingBuffer*) custTl->getLocal();
+      ColReader ck(b, 0), cn(b, 1);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         int32_t nationkey = cn.i32(idx);
+         for (auto* e = hivLookup(natView, hashI32(nationkey)); e; e = e->next) {
+            if (((NationTuple*) e)->nationkey != nationkey) continue;
+            auto* t = (KeyPayloadTuple*) buf->insert();
+            t->next = nullptr;
+            t->key = ck.i32(idx);
+            t->payload = nationkey;
+            t->hash = hashI32(t->key);
+         }
+      }
+   });
+   auto* custView = rt::HashIndexedView::build(rt::GrowingBuffer::merge(custTl));
+   // orders(date range) ⋈ customer → {o_orderkey, c_nationkey}
+   auto* ordTl = threadLocalBuffers<KeyPayloadTuple>();
+   scanTable(orders, {"o_orderkey", "o_custkey"}, {{"o_orderdate", 0, FilterOp::GTE, p.dateGe}, {"o_orderdate", 0, FilterOp::LT, p.dateLt}}, [&](rt::BatchView* b) {
+      auto* buf = (rt::GrowingBuffer*) ordTl->getLocal();
+      ColReader ok(b, 0), ck(b, 1);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         int32_t custkey = ck.i32(idx);
+         for (auto* e = hivLookup(custView, hashI32(custkey)); e; e = e->next) {
+            auto* c = (KeyPayloadTuple*) e;
+            if (c->key != custkey) continue;
+            auto* t = (KeyPayloadTuple*) buf->insert();
+            t->next = nullptr;
+            t->key = ok.i32(idx);
+            t->payload = c->payload;
+            t->hash = hashI32(t->key);
+         }
+      }
+   });
+   auto* ordView = rt::HashIndexedView::build(rt::GrowingBuffer::merge(ordTl));
+   // supplier ⋈ nation → {s_suppkey, s_nationkey, n_name}, hashed on the composite join key
+   auto* suppTl = threadLocalBuffers<SuppTuple>();
+   scanTable(supplier, {"s_suppkey", "s_nationkey"}, {}, [&](rt::BatchView* b) {
+      auto* buf = (rt::GrowingBuffer*) suppTl->getLocal();
+      ColReader sk(b, 0), sn(b, 1);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         int32_t nationkey = sn.i32(idx);
+         for (auto* e = hivLookup(natView, hashI32(nationkey)); e; e = e->next) {
+            auto* n = (NationTuple*) e;
+            if (n->nationkey != nationkey) continue;
+            auto* t = (SuppTuple*) buf->insert();
+            t->next = nullptr;
+            t->suppkey = sk.i32(idx);
+            t->nationkey = nationkey;
+            t->name = n->name;
+            t->hash = hashI32Pair(t->suppkey, t->nationkey);
+         }
+      }
+   });
+   auto* suppView = rt::HashIndexedView::build(rt::GrowingBuffer::merge(suppTl));
+   // lineitem ⋈ orders ⋈ supplier → group by n_name
+   using Frag = rt::PreAggregationHashtableFragment;
+   auto* aggTl = rt::ThreadLocal::create([](uint8_t*) -> uint8_t* { return (uint8_t*) Frag::create(sizeof(Q5Entry), false); }, nullptr);
+   scanTable(lineitem, {"l_orderkey", "l_suppkey", "l_extendedprice", "l_discount"}, {}, [&](rt::BatchView* b) {
+      auto* frag = (Frag*) aggTl->getLocal();
+      ColReader ok(b, 0), sk(b, 1), ext(b, 2), disc(b, 3);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         int32_t orderkey = ok.i32(idx);
+         for (auto* e = hivLookup(ordView, hashI32(orderkey)); e; e = e->next) {
+            auto* o = (KeyPayloadTuple*) e;
+            if (o->key != orderkey) continue;
+            int32_t suppkey = sk.i32(idx), custNation = o->payload;
+            uint64_t sh = hashI32Pair(suppkey, custNation);
+            for (auto* se = hivLookup(suppView, sh); se; se = se->next) {
+               auto* s = (SuppTuple*) se;
+               if (s->hash != sh || s->suppkey != suppkey || s->nationkey != custNation) continue;
+               i128 rev = wrapMul((i128) ext.dec64(idx), wrapSub((i128) 100, (i128) disc.dec64(idx)));
+               uint64_t gh = hashVarLen(s->name);
+               auto* cached = (Q5Entry*) frag->ht[(gh >> 6) & 1023];
+               Q5Entry* en;
+               if (cached && cached->hash == gh && cached->name.view() == s->name.view()) {
+                  en = cached;
+               } else {
+                  en = (Q5Entry*) frag->insert(gh);
+                  en->name = s->name;
+                  en->revenue = 0;
+               }
+               en->revenue = wrapAdd(en->revenue, rev);
+            }
+         }
+      }
+   });
+   constexpr size_t contentOff = offsetof(Q5Entry, name);
+   auto* merged = rt::PreAggregationHashtable::merge(
+      aggTl,
+      [](uint8_t* a, uint8_t* b) { return ((Q5Entry*) (a - contentOff))->name.view() == ((Q5Entry*) (b - contentOff))->name.view(); },
+      [](uint8_t* a, uint8_t* b) {
+         auto* x = (Q5Entry*) (a - contentOff);
+         x->revenue = wrapAdd(x->revenue, ((Q5Entry*) (b - contentOff))->revenue);
+      });
+   std::vector<Q5Row> rows;
+   rt::BufferIterator::iterate(
+      merged->createIterator(), false, [](rt::Buffer buf, void* ctx) {
+         auto& rows = *(std::vector<Q5Row>*) ctx;
+         auto** entries = (Q5Entry**) buf.ptr;
+         for (size_t i = 0; i < buf.numElements / sizeof(Q5Entry*); i++) rows.push_back(Q5Row{std::string(entries[i]->name.view()), entries[i]->revenue});
+      },
+      &rows);
+   std::sort(rows.begin(), rows.end(), [](const Q5Row& a, const Q5Row& b) { return a.revenue != b.revenue ? a.revenue > b.revenue : a.name < b.name; });
+   *seconds = now() - t0;
+   return rows;
+}
+
+} // namespace oracle

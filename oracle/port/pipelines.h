@@ -1,0 +1,54 @@
+// oracle/port/pipelines.h — TEST INFRASTRUCTURE ONLY (CPU oracle).  Query entry points of pipelines.cpp.
+#pragma once
+#include "table.h"
+#include "values.h"
+
+#include <string>
+#include <vector>
+
+namespace oracle {
+
+struct Q6Params {
+   std::string shipdateGe, shipdateLt, discountGe, discountLe;
+   int64_t quantityLt;
+};
+struct Q6Result {
+   i128 revenue; // decimal(24,4)
+   double seconds;
+};
+Q6Result runQ6(const HostTable& lineitem, const Q6Params& p);
+
+struct Q1Params {
+   std::string shipdateLe;
+};
+struct Q1Row {
+   int32_t returnflag, linestatus;
+   int64_t sumQty, sumBasePrice;  // decimal(12,2)
+   i128 sumDiscPrice;             // decimal(33,4)
+   i128 sumCharge;                // decimal(38,6)
+   i128 avgQty, avgPrice, avgDisc; // decimal(31,21)
+   int64_t count;
+};
+std::vector<Q1Row> runQ1(const HostTable& lineitem, const Q1Params& p, double* seconds);
+
+struct Q3Params {
+   std::string segment, date;
+};
+struct Q3Row {
+   int32_t orderkey;
+   i128 revenue; // decimal(33,4)
+   int32_t orderdate; // date32
+   int32_t shippriority;
+};
+std::vector<Q3Row> runQ3(const HostTable& customer, const HostTable& orders, const HostTable& lineitem, const Q3Params& p, double* seconds);
+
+struct Q5Params {
+   std::string regionName, dateGe, dateLt;
+};
+struct Q5Row {
+   std::string name;
+   i128 revenue; // decimal(33,4)
+};
+std::vector<Q5Row> runQ5(const HostTable& customer, const HostTable& orders, const HostTable& lineitem, const HostTable& supplier, const HostTable& nation, const HostTable& region, const Q5Params& p, double* seconds);
+
+} // namespace oracle
