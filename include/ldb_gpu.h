@@ -1,0 +1,237 @@
+/* ldb_gpu.h — C-ABI of the B200 backend for LingoDB's three data-parallel hot paths
+ * (Arrow scan + predicates/expressions, hash-join build+probe, hash group-by).
+ *
+ * Why a pipeline-level ABI: in the reference the per-tuple work (predicates, arithmetic, hashing, the
+ * bucket probe, the aggregate update) is generated inline by SubOpToControlFlow and JIT-compiled;
+ * src/runtime only owns state objects and calls back into JIT'd host function pointers per morsel
+ * (DataSourceIteration.h:25, PreAggregationHashtable.h:40, ThreadLocal.h:9-11).  Device code cannot
+ * call host function pointers, so this boundary receives DATA (descriptors) where the reference
+ * passes CODE.  Each entry point cites the reference interface it replaces.
+ *
+ * Conventions: plain C, no exceptions; every call returns LDB_OK (0) or an error code and fills
+ * `err` (may be NULL).  The C++ shim (lingo-db_b200/csrc/runtime_shim.h) rethrows as
+ * std::runtime_error to match the reference's convention (e.g. src/runtime/Hashtable.cpp:106).
+ * Ownership mirrors ExecutionContext::registerState (include/lingodb/runtime/ExecutionContext.h:111-113):
+ * states belong to the context and die with it; callers never free device memory themselves.
+ */
+#ifndef LDB_GPU_H
+#define LDB_GPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------ errors */
+enum LdbStatus {
+   LDB_OK = 0,
+   LDB_ERR_CUDA = 1,        /* CUDA runtime failure (reference: CudaUtils.cuh:5-20 prints and exits) */
+   LDB_ERR_UNSUPPORTED = 2, /* descriptor does not match a compiled pipeline */
+   LDB_ERR_INVALID = 3,     /* bad argument (unknown column, wrong type, NULL handle …) */
+   LDB_ERR_CAPACITY = 4,    /* a device table overflowed its declared capacity */
+   LDB_ERR_NO_DEVICE = 5    /* no CUDA device: there is NO CPU fallback on this path */
+};
+typedef struct LdbError {
+   int32_t code;
+   char message[252];
+} LdbError;
+
+/* ------------------------------------------------------------------------------------ context
+ * Replaces: runtime::ExecutionContext (state ownership) + the scheduler hand-off
+ * (scheduler::awaitChildTask, include/lingodb/scheduler/Scheduler.h:32-33): one context per device,
+ * work is issued on the context's CUDA streams instead of worker fibers. */
+typedef struct LdbContext LdbContext;
+typedef struct LdbDeviceInfo {
+   int32_t device, sm_count, cc_major, cc_minor;
+   int64_t total_mem, free_mem, l2_bytes;
+   char name[64];
+} LdbDeviceInfo;
+int ldb_gpu_context_create(int device, LdbContext** out, LdbError* err);
+void ldb_gpu_context_destroy(LdbContext* ctx);
+int ldb_gpu_device_info(LdbContext* ctx, LdbDeviceInfo* out, LdbError* err);
+int ldb_gpu_synchronize(LdbContext* ctx, LdbError* err);
+/* number of kernels this library has launched on the context since creation (bench "gpu_launches") */
+int64_t ldb_gpu_launch_count(LdbContext* ctx);
+/* CUDA-event timing on the context's compute stream (the stream every pipeline kernel runs on) */
+int ldb_gpu_timer_start(LdbContext* ctx, LdbError* err);
+int ldb_gpu_timer_stop(LdbContext* ctx, float* milliseconds, LdbError* err);
+/* device time (ms) and launch count accumulated by one named kernel family since the last reset;
+ * name = "scan_groupby" | "scan_reduce" | "join_build" | "join_probe" | … (roofline leg of bench.py) */
+int ldb_gpu_kernel_time(LdbContext* ctx, const char* family, float* ms, int64_t* launches, LdbError* err);
+int ldb_gpu_kernel_time_reset(LdbContext* ctx, int enable, LdbError* err);
+
+/* ------------------------------------------------------------------------------------ tables
+ * Replaces: ArrayView/BatchView (include/lingodb/runtime/ArrowView.h:8-29), LingoDBTable::TableChunk
+ * (src/runtime/storage/LingoDBTable.cpp:200-225) and DataSource::get (src/runtime/DataSourceIteration.cpp:57).
+ * LdbArrayView has the exact field layout of lingodb::runtime::ArrayView, so the reference's
+ * TableChunk::getArrayView() pointers can be passed through unchanged. */
+typedef struct LdbArrayView {
+   int64_t length, null_count, offset, n_buffers, n_children;
+   const void** buffers; /* [0] validity (may be NULL), [1] values or utf8 offsets, [2] utf8 bytes */
+   const struct LdbArrayView** children;
+} LdbArrayView;
+enum LdbPhysType { LDB_INT32 = 0, LDB_INT64 = 1, LDB_DATE32 = 2, LDB_DECIMAL128 = 3, LDB_FSB4 = 4, LDB_UTF8 = 5 };
+typedef struct LdbColumnSchema {
+   const char* name;
+   int32_t type; /* LdbPhysType: physical Arrow type as in LingoDBTable.cpp:122-195 */
+   int32_t precision, scale;
+} LdbColumnSchema;
+enum LdbMemLocation { LDB_MEM_HOST = 0, LDB_MEM_DEVICE = 1 };
+typedef struct LdbTable LdbTable;
+int ldb_gpu_table_create(LdbContext* ctx, const char* name, int32_t n_cols, const LdbColumnSchema* schema, LdbTable** out, LdbError* err);
+/* Append one record batch.  HOST buffers are staged to HBM with asynchronous copies on the context's
+ * copy stream (the scan of batch k overlaps the copy of batch k+1); DEVICE buffers are borrowed.
+ * utf8 columns additionally need `utf8_bytes[col]` = size of buffers[2] (0 for other columns). */
+int ldb_gpu_table_append_batch(LdbTable* t, int64_t n_rows, const LdbArrayView* columns, const int64_t* utf8_bytes, int32_t location, LdbError* err);
+int ldb_gpu_table_clear(LdbTable* t, LdbError* err); /* drop all batches (staging memory is pooled) */
+int64_t ldb_gpu_table_num_rows(const LdbTable* t);
+void ldb_gpu_table_destroy(LdbTable* t);
+
+/* ------------------------------------------------------------------------------------ states
+ * Device-resident runtime objects behind the reference's names:
+ *   LDB_STATE_SIMPLE      rt::SimpleState (src/runtime/SimpleState.cpp:8-30): keyless aggregates
+ *   LDB_STATE_GROUPBY     rt::PreAggregationHashtable(+Fragment) / rt::Hashtable
+ *                         (PreAggregationHashtable.cpp:46-170, Hashtable.cpp:10-150): small-domain group-by
+ *   LDB_STATE_JOIN_TABLE  rt::GrowingBuffer + rt::HashIndexedView (GrowingBuffer.cpp:39-113,
+ *                         LazyJoinHashtable.cpp:12-34): key → payload multimap; with aggregate
+ *                         lanes it is the group-join map of SubOpToControlFlow.cpp:2730-2839.
+ * The memory image differs from the CPU objects (open addressing, 32-bit payloads, no tagged
+ * pointers): the contract is the same MULTISET of results, not the same bytes. */
+enum LdbStateKind { LDB_STATE_SIMPLE = 1, LDB_STATE_GROUPBY = 2, LDB_STATE_JOIN_TABLE = 3 };
+typedef struct LdbState LdbState;
+typedef struct LdbI128 {
+   uint64_t lo;
+   int64_t hi;
+} LdbI128;
+
+/* Frees one state early (a query's states die together when its ExecutionContext does,
+ * ExecutionContext.cpp:27-40; long-lived contexts release per query with this). */
+void ldb_gpu_state_destroy(LdbState* s);
+
+#define LDB_MAX_AGGS 8
+#define LDB_MAX_KEYS 2
+#define LDB_MAX_SIDE 2
+
+int ldb_gpu_simple_state_create(LdbContext* ctx, int32_t n_aggs, LdbState** out, LdbError* err);
+int ldb_gpu_simple_state_read(LdbState* s, LdbI128* aggs /* n_aggs */, LdbError* err);
+
+int ldb_gpu_groupby_create(LdbContext* ctx, int32_t n_keys, int32_t n_aggs, int32_t capacity, LdbState** out, LdbError* err);
+typedef struct LdbGroupRow {
+   int32_t keys[LDB_MAX_KEYS];
+   LdbI128 aggs[LDB_MAX_AGGS];
+} LdbGroupRow;
+/* rt::PreAggregationHashtable::createIterator + BufferIterator::iterate, for a tiny result */
+int ldb_gpu_groupby_read(LdbState* s, LdbGroupRow* rows, int32_t max_rows, int32_t* n_rows, LdbError* err);
+/* fold another GPU's partial groups into this state (K7 merge; rt::PreAggregationHashtable::merge) */
+int ldb_gpu_groupby_merge_rows(LdbState* s, const LdbGroupRow* rows, int32_t n_rows, LdbError* err);
+
+/* expected_rows sizes the directory like HashIndexedView::build (nextPow2 of a multiple of n);
+ * n_side = int32 payload lanes stored beside the slot; n_aggs = int128 aggregate lanes (group-join) */
+int ldb_gpu_join_table_create(LdbContext* ctx, int64_t expected_rows, int32_t unique_keys, int32_t n_side, int32_t n_aggs, LdbState** out, LdbError* err);
+int ldb_gpu_join_table_count(LdbState* s, int64_t* n_entries, LdbError* err);
+typedef struct LdbTopKRow {
+   int32_t key, side[LDB_MAX_SIDE];
+   int32_t pad;
+   LdbI128 agg;
+} LdbTopKRow;
+/* scan of the group-join map + Heap (include/lingodb/runtime/Heap.h): marked groups ordered by
+ * (agg0 desc, side0 asc, key asc), first k */
+int ldb_gpu_join_table_topk(LdbState* s, int32_t k, LdbTopKRow* rows, int32_t* n_rows, LdbError* err);
+
+/* ------------------------------------------------------------------------------------ pipelines
+ * Replaces: one execution step of the JIT'd main() — rt::DataSourceIteration::iterate(scan_func)
+ * (DataSourceIteration.cpp:90-96) plus the inlined per-tuple code of SubOpToControlFlow
+ * (scan :1123-1203, probe :2558-2586 + :2254-2313, group-by :3065-3157, reduce :3719-3769).
+ * A pipeline = table scan → pushed-down filters → optional hash-table probes → one sink. */
+enum LdbFilterOp { LDB_EQ = 0, LDB_NEQ = 1, LDB_LT = 2, LDB_LTE = 3, LDB_GT = 4, LDB_GTE = 5, LDB_NOTNULL = 6, LDB_IN = 7 };
+/* FilterDescription (include/lingodb/runtime/storage/TableStorage.h:14-31): column-vs-constant;
+ * the constant is a string (dates "YYYY-MM-DD", decimals "0.05", char/varchar text) or an integer */
+typedef struct LdbFilterDesc {
+   const char* column;
+   int32_t op;          /* LdbFilterOp */
+   int32_t value_is_int;
+   const char* str_value;
+   int64_t int_value;
+} LdbFilterDesc;
+
+/* value expressions over decimal(12,2) columns, typed as DBOps.cpp:98-107,221-262 types them */
+enum LdbExprKind {
+   LDB_EXPR_COL = 0,               /* a                       decimal(12,2)  i64  */
+   LDB_EXPR_MUL = 1,               /* a * b                   decimal(24,4)  i128 */
+   LDB_EXPR_MUL_1MINUS = 2,        /* a * (1 - b)             decimal(33,4)  i128 */
+   LDB_EXPR_MUL_1MINUS_1PLUS = 3,  /* a * (1 - b) * (1 + c)   decimal(38,6)  i128 */
+   LDB_EXPR_ONE = 4                /* count(*) */
+};
+typedef struct LdbAggDesc {
+   int32_t expr;            /* LdbExprKind; every aggregate is SUM (count = SUM of ONE); i64 sums wrap at 64 bits */
+   const char* columns[3];  /* a, b, c */
+} LdbAggDesc;
+
+enum LdbPipelineKind {
+   /* K1  scan → filters → keyless SUMs → SimpleState                       (Q6) */
+   LDB_PIPE_SCAN_REDUCE = 1,
+   /* K2  scan → filters → group by ≤2 int32/char keys, SUMs → GroupBy      (Q1) */
+   LDB_PIPE_SCAN_GROUPBY = 2,
+   /* K3  scan → filters → [probe] → insert {key, payload, side…} → JoinTable
+    *     (subop.materialize + create_hash_indexed_view; group-join insert side) */
+   LDB_PIPE_SCAN_BUILD = 3,
+   /* K5  scan → filters → probe group-join map → atomic SUM into the entry, set marker (Q3) */
+   LDB_PIPE_SCAN_PROBE_AGG = 4,
+   /* K4  scan → filters → probe A → probe B (payload equality) → group by payload, SUM → GroupBy (Q5) */
+   LDB_PIPE_SCAN_PROBE2_GROUPBY = 5
+};
+typedef struct LdbPipelineDesc {
+   int32_t kind; /* LdbPipelineKind */
+   LdbTable* source;
+   int32_t n_filters;
+   const LdbFilterDesc* filters;
+   /* group-by keys (K2) */
+   int32_t n_keys;
+   const char* key_columns[LDB_MAX_KEYS];
+   /* aggregates (K1, K2: n_aggs; K4, K5: aggs[0]) */
+   int32_t n_aggs;
+   LdbAggDesc aggs[LDB_MAX_AGGS];
+   /* probes: probe_key_columns[i] is looked up in probe_states[i] (K3: 0 or 1, K5: 1, K4: 2) */
+   int32_t n_probes;
+   LdbState* probe_states[2];
+   const char* probe_key_columns[2];
+   /* K3 build: inserted key, inline payload (a column, or the probe's payload when NULL and a
+    * probe is present, or 0), side payload columns */
+   const char* build_key_column;
+   const char* build_payload_column;
+   int32_t n_side;
+   const char* side_columns[LDB_MAX_SIDE];
+   LdbState* sink; /* SimpleState | GroupBy | JoinTable (K5: the probed map itself) */
+} LdbPipelineDesc;
+int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* desc, LdbError* err);
+
+/* ------------------------------------------------------------------------------------ repartition (K6)
+ * No reference counterpart (the reference is single-process; SURVEY §2 "Parallelism strategies").
+ * Radix partition of a fixed-width tuple stream by the top bits of the reference hash h64(key)
+ * into per-destination contiguous blocks, ready for an NCCL all-to-all. */
+int ldb_gpu_partition_tuples(LdbContext* ctx, const int32_t* keys, const void* const* payload_cols, const int32_t* payload_widths, int32_t n_payload_cols, int64_t n_rows, int32_t n_parts,
+                             int32_t* out_keys, void* const* out_payload_cols, int64_t* out_part_offsets /* n_parts+1, host */, LdbError* err);
+/* insert already-materialised tuples (e.g. received from peers) into a JoinTable */
+int ldb_gpu_join_table_insert(LdbContext* ctx, LdbState* table, const int32_t* keys, const int32_t* payloads, const int32_t* const* side_cols, int64_t n_rows, LdbError* err);
+
+/* ------------------------------------------------------------------------------------ value-level hooks
+ * Device twins of util.hash_64 / hash_combine (LowerToLLVM.cpp:493-514), exported for the KAT tests:
+ * hashes `n` int64 values (optionally combined with a second column) on the GPU. */
+int ldb_gpu_hash_i64(LdbContext* ctx, const int64_t* host_values, const int64_t* host_values2, int64_t n, uint64_t* host_out, LdbError* err);
+
+/* ------------------------------------------------------------------------------------ device datagen
+ * Device twin of ldb_datagen.h (same tpch_gen.h); fills DEVICE buffers. */
+struct LdbGenScale;
+struct LdbGenLineitemCols;
+struct LdbGenOrdersCols;
+struct LdbGenCustomerCols;
+struct LdbGenSupplierCols;
+int ldb_gpu_datagen_lineitem(LdbContext* ctx, const struct LdbGenScale* g, int64_t row_begin, int64_t n_rows, const struct LdbGenLineitemCols* dev_cols, LdbError* err);
+int ldb_gpu_datagen_orders(LdbContext* ctx, const struct LdbGenScale* g, int64_t row_begin, int64_t n_rows, const struct LdbGenOrdersCols* dev_cols, LdbError* err);
+int ldb_gpu_datagen_customer_fixed(LdbContext* ctx, const struct LdbGenScale* g, int64_t row_begin, int64_t n_rows, const struct LdbGenCustomerCols* dev_cols, int32_t* dev_seg_lengths, LdbError* err);
+int ldb_gpu_datagen_customer_bytes(LdbContext* ctx, const struct LdbGenScale* g, int64_t row_begin, int64_t n_rows, const int32_t* dev_offsets, uint8_t* dev_data, LdbError* err);
+int ldb_gpu_datagen_supplier(LdbContext* ctx, const struct LdbGenScale* g, int64_t row_begin, int64_t n_rows, const struct LdbGenSupplierCols* dev_cols, LdbError* err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

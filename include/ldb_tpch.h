@@ -1,0 +1,58 @@
+/* ldb_tpch.h — query drivers: the sequence of pipeline calls the reference's JIT'd `main()` performs
+ * for TPC-H Q1/Q3/Q5/Q6 (DefaultCPULLVMBackend::execute → mainFunc(), src/execution/LLVMBackends.cpp:795-867),
+ * issued against the GPU C-ABI (ldb_gpu.h).  This is what a `GPUPatternList` lowering
+ * (SubOpToControlFlow.cpp:4254-4394) would emit; it lives in C++ like src/execution.
+ * Results are exact integers: decimal raw values with the scale the reference's typing gives them.
+ */
+#ifndef LDB_TPCH_H
+#define LDB_TPCH_H
+#include "ldb_gpu.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct LdbTpchTables {
+   LdbTable* lineitem;
+   LdbTable* orders;
+   LdbTable* customer;
+   LdbTable* supplier;
+   LdbTable* nation;
+   LdbTable* region;
+} LdbTpchTables;
+
+/* Q6: revenue = sum(l_extendedprice * l_discount), decimal(24,4) */
+int ldb_tpch_q6(LdbContext* ctx, const LdbTpchTables* t, const char* shipdate_ge, const char* shipdate_lt, const char* discount_ge, const char* discount_le, int64_t quantity_lt,
+                LdbI128* revenue, LdbError* err);
+/* the per-GPU half of Q6/Q1: run the scan pipeline into a fresh state and return it (rows of other
+ * GPUs are folded in with ldb_gpu_groupby_merge_rows before the finish call) */
+int ldb_tpch_q6_partial(LdbContext* ctx, const LdbTpchTables* t, const char* shipdate_ge, const char* shipdate_lt, const char* discount_ge, const char* discount_le, int64_t quantity_lt,
+                        LdbState** state, LdbError* err);
+
+typedef struct LdbQ1Row {
+   int32_t l_returnflag, l_linestatus;      /* fixed_size_binary(4) cells */
+   int64_t sum_qty, sum_base_price;         /* decimal(12,2) */
+   LdbI128 sum_disc_price;                  /* decimal(33,4) */
+   LdbI128 sum_charge;                      /* decimal(38,6) */
+   LdbI128 avg_qty, avg_price, avg_disc;    /* decimal(31,21): (sum * 10^19) sdiv count */
+   int64_t count_order;
+} LdbQ1Row;
+int ldb_tpch_q1(LdbContext* ctx, const LdbTpchTables* t, const char* shipdate_le, LdbQ1Row* rows, int32_t max_rows, int32_t* n_rows, LdbError* err);
+int ldb_tpch_q1_partial(LdbContext* ctx, const LdbTpchTables* t, const char* shipdate_le, LdbState** state, LdbError* err);
+int ldb_tpch_q1_finish(LdbState* state, LdbQ1Row* rows, int32_t max_rows, int32_t* n_rows, LdbError* err);
+
+typedef struct LdbQ3Row {
+   int32_t l_orderkey, o_orderdate, o_shippriority, pad;
+   LdbI128 revenue; /* decimal(33,4) */
+} LdbQ3Row;
+int ldb_tpch_q3(LdbContext* ctx, const LdbTpchTables* t, const char* segment, const char* date, LdbQ3Row* rows /* 10 */, int32_t* n_rows, LdbError* err);
+
+typedef struct LdbQ5Row {
+   int32_t n_nationkey, pad; /* n_name is resolved from the nation table at materialisation (host) */
+   LdbI128 revenue;          /* decimal(33,4) */
+} LdbQ5Row;
+int ldb_tpch_q5(LdbContext* ctx, const LdbTpchTables* t, const char* region_name, const char* date_ge, const char* date_lt, LdbQ5Row* rows /* 25 */, int32_t* n_rows, LdbError* err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,167 @@
+"""ctypes binding of the C-ABI (include/ldb_gpu.h, include/ldb_tpch.h) — libldb_gpu.so.
+
+Loading the library works without a GPU (the -m "not gpu" tests check the exported symbols); every
+compute entry point then fails with LDB_ERR_NO_DEVICE: there is no CPU fallback on this path.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+from .datagen import CustomerCols, GenScale, LineitemCols, OrdersCols, SupplierCols
+
+LDB_OK, LDB_ERR_CUDA, LDB_ERR_UNSUPPORTED, LDB_ERR_INVALID, LDB_ERR_CAPACITY, LDB_ERR_NO_DEVICE = range(6)
+PHYS = {"int32": 0, "int64": 1, "date32": 2, "decimal128": 3, "fsb4": 4, "utf8": 5}
+MEM_HOST, MEM_DEVICE = 0, 1
+OPS = {"=": 0, "!=": 1, "<": 2, "<=": 3, ">": 4, ">=": 5}
+EXPR = {"col": 0, "mul": 1, "mul_1minus": 2, "mul_1minus_1plus": 3, "one": 4}
+PIPE = {"scan_reduce": 1, "scan_groupby": 2, "scan_build": 3, "scan_probe_agg": 4, "scan_probe2_groupby": 5}
+MAX_AGGS, MAX_KEYS, MAX_SIDE = 8, 2, 2
+
+
+class LdbRuntimeError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"[ldb_gpu error {code}] {message}")
+        self.code = code
+
+
+class Error(C.Structure):
+    _fields_ = [("code", C.c_int32), ("message", C.c_char * 252)]
+
+
+class DeviceInfo(C.Structure):
+    _fields_ = [("device", C.c_int32), ("sm_count", C.c_int32), ("cc_major", C.c_int32), ("cc_minor", C.c_int32),
+                ("total_mem", C.c_int64), ("free_mem", C.c_int64), ("l2_bytes", C.c_int64), ("name", C.c_char * 64)]
+
+
+class ArrayView(C.Structure):
+    pass
+
+
+ArrayView._fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64), ("n_buffers", C.c_int64),
+                      ("n_children", C.c_int64), ("buffers", C.POINTER(C.c_void_p)), ("children", C.c_void_p)]
+
+
+class ColumnSchema(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("type", C.c_int32), ("precision", C.c_int32), ("scale", C.c_int32)]
+
+
+class I128(C.Structure):
+    _fields_ = [("lo", C.c_uint64), ("hi", C.c_int64)]
+
+    def value(self) -> int:
+        return (int(self.hi) << 64) | int(self.lo)
+
+
+class GroupRow(C.Structure):
+    _fields_ = [("keys", C.c_int32 * MAX_KEYS), ("aggs", I128 * MAX_AGGS)]
+
+
+class TopKRow(C.Structure):
+    _fields_ = [("key", C.c_int32), ("side", C.c_int32 * MAX_SIDE), ("pad", C.c_int32), ("agg", I128)]
+
+
+class FilterDesc(C.Structure):
+    _fields_ = [("column", C.c_char_p), ("op", C.c_int32), ("value_is_int", C.c_int32), ("str_value", C.c_char_p), ("int_value", C.c_int64)]
+
+
+class AggDesc(C.Structure):
+    _fields_ = [("expr", C.c_int32), ("columns", C.c_char_p * 3)]
+
+
+class PipelineDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("source", C.c_void_p), ("n_filters", C.c_int32), ("filters", C.POINTER(FilterDesc)),
+                ("n_keys", C.c_int32), ("key_columns", C.c_char_p * MAX_KEYS), ("n_aggs", C.c_int32), ("aggs", AggDesc * MAX_AGGS),
+                ("n_probes", C.c_int32), ("probe_states", C.c_void_p * 2), ("probe_key_columns", C.c_char_p * 2),
+                ("build_key_column", C.c_char_p), ("build_payload_column", C.c_char_p), ("n_side", C.c_int32),
+                ("side_columns", C.c_char_p * MAX_SIDE), ("sink", C.c_void_p)]
+
+
+class TpchTables(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("lineitem", "orders", "customer", "supplier", "nation", "region")]
+
+
+class Q1Row(C.Structure):
+    _fields_ = [("l_returnflag", C.c_int32), ("l_linestatus", C.c_int32), ("sum_qty", C.c_int64), ("sum_base_price", C.c_int64),
+                ("sum_disc_price", I128), ("sum_charge", I128), ("avg_qty", I128), ("avg_price", I128), ("avg_disc", I128),
+                ("count_order", C.c_int64)]
+
+
+class Q3Row(C.Structure):
+    _fields_ = [("l_orderkey", C.c_int32), ("o_orderdate", C.c_int32), ("o_shippriority", C.c_int32), ("pad", C.c_int32), ("revenue", I128)]
+
+
+class Q5Row(C.Structure):
+    _fields_ = [("n_nationkey", C.c_int32), ("pad", C.c_int32), ("revenue", I128)]
+
+
+# every symbol include/ldb_gpu.h and include/ldb_tpch.h declare: (restype, argtypes)
+_P = C.c_void_p
+_E = C.POINTER(Error)
+SIGNATURES = {
+    "ldb_gpu_context_create": (C.c_int, [C.c_int, C.POINTER(_P), _E]),
+    "ldb_gpu_context_destroy": (None, [_P]),
+    "ldb_gpu_device_info": (C.c_int, [_P, C.POINTER(DeviceInfo), _E]),
+    "ldb_gpu_synchronize": (C.c_int, [_P, _E]),
+    "ldb_gpu_launch_count": (C.c_int64, [_P]),
+    "ldb_gpu_timer_start": (C.c_int, [_P, _E]),
+    "ldb_gpu_timer_stop": (C.c_int, [_P, C.POINTER(C.c_float), _E]),
+    "ldb_gpu_kernel_time": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_int64), _E]),
+    "ldb_gpu_kernel_time_reset": (C.c_int, [_P, C.c_int, _E]),
+    "ldb_gpu_table_create": (C.c_int, [_P, C.c_char_p, C.c_int32, C.POINTER(ColumnSchema), C.POINTER(_P), _E]),
+    "ldb_gpu_table_append_batch": (C.c_int, [_P, C.c_int64, C.POINTER(ArrayView), C.POINTER(C.c_int64), C.c_int32, _E]),
+    "ldb_gpu_table_clear": (C.c_int, [_P, _E]),
+    "ldb_gpu_table_num_rows": (C.c_int64, [_P]),
+    "ldb_gpu_table_destroy": (None, [_P]),
+    "ldb_gpu_state_destroy": (None, [_P]),
+    "ldb_gpu_simple_state_create": (C.c_int, [_P, C.c_int32, C.POINTER(_P), _E]),
+    "ldb_gpu_simple_state_read": (C.c_int, [_P, C.POINTER(I128), _E]),
+    "ldb_gpu_groupby_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P), _E]),
+    "ldb_gpu_groupby_read": (C.c_int, [_P, C.POINTER(GroupRow), C.c_int32, C.POINTER(C.c_int32), _E]),
+    "ldb_gpu_groupby_merge_rows": (C.c_int, [_P, C.POINTER(GroupRow), C.c_int32, _E]),
+    "ldb_gpu_join_table_create": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P), _E]),
+    "ldb_gpu_join_table_count": (C.c_int, [_P, C.POINTER(C.c_int64), _E]),
+    "ldb_gpu_join_table_topk": (C.c_int, [_P, C.c_int32, C.POINTER(TopKRow), C.POINTER(C.c_int32), _E]),
+    "ldb_gpu_run_pipeline": (C.c_int, [_P, C.POINTER(PipelineDesc), _E]),
+    "ldb_gpu_partition_tuples": (C.c_int, [_P, _P, C.POINTER(_P), C.POINTER(C.c_int32), C.c_int32, C.c_int64, C.c_int32, _P, C.POINTER(_P), C.POINTER(C.c_int64), _E]),
+    "ldb_gpu_join_table_insert": (C.c_int, [_P, _P, _P, _P, C.POINTER(_P), C.c_int64, _E]),
+    "ldb_gpu_hash_i64": (C.c_int, [_P, _P, _P, C.c_int64, _P, _E]),
+    "ldb_gpu_datagen_lineitem": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, C.POINTER(LineitemCols), _E]),
+    "ldb_gpu_datagen_orders": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, C.POINTER(OrdersCols), _E]),
+    "ldb_gpu_datagen_customer_fixed": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, C.POINTER(CustomerCols), _P, _E]),
+    "ldb_gpu_datagen_customer_bytes": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, _P, _P, _E]),
+    "ldb_gpu_datagen_supplier": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, C.POINTER(SupplierCols), _E]),
+    "ldb_tpch_q6": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(I128), _E]),
+    "ldb_tpch_q6_partial": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(_P), _E]),
+    "ldb_tpch_q1": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.POINTER(Q1Row), C.c_int32, C.POINTER(C.c_int32), _E]),
+    "ldb_tpch_q1_partial": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.POINTER(_P), _E]),
+    "ldb_tpch_q1_finish": (C.c_int, [_P, C.POINTER(Q1Row), C.c_int32, C.POINTER(C.c_int32), _E]),
+    "ldb_tpch_q3": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.c_char_p, C.POINTER(Q3Row), C.POINTER(C.c_int32), _E]),
+    "ldb_tpch_q5": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(Q5Row), C.POINTER(C.c_int32), _E]),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.GPU_LIB
+
+
+def lib():
+    """Load libldb_gpu.so (building it in-tree if the sources changed)."""
+    global _lib
+    if _lib is None:
+        path = _build.build_gpu()
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} is missing: the GPU operator runtime has no fallback; run lingodb_b200.build.build_gpu()")
+        L = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, err: Error):
+    if rc != LDB_OK:
+        raise LdbRuntimeError(rc, err.message.decode(errors="replace"))

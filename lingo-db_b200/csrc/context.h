@@ -1,0 +1,113 @@
+// context.h — internal definitions of the opaque C-ABI handles (include/ldb_gpu.h).
+#pragma once
+#include "../../include/ldb_gpu.h"
+#include "kernels.h"
+
+#include <cuda_runtime.h>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace ldb {
+
+struct CudaError : std::runtime_error {
+   int code;
+   CudaError(int code, const std::string& m) : std::runtime_error(m), code(code) {}
+};
+inline void cudaCheck(cudaError_t e, const char* what, const char* file, int line) {
+   if (e != cudaSuccess) {
+      cudaGetLastError();
+      throw CudaError(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? LDB_ERR_NO_DEVICE : LDB_ERR_CUDA,
+                      std::string(what) + ": " + cudaGetErrorString(e) + " (" + file + ":" + std::to_string(line) + ")");
+   }
+}
+#define LDB_CUDA(x) ::ldb::cudaCheck((x), #x, __FILE__, __LINE__)
+struct ApiError : std::runtime_error {
+   int code;
+   ApiError(int code, const std::string& m) : std::runtime_error(m), code(code) {}
+};
+
+struct KernelFamilyTimer {
+   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+   double totalMs = 0;
+   int64_t launches = 0;
+};
+
+} // namespace ldb
+
+struct LdbState;
+struct LdbTable;
+
+struct LdbContext {
+   int device = 0;
+   int smCount = 0;
+   cudaDeviceProp prop{};
+   cudaStream_t compute = nullptr, copy = nullptr;
+   cudaEvent_t timerStart = nullptr, timerStop = nullptr, computeDone = nullptr;
+   int64_t launches = 0;
+   bool timing = false;
+   std::map<std::string, ldb::KernelFamilyTimer> timers;
+   std::vector<cudaEvent_t> eventPool;
+   std::vector<LdbState*> states;
+   std::vector<LdbTable*> tables;
+   // staging pool for HOST batches: size → free device buffers
+   std::multimap<size_t, void*> stagingFree;
+   std::map<void*, size_t> stagingSize;
+
+   void* stagingAlloc(size_t bytes);
+   void stagingRelease(void* p);
+   cudaEvent_t getEvent();
+   // wrap one kernel launch: counts it and, when timing is on, brackets it with events on `compute`
+   template <class Fn>
+   void launch(const char* family, const Fn& fn) {
+      launches++;
+      if (timing) {
+         auto& t = timers[family];
+         cudaEvent_t a = getEvent(), b = getEvent();
+         LDB_CUDA(cudaEventRecord(a, compute));
+         fn();
+         LDB_CUDA(cudaEventRecord(b, compute));
+         t.pending.push_back({a, b});
+         t.launches++;
+      } else {
+         fn();
+      }
+      LDB_CUDA(cudaGetLastError());
+   }
+};
+
+struct LdbBatch {
+   int64_t nRows = 0;
+   std::vector<const void*> data;  // per column: values / utf8 offsets (device)
+   std::vector<const void*> bytes; // per column: utf8 bytes (device) or null
+   std::vector<void*> owned;       // staging buffers to give back on clear
+   cudaEvent_t ready = nullptr;    // H2D of this batch finished (null for borrowed device batches)
+};
+struct LdbColumn {
+   std::string name;
+   int32_t type, precision, scale;
+};
+struct LdbTable {
+   LdbContext* ctx;
+   std::string name;
+   std::vector<LdbColumn> columns;
+   std::vector<LdbBatch> batches;
+   int64_t numRows = 0;
+   int colIndex(const char* n) const {
+      if (!n) return -1;
+      for (size_t i = 0; i < columns.size(); i++)
+         if (columns[i].name == n) return (int) i;
+      return -1;
+   }
+};
+
+struct LdbState {
+   LdbContext* ctx;
+   int32_t kind;
+   ldb::GroupTableDev group{}; // SIMPLE / GROUPBY
+   ldb::JoinTableDev join{};   // JOIN_TABLE
+   int32_t nSide = 0, nAggs = 0;
+   std::vector<void*> allocations;
+};

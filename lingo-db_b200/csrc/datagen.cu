@@ -1,0 +1,130 @@
+// datagen.cu — device twin of the deterministic TPC-H-shaped generator (tpch_gen.h): fills Arrow
+// physical column buffers directly in HBM so SF100 tables never cross PCIe.  Bit-identical to
+// datagen_host.cpp (tests/test_gpu_datagen.py).  Not on the query hot path.
+#include "context.h"
+#include "tpch_gen.h"
+#include "../../include/ldb_datagen.h"
+
+using namespace ldbgen;
+
+namespace {
+Scale toScale(const LdbGenScale* g) {
+   Scale s;
+   s.seed = g->seed;
+   s.nOrders = g->n_orders;
+   s.nCustomer = g->n_customer;
+   s.nSupplier = g->n_supplier;
+   s.nPart = g->n_part;
+   return s;
+}
+__device__ __forceinline__ void storeDec(uint8_t* col, int64_t i, int64_t v) {
+   longlong2 x;
+   x.x = v;
+   x.y = v >> 63;
+   reinterpret_cast<longlong2*>(col)[i] = x;
+}
+__global__ void lineitemKernel(Scale s, int64_t rowBegin, int64_t n, LdbGenLineitemCols c) {
+   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+      LineItem l = lineItem(s, rowBegin + i);
+      if (c.l_orderkey) c.l_orderkey[i] = l.orderkey;
+      if (c.l_partkey) c.l_partkey[i] = l.partkey;
+      if (c.l_suppkey) c.l_suppkey[i] = l.suppkey;
+      if (c.l_quantity) storeDec(c.l_quantity, i, l.quantity);
+      if (c.l_extendedprice) storeDec(c.l_extendedprice, i, l.extendedprice);
+      if (c.l_discount) storeDec(c.l_discount, i, l.discount);
+      if (c.l_tax) storeDec(c.l_tax, i, l.tax);
+      if (c.l_returnflag) c.l_returnflag[i] = l.returnflag;
+      if (c.l_linestatus) c.l_linestatus[i] = l.linestatus;
+      if (c.l_shipdate) c.l_shipdate[i] = l.shipdate;
+      if (c.l_commitdate) c.l_commitdate[i] = l.commitdate;
+      if (c.l_receiptdate) c.l_receiptdate[i] = l.receiptdate;
+   }
+}
+__global__ void ordersKernel(Scale s, int64_t rowBegin, int64_t n, LdbGenOrdersCols c) {
+   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+      int64_t o = rowBegin + i;
+      if (c.o_orderkey) c.o_orderkey[i] = orderKey(o);
+      if (c.o_custkey) c.o_custkey[i] = orderCustKey(s, o);
+      if (c.o_orderdate) c.o_orderdate[i] = orderDate(s, o);
+      if (c.o_shippriority) c.o_shippriority[i] = orderShipPriority(s, o);
+   }
+}
+__global__ void customerFixedKernel(Scale s, int64_t rowBegin, int64_t n, LdbGenCustomerCols c, int32_t* segLengths) {
+   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+      int64_t r = rowBegin + i;
+      if (c.c_custkey) c.c_custkey[i] = (int32_t) (r + 1);
+      if (c.c_nationkey) c.c_nationkey[i] = customerNationKey(s, r);
+      if (segLengths) segLengths[i] = segmentLen(customerSegment(s, r));
+   }
+}
+__global__ void customerBytesKernel(Scale s, int64_t rowBegin, int64_t n, const int32_t* offsets, uint8_t* data) {
+   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+      int32_t seg = customerSegment(s, rowBegin + i);
+      int32_t len = segmentLen(seg), off = offsets[i];
+      for (int32_t k = 0; k < len; k++) data[off + k] = (uint8_t) segmentChar(seg, k);
+   }
+}
+__global__ void supplierKernel(Scale s, int64_t rowBegin, int64_t n, LdbGenSupplierCols c) {
+   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+      int64_t r = rowBegin + i;
+      if (c.s_suppkey) c.s_suppkey[i] = (int32_t) (r + 1);
+      if (c.s_nationkey) c.s_nationkey[i] = supplierNationKey(s, r);
+   }
+}
+int gridFor(LdbContext* ctx, int64_t n) { return (int) std::min<int64_t>(std::max<int64_t>((n + 255) / 256, 1), (int64_t) ctx->smCount * 16); }
+template <class Fn>
+int guardedGen(LdbError* err, const Fn& fn) {
+   try {
+      fn();
+      if (err) {
+         err->code = LDB_OK;
+         err->message[0] = 0;
+      }
+      return LDB_OK;
+   } catch (const ldb::CudaError& e) {
+      if (err) {
+         err->code = e.code;
+         snprintf(err->message, sizeof(err->message), "%s", e.what());
+      }
+      return e.code;
+   }
+}
+} // namespace
+
+extern "C" {
+int ldb_gpu_datagen_lineitem(LdbContext* ctx, const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenLineitemCols* c, LdbError* err) {
+   return guardedGen(err, [&] {
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      lineitemKernel<<<gridFor(ctx, n_rows), 256, 0, ctx->compute>>>(toScale(g), row_begin, n_rows, *c);
+      LDB_CUDA(cudaGetLastError());
+   });
+}
+int ldb_gpu_datagen_orders(LdbContext* ctx, const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenOrdersCols* c, LdbError* err) {
+   return guardedGen(err, [&] {
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      ordersKernel<<<gridFor(ctx, n_rows), 256, 0, ctx->compute>>>(toScale(g), row_begin, n_rows, *c);
+      LDB_CUDA(cudaGetLastError());
+   });
+}
+int ldb_gpu_datagen_customer_fixed(LdbContext* ctx, const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenCustomerCols* c, int32_t* dev_seg_lengths, LdbError* err) {
+   return guardedGen(err, [&] {
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      customerFixedKernel<<<gridFor(ctx, n_rows), 256, 0, ctx->compute>>>(toScale(g), row_begin, n_rows, *c, dev_seg_lengths);
+      LDB_CUDA(cudaGetLastError());
+   });
+}
+int ldb_gpu_datagen_customer_bytes(LdbContext* ctx, const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const int32_t* dev_offsets, uint8_t* dev_data, LdbError* err) {
+   return guardedGen(err, [&] {
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      customerBytesKernel<<<gridFor(ctx, n_rows), 256, 0, ctx->compute>>>(toScale(g), row_begin, n_rows, dev_offsets, dev_data);
+      LDB_CUDA(cudaGetLastError());
+   });
+}
+int ldb_gpu_datagen_supplier(LdbContext* ctx, const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenSupplierCols* c, LdbError* err) {
+   return guardedGen(err, [&] {
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      supplierKernel<<<gridFor(ctx, n_rows), 256, 0, ctx->compute>>>(toScale(g), row_begin, n_rows, *c);
+      LDB_CUDA(cudaGetLastError());
+   });
+}
+}

@@ -1,0 +1,104 @@
+// device_utils.cuh — value-level device primitives shared by every pipeline kernel (sm_100a).
+//
+// These are the device twins of what the reference's JIT emits inline per tuple:
+//   hash64 / hashCombine          UtilToLLVM/LowerToLLVM.cpp:493-514 (KAT: test/lit/DB/hash.mlir:27-34)
+//   128-bit wrapping arithmetic   LLVM `mul/add i128` as produced by DBToStd/LowerToStd.cpp:612-700
+//   decimal128 loads (trunc i64)  ArrowToStd.cpp:67-85 + LowerToStd.cpp:111-209
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ldb {
+
+// ---------------------------------------------------------------- 128-bit two's complement, wrapping
+struct i128 {
+   uint64_t lo;
+   int64_t hi;
+};
+__device__ __forceinline__ i128 make128(int64_t v) { return i128{(uint64_t) v, v >> 63}; }
+__device__ __forceinline__ i128 add128(i128 a, i128 b) {
+   i128 r;
+   r.lo = a.lo + b.lo;
+   r.hi = (int64_t) ((uint64_t) a.hi + (uint64_t) b.hi + (r.lo < a.lo ? 1ull : 0ull));
+   return r;
+}
+// signed 64 × signed 64 → 128 (exact)
+__device__ __forceinline__ i128 mul64x64(int64_t a, int64_t b) {
+   i128 r;
+   r.lo = (uint64_t) a * (uint64_t) b;
+   r.hi = __mul64hi(a, b);
+   return r;
+}
+// i128 × signed 64 → low 128 bits (wrapping, like LLVM mul i128 with a sign-extended operand)
+__device__ __forceinline__ i128 mul128x64(i128 a, int64_t b) {
+   i128 r;
+   uint64_t ub = (uint64_t) b;
+   r.lo = a.lo * ub;
+   uint64_t hi = __umul64hi(a.lo, ub) + (uint64_t) a.hi * ub;
+   if (b < 0) hi -= a.lo; // b's sign extension contributes a.lo * (2^64 - 1 … ) = -a.lo at bit 64
+   r.hi = (int64_t) hi;
+   return r;
+}
+
+// ---------------------------------------------------------------- reference hash
+__device__ __forceinline__ uint64_t bswap64(uint64_t x) {
+   uint32_t lo = (uint32_t) x, hi = (uint32_t) (x >> 32);
+   return ((uint64_t) __byte_perm(lo, 0, 0x0123) << 32) | (uint64_t) __byte_perm(hi, 0, 0x0123);
+}
+__device__ __forceinline__ uint64_t hash64(uint64_t v) {
+   uint64_t m = v * 11400714819323198549ull; // 0x9E3779B97F4A7C55
+   return m ^ bswap64(m);
+}
+__device__ __forceinline__ uint64_t hashCombine(uint64_t newPiece, uint64_t total) { return newPiece ^ bswap64(total); }
+__device__ __forceinline__ uint64_t hashI32(int32_t k) { return hash64((uint64_t) (int64_t) k); }
+
+// ---------------------------------------------------------------- streaming loads (read-once column data)
+__device__ __forceinline__ int32_t ldStream32(const int32_t* p) {
+   int32_t v;
+   asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+   return v;
+}
+__device__ __forceinline__ int64_t ldStream64(const int64_t* p) {
+   int64_t v;
+   asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
+   return v;
+}
+
+// ---------------------------------------------------------------- filters
+// op mask: bit0 = accept a<b, bit1 = accept a==b, bit2 = accept a>b  (built on the host from LdbFilterOp)
+__device__ __forceinline__ bool cmpMask(int64_t a, int64_t b, uint32_t mask) {
+   uint32_t rel = a < b ? 1u : (a == b ? 2u : 4u);
+   return (rel & mask) != 0;
+}
+
+// ---------------------------------------------------------------- warp / block reductions
+__device__ __forceinline__ uint64_t shflXor64(uint64_t v, int m) {
+   uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t) v, m);
+   uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t) (v >> 32), m);
+   return ((uint64_t) hi << 32) | lo;
+}
+__device__ __forceinline__ uint64_t warpSum64(uint64_t v) { // wrapping
+#pragma unroll
+   for (int m = 16; m > 0; m >>= 1) v += shflXor64(v, m);
+   return v;
+}
+// exact 128-bit warp sum: the low word is split into two 32-bit limbs so that lane sums cannot lose carries
+__device__ __forceinline__ i128 warpSum128(i128 v) {
+   uint64_t s0 = warpSum64(v.lo & 0xffffffffull);
+   uint64_t s1 = warpSum64(v.lo >> 32);
+   uint64_t sh = warpSum64((uint64_t) v.hi);
+   i128 r;
+   uint64_t mid = s1 + (s0 >> 32); // < 2^38
+   r.lo = (s0 & 0xffffffffull) | (mid << 32);
+   r.hi = (int64_t) (sh + (mid >> 32));
+   return r;
+}
+// 128-bit atomic add as two 64-bit atomics with carry: commutative, exact mod 2^128 once all adds landed
+__device__ __forceinline__ void atomicAdd128(unsigned long long* lo, unsigned long long* hi, i128 v) {
+   unsigned long long old = atomicAdd(lo, (unsigned long long) v.lo);
+   unsigned long long carry = (old + v.lo) < old ? 1ull : 0ull;
+   unsigned long long h = (unsigned long long) v.hi + carry;
+   if (h != 0) atomicAdd(hi, h);
+}
+
+} // namespace ldb

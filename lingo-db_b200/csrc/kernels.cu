@@ -1,0 +1,727 @@
+// kernels.cu — hand-written sm_100a pipeline kernels for LingoDB's three hot paths.
+//
+// Design: every pipeline is ONE persistent, HBM-bound streaming kernel:
+//   grid = SMs × resident CTAs, each CTA strides over tiles of ROWS×blockDim rows; lane-contiguous
+//   rows so every warp-level load is one fully-coalesced 128 B (int32 columns) or 2×256 B
+//   (decimal128 columns, low 8 bytes of each 16 B cell — the reference truncates decimal(p<19) to
+//   i64 the same way, LowerToStd.cpp:111-209) request; all loads of a tile are issued before any
+//   arithmetic (ROWS × columns independent requests in flight per thread).  No tensor cores: the
+//   path is integer/hash work.  Aggregates are exact wrapping i64/i128 like the JIT's LLVM code.
+//   K1/K2  scanGroupByKernel      scan → filters → (group-by | keyless) SUMs
+//   K3     scanBuildKernel        scan → filters → [probe] → join-table insert
+//   K5     scanProbeAggKernel     scan → filters → probe group-join map → atomic i128 SUM
+//   K4     scanProbe2GroupByKernel scan → probe A → probe B → tiny group-by
+//   K6     partition*Kernel       radix partition by h64(key) for the NVLink all-to-all
+#include "device_utils.cuh"
+#include "kernels.h"
+#include "../../include/ldb_gpu.h"
+
+#include <string>
+
+namespace ldb {
+
+constexpr int kBlock = 256;
+
+// =================================================================================== filters
+__device__ __forceinline__ int64_t loadFilterValue(const FilterCol& f, int64_t r) {
+   if (f.kind == COL_I32) {
+      return (int64_t) __ldg((const int32_t*) f.base + r);
+   } else if (f.kind == COL_DEC128_LO64) {
+      return __ldg((const long long*) f.base + 2 * r);
+   } else { // COL_UTF8_EQ: 1 if the string equals the constant (VarLen32Filter<Eq>, Restrictions.cpp:279-325)
+      const int32_t* off = (const int32_t*) f.base + r;
+      int32_t b = __ldg(off), e = __ldg(off + 1);
+      if (e - b != f.strLen) return 0;
+      bool eq = true;
+      for (int i = 0; i < f.strLen; i++) eq &= __ldg(f.bytes + b + i) == f.str[i];
+      return eq ? 1 : 0;
+   }
+}
+__device__ __forceinline__ bool evalFilters(const FilterSet& F, int64_t r) {
+   bool pass = true;
+#pragma unroll
+   for (int i = 0; i < kMaxFilterCols; i++) {
+      if (i < F.n) {
+         int64_t v = loadFilterValue(F.c[i], r);
+         pass &= cmpMask(v, F.c[i].valA, F.c[i].maskA) & cmpMask(v, F.c[i].valB, F.c[i].maskB);
+      }
+   }
+   return pass;
+}
+
+// =================================================================================== group table (HBM)
+__device__ __forceinline__ uint64_t groupHash(const int32_t* k, int nKeys) {
+   // db.hash over the key tuple: first key starts the hash, further keys are combined in
+   // (LowerToStd.cpp:1139-1150); identical to the oracle's HashBuilder
+   uint64_t h = hashI32(k[0]);
+   if (nKeys > 1) h = hashCombine(hashI32(k[1]), h);
+   return h;
+}
+// lookup-or-insert (lowering of subop.lookup_or_insert, SubOpToControlFlow.cpp:3065-3157, as open addressing)
+__device__ int groupLookupOrInsert(const GroupTableDev& t, const int32_t* k) {
+   if (t.nKeys == 0) return 0;
+   uint32_t mask = (uint32_t) t.capacity - 1;
+   uint32_t s = (uint32_t) groupHash(k, t.nKeys) & mask;
+   for (int probes = 0; probes < t.capacity; probes++) {
+      int st = atomicCAS(&t.state[s], 0, 1);
+      if (st == 0) {
+         t.keys[s * kMaxKeys + 0] = k[0];
+         t.keys[s * kMaxKeys + 1] = t.nKeys > 1 ? k[1] : 0;
+         __threadfence();
+         atomicExch(&t.state[s], 2);
+         return (int) s;
+      }
+      while (st == 1) st = *((volatile int32_t*) &t.state[s]);
+      __threadfence();
+      const volatile int32_t* tk = t.keys + s * kMaxKeys;
+      if (tk[0] == k[0] && (t.nKeys < 2 || tk[1] == k[1])) return (int) s;
+      s = (s + 1) & mask;
+   }
+   atomicExch(t.error, 1);
+   return -1;
+}
+__device__ __forceinline__ void groupAtomicAdd(const GroupTableDev& t, int slot, int agg, i128 v, bool is64) {
+   unsigned long long* p = t.acc + ((size_t) slot * kMaxAggs + agg) * 2;
+   if (is64) atomicAdd(p, (unsigned long long) v.lo);
+   else atomicAdd128(p, p + 1, v);
+}
+
+// =================================================================================== join table (HBM)
+constexpr unsigned long long kEmptySlot = ~0ull;
+constexpr uint64_t kMaxProbe = 16384; // insert reports "table full" beyond this displacement; the host regrows
+__device__ __forceinline__ unsigned long long packSlot(int32_t key, int32_t payload) { return ((unsigned long long) (uint32_t) payload << 32) | (uint32_t) key; }
+// HashIndexedView::build's CAS push-front (LazyJoinHashtable.cpp:20-31) becomes a CAS into an open-addressing slot
+__device__ int64_t joinInsert(const JoinTableDev& t, int32_t key, int32_t payload) {
+   unsigned long long packed = packSlot(key, payload);
+   if (packed == kEmptySlot) { // (-1,-1) is the empty marker and cannot be stored
+      atomicExch(t.error, 3);
+      return -1;
+   }
+   uint64_t s = hashI32(key) & t.mask;
+   const uint64_t limit = t.mask < kMaxProbe ? t.mask + 1 : kMaxProbe; // a sanely loaded table never probes this far
+   for (uint64_t probes = 0; probes < limit; probes++) {
+      unsigned long long old = atomicCAS(&t.slots[s], kEmptySlot, packed);
+      if (old == kEmptySlot) {
+         atomicAdd(t.count, 1ull);
+         return (int64_t) s;
+      }
+      if (t.unique && (int32_t) (uint32_t) old == key) {
+         atomicExch(t.error, 2);
+         return -1;
+      }
+      s = (s + 1) & t.mask;
+   }
+   atomicExch(t.error, 1);
+   return -1;
+}
+// probe (SubOpToControlFlow.cpp:2558-2586 + chain walk :2254-2313): visit every entry with the key
+template <class Fn>
+__device__ __forceinline__ void joinProbe(const JoinTableDev& t, int32_t key, const Fn& fn) {
+   uint64_t s = hashI32(key) & t.mask;
+   const uint64_t limit = t.mask < kMaxProbe ? t.mask + 1 : kMaxProbe;
+   for (uint64_t probes = 0; probes < limit; probes++) {
+      unsigned long long e = __ldg(&t.slots[s]);
+      if (e == kEmptySlot) return;
+      if ((int32_t) (uint32_t) e == key) {
+         fn((int64_t) s, (int32_t) (uint32_t) (e >> 32));
+         if (t.unique) return;
+      }
+      s = (s + 1) & t.mask;
+   }
+}
+
+// =================================================================================== aggregate expressions
+template <int E, int A = 0, int B = 0, int C = 0>
+struct Agg {
+   static constexpr int expr = E, a = A, b = B, c = C;
+   static constexpr bool is64 = (E == LDB_EXPR_COL || E == LDB_EXPR_ONE);
+};
+template <class... As>
+struct AggList {
+   static constexpr int N = sizeof...(As);
+};
+template <int I, class... As>
+struct AggAt;
+template <int I, class A0, class... As>
+struct AggAt<I, A0, As...> : AggAt<I - 1, As...> {};
+template <class A0, class... As>
+struct AggAt<0, A0, As...> {
+   using type = A0;
+};
+
+// typed like the db dialect types them (DBOps.cpp:98-107): `1` is 10^scale of the decimal operand
+template <class A>
+__device__ __forceinline__ i128 evalAgg(const int64_t* v, int64_t one) {
+   if constexpr (A::expr == LDB_EXPR_COL) {
+      return i128{(uint64_t) v[A::a], 0};
+   } else if constexpr (A::expr == LDB_EXPR_MUL) {
+      return mul64x64(v[A::a], v[A::b]);
+   } else if constexpr (A::expr == LDB_EXPR_MUL_1MINUS) {
+      return mul64x64(v[A::a], one - v[A::b]);
+   } else if constexpr (A::expr == LDB_EXPR_MUL_1MINUS_1PLUS) {
+      return mul128x64(mul64x64(v[A::a], one - v[A::b]), one + v[A::c]);
+   } else {
+      return i128{1, 0};
+   }
+}
+__device__ __forceinline__ i128 evalAggDyn(const AggSpec& a, const int64_t* v, int64_t one) {
+   switch (a.expr) {
+      case LDB_EXPR_COL: return i128{(uint64_t) v[0], 0};
+      case LDB_EXPR_MUL: return mul64x64(v[0], v[1]);
+      case LDB_EXPR_MUL_1MINUS: return mul64x64(v[0], one - v[1]);
+      case LDB_EXPR_MUL_1MINUS_1PLUS: return mul128x64(mul64x64(v[0], one - v[1]), one + v[2]);
+      default: return i128{1, 0};
+   }
+}
+
+// compile-time aggregate list: every index below is a constant after inlining, so v[]/acc[] live in registers
+template <int... Is>
+struct Seq {};
+template <int N, int... Is>
+struct MakeSeq : MakeSeq<N - 1, N - 1, Is...> {};
+template <int... Is>
+struct MakeSeq<0, Is...> {
+   using type = Seq<Is...>;
+};
+template <class... As>
+struct Aggs {
+   static constexpr int N = sizeof...(As);
+   using S = typename MakeSeq<N>::type;
+   template <int... Is>
+   static __device__ __forceinline__ void eval(i128* v, const int64_t* vals, int64_t one, Seq<Is...>) {
+      ((v[Is] = evalAgg<As>(vals, one)), ...);
+   }
+   template <int... Is>
+   static __device__ __forceinline__ void accumulate(i128* acc, const i128* v, Seq<Is...>) {
+      ((As::is64 ? (void) (acc[Is].lo += v[Is].lo) : (void) (acc[Is] = add128(acc[Is], v[Is]))), ...);
+   }
+   template <int... Is>
+   static __device__ __forceinline__ void sharedAdd(unsigned long long (*sAcc)[2], const i128* v, Seq<Is...>) {
+      ((As::is64 ? (void) atomicAdd(&sAcc[Is][0], (unsigned long long) v[Is].lo) : atomicAdd128(&sAcc[Is][0], &sAcc[Is][1], v[Is])), ...);
+   }
+   template <int... Is>
+   static __device__ __forceinline__ void globalAdd(const GroupTableDev& t, int slot, const i128* v, Seq<Is...>) {
+      (groupAtomicAdd(t, slot, Is, v[Is], As::is64), ...);
+   }
+   template <class A, int I>
+   static __device__ __forceinline__ void warpFlushOne(unsigned long long (*sAcc)[2], const i128* acc, int lane) {
+      i128 s = A::is64 ? i128{warpSum64(acc[I].lo), 0} : warpSum128(acc[I]);
+      if (lane == 0 && (s.lo | (uint64_t) s.hi)) {
+         if (A::is64) atomicAdd(&sAcc[I][0], (unsigned long long) s.lo);
+         else atomicAdd128(&sAcc[I][0], &sAcc[I][1], s);
+      }
+   }
+   template <int... Is>
+   static __device__ __forceinline__ void warpFlush(unsigned long long (*sAcc)[2], const i128* acc, int lane, Seq<Is...>) {
+      (warpFlushOne<As, Is>(sAcc, acc, lane), ...);
+   }
+};
+
+// =================================================================================== K1 / K2
+// scan → filters → group by NK int32 keys → SUMs.  NK == 0 is the keyless form (Q6, SimpleState).
+// Hot groups (the first GREG a CTA meets) accumulate in REGISTERS with predicated adds — the
+// reference's 1024-slot per-worker pre-aggregation cache (PreAggregationHashtable.cpp:46-60) collapses to
+// this for small domains; further groups use shared-memory atomics, and only a CTA that meets
+// more than LG groups touches the HBM table per row.  One flush per CTA at the end.
+template <int NK, int NV, int ROWS, class... As>
+__global__ void __launch_bounds__(kBlock, 2) scanGroupByKernel(const __grid_constant__ GroupByParams p) {
+   using AL = Aggs<As...>;
+   constexpr int N = AL::N;
+   constexpr int GREG = NK == 0 ? 1 : 4; // register-resident groups
+   constexpr int LG = 16;                // CTA-local groups (registers + shared)
+   __shared__ int32_t sKeys[LG][kMaxKeys];
+   __shared__ int32_t sSlot[LG];
+   __shared__ int32_t sCount, sLock;
+   __shared__ unsigned long long sAcc[LG][N][2];
+
+   for (int i = threadIdx.x; i < LG * N * 2; i += kBlock) (&sAcc[0][0][0])[i] = 0;
+   if (threadIdx.x == 0) {
+      sCount = NK == 0 ? 1 : 0;
+      sLock = 0;
+      if (NK == 0) sSlot[0] = 0;
+   }
+   __syncthreads();
+
+   i128 acc[GREG][N];
+#pragma unroll
+   for (int g = 0; g < GREG; g++)
+#pragma unroll
+      for (int a = 0; a < N; a++) acc[g][a] = i128{0, 0};
+
+   const int64_t n = p.src.nRows;
+   const int64_t tileRows = (int64_t) kBlock * ROWS;
+   const int64_t one = 100; // 10^scale of decimal(12,2); checked on the host
+   int32_t lastK0 = 0, lastK1 = 0, lastId = -2;
+
+   for (int64_t base = (int64_t) blockIdx.x * tileRows; base < n; base += (int64_t) gridDim.x * tileRows) {
+      int64_t vals[ROWS][NV];
+      int32_t keys[ROWS][NK == 0 ? 1 : NK];
+      bool pass[ROWS];
+      // ---- issue every load of the tile first
+#pragma unroll
+      for (int j = 0; j < ROWS; j++) {
+         int64_t r = base + (int64_t) j * kBlock + threadIdx.x;
+         bool valid = r < n;
+         int64_t rr = valid ? r : n - 1;
+#pragma unroll
+         for (int c = 0; c < NV; c++) vals[j][c] = ldStream64((const int64_t*) p.valueCols[c] + 2 * rr);
+#pragma unroll
+         for (int k = 0; k < NK; k++) keys[j][k] = ldStream32(p.keyCols[k] + rr);
+         pass[j] = valid & evalFilters(p.src.filters, rr);
+      }
+      // ---- per row: group id, expression, accumulate
+#pragma unroll
+      for (int j = 0; j < ROWS; j++) {
+         if (!pass[j]) continue;
+         int id = 0;
+         if constexpr (NK > 0) {
+            int32_t k0 = keys[j][0], k1 = NK > 1 ? keys[j][NK - 1] : 0;
+            if (lastId != -2 && k0 == lastK0 && k1 == lastK1) {
+               id = lastId;
+            } else {
+               id = -1;
+               int cnt = *((volatile int32_t*) &sCount);
+               for (int g = 0; g < cnt; g++)
+                  if (sKeys[g][0] == k0 && sKeys[g][1] == k1) id = g;
+               if (id < 0) { // first sight in this CTA: register the group under the CTA lock
+                  bool done = false;
+                  while (!done) {
+                     if (atomicCAS(&sLock, 0, 1) == 0) {
+                        int c2 = *((volatile int32_t*) &sCount);
+                        for (int g = 0; g < c2; g++)
+                           if (((volatile int32_t*) sKeys[g])[0] == k0 && ((volatile int32_t*) sKeys[g])[1] == k1) id = g;
+                        if (id < 0 && c2 < LG) {
+                           int32_t kk[2] = {k0, k1};
+                           int slot = groupLookupOrInsert(p.table, kk);
+                           sKeys[c2][0] = k0;
+                           sKeys[c2][1] = k1;
+                           sSlot[c2] = slot;
+                           __threadfence_block();
+                           *((volatile int32_t*) &sCount) = c2 + 1;
+                           id = c2;
+                        }
+                        __threadfence_block();
+                        atomicExch(&sLock, 0);
+                        done = true;
+                     }
+                  }
+               }
+               lastK0 = k0;
+               lastK1 = k1;
+               lastId = id;
+            }
+         }
+         i128 v[N];
+         AL::eval(v, vals[j], one, typename AL::S{});
+         if (id >= 0 && id < GREG) {
+#pragma unroll
+            for (int g = 0; g < GREG; g++)
+               if (id == g) AL::accumulate(acc[g], v, typename AL::S{});
+         } else if (id >= 0) { // CTA-local but not register resident: shared-memory atomics
+            AL::sharedAdd(sAcc[id], v, typename AL::S{});
+         } else { // more groups than a CTA tracks: straight to the HBM table
+            int32_t kk[2] = {keys[j][0], NK > 1 ? keys[j][NK - 1] : 0};
+            int slot = groupLookupOrInsert(p.table, kk);
+            if (slot >= 0) AL::globalAdd(p.table, slot, v, typename AL::S{});
+         }
+      }
+   }
+   // ---- flush: registers → warp sums → shared → one HBM atomic per (CTA, group, aggregate)
+   __syncthreads();
+   const int lane = threadIdx.x & 31;
+#pragma unroll
+   for (int g = 0; g < GREG; g++) AL::warpFlush(sAcc[g], acc[g], lane, typename AL::S{});
+   __syncthreads();
+   const int cnt = sCount;
+   for (int i = threadIdx.x; i < cnt * N; i += kBlock) {
+      int g = i / N, a = i % N;
+      int slot = sSlot[g];
+      if (slot < 0) continue;
+      i128 s{sAcc[g][a][0], (int64_t) sAcc[g][a][1]};
+      if (s.lo | (uint64_t) s.hi) {
+         unsigned long long* dst = p.table.acc + ((size_t) slot * kMaxAggs + a) * 2;
+         atomicAdd128(dst, dst + 1, s); // 64-bit aggregates keep hi == 0 and are read back as i64
+      }
+   }
+}
+
+// ---- signature registry
+static std::string signature(const GroupByParams& p) {
+   std::string s = "k" + std::to_string(p.nKeys) + "v" + std::to_string(p.nValueCols);
+   for (int i = 0; i < p.nAggs; i++) {
+      const AggSpec& a = p.aggs[i];
+      int used = a.expr == LDB_EXPR_COL ? 1 : a.expr == LDB_EXPR_MUL || a.expr == LDB_EXPR_MUL_1MINUS ? 2 : a.expr == LDB_EXPR_MUL_1MINUS_1PLUS ? 3 : 0;
+      s += "|" + std::to_string(a.expr);
+      for (int k = 0; k < used; k++) s += (k ? "," : ":") + std::to_string(a.col[k]);
+   }
+   return s;
+}
+template <int NK, int NV, int ROWS, class... As>
+static void launchGB(const GroupByParams& p, int smCount, cudaStream_t s) {
+   int64_t tiles = (p.src.nRows + (int64_t) kBlock * ROWS - 1) / ((int64_t) kBlock * ROWS);
+   int grid = (int) std::min<int64_t>(std::max<int64_t>(tiles, 1), (int64_t) smCount * 2);
+   scanGroupByKernel<NK, NV, ROWS, As...><<<grid, kBlock, 0, s>>>(p);
+}
+using C0 = Agg<LDB_EXPR_COL, 0>;
+using C1 = Agg<LDB_EXPR_COL, 1>;
+using C2 = Agg<LDB_EXPR_COL, 2>;
+using ONE = Agg<LDB_EXPR_ONE>;
+bool launchScanGroupBy(const GroupByParams& p, int smCount, cudaStream_t s, const char** why) {
+   std::string sig = signature(p);
+   // Q1 pricing summary: sum(a) sum(b) sum(b*(1-c)) sum(b*(1-c)*(1+d)) sum(c) count   (resources/sql/tpch/1.sql)
+   if (sig == "k2v4|0:0|0:1|2:1,2|3:1,2,3|0:2|4") {
+      launchGB<2, 4, 2, C0, C1, Agg<LDB_EXPR_MUL_1MINUS, 1, 2>, Agg<LDB_EXPR_MUL_1MINUS_1PLUS, 1, 2, 3>, C2, ONE>(p, smCount, s);
+   } else if (sig == "k1v4|0:0|0:1|2:1,2|3:1,2,3|0:2|4") {
+      launchGB<1, 4, 2, C0, C1, Agg<LDB_EXPR_MUL_1MINUS, 1, 2>, Agg<LDB_EXPR_MUL_1MINUS_1PLUS, 1, 2, 3>, C2, ONE>(p, smCount, s);
+   } else if (sig == "k0v2|1:0,1") { // Q6 forecast revenue: sum(a*b)
+      launchGB<0, 2, 4, Agg<LDB_EXPR_MUL, 0, 1>>(p, smCount, s);
+   } else if (sig == "k0v2|2:0,1") { // keyless sum(a*(1-b))
+      launchGB<0, 2, 4, Agg<LDB_EXPR_MUL_1MINUS, 0, 1>>(p, smCount, s);
+   } else if (sig == "k0v1|0:0|4") { // keyless sum(a), count
+      launchGB<0, 1, 4, C0, ONE>(p, smCount, s);
+   } else if (sig == "k1v2|2:0,1") { // group by k: sum(a*(1-b))
+      launchGB<1, 2, 4, Agg<LDB_EXPR_MUL_1MINUS, 0, 1>>(p, smCount, s);
+   } else if (sig == "k2v2|2:0,1") {
+      launchGB<2, 2, 4, Agg<LDB_EXPR_MUL_1MINUS, 0, 1>>(p, smCount, s);
+   } else if (sig == "k1v1|0:0|4") { // group by k: sum(a), count
+      launchGB<1, 1, 4, C0, ONE>(p, smCount, s);
+   } else if (sig == "k2v1|0:0|4") {
+      launchGB<2, 1, 4, C0, ONE>(p, smCount, s);
+   } else {
+      static thread_local std::string msg;
+      msg = "no compiled group-by pipeline for aggregate signature '" + sig + "' (register it in kernels.cu:launchScanGroupBy)";
+      *why = msg.c_str();
+      return false;
+   }
+   return true;
+}
+
+// =================================================================================== K3 build
+// scan → filters → [probe parent table] → insert {key, payload, side…}
+// (subop.materialize + rt::GrowingBuffer::insert + rt::HashIndexedView::build; for the group-join
+//  the lookup_or_insert of the left input, RelAlgToSubOp.cpp:2682-2950)
+template <int ROWS>
+__global__ void __launch_bounds__(kBlock, 4) scanBuildKernel(const __grid_constant__ BuildParams p) {
+   const int64_t n = p.src.nRows;
+   const int64_t tileRows = (int64_t) kBlock * ROWS;
+   for (int64_t base = (int64_t) blockIdx.x * tileRows; base < n; base += (int64_t) gridDim.x * tileRows) {
+      int32_t key[ROWS], pkey[ROWS], pay[ROWS];
+      bool pass[ROWS];
+#pragma unroll
+      for (int j = 0; j < ROWS; j++) {
+         int64_t r = base + (int64_t) j * kBlock + threadIdx.x;
+         bool valid = r < n;
+         int64_t rr = valid ? r : n - 1;
+         key[j] = ldStream32(p.keyCol + rr);
+         pkey[j] = p.hasProbe ? ldStream32(p.probeKeyCol + rr) : 0;
+         pay[j] = p.payloadCol ? ldStream32(p.payloadCol + rr) : 0;
+         pass[j] = valid & evalFilters(p.src.filters, rr);
+      }
+#pragma unroll
+      for (int j = 0; j < ROWS; j++) {
+         if (!pass[j]) continue;
+         int64_t r = base + (int64_t) j * kBlock + threadIdx.x;
+         auto insert = [&](int32_t payload) {
+            int64_t slot = joinInsert(p.sink, key[j], payload);
+            if (slot >= 0) {
+               for (int k = 0; k < p.nSide; k++) p.sink.side[k][slot] = __ldg(p.sideCols[k] + r);
+            }
+         };
+         if (p.hasProbe) {
+            joinProbe(p.probe, pkey[j], [&](int64_t, int32_t parentPayload) { insert(p.payloadCol ? pay[j] : parentPayload); });
+         } else {
+            insert(pay[j]);
+         }
+      }
+   }
+}
+void launchScanBuild(const BuildParams& p, int smCount, cudaStream_t s) {
+   constexpr int ROWS = 4;
+   int64_t tiles = (p.src.nRows + (int64_t) kBlock * ROWS - 1) / ((int64_t) kBlock * ROWS);
+   int grid = (int) std::min<int64_t>(std::max<int64_t>(tiles, 1), (int64_t) smCount * 4);
+   scanBuildKernel<ROWS><<<grid, kBlock, 0, s>>>(p);
+}
+
+// =================================================================================== K5 probe + aggregate
+// scan → filters → pure lookup in the group-join map → SUM into the shared entry.  The reference
+// takes a per-entry spin lock (SubOpToControlFlow.cpp:4218-4251, EntryLock.cpp:9-25) or an
+// atomic_rmw; here the i128 SUM is two 64-bit atomics with carry (exact, order independent).
+template <int NV, int ROWS>
+__global__ void __launch_bounds__(kBlock, 4) scanProbeAggKernel(const __grid_constant__ ProbeAggParams p) {
+   const int64_t n = p.src.nRows;
+   const int64_t tileRows = (int64_t) kBlock * ROWS;
+   const int64_t one = 100;
+   for (int64_t base = (int64_t) blockIdx.x * tileRows; base < n; base += (int64_t) gridDim.x * tileRows) {
+      int32_t key[ROWS];
+      int64_t vals[ROWS][NV];
+      bool pass[ROWS];
+#pragma unroll
+      for (int j = 0; j < ROWS; j++) {
+         int64_t r = base + (int64_t) j * kBlock + threadIdx.x;
+         bool valid = r < n;
+         int64_t rr = valid ? r : n - 1;
+         key[j] = ldStream32(p.probeKeyCol + rr);
+#pragma unroll
+         for (int c = 0; c < NV; c++) vals[j][c] = ldStream64((const int64_t*) p.valueCols[c] + 2 * rr);
+         pass[j] = valid & evalFilters(p.src.filters, rr);
+      }
+#pragma unroll
+      for (int j = 0; j < ROWS; j++) {
+         if (!pass[j]) continue;
+         joinProbe(p.table, key[j], [&](int64_t slot, int32_t) {
+            i128 v = evalAggDyn(p.agg, vals[j], one);
+            atomicAdd128(&p.table.aggLo[slot], &p.table.aggHi[slot], v);
+            p.table.marker[slot] = 1;
+         });
+      }
+   }
+}
+bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, const char** why) {
+   constexpr int ROWS = 4;
+   int64_t tiles = (p.src.nRows + (int64_t) kBlock * ROWS - 1) / ((int64_t) kBlock * ROWS);
+   int grid = (int) std::min<int64_t>(std::max<int64_t>(tiles, 1), (int64_t) smCount * 4);
+   int nv = p.agg.expr == LDB_EXPR_COL ? 1 : p.agg.expr == LDB_EXPR_MUL_1MINUS_1PLUS ? 3 : 2;
+   if (p.agg.col[0] != 0 || (nv > 1 && p.agg.col[1] != 1) || (nv > 2 && p.agg.col[2] != 2)) {
+      *why = "probe-aggregate pipeline expects value columns in expression order";
+      return false;
+   }
+   if (nv == 1) scanProbeAggKernel<1, ROWS><<<grid, kBlock, 0, s>>>(p);
+   else if (nv == 2) scanProbeAggKernel<2, ROWS><<<grid, kBlock, 0, s>>>(p);
+   else scanProbeAggKernel<3, ROWS><<<grid, kBlock, 0, s>>>(p);
+   return true;
+}
+
+// =================================================================================== K4 probe, probe, group
+// scan → probe A on keyA → probe B on keyB → keep rows whose payloads agree (the composite join key
+// (l_suppkey, c_nationkey) = (s_suppkey, s_nationkey) of Q5) → group by that payload → SUM.
+template <int NV, int ROWS>
+__global__ void __launch_bounds__(kBlock, 4) scanProbe2GroupByKernel(const __grid_constant__ Probe2GroupByParams p) {
+   const int64_t n = p.src.nRows;
+   const int64_t tileRows = (int64_t) kBlock * ROWS;
+   const int64_t one = 100;
+   for (int64_t base = (int64_t) blockIdx.x * tileRows; base < n; base += (int64_t) gridDim.x * tileRows) {
+      int32_t ka[ROWS], kb[ROWS];
+      int64_t vals[ROWS][NV];
+      bool pass[ROWS];
+#pragma unroll
+      for (int j = 0; j < ROWS; j++) {
+         int64_t r = base + (int64_t) j * kBlock + threadIdx.x;
+         bool valid = r < n;
+         int64_t rr = valid ? r : n - 1;
+         ka[j] = ldStream32(p.keyColA + rr);
+         kb[j] = ldStream32(p.keyColB + rr);
+#pragma unroll
+         for (int c = 0; c < NV; c++) vals[j][c] = ldStream64((const int64_t*) p.valueCols[c] + 2 * rr);
+         pass[j] = valid & evalFilters(p.src.filters, rr);
+      }
+#pragma unroll
+      for (int j = 0; j < ROWS; j++) {
+         if (!pass[j]) continue;
+         joinProbe(p.tableA, ka[j], [&](int64_t, int32_t payA) {
+            joinProbe(p.tableB, kb[j], [&](int64_t, int32_t payB) {
+               if (payA != payB) return;
+               int32_t kk[2] = {payB, 0};
+               int slot = groupLookupOrInsert(p.groups, kk);
+               if (slot >= 0) groupAtomicAdd(p.groups, slot, 0, evalAggDyn(p.agg, vals[j], one), p.agg.expr == LDB_EXPR_COL || p.agg.expr == LDB_EXPR_ONE);
+            });
+         });
+      }
+   }
+}
+bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStream_t s, const char** why) {
+   constexpr int ROWS = 4;
+   int64_t tiles = (p.src.nRows + (int64_t) kBlock * ROWS - 1) / ((int64_t) kBlock * ROWS);
+   int grid = (int) std::min<int64_t>(std::max<int64_t>(tiles, 1), (int64_t) smCount * 4);
+   int nv = p.agg.expr == LDB_EXPR_COL ? 1 : p.agg.expr == LDB_EXPR_MUL_1MINUS_1PLUS ? 3 : 2;
+   if (p.agg.col[0] != 0 || (nv > 1 && p.agg.col[1] != 1) || (nv > 2 && p.agg.col[2] != 2)) {
+      *why = "probe-probe-group pipeline expects value columns in expression order";
+      return false;
+   }
+   if (nv == 1) scanProbe2GroupByKernel<1, ROWS><<<grid, kBlock, 0, s>>>(p);
+   else if (nv == 2) scanProbe2GroupByKernel<2, ROWS><<<grid, kBlock, 0, s>>>(p);
+   else scanProbe2GroupByKernel<3, ROWS><<<grid, kBlock, 0, s>>>(p);
+   return true;
+}
+
+// =================================================================================== top-k over the group-join map
+// Final scan of the map (marker == true) + Heap (include/lingodb/runtime/Heap.h): order by
+// (agg desc, side0 asc, key asc).  Each CTA keeps its own top-k in shared memory; the host merges.
+__device__ __forceinline__ bool topkBefore(const TopKRowDev& a, const TopKRowDev& b) {
+   if (a.aggHi != b.aggHi) return a.aggHi > b.aggHi;
+   if (a.aggLo != b.aggLo) return a.aggLo > b.aggLo;
+   if (a.side0 != b.side0) return a.side0 < b.side0;
+   return a.key < b.key;
+}
+constexpr int kTopKMax = 64;
+__global__ void __launch_bounds__(kBlock) joinTopKKernel(JoinTableDev t, int k, TopKRowDev* out) {
+   __shared__ TopKRowDev best[kTopKMax];
+   __shared__ int sCount, sLock;
+   if (threadIdx.x == 0) {
+      sCount = 0;
+      sLock = 0;
+   }
+   __syncthreads();
+   const uint64_t cap = t.mask + 1;
+   for (uint64_t s = (uint64_t) blockIdx.x * kBlock + threadIdx.x; s < cap; s += (uint64_t) gridDim.x * kBlock) {
+      if (!t.marker[s]) continue;
+      unsigned long long e = t.slots[s];
+      if (e == kEmptySlot) continue;
+      TopKRowDev c;
+      c.key = (int32_t) (uint32_t) e;
+      c.side0 = t.side[0] ? t.side[0][s] : 0;
+      c.side1 = t.side[1] ? t.side[1][s] : 0;
+      c.valid = 1;
+      c.aggLo = t.aggLo[s];
+      c.aggHi = (long long) t.aggHi[s];
+      // cheap reject against the current k-th without the lock
+      int cnt = *((volatile int*) &sCount);
+      if (cnt == k) {
+         TopKRowDev last;
+         last.key = ((volatile TopKRowDev*) best)[k - 1].key;
+         last.side0 = ((volatile TopKRowDev*) best)[k - 1].side0;
+         last.aggLo = ((volatile TopKRowDev*) best)[k - 1].aggLo;
+         last.aggHi = ((volatile TopKRowDev*) best)[k - 1].aggHi;
+         if (!topkBefore(c, last)) continue;
+      }
+      bool done = false;
+      while (!done) {
+         if (atomicCAS(&sLock, 0, 1) == 0) {
+            __threadfence_block();
+            int n = *((volatile int*) &sCount);
+            int pos = n;
+            while (pos > 0 && topkBefore(c, best[pos - 1])) pos--;
+            if (pos < k) {
+               int end = n < k ? n : k - 1;
+               for (int i = end; i > pos; i--) best[i] = best[i - 1];
+               best[pos] = c;
+               if (n < k) *((volatile int*) &sCount) = n + 1;
+            }
+            __threadfence_block();
+            atomicExch(&sLock, 0);
+            done = true;
+         }
+      }
+   }
+   __syncthreads();
+   for (int i = threadIdx.x; i < k; i += kBlock) {
+      TopKRowDev r = best[i < sCount ? i : 0];
+      if (i >= sCount) r.valid = 0;
+      out[(size_t) blockIdx.x * k + i] = r;
+   }
+}
+void launchJoinTopK(const JoinTableDev& t, int k, TopKRowDev* out, int* outBlocks, int smCount, cudaStream_t s) {
+   int grid = smCount * 2;
+   *outBlocks = grid;
+   joinTopKKernel<<<grid, kBlock, 0, s>>>(t, k, out);
+}
+
+// =================================================================================== small helpers
+__global__ void fill64Kernel(unsigned long long* p, unsigned long long v, int64_t n) {
+   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) p[i] = v;
+}
+void launchFill64(unsigned long long* p, unsigned long long v, int64_t n, cudaStream_t s) {
+   int grid = (int) std::min<int64_t>((n + 255) / 256, 148 * 8);
+   if (grid < 1) grid = 1;
+   fill64Kernel<<<grid, 256, 0, s>>>(p, v, n);
+}
+__global__ void insertTuplesKernel(JoinTableDev t, const int32_t* keys, const int32_t* payloads, const int32_t* side0, const int32_t* side1, int64_t n) {
+   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+      int64_t slot = joinInsert(t, keys[i], payloads ? payloads[i] : 0);
+      if (slot >= 0) {
+         if (side0) t.side[0][slot] = side0[i];
+         if (side1) t.side[1][slot] = side1[i];
+      }
+   }
+}
+void launchInsertTuples(const JoinTableDev& t, const int32_t* keys, const int32_t* payloads, const int32_t* side0, const int32_t* side1, int64_t n, int smCount, cudaStream_t s) {
+   int grid = (int) std::min<int64_t>(std::max<int64_t>((n + 255) / 256, 1), (int64_t) smCount * 8);
+   insertTuplesKernel<<<grid, 256, 0, s>>>(t, keys, payloads, side0, side1, n);
+}
+__global__ void hashI64Kernel(const int64_t* a, const int64_t* b, int64_t n, uint64_t* out) {
+   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+      uint64_t h = hash64((uint64_t) a[i]);
+      if (b) h = hashCombine(hash64((uint64_t) b[i]), h);
+      out[i] = h;
+   }
+}
+void launchHashI64(const int64_t* a, const int64_t* b, int64_t n, uint64_t* out, cudaStream_t s) {
+   int grid = (int) std::min<int64_t>(std::max<int64_t>((n + 255) / 256, 1), 1024);
+   hashI64Kernel<<<grid, 256, 0, s>>>(a, b, n, out);
+}
+// K7: fold partial groups (e.g. gathered from the other GPUs) into the table
+__global__ void groupMergeRowsKernel(GroupTableDev t, const int32_t* keys, const unsigned long long* acc, int32_t nRows) {
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nRows * t.nAggs; i += gridDim.x * blockDim.x) {
+      int r = i / t.nAggs, a = i % t.nAggs;
+      int32_t kk[2] = {keys[r * kMaxKeys], keys[r * kMaxKeys + 1]};
+      int slot = groupLookupOrInsert(t, kk);
+      if (slot < 0) continue;
+      i128 v{acc[((size_t) r * kMaxAggs + a) * 2], (int64_t) acc[((size_t) r * kMaxAggs + a) * 2 + 1]};
+      unsigned long long* dst = t.acc + ((size_t) slot * kMaxAggs + a) * 2;
+      atomicAdd128(dst, dst + 1, v);
+   }
+}
+void launchGroupMergeRows(const GroupTableDev& t, const int32_t* keys, const unsigned long long* acc, int32_t nRows, cudaStream_t s) {
+   int total = nRows * t.nAggs;
+   int grid = std::max(1, std::min((total + 127) / 128, 256));
+   groupMergeRowsKernel<<<grid, 128, 0, s>>>(t, keys, acc, nRows);
+}
+
+// =================================================================================== K6 radix partition
+// dest = top bits of the reference hash (the low bits stay for the local directory, mirroring the
+// reference's use of hash & 63 for its 64 partitions, PreAggregationHashtable.cpp:47-51)
+__device__ __forceinline__ int partOf(int32_t key, int nParts) { return (int) (((hashI32(key) >> 32) * (uint64_t) nParts) >> 32); }
+__global__ void __launch_bounds__(kBlock) partitionHistogramKernel(const int32_t* keys, int64_t n, int nParts, unsigned long long* counts) {
+   __shared__ unsigned int sCnt[64];
+   for (int i = threadIdx.x; i < 64; i += kBlock) sCnt[i] = 0;
+   __syncthreads();
+   for (int64_t i = (int64_t) blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t) gridDim.x * kBlock) atomicAdd(&sCnt[partOf(ldStream32(keys + i), nParts)], 1u);
+   __syncthreads();
+   for (int i = threadIdx.x; i < nParts; i += kBlock)
+      if (sCnt[i]) atomicAdd(&counts[i], (unsigned long long) sCnt[i]);
+}
+void launchPartitionHistogram(const int32_t* keys, int64_t n, int nParts, unsigned long long* counts, int smCount, cudaStream_t s) {
+   int grid = (int) std::min<int64_t>(std::max<int64_t>((n + kBlock - 1) / kBlock, 1), (int64_t) smCount * 8);
+   partitionHistogramKernel<<<grid, kBlock, 0, s>>>(keys, n, nParts, counts);
+}
+struct PartitionCols {
+   const void* in[4];
+   void* out[4];
+   int32_t width[4];
+   int32_t n;
+};
+__global__ void __launch_bounds__(kBlock) partitionScatterKernel(const int32_t* keys, PartitionCols cols, int64_t n, int nParts, unsigned long long* cursors, int32_t* outKeys) {
+   // warp-aggregated claims: lanes going to the same partition share one atomic (__match_any_sync)
+   for (int64_t base = (int64_t) blockIdx.x * kBlock; base < n; base += (int64_t) gridDim.x * kBlock) {
+      int64_t i = base + threadIdx.x;
+      bool valid = i < n;
+      int32_t key = valid ? ldStream32(keys + i) : 0;
+      int part = valid ? partOf(key, nParts) : -1;
+      unsigned active = __ballot_sync(0xffffffffu, valid);
+      if (!valid) continue;
+      unsigned peers = __match_any_sync(active, part);
+      int leader = __ffs(peers) - 1;
+      int lane = threadIdx.x & 31;
+      unsigned long long pos = 0;
+      if (lane == leader) pos = atomicAdd(&cursors[part], (unsigned long long) __popc(peers));
+      pos = __shfl_sync(peers, pos, leader) + __popc(peers & ((1u << lane) - 1));
+      outKeys[pos] = key;
+      for (int c = 0; c < cols.n; c++) {
+         if (cols.width[c] == 4) ((int32_t*) cols.out[c])[pos] = ((const int32_t*) cols.in[c])[i];
+         else if (cols.width[c] == 8) ((int64_t*) cols.out[c])[pos] = ((const int64_t*) cols.in[c])[i];
+         else ((int4*) cols.out[c])[pos] = ((const int4*) cols.in[c])[i];
+      }
+   }
+}
+void launchPartitionScatter(const int32_t* keys, const void* const* payloadCols, const int32_t* widths, int nPayload, int64_t n, int nParts, unsigned long long* cursors, int32_t* outKeys, void* const* outPayload, int smCount, cudaStream_t s) {
+   PartitionCols cols{};
+   cols.n = nPayload;
+   for (int c = 0; c < nPayload; c++) {
+      cols.in[c] = payloadCols[c];
+      cols.out[c] = outPayload[c];
+      cols.width[c] = widths[c];
+   }
+   int grid = (int) std::min<int64_t>(std::max<int64_t>((n + kBlock - 1) / kBlock, 1), (int64_t) smCount * 8);
+   partitionScatterKernel<<<grid, kBlock, 0, s>>>(keys, cols, n, nParts, cursors, outKeys);
+}
+
+} // namespace ldb

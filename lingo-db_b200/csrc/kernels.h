@@ -1,0 +1,127 @@
+// kernels.h — host-visible parameter blocks and launchers of the sm_100a pipeline kernels (kernels.cu).
+// Internal to libldb_gpu.so; the public surface is include/ldb_gpu.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ldb {
+
+constexpr int kMaxFilterCols = 4;
+constexpr int kMaxValueCols = 4;
+constexpr int kMaxAggs = 8;
+constexpr int kMaxKeys = 2;
+constexpr int kMaxSide = 2;
+
+enum ColKind : int32_t { COL_I32 = 0, COL_DEC128_LO64 = 1, COL_UTF8_EQ = 2 };
+
+// One pushed-down filter column with up to two predicates (e.g. a range); op masks as in cmpMask().
+// utf8 columns evaluate `string == constant` to 1/0 first, then compare that to valA (1).
+struct FilterCol {
+   const void* base;     // values (int32 / decimal128) or utf8 offsets
+   const uint8_t* bytes; // utf8 data
+   int32_t kind;
+   uint32_t maskA, maskB;
+   int64_t valA, valB;
+   uint8_t str[24];
+   int32_t strLen;
+};
+struct FilterSet {
+   int32_t n;
+   FilterCol c[kMaxFilterCols];
+};
+
+// ---- small-domain group table (rt::PreAggregationHashtable / SimpleState twin), lives in HBM
+struct GroupTableDev {
+   int32_t capacity; // power of two (1 for a keyless SimpleState)
+   int32_t nKeys, nAggs;
+   int32_t* state;           // 0 empty, 1 being written, 2 ready
+   int32_t* keys;            // [capacity][kMaxKeys]
+   unsigned long long* acc;  // [capacity][kMaxAggs][2] = {lo, hi}
+   int32_t* error;           // set to 1 on overflow
+};
+
+// ---- join table (rt::GrowingBuffer + rt::HashIndexedView twin; with agg lanes: the group-join map)
+struct JoinTableDev {
+   unsigned long long* slots; // {key = low 32 bits, payload = high 32 bits}; all ones = empty
+   uint64_t mask;             // capacity - 1
+   int32_t* side[kMaxSide];   // [capacity] int32 payload lanes
+   unsigned long long* aggLo; // [capacity]
+   unsigned long long* aggHi; // [capacity]
+   uint8_t* marker;           // [capacity]
+   unsigned long long* count; // inserted entries
+   int32_t* error;            // 1 = table full, 2 = duplicate key in a unique table
+   int32_t unique;
+};
+
+struct ScanSource {
+   int64_t nRows;
+   FilterSet filters;
+};
+
+// aggregate = SUM(expr over value columns); expr kinds mirror LdbExprKind
+struct AggSpec {
+   int32_t expr;
+   int32_t col[3]; // indices into value columns
+};
+struct GroupByParams {
+   ScanSource src;
+   int32_t nKeys;
+   const int32_t* keyCols[kMaxKeys];
+   int32_t nValueCols;
+   const void* valueCols[kMaxValueCols]; // decimal128 (16 B / value)
+   int32_t nAggs;
+   AggSpec aggs[kMaxAggs];
+   GroupTableDev table;
+};
+
+struct BuildParams {
+   ScanSource src;
+   const int32_t* keyCol;
+   const int32_t* payloadCol; // may be null
+   int32_t nSide;
+   const int32_t* sideCols[kMaxSide];
+   int32_t hasProbe;
+   JoinTableDev probe;
+   const int32_t* probeKeyCol;
+   JoinTableDev sink;
+};
+
+struct ProbeAggParams {
+   ScanSource src;
+   const int32_t* probeKeyCol;
+   JoinTableDev table;
+   AggSpec agg;
+   const void* valueCols[kMaxValueCols];
+};
+
+struct Probe2GroupByParams {
+   ScanSource src;
+   const int32_t* keyColA;
+   const int32_t* keyColB;
+   JoinTableDev tableA, tableB;
+   AggSpec agg;
+   const void* valueCols[kMaxValueCols];
+   GroupTableDev groups; // keyed by the matched payload
+};
+
+struct TopKRowDev {
+   int32_t key, side0, side1, valid;
+   unsigned long long aggLo;
+   long long aggHi;
+};
+
+// signature → instantiation registry for the group-by kernel; returns false when no compiled shape matches
+bool launchScanGroupBy(const GroupByParams& p, int smCount, cudaStream_t s, const char** why);
+void launchScanBuild(const BuildParams& p, int smCount, cudaStream_t s);
+bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, const char** why);
+bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStream_t s, const char** why);
+void launchJoinTopK(const JoinTableDev& t, int k, TopKRowDev* out, int* outBlocks, int smCount, cudaStream_t s);
+void launchFill64(unsigned long long* p, unsigned long long v, int64_t n, cudaStream_t s);
+void launchInsertTuples(const JoinTableDev& t, const int32_t* keys, const int32_t* payloads, const int32_t* side0, const int32_t* side1, int64_t n, int smCount, cudaStream_t s);
+void launchHashI64(const int64_t* a, const int64_t* b, int64_t n, uint64_t* out, cudaStream_t s);
+void launchGroupMergeRows(const GroupTableDev& t, const int32_t* keys, const unsigned long long* acc, int32_t nRows, cudaStream_t s);
+// radix partition (K6): histogram + scatter by the top bits of h64(key)
+void launchPartitionHistogram(const int32_t* keys, int64_t n, int nParts, unsigned long long* counts, int smCount, cudaStream_t s);
+void launchPartitionScatter(const int32_t* keys, const void* const* payloadCols, const int32_t* widths, int nPayload, int64_t n, int nParts, unsigned long long* cursors, int32_t* outKeys, void* const* outPayload, int smCount, cudaStream_t s);
+
+} // namespace ldb

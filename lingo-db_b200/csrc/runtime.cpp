@@ -1,0 +1,845 @@
+// runtime.cpp — C++ host runtime behind the C-ABI (include/ldb_gpu.h): context, HBM staging of
+// Arrow batches, device state objects, descriptor → kernel dispatch.  Host side of the reference's
+// src/runtime surface for the three hot paths; there is NO CPU fallback: without a CUDA device
+// every entry point fails with LDB_ERR_NO_DEVICE.
+#include "context.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+using namespace ldb;
+
+// ------------------------------------------------------------------------------------------------ helpers
+namespace {
+template <class Fn>
+int guarded(LdbError* err, const Fn& fn) {
+   auto set = [&](int code, const char* msg) {
+      if (err) {
+         err->code = code;
+         snprintf(err->message, sizeof(err->message), "%s", msg);
+      }
+      return code;
+   };
+   try {
+      fn();
+      if (err) {
+         err->code = LDB_OK;
+         err->message[0] = 0;
+      }
+      return LDB_OK;
+   } catch (const CudaError& e) {
+      return set(e.code, e.what());
+   } catch (const ApiError& e) {
+      return set(e.code, e.what());
+   } catch (const std::exception& e) {
+      return set(LDB_ERR_INVALID, e.what());
+   }
+}
+[[noreturn]] void fail(int code, const std::string& m) { throw ApiError(code, m); }
+
+uint64_t nextPow2(uint64_t v) {
+   v--;
+   v |= v >> 1;
+   v |= v >> 2;
+   v |= v >> 4;
+   v |= v >> 8;
+   v |= v >> 16;
+   v |= v >> 32;
+   return v + 1;
+}
+size_t elemWidth(int type) {
+   switch (type) {
+      case LDB_INT32:
+      case LDB_DATE32:
+      case LDB_FSB4:
+      case LDB_UTF8: return 4; // utf8: offsets
+      case LDB_INT64: return 8;
+      case LDB_DECIMAL128: return 16;
+   }
+   fail(LDB_ERR_INVALID, "unknown physical type");
+}
+// "YYYY-MM-DD" → days since epoch (constant parsing of Restrictions.cpp:17-25)
+int32_t parseDate32(const char* s) {
+   int y, m, d;
+   if (!s || sscanf(s, "%d-%d-%d", &y, &m, &d) != 3) fail(LDB_ERR_INVALID, "could not parse date");
+   y -= m <= 2;
+   int era = (y >= 0 ? y : y - 399) / 400;
+   unsigned yoe = (unsigned) (y - era * 400);
+   unsigned doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+   unsigned doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+   return era * 146097 + (int) doe - 719468;
+}
+// decimal constant at the column's scale (Restrictions.cpp:455-480)
+int64_t parseDecimal(const char* s, int scale) {
+   if (!s) fail(LDB_ERR_INVALID, "missing decimal constant");
+   bool neg = false;
+   size_t i = 0, n = strlen(s);
+   if (i < n && (s[i] == '-' || s[i] == '+')) neg = s[i++] == '-';
+   __int128 v = 0;
+   int sc = 0;
+   bool dot = false;
+   for (; i < n; i++) {
+      if (s[i] == '.') {
+         dot = true;
+         continue;
+      }
+      if (s[i] < '0' || s[i] > '9') fail(LDB_ERR_INVALID, "could not parse decimal const");
+      v = v * 10 + (s[i] - '0');
+      if (dot) sc++;
+   }
+   for (; sc < scale; sc++) v *= 10;
+   for (; sc > scale; sc--) {
+      if (v % 10) fail(LDB_ERR_INVALID, "decimal rescale would lose data");
+      v /= 10;
+   }
+   if (v > (__int128) INT64_MAX) fail(LDB_ERR_UNSUPPORTED, "decimal constant beyond 64 bits");
+   return (int64_t) (neg ? -v : v);
+}
+uint32_t opMask(int op) {
+   switch (op) {
+      case LDB_EQ: return 2;
+      case LDB_NEQ: return 5;
+      case LDB_LT: return 1;
+      case LDB_LTE: return 3;
+      case LDB_GT: return 4;
+      case LDB_GTE: return 6;
+   }
+   fail(LDB_ERR_UNSUPPORTED, "unsupported filter op"); // same message as Restrictions.cpp:346
+}
+} // namespace
+
+// ------------------------------------------------------------------------------------------------ context
+void* LdbContext::stagingAlloc(size_t bytes) {
+   bytes = std::max<size_t>(256, (bytes + 255) & ~size_t(255));
+   auto it = stagingFree.lower_bound(bytes);
+   if (it != stagingFree.end() && it->first <= bytes + bytes / 4) {
+      void* p = it->second;
+      stagingFree.erase(it);
+      return p;
+   }
+   void* p = nullptr;
+   LDB_CUDA(cudaMalloc(&p, bytes));
+   stagingSize[p] = bytes;
+   return p;
+}
+void LdbContext::stagingRelease(void* p) { stagingFree.insert({stagingSize.at(p), p}); }
+cudaEvent_t LdbContext::getEvent() {
+   cudaEvent_t e;
+   if (!eventPool.empty()) {
+      e = eventPool.back();
+      eventPool.pop_back();
+      return e;
+   }
+   LDB_CUDA(cudaEventCreate(&e));
+   return e;
+}
+
+extern "C" {
+
+int ldb_gpu_context_create(int device, LdbContext** out, LdbError* err) {
+   return guarded(err, [&] {
+      int n = 0;
+      cudaError_t e = cudaGetDeviceCount(&n);
+      if (e != cudaSuccess || n == 0) {
+         cudaGetLastError();
+         fail(LDB_ERR_NO_DEVICE, "no CUDA device available: the GPU operator runtime has no CPU fallback");
+      }
+      if (device < 0 || device >= n) fail(LDB_ERR_INVALID, "device index out of range");
+      LDB_CUDA(cudaSetDevice(device));
+      auto ctx = std::make_unique<LdbContext>();
+      ctx->device = device;
+      LDB_CUDA(cudaGetDeviceProperties(&ctx->prop, device));
+      ctx->smCount = ctx->prop.multiProcessorCount;
+      LDB_CUDA(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
+      LDB_CUDA(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
+      LDB_CUDA(cudaEventCreate(&ctx->timerStart));
+      LDB_CUDA(cudaEventCreate(&ctx->timerStop));
+      LDB_CUDA(cudaEventCreateWithFlags(&ctx->computeDone, cudaEventDisableTiming));
+      *out = ctx.release();
+   });
+}
+void ldb_gpu_table_destroy(LdbTable* t);
+static void destroyState(LdbState* s) { // device memory goes back to the context's pool
+   for (void* p : s->allocations) s->ctx->stagingRelease(p);
+   delete s;
+}
+void ldb_gpu_context_destroy(LdbContext* ctx) {
+   if (!ctx) return;
+   cudaSetDevice(ctx->device);
+   cudaDeviceSynchronize();
+   while (!ctx->tables.empty()) ldb_gpu_table_destroy(ctx->tables.back());
+   for (auto* s : ctx->states) destroyState(s);
+   for (auto& kv : ctx->stagingSize) cudaFree(kv.first);
+   for (auto e : ctx->eventPool) cudaEventDestroy(e);
+   for (auto& kv : ctx->timers)
+      for (auto& pr : kv.second.pending) {
+         cudaEventDestroy(pr.first);
+         cudaEventDestroy(pr.second);
+      }
+   cudaEventDestroy(ctx->timerStart);
+   cudaEventDestroy(ctx->timerStop);
+   cudaEventDestroy(ctx->computeDone);
+   cudaStreamDestroy(ctx->compute);
+   cudaStreamDestroy(ctx->copy);
+   delete ctx;
+}
+int ldb_gpu_device_info(LdbContext* ctx, LdbDeviceInfo* out, LdbError* err) {
+   return guarded(err, [&] {
+      if (!ctx || !out) fail(LDB_ERR_INVALID, "null argument");
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      memset(out, 0, sizeof(*out));
+      out->device = ctx->device;
+      out->sm_count = ctx->smCount;
+      out->cc_major = ctx->prop.major;
+      out->cc_minor = ctx->prop.minor;
+      out->l2_bytes = ctx->prop.l2CacheSize;
+      size_t fr, tot;
+      LDB_CUDA(cudaMemGetInfo(&fr, &tot));
+      out->total_mem = (int64_t) tot;
+      out->free_mem = (int64_t) fr;
+      snprintf(out->name, sizeof(out->name), "%s", ctx->prop.name);
+   });
+}
+int ldb_gpu_synchronize(LdbContext* ctx, LdbError* err) {
+   return guarded(err, [&] {
+      LDB_CUDA(cudaStreamSynchronize(ctx->copy));
+      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+   });
+}
+int64_t ldb_gpu_launch_count(LdbContext* ctx) { return ctx ? ctx->launches : 0; }
+int ldb_gpu_timer_start(LdbContext* ctx, LdbError* err) {
+   return guarded(err, [&] { LDB_CUDA(cudaEventRecord(ctx->timerStart, ctx->compute)); });
+}
+int ldb_gpu_timer_stop(LdbContext* ctx, float* ms, LdbError* err) {
+   return guarded(err, [&] {
+      LDB_CUDA(cudaEventRecord(ctx->timerStop, ctx->compute));
+      LDB_CUDA(cudaEventSynchronize(ctx->timerStop));
+      LDB_CUDA(cudaEventElapsedTime(ms, ctx->timerStart, ctx->timerStop));
+   });
+}
+int ldb_gpu_kernel_time_reset(LdbContext* ctx, int enable, LdbError* err) {
+   return guarded(err, [&] {
+      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+      for (auto& kv : ctx->timers) {
+         for (auto& pr : kv.second.pending) {
+            ctx->eventPool.push_back(pr.first);
+            ctx->eventPool.push_back(pr.second);
+         }
+      }
+      ctx->timers.clear();
+      ctx->timing = enable != 0;
+   });
+}
+int ldb_gpu_kernel_time(LdbContext* ctx, const char* family, float* ms, int64_t* launches, LdbError* err) {
+   return guarded(err, [&] {
+      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+      auto it = ctx->timers.find(family);
+      if (it == ctx->timers.end()) {
+         *ms = 0;
+         *launches = 0;
+         return;
+      }
+      auto& t = it->second;
+      for (auto& pr : t.pending) {
+         float e = 0;
+         LDB_CUDA(cudaEventElapsedTime(&e, pr.first, pr.second));
+         t.totalMs += e;
+         ctx->eventPool.push_back(pr.first);
+         ctx->eventPool.push_back(pr.second);
+      }
+      t.pending.clear();
+      *ms = (float) t.totalMs;
+      *launches = t.launches;
+   });
+}
+
+// ------------------------------------------------------------------------------------------------ tables
+int ldb_gpu_table_create(LdbContext* ctx, const char* name, int32_t n_cols, const LdbColumnSchema* schema, LdbTable** out, LdbError* err) {
+   return guarded(err, [&] {
+      if (!ctx || !schema || !out) fail(LDB_ERR_INVALID, "null argument");
+      auto* t = new LdbTable;
+      t->ctx = ctx;
+      t->name = name ? name : "";
+      for (int i = 0; i < n_cols; i++) {
+         elemWidth(schema[i].type);
+         t->columns.push_back({schema[i].name, schema[i].type, schema[i].precision, schema[i].scale});
+      }
+      ctx->tables.push_back(t);
+      *out = t;
+   });
+}
+int ldb_gpu_table_append_batch(LdbTable* t, int64_t n_rows, const LdbArrayView* columns, const int64_t* utf8_bytes, int32_t location, LdbError* err) {
+   return guarded(err, [&] {
+      if (!t || !columns) fail(LDB_ERR_INVALID, "null argument");
+      LdbContext* ctx = t->ctx;
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      LdbBatch b;
+      b.nRows = n_rows;
+      size_t nc = t->columns.size();
+      b.data.resize(nc);
+      b.bytes.assign(nc, nullptr);
+      for (size_t c = 0; c < nc; c++) {
+         const LdbArrayView& av = columns[c];
+         if (av.null_count != 0) fail(LDB_ERR_UNSUPPORTED, "nullable batches are not supported on the GPU path yet");
+         if (av.length < n_rows) fail(LDB_ERR_INVALID, "column shorter than the batch");
+         size_t w = elemWidth(t->columns[c].type);
+         bool utf8 = t->columns[c].type == LDB_UTF8;
+         const uint8_t* src = (const uint8_t*) av.buffers[1] + (size_t) av.offset * w;
+         size_t bytes = (size_t) (n_rows + (utf8 ? 1 : 0)) * w;
+         if (location == LDB_MEM_DEVICE) {
+            b.data[c] = src;
+            if (utf8) b.bytes[c] = av.buffers[2];
+         } else {
+            void* dst = ctx->stagingAlloc(bytes);
+            b.owned.push_back(dst);
+            LDB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy));
+            b.data[c] = dst;
+            if (utf8) {
+               if (!utf8_bytes) fail(LDB_ERR_INVALID, "utf8 column needs utf8_bytes");
+               size_t sb = std::max<int64_t>(utf8_bytes[c], 1);
+               void* d2 = ctx->stagingAlloc(sb);
+               b.owned.push_back(d2);
+               LDB_CUDA(cudaMemcpyAsync(d2, av.buffers[2], (size_t) utf8_bytes[c], cudaMemcpyHostToDevice, ctx->copy));
+               b.bytes[c] = d2;
+            }
+         }
+      }
+      if (location != LDB_MEM_DEVICE) {
+         b.ready = ctx->getEvent();
+         LDB_CUDA(cudaEventRecord(b.ready, ctx->copy));
+      }
+      t->numRows += n_rows;
+      t->batches.push_back(std::move(b));
+   });
+}
+int ldb_gpu_table_clear(LdbTable* t, LdbError* err) {
+   return guarded(err, [&] {
+      LdbContext* ctx = t->ctx;
+      // staged buffers may still be read by queued kernels: later copies wait for the compute stream
+      LDB_CUDA(cudaEventRecord(ctx->computeDone, ctx->compute));
+      LDB_CUDA(cudaStreamWaitEvent(ctx->copy, ctx->computeDone, 0));
+      for (auto& b : t->batches) {
+         for (void* p : b.owned) ctx->stagingRelease(p);
+         if (b.ready) ctx->eventPool.push_back(b.ready);
+      }
+      t->batches.clear();
+      t->numRows = 0;
+   });
+}
+int64_t ldb_gpu_table_num_rows(const LdbTable* t) { return t ? t->numRows : 0; }
+void ldb_gpu_table_destroy(LdbTable* t) {
+   if (!t) return;
+   LdbContext* ctx = t->ctx;
+   cudaStreamSynchronize(ctx->compute);
+   LdbError e;
+   ldb_gpu_table_clear(t, &e);
+   ctx->tables.erase(std::remove(ctx->tables.begin(), ctx->tables.end(), t), ctx->tables.end());
+   delete t;
+}
+
+// ------------------------------------------------------------------------------------------------ states
+static void* devAlloc(LdbState* s, size_t bytes, int fillByte) {
+   void* p = s->ctx->stagingAlloc(std::max<size_t>(bytes, 16));
+   s->allocations.push_back(p);
+   LDB_CUDA(cudaMemsetAsync(p, fillByte, std::max<size_t>(bytes, 16), s->ctx->compute));
+   return p;
+}
+static LdbState* newGroupState(LdbContext* ctx, int kind, int nKeys, int nAggs, int capacity) {
+   if (nAggs < 1 || nAggs > kMaxAggs) fail(LDB_ERR_INVALID, "n_aggs out of range");
+   if (nKeys < 0 || nKeys > kMaxKeys) fail(LDB_ERR_INVALID, "n_keys out of range");
+   LDB_CUDA(cudaSetDevice(ctx->device));
+   auto* s = new LdbState;
+   s->ctx = ctx;
+   s->kind = kind;
+   ctx->states.push_back(s);
+   auto& g = s->group;
+   g.capacity = nKeys == 0 ? 1 : (int) nextPow2((uint64_t) std::max(capacity, 16));
+   g.nKeys = nKeys;
+   g.nAggs = nAggs;
+   g.state = (int32_t*) devAlloc(s, sizeof(int32_t) * g.capacity, 0);
+   g.keys = (int32_t*) devAlloc(s, sizeof(int32_t) * kMaxKeys * g.capacity, 0);
+   g.acc = (unsigned long long*) devAlloc(s, sizeof(unsigned long long) * 2 * kMaxAggs * g.capacity, 0);
+   g.error = (int32_t*) devAlloc(s, sizeof(int32_t), 0);
+   s->nAggs = nAggs;
+   return s;
+}
+void ldb_gpu_state_destroy(LdbState* s) {
+   if (!s) return;
+   LdbContext* ctx = s->ctx;
+   cudaSetDevice(ctx->device);
+   cudaStreamSynchronize(ctx->compute);
+   ctx->states.erase(std::remove(ctx->states.begin(), ctx->states.end(), s), ctx->states.end());
+   destroyState(s);
+}
+int ldb_gpu_simple_state_create(LdbContext* ctx, int32_t n_aggs, LdbState** out, LdbError* err) {
+   return guarded(err, [&] { *out = newGroupState(ctx, LDB_STATE_SIMPLE, 0, n_aggs, 1); });
+}
+int ldb_gpu_groupby_create(LdbContext* ctx, int32_t n_keys, int32_t n_aggs, int32_t capacity, LdbState** out, LdbError* err) {
+   return guarded(err, [&] {
+      if (n_keys < 1) fail(LDB_ERR_INVALID, "group-by needs at least one key (use a simple state)");
+      *out = newGroupState(ctx, LDB_STATE_GROUPBY, n_keys, n_aggs, capacity);
+   });
+}
+static void checkGroupError(LdbState* s) {
+   int32_t e = 0;
+   LDB_CUDA(cudaMemcpyAsync(&e, s->group.error, sizeof(e), cudaMemcpyDeviceToHost, s->ctx->compute));
+   LDB_CUDA(cudaStreamSynchronize(s->ctx->compute));
+   if (e) fail(LDB_ERR_CAPACITY, "group-by table overflow: more groups than the declared capacity");
+}
+int ldb_gpu_simple_state_read(LdbState* s, LdbI128* aggs, LdbError* err) {
+   return guarded(err, [&] {
+      if (!s || s->kind != LDB_STATE_SIMPLE) fail(LDB_ERR_INVALID, "not a simple state");
+      unsigned long long h[kMaxAggs * 2];
+      LDB_CUDA(cudaMemcpyAsync(h, s->group.acc, sizeof(h), cudaMemcpyDeviceToHost, s->ctx->compute));
+      LDB_CUDA(cudaStreamSynchronize(s->ctx->compute));
+      for (int a = 0; a < s->nAggs; a++) aggs[a] = LdbI128{h[2 * a], (int64_t) h[2 * a + 1]};
+   });
+}
+int ldb_gpu_groupby_read(LdbState* s, LdbGroupRow* rows, int32_t max_rows, int32_t* n_rows, LdbError* err) {
+   return guarded(err, [&] {
+      if (!s || s->kind != LDB_STATE_GROUPBY) fail(LDB_ERR_INVALID, "not a group-by state");
+      checkGroupError(s);
+      auto& g = s->group;
+      std::vector<int32_t> st(g.capacity), keys((size_t) g.capacity * kMaxKeys);
+      std::vector<unsigned long long> acc((size_t) g.capacity * kMaxAggs * 2);
+      LDB_CUDA(cudaMemcpyAsync(st.data(), g.state, st.size() * 4, cudaMemcpyDeviceToHost, s->ctx->compute));
+      LDB_CUDA(cudaMemcpyAsync(keys.data(), g.keys, keys.size() * 4, cudaMemcpyDeviceToHost, s->ctx->compute));
+      LDB_CUDA(cudaMemcpyAsync(acc.data(), g.acc, acc.size() * 8, cudaMemcpyDeviceToHost, s->ctx->compute));
+      LDB_CUDA(cudaStreamSynchronize(s->ctx->compute));
+      int n = 0;
+      for (int i = 0; i < g.capacity; i++) {
+         if (st[i] != 2) continue;
+         if (n < max_rows) {
+            LdbGroupRow& r = rows[n];
+            memset(&r, 0, sizeof(r));
+            for (int k = 0; k < kMaxKeys; k++) r.keys[k] = keys[(size_t) i * kMaxKeys + k];
+            for (int a = 0; a < g.nAggs; a++) r.aggs[a] = LdbI128{acc[((size_t) i * kMaxAggs + a) * 2], (int64_t) acc[((size_t) i * kMaxAggs + a) * 2 + 1]};
+         }
+         n++;
+      }
+      *n_rows = n;
+   });
+}
+int ldb_gpu_groupby_merge_rows(LdbState* s, const LdbGroupRow* rows, int32_t n_rows, LdbError* err) {
+   return guarded(err, [&] {
+      if (!s || (s->kind != LDB_STATE_GROUPBY && s->kind != LDB_STATE_SIMPLE)) fail(LDB_ERR_INVALID, "not a group state");
+      if (n_rows <= 0) return;
+      LdbContext* ctx = s->ctx;
+      std::vector<int32_t> keys((size_t) n_rows * kMaxKeys);
+      std::vector<unsigned long long> acc((size_t) n_rows * kMaxAggs * 2, 0);
+      for (int r = 0; r < n_rows; r++) {
+         for (int k = 0; k < kMaxKeys; k++) keys[(size_t) r * kMaxKeys + k] = rows[r].keys[k];
+         for (int a = 0; a < s->group.nAggs; a++) {
+            acc[((size_t) r * kMaxAggs + a) * 2] = rows[r].aggs[a].lo;
+            acc[((size_t) r * kMaxAggs + a) * 2 + 1] = (unsigned long long) rows[r].aggs[a].hi;
+         }
+      }
+      void* dk = ctx->stagingAlloc(keys.size() * 4);
+      void* da = ctx->stagingAlloc(acc.size() * 8);
+      LDB_CUDA(cudaMemcpyAsync(dk, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice, ctx->compute));
+      LDB_CUDA(cudaMemcpyAsync(da, acc.data(), acc.size() * 8, cudaMemcpyHostToDevice, ctx->compute));
+      ctx->launch("group_merge", [&] { launchGroupMergeRows(s->group, (const int32_t*) dk, (const unsigned long long*) da, n_rows, ctx->compute); });
+      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+      ctx->stagingRelease(dk);
+      ctx->stagingRelease(da);
+   });
+}
+
+int ldb_gpu_join_table_create(LdbContext* ctx, int64_t expected_rows, int32_t unique_keys, int32_t n_side, int32_t n_aggs, LdbState** out, LdbError* err) {
+   return guarded(err, [&] {
+      if (!ctx || !out) fail(LDB_ERR_INVALID, "null argument");
+      if (n_side < 0 || n_side > kMaxSide || n_aggs < 0 || n_aggs > 1) fail(LDB_ERR_INVALID, "n_side/n_aggs out of range");
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      auto* s = new LdbState;
+      s->ctx = ctx;
+      s->kind = LDB_STATE_JOIN_TABLE;
+      ctx->states.push_back(s);
+      // HashIndexedView::build sizes its directory nextPow2(1.25 n) for chained buckets
+      // (LazyJoinHashtable.cpp:16); linear probing wants load factor <= 0.5
+      uint64_t cap = nextPow2((uint64_t) std::max<int64_t>(expected_rows, 8) * 2);
+      auto& j = s->join;
+      j.mask = cap - 1;
+      j.unique = unique_keys;
+      j.slots = (unsigned long long*) devAlloc(s, cap * 8, 0xff);
+      for (int k = 0; k < n_side; k++) j.side[k] = (int32_t*) devAlloc(s, cap * 4, 0);
+      if (n_aggs) {
+         j.aggLo = (unsigned long long*) devAlloc(s, cap * 8, 0);
+         j.aggHi = (unsigned long long*) devAlloc(s, cap * 8, 0);
+         j.marker = (uint8_t*) devAlloc(s, cap, 0);
+      }
+      j.count = (unsigned long long*) devAlloc(s, 8, 0);
+      j.error = (int32_t*) devAlloc(s, 4, 0);
+      s->nSide = n_side;
+      s->nAggs = n_aggs;
+      *out = s;
+   });
+}
+static void checkJoinError(LdbState* s) {
+   int32_t e = 0;
+   LDB_CUDA(cudaMemcpyAsync(&e, s->join.error, sizeof(e), cudaMemcpyDeviceToHost, s->ctx->compute));
+   LDB_CUDA(cudaStreamSynchronize(s->ctx->compute));
+   if (e == 1) fail(LDB_ERR_CAPACITY, "join table full: more build rows than expected_rows allowed");
+   if (e == 2) fail(LDB_ERR_INVALID, "duplicate key inserted into a join table declared unique");
+   if (e == 3) fail(LDB_ERR_UNSUPPORTED, "the pair (key=-1, payload=-1) cannot be stored in a join table");
+}
+int ldb_gpu_join_table_count(LdbState* s, int64_t* n_entries, LdbError* err) {
+   return guarded(err, [&] {
+      if (!s || s->kind != LDB_STATE_JOIN_TABLE) fail(LDB_ERR_INVALID, "not a join table");
+      checkJoinError(s);
+      unsigned long long c = 0;
+      LDB_CUDA(cudaMemcpyAsync(&c, s->join.count, 8, cudaMemcpyDeviceToHost, s->ctx->compute));
+      LDB_CUDA(cudaStreamSynchronize(s->ctx->compute));
+      *n_entries = (int64_t) c;
+   });
+}
+int ldb_gpu_join_table_topk(LdbState* s, int32_t k, LdbTopKRow* rows, int32_t* n_rows, LdbError* err) {
+   return guarded(err, [&] {
+      if (!s || s->kind != LDB_STATE_JOIN_TABLE || !s->nAggs) fail(LDB_ERR_INVALID, "not a group-join table");
+      if (k < 1 || k > 64) fail(LDB_ERR_INVALID, "k must be in [1, 64]");
+      checkJoinError(s);
+      LdbContext* ctx = s->ctx;
+      int blocks = ctx->smCount * 2;
+      size_t bytes = sizeof(TopKRowDev) * (size_t) blocks * k;
+      void* d = ctx->stagingAlloc(bytes);
+      ctx->launch("join_topk", [&] { launchJoinTopK(s->join, k, (TopKRowDev*) d, &blocks, ctx->smCount, ctx->compute); });
+      std::vector<TopKRowDev> h((size_t) blocks * k);
+      LDB_CUDA(cudaMemcpyAsync(h.data(), d, bytes, cudaMemcpyDeviceToHost, ctx->compute));
+      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+      ctx->stagingRelease(d);
+      std::vector<TopKRowDev> valid;
+      for (auto& r : h)
+         if (r.valid) valid.push_back(r);
+      std::sort(valid.begin(), valid.end(), [](const TopKRowDev& a, const TopKRowDev& b) {
+         if (a.aggHi != b.aggHi) return a.aggHi > b.aggHi;
+         if (a.aggLo != b.aggLo) return a.aggLo > b.aggLo;
+         if (a.side0 != b.side0) return a.side0 < b.side0;
+         return a.key < b.key;
+      });
+      int n = (int) std::min<size_t>(valid.size(), (size_t) k);
+      for (int i = 0; i < n; i++) {
+         rows[i].key = valid[i].key;
+         rows[i].side[0] = valid[i].side0;
+         rows[i].side[1] = valid[i].side1;
+         rows[i].pad = 0;
+         rows[i].agg = LdbI128{valid[i].aggLo, valid[i].aggHi};
+      }
+      *n_rows = n;
+   });
+}
+
+// ------------------------------------------------------------------------------------------------ pipelines
+namespace {
+struct Resolved {
+   LdbTable* t;
+   int col(const char* name, std::initializer_list<int> types, const char* role) const {
+      int i = t->colIndex(name);
+      if (i < 0) fail(LDB_ERR_INVALID, std::string("unknown column ") + (name ? name : "(null)") + " for " + role);
+      bool ok = false;
+      for (int ty : types) ok |= t->columns[i].type == ty;
+      if (!ok) fail(LDB_ERR_UNSUPPORTED, std::string("column ") + name + " has an unsupported physical type for " + role);
+      return i;
+   }
+};
+// FilterDescription list → per-column predicate pairs (Restrictions::create, Restrictions.cpp:392-520)
+struct FilterPlan {
+   FilterSet set{};
+   int colIdx[kMaxFilterCols];
+};
+FilterPlan planFilters(LdbTable* t, const LdbFilterDesc* f, int n) {
+   FilterPlan p;
+   p.set.n = 0;
+   for (int i = 0; i < n; i++) {
+      int c = t->colIndex(f[i].column);
+      if (c < 0) fail(LDB_ERR_INVALID, "unknown column in filter"); // Restrictions.cpp:396
+      auto& col = t->columns[c];
+      int64_t value = 0;
+      int kind = COL_I32;
+      uint32_t mask = opMask(f[i].op);
+      const char* str = nullptr;
+      switch (col.type) {
+         case LDB_INT32:
+            if (!f[i].value_is_int) fail(LDB_ERR_INVALID, "integer column needs an integer constant");
+            value = f[i].int_value;
+            break;
+         case LDB_DATE32: value = parseDate32(f[i].str_value); break;
+         case LDB_FSB4: {
+            if (!f[i].str_value || strlen(f[i].str_value) > 4) fail(LDB_ERR_INVALID, "char(1) constant too long");
+            int32_t v = 0;
+            memcpy(&v, f[i].str_value, strlen(f[i].str_value));
+            value = v;
+            break;
+         }
+         case LDB_DECIMAL128:
+            if (col.precision >= 19) fail(LDB_ERR_UNSUPPORTED, "decimal precision >= 19 is not supported on the GPU path yet");
+            kind = COL_DEC128_LO64;
+            if (f[i].value_is_int) {
+               value = f[i].int_value;
+               for (int s = 0; s < col.scale; s++) value *= 10;
+            } else {
+               value = parseDecimal(f[i].str_value, col.scale);
+            }
+            break;
+         case LDB_UTF8:
+            if (f[i].op != LDB_EQ && f[i].op != LDB_NEQ) fail(LDB_ERR_UNSUPPORTED, "unsupported filter op for string");
+            if (!f[i].str_value || strlen(f[i].str_value) > sizeof(FilterCol::str)) fail(LDB_ERR_UNSUPPORTED, "string constant longer than 24 bytes");
+            kind = COL_UTF8_EQ;
+            value = 1;
+            str = f[i].str_value;
+            break;
+         default: fail(LDB_ERR_UNSUPPORTED, "unsupported type in filter");
+      }
+      int slot = -1;
+      if (kind != COL_UTF8_EQ)
+         for (int k = 0; k < p.set.n; k++)
+            if (p.colIdx[k] == c && p.set.c[k].maskB == 7) slot = k;
+      if (slot >= 0) {
+         p.set.c[slot].maskB = mask;
+         p.set.c[slot].valB = value;
+         continue;
+      }
+      if (p.set.n == kMaxFilterCols) fail(LDB_ERR_UNSUPPORTED, "more than 4 filter columns in one pipeline");
+      FilterCol& fc = p.set.c[p.set.n];
+      memset(&fc, 0, sizeof(fc));
+      fc.kind = kind;
+      fc.maskA = mask;
+      fc.valA = value;
+      fc.maskB = 7;
+      fc.valB = 0;
+      if (str) {
+         fc.strLen = (int32_t) strlen(str);
+         memcpy(fc.str, str, fc.strLen);
+      }
+      p.colIdx[p.set.n++] = c;
+   }
+   return p;
+}
+void bindFilters(const FilterPlan& p, const LdbBatch& b, FilterSet& out) {
+   out = p.set;
+   for (int i = 0; i < out.n; i++) {
+      out.c[i].base = b.data[p.colIdx[i]];
+      out.c[i].bytes = (const uint8_t*) b.bytes[p.colIdx[i]];
+   }
+}
+// value columns of aggregate expressions, de-duplicated in first-appearance order
+struct AggPlan {
+   int nValueCols = 0;
+   int valueCol[kMaxValueCols];
+   int nAggs = 0;
+   AggSpec aggs[kMaxAggs];
+};
+AggPlan planAggs(const Resolved& R, const LdbAggDesc* a, int n) {
+   AggPlan p;
+   if (n < 1 || n > kMaxAggs) fail(LDB_ERR_INVALID, "n_aggs out of range");
+   for (int i = 0; i < n; i++) {
+      int used = a[i].expr == LDB_EXPR_COL ? 1 : (a[i].expr == LDB_EXPR_MUL || a[i].expr == LDB_EXPR_MUL_1MINUS) ? 2 : a[i].expr == LDB_EXPR_MUL_1MINUS_1PLUS ? 3 : a[i].expr == LDB_EXPR_ONE ? 0 : -1;
+      if (used < 0) fail(LDB_ERR_UNSUPPORTED, "unknown aggregate expression kind");
+      p.aggs[i].expr = a[i].expr;
+      for (int k = 0; k < 3; k++) p.aggs[i].col[k] = 0;
+      for (int k = 0; k < used; k++) {
+         int c = R.col(a[i].columns[k], {LDB_DECIMAL128}, "aggregate operand");
+         auto& col = R.t->columns[c];
+         if (col.precision >= 19 || col.scale != 2) fail(LDB_ERR_UNSUPPORTED, "aggregate operands must be decimal(p<19, 2) on the GPU path");
+         int idx = -1;
+         for (int v = 0; v < p.nValueCols; v++)
+            if (p.valueCol[v] == c) idx = v;
+         if (idx < 0) {
+            if (p.nValueCols == kMaxValueCols) fail(LDB_ERR_UNSUPPORTED, "more than 4 distinct aggregate operand columns");
+            idx = p.nValueCols;
+            p.valueCol[p.nValueCols++] = c;
+         }
+         p.aggs[i].col[k] = idx;
+      }
+   }
+   p.nAggs = n;
+   return p;
+}
+void waitBatch(LdbContext* ctx, const LdbBatch& b) {
+   if (b.ready) LDB_CUDA(cudaStreamWaitEvent(ctx->compute, b.ready, 0));
+}
+LdbState* wantState(LdbState* s, int kind, const char* role) {
+   if (!s || s->kind != kind) fail(LDB_ERR_INVALID, std::string("wrong or missing state for ") + role);
+   return s;
+}
+} // namespace
+
+int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* err) {
+   return guarded(err, [&] {
+      if (!ctx || !d || !d->source) fail(LDB_ERR_INVALID, "null argument");
+      LdbTable* t = d->source;
+      if (t->ctx != ctx) fail(LDB_ERR_INVALID, "table belongs to another context");
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      Resolved R{t};
+      FilterPlan fp = planFilters(t, d->filters, d->n_filters);
+      const char* why = "";
+      switch (d->kind) {
+         case LDB_PIPE_SCAN_REDUCE:
+         case LDB_PIPE_SCAN_GROUPBY: {
+            bool keyless = d->kind == LDB_PIPE_SCAN_REDUCE;
+            LdbState* sink = wantState(d->sink, keyless ? LDB_STATE_SIMPLE : LDB_STATE_GROUPBY, "sink");
+            AggPlan ap = planAggs(R, d->aggs, d->n_aggs);
+            if (ap.nAggs != sink->group.nAggs) fail(LDB_ERR_INVALID, "aggregate count differs from the state's");
+            int nKeys = keyless ? 0 : d->n_keys;
+            if (nKeys != sink->group.nKeys) fail(LDB_ERR_INVALID, "key count differs from the state's");
+            int keyCol[kMaxKeys] = {0, 0};
+            for (int k = 0; k < nKeys; k++) keyCol[k] = R.col(d->key_columns[k], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "group key");
+            for (auto& b : t->batches) {
+               if (b.nRows == 0) continue;
+               GroupByParams p{};
+               p.src.nRows = b.nRows;
+               bindFilters(fp, b, p.src.filters);
+               p.nKeys = nKeys;
+               for (int k = 0; k < nKeys; k++) p.keyCols[k] = (const int32_t*) b.data[keyCol[k]];
+               p.nValueCols = ap.nValueCols;
+               for (int v = 0; v < ap.nValueCols; v++) p.valueCols[v] = b.data[ap.valueCol[v]];
+               p.nAggs = ap.nAggs;
+               for (int a = 0; a < ap.nAggs; a++) p.aggs[a] = ap.aggs[a];
+               p.table = sink->group;
+               waitBatch(ctx, b);
+               bool ok = true;
+               ctx->launch(keyless ? "scan_reduce" : "scan_groupby", [&] { ok = launchScanGroupBy(p, ctx->smCount, ctx->compute, &why); });
+               if (!ok) fail(LDB_ERR_UNSUPPORTED, why);
+            }
+            break;
+         }
+         case LDB_PIPE_SCAN_BUILD: {
+            LdbState* sink = wantState(d->sink, LDB_STATE_JOIN_TABLE, "sink");
+            if (d->n_probes < 0 || d->n_probes > 1) fail(LDB_ERR_UNSUPPORTED, "build pipelines take at most one probe");
+            if (d->n_side != sink->nSide) fail(LDB_ERR_INVALID, "side column count differs from the table's");
+            int keyCol = R.col(d->build_key_column, {LDB_INT32, LDB_DATE32, LDB_FSB4}, "build key");
+            int payCol = d->build_payload_column ? R.col(d->build_payload_column, {LDB_INT32, LDB_DATE32, LDB_FSB4}, "build payload") : -1;
+            int sideCol[kMaxSide] = {0, 0};
+            for (int k = 0; k < d->n_side; k++) sideCol[k] = R.col(d->side_columns[k], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "side payload");
+            LdbState* probe = d->n_probes ? wantState(d->probe_states[0], LDB_STATE_JOIN_TABLE, "probe") : nullptr;
+            int probeCol = d->n_probes ? R.col(d->probe_key_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key") : -1;
+            for (auto& b : t->batches) {
+               if (b.nRows == 0) continue;
+               BuildParams p{};
+               p.src.nRows = b.nRows;
+               bindFilters(fp, b, p.src.filters);
+               p.keyCol = (const int32_t*) b.data[keyCol];
+               p.payloadCol = payCol >= 0 ? (const int32_t*) b.data[payCol] : nullptr;
+               p.nSide = d->n_side;
+               for (int k = 0; k < d->n_side; k++) p.sideCols[k] = (const int32_t*) b.data[sideCol[k]];
+               p.hasProbe = probe ? 1 : 0;
+               if (probe) {
+                  p.probe = probe->join;
+                  p.probeKeyCol = (const int32_t*) b.data[probeCol];
+               }
+               p.sink = sink->join;
+               waitBatch(ctx, b);
+               ctx->launch("join_build", [&] { launchScanBuild(p, ctx->smCount, ctx->compute); });
+            }
+            break;
+         }
+         case LDB_PIPE_SCAN_PROBE_AGG: {
+            LdbState* table = wantState(d->sink, LDB_STATE_JOIN_TABLE, "group-join map");
+            if (!table->nAggs) fail(LDB_ERR_INVALID, "join table was created without aggregate lanes");
+            if (d->n_probes != 1 || d->probe_states[0] != table) fail(LDB_ERR_INVALID, "probe-aggregate pipelines probe their own sink");
+            AggPlan ap = planAggs(R, d->aggs, 1);
+            int probeCol = R.col(d->probe_key_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key");
+            for (auto& b : t->batches) {
+               if (b.nRows == 0) continue;
+               ProbeAggParams p{};
+               p.src.nRows = b.nRows;
+               bindFilters(fp, b, p.src.filters);
+               p.probeKeyCol = (const int32_t*) b.data[probeCol];
+               p.table = table->join;
+               p.agg = ap.aggs[0];
+               for (int v = 0; v < ap.nValueCols; v++) p.valueCols[v] = b.data[ap.valueCol[v]];
+               waitBatch(ctx, b);
+               bool ok = true;
+               ctx->launch("join_probe_agg", [&] { ok = launchScanProbeAgg(p, ctx->smCount, ctx->compute, &why); });
+               if (!ok) fail(LDB_ERR_UNSUPPORTED, why);
+            }
+            break;
+         }
+         case LDB_PIPE_SCAN_PROBE2_GROUPBY: {
+            LdbState* sink = wantState(d->sink, LDB_STATE_GROUPBY, "sink");
+            if (sink->group.nKeys != 1 || sink->group.nAggs != 1) fail(LDB_ERR_INVALID, "probe-probe-group sink must have one key and one aggregate");
+            if (d->n_probes != 2) fail(LDB_ERR_INVALID, "probe-probe-group pipelines take two probes");
+            LdbState* ta = wantState(d->probe_states[0], LDB_STATE_JOIN_TABLE, "probe A");
+            LdbState* tb = wantState(d->probe_states[1], LDB_STATE_JOIN_TABLE, "probe B");
+            AggPlan ap = planAggs(R, d->aggs, 1);
+            int ca = R.col(d->probe_key_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key A");
+            int cb = R.col(d->probe_key_columns[1], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key B");
+            for (auto& b : t->batches) {
+               if (b.nRows == 0) continue;
+               Probe2GroupByParams p{};
+               p.src.nRows = b.nRows;
+               bindFilters(fp, b, p.src.filters);
+               p.keyColA = (const int32_t*) b.data[ca];
+               p.keyColB = (const int32_t*) b.data[cb];
+               p.tableA = ta->join;
+               p.tableB = tb->join;
+               p.agg = ap.aggs[0];
+               for (int v = 0; v < ap.nValueCols; v++) p.valueCols[v] = b.data[ap.valueCol[v]];
+               p.groups = sink->group;
+               waitBatch(ctx, b);
+               bool ok = true;
+               ctx->launch("join_probe2_groupby", [&] { ok = launchScanProbe2GroupBy(p, ctx->smCount, ctx->compute, &why); });
+               if (!ok) fail(LDB_ERR_UNSUPPORTED, why);
+            }
+            break;
+         }
+         default: fail(LDB_ERR_UNSUPPORTED, "unknown pipeline kind");
+      }
+   });
+}
+
+// ------------------------------------------------------------------------------------------------ repartition / misc
+int ldb_gpu_partition_tuples(LdbContext* ctx, const int32_t* keys, const void* const* payload_cols, const int32_t* payload_widths, int32_t n_payload_cols, int64_t n_rows, int32_t n_parts,
+                             int32_t* out_keys, void* const* out_payload_cols, int64_t* out_part_offsets, LdbError* err) {
+   return guarded(err, [&] {
+      if (n_parts < 1 || n_parts > 64) fail(LDB_ERR_INVALID, "n_parts must be in [1, 64]");
+      if (n_payload_cols < 0 || n_payload_cols > 4) fail(LDB_ERR_INVALID, "at most 4 payload columns");
+      for (int c = 0; c < n_payload_cols; c++)
+         if (payload_widths[c] != 4 && payload_widths[c] != 8 && payload_widths[c] != 16) fail(LDB_ERR_INVALID, "payload width must be 4, 8 or 16");
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      unsigned long long* counts = (unsigned long long*) ctx->stagingAlloc(64 * 8);
+      LDB_CUDA(cudaMemsetAsync(counts, 0, 64 * 8, ctx->compute));
+      if (n_rows > 0) ctx->launch("partition", [&] { launchPartitionHistogram(keys, n_rows, n_parts, counts, ctx->smCount, ctx->compute); });
+      unsigned long long h[64];
+      LDB_CUDA(cudaMemcpyAsync(h, counts, 64 * 8, cudaMemcpyDeviceToHost, ctx->compute));
+      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+      unsigned long long cursor[64];
+      int64_t off = 0;
+      for (int p = 0; p < n_parts; p++) {
+         out_part_offsets[p] = off;
+         cursor[p] = (unsigned long long) off;
+         off += (int64_t) h[p];
+      }
+      out_part_offsets[n_parts] = off;
+      LDB_CUDA(cudaMemcpyAsync(counts, cursor, 64 * 8, cudaMemcpyHostToDevice, ctx->compute));
+      if (n_rows > 0) ctx->launch("partition", [&] { launchPartitionScatter(keys, payload_cols, payload_widths, n_payload_cols, n_rows, n_parts, counts, out_keys, out_payload_cols, ctx->smCount, ctx->compute); });
+      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+      ctx->stagingRelease(counts);
+   });
+}
+int ldb_gpu_join_table_insert(LdbContext* ctx, LdbState* table, const int32_t* keys, const int32_t* payloads, const int32_t* const* side_cols, int64_t n_rows, LdbError* err) {
+   return guarded(err, [&] {
+      wantState(table, LDB_STATE_JOIN_TABLE, "insert target");
+      if (n_rows <= 0) return;
+      const int32_t* s0 = table->nSide > 0 && side_cols ? side_cols[0] : nullptr;
+      const int32_t* s1 = table->nSide > 1 && side_cols ? side_cols[1] : nullptr;
+      ctx->launch("join_build", [&] { launchInsertTuples(table->join, keys, payloads, s0, s1, n_rows, ctx->smCount, ctx->compute); });
+   });
+}
+int ldb_gpu_hash_i64(LdbContext* ctx, const int64_t* a, const int64_t* b, int64_t n, uint64_t* out, LdbError* err) {
+   return guarded(err, [&] {
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      void* da = ctx->stagingAlloc(n * 8);
+      void* db = b ? ctx->stagingAlloc(n * 8) : nullptr;
+      void* dout = ctx->stagingAlloc(n * 8);
+      LDB_CUDA(cudaMemcpyAsync(da, a, n * 8, cudaMemcpyHostToDevice, ctx->compute));
+      if (b) LDB_CUDA(cudaMemcpyAsync(db, b, n * 8, cudaMemcpyHostToDevice, ctx->compute));
+      ctx->launch("hash", [&] { launchHashI64((const int64_t*) da, (const int64_t*) db, n, (uint64_t*) dout, ctx->compute); });
+      LDB_CUDA(cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, ctx->compute));
+      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+      ctx->stagingRelease(da);
+      if (db) ctx->stagingRelease(db);
+      ctx->stagingRelease(dout);
+   });
+}
+
+} // extern "C"

@@ -1,0 +1,335 @@
+// tpch_plans.cpp — query drivers (include/ldb_tpch.h): the pipeline sequence of the reference's
+// JIT'd main() for TPC-H Q1/Q3/Q5/Q6, expressed as ldb_gpu_run_pipeline descriptors.  Host C++,
+// like src/execution; every data-parallel step runs in a CUDA kernel, the tiny result projections
+// (avg division, ORDER BY over <= 25 rows) stay on the host like the reference's result side
+// ("BOUNDARY (tiny outputs; keep on host)").
+#include "../../include/ldb_tpch.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace {
+struct PlanError : std::runtime_error {
+   LdbError e;
+   explicit PlanError(const LdbError& e) : std::runtime_error(e.message), e(e) {}
+};
+inline void check(int rc, const LdbError& e) {
+   if (rc != LDB_OK) throw PlanError(e);
+}
+template <class Fn>
+int guarded(LdbError* err, const Fn& fn) {
+   try {
+      fn();
+      if (err) {
+         err->code = LDB_OK;
+         err->message[0] = 0;
+      }
+      return LDB_OK;
+   } catch (const PlanError& p) {
+      if (err) *err = p.e;
+      return p.e.code;
+   } catch (const std::exception& ex) {
+      if (err) {
+         err->code = LDB_ERR_INVALID;
+         snprintf(err->message, sizeof(err->message), "%s", ex.what());
+      }
+      return LDB_ERR_INVALID;
+   }
+}
+LdbFilterDesc strFilter(const char* col, int op, const char* v) { return LdbFilterDesc{col, op, 0, v, 0}; }
+LdbFilterDesc intFilter(const char* col, int op, int64_t v) { return LdbFilterDesc{col, op, 1, nullptr, v}; }
+LdbAggDesc agg(int expr, const char* a = nullptr, const char* b = nullptr, const char* c = nullptr) { return LdbAggDesc{expr, {a, b, c}}; }
+
+struct StateGuard { // the query's ExecutionContext: frees every state it registered
+   std::vector<LdbState*> states;
+   ~StateGuard() {
+      for (auto* s : states) ldb_gpu_state_destroy(s);
+   }
+   LdbState* own(LdbState* s) {
+      states.push_back(s);
+      return s;
+   }
+};
+using i128 = __int128;
+i128 toI128(const LdbI128& v) { return (i128) (((unsigned __int128) (uint64_t) v.hi << 64) | v.lo); }
+LdbI128 fromI128(i128 v) { return LdbI128{(uint64_t) v, (int64_t) ((unsigned __int128) v >> 64)}; }
+// avg(x decimal(12,2)) = (sum * 10^19) sdiv count  → decimal(31,21)
+// (SimplifyAggregations.cpp:160-181; DecimalDiv lowering LowerToStd.cpp:651-700)
+LdbI128 avgDec(int64_t sum, int64_t count) {
+   i128 p = 1;
+   for (int i = 0; i < 19; i++) p *= 10;
+   return fromI128((i128) ((unsigned __int128) (i128) sum * (unsigned __int128) p) / (i128) count);
+}
+
+// Build a join table with the pipeline `d`, growing it if the cardinality estimate was too low
+// (the reference sizes after materialisation, LazyJoinHashtable.cpp:16; a GPU build must pre-size).
+LdbState* buildJoin(LdbContext* ctx, StateGuard& g, LdbPipelineDesc d, int64_t estimate, int unique, int nSide, int nAggs) {
+   LdbError e;
+   for (int attempt = 0; attempt < 6; attempt++) {
+      LdbState* s = nullptr;
+      check(ldb_gpu_join_table_create(ctx, estimate, unique, nSide, nAggs, &s, &e), e);
+      d.sink = s;
+      int rc = ldb_gpu_run_pipeline(ctx, &d, &e);
+      int64_t n = 0;
+      if (rc == LDB_OK) rc = ldb_gpu_join_table_count(s, &n, &e);
+      if (rc == LDB_OK) return g.own(s);
+      ldb_gpu_state_destroy(s);
+      if (rc != LDB_ERR_CAPACITY) throw PlanError(e);
+      estimate *= 4;
+   }
+   throw PlanError(e);
+}
+} // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------------ Q6
+int ldb_tpch_q6_partial(LdbContext* ctx, const LdbTpchTables* t, const char* dateGe, const char* dateLt, const char* discGe, const char* discLe, int64_t qtyLt, LdbState** state, LdbError* err) {
+   return guarded(err, [&] {
+      LdbError e;
+      LdbState* s = nullptr;
+      check(ldb_gpu_simple_state_create(ctx, 1, &s, &e), e);
+      LdbFilterDesc f[5] = {strFilter("l_shipdate", LDB_GTE, dateGe), strFilter("l_shipdate", LDB_LT, dateLt), strFilter("l_discount", LDB_GTE, discGe),
+                            strFilter("l_discount", LDB_LTE, discLe), intFilter("l_quantity", LDB_LT, qtyLt)};
+      LdbPipelineDesc d{};
+      d.kind = LDB_PIPE_SCAN_REDUCE;
+      d.source = t->lineitem;
+      d.n_filters = 5;
+      d.filters = f;
+      d.n_aggs = 1;
+      d.aggs[0] = agg(LDB_EXPR_MUL, "l_extendedprice", "l_discount");
+      d.sink = s;
+      int rc = ldb_gpu_run_pipeline(ctx, &d, &e);
+      if (rc != LDB_OK) {
+         ldb_gpu_state_destroy(s);
+         throw PlanError(e);
+      }
+      *state = s;
+   });
+}
+int ldb_tpch_q6(LdbContext* ctx, const LdbTpchTables* t, const char* dateGe, const char* dateLt, const char* discGe, const char* discLe, int64_t qtyLt, LdbI128* revenue, LdbError* err) {
+   return guarded(err, [&] {
+      LdbError e;
+      StateGuard g;
+      LdbState* s = nullptr;
+      check(ldb_tpch_q6_partial(ctx, t, dateGe, dateLt, discGe, discLe, qtyLt, &s, &e), e);
+      g.own(s);
+      check(ldb_gpu_simple_state_read(s, revenue, &e), e);
+   });
+}
+
+// ------------------------------------------------------------------------------------------------ Q1
+int ldb_tpch_q1_partial(LdbContext* ctx, const LdbTpchTables* t, const char* dateLe, LdbState** state, LdbError* err) {
+   return guarded(err, [&] {
+      LdbError e;
+      LdbState* s = nullptr;
+      check(ldb_gpu_groupby_create(ctx, 2, 6, 64, &s, &e), e);
+      LdbFilterDesc f[1] = {strFilter("l_shipdate", LDB_LTE, dateLe)};
+      LdbPipelineDesc d{};
+      d.kind = LDB_PIPE_SCAN_GROUPBY;
+      d.source = t->lineitem;
+      d.n_filters = 1;
+      d.filters = f;
+      d.n_keys = 2;
+      d.key_columns[0] = "l_returnflag";
+      d.key_columns[1] = "l_linestatus";
+      // avg(x) is sum(x)/count (SimplifyAggregations.cpp:160-181); equal sums are shared
+      d.n_aggs = 6;
+      d.aggs[0] = agg(LDB_EXPR_COL, "l_quantity");
+      d.aggs[1] = agg(LDB_EXPR_COL, "l_extendedprice");
+      d.aggs[2] = agg(LDB_EXPR_MUL_1MINUS, "l_extendedprice", "l_discount");
+      d.aggs[3] = agg(LDB_EXPR_MUL_1MINUS_1PLUS, "l_extendedprice", "l_discount", "l_tax");
+      d.aggs[4] = agg(LDB_EXPR_COL, "l_discount");
+      d.aggs[5] = agg(LDB_EXPR_ONE);
+      d.sink = s;
+      int rc = ldb_gpu_run_pipeline(ctx, &d, &e);
+      if (rc != LDB_OK) {
+         ldb_gpu_state_destroy(s);
+         throw PlanError(e);
+      }
+      *state = s;
+   });
+}
+int ldb_tpch_q1_finish(LdbState* state, LdbQ1Row* rows, int32_t maxRows, int32_t* nRows, LdbError* err) {
+   return guarded(err, [&] {
+      LdbError e;
+      std::vector<LdbGroupRow> g(64);
+      int32_t n = 0;
+      check(ldb_gpu_groupby_read(state, g.data(), 64, &n, &e), e);
+      std::vector<LdbQ1Row> out;
+      for (int i = 0; i < n && i < 64; i++) {
+         LdbQ1Row r{};
+         r.l_returnflag = g[i].keys[0];
+         r.l_linestatus = g[i].keys[1];
+         r.sum_qty = (int64_t) g[i].aggs[0].lo; // sum(decimal(12,2)) wraps at 64 bits like the reference's i64 accumulator
+         r.sum_base_price = (int64_t) g[i].aggs[1].lo;
+         r.sum_disc_price = g[i].aggs[2];
+         r.sum_charge = g[i].aggs[3];
+         int64_t sumDisc = (int64_t) g[i].aggs[4].lo;
+         r.count_order = (int64_t) g[i].aggs[5].lo;
+         r.avg_qty = avgDec(r.sum_qty, r.count_order);
+         r.avg_price = avgDec(r.sum_base_price, r.count_order);
+         r.avg_disc = avgDec(sumDisc, r.count_order);
+         out.push_back(r);
+      }
+      std::sort(out.begin(), out.end(), [](const LdbQ1Row& a, const LdbQ1Row& b) { return a.l_returnflag != b.l_returnflag ? a.l_returnflag < b.l_returnflag : a.l_linestatus < b.l_linestatus; });
+      *nRows = (int32_t) out.size();
+      for (int i = 0; i < (int) out.size() && i < maxRows; i++) rows[i] = out[i];
+   });
+}
+int ldb_tpch_q1(LdbContext* ctx, const LdbTpchTables* t, const char* dateLe, LdbQ1Row* rows, int32_t maxRows, int32_t* nRows, LdbError* err) {
+   return guarded(err, [&] {
+      LdbError e;
+      StateGuard g;
+      LdbState* s = nullptr;
+      check(ldb_tpch_q1_partial(ctx, t, dateLe, &s, &e), e);
+      g.own(s);
+      check(ldb_tpch_q1_finish(s, rows, maxRows, nRows, &e), e);
+   });
+}
+
+// ------------------------------------------------------------------------------------------------ Q3
+int ldb_tpch_q3(LdbContext* ctx, const LdbTpchTables* t, const char* segment, const char* date, LdbQ3Row* rows, int32_t* nRows, LdbError* err) {
+   return guarded(err, [&] {
+      LdbError e;
+      StateGuard g;
+      int64_t nCust = ldb_gpu_table_num_rows(t->customer), nOrd = ldb_gpu_table_num_rows(t->orders);
+      // P1: customer(c_mktsegment = X) → key set on c_custkey
+      LdbFilterDesc fc[1] = {strFilter("c_mktsegment", LDB_EQ, segment)};
+      LdbPipelineDesc d1{};
+      d1.kind = LDB_PIPE_SCAN_BUILD;
+      d1.source = t->customer;
+      d1.n_filters = 1;
+      d1.filters = fc;
+      d1.build_key_column = "c_custkey";
+      LdbState* cust = buildJoin(ctx, g, d1, nCust / 4 + 1024, 1, 0, 0);
+      // P2: orders(o_orderdate < D) ⋈ customer → group-join map keyed by o_orderkey {o_orderdate, o_shippriority | revenue}
+      LdbFilterDesc fo[1] = {strFilter("o_orderdate", LDB_LT, date)};
+      LdbPipelineDesc d2{};
+      d2.kind = LDB_PIPE_SCAN_BUILD;
+      d2.source = t->orders;
+      d2.n_filters = 1;
+      d2.filters = fo;
+      d2.n_probes = 1;
+      d2.probe_states[0] = cust;
+      d2.probe_key_columns[0] = "o_custkey";
+      d2.build_key_column = "o_orderkey";
+      d2.n_side = 2;
+      d2.side_columns[0] = "o_orderdate";
+      d2.side_columns[1] = "o_shippriority";
+      LdbState* map = buildJoin(ctx, g, d2, nOrd / 10 + 1024, 1, 2, 1);
+      // P3: lineitem(l_shipdate > D) pure lookup + SUM(l_extendedprice * (1 - l_discount)) into the entry
+      LdbFilterDesc fl[1] = {strFilter("l_shipdate", LDB_GT, date)};
+      LdbPipelineDesc d3{};
+      d3.kind = LDB_PIPE_SCAN_PROBE_AGG;
+      d3.source = t->lineitem;
+      d3.n_filters = 1;
+      d3.filters = fl;
+      d3.n_probes = 1;
+      d3.probe_states[0] = map;
+      d3.probe_key_columns[0] = "l_orderkey";
+      d3.n_aggs = 1;
+      d3.aggs[0] = agg(LDB_EXPR_MUL_1MINUS, "l_extendedprice", "l_discount");
+      d3.sink = map;
+      check(ldb_gpu_run_pipeline(ctx, &d3, &e), e);
+      // P4: marked groups, ORDER BY revenue desc, o_orderdate LIMIT 10
+      LdbTopKRow top[10];
+      int32_t n = 0;
+      check(ldb_gpu_join_table_topk(map, 10, top, &n, &e), e);
+      for (int i = 0; i < n; i++) rows[i] = LdbQ3Row{top[i].key, top[i].side[0], top[i].side[1], 0, top[i].agg};
+      *nRows = n;
+   });
+}
+
+// ------------------------------------------------------------------------------------------------ Q5
+int ldb_tpch_q5(LdbContext* ctx, const LdbTpchTables* t, const char* regionName, const char* dateGe, const char* dateLt, LdbQ5Row* rows, int32_t* nRows, LdbError* err) {
+   return guarded(err, [&] {
+      LdbError e;
+      StateGuard g;
+      int64_t nCust = ldb_gpu_table_num_rows(t->customer), nOrd = ldb_gpu_table_num_rows(t->orders), nSupp = ldb_gpu_table_num_rows(t->supplier);
+      // region(r_name = X) → {r_regionkey}
+      LdbFilterDesc fr[1] = {strFilter("r_name", LDB_EQ, regionName)};
+      LdbPipelineDesc dr{};
+      dr.kind = LDB_PIPE_SCAN_BUILD;
+      dr.source = t->region;
+      dr.n_filters = 1;
+      dr.filters = fr;
+      dr.build_key_column = "r_regionkey";
+      LdbState* region = buildJoin(ctx, g, dr, 16, 1, 0, 0);
+      // nation ⋈ region → {n_nationkey → n_nationkey}
+      LdbPipelineDesc dn{};
+      dn.kind = LDB_PIPE_SCAN_BUILD;
+      dn.source = t->nation;
+      dn.n_probes = 1;
+      dn.probe_states[0] = region;
+      dn.probe_key_columns[0] = "n_regionkey";
+      dn.build_key_column = "n_nationkey";
+      dn.build_payload_column = "n_nationkey";
+      LdbState* nation = buildJoin(ctx, g, dn, 64, 1, 0, 0);
+      // customer ⋈ nation → {c_custkey → c_nationkey}
+      LdbPipelineDesc dc{};
+      dc.kind = LDB_PIPE_SCAN_BUILD;
+      dc.source = t->customer;
+      dc.n_probes = 1;
+      dc.probe_states[0] = nation;
+      dc.probe_key_columns[0] = "c_nationkey";
+      dc.build_key_column = "c_custkey";
+      dc.build_payload_column = "c_nationkey";
+      LdbState* cust = buildJoin(ctx, g, dc, nCust / 4 + 1024, 1, 0, 0);
+      // orders(date range) ⋈ customer → {o_orderkey → c_nationkey}
+      LdbFilterDesc fo[2] = {strFilter("o_orderdate", LDB_GTE, dateGe), strFilter("o_orderdate", LDB_LT, dateLt)};
+      LdbPipelineDesc dor{};
+      dor.kind = LDB_PIPE_SCAN_BUILD;
+      dor.source = t->orders;
+      dor.n_filters = 2;
+      dor.filters = fo;
+      dor.n_probes = 1;
+      dor.probe_states[0] = cust;
+      dor.probe_key_columns[0] = "o_custkey";
+      dor.build_key_column = "o_orderkey";
+      LdbState* ord = buildJoin(ctx, g, dor, nOrd / 24 + 1024, 1, 0, 0);
+      // supplier ⋈ nation → {s_suppkey → s_nationkey}
+      LdbPipelineDesc ds{};
+      ds.kind = LDB_PIPE_SCAN_BUILD;
+      ds.source = t->supplier;
+      ds.n_probes = 1;
+      ds.probe_states[0] = nation;
+      ds.probe_key_columns[0] = "s_nationkey";
+      ds.build_key_column = "s_suppkey";
+      ds.build_payload_column = "s_nationkey";
+      LdbState* supp = buildJoin(ctx, g, ds, nSupp / 4 + 1024, 1, 0, 0);
+      // lineitem ⋈ orders ⋈ supplier on (l_suppkey, c_nationkey) → group by nation → SUM(ext * (1 - disc))
+      LdbState* groups = nullptr;
+      check(ldb_gpu_groupby_create(ctx, 1, 1, 64, &groups, &e), e);
+      g.own(groups);
+      LdbPipelineDesc dl{};
+      dl.kind = LDB_PIPE_SCAN_PROBE2_GROUPBY;
+      dl.source = t->lineitem;
+      dl.n_probes = 2;
+      dl.probe_states[0] = ord;
+      dl.probe_key_columns[0] = "l_orderkey";
+      dl.probe_states[1] = supp;
+      dl.probe_key_columns[1] = "l_suppkey";
+      dl.n_aggs = 1;
+      dl.aggs[0] = agg(LDB_EXPR_MUL_1MINUS, "l_extendedprice", "l_discount");
+      dl.sink = groups;
+      check(ldb_gpu_run_pipeline(ctx, &dl, &e), e);
+      std::vector<LdbGroupRow> gr(64);
+      int32_t n = 0;
+      check(ldb_gpu_groupby_read(groups, gr.data(), 64, &n, &e), e);
+      std::vector<LdbQ5Row> out;
+      for (int i = 0; i < n; i++) out.push_back(LdbQ5Row{gr[i].keys[0], 0, gr[i].aggs[0]});
+      std::sort(out.begin(), out.end(), [](const LdbQ5Row& a, const LdbQ5Row& b) {
+         i128 x = toI128(a.revenue), y = toI128(b.revenue);
+         return x != y ? x > y : a.n_nationkey < b.n_nationkey;
+      });
+      for (int i = 0; i < (int) out.size() && i < 25; i++) rows[i] = out[i];
+      *nRows = (int32_t) std::min<size_t>(out.size(), 25);
+   });
+}
+
+} // extern "C"

@@ -1,0 +1,115 @@
+"""Device-side table generation: fills torch CUDA tensors (plain HBM buffers) in the Arrow physical
+layout with the device twin of the deterministic generator (csrc/datagen.cu) and registers them
+as borrowed DEVICE batches.  torch is only the allocator here."""
+import ctypes as C
+from typing import Dict, List
+
+import torch
+
+from . import capi, datagen
+from .capi import Error, check
+from .runtime import Context, Table
+
+
+def _alloc(spec: datagen.ColumnSpec, n: int, dev):
+    if spec.phys == "decimal128":
+        return torch.empty((n, 16), dtype=torch.uint8, device=dev)
+    return torch.empty(n, dtype=torch.int32, device=dev)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def lineitem(ctx: Context, s: datagen.GenScale, columns: List[str], row_begin: int = 0, n_rows: int = None, batch_rows: int = None) -> Table:
+    dev = torch.device("cuda", ctx.device)
+    n_rows = s.n_lineitem - row_begin if n_rows is None else n_rows
+    batch_rows = n_rows if not batch_rows else batch_rows
+    specs = [c for c in datagen.LINEITEM_SCHEMA if c.name in columns]
+    tab = Table(ctx, "lineitem", specs)
+    b = 0
+    while b < n_rows:
+        n = min(batch_rows, n_rows - b)
+        tens = {c.name: _alloc(c, n, dev) for c in specs}
+        torch.cuda.synchronize(dev)
+        cols = datagen.LineitemCols(**{k: _ptr(v) for k, v in tens.items()})
+        e = Error()
+        check(ctx.L.ldb_gpu_datagen_lineitem(ctx.h, C.byref(s), row_begin + b, n, C.byref(cols), C.byref(e)), e)
+        tab.append_device(tens, n)
+        b += n
+    ctx.synchronize()
+    return tab
+
+
+def orders(ctx: Context, s: datagen.GenScale, row_begin: int = 0, n_rows: int = None) -> Table:
+    dev = torch.device("cuda", ctx.device)
+    n = s.n_orders - row_begin if n_rows is None else n_rows
+    tens = {c.name: _alloc(c, n, dev) for c in datagen.ORDERS_SCHEMA}
+    torch.cuda.synchronize(dev)
+    cols = datagen.OrdersCols(**{k: _ptr(v) for k, v in tens.items()})
+    e = Error()
+    check(ctx.L.ldb_gpu_datagen_orders(ctx.h, C.byref(s), row_begin, n, C.byref(cols), C.byref(e)), e)
+    tab = Table(ctx, "orders", datagen.ORDERS_SCHEMA)
+    tab.append_device(tens, n)
+    ctx.synchronize()
+    return tab
+
+
+def customer(ctx: Context, s: datagen.GenScale) -> Table:
+    dev = torch.device("cuda", ctx.device)
+    n = s.n_customer
+    ck = torch.empty(n, dtype=torch.int32, device=dev)
+    cn = torch.empty(n, dtype=torch.int32, device=dev)
+    lens = torch.empty(n, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize(dev)
+    e = Error()
+    cols = datagen.CustomerCols(_ptr(ck), _ptr(cn), None, None)
+    check(ctx.L.ldb_gpu_datagen_customer_fixed(ctx.h, C.byref(s), 0, n, C.byref(cols), _ptr(lens), C.byref(e)), e)
+    ctx.synchronize()
+    offs = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+    offs[1:] = torch.cumsum(lens, 0, dtype=torch.int64).to(torch.int32)
+    data = torch.empty(int(offs[-1].item()), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize(dev)
+    check(ctx.L.ldb_gpu_datagen_customer_bytes(ctx.h, C.byref(s), 0, n, _ptr(offs), _ptr(data), C.byref(e)), e)
+    tab = Table(ctx, "customer", datagen.CUSTOMER_SCHEMA)
+    tab.append_device({"c_custkey": ck, "c_nationkey": cn, "c_mktsegment": (offs, data)}, n)
+    ctx.synchronize()
+    return tab
+
+
+def supplier(ctx: Context, s: datagen.GenScale) -> Table:
+    dev = torch.device("cuda", ctx.device)
+    n = s.n_supplier
+    tens = {c.name: _alloc(c, n, dev) for c in datagen.SUPPLIER_SCHEMA}
+    torch.cuda.synchronize(dev)
+    cols = datagen.SupplierCols(**{k: _ptr(v) for k, v in tens.items()})
+    e = Error()
+    check(ctx.L.ldb_gpu_datagen_supplier(ctx.h, C.byref(s), 0, n, C.byref(cols), C.byref(e)), e)
+    tab = Table(ctx, "supplier", datagen.SUPPLIER_SCHEMA)
+    tab.append_device(tens, n)
+    ctx.synchronize()
+    return tab
+
+
+def small_tables(ctx: Context) -> Dict[str, Table]:
+    return {"nation": ctx.table_from_host(datagen.nation()), "region": ctx.table_from_host(datagen.region())}
+
+
+def to_host(tab: Table) -> datagen.TableData:
+    """Copy a device-generated table back into host TableData (tests: device twin == host generator)."""
+    t = datagen.TableData(tab.name, tab.columns)
+    for item in tab._keep:
+        if not isinstance(item, dict):
+            continue
+        chunk, n = {}, None
+        for c in tab.columns:
+            v = item[c.name]
+            if c.phys == "utf8":
+                chunk[c.name] = (v[0].cpu().numpy(), v[1].cpu().numpy())
+                n = v[0].numel() - 1
+            else:
+                chunk[c.name] = v.cpu().numpy()
+                n = v.shape[0]
+        t.chunks.append(chunk)
+        t.chunk_rows.append(n)
+    return t

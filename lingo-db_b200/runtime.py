@@ -1,0 +1,219 @@
+"""Python face of the GPU operator runtime: contexts, Arrow-layout tables in HBM, TPC-H drivers.
+
+Thin plumbing over the C-ABI (capi.py): numpy/torch only hold buffers; every data-parallel step is
+a hand-written sm_100a kernel inside libldb_gpu.so.  Results come back as exact python ints in the
+same dict shapes the CPU oracle uses, so the parity tests compare with `==`.
+"""
+import ctypes as C
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import capi, datagen
+from .capi import Error, check
+
+
+class Context:
+    """One per device (ExecutionContext + scheduler hand-off of the reference)."""
+
+    def __init__(self, device: int = 0):
+        self.L = capi.lib()
+        self.h = C.c_void_p()
+        e = Error()
+        check(self.L.ldb_gpu_context_create(device, C.byref(self.h), C.byref(e)), e)
+        self.device = device
+        self._tables = []
+
+    def close(self):
+        if self.h:
+            self.L.ldb_gpu_context_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def info(self) -> dict:
+        d, e = capi.DeviceInfo(), Error()
+        check(self.L.ldb_gpu_device_info(self.h, C.byref(d), C.byref(e)), e)
+        return {"device": d.device, "sm_count": d.sm_count, "cc": (d.cc_major, d.cc_minor), "total_mem": d.total_mem,
+                "free_mem": d.free_mem, "l2_bytes": d.l2_bytes, "name": d.name.decode()}
+
+    def synchronize(self):
+        e = Error()
+        check(self.L.ldb_gpu_synchronize(self.h, C.byref(e)), e)
+
+    def launch_count(self) -> int:
+        return int(self.L.ldb_gpu_launch_count(self.h))
+
+    def timer_start(self):
+        e = Error()
+        check(self.L.ldb_gpu_timer_start(self.h, C.byref(e)), e)
+
+    def timer_stop(self) -> float:
+        ms, e = C.c_float(), Error()
+        check(self.L.ldb_gpu_timer_stop(self.h, C.byref(ms), C.byref(e)), e)
+        return ms.value
+
+    def kernel_time_reset(self, enable: bool = True):
+        e = Error()
+        check(self.L.ldb_gpu_kernel_time_reset(self.h, int(enable), C.byref(e)), e)
+
+    def kernel_time(self, family: str):
+        ms, n, e = C.c_float(), C.c_int64(), Error()
+        check(self.L.ldb_gpu_kernel_time(self.h, family.encode(), C.byref(ms), C.byref(n), C.byref(e)), e)
+        return ms.value, n.value
+
+    # ------------------------------------------------------------------ tables
+    def table(self, name: str, columns: List[datagen.ColumnSpec]) -> "Table":
+        return Table(self, name, columns)
+
+    def table_from_host(self, t: datagen.TableData) -> "Table":
+        """Stage a host TableData (numpy Arrow buffers) to HBM, batch by batch."""
+        tab = Table(self, t.name, t.columns)
+        for chunk, n in zip(t.chunks, t.chunk_rows):
+            tab.append_host(chunk, n)
+        return tab
+
+    def hash_i64(self, a: np.ndarray, b: Optional[np.ndarray] = None) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.int64)
+        out = np.zeros(a.shape[0], dtype=np.uint64)
+        bp = None
+        if b is not None:
+            b = np.ascontiguousarray(b, dtype=np.int64)
+            bp = b.ctypes.data
+        e = Error()
+        check(self.L.ldb_gpu_hash_i64(self.h, a.ctypes.data, bp, a.shape[0], out.ctypes.data, C.byref(e)), e)
+        return out
+
+
+class Table:
+    def __init__(self, ctx: Context, name: str, columns: List[datagen.ColumnSpec]):
+        self.ctx, self.name, self.columns = ctx, name, list(columns)
+        self._names = [c.name.encode() for c in columns]
+        schema = (capi.ColumnSchema * len(columns))()
+        for i, c in enumerate(columns):
+            schema[i] = capi.ColumnSchema(self._names[i], capi.PHYS[c.phys], c.precision, c.scale)
+        self.h = C.c_void_p()
+        e = Error()
+        check(ctx.L.ldb_gpu_table_create(ctx.h, name.encode(), len(columns), schema, C.byref(self.h), C.byref(e)), e)
+        self._keep = []
+        ctx._tables.append(self)
+
+    def _append(self, n_rows: int, bufs: Dict[str, object], location: int, utf8_sizes: Dict[str, int]):
+        """bufs: column → address (int) or (offsets_addr, bytes_addr) for utf8."""
+        nc = len(self.columns)
+        views = (capi.ArrayView * nc)()
+        sizes = (C.c_int64 * nc)()
+        keep = []
+        for i, c in enumerate(self.columns):
+            arr = (C.c_void_p * 3)()
+            v = bufs[c.name]
+            if c.phys == "utf8":
+                arr[1], arr[2] = v[0], v[1]
+                sizes[i] = utf8_sizes[c.name]
+            else:
+                arr[1] = v
+            keep.append(arr)
+            views[i] = capi.ArrayView(n_rows, 0, 0, 3 if c.phys == "utf8" else 2, 0, C.cast(arr, C.POINTER(C.c_void_p)), None)
+        e = Error()
+        check(self.ctx.L.ldb_gpu_table_append_batch(self.h, n_rows, views, sizes, location, C.byref(e)), e)
+        self._keep.append((keep, views))
+
+    def append_host(self, chunk: Dict[str, object], n_rows: int):
+        bufs, sizes = {}, {}
+        for c in self.columns:
+            v = chunk[c.name]
+            if c.phys == "utf8":
+                offs, data = v
+                bufs[c.name] = (offs.ctypes.data, data.ctypes.data)
+                sizes[c.name] = int(offs[n_rows])
+            else:
+                bufs[c.name] = v.ctypes.data
+        self._keep.append(chunk)
+        self._append(n_rows, bufs, capi.MEM_HOST, sizes)
+
+    def append_device(self, tensors: Dict[str, object], n_rows: int):
+        """tensors: column → torch CUDA tensor (or (offsets, bytes) pair for utf8); borrowed."""
+        bufs, sizes = {}, {}
+        for c in self.columns:
+            v = tensors[c.name]
+            if c.phys == "utf8":
+                bufs[c.name] = (v[0].data_ptr(), v[1].data_ptr())
+                sizes[c.name] = int(v[1].numel())
+            else:
+                bufs[c.name] = v.data_ptr()
+        self._keep.append(tensors)
+        self._append(n_rows, bufs, capi.MEM_DEVICE, sizes)
+
+    def clear(self):
+        e = Error()
+        check(self.ctx.L.ldb_gpu_table_clear(self.h, C.byref(e)), e)
+        self._keep.clear()
+
+    @property
+    def num_rows(self) -> int:
+        return int(self.ctx.L.ldb_gpu_table_num_rows(self.h))
+
+
+# ---------------------------------------------------------------------- TPC-H drivers (include/ldb_tpch.h)
+class Tpch:
+    """Holds the six table handles and runs the C++ query drivers."""
+
+    def __init__(self, ctx: Context, tables: Dict[str, Table], nation_names: Optional[List[str]] = None):
+        self.ctx, self.tables = ctx, tables
+        self.t = capi.TpchTables(**{k: (tables[k].h if k in tables else None) for k in ("lineitem", "orders", "customer", "supplier", "nation", "region")})
+        self.nation_names = nation_names or [n for n, _ in datagen.NATIONS]
+
+    def q6(self, date_ge="1994-01-01", date_lt="1995-01-01", disc_ge="0.05", disc_le="0.07", qty_lt=24):
+        rev, e = capi.I128(), Error()
+        check(self.ctx.L.ldb_tpch_q6(self.ctx.h, C.byref(self.t), date_ge.encode(), date_lt.encode(), disc_ge.encode(), disc_le.encode(), qty_lt,
+                                     C.byref(rev), C.byref(e)), e)
+        return {"revenue": rev.value()}
+
+    @staticmethod
+    def _q1_rows(rows, n):
+        return [{"l_returnflag": r.l_returnflag, "l_linestatus": r.l_linestatus, "sum_qty": r.sum_qty, "sum_base_price": r.sum_base_price,
+                 "sum_disc_price": r.sum_disc_price.value(), "sum_charge": r.sum_charge.value(), "avg_qty": r.avg_qty.value(),
+                 "avg_price": r.avg_price.value(), "avg_disc": r.avg_disc.value(), "count_order": r.count_order} for r in rows[:n]]
+
+    def q1(self, date_le="1998-09-02"):
+        rows, n, e = (capi.Q1Row * 64)(), C.c_int32(), Error()
+        check(self.ctx.L.ldb_tpch_q1(self.ctx.h, C.byref(self.t), date_le.encode(), rows, 64, C.byref(n), C.byref(e)), e)
+        return self._q1_rows(rows, n.value)
+
+    def q1_partial(self, date_le="1998-09-02") -> C.c_void_p:
+        s, e = C.c_void_p(), Error()
+        check(self.ctx.L.ldb_tpch_q1_partial(self.ctx.h, C.byref(self.t), date_le.encode(), C.byref(s), C.byref(e)), e)
+        return s
+
+    def q1_finish(self, state):
+        rows, n, e = (capi.Q1Row * 64)(), C.c_int32(), Error()
+        check(self.ctx.L.ldb_tpch_q1_finish(state, rows, 64, C.byref(n), C.byref(e)), e)
+        return self._q1_rows(rows, n.value)
+
+    def q3(self, segment="BUILDING", date="1995-03-15"):
+        rows, n, e = (capi.Q3Row * 10)(), C.c_int32(), Error()
+        check(self.ctx.L.ldb_tpch_q3(self.ctx.h, C.byref(self.t), segment.encode(), date.encode(), rows, C.byref(n), C.byref(e)), e)
+        return [{"l_orderkey": r.l_orderkey, "revenue": r.revenue.value(), "o_orderdate": r.o_orderdate, "o_shippriority": r.o_shippriority}
+                for r in rows[: n.value]]
+
+    def q5(self, region_name="ASIA", date_ge="1994-01-01", date_lt="1995-01-01"):
+        rows, n, e = (capi.Q5Row * 25)(), C.c_int32(), Error()
+        check(self.ctx.L.ldb_tpch_q5(self.ctx.h, C.byref(self.t), region_name.encode(), date_ge.encode(), date_lt.encode(), rows, C.byref(n), C.byref(e)), e)
+        # n_name is resolved at materialisation from the (host) nation table
+        out = [{"n_name": self.nation_names[r.n_nationkey], "revenue": r.revenue.value()} for r in rows[: n.value]]
+        out.sort(key=lambda r: (-r["revenue"], r["n_name"]))
+        return out
+
+
+def groupby_read(ctx: Context, state) -> list:
+    rows, n, e = (capi.GroupRow * 1024)(), C.c_int32(), Error()
+    check(ctx.L.ldb_gpu_groupby_read(state, rows, 1024, C.byref(n), C.byref(e)), e)
+    return rows, n.value
+
+
+def state_destroy(ctx: Context, state):
+    ctx.L.ldb_gpu_state_destroy(state)
