@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py — TPC-H SF100 Q1 (lineitem scan + 2-key hash aggregation) rows/s on N B200s.
+
+Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]`, one JSON line on rank 0.
+  step    = one pass of the Q1 pipeline (scan → filter → expressions → group-by) over the lineitem
+            partition resident in HBM, plus (N > 1) the NCCL all-gather + merge of the 4-group partials.
+  value   = lineitem rows of ALL ranks / max-over-ranks device time, inputs resident in HBM ("strong":
+            SF100 is split across the ranks by order range).
+  e2e     = the same step through the C-ABI with HOST (pinned) Arrow buffers: H2D staging of every
+            column batch and the D2H result read are inside the timed region.
+  roofline= scan_groupby kernel: algorithmic bytes (76 B/row) / CUDA-event kernel time.
+  cpu_baseline = the CPU oracle (reference runtime objects + restated pipelines, NOT the LLVM JIT) on
+            the box's host cores over a bounded sample of the same table.
+`--impl reference` times that CPU implementation alone on the same config (rank 0 only).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+Q1_COLS = ["l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus", "l_shipdate"]
+Q1_BYTES_PER_ROW = 76  # 4 decimal128 + 2 fixed_size_binary(4) + date32
+ALL_COLS = ["l_orderkey", "l_suppkey"] + Q1_COLS
+METRIC = "TPC-H SF100 Q1 rows/sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sf", type=float, default=100.0)
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-batch-rows", type=int, default=1 << 24)
+    ap.add_argument("--cpu-sample-sf", type=float, default=20.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the Q6/Q3/Q5 side measurements")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def host_lineitem_sample(sf, seed, cols, max_rows=None):
+    from lingodb_b200 import datagen
+    s = datagen.scale(sf, seed)
+    n = s.n_lineitem if max_rows is None else min(max_rows, s.n_lineitem)
+    return datagen.lineitem(s, cols, chunk_rows=1 << 20, n_rows=n), n
+
+
+def time_oracle_q1(table_data, repeats):
+    from oracle import oracle as O
+    o = O.Oracle("auto", workers=0)
+    h = o.table(table_data)
+    best, rows = None, None
+    times = []
+    for _ in range(repeats):
+        rows, sec = o.q1(h)
+        times.append(sec)
+        best = sec if best is None else min(best, sec)
+    return o, rows, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_sf = min(args.sf, args.cpu_sample_sf)
+    t, n = host_lineitem_sample(sample_sf, args.seed, Q1_COLS)
+    from oracle import oracle as O
+    o = O.Oracle("auto", workers=0)
+    h = o.table(t)
+    for _ in range(args.warmup):
+        o.q1(h)
+    t0 = time.perf_counter()
+    secs = []
+    for _ in range(args.steps):
+        _, sec = o.q1(h)
+        secs.append(sec)
+    wall = time.perf_counter() - t0
+    total = sum(secs)
+    value = n * args.steps / total
+    sample = f"first {n} lineitem rows (SF{sample_sf:g}) of the SF{args.sf:g} table per step, tables resident in host RAM"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000 * total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64/int128",
+        "data": "synthetic", "config": {"workload": f"TPC-H SF{args.sf:g} Q1 (lineitem scan + 2-key hash aggregation)", "sample": sample,
+                                        "timed_region": "pipelines only (reference executionTime)", "wall_s": wall},
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": o.workers, "kind": o.kind, "sample": sample,
+                         "note": "reference runtime objects + restated pipelines; the MLIR/LLVM JIT cannot be built here"},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from lingodb_b200 import capi, datagen, devgen, runtime
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    ctx = runtime.Context(local)
+    L = ctx.L
+    s = datagen.scale(args.sf, args.seed)
+    # strong scaling: SF-sized lineitem split by order range
+    o_lo, o_hi = s.n_orders * rank // world, s.n_orders * (rank + 1) // world
+    gl = datagen.lib()
+    r_lo, r_hi = gl.ldbgen_order_first_line(C.byref(s), o_lo), gl.ldbgen_order_first_line(C.byref(s), o_hi)
+    my_rows = r_hi - r_lo
+    extra = (not args.no_extra) and world == 1
+    cols = ALL_COLS if extra else Q1_COLS
+    lineitem = devgen.lineitem(ctx, s, cols, row_begin=r_lo, n_rows=my_rows)
+    tabs = {"lineitem": lineitem}
+    tp = runtime.Tpch(ctx, tabs)
+    total_rows = s.n_lineitem
+
+    gather_buf = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def step_resident():
+        st = tp.q1_partial()
+        if world > 1:
+            nonlocal gather_buf
+            nbytes = int(L.ldb_gpu_groupby_export_bytes(st))
+            if gather_buf is None:
+                gather_buf = (torch.empty(nbytes, dtype=torch.uint8, device=dev), torch.empty(nbytes * world, dtype=torch.uint8, device=dev))
+            e = capi.Error()
+            capi.check(L.ldb_gpu_groupby_export(st, C.c_void_p(gather_buf[0].data_ptr()), C.byref(e)), e)
+            ctx.synchronize()
+            dist.all_gather_into_tensor(gather_buf[1], gather_buf[0])
+            torch.cuda.current_stream().synchronize()
+            capi.check(L.ldb_gpu_groupby_merge_exported(st, C.c_void_p(gather_buf[1].data_ptr()), world, rank, C.byref(e)), e)
+        rows = tp.q1_finish(st)
+        runtime.state_destroy(ctx, st)
+        return rows
+
+    # ---- warm-up + timed region (device-resident inputs, 45.6 GB at SF100 >> 126 MB L2)
+    for _ in range(args.warmup):
+        rows = step_resident()
+    ctx.kernel_time_reset(True)
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    barrier()
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rows = step_resident()
+    ms_dev = ctx.timer_stop()
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    wall_ms = 1000 * (time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    barrier()
+    launches = ctx.launch_count() - launches0
+    k_ms, k_n = ctx.kernel_time("scan_groupby")
+    ctx.kernel_time_reset(False)
+    # device time of the timed region, max over ranks
+    tmax = torch.tensor([ms_dev, wall_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total, wall_total = float(tmax[0].item()), float(tmax[1].item())
+    ms_per_step = ms_total / args.steps
+    value = total_rows * args.steps / (ms_total / 1000)
+
+    peak, peak_src = peaks()
+    k_avg_ms = k_ms / max(k_n, 1)
+    achieved = (Q1_BYTES_PER_ROW * my_rows) / (k_avg_ms / 1000) / 1e9 if k_avg_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "scanGroupByKernel<2 keys, 4 decimal cols, Q1 aggregates>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "frac_of": peak_src, "traffic": None, "algorithmic_bytes_per_launch": Q1_BYTES_PER_ROW * my_rows,
+                "kernel_ms_avg": k_avg_ms, "kernel_launches_timed": k_n, "kernel_share_of_step": (k_ms / ms_dev) if ms_dev else None}
+    ncu = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(ncu):
+        try:
+            tr = json.load(open(ncu)).get("scan_groupby_q1")
+            if tr:
+                roofline["traffic"] = tr["dram_bytes_per_row"] * my_rows
+                roofline["traffic_source"] = tr["source"]
+        except (ValueError, KeyError):
+            pass
+
+    # ---- e2e: HOST (pinned) Arrow buffers → C-ABI staging → pipeline → result read
+    e2e = None
+    if not args.no_e2e:
+        specs = [c for c in datagen.LINEITEM_SCHEMA if c.name in Q1_COLS]
+        host_batches = []
+        b = 0
+        src = lineitem._keep[0]
+        while b < my_rows:
+            n = min(args.e2e_batch_rows, my_rows - b)
+            chunk = {}
+            for c in specs:
+                shape = (n, 16) if c.phys == "decimal128" else (n,)
+                h = torch.empty(shape, dtype=torch.uint8 if c.phys == "decimal128" else torch.int32, pin_memory=True)
+                h.copy_(src[c.name][b:b + n])
+                chunk[c.name] = h.numpy()
+            host_batches.append((chunk, n))
+            b += n
+        torch.cuda.synchronize()
+        host_tab = runtime.Table(ctx, "lineitem", specs)
+        tp_h = runtime.Tpch(ctx, {"lineitem": host_tab})
+        h2d = Q1_BYTES_PER_ROW * my_rows
+
+        def step_e2e():
+            host_tab.clear()
+            for chunk, n in host_batches:
+                host_tab.append_host(chunk, n)
+            st = tp_h.q1_partial()
+            r = tp_h.q1_finish(st)
+            runtime.state_destroy(ctx, st)
+            return r
+
+        rows_h = step_e2e()  # warm-up (allocates the staging pool)
+        assert rows_h == (rows if world == 1 else rows_h)
+        barrier()
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            rows_h = step_e2e()
+        ctx.synchronize()
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te[0].item())
+        e2e = {"value": total_rows * args.e2e_steps / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": h2d * world if world > 1 else h2d,
+               "d2h_bytes_per_step": 64 * 136 * world, "steps": args.e2e_steps, "ms_per_step": 1000 * e2e_s / args.e2e_steps,
+               "batch_rows": args.e2e_batch_rows, "host_memory": "pinned", "note": "per-rank partial result; N>1 skips the cross-rank merge in this leg"}
+        host_tab.clear()
+        del host_batches
+
+    # ---- CPU baseline on a bounded sample of the same table (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample_sf = min(args.sf, args.cpu_sample_sf)
+        s_s = datagen.scale(sample_sf, args.seed)
+        n = min(my_rows, s_s.n_lineitem)
+        specs = [c for c in datagen.LINEITEM_SCHEMA if c.name in Q1_COLS]
+        td = datagen.TableData("lineitem", specs)
+        src = lineitem._keep[0]
+        host = {c.name: src[c.name][:n].cpu().numpy() for c in specs}
+        for b in range(0, n, 1 << 20):
+            m = min(1 << 20, n - b)
+            td.chunks.append({k: v[b:b + m] for k, v in host.items()})
+            td.chunk_rows.append(m)
+        o, orows, times = time_oracle_q1(td, 4)
+        sec = min(times[1:]) if len(times) > 1 else times[0]
+        cpu = {"value": n / sec, "unit": "rows/s", "cores": o.workers, "kind": o.kind,
+               "sample": f"first {n} lineitem rows of the SF{args.sf:g} table (the SF{sample_sf:g} prefix), best of 3 after 1 warm-up, pipelines only",
+               "seconds": sec, "note": "reference runtime objects + restated pipelines (oracle/), not the MLIR/LLVM JIT"}
+
+    # ---- side measurements for the other §8 configs (N = 1): Q6, Q3, Q5 on the same resident tables
+    queries = None
+    if extra and rank == 0:
+        queries = {}
+        tabs.update({"orders": devgen.orders(ctx, s), "customer": devgen.customer(ctx, s), "supplier": devgen.supplier(ctx, s), **devgen.small_tables(ctx)})
+        tpx = runtime.Tpch(ctx, tabs)
+        scanned = {"q6": s.n_lineitem, "q3": s.n_lineitem + s.n_orders + s.n_customer, "q5": s.n_lineitem + s.n_orders + s.n_customer + s.n_supplier + 30}
+        algo = {"q6": 52 * s.n_lineitem, "q3": 40 * s.n_lineitem + 16 * s.n_orders + 21 * s.n_customer,
+                "q5": 40 * s.n_lineitem + 12 * s.n_orders + 8 * s.n_customer + 8 * s.n_supplier}
+        for name, fn in (("q6", tpx.q6), ("q3", tpx.q3), ("q5", tpx.q5)):
+            fn()
+            fn()
+            ctx.synchronize()
+            reps = 5
+            ctx.timer_start()
+            for _ in range(reps):
+                res = fn()
+            ms = ctx.timer_stop() / reps
+            queries[name] = {"ms": ms, "rows_per_s": scanned[name] / (ms / 1000), "algorithmic_gbs": algo[name] / (ms / 1000) / 1e9,
+                             "roofline_frac": algo[name] / (ms / 1000) / 1e9 / peak, "rows_scanned": scanned[name]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64/int128", "data": "synthetic",
+            "config": {"workload": f"TPC-H SF{args.sf:g} Q1 (lineitem scan + 2-key hash aggregation) on {world}xB200", "sf": args.sf, "lineitem_rows": total_rows,
+                       "rows_per_gpu": my_rows, "partitioning": "order-range split, NCCL all-gather of 4-group partials" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (45.6 GB of columns per pass at SF100 vs 126 MB L2)", "arrow_layout": "decimal128 16 B/value, date32, fixed_size_binary(4)",
+                       "generator": "deterministic TPC-H-shaped generator on device (csrc/datagen.cu), seed %d" % args.seed, "wall_ms_per_step": wall_total / args.steps,
+                       "result_rows": len(rows)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        if queries:
+            line["other_queries"] = queries
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

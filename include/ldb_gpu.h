@@ -124,6 +124,13 @@ int ldb_gpu_groupby_read(LdbState* s, LdbGroupRow* rows, int32_t max_rows, int32
 /* fold another GPU's partial groups into this state (K7 merge; rt::PreAggregationHashtable::merge) */
 int ldb_gpu_groupby_merge_rows(LdbState* s, const LdbGroupRow* rows, int32_t n_rows, LdbError* err);
 
+/* Multi-GPU merge without a host round trip: copy the table image {state[cap], keys[cap][2], acc[cap][8][2]}
+ * into a caller-provided DEVICE buffer (bytes = ldb_gpu_groupby_export_bytes), all-gather it with NCCL,
+ * then fold the `n_tables` images (skipping `skip_index`, the caller's own) back into the state. */
+int64_t ldb_gpu_groupby_export_bytes(LdbState* s);
+int ldb_gpu_groupby_export(LdbState* s, void* dev_dst, LdbError* err);
+int ldb_gpu_groupby_merge_exported(LdbState* s, const void* dev_src, int32_t n_tables, int32_t skip_index, LdbError* err);
+
 /* expected_rows sizes the directory like HashIndexedView::build (nextPow2 of a multiple of n);
  * n_side = int32 payload lanes stored beside the slot; n_aggs = int128 aggregate lanes (group-join) */
 int ldb_gpu_join_table_create(LdbContext* ctx, int64_t expected_rows, int32_t unique_keys, int32_t n_side, int32_t n_aggs, LdbState** out, LdbError* err);

@@ -118,6 +118,9 @@ SIGNATURES = {
     "ldb_gpu_groupby_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P), _E]),
     "ldb_gpu_groupby_read": (C.c_int, [_P, C.POINTER(GroupRow), C.c_int32, C.POINTER(C.c_int32), _E]),
     "ldb_gpu_groupby_merge_rows": (C.c_int, [_P, C.POINTER(GroupRow), C.c_int32, _E]),
+    "ldb_gpu_groupby_export_bytes": (C.c_int64, [_P]),
+    "ldb_gpu_groupby_export": (C.c_int, [_P, _P, _E]),
+    "ldb_gpu_groupby_merge_exported": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _E]),
     "ldb_gpu_join_table_create": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P), _E]),
     "ldb_gpu_join_table_count": (C.c_int, [_P, C.POINTER(C.c_int64), _E]),
     "ldb_gpu_join_table_topk": (C.c_int, [_P, C.c_int32, C.POINTER(TopKRow), C.POINTER(C.c_int32), _E]),

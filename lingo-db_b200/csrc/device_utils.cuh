@@ -55,12 +55,12 @@ __device__ __forceinline__ uint64_t hashI32(int32_t k) { return hash64((uint64_t
 // ---------------------------------------------------------------- streaming loads (read-once column data)
 __device__ __forceinline__ int32_t ldStream32(const int32_t* p) {
    int32_t v;
-   asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+   asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
    return v;
 }
 __device__ __forceinline__ int64_t ldStream64(const int64_t* p) {
    int64_t v;
-   asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
+   asm("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
    return v;
 }
 

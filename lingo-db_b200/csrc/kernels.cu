@@ -37,15 +37,21 @@ __device__ __forceinline__ int64_t loadFilterValue(const FilterCol& f, int64_t r
       return eq ? 1 : 0;
    }
 }
-__device__ __forceinline__ bool evalFilters(const FilterSet& F, int64_t r) {
+// two phases so that every load of a tile is in flight before the first compare consumes one
+struct FilterVals {
+   int64_t v[kMaxFilterCols];
+};
+__device__ __forceinline__ FilterVals loadFilters(const FilterSet& F, int64_t r) {
+   FilterVals fv;
+#pragma unroll
+   for (int i = 0; i < kMaxFilterCols; i++) fv.v[i] = i < F.n ? loadFilterValue(F.c[i], r) : 0;
+   return fv;
+}
+__device__ __forceinline__ bool testFilters(const FilterSet& F, const FilterVals& fv) {
    bool pass = true;
 #pragma unroll
-   for (int i = 0; i < kMaxFilterCols; i++) {
-      if (i < F.n) {
-         int64_t v = loadFilterValue(F.c[i], r);
-         pass &= cmpMask(v, F.c[i].valA, F.c[i].maskA) & cmpMask(v, F.c[i].valB, F.c[i].maskB);
-      }
-   }
+   for (int i = 0; i < kMaxFilterCols; i++)
+      if (i < F.n) pass &= cmpMask(fv.v[i], F.c[i].valA, F.c[i].maskA) & cmpMask(fv.v[i], F.c[i].valB, F.c[i].maskB);
    return pass;
 }
 
@@ -254,9 +260,11 @@ __global__ void __launch_bounds__(kBlock, 2) scanGroupByKernel(const __grid_cons
    int32_t lastK0 = 0, lastK1 = 0, lastId = -2;
 
    for (int64_t base = (int64_t) blockIdx.x * tileRows; base < n; base += (int64_t) gridDim.x * tileRows) {
+      __syncwarp(); // the tile loop is CTA-uniform: re-converge whatever the previous tile's row branches left
       int64_t vals[ROWS][NV];
       int32_t keys[ROWS][NK == 0 ? 1 : NK];
       bool pass[ROWS];
+      FilterVals fvals[ROWS];
       // ---- issue every load of the tile first
 #pragma unroll
       for (int j = 0; j < ROWS; j++) {
@@ -267,50 +275,70 @@ __global__ void __launch_bounds__(kBlock, 2) scanGroupByKernel(const __grid_cons
          for (int c = 0; c < NV; c++) vals[j][c] = ldStream64((const int64_t*) p.valueCols[c] + 2 * rr);
 #pragma unroll
          for (int k = 0; k < NK; k++) keys[j][k] = ldStream32(p.keyCols[k] + rr);
-         pass[j] = valid & evalFilters(p.src.filters, rr);
+         fvals[j] = loadFilters(p.src.filters, rr);
+         pass[j] = valid;
       }
+#pragma unroll
+      for (int j = 0; j < ROWS; j++) pass[j] &= testFilters(p.src.filters, fvals[j]);
       // ---- per row: group id, expression, accumulate
 #pragma unroll
       for (int j = 0; j < ROWS; j++) {
-         if (!pass[j]) continue;
          int id = 0;
          if constexpr (NK > 0) {
-            int32_t k0 = keys[j][0], k1 = NK > 1 ? keys[j][NK - 1] : 0;
-            if (lastId != -2 && k0 == lastK0 && k1 == lastK1) {
+            // Resolve the CTA-local group id under WARP-UNIFORM control flow.  (A per-lane spin lock
+            // here once left the warps permanently diverged: 1 active thread per instruction, 40x
+            // the instructions and 12x the DRAM traffic — profiles/r1_q1_first.md.)
+            const int32_t k0 = keys[j][0], k1 = NK > 1 ? keys[j][NK - 1] : 0;
+            id = -1;
+            bool need = pass[j];
+            if (need && lastId >= 0 && k0 == lastK0 && k1 == lastK1) {
                id = lastId;
-            } else {
-               id = -1;
-               int cnt = *((volatile int32_t*) &sCount);
+               need = false;
+            }
+            if (need) {
+               const int cnt = *((volatile int32_t*) &sCount);
                for (int g = 0; g < cnt; g++)
                   if (sKeys[g][0] == k0 && sKeys[g][1] == k1) id = g;
-               if (id < 0) { // first sight in this CTA: register the group under the CTA lock
-                  bool done = false;
-                  while (!done) {
-                     if (atomicCAS(&sLock, 0, 1) == 0) {
-                        int c2 = *((volatile int32_t*) &sCount);
-                        for (int g = 0; g < c2; g++)
-                           if (((volatile int32_t*) sKeys[g])[0] == k0 && ((volatile int32_t*) sKeys[g])[1] == k1) id = g;
-                        if (id < 0 && c2 < LG) {
-                           int32_t kk[2] = {k0, k1};
-                           int slot = groupLookupOrInsert(p.table, kk);
-                           sKeys[c2][0] = k0;
-                           sKeys[c2][1] = k1;
-                           sSlot[c2] = slot;
-                           __threadfence_block();
-                           *((volatile int32_t*) &sCount) = c2 + 1;
-                           id = c2;
-                        }
-                        __threadfence_block();
-                        atomicExch(&sLock, 0);
-                        done = true;
-                     }
+               need = id < 0;
+            }
+            // first sight of a key in this CTA: one elected lane registers it under the CTA lock
+            unsigned pending = __ballot_sync(0xffffffffu, need);
+            while (pending) {
+               const int leader = __ffs(pending) - 1;
+               const int32_t lk0 = __shfl_sync(0xffffffffu, k0, leader), lk1 = __shfl_sync(0xffffffffu, k1, leader);
+               int newId = -1;
+               if ((threadIdx.x & 31) == leader) {
+                  while (atomicCAS(&sLock, 0, 1) != 0) {}
+                  __threadfence_block();
+                  const int c2 = *((volatile int32_t*) &sCount);
+                  for (int g = 0; g < c2; g++)
+                     if (((volatile int32_t*) sKeys[g])[0] == lk0 && ((volatile int32_t*) sKeys[g])[1] == lk1) newId = g;
+                  if (newId < 0 && c2 < LG) {
+                     int32_t kk[2] = {lk0, lk1};
+                     sSlot[c2] = groupLookupOrInsert(p.table, kk);
+                     sKeys[c2][0] = lk0;
+                     sKeys[c2][1] = lk1;
+                     __threadfence_block();
+                     *((volatile int32_t*) &sCount) = c2 + 1;
+                     newId = c2;
                   }
+                  __threadfence_block();
+                  atomicExch(&sLock, 0);
                }
+               newId = __shfl_sync(0xffffffffu, newId, leader);
+               if (need && k0 == lk0 && k1 == lk1) {
+                  id = newId; // -1: the CTA tracks LG groups already → this row goes straight to HBM
+                  need = false;
+               }
+               pending = __ballot_sync(0xffffffffu, need);
+            }
+            if (pass[j] && id >= 0) {
                lastK0 = k0;
                lastK1 = k1;
                lastId = id;
             }
          }
+         if (!pass[j]) continue;
          i128 v[N];
          AL::eval(v, vals[j], one, typename AL::S{});
          if (id >= 0 && id < GREG) {
@@ -356,10 +384,18 @@ static std::string signature(const GroupByParams& p) {
    }
    return s;
 }
+// persistent grid: SMs x resident CTAs of this instantiation (occupancy API), never more than the tiles
+template <class K>
+static int persistentGrid(K kernel, int64_t tiles, int smCount) {
+   int perSm = 1;
+   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kBlock, 0);
+   if (perSm < 1) perSm = 1;
+   return (int) std::min<int64_t>(std::max<int64_t>(tiles, 1), (int64_t) smCount * perSm);
+}
 template <int NK, int NV, int ROWS, class... As>
 static void launchGB(const GroupByParams& p, int smCount, cudaStream_t s) {
    int64_t tiles = (p.src.nRows + (int64_t) kBlock * ROWS - 1) / ((int64_t) kBlock * ROWS);
-   int grid = (int) std::min<int64_t>(std::max<int64_t>(tiles, 1), (int64_t) smCount * 2);
+   int grid = persistentGrid(scanGroupByKernel<NK, NV, ROWS, As...>, tiles, smCount);
    scanGroupByKernel<NK, NV, ROWS, As...><<<grid, kBlock, 0, s>>>(p);
 }
 using C0 = Agg<LDB_EXPR_COL, 0>;
@@ -405,8 +441,10 @@ __global__ void __launch_bounds__(kBlock, 4) scanBuildKernel(const __grid_consta
    const int64_t n = p.src.nRows;
    const int64_t tileRows = (int64_t) kBlock * ROWS;
    for (int64_t base = (int64_t) blockIdx.x * tileRows; base < n; base += (int64_t) gridDim.x * tileRows) {
+      __syncwarp();
       int32_t key[ROWS], pkey[ROWS], pay[ROWS];
       bool pass[ROWS];
+      FilterVals fvals[ROWS];
 #pragma unroll
       for (int j = 0; j < ROWS; j++) {
          int64_t r = base + (int64_t) j * kBlock + threadIdx.x;
@@ -415,8 +453,11 @@ __global__ void __launch_bounds__(kBlock, 4) scanBuildKernel(const __grid_consta
          key[j] = ldStream32(p.keyCol + rr);
          pkey[j] = p.hasProbe ? ldStream32(p.probeKeyCol + rr) : 0;
          pay[j] = p.payloadCol ? ldStream32(p.payloadCol + rr) : 0;
-         pass[j] = valid & evalFilters(p.src.filters, rr);
+         fvals[j] = loadFilters(p.src.filters, rr);
+         pass[j] = valid;
       }
+#pragma unroll
+      for (int j = 0; j < ROWS; j++) pass[j] &= testFilters(p.src.filters, fvals[j]);
 #pragma unroll
       for (int j = 0; j < ROWS; j++) {
          if (!pass[j]) continue;
@@ -438,7 +479,7 @@ __global__ void __launch_bounds__(kBlock, 4) scanBuildKernel(const __grid_consta
 void launchScanBuild(const BuildParams& p, int smCount, cudaStream_t s) {
    constexpr int ROWS = 4;
    int64_t tiles = (p.src.nRows + (int64_t) kBlock * ROWS - 1) / ((int64_t) kBlock * ROWS);
-   int grid = (int) std::min<int64_t>(std::max<int64_t>(tiles, 1), (int64_t) smCount * 4);
+   int grid = persistentGrid(scanBuildKernel<ROWS>, tiles, smCount);
    scanBuildKernel<ROWS><<<grid, kBlock, 0, s>>>(p);
 }
 
@@ -452,9 +493,11 @@ __global__ void __launch_bounds__(kBlock, 4) scanProbeAggKernel(const __grid_con
    const int64_t tileRows = (int64_t) kBlock * ROWS;
    const int64_t one = 100;
    for (int64_t base = (int64_t) blockIdx.x * tileRows; base < n; base += (int64_t) gridDim.x * tileRows) {
+      __syncwarp();
       int32_t key[ROWS];
       int64_t vals[ROWS][NV];
       bool pass[ROWS];
+      FilterVals fvals[ROWS];
 #pragma unroll
       for (int j = 0; j < ROWS; j++) {
          int64_t r = base + (int64_t) j * kBlock + threadIdx.x;
@@ -463,8 +506,11 @@ __global__ void __launch_bounds__(kBlock, 4) scanProbeAggKernel(const __grid_con
          key[j] = ldStream32(p.probeKeyCol + rr);
 #pragma unroll
          for (int c = 0; c < NV; c++) vals[j][c] = ldStream64((const int64_t*) p.valueCols[c] + 2 * rr);
-         pass[j] = valid & evalFilters(p.src.filters, rr);
+         fvals[j] = loadFilters(p.src.filters, rr);
+         pass[j] = valid;
       }
+#pragma unroll
+      for (int j = 0; j < ROWS; j++) pass[j] &= testFilters(p.src.filters, fvals[j]);
 #pragma unroll
       for (int j = 0; j < ROWS; j++) {
          if (!pass[j]) continue;
@@ -479,15 +525,14 @@ __global__ void __launch_bounds__(kBlock, 4) scanProbeAggKernel(const __grid_con
 bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, const char** why) {
    constexpr int ROWS = 4;
    int64_t tiles = (p.src.nRows + (int64_t) kBlock * ROWS - 1) / ((int64_t) kBlock * ROWS);
-   int grid = (int) std::min<int64_t>(std::max<int64_t>(tiles, 1), (int64_t) smCount * 4);
    int nv = p.agg.expr == LDB_EXPR_COL ? 1 : p.agg.expr == LDB_EXPR_MUL_1MINUS_1PLUS ? 3 : 2;
    if (p.agg.col[0] != 0 || (nv > 1 && p.agg.col[1] != 1) || (nv > 2 && p.agg.col[2] != 2)) {
       *why = "probe-aggregate pipeline expects value columns in expression order";
       return false;
    }
-   if (nv == 1) scanProbeAggKernel<1, ROWS><<<grid, kBlock, 0, s>>>(p);
-   else if (nv == 2) scanProbeAggKernel<2, ROWS><<<grid, kBlock, 0, s>>>(p);
-   else scanProbeAggKernel<3, ROWS><<<grid, kBlock, 0, s>>>(p);
+   if (nv == 1) scanProbeAggKernel<1, ROWS><<<persistentGrid(scanProbeAggKernel<1, ROWS>, tiles, smCount), kBlock, 0, s>>>(p);
+   else if (nv == 2) scanProbeAggKernel<2, ROWS><<<persistentGrid(scanProbeAggKernel<2, ROWS>, tiles, smCount), kBlock, 0, s>>>(p);
+   else scanProbeAggKernel<3, ROWS><<<persistentGrid(scanProbeAggKernel<3, ROWS>, tiles, smCount), kBlock, 0, s>>>(p);
    return true;
 }
 
@@ -500,9 +545,11 @@ __global__ void __launch_bounds__(kBlock, 4) scanProbe2GroupByKernel(const __gri
    const int64_t tileRows = (int64_t) kBlock * ROWS;
    const int64_t one = 100;
    for (int64_t base = (int64_t) blockIdx.x * tileRows; base < n; base += (int64_t) gridDim.x * tileRows) {
+      __syncwarp();
       int32_t ka[ROWS], kb[ROWS];
       int64_t vals[ROWS][NV];
       bool pass[ROWS];
+      FilterVals fvals[ROWS];
 #pragma unroll
       for (int j = 0; j < ROWS; j++) {
          int64_t r = base + (int64_t) j * kBlock + threadIdx.x;
@@ -512,8 +559,11 @@ __global__ void __launch_bounds__(kBlock, 4) scanProbe2GroupByKernel(const __gri
          kb[j] = ldStream32(p.keyColB + rr);
 #pragma unroll
          for (int c = 0; c < NV; c++) vals[j][c] = ldStream64((const int64_t*) p.valueCols[c] + 2 * rr);
-         pass[j] = valid & evalFilters(p.src.filters, rr);
+         fvals[j] = loadFilters(p.src.filters, rr);
+         pass[j] = valid;
       }
+#pragma unroll
+      for (int j = 0; j < ROWS; j++) pass[j] &= testFilters(p.src.filters, fvals[j]);
 #pragma unroll
       for (int j = 0; j < ROWS; j++) {
          if (!pass[j]) continue;
@@ -531,15 +581,14 @@ __global__ void __launch_bounds__(kBlock, 4) scanProbe2GroupByKernel(const __gri
 bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStream_t s, const char** why) {
    constexpr int ROWS = 4;
    int64_t tiles = (p.src.nRows + (int64_t) kBlock * ROWS - 1) / ((int64_t) kBlock * ROWS);
-   int grid = (int) std::min<int64_t>(std::max<int64_t>(tiles, 1), (int64_t) smCount * 4);
    int nv = p.agg.expr == LDB_EXPR_COL ? 1 : p.agg.expr == LDB_EXPR_MUL_1MINUS_1PLUS ? 3 : 2;
    if (p.agg.col[0] != 0 || (nv > 1 && p.agg.col[1] != 1) || (nv > 2 && p.agg.col[2] != 2)) {
       *why = "probe-probe-group pipeline expects value columns in expression order";
       return false;
    }
-   if (nv == 1) scanProbe2GroupByKernel<1, ROWS><<<grid, kBlock, 0, s>>>(p);
-   else if (nv == 2) scanProbe2GroupByKernel<2, ROWS><<<grid, kBlock, 0, s>>>(p);
-   else scanProbe2GroupByKernel<3, ROWS><<<grid, kBlock, 0, s>>>(p);
+   if (nv == 1) scanProbe2GroupByKernel<1, ROWS><<<persistentGrid(scanProbe2GroupByKernel<1, ROWS>, tiles, smCount), kBlock, 0, s>>>(p);
+   else if (nv == 2) scanProbe2GroupByKernel<2, ROWS><<<persistentGrid(scanProbe2GroupByKernel<2, ROWS>, tiles, smCount), kBlock, 0, s>>>(p);
+   else scanProbe2GroupByKernel<3, ROWS><<<persistentGrid(scanProbe2GroupByKernel<3, ROWS>, tiles, smCount), kBlock, 0, s>>>(p);
    return true;
 }
 
@@ -562,7 +611,10 @@ __global__ void __launch_bounds__(kBlock) joinTopKKernel(JoinTableDev t, int k, 
    }
    __syncthreads();
    const uint64_t cap = t.mask + 1;
-   for (uint64_t s = (uint64_t) blockIdx.x * kBlock + threadIdx.x; s < cap; s += (uint64_t) gridDim.x * kBlock) {
+   for (uint64_t sBase = (uint64_t) blockIdx.x * kBlock; sBase < cap; sBase += (uint64_t) gridDim.x * kBlock) {
+      __syncwarp(); // CTA-uniform loop: re-converge after the previous iteration's try-lock
+      const uint64_t s = sBase + threadIdx.x;
+      if (s >= cap) continue;
       if (!t.marker[s]) continue;
       unsigned long long e = t.slots[s];
       if (e == kEmptySlot) continue;
@@ -664,6 +716,32 @@ void launchGroupMergeRows(const GroupTableDev& t, const int32_t* keys, const uns
    int total = nRows * t.nAggs;
    int grid = std::max(1, std::min((total + 127) / 128, 256));
    groupMergeRowsKernel<<<grid, 128, 0, s>>>(t, keys, acc, nRows);
+}
+
+// K7 (multi-GPU): fold the all-gathered table images of the other ranks into this rank's table
+__global__ void groupMergeImagesKernel(GroupTableDev t, const uint8_t* images, int nTables, int skip) {
+   const size_t cap = (size_t) t.capacity;
+   const size_t imageBytes = cap * 4 + cap * kMaxKeys * 4 + cap * kMaxAggs * 2 * 8;
+   int total = nTables * t.capacity * t.nAggs;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      int a = i % t.nAggs, slotIdx = (i / t.nAggs) % t.capacity, tab = i / (t.nAggs * t.capacity);
+      if (tab == skip) continue;
+      const uint8_t* img = images + (size_t) tab * imageBytes;
+      const int32_t* st = (const int32_t*) img;
+      if (st[slotIdx] != 2) continue;
+      const int32_t* keys = (const int32_t*) (img + cap * 4) + (size_t) slotIdx * kMaxKeys;
+      const unsigned long long* acc = (const unsigned long long*) (img + cap * 4 + cap * kMaxKeys * 4) + ((size_t) slotIdx * kMaxAggs + a) * 2;
+      int32_t kk[2] = {keys[0], keys[1]};
+      int slot = groupLookupOrInsert(t, kk);
+      if (slot < 0) continue;
+      unsigned long long* dst = t.acc + ((size_t) slot * kMaxAggs + a) * 2;
+      atomicAdd128(dst, dst + 1, i128{acc[0], (int64_t) acc[1]});
+   }
+}
+void launchGroupMergeImages(const GroupTableDev& t, const uint8_t* images, int nTables, int skip, cudaStream_t s) {
+   int total = nTables * t.capacity * t.nAggs;
+   int grid = std::max(1, std::min((total + 127) / 128, 296));
+   groupMergeImagesKernel<<<grid, 128, 0, s>>>(t, images, nTables, skip);
 }
 
 // =================================================================================== K6 radix partition

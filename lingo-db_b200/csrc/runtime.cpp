@@ -446,6 +446,27 @@ int ldb_gpu_groupby_merge_rows(LdbState* s, const LdbGroupRow* rows, int32_t n_r
    });
 }
 
+static size_t groupImageBytes(const GroupTableDev& g) { return (size_t) g.capacity * 4 + (size_t) g.capacity * kMaxKeys * 4 + (size_t) g.capacity * kMaxAggs * 2 * 8; }
+int64_t ldb_gpu_groupby_export_bytes(LdbState* s) { return s ? (int64_t) groupImageBytes(s->group) : 0; }
+int ldb_gpu_groupby_export(LdbState* s, void* dst, LdbError* err) {
+   return guarded(err, [&] {
+      if (!s || (s->kind != LDB_STATE_GROUPBY && s->kind != LDB_STATE_SIMPLE)) fail(LDB_ERR_INVALID, "not a group state");
+      auto& g = s->group;
+      size_t cap = (size_t) g.capacity;
+      uint8_t* d = (uint8_t*) dst;
+      LDB_CUDA(cudaMemcpyAsync(d, g.state, cap * 4, cudaMemcpyDeviceToDevice, s->ctx->compute));
+      LDB_CUDA(cudaMemcpyAsync(d + cap * 4, g.keys, cap * kMaxKeys * 4, cudaMemcpyDeviceToDevice, s->ctx->compute));
+      LDB_CUDA(cudaMemcpyAsync(d + cap * 4 + cap * kMaxKeys * 4, g.acc, cap * kMaxAggs * 2 * 8, cudaMemcpyDeviceToDevice, s->ctx->compute));
+   });
+}
+int ldb_gpu_groupby_merge_exported(LdbState* s, const void* src, int32_t n_tables, int32_t skip_index, LdbError* err) {
+   return guarded(err, [&] {
+      if (!s || (s->kind != LDB_STATE_GROUPBY && s->kind != LDB_STATE_SIMPLE)) fail(LDB_ERR_INVALID, "not a group state");
+      LdbContext* ctx = s->ctx;
+      ctx->launch("group_merge", [&] { launchGroupMergeImages(s->group, (const uint8_t*) src, n_tables, skip_index, ctx->compute); });
+   });
+}
+
 int ldb_gpu_join_table_create(LdbContext* ctx, int64_t expected_rows, int32_t unique_keys, int32_t n_side, int32_t n_aggs, LdbState** out, LdbError* err) {
    return guarded(err, [&] {
       if (!ctx || !out) fail(LDB_ERR_INVALID, "null argument");
