@@ -16,10 +16,24 @@ struct i128 {
    int64_t hi;
 };
 __device__ __forceinline__ i128 make128(int64_t v) { return i128{(uint64_t) v, v >> 63}; }
-__device__ __forceinline__ i128 add128(i128 a, i128 b) {
+__device__ __forceinline__ i128 add128(i128 a, i128 b) { // one carry chain (IADD3 / IADD3.X), no compare+select
    i128 r;
-   r.lo = a.lo + b.lo;
-   r.hi = (int64_t) ((uint64_t) a.hi + (uint64_t) b.hi + (r.lo < a.lo ? 1ull : 0ull));
+   asm("add.cc.u64 %0, %2, %4;\n\taddc.u64 %1, %3, %5;" : "=l"(r.lo), "=l"(r.hi) : "l"(a.lo), "l"(a.hi), "l"(b.lo), "l"(b.hi));
+   return r;
+}
+__device__ __forceinline__ bool fitsI32(int64_t v) { return v == (int64_t) (int32_t) v; }
+// (a * b) * c for operands that fit int32 (c additionally >= 0): three 32x32→64 multiplies instead of the
+// ~25-instruction general 64x64→128 / 128x64 sequence.  Exact; callers take it only when EVERY lane of
+// the warp qualifies (warp-uniform branch), otherwise the general wrapping path runs.
+__device__ __forceinline__ i128 mul32x32(int32_t a, int32_t b) {
+   int64_t p = (int64_t) a * (int64_t) b;
+   return i128{(uint64_t) p, p >> 63};
+}
+__device__ __forceinline__ i128 mul64x32pos(int64_t p, int32_t c) { // p any i64, 0 <= c < 2^31
+   int64_t hiPart = (int64_t) (int32_t) (p >> 32) * (int64_t) c;               // signed high half
+   uint64_t loPart = (uint64_t) (uint32_t) p * (uint64_t) (uint32_t) c;         // unsigned low half
+   i128 r;
+   asm("add.cc.u64 %0, %2, %3;\n\taddc.u64 %1, %4, 0;" : "=l"(r.lo), "=l"(r.hi) : "l"(loPart), "l"((uint64_t) hiPart << 32), "l"((uint64_t) (hiPart >> 32)));
    return r;
 }
 // signed 64 × signed 64 → 128 (exact)
@@ -61,6 +75,39 @@ __device__ __forceinline__ int32_t ldStream32(const int32_t* p) {
 __device__ __forceinline__ int64_t ldStream64(const int64_t* p) {
    int64_t v;
    asm("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
+   return v;
+}
+
+// ---------------------------------------------------------------- TMA bulk copies (cp.async.bulk → SASS UBLKCP) + mbarrier
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbarInitFence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
+   asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n\t}" ::"r"(smemAddr(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global → shared bulk copy, completion counted in bytes on `bar`; src/dst 16-B aligned, bytes % 16 == 0
+__device__ __forceinline__ void bulkLoad(uint32_t dstSmem, const void* src, uint32_t bytes, uint64_t* bar) {
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dstSmem), "l"(src), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ int32_t ldShared32(uint32_t addr) {
+   int32_t v;
+   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+   return v;
+}
+__device__ __forceinline__ int64_t ldShared64(uint32_t addr) {
+   int64_t v;
+   asm volatile("ld.shared.s64 %0, [%1];" : "=l"(v) : "r"(addr));
    return v;
 }
 

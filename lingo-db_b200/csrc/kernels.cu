@@ -22,36 +22,116 @@ namespace ldb {
 
 constexpr int kBlock = 256;
 
-// =================================================================================== filters
-__device__ __forceinline__ int64_t loadFilterValue(const FilterCol& f, int64_t r) {
-   if (f.kind == COL_I32) {
-      return (int64_t) __ldg((const int32_t*) f.base + r);
-   } else if (f.kind == COL_DEC128_LO64) {
-      return __ldg((const long long*) f.base + 2 * r);
-   } else { // COL_UTF8_EQ: 1 if the string equals the constant (VarLen32Filter<Eq>, Restrictions.cpp:279-325)
-      const int32_t* off = (const int32_t*) f.base + r;
-      int32_t b = __ldg(off), e = __ldg(off + 1);
-      if (e - b != f.strLen) return 0;
-      bool eq = true;
-      for (int i = 0; i < f.strLen; i++) eq &= __ldg(f.bytes + b + i) == f.str[i];
-      return eq ? 1 : 0;
+// =================================================================================== tiles
+// A tile = kTileRows consecutive rows of every staged column.  Full tiles arrive in shared memory
+// through TMA bulk copies (one elected thread issues `n` cp.async.bulk per tile; completion is
+// counted in bytes on an mbarrier; 2 stages so the copy of tile t+2 overlaps the arithmetic on
+// tile t+1).  The last partial tile — and tables whose column bases are not 16-byte aligned —
+// are read with plain coalesced loads through the same accessor interface.
+struct SmemTile {
+   uint32_t stage; // shared-space address of the stage
+   const StagedCols* sc;
+   __device__ __forceinline__ int32_t i32(int col, int lr) const { return ldShared32(stage + sc->smemOffset[col] + lr * 4); }
+   __device__ __forceinline__ int64_t lo64(int col, int lr) const { return ldShared64(stage + sc->smemOffset[col] + lr * 16); }
+};
+struct GlobalTile {
+   int64_t rowBase;
+   const StagedCols* sc;
+   __device__ __forceinline__ int32_t i32(int col, int lr) const { return ldStream32((const int32_t*) sc->base[col] + rowBase + lr); }
+   __device__ __forceinline__ int64_t lo64(int col, int lr) const { return ldStream64((const int64_t*) sc->base[col] + 2 * (rowBase + lr)); }
+};
+__device__ __forceinline__ void issueTile(const StagedCols& sc, uint8_t* smem, uint64_t* bars, int64_t tile, int s) {
+   mbarExpectTx(&bars[s], (uint32_t) sc.stageBytes);
+   const uint32_t dst = smemAddr(smem) + (uint32_t) s * sc.stageBytes;
+   for (int c = 0; c < sc.n; c++) {
+      const uint32_t bytes = (uint32_t) sc.elemBytes[c] * kTileRows;
+      bulkLoad(dst + sc.smemOffset[c], sc.base[c] + (size_t) tile * bytes, bytes, &bars[s]);
    }
 }
-// two phases so that every load of a tile is in flight before the first compare consumes one
-struct FilterVals {
-   int64_t v[kMaxFilterCols];
-};
-__device__ __forceinline__ FilterVals loadFilters(const FilterSet& F, int64_t r) {
-   FilterVals fv;
+// fn(tile, localRow, globalRow, valid) is called for every row with all 32 lanes of a warp converged
+// (lanes beyond the end of the table come with valid == false), so fn may use warp collectives.
+template <class Fn>
+__device__ __forceinline__ void forEachRow(const StagedCols& sc, int64_t n, uint8_t* smem, uint64_t* bars, const Fn& fn) {
+   constexpr int kRowsPerThread = kTileRows / kBlock;
+   const int64_t nFull = n / kTileRows;
+   if (sc.useTma) {
+      if (threadIdx.x == 0) {
+         for (int s = 0; s < kStages; s++) mbarInit(&bars[s], 1);
+         mbarInitFence();
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+         for (int s = 0; s < kStages; s++) {
+            int64_t t = (int64_t) blockIdx.x + (int64_t) s * gridDim.x;
+            if (t < nFull) issueTile(sc, smem, bars, t, s);
+         }
+      }
+      int it = 0;
+      for (int64_t t = blockIdx.x; t < nFull; t += gridDim.x, it++) {
+         const int s = it % kStages;
+         mbarWait(&bars[s], (uint32_t) (it / kStages) & 1u);
+         SmemTile tile{smemAddr(smem) + (uint32_t) s * sc.stageBytes, &sc};
 #pragma unroll
-   for (int i = 0; i < kMaxFilterCols; i++) fv.v[i] = i < F.n ? loadFilterValue(F.c[i], r) : 0;
-   return fv;
+         for (int j = 0; j < kRowsPerThread; j++) {
+            const int lr = j * kBlock + threadIdx.x;
+            fn(tile, lr, t * kTileRows + lr, true);
+         }
+         __syncthreads(); // every thread is done with stage s → refill it
+         const int64_t nt = t + (int64_t) kStages * gridDim.x;
+         if (threadIdx.x == 0 && nt < nFull) issueTile(sc, smem, bars, nt, s);
+      }
+   } else {
+      for (int64_t t = blockIdx.x; t < nFull; t += gridDim.x) {
+         __syncwarp();
+         GlobalTile tile{t * kTileRows, &sc};
+#pragma unroll
+         for (int j = 0; j < kRowsPerThread; j++) {
+            const int lr = j * kBlock + threadIdx.x;
+            fn(tile, lr, t * kTileRows + lr, true);
+         }
+      }
+   }
+   // the partial tail tile goes to the CTA that would have been next in the round robin
+   if (nFull * kTileRows < n && (int64_t) blockIdx.x == nFull % gridDim.x) {
+      __syncwarp();
+      GlobalTile tile{nFull * kTileRows, &sc};
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; j++) {
+         const int lr = j * kBlock + threadIdx.x;
+         const bool valid = tile.rowBase + lr < n;
+         fn(tile, valid ? lr : 0, tile.rowBase + (valid ? lr : 0), valid);
+      }
+   }
 }
-__device__ __forceinline__ bool testFilters(const FilterSet& F, const FilterVals& fv) {
+
+// =================================================================================== filters
+// Conjunction of column-vs-constant predicates (Restrictions::applyFilters, Restrictions.cpp:365-390):
+// instead of one compaction pass per filter over a uint16 selection vector, every predicate is
+// evaluated in registers on the staged tile and the row is simply skipped.
+template <class Tile>
+__device__ __forceinline__ bool evalFilters(const FilterSet& F, const Tile& tile, int lr, int64_t row) {
    bool pass = true;
 #pragma unroll
-   for (int i = 0; i < kMaxFilterCols; i++)
-      if (i < F.n) pass &= cmpMask(fv.v[i], F.c[i].valA, F.c[i].maskA) & cmpMask(fv.v[i], F.c[i].valB, F.c[i].maskB);
+   for (int i = 0; i < kMaxFilterCols; i++) {
+      if (i < F.n) {
+         const FilterCol& f = F.c[i];
+         int64_t v;
+         if (f.kind == COL_I32) {
+            v = tile.i32(f.staged, lr);
+         } else if (f.kind == COL_DEC128_LO64) {
+            v = tile.lo64(f.staged, lr);
+         } else { // COL_UTF8_EQ: 1 if the string equals the constant (VarLen32Filter<Eq>, Restrictions.cpp:279-325)
+            const int32_t* off = (const int32_t*) f.base + row;
+            int32_t b = __ldg(off), e = __ldg(off + 1);
+            bool eq = e - b == f.strLen;
+            if (eq)
+               for (int k = 0; k < f.strLen; k++) eq &= __ldg(f.bytes + b + k) == f.str[k];
+            v = eq ? 1 : 0;
+         }
+         pass &= cmpMask(v, f.valA, f.maskA);
+         if (f.maskB != 7u) pass &= cmpMask(v, f.valB, f.maskB);
+      }
+   }
    return pass;
 }
 
@@ -96,7 +176,8 @@ __device__ __forceinline__ void groupAtomicAdd(const GroupTableDev& t, int slot,
 constexpr unsigned long long kEmptySlot = ~0ull;
 constexpr uint64_t kMaxProbe = 16384; // insert reports "table full" beyond this displacement; the host regrows
 __device__ __forceinline__ unsigned long long packSlot(int32_t key, int32_t payload) { return ((unsigned long long) (uint32_t) payload << 32) | (uint32_t) key; }
-// HashIndexedView::build's CAS push-front (LazyJoinHashtable.cpp:20-31) becomes a CAS into an open-addressing slot
+// HashIndexedView::build's CAS push-front (LazyJoinHashtable.cpp:20-31) becomes a CAS into an open-addressing
+// slot.  The caller counts successful inserts (one atomic per warp at kernel end, not one per tuple).
 __device__ int64_t joinInsert(const JoinTableDev& t, int32_t key, int32_t payload) {
    unsigned long long packed = packSlot(key, payload);
    if (packed == kEmptySlot) { // (-1,-1) is the empty marker and cannot be stored
@@ -107,10 +188,7 @@ __device__ int64_t joinInsert(const JoinTableDev& t, int32_t key, int32_t payloa
    const uint64_t limit = t.mask < kMaxProbe ? t.mask + 1 : kMaxProbe; // a sanely loaded table never probes this far
    for (uint64_t probes = 0; probes < limit; probes++) {
       unsigned long long old = atomicCAS(&t.slots[s], kEmptySlot, packed);
-      if (old == kEmptySlot) {
-         atomicAdd(t.count, 1ull);
-         return (int64_t) s;
-      }
+      if (old == kEmptySlot) return (int64_t) s;
       if (t.unique && (int32_t) (uint32_t) old == key) {
          atomicExch(t.error, 2);
          return -1;
@@ -142,33 +220,31 @@ struct Agg {
    static constexpr int expr = E, a = A, b = B, c = C;
    static constexpr bool is64 = (E == LDB_EXPR_COL || E == LDB_EXPR_ONE);
 };
-template <class... As>
-struct AggList {
-   static constexpr int N = sizeof...(As);
-};
-template <int I, class... As>
-struct AggAt;
-template <int I, class A0, class... As>
-struct AggAt<I, A0, As...> : AggAt<I - 1, As...> {};
-template <class A0, class... As>
-struct AggAt<0, A0, As...> {
-   using type = A0;
-};
 
-// typed like the db dialect types them (DBOps.cpp:98-107): `1` is 10^scale of the decimal operand
-template <class A>
+// typed like the db dialect types them (DBOps.cpp:98-107): `1` is 10^scale of the decimal operand.
+// FAST = every lane of the warp has operands that fit int32 (TPC-H money does): 32-bit multiplies.
+template <class A, bool FAST>
 __device__ __forceinline__ i128 evalAgg(const int64_t* v, int64_t one) {
    if constexpr (A::expr == LDB_EXPR_COL) {
       return i128{(uint64_t) v[A::a], 0};
    } else if constexpr (A::expr == LDB_EXPR_MUL) {
-      return mul64x64(v[A::a], v[A::b]);
+      return FAST ? mul32x32((int32_t) v[A::a], (int32_t) v[A::b]) : mul64x64(v[A::a], v[A::b]);
    } else if constexpr (A::expr == LDB_EXPR_MUL_1MINUS) {
-      return mul64x64(v[A::a], one - v[A::b]);
+      return FAST ? mul32x32((int32_t) v[A::a], (int32_t) (one - v[A::b])) : mul64x64(v[A::a], one - v[A::b]);
    } else if constexpr (A::expr == LDB_EXPR_MUL_1MINUS_1PLUS) {
+      if (FAST) return mul64x32pos((int64_t) (int32_t) v[A::a] * (int64_t) (int32_t) (one - v[A::b]), (int32_t) (one + v[A::c]));
       return mul128x64(mul64x64(v[A::a], one - v[A::b]), one + v[A::c]);
    } else {
       return i128{1, 0};
    }
+}
+// operands of one aggregate qualify for the 32-bit path
+template <class A>
+__device__ __forceinline__ bool aggFits32(const int64_t* v, int64_t one) {
+   if constexpr (A::expr == LDB_EXPR_MUL) return fitsI32(v[A::a]) & fitsI32(v[A::b]);
+   else if constexpr (A::expr == LDB_EXPR_MUL_1MINUS) return fitsI32(v[A::a]) & fitsI32(one - v[A::b]);
+   else if constexpr (A::expr == LDB_EXPR_MUL_1MINUS_1PLUS) return fitsI32(v[A::a]) & fitsI32(one - v[A::b]) & fitsI32(one + v[A::c]) & (one + v[A::c] >= 0);
+   else return true;
 }
 __device__ __forceinline__ i128 evalAggDyn(const AggSpec& a, const int64_t* v, int64_t one) {
    switch (a.expr) {
@@ -193,10 +269,11 @@ template <class... As>
 struct Aggs {
    static constexpr int N = sizeof...(As);
    using S = typename MakeSeq<N>::type;
-   template <int... Is>
+   template <bool FAST, int... Is>
    static __device__ __forceinline__ void eval(i128* v, const int64_t* vals, int64_t one, Seq<Is...>) {
-      ((v[Is] = evalAgg<As>(vals, one)), ...);
+      ((v[Is] = evalAgg<As, FAST>(vals, one)), ...);
    }
+   static __device__ __forceinline__ bool fits32(const int64_t* vals, int64_t one) { return (aggFits32<As>(vals, one) & ...); }
    template <int... Is>
    static __device__ __forceinline__ void accumulate(i128* acc, const i128* v, Seq<Is...>) {
       ((As::is64 ? (void) (acc[Is].lo += v[Is].lo) : (void) (acc[Is] = add128(acc[Is], v[Is]))), ...);
@@ -223,13 +300,15 @@ struct Aggs {
    }
 };
 
+extern __shared__ __align__(128) uint8_t dynSmem[];
+
 // =================================================================================== K1 / K2
 // scan → filters → group by NK int32 keys → SUMs.  NK == 0 is the keyless form (Q6, SimpleState).
 // Hot groups (the first GREG a CTA meets) accumulate in REGISTERS with predicated adds — the
 // reference's 1024-slot per-worker pre-aggregation cache (PreAggregationHashtable.cpp:46-60) collapses to
 // this for small domains; further groups use shared-memory atomics, and only a CTA that meets
 // more than LG groups touches the HBM table per row.  One flush per CTA at the end.
-template <int NK, int NV, int ROWS, class... As>
+template <int NK, int NV, class... As>
 __global__ void __launch_bounds__(kBlock, 2) scanGroupByKernel(const __grid_constant__ GroupByParams p) {
    using AL = Aggs<As...>;
    constexpr int N = AL::N;
@@ -239,6 +318,7 @@ __global__ void __launch_bounds__(kBlock, 2) scanGroupByKernel(const __grid_cons
    __shared__ int32_t sSlot[LG];
    __shared__ int32_t sCount, sLock;
    __shared__ unsigned long long sAcc[LG][N][2];
+   __shared__ __align__(8) uint64_t bars[kStages];
 
    for (int i = threadIdx.x; i < LG * N * 2; i += kBlock) (&sAcc[0][0][0])[i] = 0;
    if (threadIdx.x == 0) {
@@ -253,107 +333,88 @@ __global__ void __launch_bounds__(kBlock, 2) scanGroupByKernel(const __grid_cons
    for (int g = 0; g < GREG; g++)
 #pragma unroll
       for (int a = 0; a < N; a++) acc[g][a] = i128{0, 0};
-
-   const int64_t n = p.src.nRows;
-   const int64_t tileRows = (int64_t) kBlock * ROWS;
    const int64_t one = 100; // 10^scale of decimal(12,2); checked on the host
    int32_t lastK0 = 0, lastK1 = 0, lastId = -2;
 
-   for (int64_t base = (int64_t) blockIdx.x * tileRows; base < n; base += (int64_t) gridDim.x * tileRows) {
-      __syncwarp(); // the tile loop is CTA-uniform: re-converge whatever the previous tile's row branches left
-      int64_t vals[ROWS][NV];
-      int32_t keys[ROWS][NK == 0 ? 1 : NK];
-      bool pass[ROWS];
-      FilterVals fvals[ROWS];
-      // ---- issue every load of the tile first
+   forEachRow(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
+      int64_t vals[NV];
 #pragma unroll
-      for (int j = 0; j < ROWS; j++) {
-         int64_t r = base + (int64_t) j * kBlock + threadIdx.x;
-         bool valid = r < n;
-         int64_t rr = valid ? r : n - 1;
-#pragma unroll
-         for (int c = 0; c < NV; c++) vals[j][c] = ldStream64((const int64_t*) p.valueCols[c] + 2 * rr);
-#pragma unroll
-         for (int k = 0; k < NK; k++) keys[j][k] = ldStream32(p.keyCols[k] + rr);
-         fvals[j] = loadFilters(p.src.filters, rr);
-         pass[j] = valid;
-      }
-#pragma unroll
-      for (int j = 0; j < ROWS; j++) pass[j] &= testFilters(p.src.filters, fvals[j]);
-      // ---- per row: group id, expression, accumulate
-#pragma unroll
-      for (int j = 0; j < ROWS; j++) {
-         int id = 0;
-         if constexpr (NK > 0) {
-            // Resolve the CTA-local group id under WARP-UNIFORM control flow.  (A per-lane spin lock
-            // here once left the warps permanently diverged: 1 active thread per instruction, 40x
-            // the instructions and 12x the DRAM traffic — profiles/r1_q1_first.md.)
-            const int32_t k0 = keys[j][0], k1 = NK > 1 ? keys[j][NK - 1] : 0;
-            id = -1;
-            bool need = pass[j];
-            if (need && lastId >= 0 && k0 == lastK0 && k1 == lastK1) {
-               id = lastId;
+      for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lr);
+      int32_t k0 = 0, k1 = 0;
+      if constexpr (NK > 0) k0 = tile.i32(p.keyStage[0], lr);
+      if constexpr (NK > 1) k1 = tile.i32(p.keyStage[1], lr);
+      const bool pass = valid & evalFilters(p.src.filters, tile, lr, row);
+      int id = 0;
+      if constexpr (NK > 0) {
+         // Resolve the CTA-local group id under WARP-UNIFORM control flow.  (A per-lane spin lock
+         // here once left the warps permanently diverged: 1 active thread per instruction, 40x
+         // the instructions and 12x the DRAM traffic — profiles/r1_q1_first.md.)
+         id = -1;
+         bool need = pass;
+         if (need && lastId >= 0 && k0 == lastK0 && k1 == lastK1) {
+            id = lastId;
+            need = false;
+         }
+         if (need) {
+            const int cnt = *((volatile int32_t*) &sCount);
+            for (int g = 0; g < cnt; g++)
+               if (sKeys[g][0] == k0 && sKeys[g][1] == k1) id = g;
+            need = id < 0;
+         }
+         // first sight of a key in this CTA: one elected lane registers it under the CTA lock
+         unsigned pending = __ballot_sync(0xffffffffu, need);
+         while (pending) {
+            const int leader = __ffs(pending) - 1;
+            const int32_t lk0 = __shfl_sync(0xffffffffu, k0, leader), lk1 = __shfl_sync(0xffffffffu, k1, leader);
+            int newId = -1;
+            if ((threadIdx.x & 31) == leader) {
+               while (atomicCAS(&sLock, 0, 1) != 0) {}
+               __threadfence_block();
+               const int c2 = *((volatile int32_t*) &sCount);
+               for (int g = 0; g < c2; g++)
+                  if (((volatile int32_t*) sKeys[g])[0] == lk0 && ((volatile int32_t*) sKeys[g])[1] == lk1) newId = g;
+               if (newId < 0 && c2 < LG) {
+                  int32_t kk[2] = {lk0, lk1};
+                  sSlot[c2] = groupLookupOrInsert(p.table, kk);
+                  sKeys[c2][0] = lk0;
+                  sKeys[c2][1] = lk1;
+                  __threadfence_block();
+                  *((volatile int32_t*) &sCount) = c2 + 1;
+                  newId = c2;
+               }
+               __threadfence_block();
+               atomicExch(&sLock, 0);
+            }
+            newId = __shfl_sync(0xffffffffu, newId, leader);
+            if (need && k0 == lk0 && k1 == lk1) {
+               id = newId; // -1: the CTA tracks LG groups already → this row goes straight to HBM
                need = false;
             }
-            if (need) {
-               const int cnt = *((volatile int32_t*) &sCount);
-               for (int g = 0; g < cnt; g++)
-                  if (sKeys[g][0] == k0 && sKeys[g][1] == k1) id = g;
-               need = id < 0;
-            }
-            // first sight of a key in this CTA: one elected lane registers it under the CTA lock
-            unsigned pending = __ballot_sync(0xffffffffu, need);
-            while (pending) {
-               const int leader = __ffs(pending) - 1;
-               const int32_t lk0 = __shfl_sync(0xffffffffu, k0, leader), lk1 = __shfl_sync(0xffffffffu, k1, leader);
-               int newId = -1;
-               if ((threadIdx.x & 31) == leader) {
-                  while (atomicCAS(&sLock, 0, 1) != 0) {}
-                  __threadfence_block();
-                  const int c2 = *((volatile int32_t*) &sCount);
-                  for (int g = 0; g < c2; g++)
-                     if (((volatile int32_t*) sKeys[g])[0] == lk0 && ((volatile int32_t*) sKeys[g])[1] == lk1) newId = g;
-                  if (newId < 0 && c2 < LG) {
-                     int32_t kk[2] = {lk0, lk1};
-                     sSlot[c2] = groupLookupOrInsert(p.table, kk);
-                     sKeys[c2][0] = lk0;
-                     sKeys[c2][1] = lk1;
-                     __threadfence_block();
-                     *((volatile int32_t*) &sCount) = c2 + 1;
-                     newId = c2;
-                  }
-                  __threadfence_block();
-                  atomicExch(&sLock, 0);
-               }
-               newId = __shfl_sync(0xffffffffu, newId, leader);
-               if (need && k0 == lk0 && k1 == lk1) {
-                  id = newId; // -1: the CTA tracks LG groups already → this row goes straight to HBM
-                  need = false;
-               }
-               pending = __ballot_sync(0xffffffffu, need);
-            }
-            if (pass[j] && id >= 0) {
-               lastK0 = k0;
-               lastK1 = k1;
-               lastId = id;
-            }
+            pending = __ballot_sync(0xffffffffu, need);
          }
-         if (!pass[j]) continue;
-         i128 v[N];
-         AL::eval(v, vals[j], one, typename AL::S{});
-         if (id >= 0 && id < GREG) {
-#pragma unroll
-            for (int g = 0; g < GREG; g++)
-               if (id == g) AL::accumulate(acc[g], v, typename AL::S{});
-         } else if (id >= 0) { // CTA-local but not register resident: shared-memory atomics
-            AL::sharedAdd(sAcc[id], v, typename AL::S{});
-         } else { // more groups than a CTA tracks: straight to the HBM table
-            int32_t kk[2] = {keys[j][0], NK > 1 ? keys[j][NK - 1] : 0};
-            int slot = groupLookupOrInsert(p.table, kk);
-            if (slot >= 0) AL::globalAdd(p.table, slot, v, typename AL::S{});
+         if (pass && id >= 0) {
+            lastK0 = k0;
+            lastK1 = k1;
+            lastId = id;
          }
       }
-   }
+      // expressions: 32-bit multiplies when every lane's operands allow it, else the general i128 path
+      i128 v[N];
+      if (__all_sync(0xffffffffu, !pass || AL::fits32(vals, one))) AL::template eval<true>(v, vals, one, typename AL::S{});
+      else AL::template eval<false>(v, vals, one, typename AL::S{});
+      if (!pass) return;
+      if (id >= 0 && id < GREG) {
+#pragma unroll
+         for (int g = 0; g < GREG; g++)
+            if (id == g) AL::accumulate(acc[g], v, typename AL::S{});
+      } else if (id >= 0) { // CTA-local but not register resident: shared-memory atomics
+         AL::sharedAdd(sAcc[id], v, typename AL::S{});
+      } else { // more groups than a CTA tracks: straight to the HBM table
+         int32_t kk[2] = {k0, k1};
+         int slot = groupLookupOrInsert(p.table, kk);
+         if (slot >= 0) AL::globalAdd(p.table, slot, v, typename AL::S{});
+      }
+   });
    // ---- flush: registers → warp sums → shared → one HBM atomic per (CTA, group, aggregate)
    __syncthreads();
    const int lane = threadIdx.x & 31;
@@ -386,17 +447,20 @@ static std::string signature(const GroupByParams& p) {
 }
 // persistent grid: SMs x resident CTAs of this instantiation (occupancy API), never more than the tiles
 template <class K>
-static int persistentGrid(K kernel, int64_t tiles, int smCount) {
+static int persistentGrid(K kernel, const StagedCols& sc, int64_t nRows, int smCount, size_t* dynBytes) {
+   *dynBytes = sc.useTma ? (size_t) kStages * sc.stageBytes : 0;
+   if (*dynBytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) *dynBytes);
    int perSm = 1;
-   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kBlock, 0);
+   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kBlock, *dynBytes);
    if (perSm < 1) perSm = 1;
+   int64_t tiles = (nRows + kTileRows - 1) / kTileRows;
    return (int) std::min<int64_t>(std::max<int64_t>(tiles, 1), (int64_t) smCount * perSm);
 }
-template <int NK, int NV, int ROWS, class... As>
+template <int NK, int NV, class... As>
 static void launchGB(const GroupByParams& p, int smCount, cudaStream_t s) {
-   int64_t tiles = (p.src.nRows + (int64_t) kBlock * ROWS - 1) / ((int64_t) kBlock * ROWS);
-   int grid = persistentGrid(scanGroupByKernel<NK, NV, ROWS, As...>, tiles, smCount);
-   scanGroupByKernel<NK, NV, ROWS, As...><<<grid, kBlock, 0, s>>>(p);
+   size_t dyn;
+   int grid = persistentGrid(scanGroupByKernel<NK, NV, As...>, p.src.cols, p.src.nRows, smCount, &dyn);
+   scanGroupByKernel<NK, NV, As...><<<grid, kBlock, dyn, s>>>(p);
 }
 using C0 = Agg<LDB_EXPR_COL, 0>;
 using C1 = Agg<LDB_EXPR_COL, 1>;
@@ -406,23 +470,23 @@ bool launchScanGroupBy(const GroupByParams& p, int smCount, cudaStream_t s, cons
    std::string sig = signature(p);
    // Q1 pricing summary: sum(a) sum(b) sum(b*(1-c)) sum(b*(1-c)*(1+d)) sum(c) count   (resources/sql/tpch/1.sql)
    if (sig == "k2v4|0:0|0:1|2:1,2|3:1,2,3|0:2|4") {
-      launchGB<2, 4, 2, C0, C1, Agg<LDB_EXPR_MUL_1MINUS, 1, 2>, Agg<LDB_EXPR_MUL_1MINUS_1PLUS, 1, 2, 3>, C2, ONE>(p, smCount, s);
+      launchGB<2, 4, C0, C1, Agg<LDB_EXPR_MUL_1MINUS, 1, 2>, Agg<LDB_EXPR_MUL_1MINUS_1PLUS, 1, 2, 3>, C2, ONE>(p, smCount, s);
    } else if (sig == "k1v4|0:0|0:1|2:1,2|3:1,2,3|0:2|4") {
-      launchGB<1, 4, 2, C0, C1, Agg<LDB_EXPR_MUL_1MINUS, 1, 2>, Agg<LDB_EXPR_MUL_1MINUS_1PLUS, 1, 2, 3>, C2, ONE>(p, smCount, s);
+      launchGB<1, 4, C0, C1, Agg<LDB_EXPR_MUL_1MINUS, 1, 2>, Agg<LDB_EXPR_MUL_1MINUS_1PLUS, 1, 2, 3>, C2, ONE>(p, smCount, s);
    } else if (sig == "k0v2|1:0,1") { // Q6 forecast revenue: sum(a*b)
-      launchGB<0, 2, 4, Agg<LDB_EXPR_MUL, 0, 1>>(p, smCount, s);
+      launchGB<0, 2, Agg<LDB_EXPR_MUL, 0, 1>>(p, smCount, s);
    } else if (sig == "k0v2|2:0,1") { // keyless sum(a*(1-b))
-      launchGB<0, 2, 4, Agg<LDB_EXPR_MUL_1MINUS, 0, 1>>(p, smCount, s);
+      launchGB<0, 2, Agg<LDB_EXPR_MUL_1MINUS, 0, 1>>(p, smCount, s);
    } else if (sig == "k0v1|0:0|4") { // keyless sum(a), count
-      launchGB<0, 1, 4, C0, ONE>(p, smCount, s);
+      launchGB<0, 1, C0, ONE>(p, smCount, s);
    } else if (sig == "k1v2|2:0,1") { // group by k: sum(a*(1-b))
-      launchGB<1, 2, 4, Agg<LDB_EXPR_MUL_1MINUS, 0, 1>>(p, smCount, s);
+      launchGB<1, 2, Agg<LDB_EXPR_MUL_1MINUS, 0, 1>>(p, smCount, s);
    } else if (sig == "k2v2|2:0,1") {
-      launchGB<2, 2, 4, Agg<LDB_EXPR_MUL_1MINUS, 0, 1>>(p, smCount, s);
+      launchGB<2, 2, Agg<LDB_EXPR_MUL_1MINUS, 0, 1>>(p, smCount, s);
    } else if (sig == "k1v1|0:0|4") { // group by k: sum(a), count
-      launchGB<1, 1, 4, C0, ONE>(p, smCount, s);
+      launchGB<1, 1, C0, ONE>(p, smCount, s);
    } else if (sig == "k2v1|0:0|4") {
-      launchGB<2, 1, 4, C0, ONE>(p, smCount, s);
+      launchGB<2, 1, C0, ONE>(p, smCount, s);
    } else {
       static thread_local std::string msg;
       msg = "no compiled group-by pipeline for aggregate signature '" + sig + "' (register it in kernels.cu:launchScanGroupBy)";
@@ -432,163 +496,124 @@ bool launchScanGroupBy(const GroupByParams& p, int smCount, cudaStream_t s, cons
    return true;
 }
 
+// one atomic per warp for the build-side entry count
+__device__ __forceinline__ void flushInsertCount(const JoinTableDev& t, unsigned long long local) {
+   __syncwarp();
+   unsigned long long total = warpSum64(local);
+   if ((threadIdx.x & 31) == 0 && total) atomicAdd(t.count, total);
+}
+
 // =================================================================================== K3 build
 // scan → filters → [probe parent table] → insert {key, payload, side…}
 // (subop.materialize + rt::GrowingBuffer::insert + rt::HashIndexedView::build; for the group-join
 //  the lookup_or_insert of the left input, RelAlgToSubOp.cpp:2682-2950)
-template <int ROWS>
 __global__ void __launch_bounds__(kBlock, 4) scanBuildKernel(const __grid_constant__ BuildParams p) {
-   const int64_t n = p.src.nRows;
-   const int64_t tileRows = (int64_t) kBlock * ROWS;
-   for (int64_t base = (int64_t) blockIdx.x * tileRows; base < n; base += (int64_t) gridDim.x * tileRows) {
-      __syncwarp();
-      int32_t key[ROWS], pkey[ROWS], pay[ROWS];
-      bool pass[ROWS];
-      FilterVals fvals[ROWS];
-#pragma unroll
-      for (int j = 0; j < ROWS; j++) {
-         int64_t r = base + (int64_t) j * kBlock + threadIdx.x;
-         bool valid = r < n;
-         int64_t rr = valid ? r : n - 1;
-         key[j] = ldStream32(p.keyCol + rr);
-         pkey[j] = p.hasProbe ? ldStream32(p.probeKeyCol + rr) : 0;
-         pay[j] = p.payloadCol ? ldStream32(p.payloadCol + rr) : 0;
-         fvals[j] = loadFilters(p.src.filters, rr);
-         pass[j] = valid;
-      }
-#pragma unroll
-      for (int j = 0; j < ROWS; j++) pass[j] &= testFilters(p.src.filters, fvals[j]);
-#pragma unroll
-      for (int j = 0; j < ROWS; j++) {
-         if (!pass[j]) continue;
-         int64_t r = base + (int64_t) j * kBlock + threadIdx.x;
-         auto insert = [&](int32_t payload) {
-            int64_t slot = joinInsert(p.sink, key[j], payload);
-            if (slot >= 0) {
-               for (int k = 0; k < p.nSide; k++) p.sink.side[k][slot] = __ldg(p.sideCols[k] + r);
-            }
-         };
-         if (p.hasProbe) {
-            joinProbe(p.probe, pkey[j], [&](int64_t, int32_t parentPayload) { insert(p.payloadCol ? pay[j] : parentPayload); });
-         } else {
-            insert(pay[j]);
+   __shared__ __align__(8) uint64_t bars[kStages];
+   unsigned long long inserted = 0;
+   forEachRow(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
+      if (!(valid && evalFilters(p.src.filters, tile, lr, row))) return;
+      const int32_t key = tile.i32(p.keyStage, lr);
+      auto insert = [&](int32_t payload) {
+         int64_t slot = joinInsert(p.sink, key, payload);
+         if (slot >= 0) {
+            inserted++;
+            for (int k = 0; k < p.nSide; k++) p.sink.side[k][slot] = tile.i32(p.sideStage[k], lr);
          }
+      };
+      const int32_t ownPayload = p.payloadStage >= 0 ? tile.i32(p.payloadStage, lr) : 0;
+      if (p.hasProbe) {
+         joinProbe(p.probe, tile.i32(p.probeKeyStage, lr), [&](int64_t, int32_t parentPayload) { insert(p.payloadStage >= 0 ? ownPayload : parentPayload); });
+      } else {
+         insert(ownPayload);
       }
-   }
+   });
+   flushInsertCount(p.sink, inserted);
 }
 void launchScanBuild(const BuildParams& p, int smCount, cudaStream_t s) {
-   constexpr int ROWS = 4;
-   int64_t tiles = (p.src.nRows + (int64_t) kBlock * ROWS - 1) / ((int64_t) kBlock * ROWS);
-   int grid = persistentGrid(scanBuildKernel<ROWS>, tiles, smCount);
-   scanBuildKernel<ROWS><<<grid, kBlock, 0, s>>>(p);
+   size_t dyn;
+   int grid = persistentGrid(scanBuildKernel, p.src.cols, p.src.nRows, smCount, &dyn);
+   scanBuildKernel<<<grid, kBlock, dyn, s>>>(p);
 }
 
 // =================================================================================== K5 probe + aggregate
 // scan → filters → pure lookup in the group-join map → SUM into the shared entry.  The reference
 // takes a per-entry spin lock (SubOpToControlFlow.cpp:4218-4251, EntryLock.cpp:9-25) or an
 // atomic_rmw; here the i128 SUM is two 64-bit atomics with carry (exact, order independent).
-template <int NV, int ROWS>
+template <int NV>
 __global__ void __launch_bounds__(kBlock, 4) scanProbeAggKernel(const __grid_constant__ ProbeAggParams p) {
-   const int64_t n = p.src.nRows;
-   const int64_t tileRows = (int64_t) kBlock * ROWS;
+   __shared__ __align__(8) uint64_t bars[kStages];
    const int64_t one = 100;
-   for (int64_t base = (int64_t) blockIdx.x * tileRows; base < n; base += (int64_t) gridDim.x * tileRows) {
-      __syncwarp();
-      int32_t key[ROWS];
-      int64_t vals[ROWS][NV];
-      bool pass[ROWS];
-      FilterVals fvals[ROWS];
+   forEachRow(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
+      if (!(valid && evalFilters(p.src.filters, tile, lr, row))) return;
+      joinProbe(p.table, tile.i32(p.probeKeyStage, lr), [&](int64_t slot, int32_t) {
+         int64_t vals[NV];
 #pragma unroll
-      for (int j = 0; j < ROWS; j++) {
-         int64_t r = base + (int64_t) j * kBlock + threadIdx.x;
-         bool valid = r < n;
-         int64_t rr = valid ? r : n - 1;
-         key[j] = ldStream32(p.probeKeyCol + rr);
-#pragma unroll
-         for (int c = 0; c < NV; c++) vals[j][c] = ldStream64((const int64_t*) p.valueCols[c] + 2 * rr);
-         fvals[j] = loadFilters(p.src.filters, rr);
-         pass[j] = valid;
-      }
-#pragma unroll
-      for (int j = 0; j < ROWS; j++) pass[j] &= testFilters(p.src.filters, fvals[j]);
-#pragma unroll
-      for (int j = 0; j < ROWS; j++) {
-         if (!pass[j]) continue;
-         joinProbe(p.table, key[j], [&](int64_t slot, int32_t) {
-            i128 v = evalAggDyn(p.agg, vals[j], one);
-            atomicAdd128(&p.table.aggLo[slot], &p.table.aggHi[slot], v);
-            p.table.marker[slot] = 1;
-         });
-      }
-   }
+         for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lr);
+         i128 v = evalAggDyn(p.agg, vals, one);
+         atomicAdd128(&p.table.aggLo[slot], &p.table.aggHi[slot], v);
+         p.table.marker[slot] = 1;
+      });
+   });
 }
 bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, const char** why) {
-   constexpr int ROWS = 4;
-   int64_t tiles = (p.src.nRows + (int64_t) kBlock * ROWS - 1) / ((int64_t) kBlock * ROWS);
    int nv = p.agg.expr == LDB_EXPR_COL ? 1 : p.agg.expr == LDB_EXPR_MUL_1MINUS_1PLUS ? 3 : 2;
    if (p.agg.col[0] != 0 || (nv > 1 && p.agg.col[1] != 1) || (nv > 2 && p.agg.col[2] != 2)) {
       *why = "probe-aggregate pipeline expects value columns in expression order";
       return false;
    }
-   if (nv == 1) scanProbeAggKernel<1, ROWS><<<persistentGrid(scanProbeAggKernel<1, ROWS>, tiles, smCount), kBlock, 0, s>>>(p);
-   else if (nv == 2) scanProbeAggKernel<2, ROWS><<<persistentGrid(scanProbeAggKernel<2, ROWS>, tiles, smCount), kBlock, 0, s>>>(p);
-   else scanProbeAggKernel<3, ROWS><<<persistentGrid(scanProbeAggKernel<3, ROWS>, tiles, smCount), kBlock, 0, s>>>(p);
+   size_t dyn;
+   if (nv == 1) {
+      int grid = persistentGrid(scanProbeAggKernel<1>, p.src.cols, p.src.nRows, smCount, &dyn);
+      scanProbeAggKernel<1><<<grid, kBlock, dyn, s>>>(p);
+   } else if (nv == 2) {
+      int grid = persistentGrid(scanProbeAggKernel<2>, p.src.cols, p.src.nRows, smCount, &dyn);
+      scanProbeAggKernel<2><<<grid, kBlock, dyn, s>>>(p);
+   } else {
+      int grid = persistentGrid(scanProbeAggKernel<3>, p.src.cols, p.src.nRows, smCount, &dyn);
+      scanProbeAggKernel<3><<<grid, kBlock, dyn, s>>>(p);
+   }
    return true;
 }
 
 // =================================================================================== K4 probe, probe, group
 // scan → probe A on keyA → probe B on keyB → keep rows whose payloads agree (the composite join key
 // (l_suppkey, c_nationkey) = (s_suppkey, s_nationkey) of Q5) → group by that payload → SUM.
-template <int NV, int ROWS>
+template <int NV>
 __global__ void __launch_bounds__(kBlock, 4) scanProbe2GroupByKernel(const __grid_constant__ Probe2GroupByParams p) {
-   const int64_t n = p.src.nRows;
-   const int64_t tileRows = (int64_t) kBlock * ROWS;
+   __shared__ __align__(8) uint64_t bars[kStages];
    const int64_t one = 100;
-   for (int64_t base = (int64_t) blockIdx.x * tileRows; base < n; base += (int64_t) gridDim.x * tileRows) {
-      __syncwarp();
-      int32_t ka[ROWS], kb[ROWS];
-      int64_t vals[ROWS][NV];
-      bool pass[ROWS];
-      FilterVals fvals[ROWS];
+   forEachRow(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
+      if (!(valid && evalFilters(p.src.filters, tile, lr, row))) return;
+      joinProbe(p.tableA, tile.i32(p.keyStageA, lr), [&](int64_t, int32_t payA) {
+         joinProbe(p.tableB, tile.i32(p.keyStageB, lr), [&](int64_t, int32_t payB) {
+            if (payA != payB) return;
+            int64_t vals[NV];
 #pragma unroll
-      for (int j = 0; j < ROWS; j++) {
-         int64_t r = base + (int64_t) j * kBlock + threadIdx.x;
-         bool valid = r < n;
-         int64_t rr = valid ? r : n - 1;
-         ka[j] = ldStream32(p.keyColA + rr);
-         kb[j] = ldStream32(p.keyColB + rr);
-#pragma unroll
-         for (int c = 0; c < NV; c++) vals[j][c] = ldStream64((const int64_t*) p.valueCols[c] + 2 * rr);
-         fvals[j] = loadFilters(p.src.filters, rr);
-         pass[j] = valid;
-      }
-#pragma unroll
-      for (int j = 0; j < ROWS; j++) pass[j] &= testFilters(p.src.filters, fvals[j]);
-#pragma unroll
-      for (int j = 0; j < ROWS; j++) {
-         if (!pass[j]) continue;
-         joinProbe(p.tableA, ka[j], [&](int64_t, int32_t payA) {
-            joinProbe(p.tableB, kb[j], [&](int64_t, int32_t payB) {
-               if (payA != payB) return;
-               int32_t kk[2] = {payB, 0};
-               int slot = groupLookupOrInsert(p.groups, kk);
-               if (slot >= 0) groupAtomicAdd(p.groups, slot, 0, evalAggDyn(p.agg, vals[j], one), p.agg.expr == LDB_EXPR_COL || p.agg.expr == LDB_EXPR_ONE);
-            });
+            for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lr);
+            int32_t kk[2] = {payB, 0};
+            int slot = groupLookupOrInsert(p.groups, kk);
+            if (slot >= 0) groupAtomicAdd(p.groups, slot, 0, evalAggDyn(p.agg, vals, one), p.agg.expr == LDB_EXPR_COL || p.agg.expr == LDB_EXPR_ONE);
          });
-      }
-   }
+      });
+   });
 }
 bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStream_t s, const char** why) {
-   constexpr int ROWS = 4;
-   int64_t tiles = (p.src.nRows + (int64_t) kBlock * ROWS - 1) / ((int64_t) kBlock * ROWS);
    int nv = p.agg.expr == LDB_EXPR_COL ? 1 : p.agg.expr == LDB_EXPR_MUL_1MINUS_1PLUS ? 3 : 2;
    if (p.agg.col[0] != 0 || (nv > 1 && p.agg.col[1] != 1) || (nv > 2 && p.agg.col[2] != 2)) {
       *why = "probe-probe-group pipeline expects value columns in expression order";
       return false;
    }
-   if (nv == 1) scanProbe2GroupByKernel<1, ROWS><<<persistentGrid(scanProbe2GroupByKernel<1, ROWS>, tiles, smCount), kBlock, 0, s>>>(p);
-   else if (nv == 2) scanProbe2GroupByKernel<2, ROWS><<<persistentGrid(scanProbe2GroupByKernel<2, ROWS>, tiles, smCount), kBlock, 0, s>>>(p);
-   else scanProbe2GroupByKernel<3, ROWS><<<persistentGrid(scanProbe2GroupByKernel<3, ROWS>, tiles, smCount), kBlock, 0, s>>>(p);
+   size_t dyn;
+   if (nv == 1) {
+      int grid = persistentGrid(scanProbe2GroupByKernel<1>, p.src.cols, p.src.nRows, smCount, &dyn);
+      scanProbe2GroupByKernel<1><<<grid, kBlock, dyn, s>>>(p);
+   } else if (nv == 2) {
+      int grid = persistentGrid(scanProbe2GroupByKernel<2>, p.src.cols, p.src.nRows, smCount, &dyn);
+      scanProbe2GroupByKernel<2><<<grid, kBlock, dyn, s>>>(p);
+   } else {
+      int grid = persistentGrid(scanProbe2GroupByKernel<3>, p.src.cols, p.src.nRows, smCount, &dyn);
+      scanProbe2GroupByKernel<3><<<grid, kBlock, dyn, s>>>(p);
+   }
    return true;
 }
 
@@ -677,13 +702,16 @@ void launchFill64(unsigned long long* p, unsigned long long v, int64_t n, cudaSt
    fill64Kernel<<<grid, 256, 0, s>>>(p, v, n);
 }
 __global__ void insertTuplesKernel(JoinTableDev t, const int32_t* keys, const int32_t* payloads, const int32_t* side0, const int32_t* side1, int64_t n) {
+   unsigned long long inserted = 0;
    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
       int64_t slot = joinInsert(t, keys[i], payloads ? payloads[i] : 0);
       if (slot >= 0) {
+         inserted++;
          if (side0) t.side[0][slot] = side0[i];
          if (side1) t.side[1][slot] = side1[i];
       }
    }
+   flushInsertCount(t, inserted);
 }
 void launchInsertTuples(const JoinTableDev& t, const int32_t* keys, const int32_t* payloads, const int32_t* side0, const int32_t* side1, int64_t n, int smCount, cudaStream_t s) {
    int grid = (int) std::min<int64_t>(std::max<int64_t>((n + 255) / 256, 1), (int64_t) smCount * 8);

@@ -17,9 +17,10 @@ enum ColKind : int32_t { COL_I32 = 0, COL_DEC128_LO64 = 1, COL_UTF8_EQ = 2 };
 // One pushed-down filter column with up to two predicates (e.g. a range); op masks as in cmpMask().
 // utf8 columns evaluate `string == constant` to 1/0 first, then compare that to valA (1).
 struct FilterCol {
-   const void* base;     // values (int32 / decimal128) or utf8 offsets
+   const void* base;     // utf8 only: offsets (fixed-width columns are read through the staged tile)
    const uint8_t* bytes; // utf8 data
    int32_t kind;
+   int32_t staged;       // index into StagedCols (fixed-width columns), -1 for utf8
    uint32_t maskA, maskB;
    int64_t valA, valB;
    uint8_t str[24];
@@ -53,8 +54,23 @@ struct JoinTableDev {
    int32_t unique;
 };
 
+// The distinct fixed-width columns a pipeline touches.  Every scan kernel streams them tile by tile
+// (kTileRows rows) into shared memory with TMA bulk copies (cp.async.bulk + mbarrier, 2 stages), so
+// each column byte crosses HBM→SM exactly once and no per-row global address arithmetic is issued.
+constexpr int kMaxStagedCols = 8;
+constexpr int kTileRows = 512;
+constexpr int kStages = 2;
+struct StagedCols {
+   int32_t n;
+   int32_t stageBytes; // bytes of one stage = sum(elemBytes) * kTileRows
+   int32_t useTma;     // 0 when a column base is not 16-byte aligned: tiles are then read with plain loads
+   const uint8_t* base[kMaxStagedCols];
+   int32_t elemBytes[kMaxStagedCols];  // 4 (int32/date32/fsb4) or 16 (decimal128)
+   int32_t smemOffset[kMaxStagedCols]; // offset of the column inside a stage
+};
 struct ScanSource {
    int64_t nRows;
+   StagedCols cols;
    FilterSet filters;
 };
 
@@ -66,9 +82,9 @@ struct AggSpec {
 struct GroupByParams {
    ScanSource src;
    int32_t nKeys;
-   const int32_t* keyCols[kMaxKeys];
+   int32_t keyStage[kMaxKeys];        // staged-column indices
    int32_t nValueCols;
-   const void* valueCols[kMaxValueCols]; // decimal128 (16 B / value)
+   int32_t valueStage[kMaxValueCols]; // decimal128 (16 B / value)
    int32_t nAggs;
    AggSpec aggs[kMaxAggs];
    GroupTableDev table;
@@ -76,31 +92,30 @@ struct GroupByParams {
 
 struct BuildParams {
    ScanSource src;
-   const int32_t* keyCol;
-   const int32_t* payloadCol; // may be null
+   int32_t keyStage;
+   int32_t payloadStage; // -1: none
    int32_t nSide;
-   const int32_t* sideCols[kMaxSide];
+   int32_t sideStage[kMaxSide];
    int32_t hasProbe;
    JoinTableDev probe;
-   const int32_t* probeKeyCol;
+   int32_t probeKeyStage;
    JoinTableDev sink;
 };
 
 struct ProbeAggParams {
    ScanSource src;
-   const int32_t* probeKeyCol;
+   int32_t probeKeyStage;
    JoinTableDev table;
    AggSpec agg;
-   const void* valueCols[kMaxValueCols];
+   int32_t valueStage[kMaxValueCols];
 };
 
 struct Probe2GroupByParams {
    ScanSource src;
-   const int32_t* keyColA;
-   const int32_t* keyColB;
+   int32_t keyStageA, keyStageB;
    JoinTableDev tableA, tableB;
    AggSpec agg;
-   const void* valueCols[kMaxValueCols];
+   int32_t valueStage[kMaxValueCols];
    GroupTableDev groups; // keyed by the matched payload
 };
 

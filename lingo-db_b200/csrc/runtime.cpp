@@ -563,11 +563,37 @@ struct Resolved {
    }
 };
 // FilterDescription list → per-column predicate pairs (Restrictions::create, Restrictions.cpp:392-520)
+// distinct fixed-width columns a pipeline reads → the staged tile layout (kernels.h StagedCols)
+struct StagePlan {
+   int n = 0;
+   int colIdx[kMaxStagedCols];
+   int add(LdbTable* t, int col) {
+      for (int i = 0; i < n; i++)
+         if (colIdx[i] == col) return i;
+      if (n == kMaxStagedCols) fail(LDB_ERR_UNSUPPORTED, "a pipeline may touch at most 8 distinct fixed-width columns");
+      colIdx[n] = col;
+      return n++;
+   }
+   void bind(LdbTable* t, const LdbBatch& b, StagedCols& out) const {
+      out.n = n;
+      int off = 0;
+      bool aligned = true;
+      for (int i = 0; i < n; i++) {
+         out.base[i] = (const uint8_t*) b.data[colIdx[i]];
+         out.elemBytes[i] = (int32_t) elemWidth(t->columns[colIdx[i]].type);
+         out.smemOffset[i] = off;
+         off += out.elemBytes[i] * kTileRows;
+         aligned &= ((uintptr_t) out.base[i] % 16) == 0;
+      }
+      out.stageBytes = off;
+      out.useTma = aligned && n > 0 ? 1 : 0;
+   }
+};
 struct FilterPlan {
    FilterSet set{};
    int colIdx[kMaxFilterCols];
 };
-FilterPlan planFilters(LdbTable* t, const LdbFilterDesc* f, int n) {
+FilterPlan planFilters(LdbTable* t, const LdbFilterDesc* f, int n, StagePlan& sp) {
    FilterPlan p;
    p.set.n = 0;
    for (int i = 0; i < n; i++) {
@@ -623,6 +649,7 @@ FilterPlan planFilters(LdbTable* t, const LdbFilterDesc* f, int n) {
       FilterCol& fc = p.set.c[p.set.n];
       memset(&fc, 0, sizeof(fc));
       fc.kind = kind;
+      fc.staged = kind == COL_UTF8_EQ ? -1 : sp.add(t, c);
       fc.maskA = mask;
       fc.valA = value;
       fc.maskB = 7;
@@ -638,6 +665,7 @@ FilterPlan planFilters(LdbTable* t, const LdbFilterDesc* f, int n) {
 void bindFilters(const FilterPlan& p, const LdbBatch& b, FilterSet& out) {
    out = p.set;
    for (int i = 0; i < out.n; i++) {
+      if (out.c[i].kind != COL_UTF8_EQ) continue; // fixed-width filter columns are read from the staged tile
       out.c[i].base = b.data[p.colIdx[i]];
       out.c[i].bytes = (const uint8_t*) b.bytes[p.colIdx[i]];
    }
@@ -691,7 +719,8 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
       if (t->ctx != ctx) fail(LDB_ERR_INVALID, "table belongs to another context");
       LDB_CUDA(cudaSetDevice(ctx->device));
       Resolved R{t};
-      FilterPlan fp = planFilters(t, d->filters, d->n_filters);
+      StagePlan sp;
+      FilterPlan fp = planFilters(t, d->filters, d->n_filters, sp);
       const char* why = "";
       switch (d->kind) {
          case LDB_PIPE_SCAN_REDUCE:
@@ -703,16 +732,22 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
             int nKeys = keyless ? 0 : d->n_keys;
             if (nKeys != sink->group.nKeys) fail(LDB_ERR_INVALID, "key count differs from the state's");
             int keyCol[kMaxKeys] = {0, 0};
-            for (int k = 0; k < nKeys; k++) keyCol[k] = R.col(d->key_columns[k], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "group key");
+            int keyStage[kMaxKeys] = {0, 0}, valueStage[kMaxValueCols] = {0, 0, 0, 0};
+            for (int k = 0; k < nKeys; k++) {
+               keyCol[k] = R.col(d->key_columns[k], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "group key");
+               keyStage[k] = sp.add(t, keyCol[k]);
+            }
+            for (int v = 0; v < ap.nValueCols; v++) valueStage[v] = sp.add(t, ap.valueCol[v]);
             for (auto& b : t->batches) {
                if (b.nRows == 0) continue;
                GroupByParams p{};
                p.src.nRows = b.nRows;
                bindFilters(fp, b, p.src.filters);
+               sp.bind(t, b, p.src.cols);
                p.nKeys = nKeys;
-               for (int k = 0; k < nKeys; k++) p.keyCols[k] = (const int32_t*) b.data[keyCol[k]];
+               for (int k = 0; k < nKeys; k++) p.keyStage[k] = keyStage[k];
                p.nValueCols = ap.nValueCols;
-               for (int v = 0; v < ap.nValueCols; v++) p.valueCols[v] = b.data[ap.valueCol[v]];
+               for (int v = 0; v < ap.nValueCols; v++) p.valueStage[v] = valueStage[v];
                p.nAggs = ap.nAggs;
                for (int a = 0; a < ap.nAggs; a++) p.aggs[a] = ap.aggs[a];
                p.table = sink->group;
@@ -733,19 +768,23 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
             for (int k = 0; k < d->n_side; k++) sideCol[k] = R.col(d->side_columns[k], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "side payload");
             LdbState* probe = d->n_probes ? wantState(d->probe_states[0], LDB_STATE_JOIN_TABLE, "probe") : nullptr;
             int probeCol = d->n_probes ? R.col(d->probe_key_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key") : -1;
+            int keyStage = sp.add(t, keyCol), payStage = payCol >= 0 ? sp.add(t, payCol) : -1, probeStage = probeCol >= 0 ? sp.add(t, probeCol) : 0;
+            int sideStage[kMaxSide] = {0, 0};
+            for (int k = 0; k < d->n_side; k++) sideStage[k] = sp.add(t, sideCol[k]);
             for (auto& b : t->batches) {
                if (b.nRows == 0) continue;
                BuildParams p{};
                p.src.nRows = b.nRows;
                bindFilters(fp, b, p.src.filters);
-               p.keyCol = (const int32_t*) b.data[keyCol];
-               p.payloadCol = payCol >= 0 ? (const int32_t*) b.data[payCol] : nullptr;
+               sp.bind(t, b, p.src.cols);
+               p.keyStage = keyStage;
+               p.payloadStage = payStage;
                p.nSide = d->n_side;
-               for (int k = 0; k < d->n_side; k++) p.sideCols[k] = (const int32_t*) b.data[sideCol[k]];
+               for (int k = 0; k < d->n_side; k++) p.sideStage[k] = sideStage[k];
                p.hasProbe = probe ? 1 : 0;
                if (probe) {
                   p.probe = probe->join;
-                  p.probeKeyCol = (const int32_t*) b.data[probeCol];
+                  p.probeKeyStage = probeStage;
                }
                p.sink = sink->join;
                waitBatch(ctx, b);
@@ -759,15 +798,18 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
             if (d->n_probes != 1 || d->probe_states[0] != table) fail(LDB_ERR_INVALID, "probe-aggregate pipelines probe their own sink");
             AggPlan ap = planAggs(R, d->aggs, 1);
             int probeCol = R.col(d->probe_key_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key");
+            int probeStage = sp.add(t, probeCol), valueStage[kMaxValueCols] = {0, 0, 0, 0};
+            for (int v = 0; v < ap.nValueCols; v++) valueStage[v] = sp.add(t, ap.valueCol[v]);
             for (auto& b : t->batches) {
                if (b.nRows == 0) continue;
                ProbeAggParams p{};
                p.src.nRows = b.nRows;
                bindFilters(fp, b, p.src.filters);
-               p.probeKeyCol = (const int32_t*) b.data[probeCol];
+               sp.bind(t, b, p.src.cols);
+               p.probeKeyStage = probeStage;
                p.table = table->join;
                p.agg = ap.aggs[0];
-               for (int v = 0; v < ap.nValueCols; v++) p.valueCols[v] = b.data[ap.valueCol[v]];
+               for (int v = 0; v < ap.nValueCols; v++) p.valueStage[v] = valueStage[v];
                waitBatch(ctx, b);
                bool ok = true;
                ctx->launch("join_probe_agg", [&] { ok = launchScanProbeAgg(p, ctx->smCount, ctx->compute, &why); });
@@ -784,17 +826,20 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
             AggPlan ap = planAggs(R, d->aggs, 1);
             int ca = R.col(d->probe_key_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key A");
             int cb = R.col(d->probe_key_columns[1], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key B");
+            int stageA = sp.add(t, ca), stageB = sp.add(t, cb), valueStage[kMaxValueCols] = {0, 0, 0, 0};
+            for (int v = 0; v < ap.nValueCols; v++) valueStage[v] = sp.add(t, ap.valueCol[v]);
             for (auto& b : t->batches) {
                if (b.nRows == 0) continue;
                Probe2GroupByParams p{};
                p.src.nRows = b.nRows;
                bindFilters(fp, b, p.src.filters);
-               p.keyColA = (const int32_t*) b.data[ca];
-               p.keyColB = (const int32_t*) b.data[cb];
+               sp.bind(t, b, p.src.cols);
+               p.keyStageA = stageA;
+               p.keyStageB = stageB;
                p.tableA = ta->join;
                p.tableB = tb->join;
                p.agg = ap.aggs[0];
-               for (int v = 0; v < ap.nValueCols; v++) p.valueCols[v] = b.data[ap.valueCol[v]];
+               for (int v = 0; v < ap.nValueCols; v++) p.valueStage[v] = valueStage[v];
                p.groups = sink->group;
                waitBatch(ctx, b);
                bool ok = true;
