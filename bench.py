@@ -152,7 +152,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from lingodb_b200 import capi, datagen, devgen, runtime
+    from lingodb_b200 import datagen, devgen, parallel, runtime
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -169,9 +169,7 @@ def run_ours(args):
     L = ctx.L
     s = datagen.scale(args.sf, args.seed)
     # strong scaling: SF-sized lineitem split by order range
-    o_lo, o_hi = s.n_orders * rank // world, s.n_orders * (rank + 1) // world
-    gl = datagen.lib()
-    r_lo, r_hi = gl.ldbgen_order_first_line(C.byref(s), o_lo), gl.ldbgen_order_first_line(C.byref(s), o_hi)
+    o_lo, o_hi, r_lo, r_hi = parallel.order_range(s, rank, world)
     my_rows = r_hi - r_lo
     extra = (not args.no_extra) and world == 1
     cols = ALL_COLS if extra else Q1_COLS
@@ -180,7 +178,7 @@ def run_ours(args):
     tp = runtime.Tpch(ctx, tabs)
     total_rows = s.n_lineitem
 
-    gather_buf = None
+    gather_bufs = {}
 
     def barrier():
         if world > 1:
@@ -189,16 +187,7 @@ def run_ours(args):
     def step_resident():
         st = tp.q1_partial()
         if world > 1:
-            nonlocal gather_buf
-            nbytes = int(L.ldb_gpu_groupby_export_bytes(st))
-            if gather_buf is None:
-                gather_buf = (torch.empty(nbytes, dtype=torch.uint8, device=dev), torch.empty(nbytes * world, dtype=torch.uint8, device=dev))
-            e = capi.Error()
-            capi.check(L.ldb_gpu_groupby_export(st, C.c_void_p(gather_buf[0].data_ptr()), C.byref(e)), e)
-            ctx.synchronize()
-            dist.all_gather_into_tensor(gather_buf[1], gather_buf[0])
-            torch.cuda.current_stream().synchronize()
-            capi.check(L.ldb_gpu_groupby_merge_exported(st, C.c_void_p(gather_buf[1].data_ptr()), world, rank, C.byref(e)), e)
+            parallel.allgather_merge_state(ctx, st, world, rank, gather_bufs)
         rows = tp.q1_finish(st)
         runtime.state_destroy(ctx, st)
         return rows

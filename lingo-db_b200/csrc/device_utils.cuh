@@ -97,8 +97,16 @@ __device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 // global → shared bulk copy, completion counted in bytes on `bar`; src/dst 16-B aligned, bytes % 16 == 0
-__device__ __forceinline__ void bulkLoad(uint32_t dstSmem, const void* src, uint32_t bytes, uint64_t* bar) {
-   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dstSmem), "l"(src), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+// Column data is read exactly once: L2 evict_first keeps the 126 MB L2 for the hash-table directories and bloom filters.
+__device__ __forceinline__ uint64_t evictFirstPolicy() {
+   uint64_t pol;
+   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+   return pol;
+}
+__device__ __forceinline__ void bulkLoad(uint32_t dstSmem, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dstSmem), "l"(src), "r"(bytes),
+                "r"(smemAddr(bar)), "l"(policy)
+                : "memory");
 }
 __device__ __forceinline__ int32_t ldShared32(uint32_t addr) {
    int32_t v;

@@ -41,11 +41,12 @@ struct GlobalTile {
    __device__ __forceinline__ int64_t lo64(int col, int lr) const { return ldStream64((const int64_t*) sc->base[col] + 2 * (rowBase + lr)); }
 };
 __device__ __forceinline__ void issueTile(const StagedCols& sc, uint8_t* smem, uint64_t* bars, int64_t tile, int s) {
+   const uint64_t policy = evictFirstPolicy();
    mbarExpectTx(&bars[s], (uint32_t) sc.stageBytes);
    const uint32_t dst = smemAddr(smem) + (uint32_t) s * sc.stageBytes;
    for (int c = 0; c < sc.n; c++) {
       const uint32_t bytes = (uint32_t) sc.elemBytes[c] * kTileRows;
-      bulkLoad(dst + sc.smemOffset[c], sc.base[c] + (size_t) tile * bytes, bytes, &bars[s]);
+      bulkLoad(dst + sc.smemOffset[c], sc.base[c] + (size_t) tile * bytes, bytes, &bars[s], policy);
    }
 }
 // fn(tile, localRow, globalRow, valid) is called for every row with all 32 lanes of a warp converged
@@ -175,6 +176,13 @@ __device__ __forceinline__ void groupAtomicAdd(const GroupTableDev& t, int slot,
 // =================================================================================== join table (HBM)
 constexpr unsigned long long kEmptySlot = ~0ull;
 constexpr uint64_t kMaxProbe = 16384; // insert reports "table full" beyond this displacement; the host regrows
+// Blocked Bloom filter in front of the directory: the reference rejects most non-matching probes with a 16-bit
+// tag in the bucket pointer (helpers.h:325-346) — but only after it loaded the bucket.  Here the filter is a
+// separate array small enough to live in L2 (1 byte per directory slot), so a rejected probe never goes to HBM.
+__device__ __forceinline__ uint32_t bloomBits(uint64_t h) {
+   uint64_t g = h * 0xD6E8FEB86659FD93ull;
+   return (1u << (g >> 59)) | (1u << ((g >> 54) & 31)) | (1u << ((g >> 49) & 31));
+}
 __device__ __forceinline__ unsigned long long packSlot(int32_t key, int32_t payload) { return ((unsigned long long) (uint32_t) payload << 32) | (uint32_t) key; }
 // HashIndexedView::build's CAS push-front (LazyJoinHashtable.cpp:20-31) becomes a CAS into an open-addressing
 // slot.  The caller counts successful inserts (one atomic per warp at kernel end, not one per tuple).
@@ -184,11 +192,15 @@ __device__ int64_t joinInsert(const JoinTableDev& t, int32_t key, int32_t payloa
       atomicExch(t.error, 3);
       return -1;
    }
-   uint64_t s = hashI32(key) & t.mask;
+   const uint64_t h = hashI32(key);
+   uint64_t s = h & t.mask;
    const uint64_t limit = t.mask < kMaxProbe ? t.mask + 1 : kMaxProbe; // a sanely loaded table never probes this far
    for (uint64_t probes = 0; probes < limit; probes++) {
       unsigned long long old = atomicCAS(&t.slots[s], kEmptySlot, packed);
-      if (old == kEmptySlot) return (int64_t) s;
+      if (old == kEmptySlot) {
+         if (t.bloom) atomicOr(&t.bloom[(uint32_t) (h >> 32) & t.bloomMask], bloomBits(h));
+         return (int64_t) s;
+      }
       if (t.unique && (int32_t) (uint32_t) old == key) {
          atomicExch(t.error, 2);
          return -1;
@@ -201,7 +213,12 @@ __device__ int64_t joinInsert(const JoinTableDev& t, int32_t key, int32_t payloa
 // probe (SubOpToControlFlow.cpp:2558-2586 + chain walk :2254-2313): visit every entry with the key
 template <class Fn>
 __device__ __forceinline__ void joinProbe(const JoinTableDev& t, int32_t key, const Fn& fn) {
-   uint64_t s = hashI32(key) & t.mask;
+   const uint64_t h = hashI32(key);
+   if (t.bloom) {
+      const uint32_t bits = bloomBits(h);
+      if ((__ldg(&t.bloom[(uint32_t) (h >> 32) & t.bloomMask]) & bits) != bits) return;
+   }
+   uint64_t s = h & t.mask;
    const uint64_t limit = t.mask < kMaxProbe ? t.mask + 1 : kMaxProbe;
    for (uint64_t probes = 0; probes < limit; probes++) {
       unsigned long long e = __ldg(&t.slots[s]);

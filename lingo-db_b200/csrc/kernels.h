@@ -49,6 +49,8 @@ struct JoinTableDev {
    unsigned long long* aggLo; // [capacity]
    unsigned long long* aggHi; // [capacity]
    uint8_t* marker;           // [capacity]
+   uint32_t* bloom;           // blocked Bloom filter over the build keys (32-bit blocks, 3 bits/key), sized to stay in L2
+   uint32_t bloomMask;        // words - 1
    unsigned long long* count; // inserted entries
    int32_t* error;            // 1 = table full, 2 = duplicate key in a unique table
    int32_t unique;

@@ -491,6 +491,11 @@ int ldb_gpu_join_table_create(LdbContext* ctx, int64_t expected_rows, int32_t un
       }
       j.count = (unsigned long long*) devAlloc(s, 8, 0);
       j.error = (int32_t*) devAlloc(s, 4, 0);
+      if (cap >= 4096) { // 8 filter bits per directory slot = 16..32 bits per key at load 0.25..0.5
+         uint64_t words = cap / 4;
+         j.bloom = (uint32_t*) devAlloc(s, words * 4, 0);
+         j.bloomMask = (uint32_t) (words - 1);
+      }
       s->nSide = n_side;
       s->nAggs = n_aggs;
       *out = s;

@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Extract the reference's own known-answer vectors for the hot path into reference_kats.json.
+
+Run in the build container (needs /root/reference); the JSON is committed so the tests run anywhere.
+Sources:
+  test/lit/DB/hash.mlir                      CHECK lines 27-34 (db.hash of constants, executed through the JIT)
+  test/unittests/storage/TestStorage.cpp     dbHash64(int8 1) literal (:289, :411)
+  test/sqlite-datasets/tpchSf1.test          Q1 answer rows (:25-28): avg = (sum * 10^19) / count, Q6 (:20506)
+"""
+import json
+import os
+import re
+
+REF = "/root/reference"
+out = {"source_commit": "fab813e8", "hash": {}, "tpch_sf1": {}}
+
+mlir = open(os.path.join(REF, "test/lit/DB/hash.mlir")).read()
+checks = [int(x) for x in re.findall(r"//CHECK: index\((\d+)\)", mlir)]
+names = ["i32_10", "i64_10", "bool_true", "decimal15_2_100.01", "date_2020-06-11", "timestamp_s_2020-06-11_12:30:00", "string_hello_world!", "tuple7"]
+assert len(checks) == len(names)
+out["hash"] = dict(zip(names, checks))
+out["hash"]["file"] = "test/lit/DB/hash.mlir:27-34"
+
+ts = open(os.path.join(REF, "test/unittests/storage/TestStorage.cpp")).read()
+m = re.findall(r"(-3\d{18})", ts)  # the literal next to dbHash64 / hash(1) checks
+out["hash"]["int8_1"] = int(m[0])
+out["hash"]["int8_1_file"] = "test/unittests/storage/TestStorage.cpp:289,411"
+
+lines = open(os.path.join(REF, "test/sqlite-datasets/tpchSf1.test")).read().split("\n")
+q1 = []
+for ln in lines[24:28]:
+    f = ln.split("\t")
+    q1.append({"l_returnflag": f[0], "l_linestatus": f[1], "sum_qty": f[2], "sum_base_price": f[3], "sum_disc_price": f[4], "sum_charge": f[5],
+               "avg_qty": f[6], "avg_price": f[7], "avg_disc": f[8], "count_order": f[9]})
+out["tpch_sf1"]["q1"] = q1
+out["tpch_sf1"]["q1_file"] = "test/sqlite-datasets/tpchSf1.test:25-28"
+out["tpch_sf1"]["q6"] = lines[20505].strip()
+out["tpch_sf1"]["q6_file"] = "test/sqlite-datasets/tpchSf1.test:20506"
+json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_kats.json"), "w"), indent=1)
+print(json.dumps(out, indent=1)[:1500])

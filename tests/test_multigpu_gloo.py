@@ -1,0 +1,85 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of the Q1 sharding protocol (order-range split, table-image
+all-gather, K7 merge semantics, host finish).  The per-rank partial is computed by the CPU oracle here —
+the GPU kernels are covered by the -m gpu tests; this covers partitioning and the exchange format."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CAP = 64
+
+
+def _worker(rank, world, port, sf, seed, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lingodb_b200 import datagen, parallel
+    from oracle import oracle as O
+    s = datagen.scale(sf, seed)
+    o_lo, o_hi, r_lo, r_hi = parallel.order_range(s, rank, world)
+    mine = datagen.lineitem(s, chunk_rows=4096, row_begin=r_lo, n_rows=r_hi - r_lo)
+    o = O.Oracle("port", workers=1)
+    part, _ = o.q1(o.table(mine))
+    groups = []
+    for r in part:
+        # invert the avg: the exchanged partial carries sums and counts (SimplifyAggregations: avg = sum / count)
+        sum_disc = -(-(r["avg_disc"] * r["count_order"]) // 10**19)
+        groups.append(((r["l_returnflag"], r["l_linestatus"]),
+                       [r["sum_qty"], r["sum_base_price"], r["sum_disc_price"], r["sum_charge"], sum_disc, r["count_order"], 0, 0]))
+    img = torch.from_numpy(parallel.pack_image(CAP, groups))
+    gathered = [torch.empty_like(img) for _ in range(world)]
+    dist.all_gather(gathered, img)
+    rows = parallel.q1_rows_from_groups(parallel.merge_images_host([g.numpy() for g in gathered], CAP))
+    cover = torch.tensor([r_hi - r_lo], dtype=torch.int64)
+    dist.all_reduce(cover)
+    if rank == 0:
+        whole = datagen.lineitem(s, chunk_rows=1 << 20)
+        want, _ = o.q1(o.table(whole))
+        out.put((rows == want, int(cover.item()) == s.n_lineitem, len(rows)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_q1_sharding_protocol_gloo(world):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + os.getpid() % 1000 + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 0.02, 13, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    same, covered, n = out.get(timeout=10)
+    assert covered, "order-range split must cover every lineitem row exactly once"
+    assert same and n == 4
+
+
+def test_image_roundtrip_and_wraparound():
+    sys.path.insert(0, ROOT)
+    from lingodb_b200 import parallel
+    big = (1 << 127) + 12345
+    img = parallel.pack_image(CAP, [((65, 70), [1, -2, big, -big, 5, 6, 0, 0])])
+    assert len(img) == parallel.image_bytes(CAP)
+    (key, aggs), = parallel.unpack_image(img, CAP)
+    assert key == (65, 70) and aggs[0] == 1 and aggs[1] == (1 << 128) - 2
+    merged = parallel.merge_images_host([img, img], CAP)
+    assert merged[(65, 70)][2] == (2 * big) % (1 << 128)  # sums wrap mod 2^128 like the device atomics
+
+
+def test_order_range_partition_is_exact():
+    sys.path.insert(0, ROOT)
+    from lingodb_b200 import datagen, parallel
+    s = datagen.scale(0.013, 3)
+    for world in (1, 2, 4, 8):
+        prev = 0
+        for r in range(world):
+            o_lo, o_hi, r_lo, r_hi = parallel.order_range(s, r, world)
+            assert r_lo == prev and r_hi >= r_lo
+            prev = r_hi
+        assert prev == s.n_lineitem
