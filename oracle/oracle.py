@@ -96,6 +96,10 @@ class Oracle:
         self.workers = L.oracle_num_workers()
         self._keep = []
 
+    def set_workers(self, n: int):
+        self.lib.oracle_set_workers(int(n))
+        self.workers = self.lib.oracle_num_workers()
+
     # ---- tables: borrow the numpy buffers of a lingodb_b200.datagen.TableData
     def table(self, t):
         L = self.lib
