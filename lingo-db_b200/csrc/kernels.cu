@@ -256,12 +256,14 @@ __device__ __forceinline__ i128 evalAgg(const int64_t* v, int64_t one) {
    }
 }
 // operands of one aggregate qualify for the 32-bit path
+// OR of the operands as unsigned: zero above bit 30 ⇔ every operand is in [0, 2^31) (TPC-H money is);
+// negative or wide operands simply take the general path
 template <class A>
-__device__ __forceinline__ bool aggFits32(const int64_t* v, int64_t one) {
-   if constexpr (A::expr == LDB_EXPR_MUL) return fitsI32(v[A::a]) & fitsI32(v[A::b]);
-   else if constexpr (A::expr == LDB_EXPR_MUL_1MINUS) return fitsI32(v[A::a]) & fitsI32(one - v[A::b]);
-   else if constexpr (A::expr == LDB_EXPR_MUL_1MINUS_1PLUS) return fitsI32(v[A::a]) & fitsI32(one - v[A::b]) & fitsI32(one + v[A::c]) & (one + v[A::c] >= 0);
-   else return true;
+__device__ __forceinline__ uint64_t aggOperandBits(const int64_t* v, int64_t one) {
+   if constexpr (A::expr == LDB_EXPR_MUL) return (uint64_t) v[A::a] | (uint64_t) v[A::b];
+   else if constexpr (A::expr == LDB_EXPR_MUL_1MINUS) return (uint64_t) v[A::a] | (uint64_t) (one - v[A::b]);
+   else if constexpr (A::expr == LDB_EXPR_MUL_1MINUS_1PLUS) return (uint64_t) v[A::a] | (uint64_t) (one - v[A::b]) | (uint64_t) (one + v[A::c]);
+   else return 0;
 }
 __device__ __forceinline__ i128 evalAggDyn(const AggSpec& a, const int64_t* v, int64_t one) {
    switch (a.expr) {
@@ -290,7 +292,7 @@ struct Aggs {
    static __device__ __forceinline__ void eval(i128* v, const int64_t* vals, int64_t one, Seq<Is...>) {
       ((v[Is] = evalAgg<As, FAST>(vals, one)), ...);
    }
-   static __device__ __forceinline__ bool fits32(const int64_t* vals, int64_t one) { return (aggFits32<As>(vals, one) & ...); }
+   static __device__ __forceinline__ bool fits32(const int64_t* vals, int64_t one) { return ((aggOperandBits<As>(vals, one) | ...) >> 31) == 0; }
    template <int... Is>
    static __device__ __forceinline__ void accumulate(i128* acc, const i128* v, Seq<Is...>) {
       ((As::is64 ? (void) (acc[Is].lo += v[Is].lo) : (void) (acc[Is] = add128(acc[Is], v[Is]))), ...);
@@ -351,7 +353,11 @@ __global__ void __launch_bounds__(kBlock, 2) scanGroupByKernel(const __grid_cons
 #pragma unroll
       for (int a = 0; a < N; a++) acc[g][a] = i128{0, 0};
    const int64_t one = 100; // 10^scale of decimal(12,2); checked on the host
-   int32_t lastK0 = 0, lastK1 = 0, lastId = -2;
+   // keys of the register-resident groups live in registers too (refreshed when the CTA registers a new key)
+   int32_t rk0[GREG], rk1[GREG];
+   int rcnt = 0;
+#pragma unroll
+   for (int g = 0; g < GREG; g++) rk0[g] = rk1[g] = 0;
 
    forEachRow(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
       int64_t vals[NV];
@@ -366,53 +372,61 @@ __global__ void __launch_bounds__(kBlock, 2) scanGroupByKernel(const __grid_cons
          // Resolve the CTA-local group id under WARP-UNIFORM control flow.  (A per-lane spin lock
          // here once left the warps permanently diverged: 1 active thread per instruction, 40x
          // the instructions and 12x the DRAM traffic — profiles/r1_q1_first.md.)
+         // Fast path: branch-free compare against the register copies of the first GREG keys.
          id = -1;
-         bool need = pass;
-         if (need && lastId >= 0 && k0 == lastK0 && k1 == lastK1) {
-            id = lastId;
-            need = false;
-         }
-         if (need) {
-            const int cnt = *((volatile int32_t*) &sCount);
-            for (int g = 0; g < cnt; g++)
-               if (sKeys[g][0] == k0 && sKeys[g][1] == k1) id = g;
-            need = id < 0;
-         }
-         // first sight of a key in this CTA: one elected lane registers it under the CTA lock
+#pragma unroll
+         for (int g = 0; g < GREG; g++)
+            if (g < rcnt && k0 == rk0[g] && k1 == rk1[g]) id = g;
+         bool need = pass && id < 0;
          unsigned pending = __ballot_sync(0xffffffffu, need);
-         while (pending) {
-            const int leader = __ffs(pending) - 1;
-            const int32_t lk0 = __shfl_sync(0xffffffffu, k0, leader), lk1 = __shfl_sync(0xffffffffu, k1, leader);
-            int newId = -1;
-            if ((threadIdx.x & 31) == leader) {
-               while (atomicCAS(&sLock, 0, 1) != 0) {}
-               __threadfence_block();
-               const int c2 = *((volatile int32_t*) &sCount);
-               for (int g = 0; g < c2; g++)
-                  if (((volatile int32_t*) sKeys[g])[0] == lk0 && ((volatile int32_t*) sKeys[g])[1] == lk1) newId = g;
-               if (newId < 0 && c2 < LG) {
-                  int32_t kk[2] = {lk0, lk1};
-                  sSlot[c2] = groupLookupOrInsert(p.table, kk);
-                  sKeys[c2][0] = lk0;
-                  sKeys[c2][1] = lk1;
-                  __threadfence_block();
-                  *((volatile int32_t*) &sCount) = c2 + 1;
-                  newId = c2;
-               }
-               __threadfence_block();
-               atomicExch(&sLock, 0);
-            }
-            newId = __shfl_sync(0xffffffffu, newId, leader);
-            if (need && k0 == lk0 && k1 == lk1) {
-               id = newId; // -1: the CTA tracks LG groups already → this row goes straight to HBM
-               need = false;
+         if (pending) { // rare after the first tiles: a key outside the register-resident set
+            if (need) {
+               const int cnt = *((volatile int32_t*) &sCount);
+               for (int g = 0; g < cnt; g++)
+                  if (sKeys[g][0] == k0 && sKeys[g][1] == k1) id = g;
+               need = id < 0;
             }
             pending = __ballot_sync(0xffffffffu, need);
-         }
-         if (pass && id >= 0) {
-            lastK0 = k0;
-            lastK1 = k1;
-            lastId = id;
+            // first sight of a key in this CTA: one elected lane registers it under the CTA lock
+            while (pending) {
+               const int leader = __ffs(pending) - 1;
+               const int32_t lk0 = __shfl_sync(0xffffffffu, k0, leader), lk1 = __shfl_sync(0xffffffffu, k1, leader);
+               int newId = -1;
+               if ((threadIdx.x & 31) == leader) {
+                  while (atomicCAS(&sLock, 0, 1) != 0) {}
+                  __threadfence_block();
+                  const int c2 = *((volatile int32_t*) &sCount);
+                  for (int g = 0; g < c2; g++)
+                     if (((volatile int32_t*) sKeys[g])[0] == lk0 && ((volatile int32_t*) sKeys[g])[1] == lk1) newId = g;
+                  if (newId < 0 && c2 < LG) {
+                     int32_t kk[2] = {lk0, lk1};
+                     sSlot[c2] = groupLookupOrInsert(p.table, kk);
+                     sKeys[c2][0] = lk0;
+                     sKeys[c2][1] = lk1;
+                     __threadfence_block();
+                     *((volatile int32_t*) &sCount) = c2 + 1;
+                     newId = c2;
+                  }
+                  __threadfence_block();
+                  atomicExch(&sLock, 0);
+               }
+               newId = __shfl_sync(0xffffffffu, newId, leader);
+               if (need && k0 == lk0 && k1 == lk1) {
+                  id = newId; // -1: the CTA tracks LG groups already → this row goes straight to HBM
+                  need = false;
+               }
+               pending = __ballot_sync(0xffffffffu, need);
+            }
+            // refresh the register copies (keys are append-only, so ids never change)
+            const int cnt = *((volatile int32_t*) &sCount);
+            rcnt = cnt < GREG ? cnt : GREG;
+#pragma unroll
+            for (int g = 0; g < GREG; g++) {
+               if (g < rcnt) {
+                  rk0[g] = ((volatile int32_t*) sKeys[g])[0];
+                  rk1[g] = ((volatile int32_t*) sKeys[g])[1];
+               }
+            }
          }
       }
       // expressions: 32-bit multiplies when every lane's operands allow it, else the general i128 path
@@ -792,7 +806,9 @@ void launchGroupMergeImages(const GroupTableDev& t, const uint8_t* images, int n
 // =================================================================================== K6 radix partition
 // dest = top bits of the reference hash (the low bits stay for the local directory, mirroring the
 // reference's use of hash & 63 for its 64 partitions, PreAggregationHashtable.cpp:47-51)
-__device__ __forceinline__ int partOf(int32_t key, int nParts) { return (int) (((hashI32(key) >> 32) * (uint64_t) nParts) >> 32); }
+// (explicit __umulhi: nvcc 12.9 folded `((h >> 32) * (uint64_t) n) >> 32` feeding a shared-memory index into a
+//  32-bit IMAD that kept the LOW half — out-of-bounds shared atomics under compute-sanitizer)
+__device__ __forceinline__ int partOf(int32_t key, int nParts) { return (int) __umulhi((uint32_t) (hashI32(key) >> 32), (uint32_t) nParts); }
 __global__ void __launch_bounds__(kBlock) partitionHistogramKernel(const int32_t* keys, int64_t n, int nParts, unsigned long long* counts) {
    __shared__ unsigned int sCnt[64];
    for (int i = threadIdx.x; i < 64; i += kBlock) sCnt[i] = 0;

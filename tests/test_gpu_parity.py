@@ -153,3 +153,49 @@ def test_unsupported_and_invalid_descriptors(gpu_ctx):
     assert ei.value.code == capi.LDB_ERR_INVALID
     with pytest.raises(capi.LdbRuntimeError):
         g.q6(disc_ge="abc")
+
+
+def test_radix_partition_and_tuple_insert(gpu_ctx, oracle):
+    """K6: partition by the top bits of the reference hash; every tuple lands in exactly one contiguous block of
+    its partition, payload columns travel with their key, and re-inserting the blocks builds a probe-able table."""
+    import ctypes as C
+
+    import torch
+    from lingodb_b200 import capi
+    L = gpu_ctx.L
+    n, parts = 200000, 8
+    rng = np.random.default_rng(5)
+    keys = rng.choice(np.arange(1, 5_000_000, dtype=np.int32), size=n, replace=False)
+    pay = (keys.astype(np.int64) * 7 + 1).astype(np.int32)
+    wide = (keys.astype(np.int64) * 1000003)
+    dev = torch.device("cuda", gpu_ctx.device)
+    dk, dp, dw = (torch.from_numpy(a).to(dev) for a in (keys, pay, wide))
+    ok, op, ow = torch.empty_like(dk), torch.empty_like(dp), torch.empty_like(dw)
+    torch.cuda.synchronize()
+    cols = (C.c_void_p * 2)(dp.data_ptr(), dw.data_ptr())
+    outs = (C.c_void_p * 2)(op.data_ptr(), ow.data_ptr())
+    widths = (C.c_int32 * 2)(4, 8)
+    offs = (C.c_int64 * (parts + 1))()
+    e = capi.Error()
+    capi.check(L.ldb_gpu_partition_tuples(gpu_ctx.h, C.c_void_p(dk.data_ptr()), cols, widths, 2, n, parts, C.c_void_p(ok.data_ptr()), outs, offs, C.byref(e)), e)
+    offs = list(offs)
+    assert offs[0] == 0 and offs[-1] == n and all(a <= b for a, b in zip(offs, offs[1:]))
+    hk, hp, hw = ok.cpu().numpy(), op.cpu().numpy(), ow.cpu().numpy()
+    assert sorted(hk.tolist()) == sorted(keys.tolist())
+    assert np.array_equal(hp, (hk.astype(np.int64) * 7 + 1).astype(np.int32)) and np.array_equal(hw, hk.astype(np.int64) * 1000003)
+    for p in range(parts):  # destination = top bits of h64(key), as the oracle hashes
+        for k in hk[offs[p]:offs[p + 1]][:50]:
+            h = oracle.lib.oracle_hash_i64(int(k))
+            assert ((h >> 32) * parts) >> 32 == p
+    # the received block of one partition → join table → probe through a build pipeline is exercised by q5; here: count
+    st = C.c_void_p()
+    capi.check(L.ldb_gpu_join_table_create(gpu_ctx.h, n, 1, 0, 0, C.byref(st), C.byref(e)), e)
+    capi.check(L.ldb_gpu_join_table_insert(gpu_ctx.h, st, C.c_void_p(ok.data_ptr()), C.c_void_p(op.data_ptr()), None, n, C.byref(e)), e)
+    cnt = C.c_int64()
+    capi.check(L.ldb_gpu_join_table_count(st, C.byref(cnt), C.byref(e)), e)
+    assert cnt.value == n
+    # duplicate keys in a table declared unique are reported, not silently dropped
+    capi.check(L.ldb_gpu_join_table_insert(gpu_ctx.h, st, C.c_void_p(ok.data_ptr()), C.c_void_p(op.data_ptr()), None, 10, C.byref(e)), e)
+    rc = L.ldb_gpu_join_table_count(st, C.byref(cnt), C.byref(e))
+    assert rc == capi.LDB_ERR_INVALID
+    L.ldb_gpu_state_destroy(st)
