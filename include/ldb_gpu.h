@@ -140,6 +140,9 @@ typedef struct LdbTopKRow {
    int32_t pad;
    LdbI128 agg;
 } LdbTopKRow;
+/* The table's Bloom filter as a DEVICE buffer (NULL/0 for tiny tables): ranks that hold hash partitions of one
+ * logical build side OR their filters together (NCCL all_reduce BOR) so every rank can pre-filter its probe side. */
+int ldb_gpu_join_table_bloom(LdbState* s, void** dev_ptr, int64_t* bytes, LdbError* err);
 /* scan of the group-join map + Heap (include/lingodb/runtime/Heap.h): marked groups ordered by
  * (agg0 desc, side0 asc, key asc), first k */
 int ldb_gpu_join_table_topk(LdbState* s, int32_t k, LdbTopKRow* rows, int32_t* n_rows, LdbError* err);
@@ -184,8 +187,13 @@ enum LdbPipelineKind {
    /* K5  scan → filters → probe group-join map → atomic SUM into the entry, set marker (Q3) */
    LDB_PIPE_SCAN_PROBE_AGG = 4,
    /* K4  scan → filters → probe A → probe B (payload equality) → group by payload, SUM → GroupBy (Q5) */
-   LDB_PIPE_SCAN_PROBE2_GROUPBY = 5
+   LDB_PIPE_SCAN_PROBE2_GROUPBY = 5,
+   /* K8  scan → filters → [probe | Bloom-only semi-join] → append selected columns to dense device buffers
+    *     (subop.materialize into a rt::GrowingBuffer, GrowingBuffer.cpp:44, as compacted columns): the
+    *     tuple stream that K6 partitions for the all-to-all repartition step */
+   LDB_PIPE_SCAN_MATERIALIZE = 6
 };
+#define LDB_MAX_OUT_COLS 4
 typedef struct LdbPipelineDesc {
    int32_t kind; /* LdbPipelineKind */
    LdbTable* source;
@@ -208,6 +216,17 @@ typedef struct LdbPipelineDesc {
    int32_t n_side;
    const char* side_columns[LDB_MAX_SIDE];
    LdbState* sink; /* SimpleState | GroupBy | JoinTable (K5: the probed map itself) */
+   /* K8 materialize: out_columns[i] names a fixed-width source column, or "$payload" = the inline payload of
+    * probe 0; out_buffers[i] are DEVICE buffers of out_capacity rows (column width as in the source schema,
+    * 4 bytes for $payload); out_count is a DEVICE uint64 the kernel adds the number of appended rows to
+    * (rows beyond out_capacity are counted but not written → the caller regrows and reruns).
+    * probe_bloom_only != 0: probe 0 only consults the table's Bloom filter (semi-join reduction before a shuffle) */
+   int32_t n_out_cols;
+   const char* out_columns[LDB_MAX_OUT_COLS];
+   void* out_buffers[LDB_MAX_OUT_COLS];
+   int64_t out_capacity;
+   uint64_t* out_count;
+   int32_t probe_bloom_only;
 } LdbPipelineDesc;
 int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* desc, LdbError* err);
 

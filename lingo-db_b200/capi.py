@@ -14,7 +14,7 @@ PHYS = {"int32": 0, "int64": 1, "date32": 2, "decimal128": 3, "fsb4": 4, "utf8":
 MEM_HOST, MEM_DEVICE = 0, 1
 OPS = {"=": 0, "!=": 1, "<": 2, "<=": 3, ">": 4, ">=": 5}
 EXPR = {"col": 0, "mul": 1, "mul_1minus": 2, "mul_1minus_1plus": 3, "one": 4}
-PIPE = {"scan_reduce": 1, "scan_groupby": 2, "scan_build": 3, "scan_probe_agg": 4, "scan_probe2_groupby": 5}
+PIPE = {"scan_reduce": 1, "scan_groupby": 2, "scan_build": 3, "scan_probe_agg": 4, "scan_probe2_groupby": 5, "scan_materialize": 6}
 MAX_AGGS, MAX_KEYS, MAX_SIDE = 8, 2, 2
 
 
@@ -73,7 +73,9 @@ class PipelineDesc(C.Structure):
                 ("n_keys", C.c_int32), ("key_columns", C.c_char_p * MAX_KEYS), ("n_aggs", C.c_int32), ("aggs", AggDesc * MAX_AGGS),
                 ("n_probes", C.c_int32), ("probe_states", C.c_void_p * 2), ("probe_key_columns", C.c_char_p * 2),
                 ("build_key_column", C.c_char_p), ("build_payload_column", C.c_char_p), ("n_side", C.c_int32),
-                ("side_columns", C.c_char_p * MAX_SIDE), ("sink", C.c_void_p)]
+                ("side_columns", C.c_char_p * MAX_SIDE), ("sink", C.c_void_p),
+                ("n_out_cols", C.c_int32), ("out_columns", C.c_char_p * 4), ("out_buffers", C.c_void_p * 4), ("out_capacity", C.c_int64),
+                ("out_count", C.c_void_p), ("probe_bloom_only", C.c_int32)]
 
 
 class TpchTables(C.Structure):
@@ -123,6 +125,7 @@ SIGNATURES = {
     "ldb_gpu_groupby_merge_exported": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _E]),
     "ldb_gpu_join_table_create": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P), _E]),
     "ldb_gpu_join_table_count": (C.c_int, [_P, C.POINTER(C.c_int64), _E]),
+    "ldb_gpu_join_table_bloom": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64), _E]),
     "ldb_gpu_join_table_topk": (C.c_int, [_P, C.c_int32, C.POINTER(TopKRow), C.POINTER(C.c_int32), _E]),
     "ldb_gpu_run_pipeline": (C.c_int, [_P, C.POINTER(PipelineDesc), _E]),
     "ldb_gpu_partition_tuples": (C.c_int, [_P, _P, C.POINTER(_P), C.POINTER(C.c_int32), C.c_int32, C.c_int64, C.c_int32, _P, C.POINTER(_P), C.POINTER(C.c_int64), _E]),

@@ -33,12 +33,14 @@ struct SmemTile {
    const StagedCols* sc;
    __device__ __forceinline__ int32_t i32(int col, int lr) const { return ldShared32(stage + sc->smemOffset[col] + lr * 4); }
    __device__ __forceinline__ int64_t lo64(int col, int lr) const { return ldShared64(stage + sc->smemOffset[col] + lr * 16); }
+   __device__ __forceinline__ int64_t hi64(int col, int lr) const { return ldShared64(stage + sc->smemOffset[col] + lr * 16 + 8); }
 };
 struct GlobalTile {
    int64_t rowBase;
    const StagedCols* sc;
    __device__ __forceinline__ int32_t i32(int col, int lr) const { return ldStream32((const int32_t*) sc->base[col] + rowBase + lr); }
    __device__ __forceinline__ int64_t lo64(int col, int lr) const { return ldStream64((const int64_t*) sc->base[col] + 2 * (rowBase + lr)); }
+   __device__ __forceinline__ int64_t hi64(int col, int lr) const { return ldStream64((const int64_t*) sc->base[col] + 2 * (rowBase + lr) + 1); }
 };
 __device__ __forceinline__ void issueTile(const StagedCols& sc, uint8_t* smem, uint64_t* bars, int64_t tile, int s) {
    const uint64_t policy = evictFirstPolicy();
@@ -564,6 +566,59 @@ void launchScanBuild(const BuildParams& p, int smCount, cudaStream_t s) {
    size_t dyn;
    int grid = persistentGrid(scanBuildKernel, p.src.cols, p.src.nRows, smCount, &dyn);
    scanBuildKernel<<<grid, kBlock, dyn, s>>>(p);
+}
+
+// =================================================================================== K8 materialize
+// scan → filters → [probe / Bloom-only semi-join] → append the selected columns, compacted, to dense buffers
+// (subop.materialize; the reference appends row tuples to per-worker GrowingBuffers, GrowingBuffer.cpp:44 —
+//  here one warp-aggregated atomic claims the output range of all emitting lanes).
+__device__ __forceinline__ bool bloomMayContain(const JoinTableDev& t, int32_t key) {
+   if (!t.bloom) return true;
+   const uint64_t h = hashI32(key);
+   const uint32_t bits = bloomBits(h);
+   return (__ldg(&t.bloom[(uint32_t) (h >> 32) & t.bloomMask]) & bits) == bits;
+}
+__global__ void __launch_bounds__(kBlock, 4) scanMaterializeKernel(const __grid_constant__ MaterializeParams p) {
+   __shared__ __align__(8) uint64_t bars[kStages];
+   forEachRow(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
+      if (!(valid && evalFilters(p.src.filters, tile, lr, row))) return;
+      auto emit = [&](int32_t payload) {
+         const unsigned active = __activemask();
+         const int lane = threadIdx.x & 31, leader = __ffs(active) - 1;
+         unsigned long long base = 0;
+         if (lane == leader) base = atomicAdd(p.count, (unsigned long long) __popc(active));
+         base = __shfl_sync(active, base, leader);
+         const unsigned long long pos = base + __popc(active & ((1u << lane) - 1));
+         if (pos >= (unsigned long long) p.capacity) return;
+         for (int c = 0; c < p.nOut; c++) {
+            if (p.outStage[c] < 0) {
+               ((int32_t*) p.out[c])[pos] = payload;
+            } else if (p.outElem[c] == 4) {
+               ((int32_t*) p.out[c])[pos] = tile.i32(p.outStage[c], lr);
+            } else {
+               longlong2 v;
+               v.x = tile.lo64(p.outStage[c], lr);
+               v.y = tile.hi64(p.outStage[c], lr);
+               ((longlong2*) p.out[c])[pos] = v;
+            }
+         }
+      };
+      if (!p.hasProbe) {
+         emit(0);
+      } else {
+         const int32_t key = tile.i32(p.probeKeyStage, lr);
+         if (p.bloomOnly) {
+            if (bloomMayContain(p.probe, key)) emit(0);
+         } else {
+            joinProbe(p.probe, key, [&](int64_t, int32_t payload) { emit(payload); });
+         }
+      }
+   });
+}
+void launchScanMaterialize(const MaterializeParams& p, int smCount, cudaStream_t s) {
+   size_t dyn;
+   int grid = persistentGrid(scanMaterializeKernel, p.src.cols, p.src.nRows, smCount, &dyn);
+   scanMaterializeKernel<<<grid, kBlock, dyn, s>>>(p);
 }
 
 // =================================================================================== K5 probe + aggregate

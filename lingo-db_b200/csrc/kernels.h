@@ -121,6 +121,20 @@ struct Probe2GroupByParams {
    GroupTableDev groups; // keyed by the matched payload
 };
 
+constexpr int kMaxOutCols = 4;
+struct MaterializeParams {
+   ScanSource src;
+   int32_t hasProbe, bloomOnly;
+   JoinTableDev probe;
+   int32_t probeKeyStage;
+   int32_t nOut;
+   int32_t outStage[kMaxOutCols]; // staged column, or -1 = probe payload
+   int32_t outElem[kMaxOutCols];  // 4 or 16
+   void* out[kMaxOutCols];
+   int64_t capacity;
+   unsigned long long* count;
+};
+
 struct TopKRowDev {
    int32_t key, side0, side1, valid;
    unsigned long long aggLo;
@@ -132,6 +146,7 @@ bool launchScanGroupBy(const GroupByParams& p, int smCount, cudaStream_t s, cons
 void launchScanBuild(const BuildParams& p, int smCount, cudaStream_t s);
 bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, const char** why);
 bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStream_t s, const char** why);
+void launchScanMaterialize(const MaterializeParams& p, int smCount, cudaStream_t s);
 void launchJoinTopK(const JoinTableDev& t, int k, TopKRowDev* out, int* outBlocks, int smCount, cudaStream_t s);
 void launchFill64(unsigned long long* p, unsigned long long v, int64_t n, cudaStream_t s);
 void launchInsertTuples(const JoinTableDev& t, const int32_t* keys, const int32_t* payloads, const int32_t* side0, const int32_t* side1, int64_t n, int smCount, cudaStream_t s);

@@ -519,6 +519,13 @@ int ldb_gpu_join_table_count(LdbState* s, int64_t* n_entries, LdbError* err) {
       *n_entries = (int64_t) c;
    });
 }
+int ldb_gpu_join_table_bloom(LdbState* s, void** dev_ptr, int64_t* bytes, LdbError* err) {
+   return guarded(err, [&] {
+      if (!s || s->kind != LDB_STATE_JOIN_TABLE) fail(LDB_ERR_INVALID, "not a join table");
+      *dev_ptr = s->join.bloom;
+      *bytes = s->join.bloom ? ((int64_t) s->join.bloomMask + 1) * 4 : 0;
+   });
+}
 int ldb_gpu_join_table_topk(LdbState* s, int32_t k, LdbTopKRow* rows, int32_t* n_rows, LdbError* err) {
    return guarded(err, [&] {
       if (!s || s->kind != LDB_STATE_JOIN_TABLE || !s->nAggs) fail(LDB_ERR_INVALID, "not a group-join table");
@@ -850,6 +857,49 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                bool ok = true;
                ctx->launch("join_probe2_groupby", [&] { ok = launchScanProbe2GroupBy(p, ctx->smCount, ctx->compute, &why); });
                if (!ok) fail(LDB_ERR_UNSUPPORTED, why);
+            }
+            break;
+         }
+         case LDB_PIPE_SCAN_MATERIALIZE: {
+            if (d->n_out_cols < 1 || d->n_out_cols > kMaxOutCols) fail(LDB_ERR_INVALID, "n_out_cols out of range");
+            if (d->n_probes < 0 || d->n_probes > 1) fail(LDB_ERR_UNSUPPORTED, "materialize pipelines take at most one probe");
+            if (!d->out_count || d->out_capacity < 0) fail(LDB_ERR_INVALID, "materialize needs out_count and out_capacity");
+            LdbState* probe = d->n_probes ? wantState(d->probe_states[0], LDB_STATE_JOIN_TABLE, "probe") : nullptr;
+            int probeStage = 0;
+            if (probe) probeStage = sp.add(t, R.col(d->probe_key_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key"));
+            int outStage[kMaxOutCols], outElem[kMaxOutCols];
+            for (int c = 0; c < d->n_out_cols; c++) {
+               if (!d->out_columns[c] || !d->out_buffers[c]) fail(LDB_ERR_INVALID, "missing output column or buffer");
+               if (std::string(d->out_columns[c]) == "$payload") {
+                  if (!probe || d->probe_bloom_only) fail(LDB_ERR_INVALID, "$payload needs a full probe");
+                  outStage[c] = -1;
+                  outElem[c] = 4;
+               } else {
+                  int col = R.col(d->out_columns[c], {LDB_INT32, LDB_DATE32, LDB_FSB4, LDB_DECIMAL128}, "output column");
+                  outStage[c] = sp.add(t, col);
+                  outElem[c] = (int) elemWidth(t->columns[col].type);
+               }
+            }
+            for (auto& b : t->batches) {
+               if (b.nRows == 0) continue;
+               MaterializeParams p{};
+               p.src.nRows = b.nRows;
+               bindFilters(fp, b, p.src.filters);
+               sp.bind(t, b, p.src.cols);
+               p.hasProbe = probe ? 1 : 0;
+               p.bloomOnly = d->probe_bloom_only ? 1 : 0;
+               if (probe) p.probe = probe->join;
+               p.probeKeyStage = probeStage;
+               p.nOut = d->n_out_cols;
+               for (int c = 0; c < d->n_out_cols; c++) {
+                  p.outStage[c] = outStage[c];
+                  p.outElem[c] = outElem[c];
+                  p.out[c] = d->out_buffers[c];
+               }
+               p.capacity = d->out_capacity;
+               p.count = (unsigned long long*) d->out_count;
+               waitBatch(ctx, b);
+               ctx->launch("materialize", [&] { launchScanMaterialize(p, ctx->smCount, ctx->compute); });
             }
             break;
          }

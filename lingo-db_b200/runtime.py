@@ -217,3 +217,73 @@ def groupby_read(ctx: Context, state) -> list:
 
 def state_destroy(ctx: Context, state):
     ctx.L.ldb_gpu_state_destroy(state)
+
+
+# ---------------------------------------------------------------------- generic pipeline call
+def run_pipeline(ctx: Context, kind: str, source: Table, filters=(), keys=(), aggs=(), probes=(), build_key=None, build_payload=None,
+                 side=(), sink=None, out_columns=(), out_buffers=(), out_capacity=0, out_count=None, bloom_only=False):
+    """ldb_gpu_run_pipeline from keyword arguments.  filters: (column, op, value) with value str or int;
+    aggs: (expr, [columns]); probes: (state, key_column)."""
+    keep = []
+
+    def b(s):
+        if s is None:
+            return None
+        v = s.encode()
+        keep.append(v)
+        return v
+
+    d = capi.PipelineDesc()
+    d.kind = capi.PIPE[kind]
+    d.source = source.h
+    fl = (capi.FilterDesc * max(1, len(filters)))()
+    for i, (col, op, val) in enumerate(filters):
+        if isinstance(val, int):
+            fl[i] = capi.FilterDesc(b(col), capi.OPS[op], 1, None, val)
+        else:
+            fl[i] = capi.FilterDesc(b(col), capi.OPS[op], 0, b(val), 0)
+    d.n_filters, d.filters = len(filters), fl
+    d.n_keys = len(keys)
+    for i, k in enumerate(keys):
+        d.key_columns[i] = b(k)
+    d.n_aggs = len(aggs)
+    for i, (expr, cols) in enumerate(aggs):
+        d.aggs[i].expr = capi.EXPR[expr]
+        for j, c in enumerate(cols):
+            d.aggs[i].columns[j] = b(c)
+    d.n_probes = len(probes)
+    for i, (st, col) in enumerate(probes):
+        d.probe_states[i] = st
+        d.probe_key_columns[i] = b(col)
+    d.build_key_column, d.build_payload_column = b(build_key), b(build_payload)
+    d.n_side = len(side)
+    for i, c in enumerate(side):
+        d.side_columns[i] = b(c)
+    d.sink = sink
+    d.n_out_cols = len(out_columns)
+    for i, (c, buf) in enumerate(zip(out_columns, out_buffers)):
+        d.out_columns[i] = b(c)
+        d.out_buffers[i] = buf
+    d.out_capacity = out_capacity
+    d.out_count = out_count
+    d.probe_bloom_only = int(bloom_only)
+    e = Error()
+    check(ctx.L.ldb_gpu_run_pipeline(ctx.h, C.byref(d), C.byref(e)), e)
+
+
+def join_table(ctx: Context, expected_rows: int, unique: bool = True, n_side: int = 0, n_aggs: int = 0) -> C.c_void_p:
+    s, e = C.c_void_p(), Error()
+    check(ctx.L.ldb_gpu_join_table_create(ctx.h, int(expected_rows), int(unique), n_side, n_aggs, C.byref(s), C.byref(e)), e)
+    return s
+
+
+def join_count(ctx: Context, state) -> int:
+    n, e = C.c_int64(), Error()
+    check(ctx.L.ldb_gpu_join_table_count(state, C.byref(n), C.byref(e)), e)
+    return n.value
+
+
+def groupby_state(ctx: Context, n_keys: int, n_aggs: int, capacity: int = 64) -> C.c_void_p:
+    s, e = C.c_void_p(), Error()
+    check(ctx.L.ldb_gpu_groupby_create(ctx.h, n_keys, n_aggs, capacity, C.byref(s), C.byref(e)), e)
+    return s
