@@ -41,7 +41,7 @@ def _sources(exts):
 def _stamp(paths, extra=""):
     h = hashlib.sha256(extra.encode())
     for p in paths:
-        h.update(p.encode())
+        h.update(os.path.relpath(p, ROOT).encode())  # relative: the stamp must survive the move to the GPU box
         with open(p, "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()
@@ -63,7 +63,32 @@ def _run(cmd, verbose):
         print(r.stdout + r.stderr)
 
 
+class _Lock:
+    """One builder at a time (torchrun starts N ranks that all import the package)."""
+
+    def __enter__(self):
+        import fcntl
+        self.fh = open(os.path.join(HERE, ".build.lock"), "w")
+        fcntl.flock(self.fh, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *a):
+        import fcntl
+        fcntl.flock(self.fh, fcntl.LOCK_UN)
+        self.fh.close()
+
+
 def build_datagen_host(verbose=False, force=False):
+    with _Lock():
+        return _build_datagen_host(verbose, force)
+
+
+def build_gpu(verbose=False, force=False, ptxas_verbose=False):
+    with _Lock():
+        return _build_gpu(verbose, force, ptxas_verbose)
+
+
+def _build_datagen_host(verbose=False, force=False):
     srcs = [os.path.join(CSRC, "datagen_host.cpp")]
     deps = srcs + [os.path.join(CSRC, "tpch_gen.h"), os.path.join(INCLUDE, "ldb_datagen.h")]
     stamp = _stamp(deps)
@@ -74,11 +99,11 @@ def build_datagen_host(verbose=False, force=False):
     return GEN_LIB
 
 
-def build_gpu(verbose=False, force=False, ptxas_verbose=False):
+def _build_gpu(verbose=False, force=False, ptxas_verbose=False):
     cu = _sources((".cu",))
     cpp = [p for p in _sources((".cpp",)) if not p.endswith("datagen_host.cpp")]
     hdr = _sources((".h", ".cuh")) + [os.path.join(INCLUDE, f) for f in sorted(os.listdir(INCLUDE))]
-    stamp = _stamp(cu + cpp + hdr, " ".join(NVCC_FLAGS))
+    stamp = _stamp(cu + cpp + hdr, " ".join(NVCC_FLAGS).replace(ROOT, "$ROOT"))
     if not force and _up_to_date(GPU_LIB, stamp):
         return GPU_LIB
     objdir = os.path.join(HERE, "build")
@@ -102,7 +127,8 @@ def build_gpu(verbose=False, force=False, ptxas_verbose=False):
             print(out)
     if failed:
         raise RuntimeError("nvcc failed")
-    _run([NVCC, "-shared", "-cudart", "static", "-o", GPU_LIB] + objs, verbose)
+    _run([NVCC, "-shared", "-cudart", "static", "-o", GPU_LIB + ".tmp"] + objs, verbose)
+    os.replace(GPU_LIB + ".tmp", GPU_LIB)
     open(GPU_LIB + ".stamp", "w").write(stamp)
     return GPU_LIB
 

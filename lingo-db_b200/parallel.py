@@ -212,12 +212,16 @@ def q5_repartitioned(ctx, tables, world: int, rank: int, n_orders_total: int, re
             bp, nb = C.c_void_p(), C.c_int64()
             capi.check(L.ldb_gpu_join_table_bloom(ordp, C.byref(bp), C.byref(nb), C.byref(e)), e)
             if nb.value:
-                bloom = torch.empty(nb.value // 4, dtype=torch.int32, device=dev)
+                bloom = _device_view(bp.value, nb.value // 4, dev)  # zero-copy view of the table's own filter
                 ctx.synchronize()
-                _memcpy_d2d(bloom.data_ptr(), bp.value, nb.value)
-                dist.all_reduce(bloom, op=dist.ReduceOp.BOR)
+                gathered = torch.empty(world * bloom.numel(), dtype=torch.int32, device=dev)
+                dist.all_gather_into_tensor(gathered, bloom)  # NCCL has no bitwise-OR reduction: gather, then OR
+                gathered = gathered.view(world, -1)
+                acc = gathered[0]
+                for i in range(1, world):
+                    acc = acc | gathered[i]
+                bloom.copy_(acc)
                 torch.cuda.synchronize(dev)
-                _memcpy_d2d(bp.value, bloom.data_ptr(), nb.value)
         # lineitem share → Bloom semi-join → tuples → radix partition → all-to-all
         n_li = tables["lineitem"].num_rows
         (lk, ls, le, ld), n_l = _materialize(ctx, tables["lineitem"], ["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount"], [4, 4, 16, 16],
@@ -248,9 +252,12 @@ def q5_repartitioned(ctx, tables, world: int, rank: int, n_orders_total: int, re
             L.ldb_gpu_state_destroy(s)
 
 
-def _memcpy_d2d(dst: int, src: int, nbytes: int):
+class _CudaArray:
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+
+
+def _device_view(ptr: int, n_int32: int, dev):
+    """torch view (no copy) of device memory owned by libldb_gpu.so, so NCCL can work on it in place."""
     import torch
-    rt = torch.cuda.cudart()
-    rc = rt.cudaMemcpy(dst, src, nbytes, 3)  # cudaMemcpyDeviceToDevice
-    if int(rc) != 0:
-        raise RuntimeError(f"cudaMemcpy D2D failed: {rc}")
+    return torch.as_tensor(_CudaArray(ptr, n_int32), device=dev)
