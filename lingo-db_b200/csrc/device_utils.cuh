@@ -85,6 +85,7 @@ __device__ __forceinline__ void mbarInitFence() { asm volatile("fence.mbarrier_i
 __device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbarArrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory"); }
 __device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
    asm volatile(
       "{\n\t.reg .pred p;\n"

@@ -20,7 +20,7 @@
 
 namespace ldb {
 
-constexpr int kBlock = 256;
+constexpr int kBlock = kBlockThreads;
 
 // =================================================================================== tiles
 // A tile = kTileRows consecutive rows of every staged column.  Full tiles arrive in shared memory
@@ -42,69 +42,139 @@ struct GlobalTile {
    __device__ __forceinline__ int64_t lo64(int col, int lr) const { return ldStream64((const int64_t*) sc->base[col] + 2 * (rowBase + lr)); }
    __device__ __forceinline__ int64_t hi64(int col, int lr) const { return ldStream64((const int64_t*) sc->base[col] + 2 * (rowBase + lr) + 1); }
 };
-__device__ __forceinline__ void issueTile(const StagedCols& sc, uint8_t* smem, uint64_t* bars, int64_t tile, int s) {
+__device__ __forceinline__ void issueTile(const StagedCols& sc, uint8_t* smem, uint64_t* bars /* full[] */, int64_t tile, int s) {
    const uint64_t policy = evictFirstPolicy();
    mbarExpectTx(&bars[s], (uint32_t) sc.stageBytes);
    const uint32_t dst = smemAddr(smem) + (uint32_t) s * sc.stageBytes;
    for (int c = 0; c < sc.n; c++) {
-      const uint32_t bytes = (uint32_t) sc.elemBytes[c] * kTileRows;
+      const uint32_t bytes = (uint32_t) sc.elemBytes[c] * (uint32_t) sc.tileRows;
       bulkLoad(dst + sc.smemOffset[c], sc.base[c] + (size_t) tile * bytes, bytes, &bars[s], policy);
    }
 }
-// fn(tile, localRow, globalRow, valid) is called for every row with all 32 lanes of a warp converged
-// (lanes beyond the end of the table come with valid == false), so fn may use warp collectives.
-template <class Fn>
-__device__ __forceinline__ void forEachRow(const StagedCols& sc, int64_t n, uint8_t* smem, uint64_t* bars, const Fn& fn) {
-   constexpr int kRowsPerThread = kTileRows / kBlock;
+// fnTile(tile, rowBase, rowsInTile) is called once per tile by every CONSUMER thread (threadIdx.x < kBlock), warps converged.
+// Warp-specialised: the CTA has kBlock consumer threads plus one producer warp (kThreads = kBlock + 32).  The producer's
+// lane 0 refills a stage as soon as all consumer warps released it (`empty` mbarrier, one arrive per warp), so a warp
+// that finished its rows moves on to the next stage instead of idling at a CTA-wide barrier behind the slowest warp
+// (profiles/r1_ncu_sf100.md: 53 % of the probe kernel's stall samples were `stall_barrier` with __syncthreads()).
+constexpr int kWarps = kBlock / 32;
+constexpr int kThreads = kBlock + 32;
+struct TileBarriers {
+   uint64_t full[kStages];
+   uint64_t empty[kStages];
+};
+template <int kRowsPerThread, class Fn>
+__device__ __forceinline__ void forEachTile(const StagedCols& sc, int64_t n, uint8_t* smem, TileBarriers* bars, const Fn& fnTile) {
+   constexpr int kTileRows = kRowsPerThread * kBlock; // == sc.tileRows (host binds the same constant)
+   const int64_t nFull = n / kTileRows;
+   const bool producer = threadIdx.x >= kBlock;
+   if (sc.useTma) {
+      if (threadIdx.x == 0) {
+         for (int s = 0; s < kStages; s++) {
+            mbarInit(&bars->full[s], 1);
+            mbarInit(&bars->empty[s], kWarps);
+         }
+         mbarInitFence();
+      }
+      __syncthreads();
+      if (producer) {
+         if (threadIdx.x == kBlock) {
+            int it = 0;
+            for (int64_t t = blockIdx.x; t < nFull; t += gridDim.x, it++) {
+               const int s = it % kStages;
+               if (it >= kStages) mbarWait(&bars->empty[s], (uint32_t) (it / kStages - 1) & 1u);
+               issueTile(sc, smem, bars->full, t, s);
+            }
+         }
+      } else {
+         int it = 0;
+         for (int64_t t = blockIdx.x; t < nFull; t += gridDim.x, it++) {
+            const int s = it % kStages;
+            mbarWait(&bars->full[s], (uint32_t) (it / kStages) & 1u);
+            SmemTile tile{smemAddr(smem) + (uint32_t) s * sc.stageBytes, &sc};
+            fnTile(tile, t * kTileRows, kTileRows);
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbarArrive(&bars->empty[s]); // this warp is done with stage s
+         }
+      }
+   } else if (!producer) {
+      for (int64_t t = blockIdx.x; t < nFull; t += gridDim.x) {
+         __syncwarp();
+         GlobalTile tile{t * kTileRows, &sc};
+         fnTile(tile, t * kTileRows, kTileRows);
+      }
+   }
+   // the partial tail tile goes to the CTA that would have been next in the round robin
+   if (!producer && nFull * kTileRows < n && (int64_t) blockIdx.x == nFull % gridDim.x) {
+      __syncwarp();
+      GlobalTile tile{nFull * kTileRows, &sc};
+      fnTile(tile, nFull * kTileRows, (int) (n - nFull * kTileRows));
+   }
+}
+// Non-specialised variant for the arithmetic-bound group-by kernel (K1/K2): every row costs the same, so the CTA-wide
+// barrier is cheap (stall_barrier 0.1 per issue) and a 9th warp would only cost registers (2 CTAs x 288 threads
+// cap the kernel at 112 registers → spills).  One elected thread issues the copies, __syncthreads() recycles a stage.
+template <int kRowsPerThread, class Fn>
+__device__ __forceinline__ void forEachTileUniform(const StagedCols& sc, int64_t n, uint8_t* smem, TileBarriers* bars, const Fn& fnTile) {
+   constexpr int kTileRows = kRowsPerThread * kBlock;
    const int64_t nFull = n / kTileRows;
    if (sc.useTma) {
       if (threadIdx.x == 0) {
-         for (int s = 0; s < kStages; s++) mbarInit(&bars[s], 1);
+         for (int s = 0; s < kStages; s++) mbarInit(&bars->full[s], 1);
          mbarInitFence();
       }
       __syncthreads();
       if (threadIdx.x == 0) {
          for (int s = 0; s < kStages; s++) {
             int64_t t = (int64_t) blockIdx.x + (int64_t) s * gridDim.x;
-            if (t < nFull) issueTile(sc, smem, bars, t, s);
+            if (t < nFull) issueTile(sc, smem, bars->full, t, s);
          }
       }
       int it = 0;
       for (int64_t t = blockIdx.x; t < nFull; t += gridDim.x, it++) {
          const int s = it % kStages;
-         mbarWait(&bars[s], (uint32_t) (it / kStages) & 1u);
+         mbarWait(&bars->full[s], (uint32_t) (it / kStages) & 1u);
          SmemTile tile{smemAddr(smem) + (uint32_t) s * sc.stageBytes, &sc};
-#pragma unroll
-         for (int j = 0; j < kRowsPerThread; j++) {
-            const int lr = j * kBlock + threadIdx.x;
-            fn(tile, lr, t * kTileRows + lr, true);
-         }
+         fnTile(tile, t * kTileRows, kTileRows);
          __syncthreads(); // every thread is done with stage s → refill it
          const int64_t nt = t + (int64_t) kStages * gridDim.x;
-         if (threadIdx.x == 0 && nt < nFull) issueTile(sc, smem, bars, nt, s);
+         if (threadIdx.x == 0 && nt < nFull) issueTile(sc, smem, bars->full, nt, s);
       }
    } else {
       for (int64_t t = blockIdx.x; t < nFull; t += gridDim.x) {
          __syncwarp();
          GlobalTile tile{t * kTileRows, &sc};
-#pragma unroll
-         for (int j = 0; j < kRowsPerThread; j++) {
-            const int lr = j * kBlock + threadIdx.x;
-            fn(tile, lr, t * kTileRows + lr, true);
-         }
+         fnTile(tile, t * kTileRows, kTileRows);
       }
    }
-   // the partial tail tile goes to the CTA that would have been next in the round robin
    if (nFull * kTileRows < n && (int64_t) blockIdx.x == nFull % gridDim.x) {
       __syncwarp();
       GlobalTile tile{nFull * kTileRows, &sc};
+      fnTile(tile, nFull * kTileRows, (int) (n - nFull * kTileRows));
+   }
+}
+template <int kRowsPerThread, class Fn>
+__device__ __forceinline__ void forEachRowUniform(const StagedCols& sc, int64_t n, uint8_t* smem, TileBarriers* bars, const Fn& fn) {
+   forEachTileUniform<kRowsPerThread>(sc, n, smem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
 #pragma unroll
       for (int j = 0; j < kRowsPerThread; j++) {
          const int lr = j * kBlock + threadIdx.x;
-         const bool valid = tile.rowBase + lr < n;
-         fn(tile, valid ? lr : 0, tile.rowBase + (valid ? lr : 0), valid);
+         const bool valid = lr < rows;
+         fn(tile, valid ? lr : 0, rowBase + (valid ? lr : 0), valid);
       }
-   }
+   });
+}
+// fn(tile, localRow, globalRow, valid) is called for every row with all 32 lanes of a warp converged
+// (lanes beyond the end of the table come with valid == false), so fn may use warp collectives.
+template <int kRowsPerThread, class Fn>
+__device__ __forceinline__ void forEachRow(const StagedCols& sc, int64_t n, uint8_t* smem, TileBarriers* bars, const Fn& fn) {
+   forEachTile<kRowsPerThread>(sc, n, smem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; j++) {
+         const int lr = j * kBlock + threadIdx.x;
+         const bool valid = lr < rows;
+         fn(tile, valid ? lr : 0, rowBase + (valid ? lr : 0), valid);
+      }
+   });
 }
 
 // =================================================================================== filters
@@ -212,7 +282,35 @@ __device__ int64_t joinInsert(const JoinTableDev& t, int32_t key, int32_t payloa
    atomicExch(t.error, 1);
    return -1;
 }
-// probe (SubOpToControlFlow.cpp:2558-2586 + chain walk :2254-2313): visit every entry with the key
+// probe (SubOpToControlFlow.cpp:2558-2586 + chain walk :2254-2313): visit every entry with the key.
+// Split in two so a thread can put the Bloom loads of ALL its rows in flight before it consumes the first one.
+struct BloomProbe {
+   uint64_t h;
+   uint32_t word, bits;
+   __device__ __forceinline__ bool mayContain() const { return (word & bits) == bits; }
+};
+__device__ __forceinline__ BloomProbe bloomPrefetch(const JoinTableDev& t, int32_t key, bool wanted) {
+   BloomProbe b;
+   b.h = hashI32(key);
+   b.bits = t.bloom ? bloomBits(b.h) : 0u;
+   b.word = (t.bloom && wanted) ? __ldg(&t.bloom[(uint32_t) (b.h >> 32) & t.bloomMask]) : (wanted ? ~0u : 0u);
+   if (!wanted) b.bits = 1u; // word == 0 → mayContain() false
+   return b;
+}
+template <class Fn>
+__device__ __forceinline__ void joinProbeSlots(const JoinTableDev& t, int32_t key, uint64_t h, const Fn& fn) {
+   uint64_t s = h & t.mask;
+   const uint64_t limit = t.mask < kMaxProbe ? t.mask + 1 : kMaxProbe;
+   for (uint64_t probes = 0; probes < limit; probes++) {
+      unsigned long long e = __ldg(&t.slots[s]);
+      if (e == kEmptySlot) return;
+      if ((int32_t) (uint32_t) e == key) {
+         fn((int64_t) s, (int32_t) (uint32_t) (e >> 32));
+         if (t.unique) return;
+      }
+      s = (s + 1) & t.mask;
+   }
+}
 template <class Fn>
 __device__ __forceinline__ void joinProbe(const JoinTableDev& t, int32_t key, const Fn& fn) {
    const uint64_t h = hashI32(key);
@@ -339,7 +437,8 @@ __global__ void __launch_bounds__(kBlock, 2) scanGroupByKernel(const __grid_cons
    __shared__ int32_t sSlot[LG];
    __shared__ int32_t sCount, sLock;
    __shared__ unsigned long long sAcc[LG][N][2];
-   __shared__ __align__(8) uint64_t bars[kStages];
+   __shared__ __align__(8) TileBarriers barsStorage;
+   TileBarriers* bars = &barsStorage;
 
    for (int i = threadIdx.x; i < LG * N * 2; i += kBlock) (&sAcc[0][0][0])[i] = 0;
    if (threadIdx.x == 0) {
@@ -361,7 +460,7 @@ __global__ void __launch_bounds__(kBlock, 2) scanGroupByKernel(const __grid_cons
 #pragma unroll
    for (int g = 0; g < GREG; g++) rk0[g] = rk1[g] = 0;
 
-   forEachRow(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
+   forEachRowUniform<kRowsPerThreadScan>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
       int64_t vals[NV];
 #pragma unroll
       for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lr);
@@ -480,19 +579,19 @@ static std::string signature(const GroupByParams& p) {
 }
 // persistent grid: SMs x resident CTAs of this instantiation (occupancy API), never more than the tiles
 template <class K>
-static int persistentGrid(K kernel, const StagedCols& sc, int64_t nRows, int smCount, size_t* dynBytes) {
+static int persistentGrid(K kernel, const StagedCols& sc, int64_t nRows, int smCount, size_t* dynBytes, int threads = kThreads) {
    *dynBytes = sc.useTma ? (size_t) kStages * sc.stageBytes : 0;
    if (*dynBytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) *dynBytes);
    int perSm = 1;
-   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kBlock, *dynBytes);
+   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, threads, *dynBytes);
    if (perSm < 1) perSm = 1;
-   int64_t tiles = (nRows + kTileRows - 1) / kTileRows;
+   int64_t tiles = (nRows + sc.tileRows - 1) / sc.tileRows;
    return (int) std::min<int64_t>(std::max<int64_t>(tiles, 1), (int64_t) smCount * perSm);
 }
 template <int NK, int NV, class... As>
 static void launchGB(const GroupByParams& p, int smCount, cudaStream_t s) {
    size_t dyn;
-   int grid = persistentGrid(scanGroupByKernel<NK, NV, As...>, p.src.cols, p.src.nRows, smCount, &dyn);
+   int grid = persistentGrid(scanGroupByKernel<NK, NV, As...>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
    scanGroupByKernel<NK, NV, As...><<<grid, kBlock, dyn, s>>>(p);
 }
 using C0 = Agg<LDB_EXPR_COL, 0>;
@@ -540,10 +639,11 @@ __device__ __forceinline__ void flushInsertCount(const JoinTableDev& t, unsigned
 // scan → filters → [probe parent table] → insert {key, payload, side…}
 // (subop.materialize + rt::GrowingBuffer::insert + rt::HashIndexedView::build; for the group-join
 //  the lookup_or_insert of the left input, RelAlgToSubOp.cpp:2682-2950)
-__global__ void __launch_bounds__(kBlock, 4) scanBuildKernel(const __grid_constant__ BuildParams p) {
-   __shared__ __align__(8) uint64_t bars[kStages];
+__global__ void __launch_bounds__(kThreads, 4) scanBuildKernel(const __grid_constant__ BuildParams p) {
+   __shared__ __align__(8) TileBarriers barsStorage;
+   TileBarriers* bars = &barsStorage;
    unsigned long long inserted = 0;
-   forEachRow(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
+   forEachRow<kRowsPerThreadProbe>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
       if (!(valid && evalFilters(p.src.filters, tile, lr, row))) return;
       const int32_t key = tile.i32(p.keyStage, lr);
       auto insert = [&](int32_t payload) {
@@ -565,7 +665,7 @@ __global__ void __launch_bounds__(kBlock, 4) scanBuildKernel(const __grid_consta
 void launchScanBuild(const BuildParams& p, int smCount, cudaStream_t s) {
    size_t dyn;
    int grid = persistentGrid(scanBuildKernel, p.src.cols, p.src.nRows, smCount, &dyn);
-   scanBuildKernel<<<grid, kBlock, dyn, s>>>(p);
+   scanBuildKernel<<<grid, kThreads, dyn, s>>>(p);
 }
 
 // =================================================================================== K8 materialize
@@ -578,9 +678,10 @@ __device__ __forceinline__ bool bloomMayContain(const JoinTableDev& t, int32_t k
    const uint32_t bits = bloomBits(h);
    return (__ldg(&t.bloom[(uint32_t) (h >> 32) & t.bloomMask]) & bits) == bits;
 }
-__global__ void __launch_bounds__(kBlock, 4) scanMaterializeKernel(const __grid_constant__ MaterializeParams p) {
-   __shared__ __align__(8) uint64_t bars[kStages];
-   forEachRow(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
+__global__ void __launch_bounds__(kThreads, 4) scanMaterializeKernel(const __grid_constant__ MaterializeParams p) {
+   __shared__ __align__(8) TileBarriers barsStorage;
+   TileBarriers* bars = &barsStorage;
+   forEachRow<kRowsPerThreadProbe>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
       if (!(valid && evalFilters(p.src.filters, tile, lr, row))) return;
       auto emit = [&](int32_t payload) {
          const unsigned active = __activemask();
@@ -618,7 +719,7 @@ __global__ void __launch_bounds__(kBlock, 4) scanMaterializeKernel(const __grid_
 void launchScanMaterialize(const MaterializeParams& p, int smCount, cudaStream_t s) {
    size_t dyn;
    int grid = persistentGrid(scanMaterializeKernel, p.src.cols, p.src.nRows, smCount, &dyn);
-   scanMaterializeKernel<<<grid, kBlock, dyn, s>>>(p);
+   scanMaterializeKernel<<<grid, kThreads, dyn, s>>>(p);
 }
 
 // =================================================================================== K5 probe + aggregate
@@ -626,19 +727,37 @@ void launchScanMaterialize(const MaterializeParams& p, int smCount, cudaStream_t
 // takes a per-entry spin lock (SubOpToControlFlow.cpp:4218-4251, EntryLock.cpp:9-25) or an
 // atomic_rmw; here the i128 SUM is two 64-bit atomics with carry (exact, order independent).
 template <int NV>
-__global__ void __launch_bounds__(kBlock, 4) scanProbeAggKernel(const __grid_constant__ ProbeAggParams p) {
-   __shared__ __align__(8) uint64_t bars[kStages];
+__global__ void __launch_bounds__(kThreads, 4) scanProbeAggKernel(const __grid_constant__ ProbeAggParams p) {
+   __shared__ __align__(8) TileBarriers barsStorage;
+   TileBarriers* bars = &barsStorage;
    const int64_t one = 100;
-   forEachRow(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
-      if (!(valid && evalFilters(p.src.filters, tile, lr, row))) return;
-      joinProbe(p.table, tile.i32(p.probeKeyStage, lr), [&](int64_t slot, int32_t) {
-         int64_t vals[NV];
+   forEachTile<kRowsPerThreadProbe>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+      int32_t key[kRowsPerThreadProbe];
+      int lrs[kRowsPerThreadProbe];
+      BloomProbe bp[kRowsPerThreadProbe];
+      // phase A: filters + hash + Bloom load of every row of this thread (all loads in flight together)
 #pragma unroll
-         for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lr);
-         i128 v = evalAggDyn(p.agg, vals, one);
-         atomicAdd128(&p.table.aggLo[slot], &p.table.aggHi[slot], v);
-         p.table.marker[slot] = 1;
-      });
+      for (int j = 0; j < kRowsPerThreadProbe; j++) {
+         const int lr = j * kBlock + threadIdx.x;
+         const bool valid = lr < rows;
+         lrs[j] = valid ? lr : 0;
+         const bool ok = valid && evalFilters(p.src.filters, tile, lrs[j], rowBase + lrs[j]);
+         key[j] = tile.i32(p.probeKeyStage, lrs[j]);
+         bp[j] = bloomPrefetch(p.table, key[j], ok);
+      }
+      // phase B: the few survivors walk the directory and add into the shared entry
+#pragma unroll
+      for (int j = 0; j < kRowsPerThreadProbe; j++) {
+         if (!bp[j].mayContain()) continue;
+         joinProbeSlots(p.table, key[j], bp[j].h, [&](int64_t slot, int32_t) {
+            int64_t vals[NV];
+#pragma unroll
+            for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lrs[j]);
+            i128 v = evalAggDyn(p.agg, vals, one);
+            atomicAdd128(&p.table.aggLo[slot], &p.table.aggHi[slot], v);
+            p.table.marker[slot] = 1;
+         });
+      }
    });
 }
 bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, const char** why) {
@@ -650,13 +769,13 @@ bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, co
    size_t dyn;
    if (nv == 1) {
       int grid = persistentGrid(scanProbeAggKernel<1>, p.src.cols, p.src.nRows, smCount, &dyn);
-      scanProbeAggKernel<1><<<grid, kBlock, dyn, s>>>(p);
+      scanProbeAggKernel<1><<<grid, kThreads, dyn, s>>>(p);
    } else if (nv == 2) {
       int grid = persistentGrid(scanProbeAggKernel<2>, p.src.cols, p.src.nRows, smCount, &dyn);
-      scanProbeAggKernel<2><<<grid, kBlock, dyn, s>>>(p);
+      scanProbeAggKernel<2><<<grid, kThreads, dyn, s>>>(p);
    } else {
       int grid = persistentGrid(scanProbeAggKernel<3>, p.src.cols, p.src.nRows, smCount, &dyn);
-      scanProbeAggKernel<3><<<grid, kBlock, dyn, s>>>(p);
+      scanProbeAggKernel<3><<<grid, kThreads, dyn, s>>>(p);
    }
    return true;
 }
@@ -665,22 +784,45 @@ bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, co
 // scan → probe A on keyA → probe B on keyB → keep rows whose payloads agree (the composite join key
 // (l_suppkey, c_nationkey) = (s_suppkey, s_nationkey) of Q5) → group by that payload → SUM.
 template <int NV>
-__global__ void __launch_bounds__(kBlock, 4) scanProbe2GroupByKernel(const __grid_constant__ Probe2GroupByParams p) {
-   __shared__ __align__(8) uint64_t bars[kStages];
+__global__ void __launch_bounds__(kThreads, 4) scanProbe2GroupByKernel(const __grid_constant__ Probe2GroupByParams p) {
+   __shared__ __align__(8) TileBarriers barsStorage;
+   TileBarriers* bars = &barsStorage;
    const int64_t one = 100;
-   forEachRow(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
-      if (!(valid && evalFilters(p.src.filters, tile, lr, row))) return;
-      joinProbe(p.tableA, tile.i32(p.keyStageA, lr), [&](int64_t, int32_t payA) {
-         joinProbe(p.tableB, tile.i32(p.keyStageB, lr), [&](int64_t, int32_t payB) {
-            if (payA != payB) return;
-            int64_t vals[NV];
+   forEachTile<kRowsPerThreadProbe>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+      int32_t key[kRowsPerThreadProbe];
+      int lrs[kRowsPerThreadProbe];
+      BloomProbe bp[kRowsPerThreadProbe];
 #pragma unroll
-            for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lr);
-            int32_t kk[2] = {payB, 0};
-            int slot = groupLookupOrInsert(p.groups, kk);
-            if (slot >= 0) groupAtomicAdd(p.groups, slot, 0, evalAggDyn(p.agg, vals, one), p.agg.expr == LDB_EXPR_COL || p.agg.expr == LDB_EXPR_ONE);
+      for (int j = 0; j < kRowsPerThreadProbe; j++) { // phase A: Bloom filter of table A for every row (loads in flight together)
+         const int lr = j * kBlock + threadIdx.x;
+         const bool valid = lr < rows;
+         lrs[j] = valid ? lr : 0;
+         const bool ok = valid && evalFilters(p.src.filters, tile, lrs[j], rowBase + lrs[j]);
+         key[j] = tile.i32(p.keyStageA, lrs[j]);
+         bp[j] = bloomPrefetch(p.tableA, key[j], ok);
+      }
+      int32_t keyB[kRowsPerThreadProbe];
+      BloomProbe bpB[kRowsPerThreadProbe];
+#pragma unroll
+      for (int j = 0; j < kRowsPerThreadProbe; j++) { // phase B: survivors consult table B's filter (the plan puts the smaller table first)
+         keyB[j] = tile.i32(p.keyStageB, lrs[j]);
+         bpB[j] = bloomPrefetch(p.tableB, keyB[j], bp[j].mayContain());
+      }
+#pragma unroll
+      for (int j = 0; j < kRowsPerThreadProbe; j++) { // phase C: the few rows both filters let through walk the directories
+         if (!bpB[j].mayContain()) continue;
+         joinProbeSlots(p.tableA, key[j], bp[j].h, [&](int64_t, int32_t payA) {
+            joinProbeSlots(p.tableB, keyB[j], bpB[j].h, [&](int64_t, int32_t payB) {
+               if (payA != payB) return;
+               int64_t vals[NV];
+#pragma unroll
+               for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lrs[j]);
+               int32_t kk[2] = {payB, 0};
+               int slot = groupLookupOrInsert(p.groups, kk);
+               if (slot >= 0) groupAtomicAdd(p.groups, slot, 0, evalAggDyn(p.agg, vals, one), p.agg.expr == LDB_EXPR_COL || p.agg.expr == LDB_EXPR_ONE);
+            });
          });
-      });
+      }
    });
 }
 bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStream_t s, const char** why) {
@@ -692,13 +834,13 @@ bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStre
    size_t dyn;
    if (nv == 1) {
       int grid = persistentGrid(scanProbe2GroupByKernel<1>, p.src.cols, p.src.nRows, smCount, &dyn);
-      scanProbe2GroupByKernel<1><<<grid, kBlock, dyn, s>>>(p);
+      scanProbe2GroupByKernel<1><<<grid, kThreads, dyn, s>>>(p);
    } else if (nv == 2) {
       int grid = persistentGrid(scanProbe2GroupByKernel<2>, p.src.cols, p.src.nRows, smCount, &dyn);
-      scanProbe2GroupByKernel<2><<<grid, kBlock, dyn, s>>>(p);
+      scanProbe2GroupByKernel<2><<<grid, kThreads, dyn, s>>>(p);
    } else {
       int grid = persistentGrid(scanProbe2GroupByKernel<3>, p.src.cols, p.src.nRows, smCount, &dyn);
-      scanProbe2GroupByKernel<3><<<grid, kBlock, dyn, s>>>(p);
+      scanProbe2GroupByKernel<3><<<grid, kThreads, dyn, s>>>(p);
    }
    return true;
 }

@@ -60,11 +60,14 @@ struct JoinTableDev {
 // (kTileRows rows) into shared memory with TMA bulk copies (cp.async.bulk + mbarrier, 2 stages), so
 // each column byte crosses HBM→SM exactly once and no per-row global address arithmetic is issued.
 constexpr int kMaxStagedCols = 8;
-constexpr int kTileRows = 512;
+constexpr int kBlockThreads = 256;
+constexpr int kRowsPerThreadScan = 2;  // K1/K2: arithmetic-heavy, fewer/larger tiles
+constexpr int kRowsPerThreadProbe = 2; // K3/K4/K5/K8 (1 row/thread with 2x the CTAs measured slower: 11.8 vs 11.4 ms on Q3)
 constexpr int kStages = 2;
 struct StagedCols {
    int32_t n;
-   int32_t stageBytes; // bytes of one stage = sum(elemBytes) * kTileRows
+   int32_t tileRows;   // rows per tile = kBlockThreads * rows-per-thread of the kernel
+   int32_t stageBytes; // bytes of one stage = sum(elemBytes) * tileRows
    int32_t useTma;     // 0 when a column base is not 16-byte aligned: tiles are then read with plain loads
    const uint8_t* base[kMaxStagedCols];
    int32_t elemBytes[kMaxStagedCols];  // 4 (int32/date32/fsb4) or 16 (decimal128)

@@ -586,15 +586,16 @@ struct StagePlan {
       colIdx[n] = col;
       return n++;
    }
-   void bind(LdbTable* t, const LdbBatch& b, StagedCols& out) const {
+   void bind(LdbTable* t, const LdbBatch& b, StagedCols& out, int rowsPerThread) const {
       out.n = n;
+      out.tileRows = kBlockThreads * rowsPerThread;
       int off = 0;
       bool aligned = true;
       for (int i = 0; i < n; i++) {
          out.base[i] = (const uint8_t*) b.data[colIdx[i]];
          out.elemBytes[i] = (int32_t) elemWidth(t->columns[colIdx[i]].type);
          out.smemOffset[i] = off;
-         off += out.elemBytes[i] * kTileRows;
+         off += out.elemBytes[i] * out.tileRows;
          aligned &= ((uintptr_t) out.base[i] % 16) == 0;
       }
       out.stageBytes = off;
@@ -755,7 +756,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                GroupByParams p{};
                p.src.nRows = b.nRows;
                bindFilters(fp, b, p.src.filters);
-               sp.bind(t, b, p.src.cols);
+               sp.bind(t, b, p.src.cols, kRowsPerThreadScan);
                p.nKeys = nKeys;
                for (int k = 0; k < nKeys; k++) p.keyStage[k] = keyStage[k];
                p.nValueCols = ap.nValueCols;
@@ -788,7 +789,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                BuildParams p{};
                p.src.nRows = b.nRows;
                bindFilters(fp, b, p.src.filters);
-               sp.bind(t, b, p.src.cols);
+               sp.bind(t, b, p.src.cols, kRowsPerThreadProbe);
                p.keyStage = keyStage;
                p.payloadStage = payStage;
                p.nSide = d->n_side;
@@ -817,7 +818,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                ProbeAggParams p{};
                p.src.nRows = b.nRows;
                bindFilters(fp, b, p.src.filters);
-               sp.bind(t, b, p.src.cols);
+               sp.bind(t, b, p.src.cols, kRowsPerThreadProbe);
                p.probeKeyStage = probeStage;
                p.table = table->join;
                p.agg = ap.aggs[0];
@@ -845,7 +846,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                Probe2GroupByParams p{};
                p.src.nRows = b.nRows;
                bindFilters(fp, b, p.src.filters);
-               sp.bind(t, b, p.src.cols);
+               sp.bind(t, b, p.src.cols, kRowsPerThreadProbe);
                p.keyStageA = stageA;
                p.keyStageB = stageB;
                p.tableA = ta->join;
@@ -885,7 +886,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                MaterializeParams p{};
                p.src.nRows = b.nRows;
                bindFilters(fp, b, p.src.filters);
-               sp.bind(t, b, p.src.cols);
+               sp.bind(t, b, p.src.cols, kRowsPerThreadProbe);
                p.hasProbe = probe ? 1 : 0;
                p.bloomOnly = d->probe_bloom_only ? 1 : 0;
                if (probe) p.probe = probe->join;

@@ -310,10 +310,11 @@ int ldb_tpch_q5(LdbContext* ctx, const LdbTpchTables* t, const char* regionName,
       dl.kind = LDB_PIPE_SCAN_PROBE2_GROUPBY;
       dl.source = t->lineitem;
       dl.n_probes = 2;
-      dl.probe_states[0] = ord;
-      dl.probe_key_columns[0] = "l_orderkey";
-      dl.probe_states[1] = supp;
-      dl.probe_key_columns[1] = "l_suppkey";
+      // cheapest filter first: the supplier table (and its Bloom filter) is ~20x smaller than the orders table
+      dl.probe_states[0] = supp;
+      dl.probe_key_columns[0] = "l_suppkey";
+      dl.probe_states[1] = ord;
+      dl.probe_key_columns[1] = "l_orderkey";
       dl.n_aggs = 1;
       dl.aggs[0] = agg(LDB_EXPR_MUL_1MINUS, "l_extendedprice", "l_discount");
       dl.sink = groups;
