@@ -217,11 +217,22 @@ __device__ __forceinline__ uint64_t groupHash(const int32_t* k, int nKeys) {
    return h;
 }
 // lookup-or-insert (lowering of subop.lookup_or_insert, SubOpToControlFlow.cpp:3065-3157, as open addressing)
+__device__ __forceinline__ int32_t ldAcquire32(const int32_t* p) {
+   int32_t v;
+   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+   return v;
+}
 __device__ int groupLookupOrInsert(const GroupTableDev& t, const int32_t* k) {
    if (t.nKeys == 0) return 0;
    uint32_t mask = (uint32_t) t.capacity - 1;
    uint32_t s = (uint32_t) groupHash(k, t.nKeys) & mask;
    for (int probes = 0; probes < t.capacity; probes++) {
+      // fast path: the group exists (every row after the first of its group) — one acquire load, no CAS, no fence
+      if (ldAcquire32(&t.state[s]) == 2) {
+         if (t.keys[s * kMaxKeys] == k[0] && (t.nKeys < 2 || t.keys[s * kMaxKeys + 1] == k[1])) return (int) s;
+         s = (s + 1) & mask;
+         continue;
+      }
       int st = atomicCAS(&t.state[s], 0, 1);
       if (st == 0) {
          t.keys[s * kMaxKeys + 0] = k[0];
@@ -258,17 +269,22 @@ __device__ __forceinline__ uint32_t bloomBits(uint64_t h) {
 __device__ __forceinline__ unsigned long long packSlot(int32_t key, int32_t payload) { return ((unsigned long long) (uint32_t) payload << 32) | (uint32_t) key; }
 // HashIndexedView::build's CAS push-front (LazyJoinHashtable.cpp:20-31) becomes a CAS into an open-addressing
 // slot.  The caller counts successful inserts (one atomic per warp at kernel end, not one per tuple).
+__device__ __forceinline__ unsigned long long* slotPtr(const JoinTableDev& t, uint64_t s) { return (unsigned long long*) (t.base + s * t.stride); }
 __device__ int64_t joinInsert(const JoinTableDev& t, int32_t key, int32_t payload) {
    unsigned long long packed = packSlot(key, payload);
    if (packed == kEmptySlot) { // (-1,-1) is the empty marker and cannot be stored
       atomicExch(t.error, 3);
       return -1;
    }
+   if (t.stride == 32 && payload < 0) { // bit 31 of the payload word is the group-join marker
+      atomicExch(t.error, 4);
+      return -1;
+   }
    const uint64_t h = hashI32(key);
    uint64_t s = h & t.mask;
    const uint64_t limit = t.mask < kMaxProbe ? t.mask + 1 : kMaxProbe; // a sanely loaded table never probes this far
    for (uint64_t probes = 0; probes < limit; probes++) {
-      unsigned long long old = atomicCAS(&t.slots[s], kEmptySlot, packed);
+      unsigned long long old = atomicCAS(slotPtr(t, s), kEmptySlot, packed);
       if (old == kEmptySlot) {
          if (t.bloom) atomicOr(&t.bloom[(uint32_t) (h >> 32) & t.bloomMask], bloomBits(h));
          return (int64_t) s;
@@ -302,7 +318,7 @@ __device__ __forceinline__ void joinProbeSlots(const JoinTableDev& t, int32_t ke
    uint64_t s = h & t.mask;
    const uint64_t limit = t.mask < kMaxProbe ? t.mask + 1 : kMaxProbe;
    for (uint64_t probes = 0; probes < limit; probes++) {
-      unsigned long long e = __ldg(&t.slots[s]);
+      unsigned long long e = __ldg(slotPtr(t, s));
       if (e == kEmptySlot) return;
       if ((int32_t) (uint32_t) e == key) {
          fn((int64_t) s, (int32_t) (uint32_t) (e >> 32));
@@ -321,10 +337,10 @@ __device__ __forceinline__ void joinProbe(const JoinTableDev& t, int32_t key, co
    uint64_t s = h & t.mask;
    const uint64_t limit = t.mask < kMaxProbe ? t.mask + 1 : kMaxProbe;
    for (uint64_t probes = 0; probes < limit; probes++) {
-      unsigned long long e = __ldg(&t.slots[s]);
+      unsigned long long e = __ldg(slotPtr(t, s));
       if (e == kEmptySlot) return;
       if ((int32_t) (uint32_t) e == key) {
-         fn((int64_t) s, (int32_t) (uint32_t) (e >> 32));
+         fn((int64_t) s, (int32_t) ((uint32_t) (e >> 32) & (t.stride == 32 ? 0x7fffffffu : 0xffffffffu))); // wide tables keep the marker in bit 31
          if (t.unique) return;
       }
       s = (s + 1) & t.mask;
@@ -650,7 +666,8 @@ __global__ void __launch_bounds__(kThreads, 4) scanBuildKernel(const __grid_cons
          int64_t slot = joinInsert(p.sink, key, payload);
          if (slot >= 0) {
             inserted++;
-            for (int k = 0; k < p.nSide; k++) p.sink.side[k][slot] = tile.i32(p.sideStage[k], lr);
+            int32_t* lanes = (int32_t*) (p.sink.base + (uint64_t) slot * 32 + 8); // side0, side1 of the 32-byte entry
+            for (int k = 0; k < p.nSide; k++) lanes[k] = tile.i32(p.sideStage[k], lr);
          }
       };
       const int32_t ownPayload = p.payloadStage >= 0 ? tile.i32(p.payloadStage, lr) : 0;
@@ -749,13 +766,14 @@ __global__ void __launch_bounds__(kThreads, 4) scanProbeAggKernel(const __grid_c
 #pragma unroll
       for (int j = 0; j < kRowsPerThreadProbe; j++) {
          if (!bp[j].mayContain()) continue;
-         joinProbeSlots(p.table, key[j], bp[j].h, [&](int64_t slot, int32_t) {
+         joinProbeSlots(p.table, key[j], bp[j].h, [&](int64_t slot, int32_t payloadWord) {
             int64_t vals[NV];
 #pragma unroll
             for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lrs[j]);
             i128 v = evalAggDyn(p.agg, vals, one);
-            atomicAdd128(&p.table.aggLo[slot], &p.table.aggHi[slot], v);
-            p.table.marker[slot] = 1;
+            uint8_t* entry = p.table.base + (uint64_t) slot * 32;
+            atomicAdd128((unsigned long long*) (entry + 16), (unsigned long long*) (entry + 24), v);
+            if (payloadWord >= 0) ((int32_t*) entry)[1] = payloadWord | (int32_t) 0x80000000; // marker: idempotent plain store, same sector
          });
       }
    });
@@ -813,7 +831,7 @@ __global__ void __launch_bounds__(kThreads, 4) scanProbe2GroupByKernel(const __g
          if (!bpB[j].mayContain()) continue;
          joinProbeSlots(p.tableA, key[j], bp[j].h, [&](int64_t, int32_t payA) {
             joinProbeSlots(p.tableB, keyB[j], bpB[j].h, [&](int64_t, int32_t payB) {
-               if (payA != payB) return;
+               if (((payA ^ payB) & (p.tableA.stride == 32 || p.tableB.stride == 32 ? 0x7fffffff : -1)) != 0) return;
                int64_t vals[NV];
 #pragma unroll
                for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lrs[j]);
@@ -868,16 +886,17 @@ __global__ void __launch_bounds__(kBlock) joinTopKKernel(JoinTableDev t, int k, 
       __syncwarp(); // CTA-uniform loop: re-converge after the previous iteration's try-lock
       const uint64_t s = sBase + threadIdx.x;
       if (s >= cap) continue;
-      if (!t.marker[s]) continue;
-      unsigned long long e = t.slots[s];
+      const uint8_t* entry = t.base + s * 32;
+      const unsigned long long e = *(const unsigned long long*) entry;
       if (e == kEmptySlot) continue;
+      if (!((uint32_t) (e >> 32) & 0x80000000u)) continue; // marker bit: the group saw at least one probe-side row
       TopKRowDev c;
       c.key = (int32_t) (uint32_t) e;
-      c.side0 = t.side[0] ? t.side[0][s] : 0;
-      c.side1 = t.side[1] ? t.side[1][s] : 0;
+      c.side0 = ((const int32_t*) entry)[2];
+      c.side1 = ((const int32_t*) entry)[3];
       c.valid = 1;
-      c.aggLo = t.aggLo[s];
-      c.aggHi = (long long) t.aggHi[s];
+      c.aggLo = *(const unsigned long long*) (entry + 16);
+      c.aggHi = *(const long long*) (entry + 24);
       // cheap reject against the current k-th without the lock
       int cnt = *((volatile int*) &sCount);
       if (cnt == k) {
@@ -920,6 +939,20 @@ void launchJoinTopK(const JoinTableDev& t, int k, TopKRowDev* out, int* outBlock
    joinTopKKernel<<<grid, kBlock, 0, s>>>(t, k, out);
 }
 
+// 32-byte entries start as {empty marker, zero side lanes, zero aggregate}
+__global__ void initWideTableKernel(uint8_t* base, uint64_t capacity) {
+   for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += (uint64_t) gridDim.x * blockDim.x) {
+      ulonglong4 v;
+      v.x = kEmptySlot;
+      v.y = v.z = v.w = 0;
+      *(ulonglong4*) (base + i * 32) = v;
+   }
+}
+void launchInitWideTable(uint8_t* base, uint64_t capacity, int smCount, cudaStream_t s) {
+   int grid = (int) std::min<uint64_t>((capacity + 255) / 256, (uint64_t) smCount * 16);
+   initWideTableKernel<<<grid < 1 ? 1 : grid, 256, 0, s>>>(base, capacity);
+}
+
 // =================================================================================== small helpers
 __global__ void fill64Kernel(unsigned long long* p, unsigned long long v, int64_t n) {
    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) p[i] = v;
@@ -935,8 +968,8 @@ __global__ void insertTuplesKernel(JoinTableDev t, const int32_t* keys, const in
       int64_t slot = joinInsert(t, keys[i], payloads ? payloads[i] : 0);
       if (slot >= 0) {
          inserted++;
-         if (side0) t.side[0][slot] = side0[i];
-         if (side1) t.side[1][slot] = side1[i];
+         if (side0) ((int32_t*) (t.base + (uint64_t) slot * 32))[2] = side0[i];
+         if (side1) ((int32_t*) (t.base + (uint64_t) slot * 32))[3] = side1[i];
       }
    }
    flushInsertCount(t, inserted);

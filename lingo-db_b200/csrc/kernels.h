@@ -42,17 +42,20 @@ struct GroupTableDev {
 };
 
 // ---- join table (rt::GrowingBuffer + rt::HashIndexedView twin; with agg lanes: the group-join map)
+// Open addressing, slot s at base + s * stride.  Two layouts:
+//   stride  8  {key:32, payload:32}                                              plain joins
+//   stride 32  {key:32, marker:1|payload:31, side0:32, side1:32, aggLo:64, aggHi:64}  group-join map — ONE 32-byte
+//              sector per entry, so an insert (CAS + side lanes) or a probe hit (compare + i128 atomic add + marker)
+//              touches a single DRAM sector instead of up to four separate arrays.
+// The first 8 bytes all-ones = empty.
 struct JoinTableDev {
-   unsigned long long* slots; // {key = low 32 bits, payload = high 32 bits}; all ones = empty
+   uint8_t* base;
+   uint32_t stride;
    uint64_t mask;             // capacity - 1
-   int32_t* side[kMaxSide];   // [capacity] int32 payload lanes
-   unsigned long long* aggLo; // [capacity]
-   unsigned long long* aggHi; // [capacity]
-   uint8_t* marker;           // [capacity]
    uint32_t* bloom;           // blocked Bloom filter over the build keys (32-bit blocks, 3 bits/key), sized to stay in L2
    uint32_t bloomMask;        // words - 1
    unsigned long long* count; // inserted entries
-   int32_t* error;            // 1 = table full, 2 = duplicate key in a unique table
+   int32_t* error;            // 1 = table full, 2 = duplicate key in a unique table, 3 = unstorable pair, 4 = negative payload in a wide table
    int32_t unique;
 };
 
@@ -150,6 +153,7 @@ void launchScanBuild(const BuildParams& p, int smCount, cudaStream_t s);
 bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, const char** why);
 bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStream_t s, const char** why);
 void launchScanMaterialize(const MaterializeParams& p, int smCount, cudaStream_t s);
+void launchInitWideTable(uint8_t* base, uint64_t capacity, int smCount, cudaStream_t s);
 void launchJoinTopK(const JoinTableDev& t, int k, TopKRowDev* out, int* outBlocks, int smCount, cudaStream_t s);
 void launchFill64(unsigned long long* p, unsigned long long v, int64_t n, cudaStream_t s);
 void launchInsertTuples(const JoinTableDev& t, const int32_t* keys, const int32_t* payloads, const int32_t* side0, const int32_t* side1, int64_t n, int smCount, cudaStream_t s);

@@ -482,12 +482,14 @@ int ldb_gpu_join_table_create(LdbContext* ctx, int64_t expected_rows, int32_t un
       auto& j = s->join;
       j.mask = cap - 1;
       j.unique = unique_keys;
-      j.slots = (unsigned long long*) devAlloc(s, cap * 8, 0xff);
-      for (int k = 0; k < n_side; k++) j.side[k] = (int32_t*) devAlloc(s, cap * 4, 0);
-      if (n_aggs) {
-         j.aggLo = (unsigned long long*) devAlloc(s, cap * 8, 0);
-         j.aggHi = (unsigned long long*) devAlloc(s, cap * 8, 0);
-         j.marker = (uint8_t*) devAlloc(s, cap, 0);
+      if (n_side > 0 || n_aggs > 0) { // group-join map: one 32-byte sector per entry
+         j.stride = 32;
+         j.base = (uint8_t*) ctx->stagingAlloc(cap * 32);
+         s->allocations.push_back(j.base);
+         ctx->launch("table_init", [&] { launchInitWideTable(j.base, cap, ctx->smCount, ctx->compute); });
+      } else {
+         j.stride = 8;
+         j.base = (uint8_t*) devAlloc(s, cap * 8, 0xff);
       }
       j.count = (unsigned long long*) devAlloc(s, 8, 0);
       j.error = (int32_t*) devAlloc(s, 4, 0);
@@ -508,6 +510,7 @@ static void checkJoinError(LdbState* s) {
    if (e == 1) fail(LDB_ERR_CAPACITY, "join table full: more build rows than expected_rows allowed");
    if (e == 2) fail(LDB_ERR_INVALID, "duplicate key inserted into a join table declared unique");
    if (e == 3) fail(LDB_ERR_UNSUPPORTED, "the pair (key=-1, payload=-1) cannot be stored in a join table");
+   if (e == 4) fail(LDB_ERR_UNSUPPORTED, "join tables with side/aggregate lanes need non-negative inline payloads");
 }
 int ldb_gpu_join_table_count(LdbState* s, int64_t* n_entries, LdbError* err) {
    return guarded(err, [&] {
