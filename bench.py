@@ -180,6 +180,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # NCCL's "NCCL version …" banner goes to stdout; the contract is ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     ctx = runtime.Context(local)

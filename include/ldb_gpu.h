@@ -49,6 +49,9 @@ int ldb_gpu_context_create(int device, LdbContext** out, LdbError* err);
 void ldb_gpu_context_destroy(LdbContext* ctx);
 int ldb_gpu_device_info(LdbContext* ctx, LdbDeviceInfo* out, LdbError* err);
 int ldb_gpu_synchronize(LdbContext* ctx, LdbError* err);
+/* the CUDA stream (cudaStream_t) every pipeline kernel of this context is launched on, so callers can order their own
+ * work (NCCL collectives, allocator frees) after it without a host synchronisation */
+void* ldb_gpu_context_stream(LdbContext* ctx);
 /* number of kernels this library has launched on the context since creation (bench "gpu_launches") */
 int64_t ldb_gpu_launch_count(LdbContext* ctx);
 /* CUDA-event timing on the context's compute stream (the stream every pipeline kernel runs on) */

@@ -207,6 +207,7 @@ int ldb_gpu_synchronize(LdbContext* ctx, LdbError* err) {
       LDB_CUDA(cudaStreamSynchronize(ctx->compute));
    });
 }
+void* ldb_gpu_context_stream(LdbContext* ctx) { return ctx ? (void*) ctx->compute : nullptr; }
 int64_t ldb_gpu_launch_count(LdbContext* ctx) { return ctx ? ctx->launches : 0; }
 int ldb_gpu_timer_start(LdbContext* ctx, LdbError* err) {
    return guarded(err, [&] { LDB_CUDA(cudaEventRecord(ctx->timerStart, ctx->compute)); });

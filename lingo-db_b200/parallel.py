@@ -101,11 +101,14 @@ def allgather_merge_state(ctx, state, world: int, rank: int, bufs: dict):
         dev = torch.device("cuda", ctx.device)
         bufs["send"] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         bufs["recv"] = torch.empty(nbytes * world, dtype=torch.uint8, device=dev)
+    if "stream" not in bufs:
+        bufs["stream"] = torch.cuda.ExternalStream(int(L.ldb_gpu_context_stream(ctx.h)), device=torch.device("cuda", ctx.device))
     e = capi.Error()
     capi.check(L.ldb_gpu_groupby_export(state, C.c_void_p(bufs["send"].data_ptr()), C.byref(e)), e)
-    ctx.synchronize()  # the export ran on the context's compute stream, NCCL runs on torch's
-    dist.all_gather_into_tensor(bufs["recv"], bufs["send"])
-    torch.cuda.current_stream().synchronize()
+    # torch sees the context's compute stream as its current stream: NCCL orders itself after the export and the merge
+    # kernel after NCCL with stream events only — no host synchronisation inside the step
+    with torch.cuda.stream(bufs["stream"]):
+        dist.all_gather_into_tensor(bufs["recv"], bufs["send"])
     capi.check(L.ldb_gpu_groupby_merge_exported(state, C.c_void_p(bufs["recv"].data_ptr()), world, rank, C.byref(e)), e)
 
 
@@ -203,7 +206,9 @@ def q5_repartitioned(ctx, tables, world: int, rank: int, n_orders_total: int, re
                                      filters=[("o_orderdate", ">=", date_ge), ("o_orderdate", "<", date_lt)], probes=[(cust, "o_custkey")])
         pk, (pn,), offs = _partition(ctx, ok, [on], [4], n_t, world, dev)
         (rk, rn), n_r = _all_to_all([pk, pn], offs, world, dev)
-        ordp = own(runtime.join_table(ctx, (n_orders_total // 24 + 1024) // world * 13 // 10 + 4096))  # same size on every rank → same Bloom geometry
+        # sized for the GLOBAL key set on every rank: identical Bloom geometry everywhere, and the OR of all partitions'
+        # filters keeps the false-positive rate of a single-GPU build (a 1/world-sized filter let 8 % through at N=4)
+        ordp = own(runtime.join_table(ctx, n_orders_total // 24 + 4096))
         e = capi.Error()
         torch.cuda.synchronize(dev)
         capi.check(L.ldb_gpu_join_table_insert(ctx.h, ordp, C.c_void_p(rk.data_ptr()), C.c_void_p(rn.data_ptr()), None, n_r, C.byref(e)), e)
