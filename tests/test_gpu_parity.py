@@ -226,3 +226,143 @@ def test_materialize_pipeline_exact_rows(gpu_ctx):
     assert n == int(m.sum())  # the first attempt overflowed its 16-row buffer and was regrown
     got = sorted(zip(k[:n].cpu().tolist(), d[:n].cpu().tolist()))
     assert got == sorted(zip(c["o_orderkey"][m].tolist(), c["o_orderdate"][m].tolist()))
+
+
+def test_multimap_build_side_non_unique_keys(gpu_ctx):
+    """HashIndexedView is a multimap (chains hold duplicates, LazyJoinHashtable.cpp:20-31): a probe must visit EVERY
+    entry of a key.  Build orders by o_custkey (non-unique), probe with customer, emit one row per match."""
+    import torch
+    from lingodb_b200 import parallel, runtime
+    s = datagen.scale(0.02, seed=17)
+    orders, customer = datagen.orders(s), datagen.customer(s)
+    to, tc = gpu_ctx.table_from_host(orders), gpu_ctx.table_from_host(customer)
+    dev = torch.device("cuda", gpu_ctx.device)
+    table = runtime.join_table(gpu_ctx, s.n_orders, unique=False)
+    runtime.run_pipeline(gpu_ctx, "scan_build", to, build_key="o_custkey", build_payload="o_orderkey", sink=table)
+    assert runtime.join_count(gpu_ctx, table) == s.n_orders
+    (ck, ok), n = parallel._materialize(gpu_ctx, tc, ["c_custkey", "$payload"], [4, 4], s.n_orders + 16, dev, probes=[(table, "c_custkey")])
+    assert n == s.n_orders  # every order has exactly one customer → one output row per order
+    got = sorted(zip(ck[:n].cpu().tolist(), ok[:n].cpu().tolist()))
+    o = orders.chunks[0]
+    assert got == sorted(zip(o["o_custkey"].tolist(), o["o_orderkey"].tolist()))
+    # customers whose key is a multiple of 3 have no orders (generator rule) → they never appear
+    assert all(k % 3 != 0 for k, _ in got)
+    gpu_ctx.L.ldb_gpu_state_destroy(table)
+
+
+def _lineitem_np(t, names):
+    out = {}
+    for n in names:
+        parts = [c[n] for c in t.chunks]
+        out[n] = np.concatenate([p[:, :8].copy().view(np.int64).reshape(-1) for p in parts]) if t.spec(n).phys == "decimal128" else np.concatenate(parts)
+    return out
+
+
+def test_groupby_many_groups_register_shared_and_hbm_paths(gpu_ctx):
+    """K2 with 1, ~30 and ~400 groups: exercises the register-resident groups, the shared-memory atomics (5th..16th
+    group of a CTA) and the straight-to-HBM path (> 16 groups per CTA); checked against numpy."""
+    from lingodb_b200 import capi, runtime
+    s = datagen.scale(0.05, seed=23)
+    host = datagen.lineitem(s, chunk_rows=40000)
+    tab = gpu_ctx.table_from_host(host)
+    c = _lineitem_np(host, ["l_shipdate", "l_returnflag", "l_extendedprice", "l_discount"])
+    for lo, hi, cap in (("1995-01-01", "1995-01-01", 64), ("1995-01-01", "1995-01-30", 64), ("1994-01-01", "1995-02-04", 1024)):
+        st = runtime.groupby_state(gpu_ctx, 2, 1, cap)
+        runtime.run_pipeline(gpu_ctx, "scan_groupby", tab, filters=[("l_shipdate", ">=", lo), ("l_shipdate", "<=", hi)], keys=["l_shipdate", "l_returnflag"],
+                             aggs=[("mul_1minus", ["l_extendedprice", "l_discount"])], sink=st)
+        rows, n = runtime.groupby_read(gpu_ctx, st)
+        got = {(rows[i].keys[0], rows[i].keys[1]): rows[i].aggs[0].value() for i in range(n)}
+        d0, d1 = (np.datetime64(lo) - np.datetime64("1970-01-01")).astype(int), (np.datetime64(hi) - np.datetime64("1970-01-01")).astype(int)
+        m = (c["l_shipdate"] >= d0) & (c["l_shipdate"] <= d1)
+        want = {}
+        for sd, rf, e, d in zip(c["l_shipdate"][m].tolist(), c["l_returnflag"][m].tolist(), c["l_extendedprice"][m].tolist(), c["l_discount"][m].tolist()):
+            want[(sd, rf)] = want.get((sd, rf), 0) + e * (100 - d)
+        assert got == want and len(got) > 0
+        gpu_ctx.L.ldb_gpu_state_destroy(st)
+    # more groups than the declared capacity → LDB_ERR_CAPACITY, not a wrong answer
+    st = runtime.groupby_state(gpu_ctx, 2, 1, 16)
+    runtime.run_pipeline(gpu_ctx, "scan_groupby", tab, keys=["l_shipdate", "l_returnflag"], aggs=[("mul_1minus", ["l_extendedprice", "l_discount"])], sink=st)
+    with pytest.raises(capi.LdbRuntimeError) as ei:
+        runtime.groupby_read(gpu_ctx, st)
+    assert ei.value.code == capi.LDB_ERR_CAPACITY
+    gpu_ctx.L.ldb_gpu_state_destroy(st)
+    # an aggregate signature with no compiled kernel is refused, not approximated
+    st = runtime.groupby_state(gpu_ctx, 1, 2, 64)
+    with pytest.raises(capi.LdbRuntimeError) as ei:
+        runtime.run_pipeline(gpu_ctx, "scan_groupby", tab, keys=["l_returnflag"], aggs=[("mul", ["l_extendedprice", "l_discount"]), ("one", [])], sink=st)
+    assert ei.value.code == capi.LDB_ERR_UNSUPPORTED
+    gpu_ctx.L.ldb_gpu_state_destroy(st)
+
+
+def test_unaligned_batches_take_the_plain_load_path(gpu_ctx, oracle):
+    """ArrayView.offset != 0 breaks the 16-byte alignment TMA bulk copies need: the same kernels must then read the
+    tiles with plain coalesced loads and give identical answers (join build growth is exercised on the way)."""
+    import ctypes as C
+    from lingodb_b200 import capi, runtime
+    s = datagen.scale(0.02, seed=29)
+    host = datagen.lineitem(s, chunk_rows=1 << 20)
+    chunk, n = host.chunks[0], host.chunk_rows[0]
+    skip = 3  # rows: int32 columns start 12 bytes into their buffers
+    tab = runtime.Table(gpu_ctx, "lineitem", host.columns)
+    views = (capi.ArrayView * len(host.columns))()
+    keep = []
+    for i, col in enumerate(host.columns):
+        arr = (C.c_void_p * 3)()
+        arr[1] = chunk[col.name].ctypes.data
+        keep.append(arr)
+        views[i] = capi.ArrayView(n, 0, skip, 2, 0, C.cast(arr, C.POINTER(C.c_void_p)), None)
+    e = capi.Error()
+    capi.check(gpu_ctx.L.ldb_gpu_table_append_batch(tab.h, n - skip, views, None, capi.MEM_HOST, C.byref(e)), e)
+    sliced = datagen.lineitem(s, chunk_rows=1 << 20, row_begin=skip, n_rows=n - skip)
+    want, _ = oracle.q1(oracle.table(sliced))
+    g = runtime.Tpch(gpu_ctx, {"lineitem": tab})
+    assert g.q1() == want
+    assert g.q6() == oracle.q6(oracle.table(sliced))[0]
+
+
+def test_join_table_regrows_when_the_estimate_is_too_small(gpu_ctx):
+    from lingodb_b200 import capi, runtime
+    s = datagen.scale(0.02, seed=31)
+    to = gpu_ctx.table_from_host(datagen.orders(s))
+    small = runtime.join_table(gpu_ctx, 8)  # 16 slots for 30 000 keys
+    runtime.run_pipeline(gpu_ctx, "scan_build", to, build_key="o_orderkey", sink=small)
+    with pytest.raises(capi.LdbRuntimeError) as ei:
+        runtime.join_count(gpu_ctx, small)
+    assert ei.value.code == capi.LDB_ERR_CAPACITY  # the C++ plans catch this and rebuild 4x larger (tpch_plans.cpp buildJoin)
+    gpu_ctx.L.ldb_gpu_state_destroy(small)
+
+
+def test_full_size_properties_sf100(gpu_ctx):
+    """BASELINE-size (SF100, 600 M lineitem rows) checks through size-independent properties: aggregation is linear
+    in the input (whole table == fold of its halves), counts add up to the rows that pass the filter, and repeated
+    runs are bit-identical (order-independent exact integer sums)."""
+    import torch
+    from lingodb_b200 import devgen, parallel, runtime
+    free = torch.cuda.mem_get_info(gpu_ctx.device)[0]
+    sf = 100.0 if free > 120e9 else 10.0
+    s = datagen.scale(sf, 42)
+    cols = ["l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus", "l_shipdate"]
+    whole = devgen.lineitem(gpu_ctx, s, cols)
+    t = runtime.Tpch(gpu_ctx, {"lineitem": whole})
+    q1a, q1b = t.q1(), t.q1()
+    assert q1a == q1b and len(q1a) == 4
+    assert t.q6() == t.q6()
+    # halves, split at an order boundary; views into the same device buffers (row offset via tensor slicing)
+    _, _, _, mid = parallel.order_range(s, 0, 2)
+    tens = whole._keep[0]
+    parts = []
+    for lo, hi in ((0, mid), (mid, s.n_lineitem)):
+        tab = runtime.Table(gpu_ctx, "lineitem", whole.columns)
+        tab.append_device({k: v[lo:hi] for k, v in tens.items()}, hi - lo)
+        parts.append(runtime.Tpch(gpu_ctx, {"lineitem": tab}))
+    h0, h1 = parts[0].q1(), parts[1].q1()
+    for w, a, b in zip(q1a, h0, h1):
+        for k in ("sum_qty", "sum_base_price", "sum_disc_price", "sum_charge", "count_order"):
+            assert w[k] == a[k] + b[k], k
+        assert (w["l_returnflag"], w["l_linestatus"]) == (a["l_returnflag"], a["l_linestatus"])
+    assert t.q6()["revenue"] == parts[0].q6()["revenue"] + parts[1].q6()["revenue"]
+    # count(*) over all groups == rows with l_shipdate <= 1998-09-02, counted by an independent torch reduction
+    assert sum(r["count_order"] for r in q1a) == int((tens["l_shipdate"] <= 10471).sum().item())
+    # avg columns are consistent with their sums: avg = (sum * 10^19) div count
+    for r in q1a:
+        assert r["avg_qty"] == r["sum_qty"] * 10**19 // r["count_order"]
