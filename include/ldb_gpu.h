@@ -158,12 +158,17 @@ int ldb_gpu_join_table_topk(LdbState* s, int32_t k, LdbTopKRow* rows, int32_t* n
 enum LdbFilterOp { LDB_EQ = 0, LDB_NEQ = 1, LDB_LT = 2, LDB_LTE = 3, LDB_GT = 4, LDB_GTE = 5, LDB_NOTNULL = 6, LDB_IN = 7 };
 /* FilterDescription (include/lingodb/runtime/storage/TableStorage.h:14-31): column-vs-constant;
  * the constant is a string (dates "YYYY-MM-DD", decimals "0.05", char/varchar text) or an integer */
+#define LDB_MAX_IN_VALUES 8
 typedef struct LdbFilterDesc {
    const char* column;
    int32_t op;          /* LdbFilterOp */
    int32_t value_is_int;
    const char* str_value;
    int64_t int_value;
+   /* LDB_IN (SimpleTypeInFilter, Restrictions.cpp:194-236): up to LDB_MAX_IN_VALUES constants, typed like the single value */
+   int32_t n_values;
+   const char* str_values[LDB_MAX_IN_VALUES];
+   int64_t int_values[LDB_MAX_IN_VALUES];
 } LdbFilterDesc;
 
 /* value expressions over decimal(12,2) columns, typed as DBOps.cpp:98-107,221-262 types them */

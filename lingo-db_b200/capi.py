@@ -12,7 +12,7 @@ from .datagen import CustomerCols, GenScale, LineitemCols, OrdersCols, SupplierC
 LDB_OK, LDB_ERR_CUDA, LDB_ERR_UNSUPPORTED, LDB_ERR_INVALID, LDB_ERR_CAPACITY, LDB_ERR_NO_DEVICE = range(6)
 PHYS = {"int32": 0, "int64": 1, "date32": 2, "decimal128": 3, "fsb4": 4, "utf8": 5}
 MEM_HOST, MEM_DEVICE = 0, 1
-OPS = {"=": 0, "!=": 1, "<": 2, "<=": 3, ">": 4, ">=": 5}
+OPS = {"=": 0, "!=": 1, "<": 2, "<=": 3, ">": 4, ">=": 5, "notnull": 6, "in": 7}
 EXPR = {"col": 0, "mul": 1, "mul_1minus": 2, "mul_1minus_1plus": 3, "one": 4}
 PIPE = {"scan_reduce": 1, "scan_groupby": 2, "scan_build": 3, "scan_probe_agg": 4, "scan_probe2_groupby": 5, "scan_materialize": 6}
 MAX_AGGS, MAX_KEYS, MAX_SIDE = 8, 2, 2
@@ -61,7 +61,8 @@ class TopKRow(C.Structure):
 
 
 class FilterDesc(C.Structure):
-    _fields_ = [("column", C.c_char_p), ("op", C.c_int32), ("value_is_int", C.c_int32), ("str_value", C.c_char_p), ("int_value", C.c_int64)]
+    _fields_ = [("column", C.c_char_p), ("op", C.c_int32), ("value_is_int", C.c_int32), ("str_value", C.c_char_p), ("int_value", C.c_int64),
+                ("n_values", C.c_int32), ("str_values", C.c_char_p * 8), ("int_values", C.c_int64 * 8)]
 
 
 class AggDesc(C.Structure):

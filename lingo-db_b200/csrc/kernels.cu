@@ -201,8 +201,15 @@ __device__ __forceinline__ bool evalFilters(const FilterSet& F, const Tile& tile
                for (int k = 0; k < f.strLen; k++) eq &= __ldg(f.bytes + b + k) == f.str[k];
             v = eq ? 1 : 0;
          }
-         pass &= cmpMask(v, f.valA, f.maskA);
-         if (f.maskB != 7u) pass &= cmpMask(v, f.valB, f.maskB);
+         if (f.nIn > 0) { // IN list: linear search like the reference does for <= 10 values (Restrictions.cpp:207-218)
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < 8; k++) any |= (k < f.nIn) & (v == f.inVals[k]);
+            pass &= any;
+         } else {
+            pass &= cmpMask(v, f.valA, f.maskA);
+            if (f.maskB != 7u) pass &= cmpMask(v, f.valB, f.maskB);
+         }
       }
    }
    return pass;

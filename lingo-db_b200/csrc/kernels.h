@@ -25,6 +25,8 @@ struct FilterCol {
    int64_t valA, valB;
    uint8_t str[24];
    int32_t strLen;
+   int32_t nIn;        // > 0: IN list (the A/B predicates are unused)
+   int64_t inVals[8];
 };
 struct FilterSet {
    int32_t n;

@@ -610,6 +610,29 @@ struct FilterPlan {
    FilterSet set{};
    int colIdx[kMaxFilterCols];
 };
+// one constant of a filter, typed by the physical column type (Restrictions::create, Restrictions.cpp:392-520)
+static int64_t filterConstant(const LdbColumn& col, bool isInt, const char* str, int64_t ival) {
+   switch (col.type) {
+      case LDB_INT32:
+         if (!isInt) fail(LDB_ERR_INVALID, "integer column needs an integer constant");
+         return ival;
+      case LDB_DATE32: return parseDate32(str);
+      case LDB_FSB4: {
+         if (!str || strlen(str) > 4) fail(LDB_ERR_INVALID, "char(1) constant too long");
+         int32_t v = 0;
+         memcpy(&v, str, strlen(str));
+         return v;
+      }
+      case LDB_DECIMAL128: {
+         if (col.precision >= 19) fail(LDB_ERR_UNSUPPORTED, "decimal precision >= 19 is not supported on the GPU path yet");
+         if (!isInt) return parseDecimal(str, col.scale);
+         int64_t v = ival;
+         for (int s = 0; s < col.scale; s++) v *= 10;
+         return v;
+      }
+      default: fail(LDB_ERR_UNSUPPORTED, "unsupported type in filter");
+   }
+}
 FilterPlan planFilters(LdbTable* t, const LdbFilterDesc* f, int n, StagePlan& sp) {
    FilterPlan p;
    p.set.n = 0;
@@ -617,46 +640,38 @@ FilterPlan planFilters(LdbTable* t, const LdbFilterDesc* f, int n, StagePlan& sp
       int c = t->colIndex(f[i].column);
       if (c < 0) fail(LDB_ERR_INVALID, "unknown column in filter"); // Restrictions.cpp:396
       auto& col = t->columns[c];
+      if (f[i].op == LDB_NOTNULL) continue; // batches with nulls are rejected at append time → always true (FirstNotNullFilter fast path, Restrictions.cpp:67-75)
+      int kind = col.type == LDB_DECIMAL128 ? COL_DEC128_LO64 : COL_I32;
+      if (f[i].op == LDB_IN) {
+         if (col.type == LDB_UTF8) fail(LDB_ERR_UNSUPPORTED, "IN over strings is not supported on the GPU path yet");
+         if (f[i].n_values < 1 || f[i].n_values > LDB_MAX_IN_VALUES) fail(LDB_ERR_UNSUPPORTED, "IN lists hold 1..8 values on the GPU path");
+         if (p.set.n == kMaxFilterCols) fail(LDB_ERR_UNSUPPORTED, "more than 4 filter columns in one pipeline");
+         FilterCol& fc = p.set.c[p.set.n];
+         memset(&fc, 0, sizeof(fc));
+         fc.kind = kind;
+         fc.staged = sp.add(t, c);
+         fc.maskA = fc.maskB = 7;
+         fc.nIn = f[i].n_values;
+         for (int k = 0; k < f[i].n_values; k++) fc.inVals[k] = filterConstant(col, f[i].value_is_int != 0, f[i].str_values[k], f[i].int_values[k]);
+         p.colIdx[p.set.n++] = c;
+         continue;
+      }
       int64_t value = 0;
-      int kind = COL_I32;
       uint32_t mask = opMask(f[i].op);
       const char* str = nullptr;
-      switch (col.type) {
-         case LDB_INT32:
-            if (!f[i].value_is_int) fail(LDB_ERR_INVALID, "integer column needs an integer constant");
-            value = f[i].int_value;
-            break;
-         case LDB_DATE32: value = parseDate32(f[i].str_value); break;
-         case LDB_FSB4: {
-            if (!f[i].str_value || strlen(f[i].str_value) > 4) fail(LDB_ERR_INVALID, "char(1) constant too long");
-            int32_t v = 0;
-            memcpy(&v, f[i].str_value, strlen(f[i].str_value));
-            value = v;
-            break;
-         }
-         case LDB_DECIMAL128:
-            if (col.precision >= 19) fail(LDB_ERR_UNSUPPORTED, "decimal precision >= 19 is not supported on the GPU path yet");
-            kind = COL_DEC128_LO64;
-            if (f[i].value_is_int) {
-               value = f[i].int_value;
-               for (int s = 0; s < col.scale; s++) value *= 10;
-            } else {
-               value = parseDecimal(f[i].str_value, col.scale);
-            }
-            break;
-         case LDB_UTF8:
-            if (f[i].op != LDB_EQ && f[i].op != LDB_NEQ) fail(LDB_ERR_UNSUPPORTED, "unsupported filter op for string");
-            if (!f[i].str_value || strlen(f[i].str_value) > sizeof(FilterCol::str)) fail(LDB_ERR_UNSUPPORTED, "string constant longer than 24 bytes");
-            kind = COL_UTF8_EQ;
-            value = 1;
-            str = f[i].str_value;
-            break;
-         default: fail(LDB_ERR_UNSUPPORTED, "unsupported type in filter");
+      if (col.type == LDB_UTF8) {
+         if (f[i].op != LDB_EQ && f[i].op != LDB_NEQ) fail(LDB_ERR_UNSUPPORTED, "unsupported filter op for string");
+         if (!f[i].str_value || strlen(f[i].str_value) > sizeof(FilterCol::str)) fail(LDB_ERR_UNSUPPORTED, "string constant longer than 24 bytes");
+         kind = COL_UTF8_EQ;
+         value = 1;
+         str = f[i].str_value;
+      } else {
+         value = filterConstant(col, f[i].value_is_int != 0, f[i].str_value, f[i].int_value);
       }
       int slot = -1;
       if (kind != COL_UTF8_EQ)
          for (int k = 0; k < p.set.n; k++)
-            if (p.colIdx[k] == c && p.set.c[k].maskB == 7) slot = k;
+            if (p.colIdx[k] == c && p.set.c[k].maskB == 7 && p.set.c[k].nIn == 0) slot = k;
       if (slot >= 0) {
          p.set.c[slot].maskB = mask;
          p.set.c[slot].valB = value;

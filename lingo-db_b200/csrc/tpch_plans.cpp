@@ -40,8 +40,21 @@ int guarded(LdbError* err, const Fn& fn) {
       return LDB_ERR_INVALID;
    }
 }
-LdbFilterDesc strFilter(const char* col, int op, const char* v) { return LdbFilterDesc{col, op, 0, v, 0}; }
-LdbFilterDesc intFilter(const char* col, int op, int64_t v) { return LdbFilterDesc{col, op, 1, nullptr, v}; }
+LdbFilterDesc strFilter(const char* col, int op, const char* v) {
+   LdbFilterDesc f{};
+   f.column = col;
+   f.op = op;
+   f.str_value = v;
+   return f;
+}
+LdbFilterDesc intFilter(const char* col, int op, int64_t v) {
+   LdbFilterDesc f{};
+   f.column = col;
+   f.op = op;
+   f.value_is_int = 1;
+   f.int_value = v;
+   return f;
+}
 LdbAggDesc agg(int expr, const char* a = nullptr, const char* b = nullptr, const char* c = nullptr) { return LdbAggDesc{expr, {a, b, c}}; }
 
 struct StateGuard { // the query's ExecutionContext: frees every state it registered

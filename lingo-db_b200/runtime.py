@@ -238,7 +238,16 @@ def run_pipeline(ctx: Context, kind: str, source: Table, filters=(), keys=(), ag
     d.source = source.h
     fl = (capi.FilterDesc * max(1, len(filters)))()
     for i, (col, op, val) in enumerate(filters):
-        if isinstance(val, int):
+        if op == "in":  # list of ints or of strings
+            fd = capi.FilterDesc(b(col), capi.OPS[op], int(isinstance(val[0], int)), None, 0)
+            fd.n_values = len(val)
+            for k, v in enumerate(val):
+                if isinstance(v, int):
+                    fd.int_values[k] = v
+                else:
+                    fd.str_values[k] = b(v)
+            fl[i] = fd
+        elif isinstance(val, int):
             fl[i] = capi.FilterDesc(b(col), capi.OPS[op], 1, None, val)
         else:
             fl[i] = capi.FilterDesc(b(col), capi.OPS[op], 0, b(val), 0)

@@ -366,3 +366,25 @@ def test_full_size_properties_sf100(gpu_ctx):
     # avg columns are consistent with their sums: avg = (sum * 10^19) div count
     for r in q1a:
         assert r["avg_qty"] == r["sum_qty"] * 10**19 // r["count_order"]
+
+
+def test_in_and_notnull_filters(gpu_ctx):
+    """SimpleTypeInFilter / NotNull pushed-down filters (Restrictions.cpp:194-236, 67-162) vs numpy."""
+    from lingodb_b200 import runtime
+    s = datagen.scale(0.02, seed=37)
+    host = datagen.lineitem(s, chunk_rows=30000)
+    tab = gpu_ctx.table_from_host(host)
+    c = _lineitem_np(host, ["l_shipdate", "l_returnflag", "l_extendedprice", "l_discount", "l_quantity"])
+    st = C_state = runtime.groupby_state(gpu_ctx, 1, 1, 64)
+    runtime.run_pipeline(gpu_ctx, "scan_groupby", tab, keys=["l_returnflag"], aggs=[("mul_1minus", ["l_extendedprice", "l_discount"])], sink=st,
+                         filters=[("l_discount", "in", ["0.02", "0.05", "0.09"]), ("l_returnflag", "in", ["A", "N"]), ("l_shipdate", "in", ["1995-01-01", "1995-01-02", "1996-02-29"]),
+                                  ("l_quantity", "notnull", "")])
+    rows, n = runtime.groupby_read(gpu_ctx, st)
+    got = {rows[i].keys[0]: rows[i].aggs[0].value() for i in range(n)}
+    days = [(np.datetime64(d) - np.datetime64("1970-01-01")).astype(int) for d in ("1995-01-01", "1995-01-02", "1996-02-29")]
+    m = np.isin(c["l_discount"], [2, 5, 9]) & np.isin(c["l_returnflag"], [ord("A"), ord("N")]) & np.isin(c["l_shipdate"], days)
+    want = {}
+    for rf, e, d in zip(c["l_returnflag"][m].tolist(), c["l_extendedprice"][m].tolist(), c["l_discount"][m].tolist()):
+        want[rf] = want.get(rf, 0) + e * (100 - d)
+    assert got == want and len(got) >= 1
+    gpu_ctx.L.ldb_gpu_state_destroy(st)
