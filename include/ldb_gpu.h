@@ -86,6 +86,10 @@ int ldb_gpu_table_create(LdbContext* ctx, const char* name, int32_t n_cols, cons
  * utf8 columns additionally need `utf8_bytes[col]` = size of buffers[2] (0 for other columns). */
 int ldb_gpu_table_append_batch(LdbTable* t, int64_t n_rows, const LdbArrayView* columns, const int64_t* utf8_bytes, int32_t location, LdbError* err);
 int ldb_gpu_table_clear(LdbTable* t, LdbError* err); /* drop all batches (staging memory is pooled) */
+/* Bytes copied host→device by this context's table staging so far.  HOST decimal128(p<19) columns are narrowed on
+ * the host to the 8 bytes per value the kernels read (the JIT truncates them to i64, LowerToStd.cpp:111-209), so they
+ * cost 8 B/value of PCIe instead of 16; LDB_NARROW_STAGING=0 in the environment disables it. */
+int64_t ldb_gpu_context_h2d_bytes(LdbContext* ctx);
 int64_t ldb_gpu_table_num_rows(const LdbTable* t);
 void ldb_gpu_table_destroy(LdbTable* t);
 

@@ -106,6 +106,7 @@ SIGNATURES = {
     "ldb_gpu_device_info": (C.c_int, [_P, C.POINTER(DeviceInfo), _E]),
     "ldb_gpu_synchronize": (C.c_int, [_P, _E]),
     "ldb_gpu_context_stream": (C.c_void_p, [_P]),
+    "ldb_gpu_context_h2d_bytes": (C.c_int64, [_P]),
     "ldb_gpu_launch_count": (C.c_int64, [_P]),
     "ldb_gpu_timer_start": (C.c_int, [_P, _E]),
     "ldb_gpu_timer_stop": (C.c_int, [_P, C.POINTER(C.c_float), _E]),

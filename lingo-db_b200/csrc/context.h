@@ -4,8 +4,12 @@
 #include "kernels.h"
 
 #include <cuda_runtime.h>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -27,6 +31,29 @@ inline void cudaCheck(cudaError_t e, const char* what, const char* file, int lin
 struct ApiError : std::runtime_error {
    int code;
    ApiError(int code, const std::string& m) : std::runtime_error(m), code(code) {}
+};
+
+// Host worker pool used while staging HOST batches (narrowing decimal128 → the 8 bytes the kernels read).
+class HostPool {
+   std::vector<std::thread> threads;
+   std::mutex m;
+   std::condition_variable cvStart, cvDone;
+   std::function<void(int, int)> job; // (worker, nWorkers)
+   uint64_t generation = 0;
+   int running = 0;
+   bool stop = false;
+   void main(int id);
+
+   public:
+   explicit HostPool(int n);
+   ~HostPool();
+   int size() const { return (int) threads.size() + 1; }
+   void run(const std::function<void(int, int)>& fn); // caller is worker 0
+};
+struct PinnedSlot {
+   void* host = nullptr;
+   cudaEvent_t done = nullptr;
+   bool inFlight = false;
 };
 
 struct KernelFamilyTimer {
@@ -55,6 +82,13 @@ struct LdbContext {
    // staging pool for HOST batches: size → free device buffers
    std::multimap<size_t, void*> stagingFree;
    std::map<void*, size_t> stagingSize;
+   // narrow staging: decimal128(p<19) HOST columns cross PCIe as 8 bytes/value (the JIT truncates them to i64 anyway)
+   bool narrowStaging = true;
+   std::unique_ptr<ldb::HostPool> pool;
+   static constexpr size_t kPinnedSlotBytes = 32u << 20;
+   std::vector<ldb::PinnedSlot> pinned;
+   size_t nextPinned = 0;
+   int64_t h2dBytes = 0; // bytes this context copied host→device while staging tables
 
    void* stagingAlloc(size_t bytes);
    void stagingRelease(void* p);
@@ -82,6 +116,7 @@ struct LdbBatch {
    int64_t nRows = 0;
    std::vector<const void*> data;  // per column: values / utf8 offsets (device)
    std::vector<const void*> bytes; // per column: utf8 bytes (device) or null
+   std::vector<int32_t> elemBytes; // per column: bytes per value as staged (decimal128: 16, or 8 when narrowed)
    std::vector<void*> owned;       // staging buffers to give back on clear
    cudaEvent_t ready = nullptr;    // H2D of this batch finished (null for borrowed device batches)
 };

@@ -32,15 +32,20 @@ struct SmemTile {
    uint32_t stage; // shared-space address of the stage
    const StagedCols* sc;
    __device__ __forceinline__ int32_t i32(int col, int lr) const { return ldShared32(stage + sc->smemOffset[col] + lr * 4); }
-   __device__ __forceinline__ int64_t lo64(int col, int lr) const { return ldShared64(stage + sc->smemOffset[col] + lr * 16); }
-   __device__ __forceinline__ int64_t hi64(int col, int lr) const { return ldShared64(stage + sc->smemOffset[col] + lr * 16 + 8); }
+   // decimal cells are 16 bytes as in Arrow, or 8 when a HOST batch was narrowed while staging (runtime.cpp)
+   __device__ __forceinline__ int64_t lo64(int col, int lr) const { return ldShared64(stage + sc->smemOffset[col] + lr * sc->elemBytes[col]); }
+   __device__ __forceinline__ int64_t hi64(int col, int lr) const {
+      return sc->elemBytes[col] == 16 ? ldShared64(stage + sc->smemOffset[col] + lr * 16 + 8) : (lo64(col, lr) >> 63);
+   }
 };
 struct GlobalTile {
    int64_t rowBase;
    const StagedCols* sc;
    __device__ __forceinline__ int32_t i32(int col, int lr) const { return ldStream32((const int32_t*) sc->base[col] + rowBase + lr); }
-   __device__ __forceinline__ int64_t lo64(int col, int lr) const { return ldStream64((const int64_t*) sc->base[col] + 2 * (rowBase + lr)); }
-   __device__ __forceinline__ int64_t hi64(int col, int lr) const { return ldStream64((const int64_t*) sc->base[col] + 2 * (rowBase + lr) + 1); }
+   __device__ __forceinline__ int64_t lo64(int col, int lr) const { return ldStream64((const int64_t*) (sc->base[col] + (size_t) (rowBase + lr) * sc->elemBytes[col])); }
+   __device__ __forceinline__ int64_t hi64(int col, int lr) const {
+      return sc->elemBytes[col] == 16 ? ldStream64((const int64_t*) (sc->base[col] + (size_t) (rowBase + lr) * 16 + 8)) : (lo64(col, lr) >> 63);
+   }
 };
 __device__ __forceinline__ void issueTile(const StagedCols& sc, uint8_t* smem, uint64_t* bars /* full[] */, int64_t tile, int s) {
    const uint64_t policy = evictFirstPolicy();

@@ -109,6 +109,58 @@ uint32_t opMask(int op) {
 }
 } // namespace
 
+// ------------------------------------------------------------------------------------------------ host pool
+namespace ldb {
+HostPool::HostPool(int n) {
+   for (int i = 1; i < n; i++) threads.emplace_back([this, i] { main(i); });
+}
+HostPool::~HostPool() {
+   {
+      std::unique_lock<std::mutex> l(m);
+      stop = true;
+   }
+   cvStart.notify_all();
+   for (auto& t : threads) t.join();
+}
+void HostPool::main(int id) {
+   uint64_t seen = 0;
+   while (true) {
+      std::function<void(int, int)> fn;
+      {
+         std::unique_lock<std::mutex> l(m);
+         cvStart.wait(l, [&] { return stop || generation != seen; });
+         if (stop) return;
+         seen = generation;
+         fn = job;
+      }
+      fn(id, size());
+      std::unique_lock<std::mutex> l(m);
+      if (--running == 0) cvDone.notify_all();
+   }
+}
+void HostPool::run(const std::function<void(int, int)>& fn) {
+   {
+      std::unique_lock<std::mutex> l(m);
+      job = fn;
+      running = (int) threads.size();
+      generation++;
+   }
+   cvStart.notify_all();
+   fn(0, size());
+   std::unique_lock<std::mutex> l(m);
+   cvDone.wait(l, [&] { return running == 0; });
+}
+} // namespace ldb
+
+// decimal128 cells → their low 8 bytes, `n` values, all pool workers
+static void narrowDecimals(LdbContext* ctx, const uint8_t* src, int64_t n, uint64_t* dst) {
+   ctx->pool->run([&](int w, int nw) {
+      int64_t per = (n + nw - 1) / nw, b = per * w, e = std::min<int64_t>(n, b + per);
+      const uint64_t* s = reinterpret_cast<const uint64_t*>(src);
+      for (int64_t i = b; i < e; i++) dst[i] = s[2 * i];
+   });
+}
+
 // ------------------------------------------------------------------------------------------------ context
 void* LdbContext::stagingAlloc(size_t bytes) {
    bytes = std::max<size_t>(256, (bytes + 255) & ~size_t(255));
@@ -156,6 +208,7 @@ int ldb_gpu_context_create(int device, LdbContext** out, LdbError* err) {
       LDB_CUDA(cudaEventCreate(&ctx->timerStart));
       LDB_CUDA(cudaEventCreate(&ctx->timerStop));
       LDB_CUDA(cudaEventCreateWithFlags(&ctx->computeDone, cudaEventDisableTiming));
+      if (const char* e = getenv("LDB_NARROW_STAGING")) ctx->narrowStaging = atoi(e) != 0;
       *out = ctx.release();
    });
 }
@@ -171,6 +224,10 @@ void ldb_gpu_context_destroy(LdbContext* ctx) {
    while (!ctx->tables.empty()) ldb_gpu_table_destroy(ctx->tables.back());
    for (auto* s : ctx->states) destroyState(s);
    for (auto& kv : ctx->stagingSize) cudaFree(kv.first);
+   for (auto& ps : ctx->pinned) {
+      if (ps.host) cudaFreeHost(ps.host);
+      if (ps.done) cudaEventDestroy(ps.done);
+   }
    for (auto e : ctx->eventPool) cudaEventDestroy(e);
    for (auto& kv : ctx->timers)
       for (auto& pr : kv.second.pending) {
@@ -208,6 +265,7 @@ int ldb_gpu_synchronize(LdbContext* ctx, LdbError* err) {
    });
 }
 void* ldb_gpu_context_stream(LdbContext* ctx) { return ctx ? (void*) ctx->compute : nullptr; }
+int64_t ldb_gpu_context_h2d_bytes(LdbContext* ctx) { return ctx ? ctx->h2dBytes : 0; }
 int64_t ldb_gpu_launch_count(LdbContext* ctx) { return ctx ? ctx->launches : 0; }
 int ldb_gpu_timer_start(LdbContext* ctx, LdbError* err) {
    return guarded(err, [&] { LDB_CUDA(cudaEventRecord(ctx->timerStart, ctx->compute)); });
@@ -280,6 +338,7 @@ int ldb_gpu_table_append_batch(LdbTable* t, int64_t n_rows, const LdbArrayView* 
       size_t nc = t->columns.size();
       b.data.resize(nc);
       b.bytes.assign(nc, nullptr);
+      b.elemBytes.assign(nc, 0);
       for (size_t c = 0; c < nc; c++) {
          const LdbArrayView& av = columns[c];
          if (av.null_count != 0) fail(LDB_ERR_UNSUPPORTED, "nullable batches are not supported on the GPU path yet");
@@ -288,13 +347,43 @@ int ldb_gpu_table_append_batch(LdbTable* t, int64_t n_rows, const LdbArrayView* 
          bool utf8 = t->columns[c].type == LDB_UTF8;
          const uint8_t* src = (const uint8_t*) av.buffers[1] + (size_t) av.offset * w;
          size_t bytes = (size_t) (n_rows + (utf8 ? 1 : 0)) * w;
+         b.elemBytes[c] = (int32_t) w;
          if (location == LDB_MEM_DEVICE) {
             b.data[c] = src;
             if (utf8) b.bytes[c] = av.buffers[2];
+         } else if (ctx->narrowStaging && t->columns[c].type == LDB_DECIMAL128 && t->columns[c].precision < 19 && n_rows > 0) {
+            // narrow on the host into a ring of pinned slots, copy 8 B/value: chunk k+1 is narrowed while chunk k is on the wire
+            if (!ctx->pool) {
+               int hw = (int) std::thread::hardware_concurrency();
+               int nt = std::max(1, std::min(32, hw / 4));
+               if (const char* e = getenv("LDB_STAGING_THREADS")) nt = std::max(1, atoi(e));
+               ctx->pool = std::make_unique<HostPool>(nt);
+               ctx->pinned.resize(4);
+               for (auto& ps : ctx->pinned) {
+                  LDB_CUDA(cudaMallocHost(&ps.host, LdbContext::kPinnedSlotBytes));
+                  LDB_CUDA(cudaEventCreateWithFlags(&ps.done, cudaEventDisableTiming));
+               }
+            }
+            uint8_t* dst = (uint8_t*) ctx->stagingAlloc((size_t) n_rows * 8);
+            b.owned.push_back(dst);
+            const int64_t chunkRows = (int64_t) (LdbContext::kPinnedSlotBytes / 8);
+            for (int64_t r0 = 0; r0 < n_rows; r0 += chunkRows) {
+               int64_t m = std::min<int64_t>(chunkRows, n_rows - r0);
+               PinnedSlot& ps = ctx->pinned[ctx->nextPinned++ % ctx->pinned.size()];
+               if (ps.inFlight) LDB_CUDA(cudaEventSynchronize(ps.done));
+               narrowDecimals(ctx, src + (size_t) r0 * 16, m, (uint64_t*) ps.host);
+               LDB_CUDA(cudaMemcpyAsync(dst + (size_t) r0 * 8, ps.host, (size_t) m * 8, cudaMemcpyHostToDevice, ctx->copy));
+               LDB_CUDA(cudaEventRecord(ps.done, ctx->copy));
+               ps.inFlight = true;
+               ctx->h2dBytes += m * 8;
+            }
+            b.data[c] = dst;
+            b.elemBytes[c] = 8;
          } else {
             void* dst = ctx->stagingAlloc(bytes);
             b.owned.push_back(dst);
             LDB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy));
+            ctx->h2dBytes += (int64_t) bytes;
             b.data[c] = dst;
             if (utf8) {
                if (!utf8_bytes) fail(LDB_ERR_INVALID, "utf8 column needs utf8_bytes");
@@ -302,6 +391,7 @@ int ldb_gpu_table_append_batch(LdbTable* t, int64_t n_rows, const LdbArrayView* 
                void* d2 = ctx->stagingAlloc(sb);
                b.owned.push_back(d2);
                LDB_CUDA(cudaMemcpyAsync(d2, av.buffers[2], (size_t) utf8_bytes[c], cudaMemcpyHostToDevice, ctx->copy));
+               ctx->h2dBytes += utf8_bytes[c];
                b.bytes[c] = d2;
             }
          }
@@ -597,7 +687,7 @@ struct StagePlan {
       bool aligned = true;
       for (int i = 0; i < n; i++) {
          out.base[i] = (const uint8_t*) b.data[colIdx[i]];
-         out.elemBytes[i] = (int32_t) elemWidth(t->columns[colIdx[i]].type);
+         out.elemBytes[i] = b.elemBytes[colIdx[i]]; // as staged: decimal128 is 16, or 8 when the HOST batch was narrowed
          out.smemOffset[i] = off;
          off += out.elemBytes[i] * out.tileRows;
          aligned &= ((uintptr_t) out.base[i] % 16) == 0;
