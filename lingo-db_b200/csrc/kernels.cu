@@ -28,23 +28,28 @@ constexpr int kBlock = kBlockThreads;
 // counted in bytes on an mbarrier; 2 stages so the copy of tile t+2 overlaps the arithmetic on
 // tile t+1).  The last partial tile — and tables whose column bases are not 16-byte aligned —
 // are read with plain coalesced loads through the same accessor interface.
+// DB = bytes per decimal128 cell as staged: 16 (Arrow layout) or 8 (narrowed HOST batch) — a compile-time constant so the
+// issue-bound group-by kernel keeps immediate strides (a run-time stride cost Q1 5 %, profiles/r1_ab_filter_stride.md)
+template <int DB>
 struct SmemTile {
    uint32_t stage; // shared-space address of the stage
    const StagedCols* sc;
    __device__ __forceinline__ int32_t i32(int col, int lr) const { return ldShared32(stage + sc->smemOffset[col] + lr * 4); }
-   // decimal cells are 16 bytes as in Arrow, or 8 when a HOST batch was narrowed while staging (runtime.cpp)
-   __device__ __forceinline__ int64_t lo64(int col, int lr) const { return ldShared64(stage + sc->smemOffset[col] + lr * sc->elemBytes[col]); }
+   __device__ __forceinline__ int64_t lo64(int col, int lr) const { return ldShared64(stage + sc->smemOffset[col] + lr * DB); }
    __device__ __forceinline__ int64_t hi64(int col, int lr) const {
-      return sc->elemBytes[col] == 16 ? ldShared64(stage + sc->smemOffset[col] + lr * 16 + 8) : (lo64(col, lr) >> 63);
+      if constexpr (DB == 16) return ldShared64(stage + sc->smemOffset[col] + lr * 16 + 8);
+      else return lo64(col, lr) >> 63;
    }
 };
+template <int DB>
 struct GlobalTile {
    int64_t rowBase;
    const StagedCols* sc;
    __device__ __forceinline__ int32_t i32(int col, int lr) const { return ldStream32((const int32_t*) sc->base[col] + rowBase + lr); }
-   __device__ __forceinline__ int64_t lo64(int col, int lr) const { return ldStream64((const int64_t*) (sc->base[col] + (size_t) (rowBase + lr) * sc->elemBytes[col])); }
+   __device__ __forceinline__ int64_t lo64(int col, int lr) const { return ldStream64((const int64_t*) (sc->base[col] + (size_t) (rowBase + lr) * DB)); }
    __device__ __forceinline__ int64_t hi64(int col, int lr) const {
-      return sc->elemBytes[col] == 16 ? ldStream64((const int64_t*) (sc->base[col] + (size_t) (rowBase + lr) * 16 + 8)) : (lo64(col, lr) >> 63);
+      if constexpr (DB == 16) return ldStream64((const int64_t*) (sc->base[col] + (size_t) (rowBase + lr) * 16 + 8));
+      else return lo64(col, lr) >> 63;
    }
 };
 __device__ __forceinline__ void issueTile(const StagedCols& sc, uint8_t* smem, uint64_t* bars /* full[] */, int64_t tile, int s) {
@@ -67,7 +72,7 @@ struct TileBarriers {
    uint64_t full[kStages];
    uint64_t empty[kStages];
 };
-template <int kRowsPerThread, class Fn>
+template <int kRowsPerThread, int DB, class Fn>
 __device__ __forceinline__ void forEachTile(const StagedCols& sc, int64_t n, uint8_t* smem, TileBarriers* bars, const Fn& fnTile) {
    constexpr int kTileRows = kRowsPerThread * kBlock; // == sc.tileRows (host binds the same constant)
    const int64_t nFull = n / kTileRows;
@@ -95,7 +100,7 @@ __device__ __forceinline__ void forEachTile(const StagedCols& sc, int64_t n, uin
          for (int64_t t = blockIdx.x; t < nFull; t += gridDim.x, it++) {
             const int s = it % kStages;
             mbarWait(&bars->full[s], (uint32_t) (it / kStages) & 1u);
-            SmemTile tile{smemAddr(smem) + (uint32_t) s * sc.stageBytes, &sc};
+            SmemTile<DB> tile{smemAddr(smem) + (uint32_t) s * sc.stageBytes, &sc};
             fnTile(tile, t * kTileRows, kTileRows);
             __syncwarp();
             if ((threadIdx.x & 31) == 0) mbarArrive(&bars->empty[s]); // this warp is done with stage s
@@ -104,21 +109,21 @@ __device__ __forceinline__ void forEachTile(const StagedCols& sc, int64_t n, uin
    } else if (!producer) {
       for (int64_t t = blockIdx.x; t < nFull; t += gridDim.x) {
          __syncwarp();
-         GlobalTile tile{t * kTileRows, &sc};
+         GlobalTile<DB> tile{t * kTileRows, &sc};
          fnTile(tile, t * kTileRows, kTileRows);
       }
    }
    // the partial tail tile goes to the CTA that would have been next in the round robin
    if (!producer && nFull * kTileRows < n && (int64_t) blockIdx.x == nFull % gridDim.x) {
       __syncwarp();
-      GlobalTile tile{nFull * kTileRows, &sc};
+      GlobalTile<DB> tile{nFull * kTileRows, &sc};
       fnTile(tile, nFull * kTileRows, (int) (n - nFull * kTileRows));
    }
 }
 // Non-specialised variant for the arithmetic-bound group-by kernel (K1/K2): every row costs the same, so the CTA-wide
 // barrier is cheap (stall_barrier 0.1 per issue) and a 9th warp would only cost registers (2 CTAs x 288 threads
 // cap the kernel at 112 registers → spills).  One elected thread issues the copies, __syncthreads() recycles a stage.
-template <int kRowsPerThread, class Fn>
+template <int kRowsPerThread, int DB, class Fn>
 __device__ __forceinline__ void forEachTileUniform(const StagedCols& sc, int64_t n, uint8_t* smem, TileBarriers* bars, const Fn& fnTile) {
    constexpr int kTileRows = kRowsPerThread * kBlock;
    const int64_t nFull = n / kTileRows;
@@ -138,7 +143,7 @@ __device__ __forceinline__ void forEachTileUniform(const StagedCols& sc, int64_t
       for (int64_t t = blockIdx.x; t < nFull; t += gridDim.x, it++) {
          const int s = it % kStages;
          mbarWait(&bars->full[s], (uint32_t) (it / kStages) & 1u);
-         SmemTile tile{smemAddr(smem) + (uint32_t) s * sc.stageBytes, &sc};
+         SmemTile<DB> tile{smemAddr(smem) + (uint32_t) s * sc.stageBytes, &sc};
          fnTile(tile, t * kTileRows, kTileRows);
          __syncthreads(); // every thread is done with stage s → refill it
          const int64_t nt = t + (int64_t) kStages * gridDim.x;
@@ -147,19 +152,19 @@ __device__ __forceinline__ void forEachTileUniform(const StagedCols& sc, int64_t
    } else {
       for (int64_t t = blockIdx.x; t < nFull; t += gridDim.x) {
          __syncwarp();
-         GlobalTile tile{t * kTileRows, &sc};
+         GlobalTile<DB> tile{t * kTileRows, &sc};
          fnTile(tile, t * kTileRows, kTileRows);
       }
    }
    if (nFull * kTileRows < n && (int64_t) blockIdx.x == nFull % gridDim.x) {
       __syncwarp();
-      GlobalTile tile{nFull * kTileRows, &sc};
+      GlobalTile<DB> tile{nFull * kTileRows, &sc};
       fnTile(tile, nFull * kTileRows, (int) (n - nFull * kTileRows));
    }
 }
-template <int kRowsPerThread, class Fn>
+template <int kRowsPerThread, int DB, class Fn>
 __device__ __forceinline__ void forEachRowUniform(const StagedCols& sc, int64_t n, uint8_t* smem, TileBarriers* bars, const Fn& fn) {
-   forEachTileUniform<kRowsPerThread>(sc, n, smem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+   forEachTileUniform<kRowsPerThread, DB>(sc, n, smem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
 #pragma unroll
       for (int j = 0; j < kRowsPerThread; j++) {
          const int lr = j * kBlock + threadIdx.x;
@@ -170,9 +175,9 @@ __device__ __forceinline__ void forEachRowUniform(const StagedCols& sc, int64_t 
 }
 // fn(tile, localRow, globalRow, valid) is called for every row with all 32 lanes of a warp converged
 // (lanes beyond the end of the table come with valid == false), so fn may use warp collectives.
-template <int kRowsPerThread, class Fn>
+template <int kRowsPerThread, int DB, class Fn>
 __device__ __forceinline__ void forEachRow(const StagedCols& sc, int64_t n, uint8_t* smem, TileBarriers* bars, const Fn& fn) {
-   forEachTile<kRowsPerThread>(sc, n, smem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+   forEachTile<kRowsPerThread, DB>(sc, n, smem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
 #pragma unroll
       for (int j = 0; j < kRowsPerThread; j++) {
          const int lr = j * kBlock + threadIdx.x;
@@ -186,7 +191,14 @@ __device__ __forceinline__ void forEachRow(const StagedCols& sc, int64_t n, uint
 // Conjunction of column-vs-constant predicates (Restrictions::applyFilters, Restrictions.cpp:365-390):
 // instead of one compaction pass per filter over a uint16 selection vector, every predicate is
 // evaluated in registers on the staged tile and the row is simply skipped.
-template <class Tile>
+// IN list: linear search like the reference does for <= 10 values (Restrictions.cpp:207-218)
+__device__ __noinline__ bool inListContains(const FilterCol& f, int64_t v) {
+   bool any = false;
+   for (int k = 0; k < f.nIn; k++) any |= v == f.inVals[k];
+   return any;
+}
+// IN = the pipeline has at least one IN-list filter (host decides); pipelines without one carry no trace of it
+template <bool IN, class Tile>
 __device__ __forceinline__ bool evalFilters(const FilterSet& F, const Tile& tile, int lr, int64_t row) {
    bool pass = true;
 #pragma unroll
@@ -206,11 +218,8 @@ __device__ __forceinline__ bool evalFilters(const FilterSet& F, const Tile& tile
                for (int k = 0; k < f.strLen; k++) eq &= __ldg(f.bytes + b + k) == f.str[k];
             v = eq ? 1 : 0;
          }
-         if (f.nIn > 0) { // IN list: linear search like the reference does for <= 10 values (Restrictions.cpp:207-218)
-            bool any = false;
-#pragma unroll
-            for (int k = 0; k < 8; k++) any |= (k < f.nIn) & (v == f.inVals[k]);
-            pass &= any;
+         if (IN && f.nIn > 0) { // IN list (rare): out of line, so the hot kernels do not carry its code
+            pass &= inListContains(f, v);
          } else {
             pass &= cmpMask(v, f.valA, f.maskA);
             if (f.maskB != 7u) pass &= cmpMask(v, f.valB, f.maskB);
@@ -455,7 +464,7 @@ extern __shared__ __align__(128) uint8_t dynSmem[];
 // reference's 1024-slot per-worker pre-aggregation cache (PreAggregationHashtable.cpp:46-60) collapses to
 // this for small domains; further groups use shared-memory atomics, and only a CTA that meets
 // more than LG groups touches the HBM table per row.  One flush per CTA at the end.
-template <int NK, int NV, class... As>
+template <int DB, bool IN, int NK, int NV, class... As>
 __global__ void __launch_bounds__(kBlock, 2) scanGroupByKernel(const __grid_constant__ GroupByParams p) {
    using AL = Aggs<As...>;
    constexpr int N = AL::N;
@@ -488,14 +497,14 @@ __global__ void __launch_bounds__(kBlock, 2) scanGroupByKernel(const __grid_cons
 #pragma unroll
    for (int g = 0; g < GREG; g++) rk0[g] = rk1[g] = 0;
 
-   forEachRowUniform<kRowsPerThreadScan>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
+   forEachRowUniform<kRowsPerThreadScan, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
       int64_t vals[NV];
 #pragma unroll
       for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lr);
       int32_t k0 = 0, k1 = 0;
       if constexpr (NK > 0) k0 = tile.i32(p.keyStage[0], lr);
       if constexpr (NK > 1) k1 = tile.i32(p.keyStage[1], lr);
-      const bool pass = valid & evalFilters(p.src.filters, tile, lr, row);
+      const bool pass = valid & evalFilters<IN>(p.src.filters, tile, lr, row);
       int id = 0;
       if constexpr (NK > 0) {
          // Resolve the CTA-local group id under WARP-UNIFORM control flow.  (A per-lane spin lock
@@ -616,11 +625,27 @@ static int persistentGrid(K kernel, const StagedCols& sc, int64_t nRows, int smC
    int64_t tiles = (nRows + sc.tileRows - 1) / sc.tileRows;
    return (int) std::min<int64_t>(std::max<int64_t>(tiles, 1), (int64_t) smCount * perSm);
 }
+static bool hasInList(const FilterSet& f) {
+   for (int i = 0; i < f.n; i++)
+      if (f.c[i].nIn > 0) return true;
+   return false;
+}
+template <int DB, bool IN, int NK, int NV, class... As>
+static void launchGBd(const GroupByParams& p, int smCount, cudaStream_t s) {
+   size_t dyn;
+   int grid = persistentGrid(scanGroupByKernel<DB, IN, NK, NV, As...>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+   scanGroupByKernel<DB, IN, NK, NV, As...><<<grid, kBlock, dyn, s>>>(p);
+}
 template <int NK, int NV, class... As>
 static void launchGB(const GroupByParams& p, int smCount, cudaStream_t s) {
-   size_t dyn;
-   int grid = persistentGrid(scanGroupByKernel<NK, NV, As...>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
-   scanGroupByKernel<NK, NV, As...><<<grid, kBlock, dyn, s>>>(p);
+   const bool in = hasInList(p.src.filters);
+   if (p.src.cols.decBytes == 8) {
+      if (in) launchGBd<8, true, NK, NV, As...>(p, smCount, s);
+      else launchGBd<8, false, NK, NV, As...>(p, smCount, s);
+   } else {
+      if (in) launchGBd<16, true, NK, NV, As...>(p, smCount, s);
+      else launchGBd<16, false, NK, NV, As...>(p, smCount, s);
+   }
 }
 using C0 = Agg<LDB_EXPR_COL, 0>;
 using C1 = Agg<LDB_EXPR_COL, 1>;
@@ -667,12 +692,14 @@ __device__ __forceinline__ void flushInsertCount(const JoinTableDev& t, unsigned
 // scan → filters → [probe parent table] → insert {key, payload, side…}
 // (subop.materialize + rt::GrowingBuffer::insert + rt::HashIndexedView::build; for the group-join
 //  the lookup_or_insert of the left input, RelAlgToSubOp.cpp:2682-2950)
+template <int DB>
 __global__ void __launch_bounds__(kThreads, 4) scanBuildKernel(const __grid_constant__ BuildParams p) {
+   constexpr bool IN = true; // latency-bound kernels keep the IN path in
    __shared__ __align__(8) TileBarriers barsStorage;
    TileBarriers* bars = &barsStorage;
    unsigned long long inserted = 0;
-   forEachRow<kRowsPerThreadProbe>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
-      if (!(valid && evalFilters(p.src.filters, tile, lr, row))) return;
+   forEachRow<kRowsPerThreadProbe, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
+      if (!(valid && evalFilters<IN>(p.src.filters, tile, lr, row))) return;
       const int32_t key = tile.i32(p.keyStage, lr);
       auto insert = [&](int32_t payload) {
          int64_t slot = joinInsert(p.sink, key, payload);
@@ -693,8 +720,13 @@ __global__ void __launch_bounds__(kThreads, 4) scanBuildKernel(const __grid_cons
 }
 void launchScanBuild(const BuildParams& p, int smCount, cudaStream_t s) {
    size_t dyn;
-   int grid = persistentGrid(scanBuildKernel, p.src.cols, p.src.nRows, smCount, &dyn);
-   scanBuildKernel<<<grid, kThreads, dyn, s>>>(p);
+   if (p.src.cols.decBytes == 8) {
+      int grid = persistentGrid(scanBuildKernel<8>, p.src.cols, p.src.nRows, smCount, &dyn);
+      scanBuildKernel<8><<<grid, kThreads, dyn, s>>>(p);
+   } else {
+      int grid = persistentGrid(scanBuildKernel<16>, p.src.cols, p.src.nRows, smCount, &dyn);
+      scanBuildKernel<16><<<grid, kThreads, dyn, s>>>(p);
+   }
 }
 
 // =================================================================================== K8 materialize
@@ -707,11 +739,13 @@ __device__ __forceinline__ bool bloomMayContain(const JoinTableDev& t, int32_t k
    const uint32_t bits = bloomBits(h);
    return (__ldg(&t.bloom[(uint32_t) (h >> 32) & t.bloomMask]) & bits) == bits;
 }
+template <int DB>
 __global__ void __launch_bounds__(kThreads, 4) scanMaterializeKernel(const __grid_constant__ MaterializeParams p) {
+   constexpr bool IN = true;
    __shared__ __align__(8) TileBarriers barsStorage;
    TileBarriers* bars = &barsStorage;
-   forEachRow<kRowsPerThreadProbe>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
-      if (!(valid && evalFilters(p.src.filters, tile, lr, row))) return;
+   forEachRow<kRowsPerThreadProbe, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
+      if (!(valid && evalFilters<IN>(p.src.filters, tile, lr, row))) return;
       auto emit = [&](int32_t payload) {
          const unsigned active = __activemask();
          const int lane = threadIdx.x & 31, leader = __ffs(active) - 1;
@@ -747,20 +781,26 @@ __global__ void __launch_bounds__(kThreads, 4) scanMaterializeKernel(const __gri
 }
 void launchScanMaterialize(const MaterializeParams& p, int smCount, cudaStream_t s) {
    size_t dyn;
-   int grid = persistentGrid(scanMaterializeKernel, p.src.cols, p.src.nRows, smCount, &dyn);
-   scanMaterializeKernel<<<grid, kThreads, dyn, s>>>(p);
+   if (p.src.cols.decBytes == 8) {
+      int grid = persistentGrid(scanMaterializeKernel<8>, p.src.cols, p.src.nRows, smCount, &dyn);
+      scanMaterializeKernel<8><<<grid, kThreads, dyn, s>>>(p);
+   } else {
+      int grid = persistentGrid(scanMaterializeKernel<16>, p.src.cols, p.src.nRows, smCount, &dyn);
+      scanMaterializeKernel<16><<<grid, kThreads, dyn, s>>>(p);
+   }
 }
 
 // =================================================================================== K5 probe + aggregate
 // scan → filters → pure lookup in the group-join map → SUM into the shared entry.  The reference
 // takes a per-entry spin lock (SubOpToControlFlow.cpp:4218-4251, EntryLock.cpp:9-25) or an
 // atomic_rmw; here the i128 SUM is two 64-bit atomics with carry (exact, order independent).
-template <int NV>
+template <int NV, int DB>
 __global__ void __launch_bounds__(kThreads, 4) scanProbeAggKernel(const __grid_constant__ ProbeAggParams p) {
+   constexpr bool IN = true;
    __shared__ __align__(8) TileBarriers barsStorage;
    TileBarriers* bars = &barsStorage;
    const int64_t one = 100;
-   forEachTile<kRowsPerThreadProbe>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+   forEachTile<kRowsPerThreadProbe, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
       int32_t key[kRowsPerThreadProbe];
       int lrs[kRowsPerThreadProbe];
       BloomProbe bp[kRowsPerThreadProbe];
@@ -770,7 +810,7 @@ __global__ void __launch_bounds__(kThreads, 4) scanProbeAggKernel(const __grid_c
          const int lr = j * kBlock + threadIdx.x;
          const bool valid = lr < rows;
          lrs[j] = valid ? lr : 0;
-         const bool ok = valid && evalFilters(p.src.filters, tile, lrs[j], rowBase + lrs[j]);
+         const bool ok = valid && evalFilters<IN>(p.src.filters, tile, lrs[j], rowBase + lrs[j]);
          key[j] = tile.i32(p.probeKeyStage, lrs[j]);
          bp[j] = bloomPrefetch(p.table, key[j], ok);
       }
@@ -798,14 +838,29 @@ bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, co
    }
    size_t dyn;
    if (nv == 1) {
-      int grid = persistentGrid(scanProbeAggKernel<1>, p.src.cols, p.src.nRows, smCount, &dyn);
-      scanProbeAggKernel<1><<<grid, kThreads, dyn, s>>>(p);
+      if (p.src.cols.decBytes == 8) {
+         int grid = persistentGrid(scanProbeAggKernel<1, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbeAggKernel<1, 8><<<grid, kThreads, dyn, s>>>(p);
+      } else {
+         int grid = persistentGrid(scanProbeAggKernel<1, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbeAggKernel<1, 16><<<grid, kThreads, dyn, s>>>(p);
+      }
    } else if (nv == 2) {
-      int grid = persistentGrid(scanProbeAggKernel<2>, p.src.cols, p.src.nRows, smCount, &dyn);
-      scanProbeAggKernel<2><<<grid, kThreads, dyn, s>>>(p);
+      if (p.src.cols.decBytes == 8) {
+         int grid = persistentGrid(scanProbeAggKernel<2, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbeAggKernel<2, 8><<<grid, kThreads, dyn, s>>>(p);
+      } else {
+         int grid = persistentGrid(scanProbeAggKernel<2, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbeAggKernel<2, 16><<<grid, kThreads, dyn, s>>>(p);
+      }
    } else {
-      int grid = persistentGrid(scanProbeAggKernel<3>, p.src.cols, p.src.nRows, smCount, &dyn);
-      scanProbeAggKernel<3><<<grid, kThreads, dyn, s>>>(p);
+      if (p.src.cols.decBytes == 8) {
+         int grid = persistentGrid(scanProbeAggKernel<3, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbeAggKernel<3, 8><<<grid, kThreads, dyn, s>>>(p);
+      } else {
+         int grid = persistentGrid(scanProbeAggKernel<3, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbeAggKernel<3, 16><<<grid, kThreads, dyn, s>>>(p);
+      }
    }
    return true;
 }
@@ -813,12 +868,13 @@ bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, co
 // =================================================================================== K4 probe, probe, group
 // scan → probe A on keyA → probe B on keyB → keep rows whose payloads agree (the composite join key
 // (l_suppkey, c_nationkey) = (s_suppkey, s_nationkey) of Q5) → group by that payload → SUM.
-template <int NV>
+template <int NV, int DB>
 __global__ void __launch_bounds__(kThreads, 4) scanProbe2GroupByKernel(const __grid_constant__ Probe2GroupByParams p) {
+   constexpr bool IN = true;
    __shared__ __align__(8) TileBarriers barsStorage;
    TileBarriers* bars = &barsStorage;
    const int64_t one = 100;
-   forEachTile<kRowsPerThreadProbe>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+   forEachTile<kRowsPerThreadProbe, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
       int32_t key[kRowsPerThreadProbe];
       int lrs[kRowsPerThreadProbe];
       BloomProbe bp[kRowsPerThreadProbe];
@@ -827,7 +883,7 @@ __global__ void __launch_bounds__(kThreads, 4) scanProbe2GroupByKernel(const __g
          const int lr = j * kBlock + threadIdx.x;
          const bool valid = lr < rows;
          lrs[j] = valid ? lr : 0;
-         const bool ok = valid && evalFilters(p.src.filters, tile, lrs[j], rowBase + lrs[j]);
+         const bool ok = valid && evalFilters<IN>(p.src.filters, tile, lrs[j], rowBase + lrs[j]);
          key[j] = tile.i32(p.keyStageA, lrs[j]);
          bp[j] = bloomPrefetch(p.tableA, key[j], ok);
       }
@@ -863,14 +919,29 @@ bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStre
    }
    size_t dyn;
    if (nv == 1) {
-      int grid = persistentGrid(scanProbe2GroupByKernel<1>, p.src.cols, p.src.nRows, smCount, &dyn);
-      scanProbe2GroupByKernel<1><<<grid, kThreads, dyn, s>>>(p);
+      if (p.src.cols.decBytes == 8) {
+         int grid = persistentGrid(scanProbe2GroupByKernel<1, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbe2GroupByKernel<1, 8><<<grid, kThreads, dyn, s>>>(p);
+      } else {
+         int grid = persistentGrid(scanProbe2GroupByKernel<1, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbe2GroupByKernel<1, 16><<<grid, kThreads, dyn, s>>>(p);
+      }
    } else if (nv == 2) {
-      int grid = persistentGrid(scanProbe2GroupByKernel<2>, p.src.cols, p.src.nRows, smCount, &dyn);
-      scanProbe2GroupByKernel<2><<<grid, kThreads, dyn, s>>>(p);
+      if (p.src.cols.decBytes == 8) {
+         int grid = persistentGrid(scanProbe2GroupByKernel<2, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbe2GroupByKernel<2, 8><<<grid, kThreads, dyn, s>>>(p);
+      } else {
+         int grid = persistentGrid(scanProbe2GroupByKernel<2, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbe2GroupByKernel<2, 16><<<grid, kThreads, dyn, s>>>(p);
+      }
    } else {
-      int grid = persistentGrid(scanProbe2GroupByKernel<3>, p.src.cols, p.src.nRows, smCount, &dyn);
-      scanProbe2GroupByKernel<3><<<grid, kThreads, dyn, s>>>(p);
+      if (p.src.cols.decBytes == 8) {
+         int grid = persistentGrid(scanProbe2GroupByKernel<3, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbe2GroupByKernel<3, 8><<<grid, kThreads, dyn, s>>>(p);
+      } else {
+         int grid = persistentGrid(scanProbe2GroupByKernel<3, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbe2GroupByKernel<3, 16><<<grid, kThreads, dyn, s>>>(p);
+      }
    }
    return true;
 }

@@ -74,6 +74,7 @@ struct StagedCols {
    int32_t tileRows;   // rows per tile = kBlockThreads * rows-per-thread of the kernel
    int32_t stageBytes; // bytes of one stage = sum(elemBytes) * tileRows
    int32_t useTma;     // 0 when a column base is not 16-byte aligned: tiles are then read with plain loads
+   int32_t decBytes;   // bytes per decimal128 cell as staged: 16 (Arrow layout) or 8 (HOST batch narrowed); selects the kernel instantiation
    const uint8_t* base[kMaxStagedCols];
    int32_t elemBytes[kMaxStagedCols];  // 4 (int32/date32/fsb4) or 16 (decimal128)
    int32_t smemOffset[kMaxStagedCols]; // offset of the column inside a stage

@@ -694,6 +694,9 @@ struct StagePlan {
       }
       out.stageBytes = off;
       out.useTma = aligned && n > 0 ? 1 : 0;
+      out.decBytes = 16;
+      for (int i = 0; i < n; i++)
+         if (t->columns[colIdx[i]].type == LDB_DECIMAL128) out.decBytes = out.elemBytes[i]; // uniform per batch (all or none narrowed)
    }
 };
 struct FilterPlan {
