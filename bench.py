@@ -306,7 +306,7 @@ def run_ours(args):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te[0].item())
         e2e = {"value": total_rows * args.e2e_steps / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": h2d_step * world,
-               "host_arrow_bytes_per_step": h2d * world, "staging": "decimal128(12,2) cells narrowed to their low 8 bytes on the host (32 pool threads) before the copy; "
+               "host_arrow_bytes_per_step": h2d * world, "staging": "decimal128(12,2) cells narrowed to their low 8 bytes by a host thread pool (hw/10 threads) before the copy; "
                "int32/date32/fsb4 copied as they are",
                "d2h_bytes_per_step": 64 * 136 * world, "steps": args.e2e_steps, "ms_per_step": 1000 * e2e_s / args.e2e_steps,
                "batch_rows": args.e2e_batch_rows, "host_memory": "pinned", "note": "per-rank partial result; N>1 skips the cross-rank merge in this leg"}

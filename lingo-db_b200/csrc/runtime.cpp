@@ -355,7 +355,9 @@ int ldb_gpu_table_append_batch(LdbTable* t, int64_t n_rows, const LdbArrayView* 
             // narrow on the host into a ring of pinned slots, copy 8 B/value: chunk k+1 is narrowed while chunk k is on the wire
             if (!ctx->pool) {
                int hw = (int) std::thread::hardware_concurrency();
-               int nt = std::max(1, std::min(32, hw / 4));
+               // measured on the 2x32-core box (128 hw threads), ms per SF100 Q1 e2e step: 6 thr 796, 10 thr 634, 12 thr 531,
+               // 16 thr 621, 20 thr 573, 32 thr 946, 64 thr 1544 (no narrowing: 823) → ~hw/10; more threads fight over one NUMA node
+               int nt = std::max(2, std::min(16, hw / 10));
                if (const char* e = getenv("LDB_STAGING_THREADS")) nt = std::max(1, atoi(e));
                ctx->pool = std::make_unique<HostPool>(nt);
                ctx->pinned.resize(4);
