@@ -54,6 +54,18 @@ typedef struct LdbGenSupplierCols {
    int32_t* s_nationkey;
 } LdbGenSupplierCols;
 
+typedef struct LdbGenPartCols {
+   int32_t* p_partkey;
+   int32_t* p_name_offsets; /* utf8 offsets, n_rows + 1 */
+   uint8_t* p_name_data;
+} LdbGenPartCols;
+
+typedef struct LdbGenPartsuppCols {
+   int32_t* ps_partkey;
+   int32_t* ps_suppkey;
+   uint8_t* ps_supplycost; /* decimal128(12,2) */
+} LdbGenPartsuppCols;
+
 /* host side (libldb_datagen_host.so) */
 void ldbgen_scale(double sf, uint64_t seed, LdbGenScale* out);
 int64_t ldbgen_order_first_line(const LdbGenScale* g, int64_t order_idx);
@@ -61,6 +73,8 @@ void ldbgen_lineitem_host(const LdbGenScale* g, int64_t row_begin, int64_t n_row
 void ldbgen_orders_host(const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenOrdersCols* cols);
 int64_t ldbgen_customer_host(const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenCustomerCols* cols);
 void ldbgen_supplier_host(const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenSupplierCols* cols);
+int64_t ldbgen_part_host(const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenPartCols* cols); /* returns utf8 bytes, like customer */
+void ldbgen_partsupp_host(const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenPartsuppCols* cols); /* 4 * n_part rows */
 
 #ifdef __cplusplus
 }

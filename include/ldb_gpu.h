@@ -268,6 +268,9 @@ int ldb_gpu_datagen_orders(LdbContext* ctx, const struct LdbGenScale* g, int64_t
 int ldb_gpu_datagen_customer_fixed(LdbContext* ctx, const struct LdbGenScale* g, int64_t row_begin, int64_t n_rows, const struct LdbGenCustomerCols* dev_cols, int32_t* dev_seg_lengths, LdbError* err);
 int ldb_gpu_datagen_customer_bytes(LdbContext* ctx, const struct LdbGenScale* g, int64_t row_begin, int64_t n_rows, const int32_t* dev_offsets, uint8_t* dev_data, LdbError* err);
 int ldb_gpu_datagen_supplier(LdbContext* ctx, const struct LdbGenScale* g, int64_t row_begin, int64_t n_rows, const struct LdbGenSupplierCols* dev_cols, LdbError* err);
+int ldb_gpu_datagen_part_fixed(LdbContext* ctx, const struct LdbGenScale* g, int64_t row_begin, int64_t n_rows, const struct LdbGenPartCols* dev_cols, int32_t* dev_name_lengths, LdbError* err);
+int ldb_gpu_datagen_part_bytes(LdbContext* ctx, const struct LdbGenScale* g, int64_t row_begin, int64_t n_rows, const int32_t* dev_offsets, uint8_t* dev_data, LdbError* err);
+int ldb_gpu_datagen_partsupp(LdbContext* ctx, const struct LdbGenScale* g, int64_t row_begin, int64_t n_rows, const struct LdbGenPartsuppCols* dev_cols, LdbError* err);
 
 #ifdef __cplusplus
 }

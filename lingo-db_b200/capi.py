@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 from . import build as _build
-from .datagen import CustomerCols, GenScale, LineitemCols, OrdersCols, SupplierCols
+from .datagen import CustomerCols, GenScale, LineitemCols, OrdersCols, PartCols, PartsuppCols, SupplierCols
 
 LDB_OK, LDB_ERR_CUDA, LDB_ERR_UNSUPPORTED, LDB_ERR_INVALID, LDB_ERR_CAPACITY, LDB_ERR_NO_DEVICE = range(6)
 PHYS = {"int32": 0, "int64": 1, "date32": 2, "decimal128": 3, "fsb4": 4, "utf8": 5}
@@ -139,6 +139,9 @@ SIGNATURES = {
     "ldb_gpu_datagen_customer_fixed": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, C.POINTER(CustomerCols), _P, _E]),
     "ldb_gpu_datagen_customer_bytes": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, _P, _P, _E]),
     "ldb_gpu_datagen_supplier": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, C.POINTER(SupplierCols), _E]),
+    "ldb_gpu_datagen_part_fixed": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, C.POINTER(PartCols), _P, _E]),
+    "ldb_gpu_datagen_part_bytes": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, _P, _P, _E]),
+    "ldb_gpu_datagen_partsupp": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, C.POINTER(PartsuppCols), _E]),
     "ldb_tpch_q6": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(I128), _E]),
     "ldb_tpch_q6_partial": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(_P), _E]),
     "ldb_tpch_q1": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.POINTER(Q1Row), C.c_int32, C.POINTER(C.c_int32), _E]),

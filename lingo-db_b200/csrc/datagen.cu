@@ -71,6 +71,24 @@ __global__ void supplierKernel(Scale s, int64_t rowBegin, int64_t n, LdbGenSuppl
       if (c.s_nationkey) c.s_nationkey[i] = supplierNationKey(s, r);
    }
 }
+__global__ void partFixedKernel(Scale s, int64_t rowBegin, int64_t n, LdbGenPartCols c, int32_t* nameLengths) {
+   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+      int64_t r = rowBegin + i;
+      if (c.p_partkey) c.p_partkey[i] = (int32_t) (r + 1);
+      if (nameLengths) nameLengths[i] = partNameLen(s, r);
+   }
+}
+__global__ void partBytesKernel(Scale s, int64_t rowBegin, int64_t n, const int32_t* offsets, uint8_t* data) {
+   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) partNameWrite(s, rowBegin + i, data + offsets[i]);
+}
+__global__ void partsuppKernel(Scale s, int64_t rowBegin, int64_t n, LdbGenPartsuppCols c) {
+   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+      int64_t r = rowBegin + i;
+      if (c.ps_partkey) c.ps_partkey[i] = partSuppPartKey(r);
+      if (c.ps_suppkey) c.ps_suppkey[i] = partSuppSuppKey(s, r);
+      if (c.ps_supplycost) storeDec(c.ps_supplycost, i, partSuppSupplyCost(s, r));
+   }
+}
 int gridFor(LdbContext* ctx, int64_t n) { return (int) std::min<int64_t>(std::max<int64_t>((n + 255) / 256, 1), (int64_t) ctx->smCount * 16); }
 template <class Fn>
 int guardedGen(LdbError* err, const Fn& fn) {
@@ -124,6 +142,27 @@ int ldb_gpu_datagen_supplier(LdbContext* ctx, const LdbGenScale* g, int64_t row_
    return guardedGen(err, [&] {
       LDB_CUDA(cudaSetDevice(ctx->device));
       supplierKernel<<<gridFor(ctx, n_rows), 256, 0, ctx->compute>>>(toScale(g), row_begin, n_rows, *c);
+      LDB_CUDA(cudaGetLastError());
+   });
+}
+int ldb_gpu_datagen_part_fixed(LdbContext* ctx, const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenPartCols* c, int32_t* dev_name_lengths, LdbError* err) {
+   return guardedGen(err, [&] {
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      partFixedKernel<<<gridFor(ctx, n_rows), 256, 0, ctx->compute>>>(toScale(g), row_begin, n_rows, *c, dev_name_lengths);
+      LDB_CUDA(cudaGetLastError());
+   });
+}
+int ldb_gpu_datagen_part_bytes(LdbContext* ctx, const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const int32_t* dev_offsets, uint8_t* dev_data, LdbError* err) {
+   return guardedGen(err, [&] {
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      partBytesKernel<<<gridFor(ctx, n_rows), 256, 0, ctx->compute>>>(toScale(g), row_begin, n_rows, dev_offsets, dev_data);
+      LDB_CUDA(cudaGetLastError());
+   });
+}
+int ldb_gpu_datagen_partsupp(LdbContext* ctx, const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenPartsuppCols* c, LdbError* err) {
+   return guardedGen(err, [&] {
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      partsuppKernel<<<gridFor(ctx, n_rows), 256, 0, ctx->compute>>>(toScale(g), row_begin, n_rows, *c);
       LDB_CUDA(cudaGetLastError());
    });
 }

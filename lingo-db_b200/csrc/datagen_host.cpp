@@ -134,4 +134,30 @@ void ldbgen_supplier_host(const LdbGenScale* g, int64_t row_begin, int64_t n_row
    }
 }
 
+int64_t ldbgen_part_host(const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenPartCols* c) {
+   Scale s = toScale(g);
+   int64_t bytes = 0;
+   for (int64_t i = 0; i < n_rows; i++) {
+      int64_t r = row_begin + i;
+      if (c->p_partkey) c->p_partkey[i] = (int32_t) (r + 1);
+      if (c->p_name_offsets) c->p_name_offsets[i] = (int32_t) bytes;
+      if (c->p_name_data) partNameWrite(s, r, c->p_name_data + bytes);
+      bytes += partNameLen(s, r);
+   }
+   if (c->p_name_offsets) c->p_name_offsets[n_rows] = (int32_t) bytes;
+   return bytes;
+}
+
+void ldbgen_partsupp_host(const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenPartsuppCols* c) {
+   Scale s = toScale(g);
+   parallelFor(n_rows, [&](int64_t b, int64_t e) {
+      for (int64_t i = b; i < e; i++) {
+         int64_t r = row_begin + i;
+         if (c->ps_partkey) c->ps_partkey[i] = partSuppPartKey(r);
+         if (c->ps_suppkey) c->ps_suppkey[i] = partSuppSuppKey(s, r);
+         if (c->ps_supplycost) storeDec(c->ps_supplycost, i, partSuppSupplyCost(s, r));
+      }
+   });
+}
+
 } // extern "C"

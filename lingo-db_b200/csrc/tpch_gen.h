@@ -190,4 +190,60 @@ LDB_HD char segmentChar(int32_t seg, int32_t pos) {
    return names[seg * 10 + pos];
 }
 
+// ---------------------------------------------------------------- part / partsupp (Q9)
+// p_name = five DISTINCT words of dbgen's 92-word colour list, blank separated (TPC-H spec 4.2.3, P_NAME);
+// `p_name like '%green%'` therefore selects 5/92 = 5.4 percent of the parts.
+constexpr int32_t N_COLORS = 92;
+LDB_HD const char* colorBlob() {
+   return "almondantiqueaquamarineazurebeigebisqueblackblanchedblueblushbrownburlywoodburnishedchartreusechiffonchocolatecoralcornflowercornsilkcreamcyandarkdeepdimdodgerdrabfirebrickfloralforestfrostedgainsboroghostgoldenrodgreengreyhoneydewhotindianivorykhakilacelavenderlawnlemonlightlimelinenmagentamaroonmediummetallicmidnightmintmistymoccasinnavajonavyoliveorangeorchidpalepapayapeachperupinkplumpowderpuffpurpleredroserosyroyalsaddlesalmonsandyseashellsiennaskyslatesmokesnowspringsteeltanthistletomatoturquoisevioletwheatwhiteyellow";
+}
+LDB_HD int32_t colorOffset(int32_t i) {
+   // prefix sums of the word lengths (93 entries)
+   const uint16_t offs[93] = {0, 6, 13, 23, 28, 33, 39, 44, 52, 56, 61, 66, 75, 84, 94, 101, 110, 115, 125, 133, 138, 142, 146, 150, 153, 159, 163, 172, 178, 184, 191, 200, 205, 214, 219, 223, 231, 234, 240, 245, 250, 254, 262, 266, 271, 276, 280, 285, 292, 298, 304, 312, 320, 324, 329, 337, 343, 347, 352, 358, 364, 368, 374, 379, 383, 387, 391, 397, 401, 407, 410, 414, 418, 423, 429, 435, 440, 448, 454, 457, 462, 467, 471, 477, 482, 485, 492, 498, 507, 513, 518, 523, 529};
+   return offs[i];
+}
+LDB_HD void partNameWords(const Scale& s, int64_t partIdx, int32_t w[5]) {
+   uint64_t r = rnd(s.seed, T_PART, C_P_NAME, (uint64_t) partIdx);
+   // draw without replacement: x_k uniform over the (92-k) words not yet taken, mapped past the taken ones in ascending order
+   int32_t taken[5];
+   for (int k = 0; k < 5; k++) {
+      int32_t x = (int32_t) (((r & 0xFFF) * (uint64_t) (N_COLORS - k)) >> 12);
+      r >>= 12;
+      for (int j = 0; j < k; j++)
+         if (x >= taken[j]) x++;
+      w[k] = x;
+      int j = k; // keep `taken` sorted
+      while (j > 0 && taken[j - 1] > x) {
+         taken[j] = taken[j - 1];
+         j--;
+      }
+      taken[j] = x;
+   }
+}
+LDB_HD int32_t partNameLen(const Scale& s, int64_t partIdx) {
+   int32_t w[5];
+   partNameWords(s, partIdx, w);
+   int32_t len = 4;
+   for (int k = 0; k < 5; k++) len += colorOffset(w[k] + 1) - colorOffset(w[k]);
+   return len;
+}
+LDB_HD void partNameWrite(const Scale& s, int64_t partIdx, uint8_t* out) {
+   int32_t w[5];
+   partNameWords(s, partIdx, w);
+   const char* blob = colorBlob();
+   for (int k = 0; k < 5; k++) {
+      if (k) *out++ = ' ';
+      for (int32_t c = colorOffset(w[k]); c < colorOffset(w[k] + 1); c++) *out++ = (uint8_t) blob[c];
+   }
+}
+// partsupp row r: part r/4 + 1, its i-th supplier (spec 4.2.3 PS_SUPPKEY; the same formula picks l_suppkey above)
+LDB_HD int32_t partSuppPartKey(int64_t r) { return (int32_t) (r / 4 + 1); }
+LDB_HD int32_t partSuppSuppKey(const Scale& s, int64_t r) {
+   int64_t pk = r / 4 + 1, i = r % 4, S = s.nSupplier;
+   return (int32_t) ((pk + i * (S / 4 + (pk - 1) / S)) % S + 1);
+}
+LDB_HD int64_t partSuppSupplyCost(const Scale& s, int64_t r) { // cents, U[1.00, 1000.00]
+   return uniform(rnd(s.seed, T_PARTSUPP, C_PS_SUPPLYCOST, (uint64_t) r), 100, 100000);
+}
+
 } // namespace ldbgen

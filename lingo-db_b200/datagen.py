@@ -40,6 +40,14 @@ class SupplierCols(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("s_suppkey", "s_nationkey")]
 
 
+class PartCols(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("p_partkey", "p_name_offsets", "p_name_data")]
+
+
+class PartsuppCols(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ps_partkey", "ps_suppkey", "ps_supplycost")]
+
+
 _lib = None
 
 
@@ -55,6 +63,9 @@ def lib():
         _lib.ldbgen_customer_host.restype = C.c_int64
         _lib.ldbgen_customer_host.argtypes = [C.POINTER(GenScale), C.c_int64, C.c_int64, C.POINTER(CustomerCols)]
         _lib.ldbgen_supplier_host.argtypes = [C.POINTER(GenScale), C.c_int64, C.c_int64, C.POINTER(SupplierCols)]
+        _lib.ldbgen_part_host.restype = C.c_int64
+        _lib.ldbgen_part_host.argtypes = [C.POINTER(GenScale), C.c_int64, C.c_int64, C.POINTER(PartCols)]
+        _lib.ldbgen_partsupp_host.argtypes = [C.POINTER(GenScale), C.c_int64, C.c_int64, C.POINTER(PartsuppCols)]
     return _lib
 
 
@@ -99,6 +110,8 @@ ORDERS_SCHEMA = [ColumnSpec("o_orderkey", "int32"), ColumnSpec("o_custkey", "int
                  ColumnSpec("o_orderdate", "date32"), ColumnSpec("o_shippriority", "int32")]
 CUSTOMER_SCHEMA = [ColumnSpec("c_custkey", "int32"), ColumnSpec("c_nationkey", "int32"), ColumnSpec("c_mktsegment", "utf8")]
 SUPPLIER_SCHEMA = [ColumnSpec("s_suppkey", "int32"), ColumnSpec("s_nationkey", "int32")]
+PART_SCHEMA = [ColumnSpec("p_partkey", "int32"), ColumnSpec("p_name", "utf8")]
+PARTSUPP_SCHEMA = [ColumnSpec("ps_partkey", "int32"), ColumnSpec("ps_suppkey", "int32"), ColumnSpec("ps_supplycost", "decimal128", 12, 2)]
 NATION_SCHEMA = [ColumnSpec("n_nationkey", "int32"), ColumnSpec("n_name", "utf8"), ColumnSpec("n_regionkey", "int32")]
 REGION_SCHEMA = [ColumnSpec("r_regionkey", "int32"), ColumnSpec("r_name", "utf8")]
 
@@ -186,6 +199,32 @@ def supplier(s: GenScale, chunk_rows: int = 1 << 20) -> TableData:
     return t
 
 
+def part(s: GenScale, chunk_rows: int = 1 << 20) -> TableData:
+    t = TableData("part", PART_SCHEMA)
+    for b, n in _chunks(s.n_part, chunk_rows):
+        pk = np.zeros(n, np.int32)
+        offs = np.zeros(n + 1, np.int32)
+        pc = PartCols(_ptr(pk), _ptr(offs), None)
+        nbytes = lib().ldbgen_part_host(C.byref(s), b, n, C.byref(pc))
+        data = np.zeros(max(1, nbytes), np.uint8)
+        pc = PartCols(None, None, _ptr(data))
+        lib().ldbgen_part_host(C.byref(s), b, n, C.byref(pc))
+        t.chunks.append({"p_partkey": pk, "p_name": (offs, data)})
+        t.chunk_rows.append(n)
+    return t
+
+
+def partsupp(s: GenScale, chunk_rows: int = 1 << 20) -> TableData:
+    t = TableData("partsupp", PARTSUPP_SCHEMA)
+    for b, n in _chunks(4 * s.n_part, chunk_rows):
+        arrs = {c.name: _alloc(c, n) for c in PARTSUPP_SCHEMA}
+        pc = PartsuppCols(**{k: _ptr(v) for k, v in arrs.items()})
+        lib().ldbgen_partsupp_host(C.byref(s), b, n, C.byref(pc))
+        t.chunks.append(arrs)
+        t.chunk_rows.append(n)
+    return t
+
+
 def nation() -> TableData:
     t = TableData("nation", NATION_SCHEMA)
     t.chunks.append({"n_nationkey": np.arange(25, dtype=np.int32), "n_name": utf8_column([n for n, _ in NATIONS]),
@@ -201,10 +240,14 @@ def region() -> TableData:
     return t
 
 
-def tpch(sf: float, seed: int = 42, chunk_rows: int = 1 << 20, lineitem_columns=None) -> Dict[str, TableData]:
+def tpch(sf: float, seed: int = 42, chunk_rows: int = 1 << 20, lineitem_columns=None, with_parts: bool = False) -> Dict[str, TableData]:
     s = scale(sf, seed)
-    return {"lineitem": lineitem(s, lineitem_columns, chunk_rows), "orders": orders(s, chunk_rows),
-            "customer": customer(s, chunk_rows), "supplier": supplier(s, chunk_rows), "nation": nation(), "region": region()}
+    t = {"lineitem": lineitem(s, lineitem_columns, chunk_rows), "orders": orders(s, chunk_rows),
+         "customer": customer(s, chunk_rows), "supplier": supplier(s, chunk_rows), "nation": nation(), "region": region()}
+    if with_parts:  # Q9
+        t["part"] = part(s, chunk_rows)
+        t["partsupp"] = partsupp(s, chunk_rows)
+    return t
 
 
 def dec128_to_int(a: np.ndarray) -> np.ndarray:

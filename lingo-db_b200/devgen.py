@@ -91,6 +91,45 @@ def supplier(ctx: Context, s: datagen.GenScale) -> Table:
     return tab
 
 
+def part(ctx: Context, s: datagen.GenScale, batch_rows: int = 16 << 20) -> Table:
+    """utf8 offsets are int32 per batch: 60 M names at SF300 are > 2 GiB, so the table is made of several batches."""
+    dev = torch.device("cuda", ctx.device)
+    tab = Table(ctx, "part", datagen.PART_SCHEMA)
+    e = Error()
+    b = 0
+    while b < s.n_part:
+        n = min(batch_rows, s.n_part - b)
+        pk = torch.empty(n, dtype=torch.int32, device=dev)
+        lens = torch.empty(n, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        cols = datagen.PartCols(_ptr(pk), None, None)
+        check(ctx.L.ldb_gpu_datagen_part_fixed(ctx.h, C.byref(s), b, n, C.byref(cols), _ptr(lens), C.byref(e)), e)
+        ctx.synchronize()
+        offs = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+        offs[1:] = torch.cumsum(lens, 0, dtype=torch.int64).to(torch.int32)
+        data = torch.empty(int(offs[-1].item()), dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize(dev)
+        check(ctx.L.ldb_gpu_datagen_part_bytes(ctx.h, C.byref(s), b, n, _ptr(offs), _ptr(data), C.byref(e)), e)
+        tab.append_device({"p_partkey": pk, "p_name": (offs, data)}, n)
+        b += n
+    ctx.synchronize()
+    return tab
+
+
+def partsupp(ctx: Context, s: datagen.GenScale) -> Table:
+    dev = torch.device("cuda", ctx.device)
+    n = 4 * s.n_part
+    tens = {c.name: _alloc(c, n, dev) for c in datagen.PARTSUPP_SCHEMA}
+    torch.cuda.synchronize(dev)
+    cols = datagen.PartsuppCols(**{k: _ptr(v) for k, v in tens.items()})
+    e = Error()
+    check(ctx.L.ldb_gpu_datagen_partsupp(ctx.h, C.byref(s), 0, n, C.byref(cols), C.byref(e)), e)
+    tab = Table(ctx, "partsupp", datagen.PARTSUPP_SCHEMA)
+    tab.append_device(tens, n)
+    ctx.synchronize()
+    return tab
+
+
 def small_tables(ctx: Context) -> Dict[str, Table]:
     return {"nation": ctx.table_from_host(datagen.nation()), "region": ctx.table_from_host(datagen.region())}
 

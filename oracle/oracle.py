@@ -32,6 +32,10 @@ class Q5Row(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("revenue", C.c_int64 * 2)]
 
 
+class Q9Row(C.Structure):
+    _fields_ = [("nation", C.c_char * 32), ("year", C.c_int64), ("sum_profit", C.c_int64 * 2)]
+
+
 def i128(pair) -> int:
     """{lo, hi} int64 pair → python int (two's complement 128-bit)."""
     return (int(pair[1]) << 64) | (int(pair[0]) & 0xFFFFFFFFFFFFFFFF)
@@ -90,6 +94,10 @@ class Oracle:
         L.oracle_q1.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(Q1Row), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.oracle_q3.argtypes = [C.c_void_p] * 3 + [C.c_char_p] * 2 + [C.POINTER(Q3Row), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.oracle_q5.argtypes = [C.c_void_p] * 6 + [C.c_char_p] * 3 + [C.POINTER(Q5Row), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.oracle_q9.argtypes = [C.c_void_p] * 6 + [C.c_char_p, C.POINTER(Q9Row), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.oracle_extract_year.restype = C.c_int64
+        L.oracle_extract_year.argtypes = [C.c_int64]
+        L.oracle_const_like_contains.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p]
         self.path = path
         self.kind = L.oracle_runtime_kind().decode()
         L.oracle_set_workers(int(workers))
@@ -157,3 +165,8 @@ class Oracle:
         self._check(self.lib.oracle_q5(customer, orders, lineitem, supplier, nation, region, region_name.encode(), date_ge.encode(),
                                        date_lt.encode(), rows, 32, C.byref(n), C.byref(sec)))
         return [{"n_name": r.name.decode(), "revenue": i128(r.revenue)} for r in rows[: n.value]], sec.value
+
+    def q9(self, part, supplier, lineitem, partsupp, orders, nation, needle="green"):
+        rows, n, sec = (Q9Row * 256)(), C.c_int(), C.c_double()
+        self._check(self.lib.oracle_q9(part, supplier, lineitem, partsupp, orders, nation, needle.encode(), rows, 256, C.byref(n), C.byref(sec)))
+        return [{"nation": r.nation.decode(), "o_year": r.year, "sum_profit": i128(r.sum_profit)} for r in rows[: n.value]], sec.value

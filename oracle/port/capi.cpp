@@ -42,6 +42,11 @@ struct OracleQ5Row {
    char name[32];
    int64_t revenue[2];
 };
+struct OracleQ9Row {
+   char nation[32];
+   int64_t year;
+   int64_t sum_profit[2];
+};
 
 const char* oracle_last_error() { return lastError.c_str(); }
 const char* oracle_runtime_kind() { return rt::runtimeKind; } // "port" | "reference"
@@ -145,5 +150,19 @@ int oracle_q5(void* customer, void* orders, void* lineitem, void* supplier, void
       }
    });
 }
+int oracle_q9(void* part, void* supplier, void* lineitem, void* partsupp, void* orders, void* nation, const char* needle, OracleQ9Row* out, int maxRows, int* nRows, double* seconds) {
+   return guarded([&] {
+      auto rows = runQ9(*(HostTable*) part, *(HostTable*) supplier, *(HostTable*) lineitem, *(HostTable*) partsupp, *(HostTable*) orders, *(HostTable*) nation, Q9Params{needle}, seconds);
+      *nRows = (int) rows.size();
+      for (int i = 0; i < (int) rows.size() && i < maxRows; i++) {
+         memset(out[i].nation, 0, sizeof(out[i].nation));
+         strncpy(out[i].nation, rows[i].nation.c_str(), sizeof(out[i].nation) - 1);
+         out[i].year = rows[i].year;
+         split(rows[i].sumProfit, &out[i].sum_profit[0], &out[i].sum_profit[1]);
+      }
+   });
+}
+int64_t oracle_extract_year(int64_t ns) { return rt::extractYear(ns); }
+int oracle_const_like_contains(const char* str, uint32_t len, const char* needle) { return rt::constLikeContains(VarLen32((const uint8_t*) str, len), needle) ? 1 : 0; }
 
 } // extern "C"

@@ -518,4 +518,187 @@ std::vector<Q5Row> runQ5(const HostTable& customer, const HostTable& orders, con
    return rows;
 }
 
+// =====================================================================================  Q9
+// (resources/sql/tpch/9.sql) part(p_name like '%green%') ⋈ partsupp ⋈ lineitem ⋈ supplier ⋈ nation ⋈ orders,
+// group by n_name, extract(year from o_orderdate); amount = l_extendedprice*(1-l_discount) - ps_supplycost*l_quantity.
+// Join order: any order yields the same result (the optimizer cannot be run here).  The LIKE is a map + selection
+// above the part scan (not a pushed-down Restrictions filter: TableStorage.h:14-24 has no LIKE).
+namespace {
+struct PartSuppTuple {
+   void* next;
+   uint64_t hash;
+   int32_t partkey, suppkey;
+   int64_t supplycost; // decimal(12,2) truncated to i64 (precision < 19)
+};
+struct OrderDateTuple {
+   void* next;
+   uint64_t hash;
+   int32_t orderkey;
+   int64_t orderdateNs;
+};
+struct Q9Entry {
+   void* next;
+   uint64_t hash;
+   VarLen32 nation; // key
+   int64_t year;    // key
+   i128 sumProfit;  // value
+};
+static_assert(sizeof(Q9Entry) == 64);
+} // namespace
+std::vector<Q9Row> runQ9(const HostTable& part, const HostTable& supplier, const HostTable& lineitem, const HostTable& partsupp, const HostTable& orders, const HostTable& nation, const Q9Params& p, double* seconds) {
+   rt::QueryContextScope scope;
+   double t0 = now();
+   // nation
+   auto* natTl = threadLocalBuffers<NationTuple>();
+   scanTable(nation, {"n_nationkey", "n_name"}, {}, [&](rt::BatchView* b) {
+      auto* buf = (rt::GrowingBuffer*) natTl->getLocal();
+      ColReader nk(b, 0), nn(b, 1);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         auto* t = (NationTuple*) buf->insert();
+         t->next = nullptr;
+         t->nationkey = nk.i32(idx);
+         t->name = nn.str(idx);
+         t->hash = hashI32(t->nationkey);
+      }
+   });
+   auto* natView = rt::HashIndexedView::build(rt::GrowingBuffer::merge(natTl));
+   // supplier ⋈ nation → {s_suppkey, n_name}
+   auto* suppTl = threadLocalBuffers<SuppTuple>();
+   scanTable(supplier, {"s_suppkey", "s_nationkey"}, {}, [&](rt::BatchView* b) {
+      auto* buf = (rt::GrowingBuffer*) suppTl->getLocal();
+      ColReader sk(b, 0), sn(b, 1);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         int32_t nationkey = sn.i32(idx);
+         for (auto* e = hivLookup(natView, hashI32(nationkey)); e; e = e->next) {
+            auto* n = (NationTuple*) e;
+            if (n->nationkey != nationkey) continue;
+            auto* t = (SuppTuple*) buf->insert();
+            t->next = nullptr;
+            t->suppkey = sk.i32(idx);
+            t->nationkey = nationkey;
+            t->name = n->name;
+            t->hash = hashI32(t->suppkey);
+         }
+      }
+   });
+   auto* suppView = rt::HashIndexedView::build(rt::GrowingBuffer::merge(suppTl));
+   // part(p_name like '%needle%')
+   auto* partTl = threadLocalBuffers<KeyTuple>();
+   scanTable(part, {"p_partkey", "p_name"}, {}, [&](rt::BatchView* b) {
+      auto* buf = (rt::GrowingBuffer*) partTl->getLocal();
+      ColReader pk(b, 0), pn(b, 1);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         if (!rt::constLikeContains(pn.str(idx), p.needle)) continue;
+         auto* t = (KeyTuple*) buf->insert();
+         t->next = nullptr;
+         t->key = pk.i32(idx);
+         t->hash = hashI32(t->key);
+      }
+   });
+   auto* partView = rt::HashIndexedView::build(rt::GrowingBuffer::merge(partTl));
+   // partsupp ⋈ part → {ps_partkey, ps_suppkey, ps_supplycost}, hashed on the composite key
+   auto* psTl = threadLocalBuffers<PartSuppTuple>();
+   scanTable(partsupp, {"ps_partkey", "ps_suppkey", "ps_supplycost"}, {}, [&](rt::BatchView* b) {
+      auto* buf = (rt::GrowingBuffer*) psTl->getLocal();
+      ColReader pk(b, 0), sk(b, 1), sc(b, 2);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         int32_t partkey = pk.i32(idx);
+         for (auto* e = hivLookup(partView, hashI32(partkey)); e; e = e->next) {
+            if (((KeyTuple*) e)->key != partkey) continue;
+            auto* t = (PartSuppTuple*) buf->insert();
+            t->next = nullptr;
+            t->partkey = partkey;
+            t->suppkey = sk.i32(idx);
+            t->supplycost = sc.dec64(idx);
+            t->hash = hashI32Pair(t->partkey, t->suppkey);
+         }
+      }
+   });
+   auto* psView = rt::HashIndexedView::build(rt::GrowingBuffer::merge(psTl));
+   // orders → {o_orderkey, o_orderdate}
+   auto* ordTl = threadLocalBuffers<OrderDateTuple>();
+   scanTable(orders, {"o_orderkey", "o_orderdate"}, {}, [&](rt::BatchView* b) {
+      auto* buf = (rt::GrowingBuffer*) ordTl->getLocal();
+      ColReader ok(b, 0), od(b, 1);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         auto* t = (OrderDateTuple*) buf->insert();
+         t->next = nullptr;
+         t->orderkey = ok.i32(idx);
+         t->orderdateNs = od.dateNs(idx);
+         t->hash = hashI32(t->orderkey);
+      }
+   });
+   auto* ordView = rt::HashIndexedView::build(rt::GrowingBuffer::merge(ordTl));
+   // lineitem ⋈ partsupp ⋈ supplier ⋈ orders → group by (n_name, o_year)
+   using Frag = rt::PreAggregationHashtableFragment;
+   auto* aggTl = rt::ThreadLocal::create([](uint8_t*) -> uint8_t* { return (uint8_t*) Frag::create(sizeof(Q9Entry), false); }, nullptr);
+   scanTable(lineitem, {"l_orderkey", "l_partkey", "l_suppkey", "l_quantity", "l_extendedprice", "l_discount"}, {}, [&](rt::BatchView* b) {
+      auto* frag = (Frag*) aggTl->getLocal();
+      ColReader ok(b, 0), pk(b, 1), sk(b, 2), qty(b, 3), ext(b, 4), disc(b, 5);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         int32_t partkey = pk.i32(idx), suppkey = sk.i32(idx);
+         uint64_t ph = hashI32Pair(partkey, suppkey);
+         for (auto* pe = hivLookup(psView, ph); pe; pe = pe->next) {
+            auto* ps = (PartSuppTuple*) pe;
+            if (ps->hash != ph || ps->partkey != partkey || ps->suppkey != suppkey) continue;
+            for (auto* se = hivLookup(suppView, hashI32(suppkey)); se; se = se->next) {
+               auto* su = (SuppTuple*) se;
+               if (su->suppkey != suppkey) continue;
+               int32_t orderkey = ok.i32(idx);
+               for (auto* oe = hivLookup(ordView, hashI32(orderkey)); oe; oe = oe->next) {
+                  auto* o = (OrderDateTuple*) oe;
+                  if (o->orderkey != orderkey) continue;
+                  int64_t year = rt::extractYear(o->orderdateNs);
+                  // dec(12,2)*dec(21,2) → dec(33,4); dec(12,2)*dec(12,2) → dec(24,4); difference at scale 4 (DBOps.cpp:98-107,221-262)
+                  i128 amount = wrapSub(wrapMul((i128) ext.dec64(idx), wrapSub((i128) 100, (i128) disc.dec64(idx))), wrapMul((i128) ps->supplycost, (i128) qty.dec64(idx)));
+                  HashBuilder hb;
+                  hb.addPiece(hashVarLen(su->name));
+                  hb.addInt(year);
+                  uint64_t gh = hb.total;
+                  auto* cached = (Q9Entry*) frag->ht[(gh >> 6) & 1023];
+                  Q9Entry* en;
+                  if (cached && cached->hash == gh && cached->year == year && cached->nation.view() == su->name.view()) {
+                     en = cached;
+                  } else {
+                     en = (Q9Entry*) frag->insert(gh);
+                     en->nation = su->name;
+                     en->year = year;
+                     en->sumProfit = 0;
+                  }
+                  en->sumProfit = wrapAdd(en->sumProfit, amount);
+               }
+            }
+         }
+      }
+   });
+   constexpr size_t contentOff = offsetof(Q9Entry, nation);
+   auto* merged = rt::PreAggregationHashtable::merge(
+      aggTl,
+      [](uint8_t* a, uint8_t* b) {
+         auto *x = (Q9Entry*) (a - contentOff), *y = (Q9Entry*) (b - contentOff);
+         return x->year == y->year && x->nation.view() == y->nation.view();
+      },
+      [](uint8_t* a, uint8_t* b) {
+         auto* x = (Q9Entry*) (a - contentOff);
+         x->sumProfit = wrapAdd(x->sumProfit, ((Q9Entry*) (b - contentOff))->sumProfit);
+      });
+   std::vector<Q9Row> rows;
+   rt::BufferIterator::iterate(
+      merged->createIterator(), false, [](rt::Buffer buf, void* ctx) {
+         auto& rows = *(std::vector<Q9Row>*) ctx;
+         auto** entries = (Q9Entry**) buf.ptr;
+         for (size_t i = 0; i < buf.numElements / sizeof(Q9Entry*); i++) rows.push_back(Q9Row{std::string(entries[i]->nation.view()), entries[i]->year, entries[i]->sumProfit});
+      },
+      &rows);
+   std::sort(rows.begin(), rows.end(), [](const Q9Row& a, const Q9Row& b) { return a.nation != b.nation ? a.nation < b.nation : a.year > b.year; }); // order by nation, o_year desc
+   *seconds = now() - t0;
+   return rows;
+}
+
 } // namespace oracle

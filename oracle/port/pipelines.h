@@ -51,4 +51,14 @@ struct Q5Row {
 };
 std::vector<Q5Row> runQ5(const HostTable& customer, const HostTable& orders, const HostTable& lineitem, const HostTable& supplier, const HostTable& nation, const HostTable& region, const Q5Params& p, double* seconds);
 
+struct Q9Params {
+   std::string needle; // p_name like '%<needle>%'
+};
+struct Q9Row {
+   std::string nation;
+   int64_t year;
+   i128 sumProfit; // decimal(38,4) raw
+};
+std::vector<Q9Row> runQ9(const HostTable& part, const HostTable& supplier, const HostTable& lineitem, const HostTable& partsupp, const HostTable& orders, const HostTable& nation, const Q9Params& p, double* seconds);
+
 } // namespace oracle

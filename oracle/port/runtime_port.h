@@ -619,6 +619,8 @@ struct WorkerContextBinder { // the port keeps one process-wide context; nothing
    void bind() {}
    void unbind() {}
 };
+inline int64_t extractYear(int64_t ns) { return extractYearPort(ns); }
+inline bool constLikeContains(const oracle::VarLen32& str, std::string_view needle) { return containsPort(str.view(), needle); }
 constexpr const char* runtimeKind = "port";
 
 } // namespace oracle::port

@@ -19,7 +19,9 @@
 #include "lingodb/runtime/GrowingBuffer.h"
 #include "lingodb/runtime/LazyJoinHashtable.h"
 #include "lingodb/runtime/PreAggregationHashtable.h"
+#include "lingodb/runtime/DateRuntime.h"
 #include "lingodb/runtime/SimpleState.h"
+#include "lingodb/runtime/StringRuntime.h"
 #include "lingodb/runtime/ThreadLocal.h"
 #include "lingodb/runtime/helpers.h"
 #include "lingodb/runtime/storage/Restrictions.h"
@@ -98,6 +100,12 @@ struct WorkerContextBinder {
       if (sched::currentWorkerId() != 0) lr::setCurrentExecutionContext(nullptr);
    }
 };
+// scalar runtime of Q9: the reference's own functions (DateRuntime.cpp:99-101, StringRuntime.cpp:337-345)
+inline int64_t extractYear(int64_t ns) { return lr::DateRuntime::extractYear(ns); }
+inline bool constLikeContains(const oracle::VarLen32& str, std::string_view needle) {
+   lr::VarLen32 s((const uint8_t*) str.data(), str.len), n((const uint8_t*) needle.data(), (uint32_t) needle.size());
+   return lr::StringRuntime::findMatch(s, n, 0, str.len) != 0x8000000000000000ull;
+}
 constexpr const char* runtimeKind = "reference";
 
 } // namespace oracle::refrt

@@ -214,4 +214,29 @@ inline i128 parseDecimal(const std::string& s, int targetScale) {
    return neg ? -v : v;
 }
 
+// ---- scalar runtime used by Q9 (restated; the _ref build calls the reference's own functions instead, runtime_ref.h)
+// DateRuntime::extractYear (src/runtime/DateRuntime.cpp:99-101): year of floor<days>(ns) through
+// arrow_vendored::date::year_month_day — the published civil-from-days algorithm (H. Hinnant, "chrono-Compatible
+// Low-Level Date Algorithms"), restated.
+inline int64_t yearOfDays(int64_t days) {
+   int64_t z = days + 719468;
+   int64_t era = (z >= 0 ? z : z - 146096) / 146097;
+   int64_t doe = z - era * 146097;
+   int64_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+   int64_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+   int64_t mp = (5 * doy + 2) / 153;
+   return yoe + era * 400 + (mp >= 10 ? 1 : 0); // months Jan/Feb belong to the next civil year
+}
+inline int64_t extractYearPort(int64_t ns) {
+   constexpr int64_t dayNs = 86400000000000ll;
+   int64_t days = ns / dayNs - (ns % dayNs < 0 ? 1 : 0); // floor
+   return yearOfDays(days);
+}
+// `x like '%needle%'` with a constant pattern: ConstLike lowering (RuntimeFunctions.cpp:87-170, matchPart :60-86)
+// reduces to one StringRuntime::findMatch(str, needle, 0, len) (StringRuntime.cpp:337-345) != invalidPos.
+inline bool containsPort(std::string_view str, std::string_view needle) {
+   if (needle.size() > str.size()) return false;
+   return str.find(needle, 0) != std::string_view::npos;
+}
+
 } // namespace oracle
