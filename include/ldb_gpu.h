@@ -141,6 +141,9 @@ int ldb_gpu_groupby_merge_exported(LdbState* s, const void* dev_src, int32_t n_t
 /* expected_rows sizes the directory like HashIndexedView::build (nextPow2 of a multiple of n);
  * n_side = int32 payload lanes stored beside the slot; n_aggs = int128 aggregate lanes (group-join) */
 int ldb_gpu_join_table_create(LdbContext* ctx, int64_t expected_rows, int32_t unique_keys, int32_t n_side, int32_t n_aggs, LdbState** out, LdbError* err);
+/* composite (int32, int32) key → int64 payload (a decimal(p<19) value or an int32), hashed like db.hash over the key
+ * tuple (LowerToStd.cpp:1139-1150); Q9's partsupp side: (ps_partkey, ps_suppkey) → ps_supplycost */
+int ldb_gpu_join_table_create_pair(LdbContext* ctx, int64_t expected_rows, int32_t unique_keys, LdbState** out, LdbError* err);
 int ldb_gpu_join_table_count(LdbState* s, int64_t* n_entries, LdbError* err);
 typedef struct LdbTopKRow {
    int32_t key, side[LDB_MAX_SIDE];
@@ -159,7 +162,11 @@ int ldb_gpu_join_table_topk(LdbState* s, int32_t k, LdbTopKRow* rows, int32_t* n
  * (DataSourceIteration.cpp:90-96) plus the inlined per-tuple code of SubOpToControlFlow
  * (scan :1123-1203, probe :2558-2586 + :2254-2313, group-by :3065-3157, reduce :3719-3769).
  * A pipeline = table scan → pushed-down filters → optional hash-table probes → one sink. */
-enum LdbFilterOp { LDB_EQ = 0, LDB_NEQ = 1, LDB_LT = 2, LDB_LTE = 3, LDB_GT = 4, LDB_GTE = 5, LDB_NOTNULL = 6, LDB_IN = 7 };
+enum LdbFilterOp { LDB_EQ = 0, LDB_NEQ = 1, LDB_LT = 2, LDB_LTE = 3, LDB_GT = 4, LDB_GTE = 5, LDB_NOTNULL = 6, LDB_IN = 7,
+                   /* not a TableStorage.h FilterOp: `col like '%str_value%'` on a utf8 column, which the reference evaluates in the
+                    * JIT'd selection above the scan (ConstLike → StringRuntime::findMatch, RuntimeFunctions.cpp:60-170,
+                    * StringRuntime.cpp:337-345); the GPU scan takes it as one more predicate */
+                   LDB_CONTAINS = 8 };
 /* FilterDescription (include/lingodb/runtime/storage/TableStorage.h:14-31): column-vs-constant;
  * the constant is a string (dates "YYYY-MM-DD", decimals "0.05", char/varchar text) or an integer */
 #define LDB_MAX_IN_VALUES 8
@@ -181,7 +188,8 @@ enum LdbExprKind {
    LDB_EXPR_MUL = 1,               /* a * b                   decimal(24,4)  i128 */
    LDB_EXPR_MUL_1MINUS = 2,        /* a * (1 - b)             decimal(33,4)  i128 */
    LDB_EXPR_MUL_1MINUS_1PLUS = 3,  /* a * (1 - b) * (1 + c)   decimal(38,6)  i128 */
-   LDB_EXPR_ONE = 4                /* count(*) */
+   LDB_EXPR_ONE = 4,               /* count(*) */
+   LDB_EXPR_MUL_1MINUS_MINUS_PAYMUL = 5 /* a * (1 - b) - $payload0 * c   decimal(34,4) i128; K9 only ($payload0 = probe 0's int64 payload) */
 };
 typedef struct LdbAggDesc {
    int32_t expr;            /* LdbExprKind; every aggregate is SUM (count = SUM of ONE); i64 sums wrap at 64 bits */
@@ -203,8 +211,14 @@ enum LdbPipelineKind {
    /* K8  scan → filters → [probe | Bloom-only semi-join] → append selected columns to dense device buffers
     *     (subop.materialize into a rt::GrowingBuffer, GrowingBuffer.cpp:44, as compacted columns): the
     *     tuple stream that K6 partitions for the all-to-all repartition step */
-   LDB_PIPE_SCAN_MATERIALIZE = 6
+   LDB_PIPE_SCAN_MATERIALIZE = 6,
+   /* K9  scan → filters → probe 0 (composite key, int64 payload) → probe 1 → probe 2 → group by (payload 1, payload 2),
+    *     SUM(aggs[0]) with aggs[0].expr = LDB_EXPR_MUL_1MINUS_MINUS_PAYMUL → GroupBy with 2 keys            (Q9) */
+   LDB_PIPE_SCAN_STAR_PROBE_GROUPBY = 7
 };
+/* inline payload of a K3 build: the column's value, or extract(year from <date32 column>) (DateRuntime::extractYear) */
+enum LdbPayloadExpr { LDB_PAYLOAD_COLUMN = 0, LDB_PAYLOAD_YEAR = 1 };
+#define LDB_MAX_PROBES 3
 #define LDB_MAX_OUT_COLS 4
 typedef struct LdbPipelineDesc {
    int32_t kind; /* LdbPipelineKind */
@@ -217,14 +231,18 @@ typedef struct LdbPipelineDesc {
    /* aggregates (K1, K2: n_aggs; K4, K5: aggs[0]) */
    int32_t n_aggs;
    LdbAggDesc aggs[LDB_MAX_AGGS];
-   /* probes: probe_key_columns[i] is looked up in probe_states[i] (K3: 0 or 1, K5: 1, K4: 2) */
+   /* probes: probe_key_columns[i] (and probe_key2_columns[i] for a composite-key table) is looked up in
+    * probe_states[i] (K3: 0 or 1, K5: 1, K4: 2, K9: 3) */
    int32_t n_probes;
-   LdbState* probe_states[2];
-   const char* probe_key_columns[2];
+   LdbState* probe_states[LDB_MAX_PROBES];
+   const char* probe_key_columns[LDB_MAX_PROBES];
+   const char* probe_key2_columns[LDB_MAX_PROBES];
    /* K3 build: inserted key, inline payload (a column, or the probe's payload when NULL and a
     * probe is present, or 0), side payload columns */
    const char* build_key_column;
+   const char* build_key2_column;  /* second key column when the sink is a composite-key table, else NULL */
    const char* build_payload_column;
+   int32_t build_payload_expr;     /* LdbPayloadExpr */
    int32_t n_side;
    const char* side_columns[LDB_MAX_SIDE];
    LdbState* sink; /* SimpleState | GroupBy | JoinTable (K5: the probed map itself) */

@@ -1,5 +1,5 @@
 /* ldb_tpch.h — query drivers: the sequence of pipeline calls the reference's JIT'd `main()` performs
- * for TPC-H Q1/Q3/Q5/Q6 (DefaultCPULLVMBackend::execute → mainFunc(), src/execution/LLVMBackends.cpp:795-867),
+ * for TPC-H Q1/Q3/Q5/Q6/Q9 (DefaultCPULLVMBackend::execute → mainFunc(), src/execution/LLVMBackends.cpp:795-867),
  * issued against the GPU C-ABI (ldb_gpu.h).  This is what a `GPUPatternList` lowering
  * (SubOpToControlFlow.cpp:4254-4394) would emit; it lives in C++ like src/execution.
  * Results are exact integers: decimal raw values with the scale the reference's typing gives them.
@@ -18,6 +18,8 @@ typedef struct LdbTpchTables {
    LdbTable* supplier;
    LdbTable* nation;
    LdbTable* region;
+   LdbTable* part;     /* Q9 only */
+   LdbTable* partsupp; /* Q9 only */
 } LdbTpchTables;
 
 /* Q6: revenue = sum(l_extendedprice * l_discount), decimal(24,4) */
@@ -51,6 +53,13 @@ typedef struct LdbQ5Row {
    LdbI128 revenue;          /* decimal(33,4) */
 } LdbQ5Row;
 int ldb_tpch_q5(LdbContext* ctx, const LdbTpchTables* t, const char* region_name, const char* date_ge, const char* date_lt, LdbQ5Row* rows /* 25 */, int32_t* n_rows, LdbError* err);
+
+/* Q9 (resources/sql/tpch/9.sql): group by (nation, extract(year from o_orderdate)); ordered by n_name, o_year desc on the host */
+typedef struct LdbQ9Row {
+   int32_t n_nationkey, o_year; /* n_name is resolved from the nation table at materialisation (host) */
+   LdbI128 sum_profit;          /* decimal(34,4) raw: l_extendedprice * (1 - l_discount) - ps_supplycost * l_quantity, summed */
+} LdbQ9Row;
+int ldb_tpch_q9(LdbContext* ctx, const LdbTpchTables* t, const char* name_contains, LdbQ9Row* rows /* max_rows */, int32_t max_rows, int32_t* n_rows, LdbError* err);
 
 #ifdef __cplusplus
 }

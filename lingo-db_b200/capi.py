@@ -12,9 +12,11 @@ from .datagen import CustomerCols, GenScale, LineitemCols, OrdersCols, PartCols,
 LDB_OK, LDB_ERR_CUDA, LDB_ERR_UNSUPPORTED, LDB_ERR_INVALID, LDB_ERR_CAPACITY, LDB_ERR_NO_DEVICE = range(6)
 PHYS = {"int32": 0, "int64": 1, "date32": 2, "decimal128": 3, "fsb4": 4, "utf8": 5}
 MEM_HOST, MEM_DEVICE = 0, 1
-OPS = {"=": 0, "!=": 1, "<": 2, "<=": 3, ">": 4, ">=": 5, "notnull": 6, "in": 7}
-EXPR = {"col": 0, "mul": 1, "mul_1minus": 2, "mul_1minus_1plus": 3, "one": 4}
-PIPE = {"scan_reduce": 1, "scan_groupby": 2, "scan_build": 3, "scan_probe_agg": 4, "scan_probe2_groupby": 5, "scan_materialize": 6}
+OPS = {"=": 0, "!=": 1, "<": 2, "<=": 3, ">": 4, ">=": 5, "notnull": 6, "in": 7, "contains": 8}
+EXPR = {"col": 0, "mul": 1, "mul_1minus": 2, "mul_1minus_1plus": 3, "one": 4, "mul_1minus_minus_paymul": 5}
+PIPE = {"scan_reduce": 1, "scan_groupby": 2, "scan_build": 3, "scan_probe_agg": 4, "scan_probe2_groupby": 5, "scan_materialize": 6,
+        "scan_star_probe_groupby": 7}
+PAYLOAD_EXPR = {"column": 0, "year": 1}
 MAX_AGGS, MAX_KEYS, MAX_SIDE = 8, 2, 2
 
 
@@ -72,15 +74,17 @@ class AggDesc(C.Structure):
 class PipelineDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("source", C.c_void_p), ("n_filters", C.c_int32), ("filters", C.POINTER(FilterDesc)),
                 ("n_keys", C.c_int32), ("key_columns", C.c_char_p * MAX_KEYS), ("n_aggs", C.c_int32), ("aggs", AggDesc * MAX_AGGS),
-                ("n_probes", C.c_int32), ("probe_states", C.c_void_p * 2), ("probe_key_columns", C.c_char_p * 2),
-                ("build_key_column", C.c_char_p), ("build_payload_column", C.c_char_p), ("n_side", C.c_int32),
+                ("n_probes", C.c_int32), ("probe_states", C.c_void_p * 3), ("probe_key_columns", C.c_char_p * 3),
+                ("probe_key2_columns", C.c_char_p * 3),
+                ("build_key_column", C.c_char_p), ("build_key2_column", C.c_char_p), ("build_payload_column", C.c_char_p),
+                ("build_payload_expr", C.c_int32), ("n_side", C.c_int32),
                 ("side_columns", C.c_char_p * MAX_SIDE), ("sink", C.c_void_p),
                 ("n_out_cols", C.c_int32), ("out_columns", C.c_char_p * 4), ("out_buffers", C.c_void_p * 4), ("out_capacity", C.c_int64),
                 ("out_count", C.c_void_p), ("probe_bloom_only", C.c_int32)]
 
 
 class TpchTables(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("lineitem", "orders", "customer", "supplier", "nation", "region")]
+    _fields_ = [(n, C.c_void_p) for n in ("lineitem", "orders", "customer", "supplier", "nation", "region", "part", "partsupp")]
 
 
 class Q1Row(C.Structure):
@@ -95,6 +99,10 @@ class Q3Row(C.Structure):
 
 class Q5Row(C.Structure):
     _fields_ = [("n_nationkey", C.c_int32), ("pad", C.c_int32), ("revenue", I128)]
+
+
+class Q9Row(C.Structure):
+    _fields_ = [("n_nationkey", C.c_int32), ("o_year", C.c_int32), ("sum_profit", I128)]
 
 
 # every symbol include/ldb_gpu.h and include/ldb_tpch.h declare: (restype, argtypes)
@@ -127,6 +135,7 @@ SIGNATURES = {
     "ldb_gpu_groupby_export": (C.c_int, [_P, _P, _E]),
     "ldb_gpu_groupby_merge_exported": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _E]),
     "ldb_gpu_join_table_create": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P), _E]),
+    "ldb_gpu_join_table_create_pair": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(_P), _E]),
     "ldb_gpu_join_table_count": (C.c_int, [_P, C.POINTER(C.c_int64), _E]),
     "ldb_gpu_join_table_bloom": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64), _E]),
     "ldb_gpu_join_table_topk": (C.c_int, [_P, C.c_int32, C.POINTER(TopKRow), C.POINTER(C.c_int32), _E]),
@@ -149,6 +158,7 @@ SIGNATURES = {
     "ldb_tpch_q1_finish": (C.c_int, [_P, C.POINTER(Q1Row), C.c_int32, C.POINTER(C.c_int32), _E]),
     "ldb_tpch_q3": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.c_char_p, C.POINTER(Q3Row), C.POINTER(C.c_int32), _E]),
     "ldb_tpch_q5": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(Q5Row), C.POINTER(C.c_int32), _E]),
+    "ldb_tpch_q9": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.POINTER(Q9Row), C.c_int32, C.POINTER(C.c_int32), _E]),
 }
 
 _lib = None

@@ -21,6 +21,21 @@ __device__ __forceinline__ i128 add128(i128 a, i128 b) { // one carry chain (IAD
    asm("add.cc.u64 %0, %2, %4;\n\taddc.u64 %1, %3, %5;" : "=l"(r.lo), "=l"(r.hi) : "l"(a.lo), "l"(a.hi), "l"(b.lo), "l"(b.hi));
    return r;
 }
+__device__ __forceinline__ i128 sub128(i128 a, i128 b) {
+   i128 r;
+   asm("sub.cc.u64 %0, %2, %4;\n\tsubc.u64 %1, %3, %5;" : "=l"(r.lo), "=l"(r.hi) : "l"(a.lo), "l"(a.hi), "l"(b.lo), "l"(b.hi));
+   return r;
+}
+// DateRuntime::extractYear (src/runtime/DateRuntime.cpp:99-101) on a date32 value: civil-from-days in 32-bit arithmetic
+__device__ __forceinline__ int32_t yearOfDays(int32_t days) {
+   const int32_t z = days + 719468;
+   const int32_t era = (z >= 0 ? z : z - 146096) / 146097;
+   const uint32_t doe = (uint32_t) (z - era * 146097);
+   const uint32_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+   const uint32_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+   const uint32_t mp = (5 * doy + 2) / 153;
+   return (int32_t) yoe + era * 400 + (mp >= 10 ? 1 : 0);
+}
 __device__ __forceinline__ bool fitsI32(int64_t v) { return v == (int64_t) (int32_t) v; }
 // (a * b) * c for operands that fit int32 (c additionally >= 0): three 32x32→64 multiplies instead of the
 // ~25-instruction general 64x64→128 / 128x64 sequence.  Exact; callers take it only when EVERY lane of

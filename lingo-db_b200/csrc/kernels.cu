@@ -197,7 +197,24 @@ __device__ __noinline__ bool inListContains(const FilterCol& f, int64_t v) {
    for (int k = 0; k < f.nIn; k++) any |= v == f.inVals[k];
    return any;
 }
-// IN = the pipeline has at least one IN-list filter (host decides); pipelines without one carry no trace of it
+// `x like '%needle%'` (ConstLike → StringRuntime::findMatch, RuntimeFunctions.cpp:60-170, StringRuntime.cpp:337-345): the
+// reference evaluates it in the JIT'd selection above the scan; here it is one more predicate of the scan itself.
+__device__ __noinline__ bool utf8Contains(const FilterCol& f, int64_t row) {
+   const int32_t* off = (const int32_t*) f.base + row;
+   const int32_t b = __ldg(off), e = __ldg(off + 1), n = f.strLen;
+   if (e - b < n) return false;
+   if (n == 0) return true;
+   const uint8_t* str = f.bytes + b;
+   const uint8_t first = f.str[0];
+   for (int i = 0, last = e - b - n; i <= last; i++) {
+      if (__ldg(str + i) != first) continue;
+      int k = 1;
+      while (k < n && __ldg(str + i + k) == f.str[k]) k++;
+      if (k == n) return true;
+   }
+   return false;
+}
+// IN = the pipeline has at least one rare filter — IN list or LIKE-contains (host decides); pipelines without one carry no trace of it
 template <bool IN, class Tile>
 __device__ __forceinline__ bool evalFilters(const FilterSet& F, const Tile& tile, int lr, int64_t row) {
    bool pass = true;
@@ -210,6 +227,8 @@ __device__ __forceinline__ bool evalFilters(const FilterSet& F, const Tile& tile
             v = tile.i32(f.staged, lr);
          } else if (f.kind == COL_DEC128_LO64) {
             v = tile.lo64(f.staged, lr);
+         } else if (IN && f.kind == COL_UTF8_CONTAINS) {
+            v = utf8Contains(f, row) ? 1 : 0;
          } else { // COL_UTF8_EQ: 1 if the string equals the constant (VarLen32Filter<Eq>, Restrictions.cpp:279-325)
             const int32_t* off = (const int32_t*) f.base + row;
             int32_t b = __ldg(off), e = __ldg(off + 1);
@@ -365,6 +384,88 @@ __device__ __forceinline__ void joinProbe(const JoinTableDev& t, int32_t key, co
          if (t.unique) return;
       }
       s = (s + 1) & t.mask;
+   }
+}
+
+// ---- composite-key table (stride 16): {key0, key1} → int64 payload; hashed like db.hash over the key tuple
+__device__ __forceinline__ uint64_t hashPair(int32_t k0, int32_t k1) { return hashCombine(hashI32(k1), hashI32(k0)); }
+__device__ int64_t pairInsert(const JoinTableDev& t, int32_t k0, int32_t k1, int64_t payload) {
+   const unsigned long long packed = packSlot(k0, k1);
+   if (packed == kEmptySlot) {
+      atomicExch(t.error, 3);
+      return -1;
+   }
+   const uint64_t h = hashPair(k0, k1);
+   uint64_t s = h & t.mask;
+   const uint64_t limit = t.mask < kMaxProbe ? t.mask + 1 : kMaxProbe;
+   for (uint64_t probes = 0; probes < limit; probes++) {
+      unsigned long long old = atomicCAS(slotPtr(t, s), kEmptySlot, packed);
+      if (old == kEmptySlot) {
+         ((long long*) slotPtr(t, s))[1] = payload; // probes run in a later kernel
+         if (t.bloom) atomicOr(&t.bloom[(uint32_t) (h >> 32) & t.bloomMask], bloomBits(h));
+         return (int64_t) s;
+      }
+      if (t.unique && old == packed) {
+         atomicExch(t.error, 2);
+         return -1;
+      }
+      s = (s + 1) & t.mask;
+   }
+   atomicExch(t.error, 1);
+   return -1;
+}
+__device__ __forceinline__ BloomProbe pairBloomPrefetch(const JoinTableDev& t, int32_t k0, int32_t k1, bool wanted) {
+   BloomProbe b;
+   b.h = hashPair(k0, k1);
+   b.bits = t.bloom ? bloomBits(b.h) : 0u;
+   b.word = (t.bloom && wanted) ? __ldg(&t.bloom[(uint32_t) (b.h >> 32) & t.bloomMask]) : (wanted ? ~0u : 0u);
+   if (!wanted) b.bits = 1u;
+   return b;
+}
+template <class Fn>
+__device__ __forceinline__ void pairProbeSlots(const JoinTableDev& t, int32_t k0, int32_t k1, uint64_t h, const Fn& fn) {
+   const unsigned long long packed = packSlot(k0, k1);
+   uint64_t s = h & t.mask;
+   const uint64_t limit = t.mask < kMaxProbe ? t.mask + 1 : kMaxProbe;
+   for (uint64_t probes = 0; probes < limit; probes++) {
+      const ulonglong2 e = __ldg((const ulonglong2*) slotPtr(t, s)); // key pair + payload: one 16-byte load
+      if (e.x == kEmptySlot) return;
+      if (e.x == packed) {
+         fn((int64_t) s, (int64_t) e.y);
+         if (t.unique) return;
+      }
+      s = (s + 1) & t.mask;
+   }
+}
+
+// Probe walks that start from an already loaded first slot (the caller issued the loads of several tables together)
+template <class Fn>
+__device__ __forceinline__ void joinProbeFrom(const JoinTableDev& t, int32_t key, uint64_t h, unsigned long long e, const Fn& fn) {
+   uint64_t s = h & t.mask;
+   const uint64_t limit = t.mask < kMaxProbe ? t.mask + 1 : kMaxProbe;
+   for (uint64_t probes = 0; probes < limit; probes++) {
+      if (e == kEmptySlot) return;
+      if ((int32_t) (uint32_t) e == key) {
+         fn((int32_t) ((uint32_t) (e >> 32) & (t.stride == 32 ? 0x7fffffffu : 0xffffffffu)));
+         if (t.unique) return;
+      }
+      s = (s + 1) & t.mask;
+      e = __ldg(slotPtr(t, s));
+   }
+}
+template <class Fn>
+__device__ __forceinline__ void pairProbeFrom(const JoinTableDev& t, int32_t k0, int32_t k1, uint64_t h, ulonglong2 e, const Fn& fn) {
+   const unsigned long long packed = packSlot(k0, k1);
+   uint64_t s = h & t.mask;
+   const uint64_t limit = t.mask < kMaxProbe ? t.mask + 1 : kMaxProbe;
+   for (uint64_t probes = 0; probes < limit; probes++) {
+      if (e.x == kEmptySlot) return;
+      if (e.x == packed) {
+         fn((int64_t) e.y);
+         if (t.unique) return;
+      }
+      s = (s + 1) & t.mask;
+      e = __ldg((const ulonglong2*) slotPtr(t, s));
    }
 }
 
@@ -618,16 +719,17 @@ static std::string signature(const GroupByParams& p) {
 template <class K>
 static int persistentGrid(K kernel, const StagedCols& sc, int64_t nRows, int smCount, size_t* dynBytes, int threads = kThreads) {
    *dynBytes = sc.useTma ? (size_t) kStages * sc.stageBytes : 0;
-   if (*dynBytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) *dynBytes);
+   // static + dynamic shared memory beyond 48 KB needs the opt-in (K9 carries 12 KB of static group slots), so always ask
+   if (*dynBytes > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) *dynBytes);
    int perSm = 1;
    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, threads, *dynBytes);
    if (perSm < 1) perSm = 1;
    int64_t tiles = (nRows + sc.tileRows - 1) / sc.tileRows;
    return (int) std::min<int64_t>(std::max<int64_t>(tiles, 1), (int64_t) smCount * perSm);
 }
-static bool hasInList(const FilterSet& f) {
+static bool hasInList(const FilterSet& f) { // "rare" filters: IN lists and LIKE-contains
    for (int i = 0; i < f.n; i++)
-      if (f.c[i].nIn > 0) return true;
+      if (f.c[i].nIn > 0 || f.c[i].kind == COL_UTF8_CONTAINS) return true;
    return false;
 }
 template <int DB, bool IN, int NK, int NV, class... As>
@@ -709,7 +811,8 @@ __global__ void __launch_bounds__(kThreads, 4) scanBuildKernel(const __grid_cons
             for (int k = 0; k < p.nSide; k++) lanes[k] = tile.i32(p.sideStage[k], lr);
          }
       };
-      const int32_t ownPayload = p.payloadStage >= 0 ? tile.i32(p.payloadStage, lr) : 0;
+      int32_t ownPayload = p.payloadStage >= 0 ? tile.i32(p.payloadStage, lr) : 0;
+      if (p.payloadKind == PAYLOAD_YEAR_OF_DATE32) ownPayload = yearOfDays(ownPayload); // extract(year from <date32 column>)
       if (p.hasProbe) {
          joinProbe(p.probe, tile.i32(p.probeKeyStage, lr), [&](int64_t, int32_t parentPayload) { insert(p.payloadStage >= 0 ? ownPayload : parentPayload); });
       } else {
@@ -718,8 +821,41 @@ __global__ void __launch_bounds__(kThreads, 4) scanBuildKernel(const __grid_cons
    });
    flushInsertCount(p.sink, inserted);
 }
+// composite-key build: {key, key2} → int64 payload (a decimal(p<19) column's value or an int32 column), optionally
+// restricted to rows whose probe key exists in a parent table (Q9: partsupp ⋈ part(p_name like '%green%'))
+template <int DB>
+__global__ void __launch_bounds__(kThreads, 4) scanBuildPairKernel(const __grid_constant__ BuildParams p) {
+   constexpr bool IN = true;
+   __shared__ __align__(8) TileBarriers barsStorage;
+   TileBarriers* bars = &barsStorage;
+   unsigned long long inserted = 0;
+   forEachRow<kRowsPerThreadProbe, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
+      if (!(valid && evalFilters<IN>(p.src.filters, tile, lr, row))) return;
+      const int32_t k0 = tile.i32(p.keyStage, lr), k1 = tile.i32(p.keyStage2, lr);
+      int64_t payload = 0;
+      if (p.payloadStage >= 0) payload = p.payloadKind == PAYLOAD_DEC_LO64 ? tile.lo64(p.payloadStage, lr) : (int64_t) tile.i32(p.payloadStage, lr);
+      if (p.hasProbe) {
+         joinProbe(p.probe, tile.i32(p.probeKeyStage, lr), [&](int64_t, int32_t) {
+            if (pairInsert(p.sink, k0, k1, payload) >= 0) inserted++;
+         });
+      } else if (pairInsert(p.sink, k0, k1, payload) >= 0) {
+         inserted++;
+      }
+   });
+   flushInsertCount(p.sink, inserted);
+}
 void launchScanBuild(const BuildParams& p, int smCount, cudaStream_t s) {
    size_t dyn;
+   if (p.sink.stride == 16) {
+      if (p.src.cols.decBytes == 8) {
+         int grid = persistentGrid(scanBuildPairKernel<8>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanBuildPairKernel<8><<<grid, kThreads, dyn, s>>>(p);
+      } else {
+         int grid = persistentGrid(scanBuildPairKernel<16>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanBuildPairKernel<16><<<grid, kThreads, dyn, s>>>(p);
+      }
+      return;
+   }
    if (p.src.cols.decBytes == 8) {
       int grid = persistentGrid(scanBuildKernel<8>, p.src.cols, p.src.nRows, smCount, &dyn);
       scanBuildKernel<8><<<grid, kThreads, dyn, s>>>(p);
@@ -999,6 +1135,111 @@ bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStre
       }
    }
    return true;
+}
+
+// =================================================================================== K9 star probe, group
+// scan → probe P on the composite key (Bloom first: Q9 keeps 5 % of lineitem) → probe S → probe O → group by the two
+// int32 payloads → SUM(a * (1 - b) - c * d), c = P's int64 payload.  The reference's per-worker pre-aggregation
+// cache (PreAggregationHashtable.cpp:46-60) becomes a per-CTA shared-memory table flushed once per CTA: ~10^8 matched
+// rows over 175 groups would otherwise serialise on 175 HBM addresses.
+constexpr int kStarGroups = 512; // CTA-local group slots (power of two); further groups go straight to the HBM table
+template <int DB>
+__global__ void __launch_bounds__(kThreads, 4) scanStarProbeGroupByKernel(const __grid_constant__ StarProbeParams p) {
+   constexpr bool IN = true;
+   __shared__ __align__(8) TileBarriers barsStorage;
+   __shared__ unsigned long long sKey[kStarGroups];
+   __shared__ unsigned long long sAcc[kStarGroups][2];
+   TileBarriers* bars = &barsStorage;
+   for (int i = threadIdx.x; i < kStarGroups; i += blockDim.x) {
+      sKey[i] = kEmptySlot;
+      sAcc[i][0] = sAcc[i][1] = 0;
+   }
+   __syncthreads();
+   const int64_t one = 100;
+   auto groupAdd = [&](int32_t g0, int32_t g1, i128 v) {
+      const unsigned long long packed = packSlot(g0, g1);
+      if (packed != kEmptySlot) {
+         uint32_t s = (uint32_t) hashPair(g0, g1) & (kStarGroups - 1);
+         for (int probes = 0; probes < kStarGroups; probes++) {
+            unsigned long long cur = *((volatile unsigned long long*) &sKey[s]);
+            if (cur == kEmptySlot) cur = atomicCAS(&sKey[s], kEmptySlot, packed);
+            if (cur == kEmptySlot || cur == packed) {
+               atomicAdd128(&sAcc[s][0], &sAcc[s][1], v);
+               return;
+            }
+            s = (s + 1) & (kStarGroups - 1);
+         }
+      }
+      int32_t kk[2] = {g0, g1};
+      int slot = groupLookupOrInsert(p.groups, kk);
+      if (slot >= 0) groupAtomicAdd(p.groups, slot, 0, v, false);
+   };
+   forEachTile<kRowsPerThreadProbe, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+      int32_t k0[kRowsPerThreadProbe], k1[kRowsPerThreadProbe];
+      int lrs[kRowsPerThreadProbe];
+      BloomProbe bp[kRowsPerThreadProbe];
+#pragma unroll
+      for (int j = 0; j < kRowsPerThreadProbe; j++) { // phase A: filters + P's Bloom word for every row of the thread
+         const int lr = j * kBlock + threadIdx.x;
+         const bool valid = lr < rows;
+         lrs[j] = valid ? lr : 0;
+         const bool ok = valid && evalFilters<IN>(p.src.filters, tile, lrs[j], rowBase + lrs[j]);
+         k0[j] = tile.i32(p.keyStageP0, lrs[j]);
+         k1[j] = tile.i32(p.keyStageP1, lrs[j]);
+         bp[j] = pairBloomPrefetch(p.tableP, k0[j], k1[j], ok);
+      }
+      // phase B: the three probes of a row are independent of each other, so a survivor puts the first slot of ALL three
+      // directories in flight at once (S and O are foreign-key probes that always hit: their Bloom filters are skipped).
+      // With ~2 surviving lanes per warp the kernel is bound by this dependent-load chain, not by bandwidth: one round
+      // trip per tile instead of six (profiles/r1_q9.md).
+      ulonglong2 eP[kRowsPerThreadProbe];
+      unsigned long long eS[kRowsPerThreadProbe], eO[kRowsPerThreadProbe];
+      int32_t kS[kRowsPerThreadProbe], kO[kRowsPerThreadProbe];
+      uint64_t hS[kRowsPerThreadProbe], hO[kRowsPerThreadProbe];
+#pragma unroll
+      for (int j = 0; j < kRowsPerThreadProbe; j++) {
+         kS[j] = tile.i32(p.keyStageS, lrs[j]);
+         kO[j] = tile.i32(p.keyStageO, lrs[j]);
+         hS[j] = hashI32(kS[j]);
+         hO[j] = hashI32(kO[j]);
+         if (bp[j].mayContain()) {
+            eP[j] = __ldg((const ulonglong2*) slotPtr(p.tableP, bp[j].h & p.tableP.mask));
+            eS[j] = __ldg(slotPtr(p.tableS, hS[j] & p.tableS.mask));
+            eO[j] = __ldg(slotPtr(p.tableO, hO[j] & p.tableO.mask));
+         }
+      }
+#pragma unroll
+      for (int j = 0; j < kRowsPerThreadProbe; j++) {
+         if (!bp[j].mayContain()) continue;
+         pairProbeFrom(p.tableP, k0[j], k1[j], bp[j].h, eP[j], [&](int64_t c) {
+            joinProbeFrom(p.tableS, kS[j], hS[j], eS[j], [&](int32_t g0) {
+               joinProbeFrom(p.tableO, kO[j], hO[j], eO[j], [&](int32_t g1) {
+                  const int64_t a = tile.lo64(p.valueStage[0], lrs[j]), b = tile.lo64(p.valueStage[1], lrs[j]), d = tile.lo64(p.valueStage[2], lrs[j]);
+                  groupAdd(g0, g1, sub128(mul64x64(a, one - b), mul64x64(c, d)));
+               });
+            });
+         });
+      }
+   });
+   __syncthreads();
+   for (int i = threadIdx.x; i < kStarGroups; i += blockDim.x) { // blockDim = consumers + producer warp; all of them flush
+      const unsigned long long key = sKey[i];
+      if (key == kEmptySlot) continue;
+      const i128 v{sAcc[i][0], (int64_t) sAcc[i][1]};
+      int32_t kk[2] = {(int32_t) (uint32_t) key, (int32_t) (uint32_t) (key >> 32)};
+      int slot = groupLookupOrInsert(p.groups, kk);
+      if (slot >= 0) groupAtomicAdd(p.groups, slot, 0, v, false);
+   }
+}
+void launchScanStarProbeGroupBy(const StarProbeParams& p, int smCount, cudaStream_t s) {
+   size_t dyn;
+   if (p.src.cols.decBytes == 8) {
+      int grid = persistentGrid(scanStarProbeGroupByKernel<8>, p.src.cols, p.src.nRows, smCount, &dyn);
+      scanStarProbeGroupByKernel<8><<<grid, kThreads, dyn, s>>>(p);
+   } else {
+      int grid = persistentGrid(scanStarProbeGroupByKernel<16>, p.src.cols, p.src.nRows, smCount, &dyn);
+      scanStarProbeGroupByKernel<16><<<grid, kThreads, dyn, s>>>(p);
+   }
 }
 
 // =================================================================================== top-k over the group-join map

@@ -12,7 +12,7 @@ constexpr int kMaxAggs = 8;
 constexpr int kMaxKeys = 2;
 constexpr int kMaxSide = 2;
 
-enum ColKind : int32_t { COL_I32 = 0, COL_DEC128_LO64 = 1, COL_UTF8_EQ = 2 };
+enum ColKind : int32_t { COL_I32 = 0, COL_DEC128_LO64 = 1, COL_UTF8_EQ = 2, COL_UTF8_CONTAINS = 3 };
 
 // One pushed-down filter column with up to two predicates (e.g. a range); op masks as in cmpMask().
 // utf8 columns evaluate `string == constant` to 1/0 first, then compare that to valA (1).
@@ -46,6 +46,8 @@ struct GroupTableDev {
 // ---- join table (rt::GrowingBuffer + rt::HashIndexedView twin; with agg lanes: the group-join map)
 // Open addressing, slot s at base + s * stride.  Two layouts:
 //   stride  8  {key:32, payload:32}                                              plain joins
+//   stride 16  {key0:32, key1:32, payload:64}                                     composite (int32,int32) key → int64 payload
+//              (Q9's partsupp: (ps_partkey, ps_suppkey) → ps_supplycost); hashed like db.hash over the key pair
 //   stride 32  {key:32, marker:1|payload:31, side0:32, side1:32, aggLo:64, aggHi:64}  group-join map — ONE 32-byte
 //              sector per entry, so an insert (CAS + side lanes) or a probe hit (compare + i128 atomic add + marker)
 //              touches a single DRAM sector instead of up to four separate arrays.
@@ -101,10 +103,13 @@ struct GroupByParams {
    GroupTableDev table;
 };
 
+enum PayloadKind : int32_t { PAYLOAD_I32 = 0, PAYLOAD_YEAR_OF_DATE32 = 1, PAYLOAD_DEC_LO64 = 2 };
 struct BuildParams {
    ScanSource src;
    int32_t keyStage;
+   int32_t keyStage2;    // pair tables: second key column, else -1
    int32_t payloadStage; // -1: none
+   int32_t payloadKind;  // PayloadKind
    int32_t nSide;
    int32_t sideStage[kMaxSide];
    int32_t hasProbe;
@@ -128,6 +133,16 @@ struct Probe2GroupByParams {
    AggSpec agg;
    int32_t valueStage[kMaxValueCols];
    GroupTableDev groups; // keyed by the matched payload
+};
+
+// K9: scan → probe P (composite key → int64 payload c) → probe S (→ group key 0) → probe O (→ group key 1)
+//     → SUM(a * (1 - b) - c * d) grouped by the two payloads (Q9's lineitem pipeline)
+struct StarProbeParams {
+   ScanSource src;
+   int32_t keyStageP0, keyStageP1, keyStageS, keyStageO;
+   JoinTableDev tableP, tableS, tableO;
+   int32_t valueStage[3]; // a, b, d
+   GroupTableDev groups;  // 2 keys, 1 aggregate
 };
 
 constexpr int kMaxOutCols = 4;
@@ -155,6 +170,7 @@ bool launchScanGroupBy(const GroupByParams& p, int smCount, cudaStream_t s, cons
 void launchScanBuild(const BuildParams& p, int smCount, cudaStream_t s);
 bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, const char** why);
 bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStream_t s, const char** why);
+void launchScanStarProbeGroupBy(const StarProbeParams& p, int smCount, cudaStream_t s);
 void launchScanMaterialize(const MaterializeParams& p, int smCount, cudaStream_t s);
 void launchInitWideTable(uint8_t* base, uint64_t capacity, int smCount, cudaStream_t s);
 void launchJoinTopK(const JoinTableDev& t, int k, TopKRowDev* out, int* outBlocks, int smCount, cudaStream_t s);

@@ -596,6 +596,30 @@ int ldb_gpu_join_table_create(LdbContext* ctx, int64_t expected_rows, int32_t un
       *out = s;
    });
 }
+int ldb_gpu_join_table_create_pair(LdbContext* ctx, int64_t expected_rows, int32_t unique_keys, LdbState** out, LdbError* err) {
+   return guarded(err, [&] {
+      if (!ctx || !out) fail(LDB_ERR_INVALID, "null argument");
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      auto* s = new LdbState;
+      s->ctx = ctx;
+      s->kind = LDB_STATE_JOIN_TABLE;
+      ctx->states.push_back(s);
+      uint64_t cap = nextPow2((uint64_t) std::max<int64_t>(expected_rows, 8) * 2);
+      auto& j = s->join;
+      j.mask = cap - 1;
+      j.unique = unique_keys;
+      j.stride = 16;
+      j.base = (uint8_t*) devAlloc(s, cap * 16, 0xff);
+      j.count = (unsigned long long*) devAlloc(s, 8, 0);
+      j.error = (int32_t*) devAlloc(s, 4, 0);
+      if (cap >= 4096) {
+         uint64_t words = cap / 4;
+         j.bloom = (uint32_t*) devAlloc(s, words * 4, 0);
+         j.bloomMask = (uint32_t) (words - 1);
+      }
+      *out = s;
+   });
+}
 static void checkJoinError(LdbState* s) {
    int32_t e = 0;
    LDB_CUDA(cudaMemcpyAsync(&e, s->join.error, sizeof(e), cudaMemcpyDeviceToHost, s->ctx->compute));
@@ -752,19 +776,21 @@ FilterPlan planFilters(LdbTable* t, const LdbFilterDesc* f, int n, StagePlan& sp
          continue;
       }
       int64_t value = 0;
-      uint32_t mask = opMask(f[i].op);
+      uint32_t mask = opMask(f[i].op == LDB_CONTAINS ? (int) LDB_EQ : f[i].op); // contains: predicate value (0/1) == 1
       const char* str = nullptr;
       if (col.type == LDB_UTF8) {
-         if (f[i].op != LDB_EQ && f[i].op != LDB_NEQ) fail(LDB_ERR_UNSUPPORTED, "unsupported filter op for string");
+         if (f[i].op != LDB_EQ && f[i].op != LDB_NEQ && f[i].op != LDB_CONTAINS) fail(LDB_ERR_UNSUPPORTED, "unsupported filter op for string");
          if (!f[i].str_value || strlen(f[i].str_value) > sizeof(FilterCol::str)) fail(LDB_ERR_UNSUPPORTED, "string constant longer than 24 bytes");
-         kind = COL_UTF8_EQ;
+         kind = f[i].op == LDB_CONTAINS ? COL_UTF8_CONTAINS : COL_UTF8_EQ;
          value = 1;
          str = f[i].str_value;
       } else {
+         if (f[i].op == LDB_CONTAINS) fail(LDB_ERR_UNSUPPORTED, "LIKE-contains needs a utf8 column");
          value = filterConstant(col, f[i].value_is_int != 0, f[i].str_value, f[i].int_value);
       }
+      const bool isUtf8 = kind == COL_UTF8_EQ || kind == COL_UTF8_CONTAINS;
       int slot = -1;
-      if (kind != COL_UTF8_EQ)
+      if (!isUtf8)
          for (int k = 0; k < p.set.n; k++)
             if (p.colIdx[k] == c && p.set.c[k].maskB == 7 && p.set.c[k].nIn == 0) slot = k;
       if (slot >= 0) {
@@ -776,7 +802,7 @@ FilterPlan planFilters(LdbTable* t, const LdbFilterDesc* f, int n, StagePlan& sp
       FilterCol& fc = p.set.c[p.set.n];
       memset(&fc, 0, sizeof(fc));
       fc.kind = kind;
-      fc.staged = kind == COL_UTF8_EQ ? -1 : sp.add(t, c);
+      fc.staged = isUtf8 ? -1 : sp.add(t, c);
       fc.maskA = mask;
       fc.valA = value;
       fc.maskB = 7;
@@ -792,7 +818,7 @@ FilterPlan planFilters(LdbTable* t, const LdbFilterDesc* f, int n, StagePlan& sp
 void bindFilters(const FilterPlan& p, const LdbBatch& b, FilterSet& out) {
    out = p.set;
    for (int i = 0; i < out.n; i++) {
-      if (out.c[i].kind != COL_UTF8_EQ) continue; // fixed-width filter columns are read from the staged tile
+      if (out.c[i].kind != COL_UTF8_EQ && out.c[i].kind != COL_UTF8_CONTAINS) continue; // fixed-width filter columns are read from the staged tile
       out.c[i].base = b.data[p.colIdx[i]];
       out.c[i].bytes = (const uint8_t*) b.bytes[p.colIdx[i]];
    }
@@ -835,6 +861,11 @@ void waitBatch(LdbContext* ctx, const LdbBatch& b) {
 }
 LdbState* wantState(LdbState* s, int kind, const char* role) {
    if (!s || s->kind != kind) fail(LDB_ERR_INVALID, std::string("wrong or missing state for ") + role);
+   return s;
+}
+LdbState* wantSingleKeyTable(LdbState* s, const char* role) {
+   wantState(s, LDB_STATE_JOIN_TABLE, role);
+   if (s->join.stride == 16) fail(LDB_ERR_UNSUPPORTED, std::string("composite-key table not supported for ") + role);
    return s;
 }
 } // namespace
@@ -890,12 +921,34 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
             if (d->n_probes < 0 || d->n_probes > 1) fail(LDB_ERR_UNSUPPORTED, "build pipelines take at most one probe");
             if (d->n_side != sink->nSide) fail(LDB_ERR_INVALID, "side column count differs from the table's");
             int keyCol = R.col(d->build_key_column, {LDB_INT32, LDB_DATE32, LDB_FSB4}, "build key");
-            int payCol = d->build_payload_column ? R.col(d->build_payload_column, {LDB_INT32, LDB_DATE32, LDB_FSB4}, "build payload") : -1;
+            const bool pair = sink->join.stride == 16;
+            if (pair != (d->build_key2_column != nullptr)) fail(LDB_ERR_INVALID, "a second build key goes with a composite-key table (and only with one)");
+            if (pair && d->n_side) fail(LDB_ERR_UNSUPPORTED, "composite-key tables carry no side lanes");
+            int key2Col = pair ? R.col(d->build_key2_column, {LDB_INT32, LDB_DATE32, LDB_FSB4}, "second build key") : -1;
+            int payCol = -1, payKind = PAYLOAD_I32;
+            if (d->build_payload_column) {
+               if (pair) {
+                  payCol = R.col(d->build_payload_column, {LDB_INT32, LDB_DATE32, LDB_FSB4, LDB_DECIMAL128}, "build payload");
+                  if (t->columns[payCol].type == LDB_DECIMAL128) {
+                     if (t->columns[payCol].precision >= 19) fail(LDB_ERR_UNSUPPORTED, "decimal payloads must have precision < 19");
+                     payKind = PAYLOAD_DEC_LO64;
+                  }
+               } else {
+                  payCol = R.col(d->build_payload_column, {LDB_INT32, LDB_DATE32, LDB_FSB4}, "build payload");
+               }
+            }
+            if (d->build_payload_expr == LDB_PAYLOAD_YEAR) {
+               if (pair || payCol < 0 || t->columns[payCol].type != LDB_DATE32) fail(LDB_ERR_UNSUPPORTED, "year payloads come from a date32 column of a single-key build");
+               payKind = PAYLOAD_YEAR_OF_DATE32;
+            } else if (d->build_payload_expr != LDB_PAYLOAD_COLUMN) {
+               fail(LDB_ERR_UNSUPPORTED, "unknown build payload expression");
+            }
             int sideCol[kMaxSide] = {0, 0};
             for (int k = 0; k < d->n_side; k++) sideCol[k] = R.col(d->side_columns[k], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "side payload");
             LdbState* probe = d->n_probes ? wantState(d->probe_states[0], LDB_STATE_JOIN_TABLE, "probe") : nullptr;
+            if (probe && probe->join.stride == 16) fail(LDB_ERR_UNSUPPORTED, "build pipelines probe single-key tables");
             int probeCol = d->n_probes ? R.col(d->probe_key_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key") : -1;
-            int keyStage = sp.add(t, keyCol), payStage = payCol >= 0 ? sp.add(t, payCol) : -1, probeStage = probeCol >= 0 ? sp.add(t, probeCol) : 0;
+            int keyStage = sp.add(t, keyCol), key2Stage = key2Col >= 0 ? sp.add(t, key2Col) : -1, payStage = payCol >= 0 ? sp.add(t, payCol) : -1, probeStage = probeCol >= 0 ? sp.add(t, probeCol) : 0;
             int sideStage[kMaxSide] = {0, 0};
             for (int k = 0; k < d->n_side; k++) sideStage[k] = sp.add(t, sideCol[k]);
             for (auto& b : t->batches) {
@@ -905,7 +958,9 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                bindFilters(fp, b, p.src.filters);
                sp.bind(t, b, p.src.cols, kRowsPerThreadProbe);
                p.keyStage = keyStage;
+               p.keyStage2 = key2Stage;
                p.payloadStage = payStage;
+               p.payloadKind = payKind;
                p.nSide = d->n_side;
                for (int k = 0; k < d->n_side; k++) p.sideStage[k] = sideStage[k];
                p.hasProbe = probe ? 1 : 0;
@@ -948,8 +1003,8 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
             LdbState* sink = wantState(d->sink, LDB_STATE_GROUPBY, "sink");
             if (sink->group.nKeys != 1 || sink->group.nAggs != 1) fail(LDB_ERR_INVALID, "probe-probe-group sink must have one key and one aggregate");
             if (d->n_probes != 2) fail(LDB_ERR_INVALID, "probe-probe-group pipelines take two probes");
-            LdbState* ta = wantState(d->probe_states[0], LDB_STATE_JOIN_TABLE, "probe A");
-            LdbState* tb = wantState(d->probe_states[1], LDB_STATE_JOIN_TABLE, "probe B");
+            LdbState* ta = wantSingleKeyTable(d->probe_states[0], "probe A");
+            LdbState* tb = wantSingleKeyTable(d->probe_states[1], "probe B");
             AggPlan ap = planAggs(R, d->aggs, 1);
             int ca = R.col(d->probe_key_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key A");
             int cb = R.col(d->probe_key_columns[1], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key B");
@@ -979,7 +1034,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
             if (d->n_out_cols < 1 || d->n_out_cols > kMaxOutCols) fail(LDB_ERR_INVALID, "n_out_cols out of range");
             if (d->n_probes < 0 || d->n_probes > 1) fail(LDB_ERR_UNSUPPORTED, "materialize pipelines take at most one probe");
             if (!d->out_count || d->out_capacity < 0) fail(LDB_ERR_INVALID, "materialize needs out_count and out_capacity");
-            LdbState* probe = d->n_probes ? wantState(d->probe_states[0], LDB_STATE_JOIN_TABLE, "probe") : nullptr;
+            LdbState* probe = d->n_probes ? wantSingleKeyTable(d->probe_states[0], "probe") : nullptr;
             int probeStage = 0;
             if (probe) probeStage = sp.add(t, R.col(d->probe_key_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key"));
             int outStage[kMaxOutCols], outElem[kMaxOutCols];
@@ -1015,6 +1070,41 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                p.count = (unsigned long long*) d->out_count;
                waitBatch(ctx, b);
                ctx->launch("materialize", [&] { launchScanMaterialize(p, ctx->smCount, ctx->compute); });
+            }
+            break;
+         }
+         case LDB_PIPE_SCAN_STAR_PROBE_GROUPBY: {
+            LdbState* sink = wantState(d->sink, LDB_STATE_GROUPBY, "sink");
+            if (sink->group.nKeys != 2 || sink->group.nAggs != 1) fail(LDB_ERR_INVALID, "star-probe sink must have two keys and one aggregate");
+            if (d->n_probes != 3) fail(LDB_ERR_INVALID, "star-probe pipelines take three probes");
+            if (d->n_aggs != 1 || d->aggs[0].expr != LDB_EXPR_MUL_1MINUS_MINUS_PAYMUL) fail(LDB_ERR_UNSUPPORTED, "star-probe pipelines aggregate a * (1 - b) - $payload0 * c");
+            LdbState* tp = wantState(d->probe_states[0], LDB_STATE_JOIN_TABLE, "probe 0");
+            LdbState* ts = wantState(d->probe_states[1], LDB_STATE_JOIN_TABLE, "probe 1");
+            LdbState* to = wantState(d->probe_states[2], LDB_STATE_JOIN_TABLE, "probe 2");
+            if (tp->join.stride != 16 || !d->probe_key2_columns[0]) fail(LDB_ERR_INVALID, "probe 0 of a star-probe pipeline is a composite-key table");
+            if (ts->join.stride == 16 || to->join.stride == 16) fail(LDB_ERR_INVALID, "probes 1 and 2 of a star-probe pipeline are single-key tables");
+            StarProbeParams base{};
+            base.keyStageP0 = sp.add(t, R.col(d->probe_key_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key 0"));
+            base.keyStageP1 = sp.add(t, R.col(d->probe_key2_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key 0 (second)"));
+            base.keyStageS = sp.add(t, R.col(d->probe_key_columns[1], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key 1"));
+            base.keyStageO = sp.add(t, R.col(d->probe_key_columns[2], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key 2"));
+            for (int k = 0; k < 3; k++) {
+               int c = R.col(d->aggs[0].columns[k], {LDB_DECIMAL128}, "aggregate operand");
+               if (t->columns[c].precision >= 19 || t->columns[c].scale != 2) fail(LDB_ERR_UNSUPPORTED, "aggregate operands must be decimal(p<19, 2) on the GPU path");
+               base.valueStage[k] = sp.add(t, c);
+            }
+            for (auto& b : t->batches) {
+               if (b.nRows == 0) continue;
+               StarProbeParams p = base;
+               p.src.nRows = b.nRows;
+               bindFilters(fp, b, p.src.filters);
+               sp.bind(t, b, p.src.cols, kRowsPerThreadProbe);
+               p.tableP = tp->join;
+               p.tableS = ts->join;
+               p.tableO = to->join;
+               p.groups = sink->group;
+               waitBatch(ctx, b);
+               ctx->launch("join_star_probe_groupby", [&] { launchScanStarProbeGroupBy(p, ctx->smCount, ctx->compute); });
             }
             break;
          }
@@ -1054,7 +1144,7 @@ int ldb_gpu_partition_tuples(LdbContext* ctx, const int32_t* keys, const void* c
 }
 int ldb_gpu_join_table_insert(LdbContext* ctx, LdbState* table, const int32_t* keys, const int32_t* payloads, const int32_t* const* side_cols, int64_t n_rows, LdbError* err) {
    return guarded(err, [&] {
-      wantState(table, LDB_STATE_JOIN_TABLE, "insert target");
+      wantSingleKeyTable(table, "insert target");
       if (n_rows <= 0) return;
       const int32_t* s0 = table->nSide > 0 && side_cols ? side_cols[0] : nullptr;
       const int32_t* s1 = table->nSide > 1 && side_cols ? side_cols[1] : nullptr;

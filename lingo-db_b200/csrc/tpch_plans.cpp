@@ -80,11 +80,12 @@ LdbI128 avgDec(int64_t sum, int64_t count) {
 
 // Build a join table with the pipeline `d`, growing it if the cardinality estimate was too low
 // (the reference sizes after materialisation, LazyJoinHashtable.cpp:16; a GPU build must pre-size).
-LdbState* buildJoin(LdbContext* ctx, StateGuard& g, LdbPipelineDesc d, int64_t estimate, int unique, int nSide, int nAggs) {
+LdbState* buildJoin(LdbContext* ctx, StateGuard& g, LdbPipelineDesc d, int64_t estimate, int unique, int nSide, int nAggs, bool pairKey = false) {
    LdbError e;
    for (int attempt = 0; attempt < 6; attempt++) {
       LdbState* s = nullptr;
-      check(ldb_gpu_join_table_create(ctx, estimate, unique, nSide, nAggs, &s, &e), e);
+      if (pairKey) check(ldb_gpu_join_table_create_pair(ctx, estimate, unique, &s, &e), e);
+      else check(ldb_gpu_join_table_create(ctx, estimate, unique, nSide, nAggs, &s, &e), e);
       d.sink = s;
       int rc = ldb_gpu_run_pipeline(ctx, &d, &e);
       int64_t n = 0;
@@ -343,6 +344,78 @@ int ldb_tpch_q5(LdbContext* ctx, const LdbTpchTables* t, const char* regionName,
       });
       for (int i = 0; i < (int) out.size() && i < 25; i++) rows[i] = out[i];
       *nRows = (int32_t) std::min<size_t>(out.size(), 25);
+   });
+}
+
+// ------------------------------------------------------------------------------------------------ Q9
+// part(p_name like '%X%') → partsupp ⋈ part keyed (ps_partkey, ps_suppkey) → supplier, orders(→ year) → lineitem star probe.
+// p_partkey = l_partkey follows from ps_partkey = l_partkey and p_partkey = ps_partkey (the partsupp table only holds
+// parts that passed the LIKE), so the lineitem pipeline probes three tables, not four.
+int ldb_tpch_q9(LdbContext* ctx, const LdbTpchTables* t, const char* nameContains, LdbQ9Row* rows, int32_t maxRows, int32_t* nRows, LdbError* err) {
+   return guarded(err, [&] {
+      LdbError e;
+      StateGuard g;
+      if (!t->part || !t->partsupp) throw std::runtime_error("Q9 needs the part and partsupp tables");
+      int64_t nPart = ldb_gpu_table_num_rows(t->part), nPs = ldb_gpu_table_num_rows(t->partsupp), nOrd = ldb_gpu_table_num_rows(t->orders), nSupp = ldb_gpu_table_num_rows(t->supplier);
+      LdbFilterDesc fp[1] = {strFilter("p_name", LDB_CONTAINS, nameContains)};
+      LdbPipelineDesc dp{};
+      dp.kind = LDB_PIPE_SCAN_BUILD;
+      dp.source = t->part;
+      dp.n_filters = 1;
+      dp.filters = fp;
+      dp.build_key_column = "p_partkey";
+      LdbState* part = buildJoin(ctx, g, dp, nPart / 12 + 1024, 1, 0, 0);
+      LdbPipelineDesc dps{};
+      dps.kind = LDB_PIPE_SCAN_BUILD;
+      dps.source = t->partsupp;
+      dps.n_probes = 1;
+      dps.probe_states[0] = part;
+      dps.probe_key_columns[0] = "ps_partkey";
+      dps.build_key_column = "ps_partkey";
+      dps.build_key2_column = "ps_suppkey";
+      dps.build_payload_column = "ps_supplycost";
+      LdbState* ps = buildJoin(ctx, g, dps, nPs / 12 + 1024, 0, 0, 0, true);
+      LdbPipelineDesc ds{};
+      ds.kind = LDB_PIPE_SCAN_BUILD;
+      ds.source = t->supplier;
+      ds.build_key_column = "s_suppkey";
+      ds.build_payload_column = "s_nationkey";
+      LdbState* supp = buildJoin(ctx, g, ds, nSupp + 1024, 1, 0, 0);
+      LdbPipelineDesc dor{};
+      dor.kind = LDB_PIPE_SCAN_BUILD;
+      dor.source = t->orders;
+      dor.build_key_column = "o_orderkey";
+      dor.build_payload_column = "o_orderdate";
+      dor.build_payload_expr = LDB_PAYLOAD_YEAR;
+      LdbState* ord = buildJoin(ctx, g, dor, nOrd + 1024, 1, 0, 0);
+      LdbState* groups = nullptr;
+      check(ldb_gpu_groupby_create(ctx, 2, 1, 1024, &groups, &e), e);
+      g.own(groups);
+      LdbPipelineDesc dl{};
+      dl.kind = LDB_PIPE_SCAN_STAR_PROBE_GROUPBY;
+      dl.source = t->lineitem;
+      dl.n_probes = 3;
+      dl.probe_states[0] = ps;
+      dl.probe_key_columns[0] = "l_partkey";
+      dl.probe_key2_columns[0] = "l_suppkey";
+      dl.probe_states[1] = supp;
+      dl.probe_key_columns[1] = "l_suppkey";
+      dl.probe_states[2] = ord;
+      dl.probe_key_columns[2] = "l_orderkey";
+      dl.n_aggs = 1;
+      dl.aggs[0] = agg(LDB_EXPR_MUL_1MINUS_MINUS_PAYMUL, "l_extendedprice", "l_discount", "l_quantity");
+      dl.sink = groups;
+      check(ldb_gpu_run_pipeline(ctx, &dl, &e), e);
+      std::vector<LdbGroupRow> gr(1024);
+      int32_t n = 0;
+      check(ldb_gpu_groupby_read(groups, gr.data(), 1024, &n, &e), e);
+      std::vector<LdbQ9Row> out;
+      for (int i = 0; i < n; i++) out.push_back(LdbQ9Row{gr[i].keys[0], gr[i].keys[1], gr[i].aggs[0]});
+      // the host orders by n_name once it resolved the names; here: nationkey, year desc (stable and complete)
+      std::sort(out.begin(), out.end(), [](const LdbQ9Row& a, const LdbQ9Row& b) { return a.n_nationkey != b.n_nationkey ? a.n_nationkey < b.n_nationkey : a.o_year > b.o_year; });
+      if ((int) out.size() > maxRows) throw std::runtime_error("Q9 result has more rows than max_rows");
+      for (size_t i = 0; i < out.size(); i++) rows[i] = out[i];
+      *nRows = (int32_t) out.size();
    });
 }
 

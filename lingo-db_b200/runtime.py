@@ -164,7 +164,7 @@ class Tpch:
 
     def __init__(self, ctx: Context, tables: Dict[str, Table], nation_names: Optional[List[str]] = None):
         self.ctx, self.tables = ctx, tables
-        self.t = capi.TpchTables(**{k: (tables[k].h if k in tables else None) for k in ("lineitem", "orders", "customer", "supplier", "nation", "region")})
+        self.t = capi.TpchTables(**{k: (tables[k].h if k in tables else None) for k in ("lineitem", "orders", "customer", "supplier", "nation", "region", "part", "partsupp")})
         self.nation_names = nation_names or [n for n, _ in datagen.NATIONS]
 
     def q6(self, date_ge="1994-01-01", date_lt="1995-01-01", disc_ge="0.05", disc_le="0.07", qty_lt=24):
@@ -200,6 +200,12 @@ class Tpch:
         return [{"l_orderkey": r.l_orderkey, "revenue": r.revenue.value(), "o_orderdate": r.o_orderdate, "o_shippriority": r.o_shippriority}
                 for r in rows[: n.value]]
 
+    def q9(self, name_contains="green"):
+        rows, n, e = (capi.Q9Row * 1024)(), C.c_int32(), Error()
+        check(self.ctx.L.ldb_tpch_q9(self.ctx.h, C.byref(self.t), name_contains.encode(), rows, 1024, C.byref(n), C.byref(e)), e)
+        out = [{"nation": self.nation_names[r.n_nationkey], "o_year": r.o_year, "sum_profit": r.sum_profit.value()} for r in rows[: n.value]]
+        return sorted(out, key=lambda r: (r["nation"], -r["o_year"]))  # order by nation, o_year desc
+
     def q5(self, region_name="ASIA", date_ge="1994-01-01", date_lt="1995-01-01"):
         rows, n, e = (capi.Q5Row * 25)(), C.c_int32(), Error()
         check(self.ctx.L.ldb_tpch_q5(self.ctx.h, C.byref(self.t), region_name.encode(), date_ge.encode(), date_lt.encode(), rows, C.byref(n), C.byref(e)), e)
@@ -221,7 +227,8 @@ def state_destroy(ctx: Context, state):
 
 # ---------------------------------------------------------------------- generic pipeline call
 def run_pipeline(ctx: Context, kind: str, source: Table, filters=(), keys=(), aggs=(), probes=(), build_key=None, build_payload=None,
-                 side=(), sink=None, out_columns=(), out_buffers=(), out_capacity=0, out_count=None, bloom_only=False):
+                 side=(), sink=None, out_columns=(), out_buffers=(), out_capacity=0, out_count=None, bloom_only=False,
+                 build_key2=None, build_payload_expr="column"):
     """ldb_gpu_run_pipeline from keyword arguments.  filters: (column, op, value) with value str or int;
     aggs: (expr, [columns]); probes: (state, key_column)."""
     keep = []
@@ -261,10 +268,13 @@ def run_pipeline(ctx: Context, kind: str, source: Table, filters=(), keys=(), ag
         for j, c in enumerate(cols):
             d.aggs[i].columns[j] = b(c)
     d.n_probes = len(probes)
-    for i, (st, col) in enumerate(probes):
-        d.probe_states[i] = st
-        d.probe_key_columns[i] = b(col)
+    for i, pr in enumerate(probes):  # (state, key column[, second key column])
+        d.probe_states[i] = pr[0]
+        d.probe_key_columns[i] = b(pr[1])
+        d.probe_key2_columns[i] = b(pr[2]) if len(pr) > 2 else None
     d.build_key_column, d.build_payload_column = b(build_key), b(build_payload)
+    d.build_key2_column = b(build_key2)
+    d.build_payload_expr = capi.PAYLOAD_EXPR[build_payload_expr]
     d.n_side = len(side)
     for i, c in enumerate(side):
         d.side_columns[i] = b(c)
@@ -283,6 +293,12 @@ def run_pipeline(ctx: Context, kind: str, source: Table, filters=(), keys=(), ag
 def join_table(ctx: Context, expected_rows: int, unique: bool = True, n_side: int = 0, n_aggs: int = 0) -> C.c_void_p:
     s, e = C.c_void_p(), Error()
     check(ctx.L.ldb_gpu_join_table_create(ctx.h, int(expected_rows), int(unique), n_side, n_aggs, C.byref(s), C.byref(e)), e)
+    return s
+
+
+def join_table_pair(ctx: Context, expected_rows: int, unique: bool = True) -> C.c_void_p:
+    s, e = C.c_void_p(), Error()
+    check(ctx.L.ldb_gpu_join_table_create_pair(ctx.h, int(expected_rows), int(unique), C.byref(s), C.byref(e)), e)
     return s
 
 

@@ -5,6 +5,8 @@ Run in the build container (needs /root/reference); the JSON is committed so the
 Sources:
   test/lit/DB/hash.mlir                      CHECK lines 27-34 (db.hash of constants, executed through the JIT)
   test/unittests/storage/TestStorage.cpp     dbHash64(int8 1) literal (:289, :411)
+  test/lit/DB/dates.mlir                     ExtractFromDate(year, 2020-06-13) = 2020 (:23-26)
+  test/sqlite-datasets/tpchSf1.test          Q9 answer keys (nation, o_year): 25 nations x 1992..1998 (:20632-20807)
   test/sqlite-datasets/tpchSf1.test          Q1 answer rows (:25-28): avg = (sum * 10^19) / count, Q6 (:20506)
 """
 import json
@@ -36,5 +38,12 @@ out["tpch_sf1"]["q1"] = q1
 out["tpch_sf1"]["q1_file"] = "test/sqlite-datasets/tpchSf1.test:25-28"
 out["tpch_sf1"]["q6"] = lines[20505].strip()
 out["tpch_sf1"]["q6_file"] = "test/sqlite-datasets/tpchSf1.test:20506"
+dates = open(os.path.join(REF, "test/lit/DB/dates.mlir")).read()
+m = re.search(r'db.constant \( "(\d{4}-\d{2}-\d{2})"\) : !db.date<day>', dates)
+years = re.findall(r"//CHECK: int\((\d{4})\)", dates)
+out["dates"] = {"date": m.group(1), "extract_year": int(years[0]), "file": "test/lit/DB/dates.mlir:6,23-26"}
+q9 = [ln.split("\t")[:2] for ln in lines[20631:20807] if ln.count("\t") == 2]
+out["tpch_sf1"]["q9_keys"] = [[n.strip(), int(y)] for n, y in q9]
+out["tpch_sf1"]["q9_file"] = "test/sqlite-datasets/tpchSf1.test:20632-20807"
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_kats.json"), "w"), indent=1)
 print(json.dumps(out, indent=1)[:1500])

@@ -388,3 +388,40 @@ def test_in_and_notnull_filters(gpu_ctx):
         want[rf] = want.get(rf, 0) + e * (100 - d)
     assert got == want and len(got) >= 1
     gpu_ctx.L.ldb_gpu_state_destroy(st)
+
+
+def test_q9(gpu_ctx, oracle):
+    """Q9: LIKE-contains scan filter, composite-key join table, year payload, star probe + CTA-local group table.
+    Ragged host batches (several part/partsupp/lineitem batches) vs the oracle; a second needle; the tiny-scale case
+    where partsupp holds duplicate (partkey, suppkey) pairs (multimap semantics)."""
+    for sf, seed, chunk in ((0.05, 42, 8191), (0.002, 5, 1 << 20)):
+        t = datagen.tpch(sf, seed=seed, chunk_rows=chunk, with_parts=True)
+        oh, g = _oracle_tables(oracle, t), _gpu_tables(gpu_ctx, t)
+        for needle in ("green", "ro"):
+            want, _ = oracle.q9(oh["part"], oh["supplier"], oh["lineitem"], oh["partsupp"], oh["orders"], oh["nation"], needle)
+            got = g.q9(needle)
+            assert got == want, (sf, needle)
+            assert len(got) > 25
+        assert g.q9("no such colour") == []
+
+
+def test_q9_device_resident_matches_oracle(gpu_ctx, oracle):
+    from lingodb_b200 import devgen, runtime
+    s = datagen.scale(0.1, seed=9)
+    cols = ["l_orderkey", "l_partkey", "l_suppkey", "l_quantity", "l_extendedprice", "l_discount"]
+    tabs = {"lineitem": devgen.lineitem(gpu_ctx, s, cols, batch_rows=250000), "orders": devgen.orders(gpu_ctx, s), "supplier": devgen.supplier(gpu_ctx, s),
+            "part": devgen.part(gpu_ctx, s, batch_rows=7000), "partsupp": devgen.partsupp(gpu_ctx, s), **devgen.small_tables(gpu_ctx)}
+    # device twins of the new generators are bit-identical to the host generator
+    hp, hps = datagen.part(s, chunk_rows=7000), datagen.partsupp(s, chunk_rows=1 << 30)
+    dp, dps = devgen.to_host(tabs["part"]), devgen.to_host(tabs["partsupp"])
+    assert dp.chunk_rows == hp.chunk_rows
+    for a, b in zip(dp.chunks, hp.chunks):
+        assert np.array_equal(a["p_partkey"], b["p_partkey"])
+        assert np.array_equal(a["p_name"][0], b["p_name"][0]) and np.array_equal(a["p_name"][1], b["p_name"][1])
+    for name in ("ps_partkey", "ps_suppkey", "ps_supplycost"):
+        assert np.array_equal(dps.chunks[0][name], hps.chunks[0][name]), name
+    host = datagen.tpch(0.1, seed=9, lineitem_columns=cols, with_parts=True)
+    oh = {k: oracle.table(v) for k, v in host.items()}
+    want, _ = oracle.q9(oh["part"], oh["supplier"], oh["lineitem"], oh["partsupp"], oh["orders"], oh["nation"])
+    assert runtime.Tpch(gpu_ctx, tabs).q9() == want
+    assert len(want) == 175

@@ -194,6 +194,13 @@ def test_port_equals_reference_objects(tables):
         res.append((o.q6(h["lineitem"])[0], o.q1(h["lineitem"])[0], o.q3(h["customer"], h["orders"], h["lineitem"])[0],
                     o.q5(h["customer"], h["orders"], h["lineitem"], h["supplier"], h["nation"], h["region"])[0]))
     assert res[0] == res[1]
+    t9 = datagen.tpch(0.02, seed=4, chunk_rows=3000, with_parts=True)
+    res9 = []
+    for kind in ("port", "reference"):
+        o = O.Oracle(kind, workers=4)
+        h = {k: o.table(v) for k, v in t9.items()}
+        res9.append(o.q9(h["part"], h["supplier"], h["lineitem"], h["partsupp"], h["orders"], h["nation"])[0])
+    assert res9[0] == res9[1] and len(res9[0]) > 150
 
 
 def test_oracle_edge_cases(orc):
@@ -207,3 +214,53 @@ def test_oracle_edge_cases(orc):
     assert orc.q1(orc.table(ragged))[0] == orc.q1(orc.table(whole))[0]
     with pytest.raises(RuntimeError):
         orc.q6(orc.table(whole), date_ge="garbage")
+
+
+# ---------------------------------------------------------------- Q9 (scalar runtime + pipeline)
+def test_extract_year_and_const_like(orc):
+    import datetime
+    L, d = orc.lib, GOLD["dates"]
+    days = L.oracle_parse_date(d["date"].encode())
+    assert L.oracle_extract_year(days * 86400 * 10**9) == d["extract_year"]  # test/lit/DB/dates.mlir:23-26
+    for days in (-366, -365, -1, 0, 58, 59, 60, 364, 365, 789, 8035, 10440, 10591, 10592, 11016, 11017, 19000, 47482, -25567):
+        want = (datetime.date(1970, 1, 1) + datetime.timedelta(days=days)).year
+        assert L.oracle_extract_year(days * 86400 * 10**9) == want, days
+        assert L.oracle_extract_year(days * 86400 * 10**9 + 86399 * 10**9) == want, days  # floor<days> of a timestamp inside the day
+    for s, needle, want in ((b"forest green navy", b"green", 1), (b"greengreen", b"green", 1), (b"gree n", b"green", 0), (b"", b"green", 0),
+                            (b"a long string of more than twelve bytes ending in gree", b"green", 0), (b"xgreen", b"green", 1), (b"abc", b"", 1)):
+        assert L.oracle_const_like_contains(s, len(s), needle) == want, s
+
+
+def test_q9_matches_python(orc):
+    import datetime
+    t = datagen.tpch(0.02, seed=13, chunk_rows=4000, with_parts=True)
+    li = _cols(t["lineitem"], ["l_orderkey", "l_partkey", "l_suppkey", "l_quantity", "l_extendedprice", "l_discount"])
+    od = _cols(t["orders"], ["o_orderkey", "o_orderdate"])
+    su = _cols(t["supplier"], ["s_suppkey", "s_nationkey"])
+    ps = _cols(t["partsupp"], ["ps_partkey", "ps_suppkey", "ps_supplycost"])
+    pk = _cols(t["part"], ["p_partkey"])["p_partkey"]
+    names = []
+    for ch in t["part"].chunks:
+        offs, data = ch["p_name"]
+        b = bytes(data)
+        names += [b[offs[i]:offs[i + 1]].decode() for i in range(len(offs) - 1)]
+    h = {k: orc.table(v) for k, v in t.items()}
+    for needle in ("green", "y"):
+        parts = {int(k) for k, n in zip(pk, names) if needle in n}
+        cost = {}
+        for a, b, c in zip(ps["ps_partkey"], ps["ps_suppkey"], ps["ps_supplycost"]):
+            if int(a) in parts:
+                cost.setdefault((int(a), int(b)), []).append(int(c))
+        nat = {int(k): int(n) for k, n in zip(su["s_suppkey"], su["s_nationkey"])}
+        year = {int(k): (datetime.date(1970, 1, 1) + datetime.timedelta(days=int(d))).year for k, d in zip(od["o_orderkey"], od["o_orderdate"])}
+        acc = {}
+        for ok, p, s, q, e, dc in zip(li["l_orderkey"], li["l_partkey"], li["l_suppkey"], li["l_quantity"], li["l_extendedprice"], li["l_discount"]):
+            for c in cost.get((int(p), int(s)), ()):
+                key = (datagen.NATIONS[nat[int(s)]][0], year[int(ok)])
+                acc[key] = acc.get(key, 0) + int(e) * (100 - int(dc)) - c * int(q)
+        want = [{"nation": n, "o_year": y, "sum_profit": v} for (n, y), v in sorted(acc.items(), key=lambda kv: (kv[0][0], -kv[0][1]))]
+        got, _ = orc.q9(h["part"], h["supplier"], h["lineitem"], h["partsupp"], h["orders"], h["nation"], needle)
+        assert got == want, needle
+    # the result's key set is the one the reference's own Q9 answer has (tpchSf1.test:20632-20807): 25 nations x 1992..1998
+    got, _ = orc.q9(h["part"], h["supplier"], h["lineitem"], h["partsupp"], h["orders"], h["nation"])
+    assert [[r["nation"], r["o_year"]] for r in got] == GOLD["tpch_sf1"]["q9_keys"]
