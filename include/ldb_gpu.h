@@ -138,6 +138,10 @@ int64_t ldb_gpu_groupby_export_bytes(LdbState* s);
 int ldb_gpu_groupby_export(LdbState* s, void* dev_dst, LdbError* err);
 int ldb_gpu_groupby_merge_exported(LdbState* s, const void* dev_src, int32_t n_tables, int32_t skip_index, LdbError* err);
 
+/* unique_keys is a flag word: LDB_JOIN_UNIQUE = the build keys are unique (a probe stops at its first match, a duplicate
+ * insert is an error); LDB_JOIN_NO_BLOOM = no Bloom filter in front of the directory (foreign-key probes that always
+ * hit gain nothing from it, and the build saves one random atomic per row). */
+enum LdbJoinFlags { LDB_JOIN_UNIQUE = 1, LDB_JOIN_NO_BLOOM = 2 };
 /* expected_rows sizes the directory like HashIndexedView::build (nextPow2 of a multiple of n);
  * n_side = int32 payload lanes stored beside the slot; n_aggs = int128 aggregate lanes (group-join) */
 int ldb_gpu_join_table_create(LdbContext* ctx, int64_t expected_rows, int32_t unique_keys, int32_t n_side, int32_t n_aggs, LdbState** out, LdbError* err);

@@ -1142,18 +1142,28 @@ bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStre
 // int32 payloads → SUM(a * (1 - b) - c * d), c = P's int64 payload.  The reference's per-worker pre-aggregation
 // cache (PreAggregationHashtable.cpp:46-60) becomes a per-CTA shared-memory table flushed once per CTA: ~10^8 matched
 // rows over 175 groups would otherwise serialise on 175 HBM addresses.
-constexpr int kStarGroups = 512; // CTA-local group slots (power of two); further groups go straight to the HBM table
+constexpr int kStarGroups = 256; // CTA-local group slots (power of two); further groups go straight to the HBM table
+// Only ~5 % of the rows survive P's Bloom filter, i.e. ~2 lanes per warp.  Handled in place, the dependent part (three
+// random directory walks, two i128 products, the group update) ran with ONE active lane per instruction and held the
+// tile's stage until the slowest chain finished: 9.4 ms for a 1.7 ms scan (profiles/r1_q9.md).  So the scan and the
+// probes are decoupled inside the kernel: survivors are copied into a CTA-wide queue in shared memory, and whenever the
+// queue holds a full CTA's worth, every thread takes one entry — 256 independent chains in flight, all lanes busy.
+constexpr int kStarQueue = kBlock + kRowsPerThreadProbe * kBlock; // a drain leaves < kBlock entries; one tile adds <= tileRows
 template <int DB>
-__global__ void __launch_bounds__(kThreads, 4) scanStarProbeGroupByKernel(const __grid_constant__ StarProbeParams p) {
+__global__ void __launch_bounds__(kBlock, 2) scanStarProbeGroupByKernel(const __grid_constant__ StarProbeParams p) {
    constexpr bool IN = true;
    __shared__ __align__(8) TileBarriers barsStorage;
    __shared__ unsigned long long sKey[kStarGroups];
    __shared__ unsigned long long sAcc[kStarGroups][2];
+   __shared__ int64_t qA[kStarQueue], qB[kStarQueue], qD[kStarQueue];
+   __shared__ int32_t qK0[kStarQueue], qK1[kStarQueue], qKS[kStarQueue], qKO[kStarQueue];
+   __shared__ int qCount;
    TileBarriers* bars = &barsStorage;
    for (int i = threadIdx.x; i < kStarGroups; i += blockDim.x) {
       sKey[i] = kEmptySlot;
       sAcc[i][0] = sAcc[i][1] = 0;
    }
+   if (threadIdx.x == 0) qCount = 0;
    __syncthreads();
    const int64_t one = 100;
    auto groupAdd = [&](int32_t g0, int32_t g1, i128 v) {
@@ -1174,55 +1184,64 @@ __global__ void __launch_bounds__(kThreads, 4) scanStarProbeGroupByKernel(const 
       int slot = groupLookupOrInsert(p.groups, kk);
       if (slot >= 0) groupAtomicAdd(p.groups, slot, 0, v, false);
    };
-   forEachTile<kRowsPerThreadProbe, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
-      int32_t k0[kRowsPerThreadProbe], k1[kRowsPerThreadProbe];
-      int lrs[kRowsPerThreadProbe];
+   // the three probes of a row are independent of each other: their first slots are loaded together (S and O are
+   // foreign-key probes that always hit, so their Bloom filters are not consulted)
+   auto processEntry = [&](int i) {
+      const int32_t k0 = qK0[i], k1 = qK1[i], kS = qKS[i], kO = qKO[i];
+      const uint64_t hP = hashPair(k0, k1), hS = hashI32(kS), hO = hashI32(kO);
+      const ulonglong2 eP = __ldg((const ulonglong2*) slotPtr(p.tableP, hP & p.tableP.mask));
+      const unsigned long long eS = __ldg(slotPtr(p.tableS, hS & p.tableS.mask));
+      const unsigned long long eO = __ldg(slotPtr(p.tableO, hO & p.tableO.mask));
+      const int64_t a = qA[i], b = qB[i], d = qD[i];
+      pairProbeFrom(p.tableP, k0, k1, hP, eP, [&](int64_t c) {
+         joinProbeFrom(p.tableS, kS, hS, eS, [&](int32_t g0) {
+            joinProbeFrom(p.tableO, kO, hO, eO, [&](int32_t g1) { groupAdd(g0, g1, sub128(mul64x64(a, one - b), mul64x64(c, d))); });
+         });
+      });
+   };
+   // called by every thread after a barrier that published the pushes; leaves < kBlock entries unless `all`
+   auto drain = [&](bool all) {
+      int count = qCount;
+      if (!(count >= kBlock || (all && count > 0))) return;
+      while (count >= kBlock || (all && count > 0)) {
+         const int n = count < kBlock ? count : kBlock;
+         if ((int) threadIdx.x < n) processEntry(count - n + (int) threadIdx.x);
+         count -= n;
+      }
+      __syncthreads(); // every thread read qCount and finished its entries
+      if (threadIdx.x == 0) qCount = count;
+      __syncthreads();
+   };
+   forEachTileUniform<kRowsPerThreadProbe, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
       BloomProbe bp[kRowsPerThreadProbe];
+      int lrs[kRowsPerThreadProbe];
 #pragma unroll
-      for (int j = 0; j < kRowsPerThreadProbe; j++) { // phase A: filters + P's Bloom word for every row of the thread
+      for (int j = 0; j < kRowsPerThreadProbe; j++) { // filters + P's Bloom word for every row of the thread (loads in flight together)
          const int lr = j * kBlock + threadIdx.x;
          const bool valid = lr < rows;
          lrs[j] = valid ? lr : 0;
          const bool ok = valid && evalFilters<IN>(p.src.filters, tile, lrs[j], rowBase + lrs[j]);
-         k0[j] = tile.i32(p.keyStageP0, lrs[j]);
-         k1[j] = tile.i32(p.keyStageP1, lrs[j]);
-         bp[j] = pairBloomPrefetch(p.tableP, k0[j], k1[j], ok);
-      }
-      // phase B: the three probes of a row are independent of each other, so a survivor puts the first slot of ALL three
-      // directories in flight at once (S and O are foreign-key probes that always hit: their Bloom filters are skipped).
-      // With ~2 surviving lanes per warp the kernel is bound by this dependent-load chain, not by bandwidth: one round
-      // trip per tile instead of six (profiles/r1_q9.md).
-      ulonglong2 eP[kRowsPerThreadProbe];
-      unsigned long long eS[kRowsPerThreadProbe], eO[kRowsPerThreadProbe];
-      int32_t kS[kRowsPerThreadProbe], kO[kRowsPerThreadProbe];
-      uint64_t hS[kRowsPerThreadProbe], hO[kRowsPerThreadProbe];
-#pragma unroll
-      for (int j = 0; j < kRowsPerThreadProbe; j++) {
-         kS[j] = tile.i32(p.keyStageS, lrs[j]);
-         kO[j] = tile.i32(p.keyStageO, lrs[j]);
-         hS[j] = hashI32(kS[j]);
-         hO[j] = hashI32(kO[j]);
-         if (bp[j].mayContain()) {
-            eP[j] = __ldg((const ulonglong2*) slotPtr(p.tableP, bp[j].h & p.tableP.mask));
-            eS[j] = __ldg(slotPtr(p.tableS, hS[j] & p.tableS.mask));
-            eO[j] = __ldg(slotPtr(p.tableO, hO[j] & p.tableO.mask));
-         }
+         bp[j] = pairBloomPrefetch(p.tableP, tile.i32(p.keyStageP0, lrs[j]), tile.i32(p.keyStageP1, lrs[j]), ok);
       }
 #pragma unroll
       for (int j = 0; j < kRowsPerThreadProbe; j++) {
          if (!bp[j].mayContain()) continue;
-         pairProbeFrom(p.tableP, k0[j], k1[j], bp[j].h, eP[j], [&](int64_t c) {
-            joinProbeFrom(p.tableS, kS[j], hS[j], eS[j], [&](int32_t g0) {
-               joinProbeFrom(p.tableO, kO[j], hO[j], eO[j], [&](int32_t g1) {
-                  const int64_t a = tile.lo64(p.valueStage[0], lrs[j]), b = tile.lo64(p.valueStage[1], lrs[j]), d = tile.lo64(p.valueStage[2], lrs[j]);
-                  groupAdd(g0, g1, sub128(mul64x64(a, one - b), mul64x64(c, d)));
-               });
-            });
-         });
+         const int q = atomicAdd(&qCount, 1), lr = lrs[j];
+         qK0[q] = tile.i32(p.keyStageP0, lr);
+         qK1[q] = tile.i32(p.keyStageP1, lr);
+         qKS[q] = tile.i32(p.keyStageS, lr);
+         qKO[q] = tile.i32(p.keyStageO, lr);
+         qA[q] = tile.lo64(p.valueStage[0], lr);
+         qB[q] = tile.lo64(p.valueStage[1], lr);
+         qD[q] = tile.lo64(p.valueStage[2], lr);
       }
+      __syncthreads();
+      drain(false);
    });
    __syncthreads();
-   for (int i = threadIdx.x; i < kStarGroups; i += blockDim.x) { // blockDim = consumers + producer warp; all of them flush
+   drain(true);
+   __syncthreads();
+   for (int i = threadIdx.x; i < kStarGroups; i += blockDim.x) {
       const unsigned long long key = sKey[i];
       if (key == kEmptySlot) continue;
       const i128 v{sAcc[i][0], (int64_t) sAcc[i][1]};
@@ -1234,11 +1253,11 @@ __global__ void __launch_bounds__(kThreads, 4) scanStarProbeGroupByKernel(const 
 void launchScanStarProbeGroupBy(const StarProbeParams& p, int smCount, cudaStream_t s) {
    size_t dyn;
    if (p.src.cols.decBytes == 8) {
-      int grid = persistentGrid(scanStarProbeGroupByKernel<8>, p.src.cols, p.src.nRows, smCount, &dyn);
-      scanStarProbeGroupByKernel<8><<<grid, kThreads, dyn, s>>>(p);
+      int grid = persistentGrid(scanStarProbeGroupByKernel<8>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+      scanStarProbeGroupByKernel<8><<<grid, kBlock, dyn, s>>>(p);
    } else {
-      int grid = persistentGrid(scanStarProbeGroupByKernel<16>, p.src.cols, p.src.nRows, smCount, &dyn);
-      scanStarProbeGroupByKernel<16><<<grid, kThreads, dyn, s>>>(p);
+      int grid = persistentGrid(scanStarProbeGroupByKernel<16>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+      scanStarProbeGroupByKernel<16><<<grid, kBlock, dyn, s>>>(p);
    }
 }
 

@@ -574,7 +574,7 @@ int ldb_gpu_join_table_create(LdbContext* ctx, int64_t expected_rows, int32_t un
       uint64_t cap = nextPow2((uint64_t) std::max<int64_t>(expected_rows, 8) * 2);
       auto& j = s->join;
       j.mask = cap - 1;
-      j.unique = unique_keys;
+      j.unique = unique_keys & LDB_JOIN_UNIQUE;
       if (n_side > 0 || n_aggs > 0) { // group-join map: one 32-byte sector per entry
          j.stride = 32;
          j.base = (uint8_t*) ctx->stagingAlloc(cap * 32);
@@ -586,7 +586,7 @@ int ldb_gpu_join_table_create(LdbContext* ctx, int64_t expected_rows, int32_t un
       }
       j.count = (unsigned long long*) devAlloc(s, 8, 0);
       j.error = (int32_t*) devAlloc(s, 4, 0);
-      if (cap >= 4096) { // 8 filter bits per directory slot = 16..32 bits per key at load 0.25..0.5
+      if (cap >= 4096 && !(unique_keys & LDB_JOIN_NO_BLOOM)) { // 8 filter bits per directory slot = 16..32 bits per key at load 0.25..0.5
          uint64_t words = cap / 4;
          j.bloom = (uint32_t*) devAlloc(s, words * 4, 0);
          j.bloomMask = (uint32_t) (words - 1);
@@ -607,12 +607,12 @@ int ldb_gpu_join_table_create_pair(LdbContext* ctx, int64_t expected_rows, int32
       uint64_t cap = nextPow2((uint64_t) std::max<int64_t>(expected_rows, 8) * 2);
       auto& j = s->join;
       j.mask = cap - 1;
-      j.unique = unique_keys;
+      j.unique = unique_keys & LDB_JOIN_UNIQUE;
       j.stride = 16;
       j.base = (uint8_t*) devAlloc(s, cap * 16, 0xff);
       j.count = (unsigned long long*) devAlloc(s, 8, 0);
       j.error = (int32_t*) devAlloc(s, 4, 0);
-      if (cap >= 4096) {
+      if (cap >= 4096 && !(unique_keys & LDB_JOIN_NO_BLOOM)) {
          uint64_t words = cap / 4;
          j.bloom = (uint32_t*) devAlloc(s, words * 4, 0);
          j.bloomMask = (uint32_t) (words - 1);

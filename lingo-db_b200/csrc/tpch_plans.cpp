@@ -380,14 +380,14 @@ int ldb_tpch_q9(LdbContext* ctx, const LdbTpchTables* t, const char* nameContain
       ds.source = t->supplier;
       ds.build_key_column = "s_suppkey";
       ds.build_payload_column = "s_nationkey";
-      LdbState* supp = buildJoin(ctx, g, ds, nSupp + 1024, 1, 0, 0);
+      LdbState* supp = buildJoin(ctx, g, ds, nSupp + 1024, LDB_JOIN_UNIQUE | LDB_JOIN_NO_BLOOM, 0, 0); // foreign-key probes: always hit
       LdbPipelineDesc dor{};
       dor.kind = LDB_PIPE_SCAN_BUILD;
       dor.source = t->orders;
       dor.build_key_column = "o_orderkey";
       dor.build_payload_column = "o_orderdate";
       dor.build_payload_expr = LDB_PAYLOAD_YEAR;
-      LdbState* ord = buildJoin(ctx, g, dor, nOrd + 1024, 1, 0, 0);
+      LdbState* ord = buildJoin(ctx, g, dor, nOrd + 1024, LDB_JOIN_UNIQUE | LDB_JOIN_NO_BLOOM, 0, 0);
       LdbState* groups = nullptr;
       check(ldb_gpu_groupby_create(ctx, 2, 1, 1024, &groups, &e), e);
       g.own(groups);
