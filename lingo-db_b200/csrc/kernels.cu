@@ -1148,9 +1148,9 @@ constexpr int kStarGroups = 256; // CTA-local group slots (power of two); furthe
 // tile's stage until the slowest chain finished: 9.4 ms for a 1.7 ms scan (profiles/r1_q9.md).  So the scan and the
 // probes are decoupled inside the kernel: survivors are copied into a CTA-wide queue in shared memory, and whenever the
 // queue holds a full CTA's worth, every thread takes one entry — 256 independent chains in flight, all lanes busy.
-constexpr int kStarQueue = kBlock + kRowsPerThreadProbe * kBlock; // a drain leaves < kBlock entries; one tile adds <= tileRows
+constexpr int kStarQueue = kBlock + kRowsPerThreadStar * kBlock; // a drain leaves < kBlock entries; one tile adds <= tileRows
 template <int DB>
-__global__ void __launch_bounds__(kBlock, 2) scanStarProbeGroupByKernel(const __grid_constant__ StarProbeParams p) {
+__global__ void __launch_bounds__(kBlock, 4) scanStarProbeGroupByKernel(const __grid_constant__ StarProbeParams p) {
    constexpr bool IN = true;
    __shared__ __align__(8) TileBarriers barsStorage;
    __shared__ unsigned long long sKey[kStarGroups];
@@ -1212,11 +1212,11 @@ __global__ void __launch_bounds__(kBlock, 2) scanStarProbeGroupByKernel(const __
       if (threadIdx.x == 0) qCount = count;
       __syncthreads();
    };
-   forEachTileUniform<kRowsPerThreadProbe, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
-      BloomProbe bp[kRowsPerThreadProbe];
-      int lrs[kRowsPerThreadProbe];
+   forEachTileUniform<kRowsPerThreadStar, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+      BloomProbe bp[kRowsPerThreadStar];
+      int lrs[kRowsPerThreadStar];
 #pragma unroll
-      for (int j = 0; j < kRowsPerThreadProbe; j++) { // filters + P's Bloom word for every row of the thread (loads in flight together)
+      for (int j = 0; j < kRowsPerThreadStar; j++) { // filters + P's Bloom word for every row of the thread (loads in flight together)
          const int lr = j * kBlock + threadIdx.x;
          const bool valid = lr < rows;
          lrs[j] = valid ? lr : 0;
@@ -1224,7 +1224,7 @@ __global__ void __launch_bounds__(kBlock, 2) scanStarProbeGroupByKernel(const __
          bp[j] = pairBloomPrefetch(p.tableP, tile.i32(p.keyStageP0, lrs[j]), tile.i32(p.keyStageP1, lrs[j]), ok);
       }
 #pragma unroll
-      for (int j = 0; j < kRowsPerThreadProbe; j++) {
+      for (int j = 0; j < kRowsPerThreadStar; j++) {
          if (!bp[j].mayContain()) continue;
          const int q = atomicAdd(&qCount, 1), lr = lrs[j];
          qK0[q] = tile.i32(p.keyStageP0, lr);

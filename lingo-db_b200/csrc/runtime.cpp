@@ -1098,7 +1098,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                StarProbeParams p = base;
                p.src.nRows = b.nRows;
                bindFilters(fp, b, p.src.filters);
-               sp.bind(t, b, p.src.cols, kRowsPerThreadProbe);
+               sp.bind(t, b, p.src.cols, kRowsPerThreadStar);
                p.tableP = tp->join;
                p.tableS = ts->join;
                p.tableO = to->join;

@@ -374,7 +374,15 @@ int ldb_tpch_q9(LdbContext* ctx, const LdbTpchTables* t, const char* nameContain
       dps.build_key_column = "ps_partkey";
       dps.build_key2_column = "ps_suppkey";
       dps.build_payload_column = "ps_supplycost";
-      LdbState* ps = buildJoin(ctx, g, dps, nPs / 12 + 1024, 0, 0, 0, true);
+      // (ps_partkey, ps_suppkey) is partsupp's primary key: build a unique table (a probe stops at its first match); if the
+      // data disagrees (the tiny-scale generator repeats suppliers) the build reports the duplicate and a multimap is built
+      LdbState* ps = nullptr;
+      try {
+         ps = buildJoin(ctx, g, dps, nPs / 12 + 1024, LDB_JOIN_UNIQUE, 0, 0, true);
+      } catch (const PlanError& pe) {
+         if (pe.e.code != LDB_ERR_INVALID) throw;
+         ps = buildJoin(ctx, g, dps, nPs / 12 + 1024, 0, 0, 0, true);
+      }
       LdbPipelineDesc ds{};
       ds.kind = LDB_PIPE_SCAN_BUILD;
       ds.source = t->supplier;
