@@ -145,8 +145,9 @@ enum LdbJoinFlags { LDB_JOIN_UNIQUE = 1, LDB_JOIN_NO_BLOOM = 2 };
 /* expected_rows sizes the directory like HashIndexedView::build (nextPow2 of a multiple of n);
  * n_side = int32 payload lanes stored beside the slot; n_aggs = int128 aggregate lanes (group-join) */
 int ldb_gpu_join_table_create(LdbContext* ctx, int64_t expected_rows, int32_t unique_keys, int32_t n_side, int32_t n_aggs, LdbState** out, LdbError* err);
-/* composite (int32, int32) key → int64 payload (a decimal(p<19) value or an int32), hashed like db.hash over the key
- * tuple (LowerToStd.cpp:1139-1150); Q9's partsupp side: (ps_partkey, ps_suppkey) → ps_supplycost */
+/* composite (int32, int32) key → int64 payload (a decimal(p<19) value or an int32); Q9's partsupp side:
+ * (ps_partkey, ps_suppkey) → ps_supplycost.  Slot placement uses its own 64-bit mix, not db.hash over the tuple
+ * (LowerToStd.cpp:1139-1150), whose XOR-combine clusters correlated keys under open addressing (csrc/kernels.cu). */
 int ldb_gpu_join_table_create_pair(LdbContext* ctx, int64_t expected_rows, int32_t unique_keys, LdbState** out, LdbError* err);
 int ldb_gpu_join_table_count(LdbState* s, int64_t* n_entries, LdbError* err);
 typedef struct LdbTopKRow {

@@ -387,8 +387,22 @@ __device__ __forceinline__ void joinProbe(const JoinTableDev& t, int32_t key, co
    }
 }
 
-// ---- composite-key table (stride 16): {key0, key1} → int64 payload; hashed like db.hash over the key tuple
-__device__ __forceinline__ uint64_t hashPair(int32_t k0, int32_t k1) { return hashCombine(hashI32(k1), hashI32(k0)); }
+// ---- composite-key table (stride 16): {key0, key1} → int64 payload.
+// NOT hashed like db.hash over the key tuple: h64 is bswap-symmetric (bswap(h64(x)) == h64(x)), so the reference's
+// combine h64(k1) ^ bswap(h64(k0)) degenerates to h64(k1) ^ h64(k0) = f(k0*C ^ k1*C), and for correlated keys
+// (ps_suppkey is ps_partkey plus a small multiple, modulo S) the low bits cluster: with open addressing the P probe of
+// Q9 walked ~7 slots per lookup at SF100 and thousands at SF300 (profiles/r1_q9.md).  The reference's chained buckets
+// only lose a constant factor there; a linear-probing table needs avalanche, so the pair is mixed as ONE 64-bit word
+// (MurmurHash3's fmix64 finaliser).  Placement inside the table is an internal matter — results do not depend on it.
+__device__ __forceinline__ uint64_t hashPair(int32_t k0, int32_t k1) {
+   uint64_t x = ((uint64_t) (uint32_t) k1 << 32) | (uint32_t) k0;
+   x ^= x >> 33;
+   x *= 0xff51afd7ed558ccdull;
+   x ^= x >> 33;
+   x *= 0xc4ceb9fe1a85ec53ull;
+   x ^= x >> 33;
+   return x;
+}
 __device__ int64_t pairInsert(const JoinTableDev& t, int32_t k0, int32_t k1, int64_t payload) {
    const unsigned long long packed = packSlot(k0, k1);
    if (packed == kEmptySlot) {
