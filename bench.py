@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 
 Q1_COLS = ["l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus", "l_shipdate"]
 Q1_BYTES_PER_ROW = 76  # 4 decimal128 + 2 fixed_size_binary(4) + date32
-ALL_COLS = ["l_orderkey", "l_suppkey"] + Q1_COLS
+ALL_COLS = ["l_orderkey", "l_partkey", "l_suppkey"] + Q1_COLS
 METRIC = "TPC-H SF100 Q1 rows/sec"
 
 
@@ -333,16 +333,21 @@ def run_ours(args):
                "sample": f"first {n} lineitem rows of the SF{args.sf:g} table (the SF{sample_sf:g} prefix), best of 3 after 1 warm-up, pipelines only",
                "seconds": sec, "note": "reference runtime objects + restated pipelines (oracle/), not the MLIR/LLVM JIT"}
 
-    # ---- side measurements for the other §8 configs (N = 1): Q6, Q3, Q5 on the same resident tables
+    # ---- side measurements for the other §8 configs (N = 1): Q6, Q3, Q5, Q9 on the same resident tables
     queries = None
     if extra and rank == 0:
         queries = {}
         tabs.update({"orders": devgen.orders(ctx, s), "customer": devgen.customer(ctx, s), "supplier": devgen.supplier(ctx, s), **devgen.small_tables(ctx)})
+        tabs.update({"part": devgen.part(ctx, s), "partsupp": devgen.partsupp(ctx, s)})
         tpx = runtime.Tpch(ctx, tabs)
-        scanned = {"q6": s.n_lineitem, "q3": s.n_lineitem + s.n_orders + s.n_customer, "q5": s.n_lineitem + s.n_orders + s.n_customer + s.n_supplier + 30}
+        n_ps = 4 * s.n_part
+        scanned = {"q6": s.n_lineitem, "q3": s.n_lineitem + s.n_orders + s.n_customer, "q5": s.n_lineitem + s.n_orders + s.n_customer + s.n_supplier + 30,
+                   "q9": s.n_lineitem + s.n_orders + n_ps + s.n_part + s.n_supplier + 25}
+        # Arrow physical widths of the referenced columns, each read once (p_name: 4 B offset + ~33 B text)
         algo = {"q6": 52 * s.n_lineitem, "q3": 40 * s.n_lineitem + 16 * s.n_orders + 21 * s.n_customer,
-                "q5": 40 * s.n_lineitem + 12 * s.n_orders + 8 * s.n_customer + 8 * s.n_supplier}
-        for name, fn in (("q6", tpx.q6), ("q3", tpx.q3), ("q5", tpx.q5)):
+                "q5": 40 * s.n_lineitem + 12 * s.n_orders + 8 * s.n_customer + 8 * s.n_supplier,
+                "q9": 60 * s.n_lineitem + 24 * n_ps + 8 * s.n_orders + 41 * s.n_part + 8 * s.n_supplier}
+        for name, fn in (("q6", tpx.q6), ("q3", tpx.q3), ("q5", tpx.q5), ("q9", tpx.q9)):
             fn()
             fn()
             ctx.synchronize()
