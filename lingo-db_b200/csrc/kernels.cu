@@ -151,13 +151,13 @@ __device__ __forceinline__ void forEachTileUniform(const StagedCols& sc, int64_t
       }
    } else {
       for (int64_t t = blockIdx.x; t < nFull; t += gridDim.x) {
-         __syncwarp();
          GlobalTile<DB> tile{t * kTileRows, &sc};
          fnTile(tile, t * kTileRows, kTileRows);
+         __syncthreads(); // same contract as the TMA path: no thread starts the next tile before all finished this one
       }
    }
    if (nFull * kTileRows < n && (int64_t) blockIdx.x == nFull % gridDim.x) {
-      __syncwarp();
+      __syncthreads();
       GlobalTile<DB> tile{nFull * kTileRows, &sc};
       fnTile(tile, nFull * kTileRows, (int) (n - nFull * kTileRows));
    }
@@ -797,6 +797,87 @@ bool launchScanGroupBy(const GroupByParams& p, int smCount, cudaStream_t s, cons
    return true;
 }
 
+// =================================================================================== survivor queue
+// The probe kernels (K3 with a parent probe, K4, K5, K9) keep only a few percent of the scanned rows after the Bloom filter
+// of the first table.  Handling those in place leaves ~2 active lanes per warp on the dependent part (directory walks,
+// i128 arithmetic, atomics) and holds the tile's stage until the slowest chain is done (profiles/r1_q9.md: 9.4 ms for a
+// 1.7 ms scan).  Instead the scan COPIES each survivor's operands (NW 32-bit words) into a CTA-wide queue in shared memory;
+// whenever the queue holds a CTA's worth, every thread takes one entry: kBlock independent chains in flight, all lanes busy.
+template <int NW>
+struct SurvivorQueue {
+   static constexpr int kCap = kBlock + kRowsPerThreadStar * kBlock; // a drain leaves < kBlock entries; one tile adds <= its rows
+   int32_t w[NW][kCap];
+   int count;
+   __device__ __forceinline__ int claim() { return atomicAdd(&count, 1); }
+   __device__ __forceinline__ void put64(int word, int q, int64_t v) {
+      w[word][q] = (int32_t) (uint32_t) (uint64_t) v;
+      w[word + 1][q] = (int32_t) (uint32_t) ((uint64_t) v >> 32);
+   }
+   __device__ __forceinline__ int64_t get64(int word, int q) const { return (int64_t) (((uint64_t) (uint32_t) w[word + 1][q] << 32) | (uint32_t) w[word][q]); }
+};
+// Called by every thread of the CTA after a barrier that published the pushes.  Processes entries kBlock at a time until
+// fewer than kBlock are left (all == false) or none (all == true, at the end of the kernel).
+template <int NW, class Fn>
+__device__ __forceinline__ void drainQueue(SurvivorQueue<NW>& q, bool all, const Fn& process) {
+   int count = q.count;
+   if (!(count >= kBlock || (all && count > 0))) return;
+   while (count >= kBlock || (all && count > 0)) {
+      const int n = count < kBlock ? count : kBlock;
+      if ((int) threadIdx.x < n) process(count - n + (int) threadIdx.x);
+      count -= n;
+   }
+   __syncthreads(); // every thread read q.count and finished its entries
+   if (threadIdx.x == 0) q.count = count;
+   __syncthreads();
+}
+// CTA-local group table for the kernels that aggregate matched rows into a handful of groups (K4: 5 nations, K9: 175
+// nation-years): the reference's per-worker pre-aggregation cache (PreAggregationHashtable.cpp:46-60) as shared-memory
+// slots flushed once per CTA — 10^8 matched rows over 175 groups would otherwise serialise on 175 HBM addresses.
+constexpr int kLocalGroups = 256; // power of two; further groups go straight to the HBM table
+struct LocalGroups {
+   unsigned long long key[kLocalGroups];
+   unsigned long long acc[kLocalGroups][2];
+   __device__ __forceinline__ void init() {
+      for (int i = threadIdx.x; i < kLocalGroups; i += blockDim.x) {
+         key[i] = ~0ull;
+         acc[i][0] = acc[i][1] = 0;
+      }
+   }
+   // is64: the aggregate is a 64-bit SUM (wraps at 64 bits, hi stays 0) — LdbExprKind COL / ONE
+   __device__ __forceinline__ void add(const GroupTableDev& global, int32_t g0, int32_t g1, i128 v, bool is64);
+   __device__ __forceinline__ void flush(const GroupTableDev& global, bool is64);
+};
+
+__device__ __forceinline__ void LocalGroups::add(const GroupTableDev& global, int32_t g0, int32_t g1, i128 v, bool is64) {
+   const unsigned long long packed = packSlot(g0, g1);
+   if (packed != kEmptySlot) {
+      uint32_t s = (uint32_t) hashPair(g0, g1) & (kLocalGroups - 1);
+      for (int probes = 0; probes < kLocalGroups; probes++) {
+         unsigned long long cur = *((volatile unsigned long long*) &key[s]);
+         if (cur == kEmptySlot) cur = atomicCAS(&key[s], kEmptySlot, packed);
+         if (cur == kEmptySlot || cur == packed) {
+            if (is64) atomicAdd(&acc[s][0], (unsigned long long) v.lo);
+            else atomicAdd128(&acc[s][0], &acc[s][1], v);
+            return;
+         }
+         s = (s + 1) & (kLocalGroups - 1);
+      }
+   }
+   int32_t kk[2] = {g0, g1};
+   int slot = groupLookupOrInsert(global, kk);
+   if (slot >= 0) groupAtomicAdd(global, slot, 0, v, is64);
+}
+__device__ __forceinline__ void LocalGroups::flush(const GroupTableDev& global, bool is64) {
+   for (int i = threadIdx.x; i < kLocalGroups; i += blockDim.x) {
+      const unsigned long long k = key[i];
+      if (k == kEmptySlot) continue;
+      const i128 v{acc[i][0], (int64_t) acc[i][1]};
+      int32_t kk[2] = {(int32_t) (uint32_t) k, (int32_t) (uint32_t) (k >> 32)};
+      int slot = groupLookupOrInsert(global, kk);
+      if (slot >= 0) groupAtomicAdd(global, slot, 0, v, is64);
+   }
+}
+
 // one atomic per warp for the build-side entry count
 __device__ __forceinline__ void flushInsertCount(const JoinTableDev& t, unsigned long long local) {
    __syncwarp();
@@ -809,30 +890,61 @@ __device__ __forceinline__ void flushInsertCount(const JoinTableDev& t, unsigned
 // (subop.materialize + rt::GrowingBuffer::insert + rt::HashIndexedView::build; for the group-join
 //  the lookup_or_insert of the left input, RelAlgToSubOp.cpp:2682-2950)
 template <int DB>
-__global__ void __launch_bounds__(kThreads, 4) scanBuildKernel(const __grid_constant__ BuildParams p) {
+__global__ void __launch_bounds__(kBlock, 4) scanBuildKernel(const __grid_constant__ BuildParams p) {
    constexpr bool IN = true; // latency-bound kernels keep the IN path in
    __shared__ __align__(8) TileBarriers barsStorage;
+   __shared__ SurvivorQueue<5> queue; // {probe key, build key, own payload, side0, side1}
    TileBarriers* bars = &barsStorage;
+   if (threadIdx.x == 0) queue.count = 0;
+   __syncthreads();
    unsigned long long inserted = 0;
-   forEachRow<kRowsPerThreadProbe, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
-      if (!(valid && evalFilters<IN>(p.src.filters, tile, lr, row))) return;
-      const int32_t key = tile.i32(p.keyStage, lr);
-      auto insert = [&](int32_t payload) {
-         int64_t slot = joinInsert(p.sink, key, payload);
-         if (slot >= 0) {
-            inserted++;
-            int32_t* lanes = (int32_t*) (p.sink.base + (uint64_t) slot * 32 + 8); // side0, side1 of the 32-byte entry
-            for (int k = 0; k < p.nSide; k++) lanes[k] = tile.i32(p.sideStage[k], lr);
+   auto insert = [&](int32_t key, int32_t payload, int32_t side0, int32_t side1) {
+      int64_t slot = joinInsert(p.sink, key, payload);
+      if (slot >= 0) {
+         inserted++;
+         int32_t* lanes = (int32_t*) (p.sink.base + (uint64_t) slot * 32 + 8); // side0, side1 of the 32-byte entry
+         if (p.nSide > 0) lanes[0] = side0;
+         if (p.nSide > 1) lanes[1] = side1;
+      }
+   };
+   auto process = [&](int q) { // a queued row: walk the parent's directory, insert once per match
+      const int32_t probeKey = queue.w[0][q];
+      joinProbeSlots(p.probe, probeKey, hashI32(probeKey), [&](int64_t, int32_t parentPayload) {
+         insert(queue.w[1][q], p.payloadStage >= 0 ? queue.w[2][q] : (int32_t) (parentPayload & (p.probe.stride == 32 ? 0x7fffffff : -1)), queue.w[3][q], queue.w[4][q]);
+      });
+   };
+   forEachTileUniform<kRowsPerThreadStar, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+#pragma unroll
+      for (int j = 0; j < kRowsPerThreadStar; j++) {
+         const int lrRaw = j * kBlock + threadIdx.x;
+         const bool valid = lrRaw < rows;
+         const int lr = valid ? lrRaw : 0;
+         const bool ok = valid && evalFilters<IN>(p.src.filters, tile, lr, rowBase + lr);
+         const int32_t key = tile.i32(p.keyStage, lr);
+         int32_t ownPayload = p.payloadStage >= 0 ? tile.i32(p.payloadStage, lr) : 0;
+         if (p.payloadKind == PAYLOAD_YEAR_OF_DATE32) ownPayload = yearOfDays(ownPayload); // extract(year from <date32 column>)
+         const int32_t side0 = p.nSide > 0 ? tile.i32(p.sideStage[0], lr) : 0, side1 = p.nSide > 1 ? tile.i32(p.sideStage[1], lr) : 0;
+         if (!p.hasProbe) { // plain build: every row that passed the filters inserts — nothing to compact
+            if (ok) insert(key, ownPayload, side0, side1);
+            continue;
          }
-      };
-      int32_t ownPayload = p.payloadStage >= 0 ? tile.i32(p.payloadStage, lr) : 0;
-      if (p.payloadKind == PAYLOAD_YEAR_OF_DATE32) ownPayload = yearOfDays(ownPayload); // extract(year from <date32 column>)
+         const int32_t probeKey = tile.i32(p.probeKeyStage, lr);
+         if (bloomPrefetch(p.probe, probeKey, ok).mayContain()) {
+            const int q = queue.claim();
+            queue.w[0][q] = probeKey;
+            queue.w[1][q] = key;
+            queue.w[2][q] = ownPayload;
+            queue.w[3][q] = side0;
+            queue.w[4][q] = side1;
+         }
+      }
       if (p.hasProbe) {
-         joinProbe(p.probe, tile.i32(p.probeKeyStage, lr), [&](int64_t, int32_t parentPayload) { insert(p.payloadStage >= 0 ? ownPayload : parentPayload); });
-      } else {
-         insert(ownPayload);
+         __syncthreads();
+         drainQueue(queue, false, process);
       }
    });
+   __syncthreads();
+   drainQueue(queue, true, process);
    flushInsertCount(p.sink, inserted);
 }
 // composite-key build: {key, key2} → int64 payload (a decimal(p<19) column's value or an int32 column), optionally
@@ -843,7 +955,7 @@ __global__ void __launch_bounds__(kThreads, 4) scanBuildPairKernel(const __grid_
    __shared__ __align__(8) TileBarriers barsStorage;
    TileBarriers* bars = &barsStorage;
    unsigned long long inserted = 0;
-   forEachRow<kRowsPerThreadProbe, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
+   forEachRow<kRowsPerThreadStar, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int lr, int64_t row, bool valid) {
       if (!(valid && evalFilters<IN>(p.src.filters, tile, lr, row))) return;
       const int32_t k0 = tile.i32(p.keyStage, lr), k1 = tile.i32(p.keyStage2, lr);
       int64_t payload = 0;
@@ -871,11 +983,11 @@ void launchScanBuild(const BuildParams& p, int smCount, cudaStream_t s) {
       return;
    }
    if (p.src.cols.decBytes == 8) {
-      int grid = persistentGrid(scanBuildKernel<8>, p.src.cols, p.src.nRows, smCount, &dyn);
-      scanBuildKernel<8><<<grid, kThreads, dyn, s>>>(p);
+      int grid = persistentGrid(scanBuildKernel<8>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+      scanBuildKernel<8><<<grid, kBlock, dyn, s>>>(p);
    } else {
-      int grid = persistentGrid(scanBuildKernel<16>, p.src.cols, p.src.nRows, smCount, &dyn);
-      scanBuildKernel<16><<<grid, kThreads, dyn, s>>>(p);
+      int grid = persistentGrid(scanBuildKernel<16>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+      scanBuildKernel<16><<<grid, kBlock, dyn, s>>>(p);
    }
 }
 
@@ -1000,40 +1112,46 @@ void launchScanMaterialize(const MaterializeParams& p, int smCount, cudaStream_t
 // takes a per-entry spin lock (SubOpToControlFlow.cpp:4218-4251, EntryLock.cpp:9-25) or an
 // atomic_rmw; here the i128 SUM is two 64-bit atomics with carry (exact, order independent).
 template <int NV, int DB>
-__global__ void __launch_bounds__(kThreads, 4) scanProbeAggKernel(const __grid_constant__ ProbeAggParams p) {
+__global__ void __launch_bounds__(kBlock, 4) scanProbeAggKernel(const __grid_constant__ ProbeAggParams p) {
    constexpr bool IN = true;
    __shared__ __align__(8) TileBarriers barsStorage;
+   __shared__ SurvivorQueue<1 + 2 * NV> queue; // {probe key, value operands}
    TileBarriers* bars = &barsStorage;
+   if (threadIdx.x == 0) queue.count = 0;
+   __syncthreads();
    const int64_t one = 100;
-   forEachTile<kRowsPerThreadProbe, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
-      int32_t key[kRowsPerThreadProbe];
-      int lrs[kRowsPerThreadProbe];
-      BloomProbe bp[kRowsPerThreadProbe];
-      // phase A: filters + hash + Bloom load of every row of this thread (all loads in flight together)
+   auto process = [&](int q) {
+      const int32_t key = queue.w[0][q];
+      int64_t vals[NV];
 #pragma unroll
-      for (int j = 0; j < kRowsPerThreadProbe; j++) {
-         const int lr = j * kBlock + threadIdx.x;
-         const bool valid = lr < rows;
-         lrs[j] = valid ? lr : 0;
-         const bool ok = valid && evalFilters<IN>(p.src.filters, tile, lrs[j], rowBase + lrs[j]);
-         key[j] = tile.i32(p.probeKeyStage, lrs[j]);
-         bp[j] = bloomPrefetch(p.table, key[j], ok);
+      for (int c = 0; c < NV; c++) vals[c] = queue.get64(1 + 2 * c, q);
+      const i128 v = evalAggDyn(p.agg, vals, one);
+      joinProbeSlots(p.table, key, hashI32(key), [&](int64_t slot, int32_t payloadWord) {
+         uint8_t* entry = p.table.base + (uint64_t) slot * 32;
+         atomicAdd128((unsigned long long*) (entry + 16), (unsigned long long*) (entry + 24), v);
+         if (payloadWord >= 0) ((int32_t*) entry)[1] = payloadWord | (int32_t) 0x80000000; // marker: idempotent plain store, same sector
+      });
+   };
+   forEachTileUniform<kRowsPerThreadStar, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+#pragma unroll
+      for (int j = 0; j < kRowsPerThreadStar; j++) { // filters + hash + Bloom word; survivors join the queue
+         const int lrRaw = j * kBlock + threadIdx.x;
+         const bool valid = lrRaw < rows;
+         const int lr = valid ? lrRaw : 0;
+         const bool ok = valid && evalFilters<IN>(p.src.filters, tile, lr, rowBase + lr);
+         const int32_t key = tile.i32(p.probeKeyStage, lr);
+         if (bloomPrefetch(p.table, key, ok).mayContain()) {
+            const int q = queue.claim();
+            queue.w[0][q] = key;
+#pragma unroll
+            for (int c = 0; c < NV; c++) queue.put64(1 + 2 * c, q, tile.lo64(p.valueStage[c], lr));
+         }
       }
-      // phase B: the few survivors walk the directory and add into the shared entry
-#pragma unroll
-      for (int j = 0; j < kRowsPerThreadProbe; j++) {
-         if (!bp[j].mayContain()) continue;
-         joinProbeSlots(p.table, key[j], bp[j].h, [&](int64_t slot, int32_t payloadWord) {
-            int64_t vals[NV];
-#pragma unroll
-            for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lrs[j]);
-            i128 v = evalAggDyn(p.agg, vals, one);
-            uint8_t* entry = p.table.base + (uint64_t) slot * 32;
-            atomicAdd128((unsigned long long*) (entry + 16), (unsigned long long*) (entry + 24), v);
-            if (payloadWord >= 0) ((int32_t*) entry)[1] = payloadWord | (int32_t) 0x80000000; // marker: idempotent plain store, same sector
-         });
-      }
+      __syncthreads();
+      drainQueue(queue, false, process);
    });
+   __syncthreads();
+   drainQueue(queue, true, process);
 }
 bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, const char** why) {
    int nv = p.agg.expr == LDB_EXPR_COL ? 1 : p.agg.expr == LDB_EXPR_MUL_1MINUS_1PLUS ? 3 : 2;
@@ -1044,27 +1162,27 @@ bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, co
    size_t dyn;
    if (nv == 1) {
       if (p.src.cols.decBytes == 8) {
-         int grid = persistentGrid(scanProbeAggKernel<1, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbeAggKernel<1, 8><<<grid, kThreads, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbeAggKernel<1, 8>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+         scanProbeAggKernel<1, 8><<<grid, kBlock, dyn, s>>>(p);
       } else {
-         int grid = persistentGrid(scanProbeAggKernel<1, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbeAggKernel<1, 16><<<grid, kThreads, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbeAggKernel<1, 16>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+         scanProbeAggKernel<1, 16><<<grid, kBlock, dyn, s>>>(p);
       }
    } else if (nv == 2) {
       if (p.src.cols.decBytes == 8) {
-         int grid = persistentGrid(scanProbeAggKernel<2, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbeAggKernel<2, 8><<<grid, kThreads, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbeAggKernel<2, 8>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+         scanProbeAggKernel<2, 8><<<grid, kBlock, dyn, s>>>(p);
       } else {
-         int grid = persistentGrid(scanProbeAggKernel<2, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbeAggKernel<2, 16><<<grid, kThreads, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbeAggKernel<2, 16>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+         scanProbeAggKernel<2, 16><<<grid, kBlock, dyn, s>>>(p);
       }
    } else {
       if (p.src.cols.decBytes == 8) {
-         int grid = persistentGrid(scanProbeAggKernel<3, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbeAggKernel<3, 8><<<grid, kThreads, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbeAggKernel<3, 8>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+         scanProbeAggKernel<3, 8><<<grid, kBlock, dyn, s>>>(p);
       } else {
-         int grid = persistentGrid(scanProbeAggKernel<3, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbeAggKernel<3, 16><<<grid, kThreads, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbeAggKernel<3, 16>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+         scanProbeAggKernel<3, 16><<<grid, kBlock, dyn, s>>>(p);
       }
    }
    return true;
@@ -1074,47 +1192,58 @@ bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, co
 // scan → probe A on keyA → probe B on keyB → keep rows whose payloads agree (the composite join key
 // (l_suppkey, c_nationkey) = (s_suppkey, s_nationkey) of Q5) → group by that payload → SUM.
 template <int NV, int DB>
-__global__ void __launch_bounds__(kThreads, 4) scanProbe2GroupByKernel(const __grid_constant__ Probe2GroupByParams p) {
+__global__ void __launch_bounds__(kBlock, 4) scanProbe2GroupByKernel(const __grid_constant__ Probe2GroupByParams p) {
    constexpr bool IN = true;
    __shared__ __align__(8) TileBarriers barsStorage;
+   __shared__ SurvivorQueue<2 + 2 * NV> queue; // {key A, key B, value operands}
+   __shared__ LocalGroups groups;
    TileBarriers* bars = &barsStorage;
+   groups.init();
+   if (threadIdx.x == 0) queue.count = 0;
+   __syncthreads();
    const int64_t one = 100;
-   forEachTile<kRowsPerThreadProbe, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
-      int32_t key[kRowsPerThreadProbe];
-      int lrs[kRowsPerThreadProbe];
-      BloomProbe bp[kRowsPerThreadProbe];
+   const bool is64 = p.agg.expr == LDB_EXPR_COL || p.agg.expr == LDB_EXPR_ONE;
+   const int32_t payloadMask = p.tableA.stride == 32 || p.tableB.stride == 32 ? 0x7fffffff : -1;
+   auto process = [&](int q) { // the two directory walks are independent: both first slots are loaded before either is consumed
+      const int32_t keyA = queue.w[0][q], keyB = queue.w[1][q];
+      const uint64_t hA = hashI32(keyA), hB = hashI32(keyB);
+      const unsigned long long eA = __ldg(slotPtr(p.tableA, hA & p.tableA.mask)), eB = __ldg(slotPtr(p.tableB, hB & p.tableB.mask));
+      int64_t vals[NV];
 #pragma unroll
-      for (int j = 0; j < kRowsPerThreadProbe; j++) { // phase A: Bloom filter of table A for every row (loads in flight together)
-         const int lr = j * kBlock + threadIdx.x;
-         const bool valid = lr < rows;
-         lrs[j] = valid ? lr : 0;
-         const bool ok = valid && evalFilters<IN>(p.src.filters, tile, lrs[j], rowBase + lrs[j]);
-         key[j] = tile.i32(p.keyStageA, lrs[j]);
-         bp[j] = bloomPrefetch(p.tableA, key[j], ok);
-      }
-      int32_t keyB[kRowsPerThreadProbe];
-      BloomProbe bpB[kRowsPerThreadProbe];
-#pragma unroll
-      for (int j = 0; j < kRowsPerThreadProbe; j++) { // phase B: survivors consult table B's filter (the plan puts the smaller table first)
-         keyB[j] = tile.i32(p.keyStageB, lrs[j]);
-         bpB[j] = bloomPrefetch(p.tableB, keyB[j], bp[j].mayContain());
-      }
-#pragma unroll
-      for (int j = 0; j < kRowsPerThreadProbe; j++) { // phase C: the few rows both filters let through walk the directories
-         if (!bpB[j].mayContain()) continue;
-         joinProbeSlots(p.tableA, key[j], bp[j].h, [&](int64_t, int32_t payA) {
-            joinProbeSlots(p.tableB, keyB[j], bpB[j].h, [&](int64_t, int32_t payB) {
-               if (((payA ^ payB) & (p.tableA.stride == 32 || p.tableB.stride == 32 ? 0x7fffffff : -1)) != 0) return;
-               int64_t vals[NV];
-#pragma unroll
-               for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lrs[j]);
-               int32_t kk[2] = {payB, 0};
-               int slot = groupLookupOrInsert(p.groups, kk);
-               if (slot >= 0) groupAtomicAdd(p.groups, slot, 0, evalAggDyn(p.agg, vals, one), p.agg.expr == LDB_EXPR_COL || p.agg.expr == LDB_EXPR_ONE);
-            });
+      for (int c = 0; c < NV; c++) vals[c] = queue.get64(2 + 2 * c, q);
+      const i128 v = evalAggDyn(p.agg, vals, one);
+      joinProbeFrom(p.tableA, keyA, hA, eA, [&](int32_t payA) {
+         joinProbeFrom(p.tableB, keyB, hB, eB, [&](int32_t payB) {
+            if (((payA ^ payB) & payloadMask) != 0) return;
+            groups.add(p.groups, payB, 0, v, is64);
          });
+      });
+   };
+   forEachTileUniform<kRowsPerThreadStar, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+#pragma unroll
+      for (int j = 0; j < kRowsPerThreadStar; j++) {
+         const int lrRaw = j * kBlock + threadIdx.x;
+         const bool valid = lrRaw < rows;
+         const int lr = valid ? lrRaw : 0;
+         const bool ok = valid && evalFilters<IN>(p.src.filters, tile, lr, rowBase + lr);
+         const int32_t keyA = tile.i32(p.keyStageA, lr), keyB = tile.i32(p.keyStageB, lr);
+         // table A's filter first (the plan puts the smaller table there), B's only for A's survivors
+         const bool passA = bloomPrefetch(p.tableA, keyA, ok).mayContain();
+         if (bloomPrefetch(p.tableB, keyB, passA).mayContain()) {
+            const int q = queue.claim();
+            queue.w[0][q] = keyA;
+            queue.w[1][q] = keyB;
+#pragma unroll
+            for (int c = 0; c < NV; c++) queue.put64(2 + 2 * c, q, tile.lo64(p.valueStage[c], lr));
+         }
       }
+      __syncthreads();
+      drainQueue(queue, false, process);
    });
+   __syncthreads();
+   drainQueue(queue, true, process);
+   __syncthreads();
+   groups.flush(p.groups, is64);
 }
 bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStream_t s, const char** why) {
    int nv = p.agg.expr == LDB_EXPR_COL ? 1 : p.agg.expr == LDB_EXPR_MUL_1MINUS_1PLUS ? 3 : 2;
@@ -1125,27 +1254,27 @@ bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStre
    size_t dyn;
    if (nv == 1) {
       if (p.src.cols.decBytes == 8) {
-         int grid = persistentGrid(scanProbe2GroupByKernel<1, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbe2GroupByKernel<1, 8><<<grid, kThreads, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbe2GroupByKernel<1, 8>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+         scanProbe2GroupByKernel<1, 8><<<grid, kBlock, dyn, s>>>(p);
       } else {
-         int grid = persistentGrid(scanProbe2GroupByKernel<1, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbe2GroupByKernel<1, 16><<<grid, kThreads, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbe2GroupByKernel<1, 16>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+         scanProbe2GroupByKernel<1, 16><<<grid, kBlock, dyn, s>>>(p);
       }
    } else if (nv == 2) {
       if (p.src.cols.decBytes == 8) {
-         int grid = persistentGrid(scanProbe2GroupByKernel<2, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbe2GroupByKernel<2, 8><<<grid, kThreads, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbe2GroupByKernel<2, 8>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+         scanProbe2GroupByKernel<2, 8><<<grid, kBlock, dyn, s>>>(p);
       } else {
-         int grid = persistentGrid(scanProbe2GroupByKernel<2, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbe2GroupByKernel<2, 16><<<grid, kThreads, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbe2GroupByKernel<2, 16>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+         scanProbe2GroupByKernel<2, 16><<<grid, kBlock, dyn, s>>>(p);
       }
    } else {
       if (p.src.cols.decBytes == 8) {
-         int grid = persistentGrid(scanProbe2GroupByKernel<3, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbe2GroupByKernel<3, 8><<<grid, kThreads, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbe2GroupByKernel<3, 8>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+         scanProbe2GroupByKernel<3, 8><<<grid, kBlock, dyn, s>>>(p);
       } else {
-         int grid = persistentGrid(scanProbe2GroupByKernel<3, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbe2GroupByKernel<3, 16><<<grid, kThreads, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbe2GroupByKernel<3, 16>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+         scanProbe2GroupByKernel<3, 16><<<grid, kBlock, dyn, s>>>(p);
       }
    }
    return true;
@@ -1156,113 +1285,58 @@ bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStre
 // int32 payloads → SUM(a * (1 - b) - c * d), c = P's int64 payload.  The reference's per-worker pre-aggregation
 // cache (PreAggregationHashtable.cpp:46-60) becomes a per-CTA shared-memory table flushed once per CTA: ~10^8 matched
 // rows over 175 groups would otherwise serialise on 175 HBM addresses.
-constexpr int kStarGroups = 256; // CTA-local group slots (power of two); further groups go straight to the HBM table
-// Only ~5 % of the rows survive P's Bloom filter, i.e. ~2 lanes per warp.  Handled in place, the dependent part (three
-// random directory walks, two i128 products, the group update) ran with ONE active lane per instruction and held the
-// tile's stage until the slowest chain finished: 9.4 ms for a 1.7 ms scan (profiles/r1_q9.md).  So the scan and the
-// probes are decoupled inside the kernel: survivors are copied into a CTA-wide queue in shared memory, and whenever the
-// queue holds a full CTA's worth, every thread takes one entry — 256 independent chains in flight, all lanes busy.
-constexpr int kStarQueue = kBlock + kRowsPerThreadStar * kBlock; // a drain leaves < kBlock entries; one tile adds <= tileRows
 template <int DB>
 __global__ void __launch_bounds__(kBlock, 4) scanStarProbeGroupByKernel(const __grid_constant__ StarProbeParams p) {
    constexpr bool IN = true;
    __shared__ __align__(8) TileBarriers barsStorage;
-   __shared__ unsigned long long sKey[kStarGroups];
-   __shared__ unsigned long long sAcc[kStarGroups][2];
-   __shared__ int64_t qA[kStarQueue], qB[kStarQueue], qD[kStarQueue];
-   __shared__ int32_t qK0[kStarQueue], qK1[kStarQueue], qKS[kStarQueue], qKO[kStarQueue];
-   __shared__ int qCount;
+   __shared__ SurvivorQueue<10> queue; // {k0, k1, kS, kO, a, b, d}
+   __shared__ LocalGroups groups;
    TileBarriers* bars = &barsStorage;
-   for (int i = threadIdx.x; i < kStarGroups; i += blockDim.x) {
-      sKey[i] = kEmptySlot;
-      sAcc[i][0] = sAcc[i][1] = 0;
-   }
-   if (threadIdx.x == 0) qCount = 0;
+   groups.init();
+   if (threadIdx.x == 0) queue.count = 0;
    __syncthreads();
    const int64_t one = 100;
-   auto groupAdd = [&](int32_t g0, int32_t g1, i128 v) {
-      const unsigned long long packed = packSlot(g0, g1);
-      if (packed != kEmptySlot) {
-         uint32_t s = (uint32_t) hashPair(g0, g1) & (kStarGroups - 1);
-         for (int probes = 0; probes < kStarGroups; probes++) {
-            unsigned long long cur = *((volatile unsigned long long*) &sKey[s]);
-            if (cur == kEmptySlot) cur = atomicCAS(&sKey[s], kEmptySlot, packed);
-            if (cur == kEmptySlot || cur == packed) {
-               atomicAdd128(&sAcc[s][0], &sAcc[s][1], v);
-               return;
-            }
-            s = (s + 1) & (kStarGroups - 1);
-         }
-      }
-      int32_t kk[2] = {g0, g1};
-      int slot = groupLookupOrInsert(p.groups, kk);
-      if (slot >= 0) groupAtomicAdd(p.groups, slot, 0, v, false);
-   };
    // the three probes of a row are independent of each other: their first slots are loaded together (S and O are
    // foreign-key probes that always hit, so their Bloom filters are not consulted)
-   auto processEntry = [&](int i) {
-      const int32_t k0 = qK0[i], k1 = qK1[i], kS = qKS[i], kO = qKO[i];
+   auto process = [&](int q) {
+      const int32_t k0 = queue.w[0][q], k1 = queue.w[1][q], kS = queue.w[2][q], kO = queue.w[3][q];
       const uint64_t hP = hashPair(k0, k1), hS = hashI32(kS), hO = hashI32(kO);
       const ulonglong2 eP = __ldg((const ulonglong2*) slotPtr(p.tableP, hP & p.tableP.mask));
       const unsigned long long eS = __ldg(slotPtr(p.tableS, hS & p.tableS.mask));
       const unsigned long long eO = __ldg(slotPtr(p.tableO, hO & p.tableO.mask));
-      const int64_t a = qA[i], b = qB[i], d = qD[i];
+      const int64_t a = queue.get64(4, q), b = queue.get64(6, q), d = queue.get64(8, q);
       pairProbeFrom(p.tableP, k0, k1, hP, eP, [&](int64_t c) {
          joinProbeFrom(p.tableS, kS, hS, eS, [&](int32_t g0) {
-            joinProbeFrom(p.tableO, kO, hO, eO, [&](int32_t g1) { groupAdd(g0, g1, sub128(mul64x64(a, one - b), mul64x64(c, d))); });
+            joinProbeFrom(p.tableO, kO, hO, eO, [&](int32_t g1) { groups.add(p.groups, g0, g1, sub128(mul64x64(a, one - b), mul64x64(c, d)), false); });
          });
       });
    };
-   // called by every thread after a barrier that published the pushes; leaves < kBlock entries unless `all`
-   auto drain = [&](bool all) {
-      int count = qCount;
-      if (!(count >= kBlock || (all && count > 0))) return;
-      while (count >= kBlock || (all && count > 0)) {
-         const int n = count < kBlock ? count : kBlock;
-         if ((int) threadIdx.x < n) processEntry(count - n + (int) threadIdx.x);
-         count -= n;
-      }
-      __syncthreads(); // every thread read qCount and finished its entries
-      if (threadIdx.x == 0) qCount = count;
-      __syncthreads();
-   };
    forEachTileUniform<kRowsPerThreadStar, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
-      BloomProbe bp[kRowsPerThreadStar];
-      int lrs[kRowsPerThreadStar];
 #pragma unroll
-      for (int j = 0; j < kRowsPerThreadStar; j++) { // filters + P's Bloom word for every row of the thread (loads in flight together)
-         const int lr = j * kBlock + threadIdx.x;
-         const bool valid = lr < rows;
-         lrs[j] = valid ? lr : 0;
-         const bool ok = valid && evalFilters<IN>(p.src.filters, tile, lrs[j], rowBase + lrs[j]);
-         bp[j] = pairBloomPrefetch(p.tableP, tile.i32(p.keyStageP0, lrs[j]), tile.i32(p.keyStageP1, lrs[j]), ok);
-      }
-#pragma unroll
-      for (int j = 0; j < kRowsPerThreadStar; j++) {
-         if (!bp[j].mayContain()) continue;
-         const int q = atomicAdd(&qCount, 1), lr = lrs[j];
-         qK0[q] = tile.i32(p.keyStageP0, lr);
-         qK1[q] = tile.i32(p.keyStageP1, lr);
-         qKS[q] = tile.i32(p.keyStageS, lr);
-         qKO[q] = tile.i32(p.keyStageO, lr);
-         qA[q] = tile.lo64(p.valueStage[0], lr);
-         qB[q] = tile.lo64(p.valueStage[1], lr);
-         qD[q] = tile.lo64(p.valueStage[2], lr);
+      for (int j = 0; j < kRowsPerThreadStar; j++) { // filters + P's Bloom word; survivors join the queue
+         const int lrRaw = j * kBlock + threadIdx.x;
+         const bool valid = lrRaw < rows;
+         const int lr = valid ? lrRaw : 0;
+         const bool ok = valid && evalFilters<IN>(p.src.filters, tile, lr, rowBase + lr);
+         const int32_t k0 = tile.i32(p.keyStageP0, lr), k1 = tile.i32(p.keyStageP1, lr);
+         if (pairBloomPrefetch(p.tableP, k0, k1, ok).mayContain()) {
+            const int q = queue.claim();
+            queue.w[0][q] = k0;
+            queue.w[1][q] = k1;
+            queue.w[2][q] = tile.i32(p.keyStageS, lr);
+            queue.w[3][q] = tile.i32(p.keyStageO, lr);
+            queue.put64(4, q, tile.lo64(p.valueStage[0], lr));
+            queue.put64(6, q, tile.lo64(p.valueStage[1], lr));
+            queue.put64(8, q, tile.lo64(p.valueStage[2], lr));
+         }
       }
       __syncthreads();
-      drain(false);
+      drainQueue(queue, false, process);
    });
    __syncthreads();
-   drain(true);
+   drainQueue(queue, true, process);
    __syncthreads();
-   for (int i = threadIdx.x; i < kStarGroups; i += blockDim.x) {
-      const unsigned long long key = sKey[i];
-      if (key == kEmptySlot) continue;
-      const i128 v{sAcc[i][0], (int64_t) sAcc[i][1]};
-      int32_t kk[2] = {(int32_t) (uint32_t) key, (int32_t) (uint32_t) (key >> 32)};
-      int slot = groupLookupOrInsert(p.groups, kk);
-      if (slot >= 0) groupAtomicAdd(p.groups, slot, 0, v, false);
-   }
+   groups.flush(p.groups, false);
 }
 void launchScanStarProbeGroupBy(const StarProbeParams& p, int smCount, cudaStream_t s) {
    size_t dyn;
