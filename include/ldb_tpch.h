@@ -59,6 +59,8 @@ typedef struct LdbQ9Row {
    int32_t n_nationkey, o_year; /* n_name is resolved from the nation table at materialisation (host) */
    LdbI128 sum_profit;          /* decimal(34,4) raw: l_extendedprice * (1 - l_discount) - ps_supplycost * l_quantity, summed */
 } LdbQ9Row;
+int ldb_tpch_q9_partial(LdbContext* ctx, const LdbTpchTables* t, const char* name_contains, LdbState** group_state, LdbError* err);
+int ldb_tpch_q9_finish(LdbState* group_state, LdbQ9Row* rows /* max_rows */, int32_t max_rows, int32_t* n_rows, LdbError* err);
 int ldb_tpch_q9(LdbContext* ctx, const LdbTpchTables* t, const char* name_contains, LdbQ9Row* rows /* max_rows */, int32_t max_rows, int32_t* n_rows, LdbError* err);
 
 #ifdef __cplusplus

@@ -158,6 +158,8 @@ SIGNATURES = {
     "ldb_tpch_q1_finish": (C.c_int, [_P, C.POINTER(Q1Row), C.c_int32, C.POINTER(C.c_int32), _E]),
     "ldb_tpch_q3": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.c_char_p, C.POINTER(Q3Row), C.POINTER(C.c_int32), _E]),
     "ldb_tpch_q5": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(Q5Row), C.POINTER(C.c_int32), _E]),
+    "ldb_tpch_q9_partial": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.POINTER(_P), _E]),
+    "ldb_tpch_q9_finish": (C.c_int, [_P, C.POINTER(Q9Row), C.c_int32, C.POINTER(C.c_int32), _E]),
     "ldb_tpch_q9": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.POINTER(Q9Row), C.c_int32, C.POINTER(C.c_int32), _E]),
 }
 

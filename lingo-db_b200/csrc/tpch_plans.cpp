@@ -351,7 +351,10 @@ int ldb_tpch_q5(LdbContext* ctx, const LdbTpchTables* t, const char* regionName,
 // part(p_name like '%X%') → partsupp ⋈ part keyed (ps_partkey, ps_suppkey) → supplier, orders(→ year) → lineitem star probe.
 // p_partkey = l_partkey follows from ps_partkey = l_partkey and p_partkey = ps_partkey (the partsupp table only holds
 // parts that passed the LIKE), so the lineitem pipeline probes three tables, not four.
-int ldb_tpch_q9(LdbContext* ctx, const LdbTpchTables* t, const char* nameContains, LdbQ9Row* rows, int32_t maxRows, int32_t* nRows, LdbError* err) {
+// _partial runs every pipeline over the tables it is given and returns the (nation, year) group state; with lineitem and
+// orders sharded by the same order range (the join is co-partitioned) and the small sides replicated, each GPU of a
+// multi-GPU run calls it on its shard, the group images are all-gathered + merged (K7), then _finish materialises.
+int ldb_tpch_q9_partial(LdbContext* ctx, const LdbTpchTables* t, const char* nameContains, LdbState** state, LdbError* err) {
    return guarded(err, [&] {
       LdbError e;
       StateGuard g;
@@ -398,7 +401,6 @@ int ldb_tpch_q9(LdbContext* ctx, const LdbTpchTables* t, const char* nameContain
       LdbState* ord = buildJoin(ctx, g, dor, nOrd + 1024, LDB_JOIN_UNIQUE | LDB_JOIN_NO_BLOOM, 0, 0);
       LdbState* groups = nullptr;
       check(ldb_gpu_groupby_create(ctx, 2, 1, 1024, &groups, &e), e);
-      g.own(groups);
       LdbPipelineDesc dl{};
       dl.kind = LDB_PIPE_SCAN_STAR_PROBE_GROUPBY;
       dl.source = t->lineitem;
@@ -413,7 +415,17 @@ int ldb_tpch_q9(LdbContext* ctx, const LdbTpchTables* t, const char* nameContain
       dl.n_aggs = 1;
       dl.aggs[0] = agg(LDB_EXPR_MUL_1MINUS_MINUS_PAYMUL, "l_extendedprice", "l_discount", "l_quantity");
       dl.sink = groups;
-      check(ldb_gpu_run_pipeline(ctx, &dl, &e), e);
+      int rc = ldb_gpu_run_pipeline(ctx, &dl, &e);
+      if (rc != LDB_OK) {
+         ldb_gpu_state_destroy(groups);
+         throw PlanError(e);
+      }
+      *state = groups; // the join tables die here (StateGuard); the caller owns the group state
+   });
+}
+int ldb_tpch_q9_finish(LdbState* groups, LdbQ9Row* rows, int32_t maxRows, int32_t* nRows, LdbError* err) {
+   return guarded(err, [&] {
+      LdbError e;
       std::vector<LdbGroupRow> gr(1024);
       int32_t n = 0;
       check(ldb_gpu_groupby_read(groups, gr.data(), 1024, &n, &e), e);
@@ -424,6 +436,16 @@ int ldb_tpch_q9(LdbContext* ctx, const LdbTpchTables* t, const char* nameContain
       if ((int) out.size() > maxRows) throw std::runtime_error("Q9 result has more rows than max_rows");
       for (size_t i = 0; i < out.size(); i++) rows[i] = out[i];
       *nRows = (int32_t) out.size();
+   });
+}
+int ldb_tpch_q9(LdbContext* ctx, const LdbTpchTables* t, const char* nameContains, LdbQ9Row* rows, int32_t maxRows, int32_t* nRows, LdbError* err) {
+   return guarded(err, [&] {
+      LdbError e;
+      StateGuard g;
+      LdbState* s = nullptr;
+      check(ldb_tpch_q9_partial(ctx, t, nameContains, &s, &e), e);
+      g.own(s);
+      check(ldb_tpch_q9_finish(s, rows, maxRows, nRows, &e), e);
    });
 }
 

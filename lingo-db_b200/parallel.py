@@ -112,6 +112,18 @@ def allgather_merge_state(ctx, state, world: int, rank: int, bufs: dict):
     capi.check(L.ldb_gpu_groupby_merge_exported(state, C.c_void_p(bufs["recv"].data_ptr()), world, rank, C.byref(e)), e)
 
 
+def q9_sharded(ctx, tpch, world: int, rank: int, bufs: dict, name_contains: str = "green"):
+    """Q9 with lineitem ⋈ orders co-partitioned by order range (each rank's `tpch` holds its lineitem/orders shard and
+    replicas of part, partsupp, supplier, nation): per-rank pipelines → all-gather of the group-table images → K7 merge."""
+    from . import runtime
+    st = tpch.q9_partial(name_contains)
+    if world > 1:
+        allgather_merge_state(ctx, st, world, rank, bufs)
+    rows = tpch.q9_finish(st)
+    runtime.state_destroy(ctx, st)
+    return rows
+
+
 # ------------------------------------------------------------------------------------------------ Q5 with repartition
 def _all_to_all(cols, send_offsets, world, dev):
     """Exchange per-destination contiguous blocks (K6 output) of several columns; returns received columns + row count."""

@@ -200,11 +200,24 @@ class Tpch:
         return [{"l_orderkey": r.l_orderkey, "revenue": r.revenue.value(), "o_orderdate": r.o_orderdate, "o_shippriority": r.o_shippriority}
                 for r in rows[: n.value]]
 
+    def _q9_rows(self, rows, n):
+        out = [{"nation": self.nation_names[r.n_nationkey], "o_year": r.o_year, "sum_profit": r.sum_profit.value()} for r in rows[:n]]
+        return sorted(out, key=lambda r: (r["nation"], -r["o_year"]))  # order by nation, o_year desc
+
     def q9(self, name_contains="green"):
         rows, n, e = (capi.Q9Row * 1024)(), C.c_int32(), Error()
         check(self.ctx.L.ldb_tpch_q9(self.ctx.h, C.byref(self.t), name_contains.encode(), rows, 1024, C.byref(n), C.byref(e)), e)
-        out = [{"nation": self.nation_names[r.n_nationkey], "o_year": r.o_year, "sum_profit": r.sum_profit.value()} for r in rows[: n.value]]
-        return sorted(out, key=lambda r: (r["nation"], -r["o_year"]))  # order by nation, o_year desc
+        return self._q9_rows(rows, n.value)
+
+    def q9_partial(self, name_contains="green") -> C.c_void_p:
+        s, e = C.c_void_p(), Error()
+        check(self.ctx.L.ldb_tpch_q9_partial(self.ctx.h, C.byref(self.t), name_contains.encode(), C.byref(s), C.byref(e)), e)
+        return s
+
+    def q9_finish(self, state):
+        rows, n, e = (capi.Q9Row * 1024)(), C.c_int32(), Error()
+        check(self.ctx.L.ldb_tpch_q9_finish(state, rows, 1024, C.byref(n), C.byref(e)), e)
+        return self._q9_rows(rows, n.value)
 
     def q5(self, region_name="ASIA", date_ge="1994-01-01", date_lt="1995-01-01"):
         rows, n, e = (capi.Q5Row * 25)(), C.c_int32(), Error()

@@ -425,3 +425,35 @@ def test_q9_device_resident_matches_oracle(gpu_ctx, oracle):
     want, _ = oracle.q9(oh["part"], oh["supplier"], oh["lineitem"], oh["partsupp"], oh["orders"], oh["nation"])
     assert runtime.Tpch(gpu_ctx, tabs).q9() == want
     assert len(want) == 175
+
+
+def test_q9_sharded_partials_merge_to_the_whole(gpu_ctx, oracle):
+    """Multi-GPU Q9 shape on one GPU: two order-range shards (lineitem + orders co-partitioned, small sides replicated) →
+    per-shard group tables → export / merge_exported (what ranks do after the NCCL all-gather) → same rows as the oracle."""
+    import ctypes as C
+    import torch
+    from lingodb_b200 import capi, devgen, parallel, runtime
+    s = datagen.scale(0.05, seed=11)
+    cols = ["l_orderkey", "l_partkey", "l_suppkey", "l_quantity", "l_extendedprice", "l_discount"]
+    shared = {"supplier": devgen.supplier(gpu_ctx, s), "part": devgen.part(gpu_ctx, s), "partsupp": devgen.partsupp(gpu_ctx, s), **devgen.small_tables(gpu_ctx)}
+    states, tps = [], []
+    for r in range(2):
+        o_lo, o_hi, r_lo, r_hi = parallel.order_range(s, r, 2)
+        tabs = dict(shared, lineitem=devgen.lineitem(gpu_ctx, s, cols, row_begin=r_lo, n_rows=r_hi - r_lo), orders=devgen.orders(gpu_ctx, s, row_begin=o_lo, n_rows=o_hi - o_lo))
+        tps.append(runtime.Tpch(gpu_ctx, tabs))
+        states.append(tps[-1].q9_partial())
+    L = gpu_ctx.L
+    nbytes = int(L.ldb_gpu_groupby_export_bytes(states[0]))
+    recv = torch.empty(2 * nbytes, dtype=torch.uint8, device=torch.device("cuda", gpu_ctx.device))
+    e = capi.Error()
+    for r in range(2):
+        capi.check(L.ldb_gpu_groupby_export(states[r], C.c_void_p(recv.data_ptr() + r * nbytes), C.byref(e)), e)
+    gpu_ctx.synchronize()
+    capi.check(L.ldb_gpu_groupby_merge_exported(states[0], C.c_void_p(recv.data_ptr()), 2, 0, C.byref(e)), e)
+    got = tps[0].q9_finish(states[0])
+    host = datagen.tpch(0.05, seed=11, lineitem_columns=cols, with_parts=True)
+    oh = {k: oracle.table(v) for k, v in host.items()}
+    want, _ = oracle.q9(oh["part"], oh["supplier"], oh["lineitem"], oh["partsupp"], oh["orders"], oh["nation"])
+    assert got == want
+    for st in states:
+        runtime.state_destroy(gpu_ctx, st)
