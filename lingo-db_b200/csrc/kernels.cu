@@ -1108,50 +1108,47 @@ void launchScanMaterialize(const MaterializeParams& p, int smCount, cudaStream_t
 }
 
 // =================================================================================== K5 probe + aggregate
+// (K4 and K5 handle their survivors IN PLACE under the warp-specialised driver: measured against the survivor-queue form
+//  at SF100, K5 4.27 vs 5.13 ms and K4 5.2 vs 5.9 ms — their dependent part is one directory walk plus an atomic, too short
+//  to pay for a CTA barrier per 256-row tile; K3-with-probe and K9, whose chains are long, gain 1.8x / 2.9x from the queue.)
 // scan → filters → pure lookup in the group-join map → SUM into the shared entry.  The reference
 // takes a per-entry spin lock (SubOpToControlFlow.cpp:4218-4251, EntryLock.cpp:9-25) or an
 // atomic_rmw; here the i128 SUM is two 64-bit atomics with carry (exact, order independent).
 template <int NV, int DB>
-__global__ void __launch_bounds__(kBlock, 4) scanProbeAggKernel(const __grid_constant__ ProbeAggParams p) {
+__global__ void __launch_bounds__(kThreads, 4) scanProbeAggKernel(const __grid_constant__ ProbeAggParams p) {
    constexpr bool IN = true;
    __shared__ __align__(8) TileBarriers barsStorage;
-   __shared__ SurvivorQueue<1 + 2 * NV> queue; // {probe key, value operands}
    TileBarriers* bars = &barsStorage;
-   if (threadIdx.x == 0) queue.count = 0;
-   __syncthreads();
    const int64_t one = 100;
-   auto process = [&](int q) {
-      const int32_t key = queue.w[0][q];
-      int64_t vals[NV];
+   forEachTile<kRowsPerThreadProbe, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+      int32_t key[kRowsPerThreadProbe];
+      int lrs[kRowsPerThreadProbe];
+      BloomProbe bp[kRowsPerThreadProbe];
+      // phase A: filters + hash + Bloom load of every row of this thread (all loads in flight together)
 #pragma unroll
-      for (int c = 0; c < NV; c++) vals[c] = queue.get64(1 + 2 * c, q);
-      const i128 v = evalAggDyn(p.agg, vals, one);
-      joinProbeSlots(p.table, key, hashI32(key), [&](int64_t slot, int32_t payloadWord) {
-         uint8_t* entry = p.table.base + (uint64_t) slot * 32;
-         atomicAdd128((unsigned long long*) (entry + 16), (unsigned long long*) (entry + 24), v);
-         if (payloadWord >= 0) ((int32_t*) entry)[1] = payloadWord | (int32_t) 0x80000000; // marker: idempotent plain store, same sector
-      });
-   };
-   forEachTileUniform<kRowsPerThreadStar, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
-#pragma unroll
-      for (int j = 0; j < kRowsPerThreadStar; j++) { // filters + hash + Bloom word; survivors join the queue
-         const int lrRaw = j * kBlock + threadIdx.x;
-         const bool valid = lrRaw < rows;
-         const int lr = valid ? lrRaw : 0;
-         const bool ok = valid && evalFilters<IN>(p.src.filters, tile, lr, rowBase + lr);
-         const int32_t key = tile.i32(p.probeKeyStage, lr);
-         if (bloomPrefetch(p.table, key, ok).mayContain()) {
-            const int q = queue.claim();
-            queue.w[0][q] = key;
-#pragma unroll
-            for (int c = 0; c < NV; c++) queue.put64(1 + 2 * c, q, tile.lo64(p.valueStage[c], lr));
-         }
+      for (int j = 0; j < kRowsPerThreadProbe; j++) {
+         const int lr = j * kBlock + threadIdx.x;
+         const bool valid = lr < rows;
+         lrs[j] = valid ? lr : 0;
+         const bool ok = valid && evalFilters<IN>(p.src.filters, tile, lrs[j], rowBase + lrs[j]);
+         key[j] = tile.i32(p.probeKeyStage, lrs[j]);
+         bp[j] = bloomPrefetch(p.table, key[j], ok);
       }
-      __syncthreads();
-      drainQueue(queue, false, process);
+      // phase B: the few survivors walk the directory and add into the shared entry
+#pragma unroll
+      for (int j = 0; j < kRowsPerThreadProbe; j++) {
+         if (!bp[j].mayContain()) continue;
+         joinProbeSlots(p.table, key[j], bp[j].h, [&](int64_t slot, int32_t payloadWord) {
+            int64_t vals[NV];
+#pragma unroll
+            for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lrs[j]);
+            i128 v = evalAggDyn(p.agg, vals, one);
+            uint8_t* entry = p.table.base + (uint64_t) slot * 32;
+            atomicAdd128((unsigned long long*) (entry + 16), (unsigned long long*) (entry + 24), v);
+            if (payloadWord >= 0) ((int32_t*) entry)[1] = payloadWord | (int32_t) 0x80000000; // marker: idempotent plain store, same sector
+         });
+      }
    });
-   __syncthreads();
-   drainQueue(queue, true, process);
 }
 bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, const char** why) {
    int nv = p.agg.expr == LDB_EXPR_COL ? 1 : p.agg.expr == LDB_EXPR_MUL_1MINUS_1PLUS ? 3 : 2;
@@ -1162,27 +1159,27 @@ bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, co
    size_t dyn;
    if (nv == 1) {
       if (p.src.cols.decBytes == 8) {
-         int grid = persistentGrid(scanProbeAggKernel<1, 8>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
-         scanProbeAggKernel<1, 8><<<grid, kBlock, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbeAggKernel<1, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbeAggKernel<1, 8><<<grid, kThreads, dyn, s>>>(p);
       } else {
-         int grid = persistentGrid(scanProbeAggKernel<1, 16>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
-         scanProbeAggKernel<1, 16><<<grid, kBlock, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbeAggKernel<1, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbeAggKernel<1, 16><<<grid, kThreads, dyn, s>>>(p);
       }
    } else if (nv == 2) {
       if (p.src.cols.decBytes == 8) {
-         int grid = persistentGrid(scanProbeAggKernel<2, 8>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
-         scanProbeAggKernel<2, 8><<<grid, kBlock, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbeAggKernel<2, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbeAggKernel<2, 8><<<grid, kThreads, dyn, s>>>(p);
       } else {
-         int grid = persistentGrid(scanProbeAggKernel<2, 16>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
-         scanProbeAggKernel<2, 16><<<grid, kBlock, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbeAggKernel<2, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbeAggKernel<2, 16><<<grid, kThreads, dyn, s>>>(p);
       }
    } else {
       if (p.src.cols.decBytes == 8) {
-         int grid = persistentGrid(scanProbeAggKernel<3, 8>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
-         scanProbeAggKernel<3, 8><<<grid, kBlock, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbeAggKernel<3, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbeAggKernel<3, 8><<<grid, kThreads, dyn, s>>>(p);
       } else {
-         int grid = persistentGrid(scanProbeAggKernel<3, 16>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
-         scanProbeAggKernel<3, 16><<<grid, kBlock, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbeAggKernel<3, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbeAggKernel<3, 16><<<grid, kThreads, dyn, s>>>(p);
       }
    }
    return true;
@@ -1192,58 +1189,47 @@ bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, co
 // scan → probe A on keyA → probe B on keyB → keep rows whose payloads agree (the composite join key
 // (l_suppkey, c_nationkey) = (s_suppkey, s_nationkey) of Q5) → group by that payload → SUM.
 template <int NV, int DB>
-__global__ void __launch_bounds__(kBlock, 4) scanProbe2GroupByKernel(const __grid_constant__ Probe2GroupByParams p) {
+__global__ void __launch_bounds__(kThreads, 4) scanProbe2GroupByKernel(const __grid_constant__ Probe2GroupByParams p) {
    constexpr bool IN = true;
    __shared__ __align__(8) TileBarriers barsStorage;
-   __shared__ SurvivorQueue<2 + 2 * NV> queue; // {key A, key B, value operands}
-   __shared__ LocalGroups groups;
    TileBarriers* bars = &barsStorage;
-   groups.init();
-   if (threadIdx.x == 0) queue.count = 0;
-   __syncthreads();
    const int64_t one = 100;
-   const bool is64 = p.agg.expr == LDB_EXPR_COL || p.agg.expr == LDB_EXPR_ONE;
-   const int32_t payloadMask = p.tableA.stride == 32 || p.tableB.stride == 32 ? 0x7fffffff : -1;
-   auto process = [&](int q) { // the two directory walks are independent: both first slots are loaded before either is consumed
-      const int32_t keyA = queue.w[0][q], keyB = queue.w[1][q];
-      const uint64_t hA = hashI32(keyA), hB = hashI32(keyB);
-      const unsigned long long eA = __ldg(slotPtr(p.tableA, hA & p.tableA.mask)), eB = __ldg(slotPtr(p.tableB, hB & p.tableB.mask));
-      int64_t vals[NV];
+   forEachTile<kRowsPerThreadProbe, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+      int32_t key[kRowsPerThreadProbe];
+      int lrs[kRowsPerThreadProbe];
+      BloomProbe bp[kRowsPerThreadProbe];
 #pragma unroll
-      for (int c = 0; c < NV; c++) vals[c] = queue.get64(2 + 2 * c, q);
-      const i128 v = evalAggDyn(p.agg, vals, one);
-      joinProbeFrom(p.tableA, keyA, hA, eA, [&](int32_t payA) {
-         joinProbeFrom(p.tableB, keyB, hB, eB, [&](int32_t payB) {
-            if (((payA ^ payB) & payloadMask) != 0) return;
-            groups.add(p.groups, payB, 0, v, is64);
-         });
-      });
-   };
-   forEachTileUniform<kRowsPerThreadStar, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
-#pragma unroll
-      for (int j = 0; j < kRowsPerThreadStar; j++) {
-         const int lrRaw = j * kBlock + threadIdx.x;
-         const bool valid = lrRaw < rows;
-         const int lr = valid ? lrRaw : 0;
-         const bool ok = valid && evalFilters<IN>(p.src.filters, tile, lr, rowBase + lr);
-         const int32_t keyA = tile.i32(p.keyStageA, lr), keyB = tile.i32(p.keyStageB, lr);
-         // table A's filter first (the plan puts the smaller table there), B's only for A's survivors
-         const bool passA = bloomPrefetch(p.tableA, keyA, ok).mayContain();
-         if (bloomPrefetch(p.tableB, keyB, passA).mayContain()) {
-            const int q = queue.claim();
-            queue.w[0][q] = keyA;
-            queue.w[1][q] = keyB;
-#pragma unroll
-            for (int c = 0; c < NV; c++) queue.put64(2 + 2 * c, q, tile.lo64(p.valueStage[c], lr));
-         }
+      for (int j = 0; j < kRowsPerThreadProbe; j++) { // phase A: Bloom filter of table A for every row (loads in flight together)
+         const int lr = j * kBlock + threadIdx.x;
+         const bool valid = lr < rows;
+         lrs[j] = valid ? lr : 0;
+         const bool ok = valid && evalFilters<IN>(p.src.filters, tile, lrs[j], rowBase + lrs[j]);
+         key[j] = tile.i32(p.keyStageA, lrs[j]);
+         bp[j] = bloomPrefetch(p.tableA, key[j], ok);
       }
-      __syncthreads();
-      drainQueue(queue, false, process);
+      int32_t keyB[kRowsPerThreadProbe];
+      BloomProbe bpB[kRowsPerThreadProbe];
+#pragma unroll
+      for (int j = 0; j < kRowsPerThreadProbe; j++) { // phase B: survivors consult table B's filter (the plan puts the smaller table first)
+         keyB[j] = tile.i32(p.keyStageB, lrs[j]);
+         bpB[j] = bloomPrefetch(p.tableB, keyB[j], bp[j].mayContain());
+      }
+#pragma unroll
+      for (int j = 0; j < kRowsPerThreadProbe; j++) { // phase C: the few rows both filters let through walk the directories
+         if (!bpB[j].mayContain()) continue;
+         joinProbeSlots(p.tableA, key[j], bp[j].h, [&](int64_t, int32_t payA) {
+            joinProbeSlots(p.tableB, keyB[j], bpB[j].h, [&](int64_t, int32_t payB) {
+               if (((payA ^ payB) & (p.tableA.stride == 32 || p.tableB.stride == 32 ? 0x7fffffff : -1)) != 0) return;
+               int64_t vals[NV];
+#pragma unroll
+               for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lrs[j]);
+               int32_t kk[2] = {payB, 0};
+               int slot = groupLookupOrInsert(p.groups, kk);
+               if (slot >= 0) groupAtomicAdd(p.groups, slot, 0, evalAggDyn(p.agg, vals, one), p.agg.expr == LDB_EXPR_COL || p.agg.expr == LDB_EXPR_ONE);
+            });
+         });
+      }
    });
-   __syncthreads();
-   drainQueue(queue, true, process);
-   __syncthreads();
-   groups.flush(p.groups, is64);
 }
 bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStream_t s, const char** why) {
    int nv = p.agg.expr == LDB_EXPR_COL ? 1 : p.agg.expr == LDB_EXPR_MUL_1MINUS_1PLUS ? 3 : 2;
@@ -1254,27 +1240,27 @@ bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStre
    size_t dyn;
    if (nv == 1) {
       if (p.src.cols.decBytes == 8) {
-         int grid = persistentGrid(scanProbe2GroupByKernel<1, 8>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
-         scanProbe2GroupByKernel<1, 8><<<grid, kBlock, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbe2GroupByKernel<1, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbe2GroupByKernel<1, 8><<<grid, kThreads, dyn, s>>>(p);
       } else {
-         int grid = persistentGrid(scanProbe2GroupByKernel<1, 16>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
-         scanProbe2GroupByKernel<1, 16><<<grid, kBlock, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbe2GroupByKernel<1, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbe2GroupByKernel<1, 16><<<grid, kThreads, dyn, s>>>(p);
       }
    } else if (nv == 2) {
       if (p.src.cols.decBytes == 8) {
-         int grid = persistentGrid(scanProbe2GroupByKernel<2, 8>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
-         scanProbe2GroupByKernel<2, 8><<<grid, kBlock, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbe2GroupByKernel<2, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbe2GroupByKernel<2, 8><<<grid, kThreads, dyn, s>>>(p);
       } else {
-         int grid = persistentGrid(scanProbe2GroupByKernel<2, 16>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
-         scanProbe2GroupByKernel<2, 16><<<grid, kBlock, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbe2GroupByKernel<2, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbe2GroupByKernel<2, 16><<<grid, kThreads, dyn, s>>>(p);
       }
    } else {
       if (p.src.cols.decBytes == 8) {
-         int grid = persistentGrid(scanProbe2GroupByKernel<3, 8>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
-         scanProbe2GroupByKernel<3, 8><<<grid, kBlock, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbe2GroupByKernel<3, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbe2GroupByKernel<3, 8><<<grid, kThreads, dyn, s>>>(p);
       } else {
-         int grid = persistentGrid(scanProbe2GroupByKernel<3, 16>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
-         scanProbe2GroupByKernel<3, 16><<<grid, kBlock, dyn, s>>>(p);
+         int grid = persistentGrid(scanProbe2GroupByKernel<3, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
+         scanProbe2GroupByKernel<3, 16><<<grid, kThreads, dyn, s>>>(p);
       }
    }
    return true;

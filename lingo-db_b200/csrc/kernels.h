@@ -69,8 +69,8 @@ struct JoinTableDev {
 constexpr int kMaxStagedCols = 8;
 constexpr int kBlockThreads = 256;
 constexpr int kRowsPerThreadScan = 2;  // K1/K2: arithmetic-heavy, fewer/larger tiles
-constexpr int kRowsPerThreadProbe = 2; // K8 materialize
-constexpr int kRowsPerThreadStar = 1;  // K3/K4/K5/K9 (survivor-queue kernels): small tiles → >= 4 CTAs/SM; they are latency-bound between tiles, not arithmetic-bound
+constexpr int kRowsPerThreadProbe = 2; // K4/K5/K8 (1 row/thread with 2x the CTAs measured slower there: 11.8 vs 11.4 ms on Q3)
+constexpr int kRowsPerThreadStar = 1;  // K3/K9 (survivor-queue kernels): small tiles → >= 4 CTAs/SM; they are latency-bound between tiles, not arithmetic-bound
 constexpr int kStages = 2;
 struct StagedCols {
    int32_t n;

@@ -987,7 +987,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                ProbeAggParams p{};
                p.src.nRows = b.nRows;
                bindFilters(fp, b, p.src.filters);
-               sp.bind(t, b, p.src.cols, kRowsPerThreadStar);
+               sp.bind(t, b, p.src.cols, kRowsPerThreadProbe);
                p.probeKeyStage = probeStage;
                p.table = table->join;
                p.agg = ap.aggs[0];
@@ -1015,7 +1015,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                Probe2GroupByParams p{};
                p.src.nRows = b.nRows;
                bindFilters(fp, b, p.src.filters);
-               sp.bind(t, b, p.src.cols, kRowsPerThreadStar);
+               sp.bind(t, b, p.src.cols, kRowsPerThreadProbe);
                p.keyStageA = stageA;
                p.keyStageB = stageB;
                p.tableA = ta->join;
