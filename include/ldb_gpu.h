@@ -149,6 +149,13 @@ int ldb_gpu_join_table_create(LdbContext* ctx, int64_t expected_rows, int32_t un
  * (ps_partkey, ps_suppkey) → ps_supplycost.  Slot placement uses its own 64-bit mix, not db.hash over the tuple
  * (LowerToStd.cpp:1139-1150), whose XOR-combine clusters correlated keys under open addressing (csrc/kernels.cu). */
 int ldb_gpu_join_table_create_pair(LdbContext* ctx, int64_t expected_rows, int32_t unique_keys, LdbState** out, LdbError* err);
+/* Direct-address table for DENSE unique int32 keys in [key_min, key_max] (surrogate primary keys): slot = key - key_min
+ * holds the int32 payload.  No reference counterpart as an object — it is what the reference's INLJ over a primary-key
+ * index degenerates to for dense keys (OptimizeImplementations.cpp:226-244, LingoDBHashIndex.cpp:32-147).  Accepted as the
+ * sink of a K3 build without side lanes and as probe 1/2 of a K9 star probe; a key outside the range or a duplicate key
+ * fails the build (LDB_ERR_INVALID).  ldb_gpu_table_column_range gives the plan the column's min/max (one streaming pass). */
+int ldb_gpu_join_table_create_direct(LdbContext* ctx, int32_t key_min, int32_t key_max, LdbState** out, LdbError* err);
+int ldb_gpu_table_column_range(LdbTable* t, const char* column, int32_t* min, int32_t* max, LdbError* err);
 int ldb_gpu_join_table_count(LdbState* s, int64_t* n_entries, LdbError* err);
 typedef struct LdbTopKRow {
    int32_t key, side[LDB_MAX_SIDE];

@@ -136,6 +136,8 @@ SIGNATURES = {
     "ldb_gpu_groupby_merge_exported": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _E]),
     "ldb_gpu_join_table_create": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P), _E]),
     "ldb_gpu_join_table_create_pair": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(_P), _E]),
+    "ldb_gpu_join_table_create_direct": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P), _E]),
+    "ldb_gpu_table_column_range": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _E]),
     "ldb_gpu_join_table_count": (C.c_int, [_P, C.POINTER(C.c_int64), _E]),
     "ldb_gpu_join_table_bloom": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64), _E]),
     "ldb_gpu_join_table_topk": (C.c_int, [_P, C.c_int32, C.POINTER(TopKRow), C.POINTER(C.c_int32), _E]),

@@ -338,6 +338,28 @@ __device__ int64_t joinInsert(const JoinTableDev& t, int32_t key, int32_t payloa
    atomicExch(t.error, 1);
    return -1;
 }
+// direct-address table (dense integer keys): slot = key - keyMin holds the payload
+__device__ __forceinline__ int64_t directInsert(const JoinTableDev& t, int32_t key, int32_t payload) {
+   const uint32_t idx = (uint32_t) key - (uint32_t) t.keyMin;
+   if (idx >= t.range) {
+      atomicExch(t.error, 5);
+      return -1;
+   }
+   if (payload == kDirectEmpty) {
+      atomicExch(t.error, 3);
+      return -1;
+   }
+   const int32_t old = atomicExch((int32_t*) t.base + idx, payload); // consecutive keys: consecutive addresses, one sector per 8 rows
+   if (old != kDirectEmpty) { // primary keys are unique; a second row with the key is a plan error, not a multimap
+      atomicExch(t.error, 2);
+      return -1;
+   }
+   return (int64_t) idx;
+}
+__device__ __forceinline__ int32_t directLoad(const JoinTableDev& t, int32_t key) {
+   const uint32_t idx = (uint32_t) key - (uint32_t) t.keyMin;
+   return idx < t.range ? __ldg((const int32_t*) t.base + idx) : kDirectEmpty;
+}
 // probe (SubOpToControlFlow.cpp:2558-2586 + chain walk :2254-2313): visit every entry with the key.
 // Split in two so a thread can put the Bloom loads of ALL its rows in flight before it consumes the first one.
 struct BloomProbe {
@@ -481,6 +503,20 @@ __device__ __forceinline__ void pairProbeFrom(const JoinTableDev& t, int32_t k0,
       s = (s + 1) & t.mask;
       e = __ldg((const ulonglong2*) slotPtr(t, s));
    }
+}
+
+// foreign-key side of a star probe: a hash directory (first slot pre-loaded) or a direct-address table (the payload itself)
+__device__ __forceinline__ unsigned long long fkFirstSlot(const JoinTableDev& t, int32_t key, uint64_t h) {
+   if (t.direct) return (unsigned long long) (uint32_t) directLoad(t, key);
+   return __ldg(slotPtr(t, h & t.mask));
+}
+template <class Fn>
+__device__ __forceinline__ void fkProbeFrom(const JoinTableDev& t, int32_t key, uint64_t h, unsigned long long e, const Fn& fn) {
+   if (t.direct) {
+      if ((int32_t) (uint32_t) e != kDirectEmpty) fn((int32_t) (uint32_t) e);
+      return;
+   }
+   joinProbeFrom(t, key, h, e, fn);
 }
 
 // =================================================================================== aggregate expressions
@@ -899,6 +935,10 @@ __global__ void __launch_bounds__(kBlock, 4) scanBuildKernel(const __grid_consta
    __syncthreads();
    unsigned long long inserted = 0;
    auto insert = [&](int32_t key, int32_t payload, int32_t side0, int32_t side1) {
+      if (p.sink.direct) {
+         if (directInsert(p.sink, key, payload) >= 0) inserted++;
+         return;
+      }
       int64_t slot = joinInsert(p.sink, key, payload);
       if (slot >= 0) {
          inserted++;
@@ -1286,14 +1326,13 @@ __global__ void __launch_bounds__(kBlock, 4) scanStarProbeGroupByKernel(const __
    // foreign-key probes that always hit, so their Bloom filters are not consulted)
    auto process = [&](int q) {
       const int32_t k0 = queue.w[0][q], k1 = queue.w[1][q], kS = queue.w[2][q], kO = queue.w[3][q];
-      const uint64_t hP = hashPair(k0, k1), hS = hashI32(kS), hO = hashI32(kO);
+      const uint64_t hP = hashPair(k0, k1), hS = p.tableS.direct ? 0 : hashI32(kS), hO = p.tableO.direct ? 0 : hashI32(kO);
       const ulonglong2 eP = __ldg((const ulonglong2*) slotPtr(p.tableP, hP & p.tableP.mask));
-      const unsigned long long eS = __ldg(slotPtr(p.tableS, hS & p.tableS.mask));
-      const unsigned long long eO = __ldg(slotPtr(p.tableO, hO & p.tableO.mask));
+      const unsigned long long eS = fkFirstSlot(p.tableS, kS, hS), eO = fkFirstSlot(p.tableO, kO, hO);
       const int64_t a = queue.get64(4, q), b = queue.get64(6, q), d = queue.get64(8, q);
       pairProbeFrom(p.tableP, k0, k1, hP, eP, [&](int64_t c) {
-         joinProbeFrom(p.tableS, kS, hS, eS, [&](int32_t g0) {
-            joinProbeFrom(p.tableO, kO, hO, eO, [&](int32_t g1) { groups.add(p.groups, g0, g1, sub128(mul64x64(a, one - b), mul64x64(c, d)), false); });
+         fkProbeFrom(p.tableS, kS, hS, eS, [&](int32_t g0) {
+            fkProbeFrom(p.tableO, kO, hO, eO, [&](int32_t g1) { groups.add(p.groups, g0, g1, sub128(mul64x64(a, one - b), mul64x64(c, d)), false); });
          });
       });
    };
@@ -1449,6 +1488,28 @@ __global__ void insertTuplesKernel(JoinTableDev t, const int32_t* keys, const in
 void launchInsertTuples(const JoinTableDev& t, const int32_t* keys, const int32_t* payloads, const int32_t* side0, const int32_t* side1, int64_t n, int smCount, cudaStream_t s) {
    int grid = (int) std::min<int64_t>(std::max<int64_t>((n + 255) / 256, 1), (int64_t) smCount * 8);
    insertTuplesKernel<<<grid, 256, 0, s>>>(t, keys, payloads, side0, side1, n);
+}
+// min/max of an int32 column (the plan's density test for a direct-address table)
+__global__ void columnRangeKernel(const int32_t* col, int64_t n, int32_t* minMax) {
+   int32_t lo = INT32_MAX, hi = INT32_MIN;
+   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+      const int32_t v = ldStream32(col + i);
+      lo = v < lo ? v : lo;
+      hi = v > hi ? v : hi;
+   }
+   for (int o = 16; o > 0; o >>= 1) {
+      const int32_t l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+      lo = l2 < lo ? l2 : lo;
+      hi = h2 > hi ? h2 : hi;
+   }
+   if ((threadIdx.x & 31) == 0) {
+      atomicMin(&minMax[0], lo);
+      atomicMax(&minMax[1], hi);
+   }
+}
+void launchColumnRange(const int32_t* col, int64_t n, int32_t* minMax, int smCount, cudaStream_t s) {
+   int grid = (int) std::min<int64_t>(std::max<int64_t>((n + 1023) / 1024, 1), (int64_t) smCount * 8);
+   columnRangeKernel<<<grid, 256, 0, s>>>(col, n, minMax);
 }
 __global__ void hashI64Kernel(const int64_t* a, const int64_t* b, int64_t n, uint64_t* out) {
    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {

@@ -48,6 +48,9 @@ struct GroupTableDev {
 //   stride  8  {key:32, payload:32}                                              plain joins
 //   stride 16  {key0:32, key1:32, payload:64}                                     composite (int32,int32) key → int64 payload
 //              (Q9's partsupp: (ps_partkey, ps_suppkey) → ps_supplycost); hashed like db.hash over the key pair
+//   stride  4  DIRECT-ADDRESS table for dense integer keys (surrogate primary keys: o_orderkey, s_suppkey): slot = key - keyMin,
+//              the slot holds the int32 payload (kDirectEmpty = no such key).  No hashing, no CAS retry, no key compare; a
+//              build in key order writes sequentially.  Chosen by the plan when (max - min + 1) <= 8 x rows (tpch_plans.cpp).
 //   stride 32  {key:32, marker:1|payload:31, side0:32, side1:32, aggLo:64, aggHi:64}  group-join map — ONE 32-byte
 //              sector per entry, so an insert (CAS + side lanes) or a probe hit (compare + i128 atomic add + marker)
 //              touches a single DRAM sector instead of up to four separate arrays.
@@ -59,9 +62,14 @@ struct JoinTableDev {
    uint32_t* bloom;           // blocked Bloom filter over the build keys (32-bit blocks, 3 bits/key), sized to stay in L2
    uint32_t bloomMask;        // words - 1
    unsigned long long* count; // inserted entries
-   int32_t* error;            // 1 = table full, 2 = duplicate key in a unique table, 3 = unstorable pair, 4 = negative payload in a wide table
+   int32_t* error;            // 1 = table full, 2 = duplicate key in a unique table, 3 = unstorable pair, 4 = negative payload in a wide table,
+                              // 5 = key outside the declared range of a direct-address table
    int32_t unique;
+   int32_t direct;            // stride 4: direct-address table
+   int32_t keyMin;
+   uint32_t range;            // number of slots of a direct-address table
 };
+constexpr int32_t kDirectEmpty = (int32_t) 0x80808080; // byte-fill pattern, so a cudaMemset initialises the table
 
 // The distinct fixed-width columns a pipeline touches.  Every scan kernel streams them tile by tile
 // (kTileRows rows) into shared memory with TMA bulk copies (cp.async.bulk + mbarrier, 2 stages), so
@@ -177,6 +185,7 @@ void launchInitWideTable(uint8_t* base, uint64_t capacity, int smCount, cudaStre
 void launchJoinTopK(const JoinTableDev& t, int k, TopKRowDev* out, int* outBlocks, int smCount, cudaStream_t s);
 void launchFill64(unsigned long long* p, unsigned long long v, int64_t n, cudaStream_t s);
 void launchInsertTuples(const JoinTableDev& t, const int32_t* keys, const int32_t* payloads, const int32_t* side0, const int32_t* side1, int64_t n, int smCount, cudaStream_t s);
+void launchColumnRange(const int32_t* col, int64_t n, int32_t* minMax /* device: {min, max} */, int smCount, cudaStream_t s);
 void launchHashI64(const int64_t* a, const int64_t* b, int64_t n, uint64_t* out, cudaStream_t s);
 void launchGroupMergeRows(const GroupTableDev& t, const int32_t* keys, const unsigned long long* acc, int32_t nRows, cudaStream_t s);
 void launchGroupMergeImages(const GroupTableDev& t, const uint8_t* images, int nTables, int skip, cudaStream_t s);

@@ -620,6 +620,53 @@ int ldb_gpu_join_table_create_pair(LdbContext* ctx, int64_t expected_rows, int32
       *out = s;
    });
 }
+int ldb_gpu_join_table_create_direct(LdbContext* ctx, int32_t key_min, int32_t key_max, LdbState** out, LdbError* err) {
+   return guarded(err, [&] {
+      if (!ctx || !out) fail(LDB_ERR_INVALID, "null argument");
+      if (key_max < key_min) fail(LDB_ERR_INVALID, "empty key range");
+      const uint64_t range = (uint64_t) ((int64_t) key_max - (int64_t) key_min) + 1;
+      if (range > (1ull << 32) - 1) fail(LDB_ERR_UNSUPPORTED, "key range too wide for a direct-address table");
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      auto* s = new LdbState;
+      s->ctx = ctx;
+      s->kind = LDB_STATE_JOIN_TABLE;
+      ctx->states.push_back(s);
+      auto& j = s->join;
+      j.stride = 4;
+      j.direct = 1;
+      j.unique = 1;
+      j.keyMin = key_min;
+      j.range = (uint32_t) range;
+      j.mask = 0;
+      j.base = (uint8_t*) devAlloc(s, range * 4, 0x80); // kDirectEmpty in every slot
+      j.count = (unsigned long long*) devAlloc(s, 8, 0);
+      j.error = (int32_t*) devAlloc(s, 4, 0);
+      *out = s;
+   });
+}
+int ldb_gpu_table_column_range(LdbTable* t, const char* column, int32_t* mn, int32_t* mx, LdbError* err) {
+   return guarded(err, [&] {
+      if (!t || !mn || !mx) fail(LDB_ERR_INVALID, "null argument");
+      LdbContext* ctx = t->ctx;
+      int c = t->colIndex(column);
+      if (c < 0) fail(LDB_ERR_INVALID, "unknown column");
+      if (t->columns[c].type != LDB_INT32 && t->columns[c].type != LDB_DATE32) fail(LDB_ERR_UNSUPPORTED, "column range needs an int32/date32 column");
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      int32_t init[2] = {INT32_MAX, INT32_MIN};
+      int32_t* d = (int32_t*) ctx->stagingAlloc(8);
+      LDB_CUDA(cudaMemcpyAsync(d, init, 8, cudaMemcpyHostToDevice, ctx->compute));
+      for (auto& b : t->batches) {
+         if (b.nRows == 0) continue;
+         if (b.ready) LDB_CUDA(cudaStreamWaitEvent(ctx->compute, b.ready, 0));
+         ctx->launch("column_range", [&] { launchColumnRange((const int32_t*) b.data[c], b.nRows, d, ctx->smCount, ctx->compute); });
+      }
+      LDB_CUDA(cudaMemcpyAsync(init, d, 8, cudaMemcpyDeviceToHost, ctx->compute));
+      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+      ctx->stagingRelease(d);
+      *mn = init[0];
+      *mx = init[1];
+   });
+}
 static void checkJoinError(LdbState* s) {
    int32_t e = 0;
    LDB_CUDA(cudaMemcpyAsync(&e, s->join.error, sizeof(e), cudaMemcpyDeviceToHost, s->ctx->compute));
@@ -628,6 +675,7 @@ static void checkJoinError(LdbState* s) {
    if (e == 2) fail(LDB_ERR_INVALID, "duplicate key inserted into a join table declared unique");
    if (e == 3) fail(LDB_ERR_UNSUPPORTED, "the pair (key=-1, payload=-1) cannot be stored in a join table");
    if (e == 4) fail(LDB_ERR_UNSUPPORTED, "join tables with side/aggregate lanes need non-negative inline payloads");
+   if (e == 5) fail(LDB_ERR_INVALID, "key outside the declared range of a direct-address table");
 }
 int ldb_gpu_join_table_count(LdbState* s, int64_t* n_entries, LdbError* err) {
    return guarded(err, [&] {
@@ -866,6 +914,7 @@ LdbState* wantState(LdbState* s, int kind, const char* role) {
 LdbState* wantSingleKeyTable(LdbState* s, const char* role) {
    wantState(s, LDB_STATE_JOIN_TABLE, role);
    if (s->join.stride == 16) fail(LDB_ERR_UNSUPPORTED, std::string("composite-key table not supported for ") + role);
+   if (s->join.direct) fail(LDB_ERR_UNSUPPORTED, std::string("direct-address table not supported for ") + role);
    return s;
 }
 } // namespace
@@ -924,6 +973,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
             const bool pair = sink->join.stride == 16;
             if (pair != (d->build_key2_column != nullptr)) fail(LDB_ERR_INVALID, "a second build key goes with a composite-key table (and only with one)");
             if (pair && d->n_side) fail(LDB_ERR_UNSUPPORTED, "composite-key tables carry no side lanes");
+            if (sink->join.direct && d->n_side) fail(LDB_ERR_UNSUPPORTED, "direct-address tables carry no side lanes");
             int key2Col = pair ? R.col(d->build_key2_column, {LDB_INT32, LDB_DATE32, LDB_FSB4}, "second build key") : -1;
             int payCol = -1, payKind = PAYLOAD_I32;
             if (d->build_payload_column) {
@@ -946,7 +996,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
             int sideCol[kMaxSide] = {0, 0};
             for (int k = 0; k < d->n_side; k++) sideCol[k] = R.col(d->side_columns[k], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "side payload");
             LdbState* probe = d->n_probes ? wantState(d->probe_states[0], LDB_STATE_JOIN_TABLE, "probe") : nullptr;
-            if (probe && probe->join.stride == 16) fail(LDB_ERR_UNSUPPORTED, "build pipelines probe single-key tables");
+            if (probe && (probe->join.stride == 16 || probe->join.direct)) fail(LDB_ERR_UNSUPPORTED, "build pipelines probe single-key hash tables");
             int probeCol = d->n_probes ? R.col(d->probe_key_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key") : -1;
             int keyStage = sp.add(t, keyCol), key2Stage = key2Col >= 0 ? sp.add(t, key2Col) : -1, payStage = payCol >= 0 ? sp.add(t, payCol) : -1, probeStage = probeCol >= 0 ? sp.add(t, probeCol) : 0;
             int sideStage[kMaxSide] = {0, 0};

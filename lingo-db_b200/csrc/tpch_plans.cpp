@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -96,6 +97,29 @@ LdbState* buildJoin(LdbContext* ctx, StateGuard& g, LdbPipelineDesc d, int64_t e
       estimate *= 4;
    }
    throw PlanError(e);
+}
+// Foreign-key build side {key → payload} over an unfiltered primary-key column: a direct-address table when the keys are
+// dense ((max - min + 1) <= 8 x rows: TPC-H surrogate keys are; o_orderkey uses 8 of every 32 values), else a hash table
+// without Bloom filter (FK probes always hit).  LDB_DIRECT_TABLES=0 forces the hash table (tests cover both).
+LdbState* buildForeignKeyTable(LdbContext* ctx, StateGuard& g, LdbPipelineDesc d, LdbTable* table, const char* keyColumn) {
+   LdbError e;
+   const int64_t n = ldb_gpu_table_num_rows(table);
+   const char* env = getenv("LDB_DIRECT_TABLES");
+   if (n > 0 && !(env && env[0] == '0')) {
+      int32_t lo = 0, hi = -1;
+      check(ldb_gpu_table_column_range(table, keyColumn, &lo, &hi, &e), e);
+      if (hi >= lo && (int64_t) hi - lo + 1 <= 8 * n) {
+         LdbState* s = nullptr;
+         check(ldb_gpu_join_table_create_direct(ctx, lo, hi, &s, &e), e);
+         g.own(s);
+         d.sink = s;
+         check(ldb_gpu_run_pipeline(ctx, &d, &e), e);
+         int64_t cnt = 0;
+         check(ldb_gpu_join_table_count(s, &cnt, &e), e); // surfaces duplicate / out-of-range keys
+         return s;
+      }
+   }
+   return buildJoin(ctx, g, d, n + 1024, LDB_JOIN_UNIQUE | LDB_JOIN_NO_BLOOM, 0, 0);
 }
 } // namespace
 
@@ -359,7 +383,7 @@ int ldb_tpch_q9_partial(LdbContext* ctx, const LdbTpchTables* t, const char* nam
       LdbError e;
       StateGuard g;
       if (!t->part || !t->partsupp) throw std::runtime_error("Q9 needs the part and partsupp tables");
-      int64_t nPart = ldb_gpu_table_num_rows(t->part), nPs = ldb_gpu_table_num_rows(t->partsupp), nOrd = ldb_gpu_table_num_rows(t->orders), nSupp = ldb_gpu_table_num_rows(t->supplier);
+      int64_t nPart = ldb_gpu_table_num_rows(t->part), nPs = ldb_gpu_table_num_rows(t->partsupp);
       LdbFilterDesc fp[1] = {strFilter("p_name", LDB_CONTAINS, nameContains)};
       LdbPipelineDesc dp{};
       dp.kind = LDB_PIPE_SCAN_BUILD;
@@ -391,14 +415,14 @@ int ldb_tpch_q9_partial(LdbContext* ctx, const LdbTpchTables* t, const char* nam
       ds.source = t->supplier;
       ds.build_key_column = "s_suppkey";
       ds.build_payload_column = "s_nationkey";
-      LdbState* supp = buildJoin(ctx, g, ds, nSupp + 1024, LDB_JOIN_UNIQUE | LDB_JOIN_NO_BLOOM, 0, 0); // foreign-key probes: always hit
+      LdbState* supp = buildForeignKeyTable(ctx, g, ds, t->supplier, "s_suppkey");
       LdbPipelineDesc dor{};
       dor.kind = LDB_PIPE_SCAN_BUILD;
       dor.source = t->orders;
       dor.build_key_column = "o_orderkey";
       dor.build_payload_column = "o_orderdate";
       dor.build_payload_expr = LDB_PAYLOAD_YEAR;
-      LdbState* ord = buildJoin(ctx, g, dor, nOrd + 1024, LDB_JOIN_UNIQUE | LDB_JOIN_NO_BLOOM, 0, 0);
+      LdbState* ord = buildForeignKeyTable(ctx, g, dor, t->orders, "o_orderkey");
       LdbState* groups = nullptr;
       check(ldb_gpu_groupby_create(ctx, 2, 1, 1024, &groups, &e), e);
       LdbPipelineDesc dl{};

@@ -315,6 +315,18 @@ def join_table_pair(ctx: Context, expected_rows: int, unique: bool = True) -> C.
     return s
 
 
+def join_table_direct(ctx: Context, key_min: int, key_max: int) -> C.c_void_p:
+    s, e = C.c_void_p(), Error()
+    check(ctx.L.ldb_gpu_join_table_create_direct(ctx.h, int(key_min), int(key_max), C.byref(s), C.byref(e)), e)
+    return s
+
+
+def column_range(ctx: Context, table: Table, column: str):
+    lo, hi, e = C.c_int32(), C.c_int32(), Error()
+    check(ctx.L.ldb_gpu_table_column_range(table.h, column.encode(), C.byref(lo), C.byref(hi), C.byref(e)), e)
+    return lo.value, hi.value
+
+
 def join_count(ctx: Context, state) -> int:
     n, e = C.c_int64(), Error()
     check(ctx.L.ldb_gpu_join_table_count(state, C.byref(n), C.byref(e)), e)

@@ -1,4 +1,6 @@
 """GPU parity tests proper: the CUDA path through the C-ABI vs the CPU oracle, bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -403,6 +405,12 @@ def test_q9(gpu_ctx, oracle):
             assert got == want, (sf, needle)
             assert len(got) > 25
         assert g.q9("no such colour") == []
+        # the foreign-key sides (supplier, orders) are direct-address tables by default; the hash-table form must agree
+        os.environ["LDB_DIRECT_TABLES"] = "0"
+        try:
+            assert g.q9("green") == oracle.q9(oh["part"], oh["supplier"], oh["lineitem"], oh["partsupp"], oh["orders"], oh["nation"], "green")[0]
+        finally:
+            del os.environ["LDB_DIRECT_TABLES"]
 
 
 def test_q9_device_resident_matches_oracle(gpu_ctx, oracle):
@@ -456,4 +464,28 @@ def test_q9_sharded_partials_merge_to_the_whole(gpu_ctx, oracle):
     want, _ = oracle.q9(oh["part"], oh["supplier"], oh["lineitem"], oh["partsupp"], oh["orders"], oh["nation"])
     assert got == want
     for st in states:
+        runtime.state_destroy(gpu_ctx, st)
+
+
+def test_direct_address_table_contract(gpu_ctx):
+    """Dense-key join table: column range, build, entry count, and the two ways a build must fail."""
+    from lingodb_b200 import capi, runtime
+    s = datagen.scale(0.01, seed=3)
+    orders = gpu_ctx.table_from_host(datagen.orders(s, chunk_rows=4000))
+    lo, hi = runtime.column_range(gpu_ctx, orders, "o_orderkey")
+    keys = np.concatenate([c["o_orderkey"] for c in datagen.orders(s).chunks])
+    assert (lo, hi) == (int(keys.min()), int(keys.max()))
+    t = runtime.join_table_direct(gpu_ctx, lo, hi)
+    runtime.run_pipeline(gpu_ctx, "scan_build", orders, build_key="o_orderkey", build_payload="o_orderdate", build_payload_expr="year", sink=t)
+    assert runtime.join_count(gpu_ctx, t) == s.n_orders
+    with pytest.raises(capi.LdbRuntimeError):  # same keys again: duplicates
+        runtime.run_pipeline(gpu_ctx, "scan_build", orders, build_key="o_orderkey", build_payload="o_orderdate", sink=t)
+        runtime.join_count(gpu_ctx, t)
+    t2 = runtime.join_table_direct(gpu_ctx, lo, hi - 64)  # range too small
+    with pytest.raises(capi.LdbRuntimeError):
+        runtime.run_pipeline(gpu_ctx, "scan_build", orders, build_key="o_orderkey", build_payload="o_orderdate", sink=t2)
+        runtime.join_count(gpu_ctx, t2)
+    with pytest.raises(capi.LdbRuntimeError):  # not accepted where a hash directory is expected
+        runtime.run_pipeline(gpu_ctx, "scan_build", orders, probes=[(t, "o_custkey")], build_key="o_orderkey", sink=runtime.join_table(gpu_ctx, 1000))
+    for st in (t, t2):
         runtime.state_destroy(gpu_ctx, st)
