@@ -1,17 +1,20 @@
 // kernels.cu — hand-written sm_100a pipeline kernels for LingoDB's three hot paths.
 //
 // Design: every pipeline is ONE persistent, HBM-bound streaming kernel:
-//   grid = SMs × resident CTAs, each CTA strides over tiles of ROWS×blockDim rows; lane-contiguous
-//   rows so every warp-level load is one fully-coalesced 128 B (int32 columns) or 2×256 B
-//   (decimal128 columns, low 8 bytes of each 16 B cell — the reference truncates decimal(p<19) to
-//   i64 the same way, LowerToStd.cpp:111-209) request; all loads of a tile are issued before any
-//   arithmetic (ROWS × columns independent requests in flight per thread).  No tensor cores: the
-//   path is integer/hash work.  Aggregates are exact wrapping i64/i128 like the JIT's LLVM code.
-//   K1/K2  scanGroupByKernel      scan → filters → (group-by | keyless) SUMs
-//   K3     scanBuildKernel        scan → filters → [probe] → join-table insert
-//   K5     scanProbeAggKernel     scan → filters → probe group-join map → atomic i128 SUM
-//   K4     scanProbe2GroupByKernel scan → probe A → probe B → tiny group-by
-//   K6     partition*Kernel       radix partition by h64(key) for the NVLink all-to-all
+//   grid = SMs × resident CTAs; each CTA strides over tiles of 256 or 512 rows of every distinct fixed-width column the
+//   pipeline reads, brought to shared memory by TMA bulk copies (2 stages, L2 evict_first), so each column byte crosses
+//   HBM→SM once.  decimal(p<19) is computed from the low 8 bytes of its 16-byte cell — the reference truncates to i64 the
+//   same way, LowerToStd.cpp:111-209.  No tensor cores: the path is integer/hash work.  Aggregates are exact wrapping
+//   i64/i128 like the JIT's LLVM code.  Rows that survive a selective probe are either handled in place (warp-specialised
+//   driver: K4, K5, K8) or copied to a CTA-wide survivor queue and handled by full warps (K3 with a probe, K9).
+//   K1/K2  scanGroupByKernel          scan → filters → (group-by | keyless) SUMs                       Q6, Q1
+//   K3     scanBuild[Pair]Kernel      scan → filters → [probe] → join-table insert (hash | composite key | direct address)
+//   K4     scanProbe2GroupByKernel    scan → probe A → probe B → tiny group-by                         Q5
+//   K5     scanProbeAggKernel         scan → filters → probe group-join map → atomic i128 SUM          Q3
+//   K6     partition*Kernel           radix partition by h64(key) for the NVLink all-to-all
+//   K7     groupMerge*Kernel          fold other GPUs' group-table images into the local table
+//   K8     scanMaterializeKernel      scan → filters → [probe | Bloom-only] → compacted columns (repartition input)
+//   K9     scanStarProbeGroupByKernel scan → composite-key probe → two foreign-key probes → 2-key group-by   Q9
 #include "device_utils.cuh"
 #include "kernels.h"
 #include "../../include/ldb_gpu.h"
