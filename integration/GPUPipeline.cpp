@@ -61,6 +61,12 @@ LdbState* GPUPipeline::createJoinTablePair(int64_t expectedRows, int32_t flags) 
    check(ldb_gpu_join_table_create_pair(context(), expectedRows, flags, &s, &e), e);
    return own(s);
 }
+LdbState* GPUPipeline::createJoinTableDirect(int32_t keyMin, int32_t keyMax) {
+   LdbState* s = nullptr;
+   LdbError e;
+   check(ldb_gpu_join_table_create_direct(context(), keyMin, keyMax, &s, &e), e);
+   return own(s);
+}
 void GPUPipeline::run(const LdbPipelineDesc& desc) {
    LdbError e;
    check(ldb_gpu_run_pipeline(context(), &desc, &e), e);

@@ -22,6 +22,7 @@ class GPUPipeline {
    static LdbState* createGroupBy(int32_t nKeys, int32_t nAggs, int32_t capacity);                   // rt::PreAggregationHashtable
    static LdbState* createJoinTable(int64_t expectedRows, int32_t flags, int32_t nSide, int32_t nAggs); // rt::GrowingBuffer + rt::HashIndexedView
    static LdbState* createJoinTablePair(int64_t expectedRows, int32_t flags);                        // composite (i32, i32) key
+   static LdbState* createJoinTableDirect(int32_t keyMin, int32_t keyMax);                           // dense surrogate keys: slot = key - min
    // one execution step (scan → pushed-down filters → probes → sink) instead of DataSourceIteration::iterate(scan_func)
    static void run(const LdbPipelineDesc& desc);
    // TableChunk::getArrayView() results (LingoDBTable.cpp:200-225) go through unchanged: LdbArrayView IS ArrayView

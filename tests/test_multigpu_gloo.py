@@ -83,3 +83,17 @@ def test_order_range_partition_is_exact():
             assert r_lo == prev and r_hi >= r_lo
             prev = r_hi
         assert prev == s.n_lineitem
+
+
+def test_q9_shaped_group_images_merge_on_the_host():
+    """Two-key (nation, year) partial group tables of two ranks fold into the totals: the host twin of what
+    parallel.q9_sharded does with all_gather + the K7 merge kernel."""
+    from lingodb_b200 import parallel
+    cap = 1024
+    r0 = [((n, 1992 + y), [1000 * n + y]) for n in range(25) for y in range(7) if (n + y) % 3 != 0]
+    r1 = [((n, 1992 + y), [-(7 * n) + (1 << 70) * y]) for n in range(25) for y in range(7) if (n + y) % 2 == 0]
+    merged = dict(parallel.merge_images_host([parallel.pack_image(cap, r0), parallel.pack_image(cap, r1)], cap))
+    want = {}
+    for k, v in r0 + r1:
+        want[k] = (want.get(k, 0) + v[0]) % (1 << 128)
+    assert {k: v[0] % (1 << 128) for k, v in merged.items()} == want
