@@ -45,5 +45,19 @@ out["dates"] = {"date": m.group(1), "extract_year": int(years[0]), "file": "test
 q9 = [ln.split("\t")[:2] for ln in lines[20631:20807] if ln.count("\t") == 2]
 out["tpch_sf1"]["q9_keys"] = [[n.strip(), int(y)] for n, y in q9]
 out["tpch_sf1"]["q9_file"] = "test/sqlite-datasets/tpchSf1.test:20632-20807"
+def answer_rows(tag):
+    """rows between the '----' after `query … tag` and the next blank line"""
+    i = next(k for k, ln in enumerate(lines) if ln.startswith("query") and ln.rstrip().endswith(tag))
+    j = next(k for k in range(i, len(lines)) if lines[k].strip() == "----")
+    rows = []
+    for ln in lines[j + 1:]:
+        if not ln.strip():
+            break
+        rows.append([f.strip() for f in ln.split("\t")])
+    return rows, f"test/sqlite-datasets/tpchSf1.test:{j + 2}-{j + 1 + len(rows)}"
+
+
+for q in ("q3", "q5", "q9"):
+    out["tpch_sf1"][q + "_rows"], out["tpch_sf1"][q + "_rows_file"] = answer_rows("tpch" + q)
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_kats.json"), "w"), indent=1)
 print(json.dumps(out, indent=1)[:1500])

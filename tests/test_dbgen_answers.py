@@ -1,0 +1,67 @@
+"""EXTERNAL PIN: on dbgen-faithful SF1 tables (lingodb_b200/dbgen.py restates the TPC's generator) the oracle — and the GPU path —
+must reproduce the reference's OWN expected answers, test/sqlite-datasets/tpchSf1.test, digit for digit
+(tests/golden/reference_kats.json holds them, extracted by tests/golden/make_golden.py)."""
+import datetime
+import json
+import os
+
+import numpy as np
+import pytest
+
+from lingodb_b200 import dbgen
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))["tpch_sf1"]
+
+
+def dec(v: int, scale: int) -> str:
+    s = "-" if v < 0 else ""
+    v = abs(v)
+    return f"{s}{v // 10**scale}.{v % 10**scale:0{scale}d}"
+
+
+def day(d: int) -> str:
+    return (datetime.date(1970, 1, 1) + datetime.timedelta(days=d)).isoformat()
+
+
+@pytest.fixture(scope="module")
+def sf1():
+    return dbgen.tpch(1.0)
+
+
+def check_all(q1, q6, q3, q5, q9):
+    assert dec(q6["revenue"], 4) == GOLD["q6"]  # tpchSf1.test:20506
+    want = GOLD["q1"]  # :25-28
+    assert len(q1) == 4
+    for r, w in zip(q1, want):
+        got = {"l_returnflag": chr(r["l_returnflag"] & 0xFF), "l_linestatus": chr(r["l_linestatus"] & 0xFF), "sum_qty": dec(r["sum_qty"], 2),
+               "sum_base_price": dec(r["sum_base_price"], 2), "sum_disc_price": dec(r["sum_disc_price"], 4), "sum_charge": dec(r["sum_charge"], 6),
+               "avg_qty": dec(r["avg_qty"], 21), "avg_price": dec(r["avg_price"], 21), "avg_disc": dec(r["avg_disc"], 21), "count_order": str(r["count_order"])}
+        assert got == w
+    assert [[str(r["l_orderkey"]), dec(r["revenue"], 4), day(r["o_orderdate"]), str(r["o_shippriority"])] for r in q3] == GOLD["q3_rows"]  # :20420-20429
+    assert [[r["n_name"], dec(r["revenue"], 4)] for r in q5] == GOLD["q5_rows"]  # :20488-20492
+    assert [[r["nation"], str(r["o_year"]), dec(r["sum_profit"], 4)] for r in q9] == GOLD["q9_rows"]  # :20633-20807
+
+
+def test_generator_matches_dbgen_landmarks(sf1):
+    assert sf1["lineitem"].num_rows == 6001215 and sf1["orders"].num_rows == 1500000  # dbgen SF1 cardinalities
+    offs, data = sf1["part"].chunks[0]["p_name"]
+    first = [bytes(data[offs[i]:offs[i + 1]]).decode() for i in range(3)]
+    assert first == ["goldenrod lavender spring chocolate lace", "blush thistle blue yellow saddle", "spring green yellow purple cornsilk"]  # part.tbl rows 1-3
+    assert not (np.concatenate([c["o_custkey"] for c in sf1["orders"].chunks]) % 3 == 0).any()
+    assert dbgen.tpch(0.01)["lineitem"].num_rows == 60175  # dbgen SF0.01
+
+
+def test_oracle_reproduces_the_references_sf1_answers(sf1):
+    from oracle import oracle as O
+    o = O.Oracle("auto", workers=8)
+    h = {k: o.table(v) for k, v in sf1.items()}
+    check_all(o.q1(h["lineitem"])[0], o.q6(h["lineitem"])[0], o.q3(h["customer"], h["orders"], h["lineitem"])[0],
+              o.q5(h["customer"], h["orders"], h["lineitem"], h["supplier"], h["nation"], h["region"])[0],
+              o.q9(h["part"], h["supplier"], h["lineitem"], h["partsupp"], h["orders"], h["nation"])[0])
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_the_references_sf1_answers(sf1, gpu_ctx):
+    from lingodb_b200 import runtime
+    g = runtime.Tpch(gpu_ctx, {k: gpu_ctx.table_from_host(v) for k, v in sf1.items()})
+    check_all(g.q1(), g.q6(), g.q3(), g.q5(), g.q9())
