@@ -16,7 +16,7 @@ the oracle and for the GPU path:
     received by 1995-06-17, else 'N'; l_linestatus 'F' iff shipped by 1995-06-17; p_name = first 5 of a fresh Fisher-Yates
     pass over the 92 colours (swap position i with UnifInt(i, 91)).
 
-Pinned by tests/test_dbgen_answers.py: at SF1 the oracle reproduces tpchSf1.test's Q1, Q3, Q5, Q6 and Q9 answers digit for
+Pinned by tests/test_reference_answers_sf1.py: at SF1 the oracle reproduces tpchSf1.test's Q1, Q3, Q5, Q6 and Q9 answers digit for
 digit from these tables (6 001 215 lineitem rows, part 1 = "goldenrod lavender spring chocolate lace").
 Plain numpy: meant for SF <= ~3 in tests, not for the SF100 bench (csrc/tpch_gen.h is the counter-based device generator).
 """
