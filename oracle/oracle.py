@@ -1,7 +1,8 @@
 """oracle.py — TEST INFRASTRUCTURE ONLY: ctypes front of the CPU oracle.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may
-import this module.  It loads oracle/_ref/liboracle_ref.so (the reference's own runtime objects
+import this module.  Parity status: pinned (reference KATs + the reference's own tpchSf1.test answers on dbgen-faithful
+tables, tests/test_reference_answers_sf1.py).  It loads oracle/_ref/liboracle_ref.so (the reference's own runtime objects
 compiled from /root/reference, kind "reference") when that library exists and loads, else
 oracle/liboracle_port.so (self-contained restatement, kind "port").
 """
