@@ -76,6 +76,20 @@ void ldbgen_supplier_host(const LdbGenScale* g, int64_t row_begin, int64_t n_row
 int64_t ldbgen_part_host(const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenPartCols* cols); /* returns utf8 bytes, like customer */
 void ldbgen_partsupp_host(const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenPartsuppCols* cols); /* 4 * n_part rows */
 
+/* ---- dbgen-faithful variant (csrc/dbgen_gen.h): the TPC generator's own random streams for the same columns, so that
+ * tables are the ones `dbgen -s SF` writes (validated against the reference's SF1 answers, tests/test_reference_answers_sf1.py).
+ * Line counts per order are random (1..7), so lineitem is addressed by ORDER: the caller takes the counts, prefix-sums them
+ * and passes each order's first output row.  LdbGenScale.seed is unused (dbgen's seeds are fixed); n_lineitem is filled by
+ * ldbgen_dbgen_scale when count_lines != 0 (one pass over the line-count stream). */
+void ldbgen_dbgen_scale(double sf, int32_t count_lines, LdbGenScale* out);
+void ldbgen_dbgen_line_counts_host(const LdbGenScale* g, int64_t order_begin, int64_t n_orders, int32_t* counts);
+void ldbgen_dbgen_lineitem_host(const LdbGenScale* g, int64_t order_begin, int64_t n_orders, const int64_t* first_row /* per order, into cols */, const LdbGenLineitemCols* cols);
+void ldbgen_dbgen_orders_host(const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenOrdersCols* cols);
+int64_t ldbgen_dbgen_customer_host(const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenCustomerCols* cols);
+void ldbgen_dbgen_supplier_host(const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenSupplierCols* cols);
+int64_t ldbgen_dbgen_part_host(const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenPartCols* cols);
+void ldbgen_dbgen_partsupp_host(const LdbGenScale* g, int64_t row_begin, int64_t n_rows, const LdbGenPartsuppCols* cols);
+
 #ifdef __cplusplus
 }
 #endif

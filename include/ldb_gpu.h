@@ -301,6 +301,13 @@ int ldb_gpu_datagen_supplier(LdbContext* ctx, const struct LdbGenScale* g, int64
 int ldb_gpu_datagen_part_fixed(LdbContext* ctx, const struct LdbGenScale* g, int64_t row_begin, int64_t n_rows, const struct LdbGenPartCols* dev_cols, int32_t* dev_name_lengths, LdbError* err);
 int ldb_gpu_datagen_part_bytes(LdbContext* ctx, const struct LdbGenScale* g, int64_t row_begin, int64_t n_rows, const int32_t* dev_offsets, uint8_t* dev_data, LdbError* err);
 int ldb_gpu_datagen_partsupp(LdbContext* ctx, const struct LdbGenScale* g, int64_t row_begin, int64_t n_rows, const struct LdbGenPartsuppCols* dev_cols, LdbError* err);
+/* dbgen-faithful variant (ldb_datagen.h, csrc/dbgen_gen.h): lineitem is generated per ORDER at dev_first_row[order] (prefix sum of
+ * the line counts); `table` of the two small-table entry points: 0 customer, 1 supplier, 2 part, 3 partsupp (bytes: 0 or 2). */
+int ldb_gpu_dbgen_line_counts(LdbContext* ctx, const struct LdbGenScale* g, int64_t order_begin, int64_t n_orders, int32_t* dev_counts, LdbError* err);
+int ldb_gpu_dbgen_lineitem(LdbContext* ctx, const struct LdbGenScale* g, int64_t order_begin, int64_t n_orders, const int64_t* dev_first_row, const struct LdbGenLineitemCols* dev_cols, LdbError* err);
+int ldb_gpu_dbgen_orders(LdbContext* ctx, const struct LdbGenScale* g, int64_t row_begin, int64_t n_rows, const struct LdbGenOrdersCols* dev_cols, LdbError* err);
+int ldb_gpu_dbgen_small_fixed(LdbContext* ctx, const struct LdbGenScale* g, int32_t table, int64_t row_begin, int64_t n_rows, int32_t* dev_key, int32_t* dev_second, uint8_t* dev_decimal, int32_t* dev_lengths, LdbError* err);
+int ldb_gpu_dbgen_bytes(LdbContext* ctx, const struct LdbGenScale* g, int32_t table, int64_t row_begin, int64_t n_rows, const int32_t* dev_offsets, uint8_t* dev_data, LdbError* err);
 
 #ifdef __cplusplus
 }

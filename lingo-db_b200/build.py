@@ -90,7 +90,7 @@ def build_gpu(verbose=False, force=False, ptxas_verbose=False):
 
 def _build_datagen_host(verbose=False, force=False):
     srcs = [os.path.join(CSRC, "datagen_host.cpp")]
-    deps = srcs + [os.path.join(CSRC, "tpch_gen.h"), os.path.join(INCLUDE, "ldb_datagen.h")]
+    deps = srcs + [os.path.join(CSRC, "tpch_gen.h"), os.path.join(CSRC, "dbgen_gen.h"), os.path.join(INCLUDE, "ldb_datagen.h")]
     stamp = _stamp(deps)
     if not force and _up_to_date(GEN_LIB, stamp):
         return GEN_LIB

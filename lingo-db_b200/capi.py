@@ -153,6 +153,11 @@ SIGNATURES = {
     "ldb_gpu_datagen_part_fixed": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, C.POINTER(PartCols), _P, _E]),
     "ldb_gpu_datagen_part_bytes": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, _P, _P, _E]),
     "ldb_gpu_datagen_partsupp": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, C.POINTER(PartsuppCols), _E]),
+    "ldb_gpu_dbgen_line_counts": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, _P, _E]),
+    "ldb_gpu_dbgen_lineitem": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, _P, C.POINTER(LineitemCols), _E]),
+    "ldb_gpu_dbgen_orders": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, C.POINTER(OrdersCols), _E]),
+    "ldb_gpu_dbgen_small_fixed": (C.c_int, [_P, C.POINTER(GenScale), C.c_int32, C.c_int64, C.c_int64, _P, _P, _P, _P, _E]),
+    "ldb_gpu_dbgen_bytes": (C.c_int, [_P, C.POINTER(GenScale), C.c_int32, C.c_int64, C.c_int64, _P, _P, _E]),
     "ldb_tpch_q6": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(I128), _E]),
     "ldb_tpch_q6_partial": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(_P), _E]),
     "ldb_tpch_q1": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.POINTER(Q1Row), C.c_int32, C.POINTER(C.c_int32), _E]),

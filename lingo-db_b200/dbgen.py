@@ -170,3 +170,67 @@ def tpch(sf: float = 1.0, chunk_rows: int = 1 << 20) -> Dict[str, TableData]:
             "customer": _chunked("customer", CUSTOMER_SCHEMA, customer, n_c, chunk_rows), "supplier": _chunked("supplier", SUPPLIER_SCHEMA, supplier, n_s, chunk_rows),
             "part": _chunked("part", PART_SCHEMA, part, n_p, chunk_rows), "partsupp": _chunked("partsupp", PARTSUPP_SCHEMA, partsupp, 4 * n_p, chunk_rows),
             "nation": nation(), "region": region()}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# compiled twin (csrc/dbgen_gen.h through libldb_datagen_host.so): same tables, random access, multi-threaded — and the
+# code the device generator shares.  tests/test_datagen.py checks it against the numpy version above.
+def scale_compiled(sf: float, count_lines: bool = True):
+    import ctypes as C
+
+    from . import datagen
+    L = datagen.lib()
+    L.ldbgen_dbgen_scale.argtypes = [C.c_double, C.c_int32, C.POINTER(datagen.GenScale)]
+    s = datagen.GenScale()
+    L.ldbgen_dbgen_scale(float(sf), int(count_lines), C.byref(s))
+    return s
+
+
+def tpch_compiled(sf: float = 1.0, chunk_rows: int = 1 << 20) -> Dict[str, TableData]:
+    import ctypes as C
+
+    from . import datagen
+    L = datagen.lib()
+    G = C.POINTER(datagen.GenScale)
+    L.ldbgen_dbgen_line_counts_host.argtypes = [G, C.c_int64, C.c_int64, C.c_void_p]
+    L.ldbgen_dbgen_lineitem_host.argtypes = [G, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(datagen.LineitemCols)]
+    L.ldbgen_dbgen_orders_host.argtypes = [G, C.c_int64, C.c_int64, C.POINTER(datagen.OrdersCols)]
+    L.ldbgen_dbgen_customer_host.restype = C.c_int64
+    L.ldbgen_dbgen_customer_host.argtypes = [G, C.c_int64, C.c_int64, C.POINTER(datagen.CustomerCols)]
+    L.ldbgen_dbgen_supplier_host.argtypes = [G, C.c_int64, C.c_int64, C.POINTER(datagen.SupplierCols)]
+    L.ldbgen_dbgen_part_host.restype = C.c_int64
+    L.ldbgen_dbgen_part_host.argtypes = [G, C.c_int64, C.c_int64, C.POINTER(datagen.PartCols)]
+    L.ldbgen_dbgen_partsupp_host.argtypes = [G, C.c_int64, C.c_int64, C.POINTER(datagen.PartsuppCols)]
+    s = scale_compiled(sf)
+    ptr = datagen._ptr
+    n_o = s.n_orders
+    counts = np.zeros(n_o, np.int32)
+    L.ldbgen_dbgen_line_counts_host(C.byref(s), 0, n_o, ptr(counts))
+    first = np.zeros(n_o + 1, np.int64)
+    np.cumsum(counts, out=first[1:])
+    n_l = int(first[-1])
+    assert n_l == s.n_lineitem
+    li = {c.name: datagen._alloc(c, n_l) for c in LINEITEM_SCHEMA}
+    L.ldbgen_dbgen_lineitem_host(C.byref(s), 0, n_o, ptr(first), C.byref(datagen.LineitemCols(**{k: ptr(v) for k, v in li.items()})))
+    od = {c.name: datagen._alloc(c, n_o) for c in ORDERS_SCHEMA}
+    L.ldbgen_dbgen_orders_host(C.byref(s), 0, n_o, C.byref(datagen.OrdersCols(**{k: ptr(v) for k, v in od.items()})))
+
+    def utf8(fn, cols_cls, n, fixed):
+        offs = np.zeros(n + 1, np.int32)
+        nbytes = fn(C.byref(s), 0, n, C.byref(cols_cls(*[ptr(a) for a in fixed], ptr(offs), None)))
+        data = np.zeros(max(1, nbytes), np.uint8)
+        fn(C.byref(s), 0, n, C.byref(cols_cls(*[None for _ in fixed], None, ptr(data))))
+        return offs.astype(np.int64), data
+
+    ck, cn = np.zeros(s.n_customer, np.int32), np.zeros(s.n_customer, np.int32)
+    cu = {"c_custkey": ck, "c_nationkey": cn, "c_mktsegment": utf8(L.ldbgen_dbgen_customer_host, datagen.CustomerCols, s.n_customer, [ck, cn])}
+    su = {c.name: datagen._alloc(c, s.n_supplier) for c in SUPPLIER_SCHEMA}
+    L.ldbgen_dbgen_supplier_host(C.byref(s), 0, s.n_supplier, C.byref(datagen.SupplierCols(**{k: ptr(v) for k, v in su.items()})))
+    pk = np.zeros(s.n_part, np.int32)
+    pa = {"p_partkey": pk, "p_name": utf8(L.ldbgen_dbgen_part_host, datagen.PartCols, s.n_part, [pk])}
+    ps = {c.name: datagen._alloc(c, 4 * s.n_part) for c in PARTSUPP_SCHEMA}
+    L.ldbgen_dbgen_partsupp_host(C.byref(s), 0, 4 * s.n_part, C.byref(datagen.PartsuppCols(**{k: ptr(v) for k, v in ps.items()})))
+    return {"lineitem": _chunked("lineitem", LINEITEM_SCHEMA, li, n_l, chunk_rows), "orders": _chunked("orders", ORDERS_SCHEMA, od, n_o, chunk_rows),
+            "customer": _chunked("customer", CUSTOMER_SCHEMA, cu, s.n_customer, chunk_rows), "supplier": _chunked("supplier", SUPPLIER_SCHEMA, su, s.n_supplier, chunk_rows),
+            "part": _chunked("part", PART_SCHEMA, pa, s.n_part, chunk_rows), "partsupp": _chunked("partsupp", PARTSUPP_SCHEMA, ps, 4 * s.n_part, chunk_rows),
+            "nation": nation(), "region": region()}

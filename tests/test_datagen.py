@@ -59,3 +59,27 @@ def test_utf8_layout():
     assert segs <= {"AUTOMOBILE", "BUILDING", "FURNITURE", "MACHINERY", "HOUSEHOLD"}
     n = datagen.nation().chunks[0]
     assert bytes(n["n_name"][1][n["n_name"][0][8]:n["n_name"][0][9]]) == b"INDIA"
+
+
+def test_compiled_dbgen_twin_equals_numpy():
+    """csrc/dbgen_gen.h (host build; the device generator compiles the same functions) == lingodb_b200/dbgen.py (numpy), which
+    tests/test_reference_answers_sf1.py validates against the reference's SF1 answers."""
+    from lingodb_b200 import dbgen
+    a, b = dbgen.tpch(0.05, chunk_rows=1 << 30), dbgen.tpch_compiled(0.05, chunk_rows=1 << 30)
+    assert a["lineitem"].num_rows == b["lineitem"].num_rows > 290000
+    for name in a:
+        for c in a[name].columns:
+            x, y = a[name].chunks[0][c.name], b[name].chunks[0][c.name]
+            if isinstance(x, tuple):
+                assert np.array_equal(x[0], y[0]) and np.array_equal(x[1][: x[0][-1]], y[1][: y[0][-1]]), (name, c.name)
+            else:
+                assert np.array_equal(x, y), (name, c.name)
+    # random access: an order range generated on its own equals the slice of the whole
+    import ctypes as C
+    from lingodb_b200 import datagen
+    L = datagen.lib()
+    s = dbgen.scale_compiled(0.05)
+    counts = np.zeros(1000, np.int32)
+    L.ldbgen_dbgen_line_counts_host(C.byref(s), 40000, 1000, datagen._ptr(counts))
+    _, per_order = np.unique(a["lineitem"].chunks[0]["l_orderkey"], return_counts=True)  # order keys ascend with the order index
+    assert counts.tolist() == per_order[40000:41000].tolist()

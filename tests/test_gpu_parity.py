@@ -489,3 +489,18 @@ def test_direct_address_table_contract(gpu_ctx):
         runtime.run_pipeline(gpu_ctx, "scan_build", orders, probes=[(t, "o_custkey")], build_key="o_orderkey", sink=runtime.join_table(gpu_ctx, 1000))
     for st in (t, t2):
         runtime.state_destroy(gpu_ctx, st)
+
+
+@pytest.mark.skipif(os.environ.get("LDB_TEST_DBGEN_DEVICE") != "1", reason="device dbgen twin: opt-in until it has run on a GPU once (LDB_TEST_DBGEN_DEVICE=1)")
+def test_device_dbgen_twin_matches_host_twin(gpu_ctx):
+    from lingodb_b200 import dbgen, devgen
+    host = dbgen.tpch_compiled(0.05, chunk_rows=1 << 30)
+    dev = devgen.dbgen_tables(gpu_ctx, 0.05)
+    for name in ("lineitem", "orders", "customer", "supplier", "part", "partsupp"):
+        d = devgen.to_host(dev[name])
+        for c in host[name].columns:
+            x, y = host[name].chunks[0][c.name], d.chunks[0][c.name]
+            if isinstance(x, tuple):
+                assert np.array_equal(x[0], y[0]) and np.array_equal(x[1][: x[0][-1]], y[1][: y[0][-1]]), (name, c.name)
+            else:
+                assert np.array_equal(x, y), (name, c.name)
