@@ -133,8 +133,8 @@ def partsupp(ctx: Context, s: datagen.GenScale) -> Table:
 def dbgen_tables(ctx: Context, sf: float, lineitem_columns: List[str] = None, order_begin: int = 0, n_orders: int = None, part_batch_rows: int = 16 << 20) -> Dict[str, Table]:
     """dbgen-faithful tables generated in HBM (csrc/dbgen_gen.h; host twin: dbgen.tpch_compiled).  lineitem/orders may be an
     order range [order_begin, order_begin + n_orders) — the shard of one GPU; the small tables are always whole.
-    NOTE: the device kernels share every value function with the host twin that tests/test_datagen.py validates, but the
-    device launch path itself is exercised only by the LDB_TEST_DBGEN_DEVICE=1 test so far."""
+    The device kernels share every value function with the host twin (tests/test_datagen.py) and are compared with it bit
+    for bit by tests/test_gpu_parity.py::test_device_dbgen_twin_matches_host_twin."""
     from . import dbgen
     dev = torch.device("cuda", ctx.device)
     s = dbgen.scale_compiled(sf, count_lines=False)

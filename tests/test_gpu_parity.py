@@ -491,7 +491,6 @@ def test_direct_address_table_contract(gpu_ctx):
         runtime.state_destroy(gpu_ctx, st)
 
 
-@pytest.mark.skipif(os.environ.get("LDB_TEST_DBGEN_DEVICE") != "1", reason="device dbgen twin: opt-in until it has run on a GPU once (LDB_TEST_DBGEN_DEVICE=1)")
 def test_device_dbgen_twin_matches_host_twin(gpu_ctx):
     from lingodb_b200 import dbgen, devgen
     host = dbgen.tpch_compiled(0.05, chunk_rows=1 << 30)
