@@ -42,6 +42,11 @@ SEED = {"o_orderdate": 1066728069, "o_custkey": 851767375, "o_linecount": 143486
         "l_receiptdate": 373135028, "l_returnflag": 717419739, "c_mktsegment": 1140279430, "c_nationkey": 1489529863, "s_nationkey": 110356601,
         "p_name": 709314158, "ps_supplycost": 1051288424}
 
+# further streams, verified against tpchSf1.test's Q4 / Q12 answers (tests/test_reference_answers_sf1.py); not yet columns of the tables
+SEED.update({"o_orderpriority": 591449447, "l_shipmode": 675466456})
+ORDER_PRIORITIES = ["1-URGENT", "2-HIGH", "3-MEDIUM", "4-NOT SPECIFIED", "5-LOW"]
+SHIP_MODES = ["REG AIR", "AIR", "RAIL", "TRUCK", "MAIL", "FOB", "SHIP"]  # positions of MAIL and SHIP are pinned by Q12; the rest follows dists.dss
+
 _POW = None
 
 
@@ -170,6 +175,15 @@ def tpch(sf: float = 1.0, chunk_rows: int = 1 << 20) -> Dict[str, TableData]:
             "customer": _chunked("customer", CUSTOMER_SCHEMA, customer, n_c, chunk_rows), "supplier": _chunked("supplier", SUPPLIER_SCHEMA, supplier, n_s, chunk_rows),
             "part": _chunked("part", PART_SCHEMA, part, n_p, chunk_rows), "partsupp": _chunked("partsupp", PARTSUPP_SCHEMA, partsupp, 4 * n_p, chunk_rows),
             "nation": nation(), "region": region()}
+
+
+def extra_columns(sf: float, line_counts: np.ndarray) -> Dict[str, np.ndarray]:
+    """o_orderpriority (index into ORDER_PRIORITIES, per order) and l_shipmode (index into SHIP_MODES, per lineitem row) —
+    the next columns a widening to Q4 / Q12 needs.  line_counts = lines per order (e.g. from the compiled twin)."""
+    n_o = int(1500000 * sf)
+    valid = np.arange(7)[None, :] < line_counts[:, None]
+    return {"o_orderpriority": unif(stream(SEED["o_orderpriority"], n_o), 0, 4).astype(np.int32),
+            "l_shipmode": unif(stream(SEED["l_shipmode"], 7 * n_o), 0, 6).reshape(n_o, 7)[valid].astype(np.int32)}
 
 
 # ---------------------------------------------------------------------------------------------------------------------

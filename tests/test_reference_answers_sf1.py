@@ -60,6 +60,26 @@ def test_oracle_reproduces_the_references_sf1_answers(sf1):
               o.q9(h["part"], h["supplier"], h["lineitem"], h["partsupp"], h["orders"], h["nation"])[0])
 
 
+def test_next_columns_reproduce_q4_and_q12(sf1):
+    """o_orderpriority and l_shipmode streams (dbgen.extra_columns) against tpchSf1.test's Q4 (:20455-20459) and Q12 (:1197-1198),
+    evaluated in numpy — the data side of the next widening step is pinned before any operator is written."""
+    li = {k: np.concatenate([c[k] for c in sf1["lineitem"].chunks]) for k in ("l_orderkey", "l_shipdate", "l_commitdate", "l_receiptdate")}
+    od = {k: np.concatenate([c[k] for c in sf1["orders"].chunks]) for k in ("o_orderkey", "o_orderdate")}
+    counts = np.diff(np.r_[0, np.flatnonzero(np.r_[np.diff(li["l_orderkey"]) != 0, True]) + 1])
+    x = dbgen.extra_columns(1.0, counts)
+    d = lambda s: (datetime.date.fromisoformat(s) - datetime.date(1970, 1, 1)).days
+    late = np.unique(li["l_orderkey"][li["l_commitdate"] < li["l_receiptdate"]])
+    m = (od["o_orderdate"] >= d("1993-07-01")) & (od["o_orderdate"] < d("1993-10-01")) & np.isin(od["o_orderkey"], late)
+    assert [[p, str(int((x["o_orderpriority"][m] == i).sum()))] for i, p in enumerate(dbgen.ORDER_PRIORITIES)] == GOLD["q4_rows"]
+    prio = np.repeat(x["o_orderpriority"], counts)
+    m = (li["l_commitdate"] < li["l_receiptdate"]) & (li["l_shipdate"] < li["l_commitdate"]) & (li["l_receiptdate"] >= d("1994-01-01")) & (li["l_receiptdate"] < d("1995-01-01"))
+    got = []
+    for mode in ("MAIL", "SHIP"):
+        g = m & (x["l_shipmode"] == dbgen.SHIP_MODES.index(mode))
+        got.append([mode, str(int((prio[g] < 2).sum())), str(int((prio[g] >= 2).sum()))])
+    assert got == GOLD["q12_rows"]
+
+
 @pytest.mark.gpu
 def test_gpu_reproduces_the_references_sf1_answers(sf1, gpu_ctx):
     from lingodb_b200 import runtime
