@@ -107,7 +107,16 @@ def part_supplier(partkey: np.ndarray, j: np.ndarray, n_supp: int) -> np.ndarray
     return (partkey + j * (n_supp // 4 + (partkey - 1) // n_supp)) % n_supp + 1
 
 
-def tpch(sf: float = 1.0, chunk_rows: int = 1 << 20) -> Dict[str, TableData]:
+def _categorical_utf8(idx: np.ndarray, names):
+    enc = [n.encode() for n in names]
+    lens = np.array([len(e) for e in enc], dtype=np.int64)[idx]
+    offs = np.zeros(len(idx) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offs[1:])
+    return offs, np.frombuffer(b"".join(enc[i] for i in idx.tolist()), dtype=np.uint8).copy()
+
+
+def tpch(sf: float = 1.0, chunk_rows: int = 1 << 20, extended: bool = False) -> Dict[str, TableData]:
+    """extended=True adds orders.o_orderpriority and lineitem.l_shipmode (utf8) — the columns of the Q4 / Q12 oracle twins."""
     n_o, n_c, n_s, n_p = int(1500000 * sf), int(150000 * sf), int(10000 * sf), int(200000 * sf)
     # ---- orders
     idx = np.arange(1, n_o + 1, dtype=np.int64)
@@ -171,7 +180,15 @@ def tpch(sf: float = 1.0, chunk_rows: int = 1 << 20) -> Dict[str, TableData]:
     jj = np.tile(np.arange(4, dtype=np.int64), n_p)
     partsupp = {"ps_partkey": pp.astype(np.int32), "ps_suppkey": part_supplier(pp, jj, n_s).astype(np.int32),
                 "ps_supplycost": _dec128(unif(stream(SEED["ps_supplycost"], 4 * n_p), 100, 100000))}
-    return {"lineitem": _chunked("lineitem", LINEITEM_SCHEMA, lineitem, n_l, chunk_rows), "orders": _chunked("orders", ORDERS_SCHEMA, orders, n_o, chunk_rows),
+    li_schema, od_schema = list(LINEITEM_SCHEMA), list(ORDERS_SCHEMA)
+    if extended:
+        from .datagen import ColumnSpec
+        x = extra_columns(sf, lcnt)
+        orders["o_orderpriority"] = _categorical_utf8(x["o_orderpriority"], ORDER_PRIORITIES)
+        lineitem["l_shipmode"] = _categorical_utf8(x["l_shipmode"], SHIP_MODES)
+        od_schema.append(ColumnSpec("o_orderpriority", "utf8"))
+        li_schema.append(ColumnSpec("l_shipmode", "utf8"))
+    return {"lineitem": _chunked("lineitem", li_schema, lineitem, n_l, chunk_rows), "orders": _chunked("orders", od_schema, orders, n_o, chunk_rows),
             "customer": _chunked("customer", CUSTOMER_SCHEMA, customer, n_c, chunk_rows), "supplier": _chunked("supplier", SUPPLIER_SCHEMA, supplier, n_s, chunk_rows),
             "part": _chunked("part", PART_SCHEMA, part, n_p, chunk_rows), "partsupp": _chunked("partsupp", PARTSUPP_SCHEMA, partsupp, 4 * n_p, chunk_rows),
             "nation": nation(), "region": region()}

@@ -33,6 +33,10 @@ class Q5Row(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("revenue", C.c_int64 * 2)]
 
 
+class CountRow(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("a", C.c_int64), ("b", C.c_int64)]
+
+
 class Q9Row(C.Structure):
     _fields_ = [("nation", C.c_char * 32), ("year", C.c_int64), ("sum_profit", C.c_int64 * 2)]
 
@@ -96,6 +100,8 @@ class Oracle:
         L.oracle_q3.argtypes = [C.c_void_p] * 3 + [C.c_char_p] * 2 + [C.POINTER(Q3Row), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.oracle_q5.argtypes = [C.c_void_p] * 6 + [C.c_char_p] * 3 + [C.POINTER(Q5Row), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.oracle_q9.argtypes = [C.c_void_p] * 6 + [C.c_char_p, C.POINTER(Q9Row), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.oracle_q4.argtypes = [C.c_void_p] * 2 + [C.c_char_p] * 2 + [C.POINTER(CountRow), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.oracle_q12.argtypes = [C.c_void_p] * 2 + [C.c_char_p] * 4 + [C.POINTER(CountRow), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.oracle_extract_year.restype = C.c_int64
         L.oracle_extract_year.argtypes = [C.c_int64]
         L.oracle_const_like_contains.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p]
@@ -171,3 +177,14 @@ class Oracle:
         rows, n, sec = (Q9Row * 256)(), C.c_int(), C.c_double()
         self._check(self.lib.oracle_q9(part, supplier, lineitem, partsupp, orders, nation, needle.encode(), rows, 256, C.byref(n), C.byref(sec)))
         return [{"nation": r.nation.decode(), "o_year": r.year, "sum_profit": i128(r.sum_profit)} for r in rows[: n.value]], sec.value
+
+    # oracle twins prepared for the next widening step (no GPU operator yet)
+    def q4(self, orders, lineitem, date_ge="1993-07-01", date_lt="1993-10-01"):
+        rows, n, sec = (CountRow * 16)(), C.c_int(), C.c_double()
+        self._check(self.lib.oracle_q4(orders, lineitem, date_ge.encode(), date_lt.encode(), rows, 16, C.byref(n), C.byref(sec)))
+        return [{"o_orderpriority": r.name.decode(), "order_count": r.a} for r in rows[: n.value]], sec.value
+
+    def q12(self, orders, lineitem, mode1="MAIL", mode2="SHIP", date_ge="1994-01-01", date_lt="1995-01-01"):
+        rows, n, sec = (CountRow * 16)(), C.c_int(), C.c_double()
+        self._check(self.lib.oracle_q12(orders, lineitem, mode1.encode(), mode2.encode(), date_ge.encode(), date_lt.encode(), rows, 16, C.byref(n), C.byref(sec)))
+        return [{"l_shipmode": r.name.decode(), "high_line_count": r.a, "low_line_count": r.b} for r in rows[: n.value]], sec.value

@@ -42,6 +42,10 @@ struct OracleQ5Row {
    char name[32];
    int64_t revenue[2];
 };
+struct OracleCountRow { // Q4: {name, a}; Q12: {name, a, b}
+   char name[32];
+   int64_t a, b;
+};
 struct OracleQ9Row {
    char nation[32];
    int64_t year;
@@ -159,6 +163,30 @@ int oracle_q9(void* part, void* supplier, void* lineitem, void* partsupp, void* 
          strncpy(out[i].nation, rows[i].nation.c_str(), sizeof(out[i].nation) - 1);
          out[i].year = rows[i].year;
          split(rows[i].sumProfit, &out[i].sum_profit[0], &out[i].sum_profit[1]);
+      }
+   });
+}
+int oracle_q4(void* orders, void* lineitem, const char* dateGe, const char* dateLt, OracleCountRow* out, int maxRows, int* nRows, double* seconds) {
+   return guarded([&] {
+      auto rows = runQ4(*(HostTable*) orders, *(HostTable*) lineitem, Q4Params{dateGe, dateLt}, seconds);
+      *nRows = (int) rows.size();
+      for (int i = 0; i < (int) rows.size() && i < maxRows; i++) {
+         memset(out[i].name, 0, sizeof(out[i].name));
+         strncpy(out[i].name, rows[i].priority.c_str(), sizeof(out[i].name) - 1);
+         out[i].a = rows[i].orderCount;
+         out[i].b = 0;
+      }
+   });
+}
+int oracle_q12(void* orders, void* lineitem, const char* mode1, const char* mode2, const char* dateGe, const char* dateLt, OracleCountRow* out, int maxRows, int* nRows, double* seconds) {
+   return guarded([&] {
+      auto rows = runQ12(*(HostTable*) orders, *(HostTable*) lineitem, Q12Params{mode1, mode2, dateGe, dateLt}, seconds);
+      *nRows = (int) rows.size();
+      for (int i = 0; i < (int) rows.size() && i < maxRows; i++) {
+         memset(out[i].name, 0, sizeof(out[i].name));
+         strncpy(out[i].name, rows[i].shipmode.c_str(), sizeof(out[i].name) - 1);
+         out[i].a = rows[i].highLineCount;
+         out[i].b = rows[i].lowLineCount;
       }
    });
 }

@@ -705,4 +705,187 @@ std::vector<Q9Row> runQ9(const HostTable& part, const HostTable& supplier, const
    return rows;
 }
 
+// =====================================================================================  Q4
+// (resources/sql/tpch/4.sql) orders(date range) semi-join lineitem(l_commitdate < l_receiptdate), group by o_orderpriority.
+// Restated as the marker form of a hash semi-join with the (much smaller) filtered orders as build side: build tuples carry a
+// marker byte, the lineitem pipeline sets it on a match (the reference's atomic store of the flag), a final scan of the build
+// buffer keeps the marked tuples and aggregates them.  The column-vs-column predicate is not a pushed-down Restrictions filter
+// (TableStorage.h:14-31 compares a column with a constant): it is a selection in the scan function.
+namespace {
+struct Q4BuildTuple {
+   void* next;
+   uint64_t hash;
+   int32_t orderkey;
+   VarLen32 priority;
+   uint8_t marker;
+};
+struct Q4Entry {
+   void* next;
+   uint64_t hash;
+   VarLen32 priority; // key
+   int64_t count;     // value
+};
+} // namespace
+std::vector<Q4Row> runQ4(const HostTable& orders, const HostTable& lineitem, const Q4Params& p, double* seconds) {
+   rt::QueryContextScope scope;
+   double t0 = now();
+   auto* ordTl = threadLocalBuffers<Q4BuildTuple>();
+   scanTable(orders, {"o_orderkey", "o_orderpriority"}, {{"o_orderdate", 0, FilterOp::GTE, p.dateGe}, {"o_orderdate", 0, FilterOp::LT, p.dateLt}}, [&](rt::BatchView* b) {
+      auto* buf = (rt::GrowingBuffer*) ordTl->getLocal();
+      ColReader ok(b, 0), pr(b, 1);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         auto* t = (Q4BuildTuple*) buf->insert();
+         t->next = nullptr;
+         t->orderkey = ok.i32(idx);
+         t->priority = pr.str(idx);
+         t->marker = 0;
+         t->hash = hashI32(t->orderkey);
+      }
+   });
+   auto* ordBuf = rt::GrowingBuffer::merge(ordTl);
+   auto* ordView = rt::HashIndexedView::build(ordBuf);
+   scanTable(lineitem, {"l_orderkey", "l_commitdate", "l_receiptdate"}, {}, [&](rt::BatchView* b) {
+      ColReader ok(b, 0), cd(b, 1), rd(b, 2);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         if (!(cd.i32(idx) < rd.i32(idx))) continue; // date32 values compare like their nanosecond images
+         int32_t orderkey = ok.i32(idx);
+         for (auto* e = hivLookup(ordView, hashI32(orderkey)); e; e = e->next) {
+            auto* t = (Q4BuildTuple*) e;
+            if (t->orderkey == orderkey) __atomic_store_n(&t->marker, (uint8_t) 1, __ATOMIC_RELAXED);
+         }
+      }
+   });
+   using Frag = rt::PreAggregationHashtableFragment;
+   auto* aggTl = rt::ThreadLocal::create([](uint8_t*) -> uint8_t* { return (uint8_t*) Frag::create(sizeof(Q4Entry), false); }, nullptr);
+   struct Ctx {
+      rt::ThreadLocal* aggTl;
+   } ctx{aggTl};
+   rt::BufferIterator::iterate(
+      ordBuf->createIterator(), false, [](rt::Buffer buf, void* c) {
+         auto* frag = (Frag*) ((Ctx*) c)->aggTl->getLocal();
+         auto* tuples = (Q4BuildTuple*) buf.ptr;
+         for (size_t i = 0; i < buf.numElements / sizeof(Q4BuildTuple); i++) {
+            if (!tuples[i].marker) continue;
+            uint64_t gh = hashVarLen(tuples[i].priority);
+            auto* cached = (Q4Entry*) frag->ht[(gh >> 6) & 1023];
+            Q4Entry* en;
+            if (cached && cached->hash == gh && cached->priority.view() == tuples[i].priority.view()) {
+               en = cached;
+            } else {
+               en = (Q4Entry*) frag->insert(gh);
+               en->priority = tuples[i].priority;
+               en->count = 0;
+            }
+            en->count++;
+         }
+      },
+      &ctx);
+   constexpr size_t contentOff = offsetof(Q4Entry, priority);
+   auto* merged = rt::PreAggregationHashtable::merge(
+      aggTl, [](uint8_t* a, uint8_t* b) { return ((Q4Entry*) (a - contentOff))->priority.view() == ((Q4Entry*) (b - contentOff))->priority.view(); },
+      [](uint8_t* a, uint8_t* b) { ((Q4Entry*) (a - contentOff))->count += ((Q4Entry*) (b - contentOff))->count; });
+   std::vector<Q4Row> rows;
+   rt::BufferIterator::iterate(
+      merged->createIterator(), false, [](rt::Buffer buf, void* c) {
+         auto& rows = *(std::vector<Q4Row>*) c;
+         auto** entries = (Q4Entry**) buf.ptr;
+         for (size_t i = 0; i < buf.numElements / sizeof(Q4Entry*); i++) rows.push_back(Q4Row{std::string(entries[i]->priority.view()), entries[i]->count});
+      },
+      &rows);
+   std::sort(rows.begin(), rows.end(), [](const Q4Row& a, const Q4Row& b) { return a.priority < b.priority; });
+   *seconds = now() - t0;
+   return rows;
+}
+
+// =====================================================================================  Q12
+// (resources/sql/tpch/12.sql) orders ⋈ lineitem(l_shipmode in (M1, M2), l_commitdate < l_receiptdate, l_shipdate < l_commitdate,
+// l_receiptdate in [D, D + 1 year)), group by l_shipmode: two conditional counts on o_orderpriority.
+// Build side = the filtered lineitem rows (tens of thousands), probe = orders.  The receipt-date range is a pushed-down
+// Restrictions filter; the string IN list and the column-vs-column predicates are selections in the scan function.
+namespace {
+struct Q12BuildTuple {
+   void* next;
+   uint64_t hash;
+   int32_t orderkey;
+   VarLen32 shipmode;
+};
+struct Q12Entry {
+   void* next;
+   uint64_t hash;
+   VarLen32 shipmode;   // key
+   int64_t high, low;   // values
+};
+} // namespace
+std::vector<Q12Row> runQ12(const HostTable& orders, const HostTable& lineitem, const Q12Params& p, double* seconds) {
+   rt::QueryContextScope scope;
+   double t0 = now();
+   auto* liTl = threadLocalBuffers<Q12BuildTuple>();
+   scanTable(lineitem, {"l_orderkey", "l_shipmode", "l_shipdate", "l_commitdate", "l_receiptdate"},
+             {{"l_receiptdate", 0, FilterOp::GTE, p.dateGe}, {"l_receiptdate", 0, FilterOp::LT, p.dateLt}}, [&](rt::BatchView* b) {
+                auto* buf = (rt::GrowingBuffer*) liTl->getLocal();
+                ColReader ok(b, 0), sm(b, 1), sd(b, 2), cd(b, 3), rd(b, 4);
+                for (int64_t i = 0; i < b->length; i++) {
+                   int64_t idx = b->selectionVector[i];
+                   VarLen32 mode = sm.str(idx);
+                   if (!(mode.view() == p.mode1 || mode.view() == p.mode2)) continue;
+                   if (!(cd.i32(idx) < rd.i32(idx) && sd.i32(idx) < cd.i32(idx))) continue;
+                   auto* t = (Q12BuildTuple*) buf->insert();
+                   t->next = nullptr;
+                   t->orderkey = ok.i32(idx);
+                   t->shipmode = mode;
+                   t->hash = hashI32(t->orderkey);
+                }
+             });
+   auto* liView = rt::HashIndexedView::build(rt::GrowingBuffer::merge(liTl));
+   using Frag = rt::PreAggregationHashtableFragment;
+   auto* aggTl = rt::ThreadLocal::create([](uint8_t*) -> uint8_t* { return (uint8_t*) Frag::create(sizeof(Q12Entry), false); }, nullptr);
+   scanTable(orders, {"o_orderkey", "o_orderpriority"}, {}, [&](rt::BatchView* b) {
+      auto* frag = (Frag*) aggTl->getLocal();
+      ColReader ok(b, 0), pr(b, 1);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         int32_t orderkey = ok.i32(idx);
+         for (auto* e = hivLookup(liView, hashI32(orderkey)); e; e = e->next) {
+            auto* t = (Q12BuildTuple*) e;
+            if (t->orderkey != orderkey) continue;
+            std::string_view prio = pr.str(idx).view();
+            const bool high = prio == "1-URGENT" || prio == "2-HIGH";
+            uint64_t gh = hashVarLen(t->shipmode);
+            auto* cached = (Q12Entry*) frag->ht[(gh >> 6) & 1023];
+            Q12Entry* en;
+            if (cached && cached->hash == gh && cached->shipmode.view() == t->shipmode.view()) {
+               en = cached;
+            } else {
+               en = (Q12Entry*) frag->insert(gh);
+               en->shipmode = t->shipmode;
+               en->high = en->low = 0;
+            }
+            en->high += high ? 1 : 0;
+            en->low += high ? 0 : 1;
+         }
+      }
+   });
+   constexpr size_t contentOff = offsetof(Q12Entry, shipmode);
+   auto* merged = rt::PreAggregationHashtable::merge(
+      aggTl, [](uint8_t* a, uint8_t* b) { return ((Q12Entry*) (a - contentOff))->shipmode.view() == ((Q12Entry*) (b - contentOff))->shipmode.view(); },
+      [](uint8_t* a, uint8_t* b) {
+         auto *x = (Q12Entry*) (a - contentOff), *y = (Q12Entry*) (b - contentOff);
+         x->high += y->high;
+         x->low += y->low;
+      });
+   std::vector<Q12Row> rows;
+   rt::BufferIterator::iterate(
+      merged->createIterator(), false, [](rt::Buffer buf, void* c) {
+         auto& rows = *(std::vector<Q12Row>*) c;
+         auto** entries = (Q12Entry**) buf.ptr;
+         for (size_t i = 0; i < buf.numElements / sizeof(Q12Entry*); i++) rows.push_back(Q12Row{std::string(entries[i]->shipmode.view()), entries[i]->high, entries[i]->low});
+      },
+      &rows);
+   std::sort(rows.begin(), rows.end(), [](const Q12Row& a, const Q12Row& b) { return a.shipmode < b.shipmode; });
+   *seconds = now() - t0;
+   return rows;
+}
+
 } // namespace oracle

@@ -61,4 +61,22 @@ struct Q9Row {
 };
 std::vector<Q9Row> runQ9(const HostTable& part, const HostTable& supplier, const HostTable& lineitem, const HostTable& partsupp, const HostTable& orders, const HostTable& nation, const Q9Params& p, double* seconds);
 
+// Q4 / Q12: oracle twins prepared for the next widening step (semi-join with marker, conditional sums); no GPU operator yet
+struct Q4Params {
+   std::string dateGe, dateLt;
+};
+struct Q4Row {
+   std::string priority;
+   int64_t orderCount;
+};
+std::vector<Q4Row> runQ4(const HostTable& orders, const HostTable& lineitem, const Q4Params& p, double* seconds);
+struct Q12Params {
+   std::string mode1, mode2, dateGe, dateLt;
+};
+struct Q12Row {
+   std::string shipmode;
+   int64_t highLineCount, lowLineCount;
+};
+std::vector<Q12Row> runQ12(const HostTable& orders, const HostTable& lineitem, const Q12Params& p, double* seconds);
+
 } // namespace oracle

@@ -25,7 +25,7 @@ def day(d: int) -> str:
 
 @pytest.fixture(scope="module")
 def sf1():
-    return dbgen.tpch(1.0)
+    return dbgen.tpch(1.0, extended=True)  # + o_orderpriority, l_shipmode for the Q4 / Q12 oracle twins
 
 
 def check_all(q1, q6, q3, q5, q9):
@@ -80,8 +80,25 @@ def test_next_columns_reproduce_q4_and_q12(sf1):
     assert got == GOLD["q12_rows"]
 
 
+def test_oracle_q4_q12_twins_reproduce_the_references_answers(sf1):
+    """Semi-join with marker (Q4) and conditional counts over a join (Q12) on the reference's runtime objects: the oracle side of the
+    next widening step, pinned before the GPU operators exist."""
+    from oracle import oracle as O
+    for kind in (["port", "reference"] if os.path.exists(O.REF_LIB) else ["port"]):
+        o = O.Oracle(kind, workers=8)
+        od, li = o.table(sf1["orders"]), o.table(sf1["lineitem"])
+        assert [[r["o_orderpriority"], str(r["order_count"])] for r in o.q4(od, li)[0]] == GOLD["q4_rows"]  # tpchSf1.test:20455-20459
+        assert [[r["l_shipmode"], str(r["high_line_count"]), str(r["low_line_count"])] for r in o.q12(od, li)[0]] == GOLD["q12_rows"]  # :1197-1198
+
+
 @pytest.mark.gpu
 def test_gpu_reproduces_the_references_sf1_answers(sf1, gpu_ctx):
     from lingodb_b200 import runtime
-    g = runtime.Tpch(gpu_ctx, {k: gpu_ctx.table_from_host(v) for k, v in sf1.items()})
+    from lingodb_b200.datagen import TableData
+
+    def base(t):  # without the two extra utf8 columns of the Q4 / Q12 twins (no GPU operator reads them yet)
+        keep = [c for c in t.columns if c.name not in ("o_orderpriority", "l_shipmode")]
+        return TableData(t.name, keep, [{c.name: ch[c.name] for c in keep} for ch in t.chunks], list(t.chunk_rows))
+
+    g = runtime.Tpch(gpu_ctx, {k: gpu_ctx.table_from_host(base(v)) for k, v in sf1.items()})
     check_all(g.q1(), g.q6(), g.q3(), g.q5(), g.q9())
