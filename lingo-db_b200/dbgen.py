@@ -116,7 +116,7 @@ def _categorical_utf8(idx: np.ndarray, names):
 
 
 def tpch(sf: float = 1.0, chunk_rows: int = 1 << 20, extended: bool = False) -> Dict[str, TableData]:
-    """extended=True adds orders.o_orderpriority and lineitem.l_shipmode (utf8) — the columns of the Q4 / Q12 oracle twins."""
+    """extended=True adds orders.o_orderpriority and lineitem.l_shipmode (utf8) — the columns the Q4 / Q12 twins of the oracle read."""
     n_o, n_c, n_s, n_p = int(1500000 * sf), int(150000 * sf), int(10000 * sf), int(200000 * sf)
     # ---- orders
     idx = np.arange(1, n_o + 1, dtype=np.int64)
