@@ -116,7 +116,8 @@ def _categorical_utf8(idx: np.ndarray, names):
 
 
 def tpch(sf: float = 1.0, chunk_rows: int = 1 << 20, extended: bool = False) -> Dict[str, TableData]:
-    """extended=True adds orders.o_orderpriority and lineitem.l_shipmode (utf8) — the columns the Q4 / Q12 twins of the oracle read."""
+    """extended=True adds orders.o_orderpriority, orders.o_totalprice, lineitem.l_shipmode and customer.c_name — the columns the
+    Q4 / Q12 / Q18 twins of the oracle read."""
     n_o, n_c, n_s, n_p = int(1500000 * sf), int(150000 * sf), int(10000 * sf), int(200000 * sf)
     # ---- orders
     idx = np.arange(1, n_o + 1, dtype=np.int64)
@@ -180,7 +181,7 @@ def tpch(sf: float = 1.0, chunk_rows: int = 1 << 20, extended: bool = False) -> 
     jj = np.tile(np.arange(4, dtype=np.int64), n_p)
     partsupp = {"ps_partkey": pp.astype(np.int32), "ps_suppkey": part_supplier(pp, jj, n_s).astype(np.int32),
                 "ps_supplycost": _dec128(unif(stream(SEED["ps_supplycost"], 4 * n_p), 100, 100000))}
-    li_schema, od_schema = list(LINEITEM_SCHEMA), list(ORDERS_SCHEMA)
+    li_schema, od_schema, cu_schema = list(LINEITEM_SCHEMA), list(ORDERS_SCHEMA), list(CUSTOMER_SCHEMA)
     if extended:
         from .datagen import ColumnSpec
         x = extra_columns(sf, lcnt)
@@ -188,8 +189,17 @@ def tpch(sf: float = 1.0, chunk_rows: int = 1 << 20, extended: bool = False) -> 
         lineitem["l_shipmode"] = _categorical_utf8(x["l_shipmode"], SHIP_MODES)
         od_schema.append(ColumnSpec("o_orderpriority", "utf8"))
         li_schema.append(ColumnSpec("l_shipmode", "utf8"))
+        # o_totalprice = sum over the order's lines of ((eprice * (100 - disc)) / 100) * (100 + tax) / 100, integer cents (dbgen mk_order);
+        # pinned by Q18's answer rows
+        line_total = ((qty * price) * (100 - disc) // 100) * (100 + tax) // 100
+        total = np.zeros(n_o, dtype=np.int64)
+        np.add.at(total, np.repeat(np.arange(n_o), lcnt), line_total)
+        orders["o_totalprice"] = _dec128(total)
+        od_schema.append(ColumnSpec("o_totalprice", "decimal128", 12, 2))
+        customer["c_name"] = _utf8(["Customer#%09d" % k for k in range(1, n_c + 1)])
+        cu_schema.append(ColumnSpec("c_name", "utf8"))
     return {"lineitem": _chunked("lineitem", li_schema, lineitem, n_l, chunk_rows), "orders": _chunked("orders", od_schema, orders, n_o, chunk_rows),
-            "customer": _chunked("customer", CUSTOMER_SCHEMA, customer, n_c, chunk_rows), "supplier": _chunked("supplier", SUPPLIER_SCHEMA, supplier, n_s, chunk_rows),
+            "customer": _chunked("customer", cu_schema, customer, n_c, chunk_rows), "supplier": _chunked("supplier", SUPPLIER_SCHEMA, supplier, n_s, chunk_rows),
             "part": _chunked("part", PART_SCHEMA, part, n_p, chunk_rows), "partsupp": _chunked("partsupp", PARTSUPP_SCHEMA, partsupp, 4 * n_p, chunk_rows),
             "nation": nation(), "region": region()}
 

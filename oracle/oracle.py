@@ -37,6 +37,11 @@ class CountRow(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("a", C.c_int64), ("b", C.c_int64)]
 
 
+class Q18Row(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("custkey", C.c_int32), ("orderkey", C.c_int32), ("orderdate", C.c_int32), ("pad", C.c_int32),
+                ("totalprice", C.c_int64), ("sum_quantity", C.c_int64)]
+
+
 class Q9Row(C.Structure):
     _fields_ = [("nation", C.c_char * 32), ("year", C.c_int64), ("sum_profit", C.c_int64 * 2)]
 
@@ -102,6 +107,7 @@ class Oracle:
         L.oracle_q9.argtypes = [C.c_void_p] * 6 + [C.c_char_p, C.POINTER(Q9Row), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.oracle_q4.argtypes = [C.c_void_p] * 2 + [C.c_char_p] * 2 + [C.POINTER(CountRow), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.oracle_q12.argtypes = [C.c_void_p] * 2 + [C.c_char_p] * 4 + [C.POINTER(CountRow), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.oracle_q18.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.POINTER(Q18Row), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.oracle_extract_year.restype = C.c_int64
         L.oracle_extract_year.argtypes = [C.c_int64]
         L.oracle_const_like_contains.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p]
@@ -188,3 +194,9 @@ class Oracle:
         rows, n, sec = (CountRow * 16)(), C.c_int(), C.c_double()
         self._check(self.lib.oracle_q12(orders, lineitem, mode1.encode(), mode2.encode(), date_ge.encode(), date_lt.encode(), rows, 16, C.byref(n), C.byref(sec)))
         return [{"l_shipmode": r.name.decode(), "high_line_count": r.a, "low_line_count": r.b} for r in rows[: n.value]], sec.value
+
+    def q18(self, customer, orders, lineitem, quantity_gt=300):
+        rows, n, sec = (Q18Row * 128)(), C.c_int(), C.c_double()
+        self._check(self.lib.oracle_q18(customer, orders, lineitem, quantity_gt, rows, 128, C.byref(n), C.byref(sec)))
+        return [{"c_name": r.name.decode(), "c_custkey": r.custkey, "o_orderkey": r.orderkey, "o_orderdate": r.orderdate, "o_totalprice": r.totalprice,
+                 "sum_quantity": r.sum_quantity} for r in rows[: n.value]], sec.value

@@ -46,6 +46,11 @@ struct OracleCountRow { // Q4: {name, a}; Q12: {name, a, b}
    char name[32];
    int64_t a, b;
 };
+struct OracleQ18Row {
+   char name[32];
+   int32_t custkey, orderkey, orderdate, pad;
+   int64_t totalprice, sum_quantity;
+};
 struct OracleQ9Row {
    char nation[32];
    int64_t year;
@@ -187,6 +192,21 @@ int oracle_q12(void* orders, void* lineitem, const char* mode1, const char* mode
          strncpy(out[i].name, rows[i].shipmode.c_str(), sizeof(out[i].name) - 1);
          out[i].a = rows[i].highLineCount;
          out[i].b = rows[i].lowLineCount;
+      }
+   });
+}
+int oracle_q18(void* customer, void* orders, void* lineitem, int64_t quantityGt, OracleQ18Row* out, int maxRows, int* nRows, double* seconds) {
+   return guarded([&] {
+      auto rows = runQ18(*(HostTable*) customer, *(HostTable*) orders, *(HostTable*) lineitem, quantityGt, seconds);
+      *nRows = (int) rows.size();
+      for (int i = 0; i < (int) rows.size() && i < maxRows; i++) {
+         memset(&out[i], 0, sizeof(out[i]));
+         strncpy(out[i].name, rows[i].name.c_str(), sizeof(out[i].name) - 1);
+         out[i].custkey = rows[i].custkey;
+         out[i].orderkey = rows[i].orderkey;
+         out[i].orderdate = rows[i].orderdate;
+         out[i].totalprice = rows[i].totalprice;
+         out[i].sum_quantity = rows[i].sumQuantity;
       }
    });
 }

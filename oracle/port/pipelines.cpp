@@ -888,4 +888,199 @@ std::vector<Q12Row> runQ12(const HostTable& orders, const HostTable& lineitem, c
    return rows;
 }
 
+// =====================================================================================  Q18
+// (resources/sql/tpch/18.sql) o_orderkey in (select l_orderkey from lineitem group by l_orderkey having sum(l_quantity) > X),
+// joined with customer and lineitem, grouped by (c_name, c_custkey, o_orderkey, o_orderdate, o_totalprice), top 100.
+// The inner aggregation has one group per order: the partitioned merge of PreAggregationHashtable.cpp:76-170 at full scale.
+namespace {
+struct Q18SumEntry {
+   void* next;
+   uint64_t hash;
+   int32_t orderkey; // key
+   int64_t sumQty;   // value: sum(decimal(12,2)) as i64
+};
+struct Q18KeyTuple {
+   void* next;
+   uint64_t hash;
+   int32_t orderkey;
+};
+struct Q18CustTuple {
+   void* next;
+   uint64_t hash;
+   int32_t custkey;
+   VarLen32 name;
+};
+struct Q18OrderTuple {
+   void* next;
+   uint64_t hash;
+   int32_t orderkey, custkey;
+   VarLen32 name;
+   int64_t orderdateNs, totalprice;
+};
+struct Q18Entry {
+   void* next;
+   uint64_t hash;
+   VarLen32 name; // keys
+   int32_t custkey, orderkey;
+   int64_t orderdateNs, totalprice;
+   int64_t sumQty; // value
+};
+} // namespace
+std::vector<Q18Row> runQ18(const HostTable& customer, const HostTable& orders, const HostTable& lineitem, int64_t quantityGt, double* seconds) {
+   rt::QueryContextScope scope;
+   double t0 = now();
+   using Frag = rt::PreAggregationHashtableFragment;
+   // ---- lineitem → group by l_orderkey: sum(l_quantity)
+   auto* sumTl = rt::ThreadLocal::create([](uint8_t*) -> uint8_t* { return (uint8_t*) Frag::create(sizeof(Q18SumEntry), false); }, nullptr);
+   scanTable(lineitem, {"l_orderkey", "l_quantity"}, {}, [&](rt::BatchView* b) {
+      auto* frag = (Frag*) sumTl->getLocal();
+      ColReader ok(b, 0), qty(b, 1);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         int32_t orderkey = ok.i32(idx);
+         uint64_t h = hashI32(orderkey);
+         auto* cached = (Q18SumEntry*) frag->ht[(h >> 6) & 1023];
+         Q18SumEntry* en;
+         if (cached && cached->hash == h && cached->orderkey == orderkey) {
+            en = cached;
+         } else {
+            en = (Q18SumEntry*) frag->insert(h);
+            en->orderkey = orderkey;
+            en->sumQty = 0;
+         }
+         en->sumQty += qty.dec64(idx);
+      }
+   });
+   constexpr size_t sumOff = offsetof(Q18SumEntry, orderkey);
+   auto* sums = rt::PreAggregationHashtable::merge(
+      sumTl, [](uint8_t* a, uint8_t* b) { return ((Q18SumEntry*) (a - sumOff))->orderkey == ((Q18SumEntry*) (b - sumOff))->orderkey; },
+      [](uint8_t* a, uint8_t* b) { ((Q18SumEntry*) (a - sumOff))->sumQty += ((Q18SumEntry*) (b - sumOff))->sumQty; });
+   // ---- HAVING sum > X → key set
+   auto* keyTl = threadLocalBuffers<Q18KeyTuple>();
+   struct HavingCtx {
+      rt::ThreadLocal* keyTl;
+      int64_t limit;
+   } hctx{keyTl, quantityGt * 100};
+   rt::BufferIterator::iterate(
+      sums->createIterator(), false, [](rt::Buffer buf, void* c) {
+         auto* hc = (HavingCtx*) c;
+         auto* out = (rt::GrowingBuffer*) hc->keyTl->getLocal();
+         auto** entries = (Q18SumEntry**) buf.ptr;
+         for (size_t i = 0; i < buf.numElements / sizeof(Q18SumEntry*); i++) {
+            if (!(entries[i]->sumQty > hc->limit)) continue;
+            auto* t = (Q18KeyTuple*) out->insert();
+            t->next = nullptr;
+            t->orderkey = entries[i]->orderkey;
+            t->hash = hashI32(t->orderkey);
+         }
+      },
+      &hctx);
+   auto* keyView = rt::HashIndexedView::build(rt::GrowingBuffer::merge(keyTl));
+   // ---- customer → {c_custkey, c_name}
+   auto* custTl = threadLocalBuffers<Q18CustTuple>();
+   scanTable(customer, {"c_custkey", "c_name"}, {}, [&](rt::BatchView* b) {
+      auto* buf = (rt::GrowingBuffer*) custTl->getLocal();
+      ColReader ck(b, 0), cn(b, 1);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         auto* t = (Q18CustTuple*) buf->insert();
+         t->next = nullptr;
+         t->custkey = ck.i32(idx);
+         t->name = cn.str(idx);
+         t->hash = hashI32(t->custkey);
+      }
+   });
+   auto* custView = rt::HashIndexedView::build(rt::GrowingBuffer::merge(custTl));
+   // ---- orders semi-join key set, join customer → build side for the last join
+   auto* ordTl = threadLocalBuffers<Q18OrderTuple>();
+   scanTable(orders, {"o_orderkey", "o_custkey", "o_orderdate", "o_totalprice"}, {}, [&](rt::BatchView* b) {
+      auto* buf = (rt::GrowingBuffer*) ordTl->getLocal();
+      ColReader ok(b, 0), ck(b, 1), od(b, 2), tp(b, 3);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         int32_t orderkey = ok.i32(idx);
+         bool in = false;
+         for (auto* e = hivLookup(keyView, hashI32(orderkey)); e && !in; e = e->next) in = ((Q18KeyTuple*) e)->orderkey == orderkey;
+         if (!in) continue;
+         int32_t custkey = ck.i32(idx);
+         for (auto* e = hivLookup(custView, hashI32(custkey)); e; e = e->next) {
+            auto* c = (Q18CustTuple*) e;
+            if (c->custkey != custkey) continue;
+            auto* t = (Q18OrderTuple*) buf->insert();
+            t->next = nullptr;
+            t->orderkey = orderkey;
+            t->custkey = custkey;
+            t->name = c->name;
+            t->orderdateNs = od.dateNs(idx);
+            t->totalprice = tp.dec64(idx);
+            t->hash = hashI32(orderkey);
+         }
+      }
+   });
+   auto* ordView = rt::HashIndexedView::build(rt::GrowingBuffer::merge(ordTl));
+   // ---- lineitem ⋈ that → group by the five keys: sum(l_quantity)
+   auto* aggTl = rt::ThreadLocal::create([](uint8_t*) -> uint8_t* { return (uint8_t*) Frag::create(sizeof(Q18Entry), false); }, nullptr);
+   scanTable(lineitem, {"l_orderkey", "l_quantity"}, {}, [&](rt::BatchView* b) {
+      auto* frag = (Frag*) aggTl->getLocal();
+      ColReader ok(b, 0), qty(b, 1);
+      for (int64_t i = 0; i < b->length; i++) {
+         int64_t idx = b->selectionVector[i];
+         int32_t orderkey = ok.i32(idx);
+         for (auto* e = hivLookup(ordView, hashI32(orderkey)); e; e = e->next) {
+            auto* o = (Q18OrderTuple*) e;
+            if (o->orderkey != orderkey) continue;
+            HashBuilder hb; // db.hash over (c_name, c_custkey, o_orderkey, o_orderdate, o_totalprice)
+            hb.addPiece(hashVarLen(o->name));
+            hb.addInt(o->custkey);
+            hb.addInt(o->orderkey);
+            hb.addInt(o->orderdateNs);
+            hb.addInt(o->totalprice);
+            uint64_t gh = hb.total;
+            auto same = [&](Q18Entry* x) { return x->orderkey == o->orderkey && x->custkey == o->custkey && x->orderdateNs == o->orderdateNs && x->totalprice == o->totalprice && x->name.view() == o->name.view(); };
+            auto* cached = (Q18Entry*) frag->ht[(gh >> 6) & 1023];
+            Q18Entry* en;
+            if (cached && cached->hash == gh && same(cached)) {
+               en = cached;
+            } else {
+               en = (Q18Entry*) frag->insert(gh);
+               en->name = o->name;
+               en->custkey = o->custkey;
+               en->orderkey = o->orderkey;
+               en->orderdateNs = o->orderdateNs;
+               en->totalprice = o->totalprice;
+               en->sumQty = 0;
+            }
+            en->sumQty += qty.dec64(idx);
+         }
+      }
+   });
+   constexpr size_t off = offsetof(Q18Entry, name);
+   auto* merged = rt::PreAggregationHashtable::merge(
+      aggTl,
+      [](uint8_t* a, uint8_t* b) {
+         auto *x = (Q18Entry*) (a - off), *y = (Q18Entry*) (b - off);
+         return x->orderkey == y->orderkey && x->custkey == y->custkey && x->orderdateNs == y->orderdateNs && x->totalprice == y->totalprice && x->name.view() == y->name.view();
+      },
+      [](uint8_t* a, uint8_t* b) { ((Q18Entry*) (a - off))->sumQty += ((Q18Entry*) (b - off))->sumQty; });
+   std::vector<Q18Row> rows;
+   rt::BufferIterator::iterate(
+      merged->createIterator(), false, [](rt::Buffer buf, void* c) {
+         auto& rows = *(std::vector<Q18Row>*) c;
+         auto** entries = (Q18Entry**) buf.ptr;
+         for (size_t i = 0; i < buf.numElements / sizeof(Q18Entry*); i++) {
+            auto* e = entries[i];
+            rows.push_back(Q18Row{std::string(e->name.view()), e->custkey, e->orderkey, (int32_t) (e->orderdateNs / 86400000000000ll), e->totalprice, e->sumQty});
+         }
+      },
+      &rows);
+   std::sort(rows.begin(), rows.end(), [](const Q18Row& a, const Q18Row& b) {
+      if (a.totalprice != b.totalprice) return a.totalprice > b.totalprice;
+      if (a.orderdate != b.orderdate) return a.orderdate < b.orderdate;
+      return a.orderkey < b.orderkey;
+   });
+   if (rows.size() > 100) rows.resize(100);
+   *seconds = now() - t0;
+   return rows;
+}
+
 } // namespace oracle

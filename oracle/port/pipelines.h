@@ -79,4 +79,12 @@ struct Q12Row {
 };
 std::vector<Q12Row> runQ12(const HostTable& orders, const HostTable& lineitem, const Q12Params& p, double* seconds);
 
+// Q18: a group-by with as many groups as orders (the PreAggregationHashtable merge path at scale), HAVING, semi-join, top-100
+struct Q18Row {
+   std::string name;
+   int32_t custkey, orderkey, orderdate;
+   int64_t totalprice, sumQuantity; // decimal(12,2) raw
+};
+std::vector<Q18Row> runQ18(const HostTable& customer, const HostTable& orders, const HostTable& lineitem, int64_t quantityGt, double* seconds);
+
 } // namespace oracle

@@ -89,6 +89,9 @@ def test_oracle_q4_q12_twins_reproduce_the_references_answers(sf1):
         od, li = o.table(sf1["orders"]), o.table(sf1["lineitem"])
         assert [[r["o_orderpriority"], str(r["order_count"])] for r in o.q4(od, li)[0]] == GOLD["q4_rows"]  # tpchSf1.test:20455-20459
         assert [[r["l_shipmode"], str(r["high_line_count"]), str(r["low_line_count"])] for r in o.q12(od, li)[0]] == GOLD["q12_rows"]  # :1197-1198
+        # Q18: one group per order (1.5 M groups through PreAggregationHashtable::merge), HAVING, semi-join, top 100 (:19726-19782)
+        got = o.q18(o.table(sf1["customer"]), od, li)[0]
+        assert [[r["c_name"], str(r["c_custkey"]), str(r["o_orderkey"]), day(r["o_orderdate"]), dec(r["o_totalprice"], 2), dec(r["sum_quantity"], 2)] for r in got] == GOLD["q18_rows"]
 
 
 @pytest.mark.gpu
