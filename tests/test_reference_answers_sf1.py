@@ -80,6 +80,45 @@ def test_next_columns_reproduce_q4_and_q12(sf1):
     assert got == GOLD["q12_rows"]
 
 
+def test_data_also_reproduces_q7_and_q21(sf1):
+    """Two more answers evaluated in numpy on the same tables (no new columns: o_orderstatus and s_name are derived as dbgen
+    derives them): Q7 (:20550-20553) and Q21 with its EXISTS / NOT EXISTS pair (:20244-20343)."""
+    import collections
+    from lingodb_b200 import datagen
+    cat = lambda t, k: np.concatenate([c[k] for c in sf1[t].chunks])
+    lo = lambda a: a[:, :8].copy().view(np.int64).reshape(-1)
+    d = lambda s: (datetime.date.fromisoformat(s) - datetime.date(1970, 1, 1)).days
+    lkey, lsupp, lship, lcommit, lreceipt, lstat = (cat("lineitem", k) for k in ("l_orderkey", "l_suppkey", "l_shipdate", "l_commitdate", "l_receiptdate", "l_linestatus"))
+    counts = np.diff(np.r_[0, np.flatnonzero(np.r_[np.diff(lkey) != 0, True]) + 1])
+    n_o = len(counts)
+    oidx = np.repeat(np.arange(n_o), counts)
+    snat, cnat, ocust = cat("supplier", "s_nationkey"), cat("customer", "c_nationkey"), cat("orders", "o_custkey")
+    names = [n for n, _ in datagen.NATIONS]
+    # ---- Q7
+    fr, ge = names.index("FRANCE"), names.index("GERMANY")
+    sn, cn = snat[lsupp - 1], cnat[ocust[oidx] - 1]
+    m = (lship >= d("1995-01-01")) & (lship <= d("1996-12-31")) & (((sn == fr) & (cn == ge)) | ((sn == ge) & (cn == fr)))
+    vol = lo(cat("lineitem", "l_extendedprice")) * (100 - lo(cat("lineitem", "l_discount")))
+    year = {int(x): (datetime.date(1970, 1, 1) + datetime.timedelta(days=int(x))).year for x in np.unique(lship[m])}
+    r7 = collections.Counter()
+    for a, b, s_, v in zip(sn[m].tolist(), cn[m].tolist(), lship[m].tolist(), vol[m].tolist()):
+        r7[(names[a], names[b], year[s_])] += v
+    assert [[a, b, str(y), dec(v, 4)] for (a, b, y), v in sorted(r7.items())] == GOLD["q7_rows"]
+    # ---- Q21: o_orderstatus = 'F' iff every line of the order is 'F'
+    n_f = np.bincount(oidx, weights=(lstat == ord("F")), minlength=n_o).astype(np.int64)
+    status_f = n_f == counts
+    late = lreceipt > lcommit
+    first = np.r_[0, np.cumsum(counts)]
+    waits = collections.Counter()
+    for r in np.flatnonzero(late & (snat[lsupp - 1] == names.index("SAUDI ARABIA")) & status_f[oidx]).tolist():
+        a, b = first[oidx[r]], first[oidx[r] + 1]
+        other = lsupp[a:b] != lsupp[r]
+        if other.any() and not (late[a:b] & other).any():
+            waits[int(lsupp[r])] += 1
+    top = sorted((("Supplier#%09d" % k, v) for k, v in waits.items()), key=lambda kv: (-kv[1], kv[0]))[:100]
+    assert [[n, str(v)] for n, v in top] == GOLD["q21_rows"]
+
+
 def test_oracle_q4_q12_twins_reproduce_the_references_answers(sf1):
     """Semi-join with marker (Q4) and conditional counts over a join (Q12) on the reference's runtime objects: the oracle side of the
     next widening step, pinned before the GPU operators exist."""
