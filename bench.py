@@ -1,16 +1,18 @@
 #!/usr/bin/env python
-"""bench.py — TPC-H SF100 Q1 (lineitem scan + 2-key hash aggregation) rows/s on N B200s.
+"""bench.py — TPC-H SF100 Q1 (lineitem scan + 2-key hash aggregation) rows/s on N B200s, plus Q3/Q5 (BASELINE.json's metric
+names all three), Q6 and Q9 as side entries.
 
 Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]`, one JSON line on rank 0.
-  step    = one pass of the Q1 pipeline (scan → filter → expressions → group-by) over the lineitem
-            partition resident in HBM, plus (N > 1) the NCCL all-gather + merge of the 4-group partials.
-  value   = lineitem rows of ALL ranks / max-over-ranks device time, inputs resident in HBM ("strong":
-            SF100 is split across the ranks by order range).
-  e2e     = the same step through the C-ABI with HOST (pinned) Arrow buffers: H2D staging of every
-            column batch and the D2H result read are inside the timed region.
+  step    = one pass of the Q1 pipeline (scan → filter → expressions → group-by) over the lineitem partition resident in HBM,
+            plus (N > 1) the peer-mapped all-merge of the 4-group partials over NVLink (one kernel, csrc/peer.cu).
+  value   = lineitem rows of ALL ranks / max-over-ranks device time, inputs resident in HBM ("strong": SF100 is split across
+            the ranks by order range).
+  e2e     = the same step through the C-ABI with HOST (pinned) Arrow buffers: H2D staging of every column batch (compressed
+            staging: host threads pack, the GPU unpacks — csrc/staging.cu) and the D2H result read are inside the timed region.
   roofline= scan_groupby kernel: algorithmic bytes (76 B/row) / CUDA-event kernel time.
-  cpu_baseline = the CPU oracle (reference runtime objects + restated pipelines, NOT the LLVM JIT) on
-            the box's host cores over a bounded sample of the same table.
+  parity  = every timed leg is gated: the CUDA result over the FULL table must equal the CPU oracle's on the same bytes.
+  cpu_baseline = the CPU oracle (reference runtime objects + restated pipelines, NOT the LLVM JIT) on the box's host cores
+            over a bounded sample of the same table.
 `--impl reference` times that CPU implementation alone on the same config (rank 0 only).
 """
 import argparse
@@ -43,9 +45,11 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-batch-rows", type=int, default=1 << 24)
     ap.add_argument("--cpu-sample-sf", type=float, default=20.0)
+    ap.add_argument("--merge", default="peer", choices=["peer", "nccl"], help="N>1: peer-mapped all-merge kernel (default) or NCCL all-gather + K7")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the Q6/Q3/Q5 side measurements")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-size oracle gates (profiling runs only)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the Q6/Q3/Q5/Q9 entries")
     return ap.parse_args()
 
 
@@ -54,6 +58,14 @@ def peaks():
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def host_available_bytes():
+    try:
+        import psutil
+        return int(psutil.virtual_memory().available)
+    except Exception:
+        return 64 << 30
 
 
 class ClockSampler:
@@ -93,52 +105,62 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- reference arm
-def host_lineitem_sample(sf, seed, cols, max_rows=None):
+def host_lineitem(sf, seed, cols, n_rows, gen_rows=1 << 23):
+    """lineitem prefix in host RAM as <= 2^20-row record batches.  Generated 8 Mi rows at a time by the host generator's
+    thread team (one contiguous slice per thread), so the pages of every column are first-touched by threads spread over all
+    cores of both sockets — the table ends up interleaved across the NUMA nodes at 64 Ki-row granularity."""
     from lingodb_b200 import datagen
     s = datagen.scale(sf, seed)
-    n = s.n_lineitem if max_rows is None else min(max_rows, s.n_lineitem)
-    return datagen.lineitem(s, cols, chunk_rows=1 << 20, n_rows=n), n
+    n_rows = min(n_rows, s.n_lineitem)
+    specs = [c for c in datagen.LINEITEM_SCHEMA if c.name in cols]
+    td = datagen.TableData("lineitem", specs)
+    b = 0
+    while b < n_rows:
+        n = min(gen_rows, n_rows - b)
+        big = datagen.lineitem(s, cols, chunk_rows=n, row_begin=b, n_rows=n)
+        arrs = big.chunks[0]
+        for o in range(0, n, 1 << 20):
+            m = min(1 << 20, n - o)
+            td.chunks.append({k: v[o:o + m] for k, v in arrs.items()})
+            td.chunk_rows.append(m)
+        b += n
+    return td, n_rows
 
 
-def best_oracle_workers(o, h):
-    """The oracle's std::thread scheduler shim stops scaling well before 2 hyper-threaded sockets are full:
-    give the CPU side the worker count it is fastest with (tried: all hardware threads, 1/2, 1/4, 1/8)."""
+def sweep_oracle_workers(o, run, cands=None):
+    """Give the CPU side the worker count it is fastest with: all hardware threads down to 1/8 of them (the scan is DRAM-bound
+    well before two hyper-threaded sockets are full).  Returns {workers: seconds}."""
     ncpu = os.cpu_count() or 1
     env = os.environ.get("ORACLE_PARALLELISM")
-    cands = [int(env)] if env else sorted({max(1, ncpu // d) for d in (1, 2, 4, 8)}, reverse=True)
-    best = None
+    if cands is None:
+        cands = [int(env)] if env else sorted({max(1, int(ncpu * f)) for f in (1, 0.75, 0.5, 0.375, 0.25, 0.125)}, reverse=True)
+    seen = {}
     for w in cands:
         o.set_workers(w)
-        o.q1(h)
-        _, sec = o.q1(h)
-        if best is None or sec < best[1]:
-            best = (w, sec)
-    o.set_workers(best[0])
-    return best[0], {w: None for w in cands}
-
-
-def time_oracle_q1(table_data, repeats):
-    from oracle import oracle as O
-    o = O.Oracle("auto", workers=0)
-    h = o.table(table_data)
-    best_oracle_workers(o, h)
-    rows, times = None, []
-    for _ in range(repeats):
-        rows, sec = o.q1(h)
-        times.append(sec)
-    return o, rows, times
+        run()
+        seen[w] = min(run(), run())
+    best = min(seen, key=seen.get)
+    o.set_workers(best)
+    return seen
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_sf = min(args.sf, args.cpu_sample_sf)
-    t, n = host_lineitem_sample(sample_sf, args.seed, Q1_COLS)
+    from lingodb_b200 import datagen
     from oracle import oracle as O
+    s = datagen.scale(args.sf, args.seed)
+    need = Q1_BYTES_PER_ROW * s.n_lineitem
+    avail = host_available_bytes()
+    # the full table when host RAM allows (it does on the 8xB200 box), else the largest prefix that leaves half of RAM free
+    n_rows = s.n_lineitem if need < 0.6 * avail else int(0.5 * avail / Q1_BYTES_PER_ROW)
+    t0 = time.perf_counter()
+    t, n = host_lineitem(args.sf, args.seed, Q1_COLS, n_rows)
+    gen_s = time.perf_counter() - t0
     o = O.Oracle("auto", workers=0)
     h = o.table(t)
-    best_oracle_workers(o, h)
+    sweep = sweep_oracle_workers(o, lambda: o.q1(h)[1])
     for _ in range(args.warmup):
         o.q1(h)
     t0 = time.perf_counter()
@@ -149,14 +171,16 @@ def run_reference(args):
     wall = time.perf_counter() - t0
     total = sum(secs)
     value = n * args.steps / total
-    sample = f"first {n} lineitem rows (SF{sample_sf:g}) of the SF{args.sf:g} table per step, tables resident in host RAM"
+    sample = (f"the full SF{args.sf:g} lineitem table ({n} rows) per step" if n == s.n_lineitem else f"first {n} lineitem rows of the SF{args.sf:g} table per step (host RAM bound)") + \
+        ", resident in host RAM, pages first-touched by generator threads on all cores (NUMA-interleaved)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000 * total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64/int128",
-        "data": "synthetic", "config": {"workload": f"TPC-H SF{args.sf:g} Q1 (lineitem scan + 2-key hash aggregation)", "sample": sample,
-                                        "timed_region": "pipelines only (reference executionTime)", "wall_s": wall},
+        "data": "synthetic", "config": {"workload": f"TPC-H SF{args.sf:g} Q1 (lineitem scan + 2-key hash aggregation)", "sf": args.sf, "lineitem_rows": n, "sample": sample,
+                                        "timed_region": "pipelines only (reference executionTime)", "wall_s": wall, "generate_s": gen_s},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": o.workers, "host_threads": os.cpu_count(), "kind": o.kind, "sample": sample,
-                         "note": "worker count = fastest of {all, 1/2, 1/4, 1/8} hardware threads; reference runtime objects + restated pipelines; the MLIR/LLVM JIT cannot be built here"},
+                         "worker_sweep_s": {str(k): v for k, v in sweep.items()},
+                         "note": "worker count = fastest of the sweep; reference runtime objects + restated pipelines; the MLIR/LLVM JIT cannot be built here"},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -164,18 +188,76 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------- our arm
+def device_table_to_host(tab, want=None, pinned=(), batch_rows=1 << 24):
+    """Copy a table's batches (DEVICE tensors from devgen, or host numpy chunks) to host RAM.  Returns (TableData with
+    <= 2^20-row chunks for the oracle, [(chunk dict, rows)] of the fixed-width columns in <= `batch_rows` batches for the
+    C-ABI's HOST path).  Columns in `pinned` land in pinned memory."""
+    import numpy as np
+    import torch
+
+    from lingodb_b200 import datagen
+    specs = [c for c in tab.columns if want is None or c.name in want]
+    td = datagen.TableData(tab.name, specs)
+    batches = []
+
+    def to_host(v, pin):
+        if isinstance(v, np.ndarray):
+            return v
+        if not pin:
+            return v.cpu().numpy()
+        h = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+        for b in range(0, v.shape[0], batch_rows):  # bounded transfers: one slice at a time
+            h[b:b + batch_rows].copy_(v[b:b + batch_rows])
+        return h.numpy()
+
+    for item in tab._keep:
+        if not isinstance(item, dict):
+            continue
+        host, n = {}, None
+        for c in specs:
+            v = item[c.name]
+            if c.phys == "utf8":
+                host[c.name] = (to_host(v[0], False), to_host(v[1], False))
+                n = host[c.name][0].shape[0] - 1
+            else:
+                host[c.name] = to_host(v, c.name in pinned)
+                n = host[c.name].shape[0]
+        torch.cuda.synchronize()
+        for b in range(0, n, 1 << 20):
+            m = min(1 << 20, n - b)
+            ch = {}
+            for c in specs:
+                a = host[c.name]
+                ch[c.name] = (a[0][b:b + m + 1], a[1]) if c.phys == "utf8" else a[b:b + m]
+            td.chunks.append(ch)
+            td.chunk_rows.append(m)
+        for b in range(0, n, batch_rows):
+            m = min(batch_rows, n - b)
+            batches.append(({c.name: host[c.name][b:b + m] for c in specs if c.phys != "utf8"}, m))
+    return td, batches
+
+
+def q1_sums(rows):
+    """Q1 rows → {(flag, status): (sum_qty, sum_base, sum_disc_price, sum_charge, count)} — the exactly mergeable part."""
+    return {(r["l_returnflag"], r["l_linestatus"]): (r["sum_qty"], r["sum_base_price"], r["sum_disc_price"], r["sum_charge"], r["count_order"]) for r in rows}
+
+
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-
-    from lingodb_b200 import datagen, devgen, parallel, runtime
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    ncpu = os.cpu_count() or 8
+    # one staging engine per rank: the ranks of a box share its cores
+    os.environ.setdefault("LDB_STAGING_THREADS", str(max(4, min(64, ncpu // 2) if world == 1 else (ncpu * 3 // 4) // world)))
+
+    from lingodb_b200 import datagen, devgen, parallel, runtime
+
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -185,17 +267,18 @@ def run_ours(args):
 
     ctx = runtime.Context(local)
     L = ctx.L
+    comm = parallel.Comm(ctx, rank, world) if world > 1 else None
     s = datagen.scale(args.sf, args.seed)
     # strong scaling: SF-sized lineitem split by order range
     o_lo, o_hi, r_lo, r_hi = parallel.order_range(s, rank, world)
     my_rows = r_hi - r_lo
-    extra = (not args.no_extra) and world == 1
-    extra_mg = (not args.no_extra) and world > 1
-    cols = ALL_COLS if (extra or extra_mg) else Q1_COLS
+    extra = not args.no_extra
+    cols = ALL_COLS if extra else Q1_COLS
     lineitem = devgen.lineitem(ctx, s, cols, row_begin=r_lo, n_rows=my_rows)
     tabs = {"lineitem": lineitem}
     tp = runtime.Tpch(ctx, tabs)
     total_rows = s.n_lineitem
+    notes = []
 
     gather_bufs = {}
 
@@ -203,13 +286,59 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
 
+    def gather_objects(obj):
+        if world == 1:
+            return [obj]
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
     def step_resident():
         st = tp.q1_partial()
         if world > 1:
-            parallel.allgather_merge_state(ctx, st, world, rank, gather_bufs)
+            if args.merge == "peer":
+                comm.allmerge(st)
+            else:
+                parallel.allgather_merge_state(ctx, st, world, rank, gather_bufs)
         rows = tp.q1_finish(st)
         runtime.state_destroy(ctx, st)
         return rows
+
+    # ---- host copy of this rank's shard (pinned): input of the e2e leg AND of the full-size oracle gate
+    avail = host_available_bytes()
+    host_cols = Q1_COLS
+    host_bytes = Q1_BYTES_PER_ROW * my_rows
+    have_host = (not args.no_e2e or not args.no_parity) and host_bytes * world < 0.6 * avail
+    if not have_host and not (args.no_e2e and args.no_parity):
+        notes.append(f"host copy skipped: {host_bytes * world >> 30} GiB needed, {avail >> 30} GiB available")
+    td_li = host_batches = None
+    if have_host:
+        td_li, host_batches = device_table_to_host(lineitem, host_cols, pinned=set(host_cols), batch_rows=args.e2e_batch_rows)
+
+    # ---- parity gate 1 (full size): resident CUDA result == oracle on the same bytes, merged across ranks
+    parity = {}
+    oracle = None
+    if have_host and not args.no_parity:
+        from oracle import oracle as O
+        oracle = O.Oracle("auto", workers=max(2, min(32, ncpu // 2) // world))
+        oh_li = oracle.table(td_li)
+        t0 = time.perf_counter()
+        mine = q1_sums(oracle.q1(oh_li)[0])
+        merged = {}
+        for part in gather_objects(mine):
+            for k, v in part.items():
+                cur = merged.get(k, (0, 0, 0, 0, 0))
+                merged[k] = tuple(a + b for a, b in zip(cur, v))
+        got_rows = step_resident()
+        if q1_sums(got_rows) != merged:
+            raise SystemExit(f"PARITY FAILURE (Q1 resident, rank {rank}): CUDA {q1_sums(got_rows)} != oracle {merged}")
+        for r in got_rows:  # avg = (sum * 10^19) sdiv count, recomputed from the merged exact sums
+            for name, ssum in (("avg_qty", r["sum_qty"]), ("avg_price", r["sum_base_price"])):
+                exp = abs(ssum * 10**19) // r["count_order"] * (1 if ssum >= 0 else -1)
+                if r[name] != exp:
+                    raise SystemExit(f"PARITY FAILURE (Q1 {name})")
+        parity["q1_resident"] = {"ok": True, "rows": total_rows, "oracle": oracle.kind, "seconds": time.perf_counter() - t0,
+                                 "what": "sums/counts of every group == oracle over the same bytes (all ranks' shards merged); averages recomputed"}
 
     # ---- warm-up + timed region (device-resident inputs, 45.6 GB at SF100 >> 126 MB L2)
     for _ in range(args.warmup):
@@ -234,7 +363,10 @@ def run_ours(args):
     barrier()
     launches = ctx.launch_count() - launches0
     k_ms, k_n = ctx.kernel_time("scan_groupby")
+    m_ms, m_n = ctx.kernel_time("peer_group_allmerge" if args.merge == "peer" else "group_merge")
     ctx.kernel_time_reset(False)
+    if comm:
+        comm.check()
     # device time of the timed region, max over ranks
     tmax = torch.tensor([ms_dev, wall_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -249,6 +381,9 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": "scanGroupByKernel<2 keys, 4 decimal cols, Q1 aggregates>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "frac_of": peak_src, "traffic": None, "algorithmic_bytes_per_launch": Q1_BYTES_PER_ROW * my_rows,
                 "kernel_ms_avg": k_avg_ms, "kernel_launches_timed": k_n, "kernel_share_of_step": (k_ms / ms_dev) if ms_dev else None}
+    if world > 1:
+        roofline["merge_kernel_ms_avg"] = m_ms / max(m_n, 1)
+        roofline["merge"] = "peer-mapped all-merge kernel over NVLink (csrc/peer.cu); its time includes waiting for the slowest rank" if args.merge == "peer" else "NCCL all_gather_into_tensor + K7"
     ncu = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(ncu):
         try:
@@ -261,22 +396,8 @@ def run_ours(args):
 
     # ---- e2e: HOST (pinned) Arrow buffers → C-ABI staging → pipeline → result read
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and have_host:
         specs = [c for c in datagen.LINEITEM_SCHEMA if c.name in Q1_COLS]
-        host_batches = []
-        b = 0
-        src = lineitem._keep[0]
-        while b < my_rows:
-            n = min(args.e2e_batch_rows, my_rows - b)
-            chunk = {}
-            for c in specs:
-                shape = (n, 16) if c.phys == "decimal128" else (n,)
-                h = torch.empty(shape, dtype=torch.uint8 if c.phys == "decimal128" else torch.int32, pin_memory=True)
-                h.copy_(src[c.name][b:b + n])
-                chunk[c.name] = h.numpy()
-            host_batches.append((chunk, n))
-            b += n
-        torch.cuda.synchronize()
         host_tab = runtime.Table(ctx, "lineitem", specs)
         tp_h = runtime.Tpch(ctx, {"lineitem": host_tab})
         h2d = Q1_BYTES_PER_ROW * my_rows
@@ -286,12 +407,16 @@ def run_ours(args):
             for chunk, n in host_batches:
                 host_tab.append_host(chunk, n)
             st = tp_h.q1_partial()
+            if world > 1 and args.merge == "peer":
+                comm.allmerge(st)
             r = tp_h.q1_finish(st)
             runtime.state_destroy(ctx, st)
             return r
 
-        rows_h = step_e2e()  # warm-up (allocates the staging pool)
-        assert rows_h == (rows if world == 1 else rows_h)
+        rows_h = step_e2e()  # warm-up (starts the staging engine, allocates its slots)
+        if rows_h != rows:  # parity gate 2: the staged (packed → unpacked) path gives the resident path's rows, bit for bit
+            raise SystemExit(f"PARITY FAILURE (Q1 e2e, rank {rank}): host-staged result differs from the resident result")
+        parity["q1_e2e"] = {"ok": True, "what": "rows through HOST staging == rows of the resident path (== oracle)"}
         barrier()
         ctx.synchronize()
         h2d0 = int(L.ldb_gpu_context_h2d_bytes(ctx.h))
@@ -301,100 +426,193 @@ def run_ours(args):
         ctx.synchronize()
         e2e_s = time.perf_counter() - t0
         h2d_step = (int(L.ldb_gpu_context_h2d_bytes(ctx.h)) - h2d0) // args.e2e_steps
-        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        # column-cache hit: the staged table stays in HBM (LingoDBTable.cpp:294-305 ownership), the same call reads it again
+        t0 = time.perf_counter()
+        for _ in range(3):
+            st = tp_h.q1_partial()
+            if world > 1 and args.merge == "peer":
+                comm.allmerge(st)
+            rc = tp_h.q1_finish(st)
+            runtime.state_destroy(ctx, st)
+        cached_s = (time.perf_counter() - t0) / 3
+        assert rc == rows
+        te = torch.tensor([e2e_s, cached_s], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te[0].item())
-        e2e = {"value": total_rows * args.e2e_steps / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": h2d_step * world,
-               "host_arrow_bytes_per_step": h2d * world, "staging": "decimal128(12,2) cells narrowed to their low 8 bytes by a host thread pool (hw/10 threads) before the copy; "
-               "int32/date32/fsb4 copied as they are",
-               "d2h_bytes_per_step": 64 * 136 * world, "steps": args.e2e_steps, "ms_per_step": 1000 * e2e_s / args.e2e_steps,
-               "batch_rows": args.e2e_batch_rows, "host_memory": "pinned", "note": "per-rank partial result; N>1 skips the cross-rank merge in this leg"}
+        e2e_s, cached_s = float(te[0].item()), float(te[1].item())
+        hsum = torch.tensor([h2d_step], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(hsum)
+        e2e = {"value": total_rows * args.e2e_steps / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": int(hsum.item()),
+               "host_arrow_bytes_per_step": h2d * world,
+               "staging": f"compressed staging: {os.environ['LDB_STAGING_THREADS']} host threads/rank pack 64Ki-value frame-of-reference blocks (1/2/4/8 B per value; decimal128(12,2) → its low 8 bytes first) "
+                          "into pinned slots, one CUDA stream per thread copies them and a kernel unpacks into the staged layout (csrc/staging.cu)",
+               "d2h_bytes_per_step": (64 * 140 + 16) * world, "steps": args.e2e_steps, "ms_per_step": 1000 * e2e_s / args.e2e_steps,
+               "batch_rows": args.e2e_batch_rows, "host_memory": "pinned", "cold": True,
+               "cached_value": total_rows / cached_s, "cached_note": "same C-ABI call with the table already staged (column-cache hit): no H2D, result D2H only; wall clock"}
         host_tab.clear()
-        del host_batches
 
     # ---- CPU baseline on a bounded sample of the same table (rank 0, N=1 only)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and have_host:
+        from oracle import oracle as O
         sample_sf = min(args.sf, args.cpu_sample_sf)
         s_s = datagen.scale(sample_sf, args.seed)
         n = min(my_rows, s_s.n_lineitem)
-        specs = [c for c in datagen.LINEITEM_SCHEMA if c.name in Q1_COLS]
-        td = datagen.TableData("lineitem", specs)
-        src = lineitem._keep[0]
-        host = {c.name: src[c.name][:n].cpu().numpy() for c in specs}
-        for b in range(0, n, 1 << 20):
-            m = min(1 << 20, n - b)
-            td.chunks.append({k: v[b:b + m] for k, v in host.items()})
-            td.chunk_rows.append(m)
-        o, orows, times = time_oracle_q1(td, 4)
-        sec = min(times[1:]) if len(times) > 1 else times[0]
+        td = datagen.TableData("lineitem", td_li.columns)
+        acc = 0
+        for ch, m in zip(td_li.chunks, td_li.chunk_rows):
+            if acc >= n:
+                break
+            m2 = min(m, n - acc)
+            td.chunks.append({k: v[:m2] for k, v in ch.items()})
+            td.chunk_rows.append(m2)
+            acc += m2
+        o = O.Oracle("auto", workers=0)
+        oh = o.table(td)
+        sweep = sweep_oracle_workers(o, lambda: o.q1(oh)[1])
+        sec = min(o.q1(oh)[1] for _ in range(3))
         cpu = {"value": n / sec, "unit": "rows/s", "cores": o.workers, "host_threads": os.cpu_count(), "kind": o.kind,
-               "sample": f"first {n} lineitem rows of the SF{args.sf:g} table (the SF{sample_sf:g} prefix), best of 3 after 1 warm-up, pipelines only",
-               "seconds": sec, "note": "reference runtime objects + restated pipelines (oracle/), not the MLIR/LLVM JIT"}
+               "sample": f"first {n} lineitem rows of the SF{args.sf:g} table (the SF{sample_sf:g} prefix), best of 3 after the worker sweep, pipelines only",
+               "seconds": sec, "worker_sweep_s": {str(k): v for k, v in sweep.items()},
+               "note": "reference runtime objects + restated pipelines (oracle/), not the MLIR/LLVM JIT; pinned host copy of the device table"}
 
-    # ---- side measurements for the other §8 configs (N = 1): Q6, Q3, Q5, Q9 on the same resident tables
+    # ---- the other §8 configs on the same resident tables (N = 1): Q3 and Q5 are BASELINE.json metric entries, Q6/Q9 ride along
     queries = None
-    if extra and rank == 0:
-        queries = {}
-        tabs.update({"orders": devgen.orders(ctx, s), "customer": devgen.customer(ctx, s), "supplier": devgen.supplier(ctx, s), **devgen.small_tables(ctx)})
-        tabs.update({"part": devgen.part(ctx, s), "partsupp": devgen.partsupp(ctx, s)})
-        tpx = runtime.Tpch(ctx, tabs)
-        n_ps = 4 * s.n_part
-        scanned = {"q6": s.n_lineitem, "q3": s.n_lineitem + s.n_orders + s.n_customer, "q5": s.n_lineitem + s.n_orders + s.n_customer + s.n_supplier + 30,
-                   "q9": s.n_lineitem + s.n_orders + n_ps + s.n_part + s.n_supplier + 25}
-        # Arrow physical widths of the referenced columns, each read once (p_name: 4 B offset + ~33 B text)
-        algo = {"q6": 52 * s.n_lineitem, "q3": 40 * s.n_lineitem + 16 * s.n_orders + 21 * s.n_customer,
-                "q5": 40 * s.n_lineitem + 12 * s.n_orders + 8 * s.n_customer + 8 * s.n_supplier,
-                "q9": 60 * s.n_lineitem + 24 * n_ps + 8 * s.n_orders + 41 * s.n_part + 8 * s.n_supplier}
-        for name, fn in (("q6", tpx.q6), ("q3", tpx.q3), ("q5", tpx.q5), ("q9", tpx.q9)):
-            fn()
-            fn()
-            ctx.synchronize()
-            reps = 5
-            ctx.timer_start()
-            for _ in range(reps):
-                res = fn()
-            ms = ctx.timer_stop() / reps
-            queries[name] = {"ms": ms, "rows_per_s": scanned[name] / (ms / 1000), "algorithmic_gbs": algo[name] / (ms / 1000) / 1e9,
-                             "roofline_frac": algo[name] / (ms / 1000) / 1e9 / peak, "rows_scanned": scanned[name]}
-
-    # ---- N > 1: Q5 with the orders-lineitem join radix-partitioned across the ranks (K8 -> K6 -> NCCL all-to-all)
-    if extra_mg:
-        tabs.update({"orders": devgen.orders(ctx, s, row_begin=o_lo, n_rows=o_hi - o_lo), "customer": devgen.customer(ctx, s),
-                     "supplier": devgen.supplier(ctx, s), **devgen.small_tables(ctx)})
-        secs = []
-        for _ in range(4):
-            barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            q5rows, q5stats = parallel.q5_repartitioned(ctx, tabs, world, rank, s.n_orders)
-            torch.cuda.synchronize()
-            secs.append(time.perf_counter() - t0)
-        t5 = torch.tensor([min(secs[1:])], dtype=torch.float64, device=dev)
-        dist.all_reduce(t5, op=dist.ReduceOp.MAX)
-        scanned5 = s.n_lineitem + s.n_orders + s.n_customer + s.n_supplier + 30
-        queries = {"q5_repartitioned": {"ms": 1000 * float(t5.item()), "rows_per_s": scanned5 / float(t5.item()), "rows_scanned": scanned5,
-                                        "timing": "wall clock around the whole plan incl. host orchestration, max over ranks, best of 3",
-                                        "rank0_shuffle": q5stats, "result": [[r["n_name"], r["revenue"]] for r in q5rows]}}
+    metrics = None
+    if extra and world == 1:
+        queries, metrics = side_queries(args, ctx, s, tabs, lineitem, td_li, oracle, peak, parity, notes)
+    elif extra and world > 1:
+        queries = side_queries_multi(args, ctx, comm, s, tabs, rank, world, o_lo, o_hi, dev, notes)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64/int128", "data": "synthetic",
             "config": {"workload": f"TPC-H SF{args.sf:g} Q1 (lineitem scan + 2-key hash aggregation) on {world}xB200", "sf": args.sf, "lineitem_rows": total_rows,
-                       "rows_per_gpu": my_rows, "partitioning": "order-range split, NCCL all-gather of 4-group partials" if world > 1 else "single GPU",
+                       "rows_per_gpu": my_rows, "partitioning": ("order-range split; partial group tables merged by a peer-mapped NVLink kernel" if args.merge == "peer" else "order-range split; NCCL all-gather of the partials") if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (45.6 GB of columns per pass at SF100 vs 126 MB L2)", "arrow_layout": "decimal128 16 B/value, date32, fixed_size_binary(4)",
                        "generator": "deterministic TPC-H-shaped generator on device (csrc/datagen.cu), seed %d" % args.seed, "wall_ms_per_step": wall_total / args.steps,
                        "result_rows": len(rows)},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity": parity,
         }
+        if metrics:
+            line["metrics"] = metrics
         if queries:
             line["other_queries"] = queries
+        if notes:
+            line["notes"] = notes
         print(json.dumps(line), flush=True)
+    if comm:
+        ctx.synchronize()
+        barrier()
+        comm.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+KERNEL_FAMILIES = ["scan_reduce", "scan_groupby", "join_build", "join_probe_agg", "join_probe2_groupby", "join_star_probe_groupby", "join_topk", "table_init",
+                   "column_range", "materialize", "partition", "group_merge"]
+
+
+def side_queries(args, ctx, s, tabs, lineitem, td_li, oracle, peak, parity, notes):
+    """Q6/Q3/Q5/Q9 on one GPU: parity gate (full-size oracle where host RAM and time allow), then 5 timed repetitions with the
+    per-kernel-family CUDA-event times of the timed region (roofline of the whole query = algorithmic bytes / query time)."""
+    from lingodb_b200 import devgen, runtime
+    tabs.update({"orders": devgen.orders(ctx, s), "customer": devgen.customer(ctx, s), "supplier": devgen.supplier(ctx, s), **devgen.small_tables(ctx)})
+    tabs.update({"part": devgen.part(ctx, s), "partsupp": devgen.partsupp(ctx, s)})
+    tpx = runtime.Tpch(ctx, tabs)
+    n_ps = 4 * s.n_part
+    scanned = {"q6": s.n_lineitem, "q3": s.n_lineitem + s.n_orders + s.n_customer, "q5": s.n_lineitem + s.n_orders + s.n_customer + s.n_supplier + 30,
+               "q9": s.n_lineitem + s.n_orders + n_ps + s.n_part + s.n_supplier + 25}
+    # SURVEY.md §8(d): Arrow physical widths of the referenced columns, each read once (p_name: 4 B offset + ~33 B text)
+    algo = {"q6": 52 * s.n_lineitem, "q3": 40 * s.n_lineitem + 16 * s.n_orders + 21 * s.n_customer,
+            "q5": 40 * s.n_lineitem + 12 * s.n_orders + 8 * s.n_customer + 8 * s.n_supplier,
+            "q9": 60 * s.n_lineitem + 24 * n_ps + 8 * s.n_orders + 41 * s.n_part + 8 * s.n_supplier}
+    # ---- parity gates at full size: host copies of the build sides + the lineitem key columns (pageable)
+    gate = {}
+    if oracle is not None and td_li is not None and not args.no_parity:
+        try:
+            t0 = time.perf_counter()
+            td_keys, _ = device_table_to_host(lineitem, ["l_orderkey", "l_partkey", "l_suppkey"])
+            for ch, kc in zip(td_li.chunks, td_keys.chunks):
+                ch.update(kc)
+            td_li.columns = list(td_li.columns) + [c for c in td_keys.columns]
+            oh = {"lineitem": oracle.table(td_li)}
+            for name in ("orders", "customer", "supplier", "nation", "region", "part", "partsupp"):
+                oh[name] = oracle.table(device_table_to_host(tabs[name])[0])
+            oracle.set_workers(min(32, max(2, (os.cpu_count() or 8) // 2)))
+            gate["q6"] = lambda: oracle.q6(oh["lineitem"])[0]
+            gate["q3"] = lambda: oracle.q3(oh["customer"], oh["orders"], oh["lineitem"])[0]
+            gate["q5"] = lambda: oracle.q5(oh["customer"], oh["orders"], oh["lineitem"], oh["supplier"], oh["nation"], oh["region"])[0]
+            gate["q9"] = lambda: oracle.q9(oh["part"], oh["supplier"], oh["lineitem"], oh["partsupp"], oh["orders"], oh["nation"])[0]
+            notes.append(f"host copies for the Q3/Q5/Q9 gates: {time.perf_counter() - t0:.1f} s")
+        except MemoryError:
+            notes.append("Q3/Q5/Q9 gates skipped: host RAM")
+    queries, metrics = {}, []
+    for name, fn in (("q6", tpx.q6), ("q3", tpx.q3), ("q5", tpx.q5), ("q9", tpx.q9)):
+        res = fn()
+        if name in gate:  # parity gate in front of the timed leg
+            t0 = time.perf_counter()
+            exp = gate[name]()
+            if res != exp:
+                raise SystemExit(f"PARITY FAILURE ({name} at SF{args.sf:g}): CUDA {str(res)[:300]} != oracle {str(exp)[:300]}")
+            parity[name] = {"ok": True, "oracle_seconds": time.perf_counter() - t0, "what": f"full result rows == oracle at SF{args.sf:g}"}
+        fn()
+        ctx.synchronize()
+        reps = 5
+        ctx.kernel_time_reset(True)
+        ctx.timer_start()
+        for _ in range(reps):
+            res = fn()
+        ms = ctx.timer_stop() / reps
+        kern = {}
+        for fam in KERNEL_FAMILIES:
+            kms, kn = ctx.kernel_time(fam)
+            if kn:
+                kern[fam] = {"ms_per_query": kms / reps, "launches_per_query": kn / reps}
+        ctx.kernel_time_reset(False)
+        gbs = algo[name] / (ms / 1000) / 1e9
+        queries[name] = {"ms": ms, "rows_per_s": scanned[name] / (ms / 1000), "rows_scanned": scanned[name], "kernels": kern,
+                         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "algorithmic_bytes": algo[name],
+                                      "kernel_ms_sum": sum(k["ms_per_query"] for k in kern.values())},
+                         "parity": "oracle ok" if name in parity else "not gated"}
+        if name in ("q3", "q5"):
+            metrics.append({"metric": f"TPC-H SF{args.sf:g} {name.upper()} rows/sec", "value": scanned[name] / (ms / 1000), "unit": "rows/s", "ms_per_query": ms,
+                            "roofline_frac": gbs / peak, "parity": queries[name]["parity"]})
+    return queries, metrics
+
+
+def side_queries_multi(args, ctx, comm, s, tabs, rank, world, o_lo, o_hi, dev, notes):
+    """N > 1: Q9 with lineitem ⋈ orders co-partitioned by order range (no exchange), group tables merged over NVLink."""
+    import torch
+    import torch.distributed as dist
+
+    from lingodb_b200 import devgen, parallel, runtime
+    tabs.update({"orders": devgen.orders(ctx, s, row_begin=o_lo, n_rows=o_hi - o_lo), "customer": devgen.customer(ctx, s),
+                 "supplier": devgen.supplier(ctx, s), **devgen.small_tables(ctx)})
+    tabs.update({"part": devgen.part(ctx, s), "partsupp": devgen.partsupp(ctx, s)})
+    tpx = runtime.Tpch(ctx, tabs)
+    queries = {}
+    res = parallel.q9_sharded(ctx, tpx, world, rank, {}, comm=comm)
+    parallel.q9_sharded(ctx, tpx, world, rank, {}, comm=comm)
+    ctx.synchronize()
+    dist.barrier()
+    reps = 3
+    ctx.timer_start()
+    for _ in range(reps):
+        res = parallel.q9_sharded(ctx, tpx, world, rank, {}, comm=comm)
+    ms = ctx.timer_stop() / reps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    n_ps = 4 * s.n_part
+    scanned = s.n_lineitem + s.n_orders + world * (n_ps + s.n_part + s.n_supplier + 25)
+    queries["q9_sharded"] = {"ms": float(t.item()), "rows_per_s": scanned / (float(t.item()) / 1000), "rows_scanned": scanned, "groups": len(res),
+                             "checksum_sum_profit": sum(r["sum_profit"] for r in res),
+                             "plan": "lineitem and orders sharded by the same order range (co-partitioned join), part/partsupp/supplier replicated, peer-mapped all-merge of the 175-group tables"}
+    comm.check()
+    return queries
 
 
 def main():

@@ -9,7 +9,7 @@
  * passes CODE.  Each entry point cites the reference interface it replaces.
  *
  * Conventions: plain C, no exceptions; every call returns LDB_OK (0) or an error code and fills
- * `err` (may be NULL).  The C++ shim (lingo-db_b200/csrc/runtime_shim.h) rethrows as
+ * `err` (may be NULL).  The C++ shim (integration/GPUPipeline.cpp) rethrows as
  * std::runtime_error to match the reference's convention (e.g. src/runtime/Hashtable.cpp:106).
  * Ownership mirrors ExecutionContext::registerState (include/lingodb/runtime/ExecutionContext.h:111-113):
  * states belong to the context and die with it; callers never free device memory themselves.
@@ -280,6 +280,40 @@ int ldb_gpu_partition_tuples(LdbContext* ctx, const int32_t* keys, const void* c
                              int32_t* out_keys, void* const* out_payload_cols, int64_t* out_part_offsets /* n_parts+1, host */, LdbError* err);
 /* insert already-materialised tuples (e.g. received from peers) into a JoinTable */
 int ldb_gpu_join_table_insert(LdbContext* ctx, LdbState* table, const int32_t* keys, const int32_t* payloads, const int32_t* const* side_cols, int64_t n_rows, LdbError* err);
+
+/* ------------------------------------------------------------------------------------ multi-GPU: peer-mapped exchange
+ * No reference counterpart (the reference is single-process; SURVEY §2 "Parallelism strategies", §8(e)).  One process per
+ * GPU; every rank owns a symmetric heap its peers map through CUDA IPC, and a transfer is a kernel that stores into the
+ * peer's HBM over NVLink 5 / NVSwitch and publishes a flag — no NCCL call and no host round trip on the data path
+ * (csrc/peer.cu).  Bootstrap: each rank creates its comm, the 64-byte handles are exchanged by the caller (any transport:
+ * torch.distributed, MPI, a file) and passed to ldb_gpu_comm_connect in rank order.  Collectives are enqueued on the
+ * context's compute stream and must be called by every rank in the same order. */
+typedef struct LdbComm LdbComm;
+#define LDB_IPC_HANDLE_BYTES 64
+int ldb_gpu_comm_create(LdbContext* ctx, int32_t rank, int32_t world, int64_t user_heap_bytes, LdbComm** out, uint8_t* handle_out /* 64 */, LdbError* err);
+int ldb_gpu_comm_connect(LdbComm* comm, const uint8_t* all_handles /* world x 64, rank order */, LdbError* err);
+/* one process driving several devices (tests): comms[i] is rank i of a world of n */
+int ldb_gpu_comm_connect_local(LdbComm** comms, int32_t n, LdbError* err);
+void ldb_gpu_comm_destroy(LdbComm* comm);
+int32_t ldb_gpu_comm_rank(LdbComm* comm);
+int32_t ldb_gpu_comm_world(LdbComm* comm);
+int64_t ldb_gpu_comm_reserved_bytes(void); /* control + mailbox bytes in front of the user region */
+int64_t ldb_gpu_comm_slot_bytes(void);     /* largest block of ldb_gpu_comm_allgather_small */
+/* the user region of this rank's heap (device pointer); the same offset addresses the same region on every peer */
+void* ldb_gpu_comm_heap(LdbComm* comm, int64_t* user_bytes);
+/* device-side barrier: orders everything this rank stored into peer heaps before it against the peers' later reads */
+int ldb_gpu_comm_barrier(LdbComm* comm, LdbError* err);
+/* all-gather of one small DEVICE block (multiple of 16 bytes, <= slot bytes); *result = device address of the gathered
+ * blocks (rank r at r * slot_bytes), valid until the next-but-one gather */
+int ldb_gpu_comm_allgather_small(LdbComm* comm, const void* dev_src, int64_t bytes, void** result, LdbError* err);
+/* K7 over NVLink (rt::PreAggregationHashtable::merge across GPUs): every rank pushes its group-table image to every peer
+ * and folds the peers' images into its own table — ONE kernel instead of export + all-gather + merge.  Afterwards every
+ * rank holds the full result.  SIMPLE and GROUPBY states (capacity <= 1024). */
+int ldb_gpu_groupby_allmerge(LdbState* s, LdbComm* comm, LdbError* err);
+/* OR-all-reduce of heap[user_offset, +bytes) across the ranks (Bloom filters of hash partitions); barrier before and after */
+int ldb_gpu_comm_or_reduce(LdbComm* comm, int64_t user_offset, int64_t bytes, LdbError* err);
+/* synchronises and reports a collective that timed out on a dead peer (LDB_PEER_TIMEOUT_MS, default 20000) */
+int ldb_gpu_comm_check(LdbComm* comm, LdbError* err);
 
 /* ------------------------------------------------------------------------------------ value-level hooks
  * Device twins of util.hash_64 / hash_combine (LowerToLLVM.cpp:493-514), exported for the KAT tests:

@@ -6,4 +6,4 @@ The directory name carries a hyphen (fixed by the task layout); import it as `li
 """
 from . import build  # noqa: F401
 
-__all__ = ["build", "datagen", "capi", "runtime", "tpch"]
+__all__ = ["build", "datagen", "capi", "runtime", "parallel", "devgen", "dbgen", "arrow_io"]

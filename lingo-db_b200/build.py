@@ -101,9 +101,10 @@ def _build_datagen_host(verbose=False, force=False):
 
 def _build_gpu(verbose=False, force=False, ptxas_verbose=False):
     cu = _sources((".cu",))
-    cpp = [p for p in _sources((".cpp",)) if not p.endswith("datagen_host.cpp")]
+    cpp = [p for p in _sources((".cpp",)) if not p.endswith("_host.cpp")]
+    host_cpp = [p for p in _sources((".cpp",)) if p.endswith("_host.cpp") and not p.endswith("datagen_host.cpp")]  # g++ only (function multi-versioning)
     hdr = _sources((".h", ".cuh")) + [os.path.join(INCLUDE, f) for f in sorted(os.listdir(INCLUDE))]
-    stamp = _stamp(cu + cpp + hdr, " ".join(NVCC_FLAGS).replace(ROOT, "$ROOT"))
+    stamp = _stamp(cu + cpp + host_cpp + hdr, " ".join(NVCC_FLAGS).replace(ROOT, "$ROOT"))
     if not force and _up_to_date(GPU_LIB, stamp):
         return GPU_LIB
     objdir = os.path.join(HERE, "build")
@@ -114,6 +115,13 @@ def _build_gpu(verbose=False, force=False, ptxas_verbose=False):
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
         objs.append(obj)
         cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_verbose else []) + ["-x", "cu", "-c", src, "-o", obj]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src in host_cpp:
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        objs.append(obj)
+        cmd = [CXX, "-std=c++17", "-O3", "-fPIC", "-Wall", "-c", src, "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -144,6 +144,20 @@ SIGNATURES = {
     "ldb_gpu_run_pipeline": (C.c_int, [_P, C.POINTER(PipelineDesc), _E]),
     "ldb_gpu_partition_tuples": (C.c_int, [_P, _P, C.POINTER(_P), C.POINTER(C.c_int32), C.c_int32, C.c_int64, C.c_int32, _P, C.POINTER(_P), C.POINTER(C.c_int64), _E]),
     "ldb_gpu_join_table_insert": (C.c_int, [_P, _P, _P, _P, C.POINTER(_P), C.c_int64, _E]),
+    "ldb_gpu_comm_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, C.POINTER(_P), _P, _E]),
+    "ldb_gpu_comm_connect": (C.c_int, [_P, _P, _E]),
+    "ldb_gpu_comm_connect_local": (C.c_int, [C.POINTER(_P), C.c_int32, _E]),
+    "ldb_gpu_comm_destroy": (None, [_P]),
+    "ldb_gpu_comm_rank": (C.c_int32, [_P]),
+    "ldb_gpu_comm_world": (C.c_int32, [_P]),
+    "ldb_gpu_comm_reserved_bytes": (C.c_int64, []),
+    "ldb_gpu_comm_slot_bytes": (C.c_int64, []),
+    "ldb_gpu_comm_heap": (C.c_void_p, [_P, C.POINTER(C.c_int64)]),
+    "ldb_gpu_comm_barrier": (C.c_int, [_P, _E]),
+    "ldb_gpu_comm_allgather_small": (C.c_int, [_P, _P, C.c_int64, C.POINTER(_P), _E]),
+    "ldb_gpu_groupby_allmerge": (C.c_int, [_P, _P, _E]),
+    "ldb_gpu_comm_or_reduce": (C.c_int, [_P, C.c_int64, C.c_int64, _E]),
+    "ldb_gpu_comm_check": (C.c_int, [_P, _E]),
     "ldb_gpu_hash_i64": (C.c_int, [_P, _P, _P, C.c_int64, _P, _E]),
     "ldb_gpu_datagen_lineitem": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, C.POINTER(LineitemCols), _E]),
     "ldb_gpu_datagen_orders": (C.c_int, [_P, C.POINTER(GenScale), C.c_int64, C.c_int64, C.POINTER(OrdersCols), _E]),

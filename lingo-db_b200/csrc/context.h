@@ -4,6 +4,7 @@
 #include "kernels.h"
 
 #include <cuda_runtime.h>
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <map>
@@ -62,6 +63,9 @@ struct KernelFamilyTimer {
    int64_t launches = 0;
 };
 
+class StagingEngine;
+struct PackedBatch;
+
 } // namespace ldb
 
 struct LdbState;
@@ -88,7 +92,12 @@ struct LdbContext {
    static constexpr size_t kPinnedSlotBytes = 32u << 20;
    std::vector<ldb::PinnedSlot> pinned;
    size_t nextPinned = 0;
-   int64_t h2dBytes = 0; // bytes this context copied host→device while staging tables
+   std::atomic<int64_t> h2dBytes{0}; // bytes this context copied host→device while staging tables
+   // compressed staging (staging.h): HOST batches of >= one block are re-encoded by a pool of independent pipelines
+   bool packedStaging = true;
+   std::shared_ptr<ldb::StagingEngine> staging;
+   std::atomic<uint64_t> stagingGen{0};      // bumped by ldb_gpu_table_clear: workers order their next write after computeDone
+   std::atomic<int64_t> stagingLaunches{0};  // unpack kernels launched by the staging workers
 
    void* stagingAlloc(size_t bytes);
    void stagingRelease(void* p);
@@ -119,6 +128,7 @@ struct LdbBatch {
    std::vector<int32_t> elemBytes; // per column: bytes per value as staged (decimal128: 16, or 8 when narrowed)
    std::vector<void*> owned;       // staging buffers to give back on clear
    cudaEvent_t ready = nullptr;    // H2D of this batch finished (null for borrowed device batches)
+   std::shared_ptr<ldb::PackedBatch> packed; // columns staged through the compressed staging engine (host wait + worker events)
 };
 struct LdbColumn {
    std::string name;
@@ -144,5 +154,6 @@ struct LdbState {
    ldb::GroupTableDev group{}; // SIMPLE / GROUPBY
    ldb::JoinTableDev join{};   // JOIN_TABLE
    int32_t nSide = 0, nAggs = 0;
+   uint32_t is64Mask = 0; // aggregates that are 64-bit sums (COL / ONE): normalised to a sign-extended i64 on read
    std::vector<void*> allocations;
 };

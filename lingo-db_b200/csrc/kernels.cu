@@ -378,12 +378,14 @@ __device__ __forceinline__ BloomProbe bloomPrefetch(const JoinTableDev& t, int32
    if (!wanted) b.bits = 1u; // word == 0 → mayContain() false
    return b;
 }
-template <class Fn>
+// COHERENT: the probed entries are written by the same kernel (K5 sets the marker bit in the payload word) → plain loads, not
+// the read-only (ld.global.nc) path
+template <bool COHERENT = false, class Fn>
 __device__ __forceinline__ void joinProbeSlots(const JoinTableDev& t, int32_t key, uint64_t h, const Fn& fn) {
    uint64_t s = h & t.mask;
    const uint64_t limit = t.mask < kMaxProbe ? t.mask + 1 : kMaxProbe;
    for (uint64_t probes = 0; probes < limit; probes++) {
-      unsigned long long e = __ldg(slotPtr(t, s));
+      unsigned long long e = COHERENT ? *((const volatile unsigned long long*) slotPtr(t, s)) : __ldg(slotPtr(t, s));
       if (e == kEmptySlot) return;
       if ((int32_t) (uint32_t) e == key) {
          fn((int64_t) s, (int32_t) (uint32_t) (e >> 32));
@@ -1181,7 +1183,7 @@ __global__ void __launch_bounds__(kThreads, 4) scanProbeAggKernel(const __grid_c
 #pragma unroll
       for (int j = 0; j < kRowsPerThreadProbe; j++) {
          if (!bp[j].mayContain()) continue;
-         joinProbeSlots(p.table, key[j], bp[j].h, [&](int64_t slot, int32_t payloadWord) {
+         joinProbeSlots<true>(p.table, key[j], bp[j].h, [&](int64_t slot, int32_t payloadWord) {
             int64_t vals[NV];
 #pragma unroll
             for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lrs[j]);
@@ -1266,7 +1268,7 @@ __global__ void __launch_bounds__(kThreads, 4) scanProbe2GroupByKernel(const __g
                int64_t vals[NV];
 #pragma unroll
                for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lrs[j]);
-               int32_t kk[2] = {payB, 0};
+               int32_t kk[2] = {p.tableB.stride == 32 ? (payB & 0x7fffffff) : payB, 0}; // bit 31 of a wide entry is the group-join marker, not payload
                int slot = groupLookupOrInsert(p.groups, kk);
                if (slot >= 0) groupAtomicAdd(p.groups, slot, 0, evalAggDyn(p.agg, vals, one), p.agg.expr == LDB_EXPR_COL || p.agg.expr == LDB_EXPR_ONE);
             });
@@ -1389,10 +1391,13 @@ __device__ __forceinline__ bool topkBefore(const TopKRowDev& a, const TopKRowDev
 constexpr int kTopKMax = 64;
 __global__ void __launch_bounds__(kBlock) joinTopKKernel(JoinTableDev t, int k, TopKRowDev* out) {
    __shared__ TopKRowDev best[kTopKMax];
+   __shared__ TopKRowDev sKth; // published copy of best[k - 1] (valid once sCount == k), guarded by sSeq
+   __shared__ unsigned sSeq;
    __shared__ int sCount, sLock;
    if (threadIdx.x == 0) {
       sCount = 0;
       sLock = 0;
+      sSeq = 0;
    }
    __syncthreads();
    const uint64_t cap = t.mask + 1;
@@ -1411,15 +1416,19 @@ __global__ void __launch_bounds__(kBlock) joinTopKKernel(JoinTableDev t, int k, 
       c.valid = 1;
       c.aggLo = *(const unsigned long long*) (entry + 16);
       c.aggHi = *(const long long*) (entry + 24);
-      // cheap reject against the current k-th without the lock
-      int cnt = *((volatile int*) &sCount);
-      if (cnt == k) {
+      // cheap reject against the current k-th without the lock: the k-th entry is republished under a sequence counter
+      // (odd while the holder shifts entries), so a reader either sees a consistent snapshot or falls through to the lock
+      if (*((volatile int*) &sCount) == k) {
+         const unsigned seq0 = *((volatile unsigned*) &sSeq);
+         __threadfence_block();
          TopKRowDev last;
-         last.key = ((volatile TopKRowDev*) best)[k - 1].key;
-         last.side0 = ((volatile TopKRowDev*) best)[k - 1].side0;
-         last.aggLo = ((volatile TopKRowDev*) best)[k - 1].aggLo;
-         last.aggHi = ((volatile TopKRowDev*) best)[k - 1].aggHi;
-         if (!topkBefore(c, last)) continue;
+         last.key = ((volatile TopKRowDev*) &sKth)->key;
+         last.side0 = ((volatile TopKRowDev*) &sKth)->side0;
+         last.aggLo = ((volatile TopKRowDev*) &sKth)->aggLo;
+         last.aggHi = ((volatile TopKRowDev*) &sKth)->aggHi;
+         __threadfence_block();
+         const unsigned seq1 = *((volatile unsigned*) &sSeq);
+         if (seq0 == seq1 && !(seq0 & 1u) && !topkBefore(c, last)) continue;
       }
       bool done = false;
       while (!done) {
@@ -1432,6 +1441,18 @@ __global__ void __launch_bounds__(kBlock) joinTopKKernel(JoinTableDev t, int k, 
                int end = n < k ? n : k - 1;
                for (int i = end; i > pos; i--) best[i] = best[i - 1];
                best[pos] = c;
+               const int n2 = n < k ? n + 1 : k;
+               if (n2 == k) { // republish the k-th before the count says "full"
+                  *((volatile unsigned*) &sSeq) = sSeq + 1;
+                  __threadfence_block();
+                  ((volatile TopKRowDev*) &sKth)->key = best[k - 1].key;
+                  ((volatile TopKRowDev*) &sKth)->side0 = best[k - 1].side0;
+                  ((volatile TopKRowDev*) &sKth)->aggLo = best[k - 1].aggLo;
+                  ((volatile TopKRowDev*) &sKth)->aggHi = best[k - 1].aggHi;
+                  __threadfence_block();
+                  *((volatile unsigned*) &sSeq) = sSeq + 1;
+                  __threadfence_block();
+               }
                if (n < k) *((volatile int*) &sCount) = n + 1;
             }
             __threadfence_block();
@@ -1527,8 +1548,10 @@ void launchHashI64(const int64_t* a, const int64_t* b, int64_t n, uint64_t* out,
 }
 // K7: fold partial groups (e.g. gathered from the other GPUs) into the table
 __global__ void groupMergeRowsKernel(GroupTableDev t, const int32_t* keys, const unsigned long long* acc, int32_t nRows) {
-   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nRows * t.nAggs; i += gridDim.x * blockDim.x) {
-      int r = i / t.nAggs, a = i % t.nAggs;
+   const int64_t total = (int64_t) nRows * t.nAggs;
+   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t) gridDim.x * blockDim.x) {
+      const int64_t r = i / t.nAggs;
+      const int a = (int) (i % t.nAggs);
       int32_t kk[2] = {keys[r * kMaxKeys], keys[r * kMaxKeys + 1]};
       int slot = groupLookupOrInsert(t, kk);
       if (slot < 0) continue;
@@ -1538,22 +1561,24 @@ __global__ void groupMergeRowsKernel(GroupTableDev t, const int32_t* keys, const
    }
 }
 void launchGroupMergeRows(const GroupTableDev& t, const int32_t* keys, const unsigned long long* acc, int32_t nRows, cudaStream_t s) {
-   int total = nRows * t.nAggs;
-   int grid = std::max(1, std::min((total + 127) / 128, 256));
+   const int64_t total = (int64_t) nRows * t.nAggs;
+   int grid = (int) std::max<int64_t>(1, std::min<int64_t>((total + 127) / 128, 256));
    groupMergeRowsKernel<<<grid, 128, 0, s>>>(t, keys, acc, nRows);
 }
 
 // K7 (multi-GPU): fold the all-gathered table images of the other ranks into this rank's table
 __global__ void groupMergeImagesKernel(GroupTableDev t, const uint8_t* images, int nTables, int skip) {
    const size_t cap = (size_t) t.capacity;
-   const size_t imageBytes = cap * 4 + cap * kMaxKeys * 4 + cap * kMaxAggs * 2 * 8;
-   int total = nTables * t.capacity * t.nAggs;
-   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-      int a = i % t.nAggs, slotIdx = (i / t.nAggs) % t.capacity, tab = i / (t.nAggs * t.capacity);
+   const size_t imageBytes = groupImageBytes(t.capacity);
+   const int64_t total = (int64_t) nTables * t.capacity * t.nAggs;
+   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t) gridDim.x * blockDim.x) {
+      const int a = (int) (i % t.nAggs);
+      const int64_t slotIdx = (i / t.nAggs) % t.capacity;
+      const int tab = (int) (i / ((int64_t) t.nAggs * t.capacity));
       if (tab == skip) continue;
       const uint8_t* img = images + (size_t) tab * imageBytes;
       const int32_t* st = (const int32_t*) img;
-      if (st[slotIdx] != 2) continue;
+      if (t.nKeys != 0 && st[slotIdx] != 2) continue; // a keyless SimpleState has one always-occupied slot (its state word is never written)
       const int32_t* keys = (const int32_t*) (img + cap * 4) + (size_t) slotIdx * kMaxKeys;
       const unsigned long long* acc = (const unsigned long long*) (img + cap * 4 + cap * kMaxKeys * 4) + ((size_t) slotIdx * kMaxAggs + a) * 2;
       int32_t kk[2] = {keys[0], keys[1]};
@@ -1564,8 +1589,8 @@ __global__ void groupMergeImagesKernel(GroupTableDev t, const uint8_t* images, i
    }
 }
 void launchGroupMergeImages(const GroupTableDev& t, const uint8_t* images, int nTables, int skip, cudaStream_t s) {
-   int total = nTables * t.capacity * t.nAggs;
-   int grid = std::max(1, std::min((total + 127) / 128, 296));
+   const int64_t total = (int64_t) nTables * t.capacity * t.nAggs;
+   int grid = (int) std::max<int64_t>(1, std::min<int64_t>((total + 127) / 128, 296));
    groupMergeImagesKernel<<<grid, 128, 0, s>>>(t, images, nTables, skip);
 }
 

@@ -43,6 +43,10 @@ struct GroupTableDev {
    int32_t* error;           // set to 1 on overflow
 };
 
+// The table is ONE allocation laid out as the image ranks exchange: state[cap] | keys[cap][kMaxKeys] | acc[cap][kMaxAggs][2],
+// followed by the error word — so an export is a single copy and a peer can be handed the table itself.
+__host__ __device__ inline size_t groupImageBytes(int64_t capacity) { return (size_t) capacity * 4 + (size_t) capacity * kMaxKeys * 4 + (size_t) capacity * kMaxAggs * 2 * 8; }
+
 // ---- join table (rt::GrowingBuffer + rt::HashIndexedView twin; with agg lanes: the group-join map)
 // Open addressing, slot s at base + s * stride.  Two layouts:
 //   stride  8  {key:32, payload:32}                                              plain joins

@@ -3,6 +3,7 @@
 // src/runtime surface for the three hot paths; there is NO CPU fallback: without a CUDA device
 // every entry point fails with LDB_ERR_NO_DEVICE.
 #include "context.h"
+#include "staging.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -109,6 +110,18 @@ uint32_t opMask(int op) {
 }
 } // namespace
 
+namespace {
+// order the compute stream after the staging of one batch
+void waitBatch(LdbContext* ctx, const LdbBatch& b) {
+   if (b.ready) LDB_CUDA(cudaStreamWaitEvent(ctx->compute, b.ready, 0));
+   if (b.packed) { // compressed staging: every task of the batch issued (host), then order the scan after the workers' streams
+      StagingEngine::wait(*b.packed);
+      for (size_t w = 0; w < b.packed->used.size(); w++)
+         if (b.packed->used[w]) LDB_CUDA(cudaStreamWaitEvent(ctx->compute, ctx->staging->events[w], 0));
+   }
+}
+}
+
 // ------------------------------------------------------------------------------------------------ host pool
 namespace ldb {
 HostPool::HostPool(int n) {
@@ -209,6 +222,7 @@ int ldb_gpu_context_create(int device, LdbContext** out, LdbError* err) {
       LDB_CUDA(cudaEventCreate(&ctx->timerStop));
       LDB_CUDA(cudaEventCreateWithFlags(&ctx->computeDone, cudaEventDisableTiming));
       if (const char* e = getenv("LDB_NARROW_STAGING")) ctx->narrowStaging = atoi(e) != 0;
+      if (const char* e = getenv("LDB_PACKED_STAGING")) ctx->packedStaging = atoi(e) != 0;
       *out = ctx.release();
    });
 }
@@ -222,6 +236,7 @@ void ldb_gpu_context_destroy(LdbContext* ctx) {
    cudaSetDevice(ctx->device);
    cudaDeviceSynchronize();
    while (!ctx->tables.empty()) ldb_gpu_table_destroy(ctx->tables.back());
+   ctx->staging.reset(); // joins the staging workers (their streams are drained first)
    for (auto* s : ctx->states) destroyState(s);
    for (auto& kv : ctx->stagingSize) cudaFree(kv.first);
    for (auto& ps : ctx->pinned) {
@@ -265,8 +280,8 @@ int ldb_gpu_synchronize(LdbContext* ctx, LdbError* err) {
    });
 }
 void* ldb_gpu_context_stream(LdbContext* ctx) { return ctx ? (void*) ctx->compute : nullptr; }
-int64_t ldb_gpu_context_h2d_bytes(LdbContext* ctx) { return ctx ? ctx->h2dBytes : 0; }
-int64_t ldb_gpu_launch_count(LdbContext* ctx) { return ctx ? ctx->launches : 0; }
+int64_t ldb_gpu_context_h2d_bytes(LdbContext* ctx) { return ctx ? ctx->h2dBytes.load() : 0; }
+int64_t ldb_gpu_launch_count(LdbContext* ctx) { return ctx ? ctx->launches + ctx->stagingLaunches.load() : 0; }
 int ldb_gpu_timer_start(LdbContext* ctx, LdbError* err) {
    return guarded(err, [&] { LDB_CUDA(cudaEventRecord(ctx->timerStart, ctx->compute)); });
 }
@@ -339,6 +354,21 @@ int ldb_gpu_table_append_batch(LdbTable* t, int64_t n_rows, const LdbArrayView* 
       b.data.resize(nc);
       b.bytes.assign(nc, nullptr);
       b.elemBytes.assign(nc, 0);
+      // compressed staging (staging.h): fixed-width HOST columns of batches that span at least one block are re-encoded by
+      // the staging engine's independent pipelines (pack on a host thread → H2D on its stream → decode kernel) and this call
+      // returns at once; the Arrow buffers must stay valid until the table is cleared (they belong to the table storage)
+      const bool packThis = location != LDB_MEM_DEVICE && ctx->packedStaging && n_rows >= kPackBlockRows;
+      std::shared_ptr<PackedBatch> pk;
+      if (packThis) {
+         if (!ctx->staging) {
+            int hw = (int) std::thread::hardware_concurrency();
+            int nt = std::max(2, std::min(64, hw / 2));
+            if (const char* e = getenv("LDB_STAGING_THREADS")) nt = std::max(1, std::min(256, atoi(e)));
+            ctx->staging = std::make_shared<StagingEngine>(ctx, nt);
+         }
+         pk = std::make_shared<PackedBatch>();
+         pk->nRows = n_rows;
+      }
       for (size_t c = 0; c < nc; c++) {
          const LdbArrayView& av = columns[c];
          if (av.null_count != 0) fail(LDB_ERR_UNSUPPORTED, "nullable batches are not supported on the GPU path yet");
@@ -348,9 +378,19 @@ int ldb_gpu_table_append_batch(LdbTable* t, int64_t n_rows, const LdbArrayView* 
          const uint8_t* src = (const uint8_t*) av.buffers[1] + (size_t) av.offset * w;
          size_t bytes = (size_t) (n_rows + (utf8 ? 1 : 0)) * w;
          b.elemBytes[c] = (int32_t) w;
+         const int ty = t->columns[c].type;
+         const bool packable = packThis && !utf8 && (ty != LDB_DECIMAL128 || t->columns[c].precision < 19) && pk->cols.size() < (size_t) kMaxPackCols;
          if (location == LDB_MEM_DEVICE) {
             b.data[c] = src;
             if (utf8) b.bytes[c] = av.buffers[2];
+         } else if (packable) {
+            const int kind = ty == LDB_DECIMAL128 ? 2 : ty == LDB_INT64 ? 1 : 0;
+            const int outBytes = kind == 0 ? 4 : 8;
+            uint8_t* dst = (uint8_t*) ctx->stagingAlloc((size_t) n_rows * outBytes);
+            b.owned.push_back(dst);
+            pk->cols.push_back(PackedBatch::Col{src, kind, (int32_t) w, dst, outBytes});
+            b.data[c] = dst;
+            b.elemBytes[c] = outBytes;
          } else if (ctx->narrowStaging && t->columns[c].type == LDB_DECIMAL128 && t->columns[c].precision < 19 && n_rows > 0) {
             // narrow on the host into a ring of pinned slots, copy 8 B/value: chunk k+1 is narrowed while chunk k is on the wire
             if (!ctx->pool) {
@@ -402,6 +442,10 @@ int ldb_gpu_table_append_batch(LdbTable* t, int64_t n_rows, const LdbArrayView* 
          b.ready = ctx->getEvent();
          LDB_CUDA(cudaEventRecord(b.ready, ctx->copy));
       }
+      if (pk && !pk->cols.empty()) {
+         b.packed = pk;
+         ctx->staging->submit(pk);
+      }
       t->numRows += n_rows;
       t->batches.push_back(std::move(b));
    });
@@ -409,9 +453,20 @@ int ldb_gpu_table_append_batch(LdbTable* t, int64_t n_rows, const LdbArrayView* 
 int ldb_gpu_table_clear(LdbTable* t, LdbError* err) {
    return guarded(err, [&] {
       LdbContext* ctx = t->ctx;
+      // staging workers may still be writing into buffers released below: let them finish issuing (host wait, errors ignored)
+      for (auto& b : t->batches)
+         if (b.packed) {
+            try {
+               StagingEngine::wait(*b.packed);
+            } catch (const std::exception&) {
+            }
+            for (size_t w = 0; w < b.packed->used.size(); w++)
+               if (b.packed->used[w]) LDB_CUDA(cudaStreamWaitEvent(ctx->compute, ctx->staging->events[w], 0));
+         }
       // staged buffers may still be read by queued kernels: later copies wait for the compute stream
       LDB_CUDA(cudaEventRecord(ctx->computeDone, ctx->compute));
       LDB_CUDA(cudaStreamWaitEvent(ctx->copy, ctx->computeDone, 0));
+      ctx->stagingGen.fetch_add(1);
       for (auto& b : t->batches) {
          for (void* p : b.owned) ctx->stagingRelease(p);
          if (b.ready) ctx->eventPool.push_back(b.ready);
@@ -447,13 +502,16 @@ static LdbState* newGroupState(LdbContext* ctx, int kind, int nKeys, int nAggs, 
    s->kind = kind;
    ctx->states.push_back(s);
    auto& g = s->group;
-   g.capacity = nKeys == 0 ? 1 : (int) nextPow2((uint64_t) std::max(capacity, 16));
+   g.capacity = nKeys == 0 ? 2 : (int) nextPow2((uint64_t) std::max(capacity, 16)); // keyless: slot 0 only (2 keeps the accumulators 8-byte aligned inside the image)
    g.nKeys = nKeys;
    g.nAggs = nAggs;
-   g.state = (int32_t*) devAlloc(s, sizeof(int32_t) * g.capacity, 0);
-   g.keys = (int32_t*) devAlloc(s, sizeof(int32_t) * kMaxKeys * g.capacity, 0);
-   g.acc = (unsigned long long*) devAlloc(s, sizeof(unsigned long long) * 2 * kMaxAggs * g.capacity, 0);
-   g.error = (int32_t*) devAlloc(s, sizeof(int32_t), 0);
+   // one allocation, one memset: the exchange image (state | keys | acc) followed by the error word
+   const size_t image = groupImageBytes(g.capacity);
+   uint8_t* base = (uint8_t*) devAlloc(s, image + 16, 0);
+   g.state = (int32_t*) base;
+   g.keys = (int32_t*) (base + (size_t) g.capacity * 4);
+   g.acc = (unsigned long long*) (base + (size_t) g.capacity * 4 + (size_t) g.capacity * kMaxKeys * 4);
+   g.error = (int32_t*) (base + image);
    s->nAggs = nAggs;
    return s;
 }
@@ -486,20 +544,22 @@ int ldb_gpu_simple_state_read(LdbState* s, LdbI128* aggs, LdbError* err) {
       unsigned long long h[kMaxAggs * 2];
       LDB_CUDA(cudaMemcpyAsync(h, s->group.acc, sizeof(h), cudaMemcpyDeviceToHost, s->ctx->compute));
       LDB_CUDA(cudaStreamSynchronize(s->ctx->compute));
-      for (int a = 0; a < s->nAggs; a++) aggs[a] = LdbI128{h[2 * a], (int64_t) h[2 * a + 1]};
+      for (int a = 0; a < s->nAggs; a++) aggs[a] = (s->is64Mask >> a) & 1u ? LdbI128{h[2 * a], (int64_t) h[2 * a] >> 63} : LdbI128{h[2 * a], (int64_t) h[2 * a + 1]};
    });
 }
 int ldb_gpu_groupby_read(LdbState* s, LdbGroupRow* rows, int32_t max_rows, int32_t* n_rows, LdbError* err) {
    return guarded(err, [&] {
       if (!s || s->kind != LDB_STATE_GROUPBY) fail(LDB_ERR_INVALID, "not a group-by state");
-      checkGroupError(s);
       auto& g = s->group;
-      std::vector<int32_t> st(g.capacity), keys((size_t) g.capacity * kMaxKeys);
-      std::vector<unsigned long long> acc((size_t) g.capacity * kMaxAggs * 2);
-      LDB_CUDA(cudaMemcpyAsync(st.data(), g.state, st.size() * 4, cudaMemcpyDeviceToHost, s->ctx->compute));
-      LDB_CUDA(cudaMemcpyAsync(keys.data(), g.keys, keys.size() * 4, cudaMemcpyDeviceToHost, s->ctx->compute));
-      LDB_CUDA(cudaMemcpyAsync(acc.data(), g.acc, acc.size() * 8, cudaMemcpyDeviceToHost, s->ctx->compute));
+      // the table is one allocation (image + error word): one copy, one synchronisation
+      const size_t image = groupImageBytes(g.capacity);
+      std::vector<uint8_t> host(image + 16);
+      LDB_CUDA(cudaMemcpyAsync(host.data(), g.state, image + 16, cudaMemcpyDeviceToHost, s->ctx->compute));
       LDB_CUDA(cudaStreamSynchronize(s->ctx->compute));
+      if (*(const int32_t*) (host.data() + image)) fail(LDB_ERR_CAPACITY, "group-by table overflow: more groups than the declared capacity");
+      const int32_t* st = (const int32_t*) host.data();
+      const int32_t* keys = (const int32_t*) (host.data() + (size_t) g.capacity * 4);
+      const unsigned long long* acc = (const unsigned long long*) (host.data() + (size_t) g.capacity * 4 + (size_t) g.capacity * kMaxKeys * 4);
       int n = 0;
       for (int i = 0; i < g.capacity; i++) {
          if (st[i] != 2) continue;
@@ -507,7 +567,11 @@ int ldb_gpu_groupby_read(LdbState* s, LdbGroupRow* rows, int32_t max_rows, int32
             LdbGroupRow& r = rows[n];
             memset(&r, 0, sizeof(r));
             for (int k = 0; k < kMaxKeys; k++) r.keys[k] = keys[(size_t) i * kMaxKeys + k];
-            for (int a = 0; a < g.nAggs; a++) r.aggs[a] = LdbI128{acc[((size_t) i * kMaxAggs + a) * 2], (int64_t) acc[((size_t) i * kMaxAggs + a) * 2 + 1]};
+            for (int a = 0; a < g.nAggs; a++) {
+               const unsigned long long lo = acc[((size_t) i * kMaxAggs + a) * 2];
+               // 64-bit aggregates wrap at 64 bits; their hi word only collected carries of the two-word atomics → sign-extend lo
+               r.aggs[a] = (s->is64Mask >> a) & 1u ? LdbI128{lo, (int64_t) lo >> 63} : LdbI128{lo, (int64_t) acc[((size_t) i * kMaxAggs + a) * 2 + 1]};
+            }
          }
          n++;
       }
@@ -539,17 +603,12 @@ int ldb_gpu_groupby_merge_rows(LdbState* s, const LdbGroupRow* rows, int32_t n_r
    });
 }
 
-static size_t groupImageBytes(const GroupTableDev& g) { return (size_t) g.capacity * 4 + (size_t) g.capacity * kMaxKeys * 4 + (size_t) g.capacity * kMaxAggs * 2 * 8; }
-int64_t ldb_gpu_groupby_export_bytes(LdbState* s) { return s ? (int64_t) groupImageBytes(s->group) : 0; }
+int64_t ldb_gpu_groupby_export_bytes(LdbState* s) { return s ? (int64_t) groupImageBytes(s->group.capacity) : 0; }
 int ldb_gpu_groupby_export(LdbState* s, void* dst, LdbError* err) {
    return guarded(err, [&] {
       if (!s || (s->kind != LDB_STATE_GROUPBY && s->kind != LDB_STATE_SIMPLE)) fail(LDB_ERR_INVALID, "not a group state");
-      auto& g = s->group;
-      size_t cap = (size_t) g.capacity;
-      uint8_t* d = (uint8_t*) dst;
-      LDB_CUDA(cudaMemcpyAsync(d, g.state, cap * 4, cudaMemcpyDeviceToDevice, s->ctx->compute));
-      LDB_CUDA(cudaMemcpyAsync(d + cap * 4, g.keys, cap * kMaxKeys * 4, cudaMemcpyDeviceToDevice, s->ctx->compute));
-      LDB_CUDA(cudaMemcpyAsync(d + cap * 4 + cap * kMaxKeys * 4, g.acc, cap * kMaxAggs * 2 * 8, cudaMemcpyDeviceToDevice, s->ctx->compute));
+      auto& g = s->group; // the table IS the image (newGroupState): one copy
+      LDB_CUDA(cudaMemcpyAsync(dst, g.state, groupImageBytes(g.capacity), cudaMemcpyDeviceToDevice, s->ctx->compute));
    });
 }
 int ldb_gpu_groupby_merge_exported(LdbState* s, const void* src, int32_t n_tables, int32_t skip_index, LdbError* err) {
@@ -657,7 +716,7 @@ int ldb_gpu_table_column_range(LdbTable* t, const char* column, int32_t* mn, int
       LDB_CUDA(cudaMemcpyAsync(d, init, 8, cudaMemcpyHostToDevice, ctx->compute));
       for (auto& b : t->batches) {
          if (b.nRows == 0) continue;
-         if (b.ready) LDB_CUDA(cudaStreamWaitEvent(ctx->compute, b.ready, 0));
+         waitBatch(ctx, b);
          ctx->launch("column_range", [&] { launchColumnRange((const int32_t*) b.data[c], b.nRows, d, ctx->smCount, ctx->compute); });
       }
       LDB_CUDA(cudaMemcpyAsync(init, d, 8, cudaMemcpyDeviceToHost, ctx->compute));
@@ -904,9 +963,6 @@ AggPlan planAggs(const Resolved& R, const LdbAggDesc* a, int n) {
    p.nAggs = n;
    return p;
 }
-void waitBatch(LdbContext* ctx, const LdbBatch& b) {
-   if (b.ready) LDB_CUDA(cudaStreamWaitEvent(ctx->compute, b.ready, 0));
-}
 LdbState* wantState(LdbState* s, int kind, const char* role) {
    if (!s || s->kind != kind) fail(LDB_ERR_INVALID, std::string("wrong or missing state for ") + role);
    return s;
@@ -936,6 +992,8 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
             LdbState* sink = wantState(d->sink, keyless ? LDB_STATE_SIMPLE : LDB_STATE_GROUPBY, "sink");
             AggPlan ap = planAggs(R, d->aggs, d->n_aggs);
             if (ap.nAggs != sink->group.nAggs) fail(LDB_ERR_INVALID, "aggregate count differs from the state's");
+            for (int a = 0; a < ap.nAggs; a++)
+               if (ap.aggs[a].expr == LDB_EXPR_COL || ap.aggs[a].expr == LDB_EXPR_ONE) sink->is64Mask |= 1u << a;
             int nKeys = keyless ? 0 : d->n_keys;
             if (nKeys != sink->group.nKeys) fail(LDB_ERR_INVALID, "key count differs from the state's");
             int keyCol[kMaxKeys] = {0, 0};
@@ -1073,6 +1131,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                p.agg = ap.aggs[0];
                for (int v = 0; v < ap.nValueCols; v++) p.valueStage[v] = valueStage[v];
                p.groups = sink->group;
+               if (p.agg.expr == LDB_EXPR_COL || p.agg.expr == LDB_EXPR_ONE) sink->is64Mask |= 1u;
                waitBatch(ctx, b);
                bool ok = true;
                ctx->launch("join_probe2_groupby", [&] { ok = launchScanProbe2GroupBy(p, ctx->smCount, ctx->compute, &why); });

@@ -89,8 +89,69 @@ def q1_rows_from_groups(total) -> list:
     return rows
 
 
+class Comm:
+    """Peer-mapped exchange over NVLink (include/ldb_gpu.h "multi-GPU", csrc/peer.cu): every rank's symmetric heap is mapped
+    into its peers through CUDA IPC; collectives are kernels that store into peer HBM and publish a flag.  torch.distributed
+    only carries the 64-byte handles at start-up (`exchange` may be any callable bytes → [bytes per rank])."""
+
+    def __init__(self, ctx, rank: int, world: int, user_bytes: int = 0, exchange=None, connect: bool = True):
+        from . import capi
+        self.ctx, self.rank, self.world, self.L = ctx, rank, world, ctx.L
+        self.h = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        e = capi.Error()
+        capi.check(self.L.ldb_gpu_comm_create(ctx.h, rank, world, int(user_bytes), C.byref(self.h), handle, C.byref(e)), e)
+        if world > 1 and connect:
+            if exchange is None:
+                import torch.distributed as dist
+
+                def exchange(b):
+                    out = [None] * world
+                    dist.all_gather_object(out, b)
+                    return out
+            handles = exchange(bytes(handle))
+            blob = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
+            capi.check(self.L.ldb_gpu_comm_connect(self.h, blob, C.byref(e)), e)
+
+    @classmethod
+    def local_group(cls, ctxs, user_bytes: int = 0):
+        """All ranks inside ONE process (tests; contexts may share a device): peers are wired by pointer, no IPC."""
+        from . import capi
+        comms = [cls(c, r, len(ctxs), user_bytes, connect=False) for r, c in enumerate(ctxs)]
+        arr = (C.c_void_p * len(comms))(*[c.h for c in comms])
+        e = capi.Error()
+        capi.check(comms[0].L.ldb_gpu_comm_connect_local(arr, len(comms), C.byref(e)), e)
+        return comms
+
+    def close(self):
+        if self.h:
+            self.L.ldb_gpu_comm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def barrier(self):
+        from . import capi
+        e = capi.Error()
+        capi.check(self.L.ldb_gpu_comm_barrier(self.h, C.byref(e)), e)
+
+    def allmerge(self, state):
+        """K7 over NVLink: afterwards every rank's group state holds the merged groups of all ranks."""
+        from . import capi
+        e = capi.Error()
+        capi.check(self.L.ldb_gpu_groupby_allmerge(state, self.h, C.byref(e)), e)
+
+    def check(self):
+        from . import capi
+        e = capi.Error()
+        capi.check(self.L.ldb_gpu_comm_check(self.h, C.byref(e)), e)
+
+    def heap(self):
+        n = C.c_int64()
+        p = self.L.ldb_gpu_comm_heap(self.h, C.byref(n))
+        return int(p or 0), int(n.value)
+
+
 def allgather_merge_state(ctx, state, world: int, rank: int, bufs: dict):
-    """NCCL path used by bench.py: export → all_gather_into_tensor → merge kernel, all on the device."""
+    """NCCL path (kept as the comparison arm of bench.py --merge nccl): export → all_gather_into_tensor → merge kernel."""
     import torch
     import torch.distributed as dist
 
@@ -112,13 +173,17 @@ def allgather_merge_state(ctx, state, world: int, rank: int, bufs: dict):
     capi.check(L.ldb_gpu_groupby_merge_exported(state, C.c_void_p(bufs["recv"].data_ptr()), world, rank, C.byref(e)), e)
 
 
-def q9_sharded(ctx, tpch, world: int, rank: int, bufs: dict, name_contains: str = "green"):
+def q9_sharded(ctx, tpch, world: int, rank: int, bufs: dict, name_contains: str = "green", comm: "Comm" = None):
     """Q9 with lineitem ⋈ orders co-partitioned by order range (each rank's `tpch` holds its lineitem/orders shard and
-    replicas of part, partsupp, supplier, nation): per-rank pipelines → all-gather of the group-table images → K7 merge."""
+    replicas of part, partsupp, supplier, nation): per-rank pipelines → merge of the group tables across ranks (peer-mapped
+    all-merge kernel when a Comm is given, else NCCL all-gather + K7)."""
     from . import runtime
     st = tpch.q9_partial(name_contains)
     if world > 1:
-        allgather_merge_state(ctx, st, world, rank, bufs)
+        if comm is not None:
+            comm.allmerge(st)
+        else:
+            allgather_merge_state(ctx, st, world, rank, bufs)
     rows = tpch.q9_finish(st)
     runtime.state_destroy(ctx, st)
     return rows

@@ -1,0 +1,180 @@
+"""Round-2 GPU tests: compressed HOST staging, keyless partial merge, 64-bit aggregate normalisation and the peer-mapped
+(NVLink) collectives — all through the C-ABI, all against the CPU oracle."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from lingodb_b200 import datagen
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _tpch(ctx, t):
+    from lingodb_b200 import runtime
+    return runtime.Tpch(ctx, {k: ctx.table_from_host(v) for k, v in t.items()})
+
+
+def test_compressed_staging_gives_the_oracles_rows(gpu_ctx, oracle):
+    """HOST batches of >= 64 Ki rows go through pack (host) → copy → unpack kernel; ragged lengths, every query shape."""
+    from lingodb_b200 import capi
+    L = gpu_ctx.L
+    t = datagen.tpch(0.1, seed=5, chunk_rows=200_003, with_parts=True)  # 600 K lineitem rows in ragged >64Ki batches
+    oh = {k: oracle.table(v) for k, v in t.items()}
+    h2d0 = int(L.ldb_gpu_context_h2d_bytes(gpu_ctx.h))
+    g = _tpch(gpu_ctx, t)
+    assert g.q1() == oracle.q1(oh["lineitem"])[0]
+    staged = int(L.ldb_gpu_context_h2d_bytes(gpu_ctx.h)) - h2d0
+    arrow = sum(v.nbytes if not isinstance(v, tuple) else v[0].nbytes + v[1].nbytes for tab in t.values() for ch in tab.chunks for v in ch.values())
+    assert staged < 0.45 * arrow, (staged, arrow)  # the packed bytes that crossed the link, not the Arrow bytes
+    assert g.q6() == oracle.q6(oh["lineitem"])[0]
+    assert g.q3() == oracle.q3(oh["customer"], oh["orders"], oh["lineitem"])[0]
+    assert g.q5() == oracle.q5(oh["customer"], oh["orders"], oh["lineitem"], oh["supplier"], oh["nation"], oh["region"])[0]
+    assert g.q9() == oracle.q9(oh["part"], oh["supplier"], oh["lineitem"], oh["partsupp"], oh["orders"], oh["nation"])[0]
+    # restaging after a clear reuses the staging buffers (generation handshake with the workers)
+    li = g.tables["lineitem"]
+    for _ in range(2):
+        li.clear()
+        for chunk, n in zip(t["lineitem"].chunks, t["lineitem"].chunk_rows):
+            li.append_host(chunk, n)
+        assert g.q1() == oracle.q1(oh["lineitem"])[0]
+
+
+def test_compressed_staging_handles_negative_and_wide_values(gpu_ctx, oracle):
+    """Blocks whose range needs 8 bytes per value, negative decimals, int32 extremes: unpack must reproduce every cell."""
+    from lingodb_b200 import runtime
+    rng = np.random.default_rng(3)
+    n = 70_001
+    specs = [c for c in datagen.LINEITEM_SCHEMA if c.name in ("l_quantity", "l_extendedprice", "l_discount", "l_shipdate")]
+    qty = rng.integers(-2**40, 2**40, n, dtype=np.int64)
+    ext = rng.integers(-10**7, 10**7, n, dtype=np.int64)
+    disc = rng.integers(0, 11, n, dtype=np.int64)
+
+    def dec(v):
+        a = np.zeros((n, 2), np.int64)
+        a[:, 0] = v
+        a[:, 1] = v >> 63
+        return a.view(np.uint8).reshape(n, 16)
+
+    chunk = {"l_quantity": dec(qty), "l_extendedprice": dec(ext), "l_discount": dec(disc), "l_shipdate": rng.integers(-2**31, 2**31 - 1, n, dtype=np.int64).astype(np.int32)}
+    td = datagen.TableData("lineitem", specs)
+    td.chunks.append(chunk)
+    td.chunk_rows.append(n)
+    tab = gpu_ctx.table_from_host(td)
+    from lingodb_b200 import capi
+    s2, e = C.c_void_p(), capi.Error()
+    capi.check(gpu_ctx.L.ldb_gpu_simple_state_create(gpu_ctx.h, 2, C.byref(s2), C.byref(e)), e)
+    runtime.run_pipeline(gpu_ctx, "scan_reduce", tab, aggs=[("col", ["l_quantity"]), ("one", [])], sink=s2)
+    out = (capi.I128 * 8)()
+    capi.check(gpu_ctx.L.ldb_gpu_simple_state_read(s2, out, C.byref(e)), e)
+    want = int(qty.sum())
+    assert out[0].value() - (1 << 128 if out[0].hi < 0 else 0) == want  # negative i64 sums come back sign-extended
+    assert out[1].value() == n
+    runtime.state_destroy(gpu_ctx, s2)
+    s3 = C.c_void_p()
+    capi.check(gpu_ctx.L.ldb_gpu_simple_state_create(gpu_ctx.h, 1, C.byref(s3), C.byref(e)), e)
+    runtime.run_pipeline(gpu_ctx, "scan_reduce", tab, aggs=[("mul", ["l_extendedprice", "l_discount"])], sink=s3)
+    capi.check(gpu_ctx.L.ldb_gpu_simple_state_read(s3, out, C.byref(e)), e)
+    got = out[0].value() - (1 << 128 if out[0].hi < 0 else 0)
+    assert got == int((ext.astype(object) * disc.astype(object)).sum())
+    runtime.state_destroy(gpu_ctx, s3)
+
+
+def test_keyless_partials_export_and_merge(gpu_ctx, oracle):
+    """Two lineitem shards → two keyless Q6 partial states → export / merge_exported == the oracle over the whole table."""
+    import torch
+    from lingodb_b200 import capi, runtime
+    t = datagen.tpch(0.05, seed=21, chunk_rows=50_000)
+    whole = oracle.q6(oracle.table(t["lineitem"]))[0]
+    li = t["lineitem"]
+    half = len(li.chunks) // 2
+    states = []
+    for part in (range(0, half), range(half, len(li.chunks))):
+        td = datagen.TableData("lineitem", li.columns)
+        for i in part:
+            td.chunks.append(li.chunks[i])
+            td.chunk_rows.append(li.chunk_rows[i])
+        tp = runtime.Tpch(gpu_ctx, {"lineitem": gpu_ctx.table_from_host(td)})
+        s, e = C.c_void_p(), capi.Error()
+        capi.check(gpu_ctx.L.ldb_tpch_q6_partial(gpu_ctx.h, C.byref(tp.t), b"1994-01-01", b"1995-01-01", b"0.05", b"0.07", 24, C.byref(s), C.byref(e)), e)
+        states.append(s)
+    L = gpu_ctx.L
+    nbytes = int(L.ldb_gpu_groupby_export_bytes(states[0]))
+    recv = torch.empty(2 * nbytes, dtype=torch.uint8, device=torch.device("cuda", gpu_ctx.device))
+    e = capi.Error()
+    for r in range(2):
+        capi.check(L.ldb_gpu_groupby_export(states[r], C.c_void_p(recv.data_ptr() + r * nbytes), C.byref(e)), e)
+    gpu_ctx.synchronize()
+    capi.check(L.ldb_gpu_groupby_merge_exported(states[0], C.c_void_p(recv.data_ptr()), 2, 0, C.byref(e)), e)
+    out = (capi.I128 * 8)()
+    capi.check(L.ldb_gpu_simple_state_read(states[0], out, C.byref(e)), e)
+    assert {"revenue": out[0].value()} == whole
+    for s in states:
+        runtime.state_destroy(gpu_ctx, s)
+
+
+def _shard_tables(ctx, s, cols, r, world):
+    from lingodb_b200 import devgen, parallel
+    o_lo, o_hi, r_lo, r_hi = parallel.order_range(s, r, world)
+    return {"lineitem": devgen.lineitem(ctx, s, cols, row_begin=r_lo, n_rows=r_hi - r_lo)}
+
+
+def test_peer_allmerge_protocol_on_one_device(oracle):
+    """The peer-mapped all-merge (csrc/peer.cu) with 3 'ranks' that are 3 contexts of this process on device 0: same kernels,
+    flags and mailboxes as the multi-process NVLink path, peers wired by pointer.  Every rank must end with the whole result,
+    twice in a row (epoch parity), for Q1 (4 groups) and the keyless Q6."""
+    from lingodb_b200 import capi, parallel, runtime
+    world = 3
+    s = datagen.scale(0.05, seed=13)
+    cols = ["l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus", "l_shipdate"]
+    host = datagen.lineitem(s, cols)
+    oh = oracle.table(host)
+    want_q1, want_q6 = oracle.q1(oh)[0], oracle.q6(oh)[0]
+    ctxs = [runtime.Context(0) for _ in range(world)]
+    try:
+        comms = parallel.Comm.local_group(ctxs)
+        tps = [runtime.Tpch(c, _shard_tables(c, s, cols, r, world)) for r, c in enumerate(ctxs)]
+        for _ in range(2):
+            sts = [tp.q1_partial() for tp in tps]
+            for cm, st in zip(comms, sts):  # enqueue on every rank before anyone synchronises: the kernels wait for each other
+                cm.allmerge(st)
+            for r in range(world):
+                assert tps[r].q1_finish(sts[r]) == want_q1, f"rank {r}"
+                runtime.state_destroy(ctxs[r], sts[r])
+            sts = []
+            for c, tp in zip(ctxs, tps):
+                st, e = C.c_void_p(), capi.Error()
+                capi.check(c.L.ldb_tpch_q6_partial(c.h, C.byref(tp.t), b"1994-01-01", b"1995-01-01", b"0.05", b"0.07", 24, C.byref(st), C.byref(e)), e)
+                sts.append(st)
+            for cm, st in zip(comms, sts):
+                cm.allmerge(st)
+            for r in range(world):
+                out, e = (capi.I128 * 8)(), capi.Error()
+                capi.check(ctxs[r].L.ldb_gpu_simple_state_read(sts[r], out, C.byref(e)), e)
+                assert {"revenue": out[0].value()} == want_q6, f"rank {r}"
+                runtime.state_destroy(ctxs[r], sts[r])
+        for cm in comms:
+            cm.barrier()
+        for cm in comms:
+            cm.check()
+        for cm in comms:
+            cm.close()
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_peer_collectives_across_processes_and_gpus():
+    """world = 2 processes on 2 GPUs (CUDA IPC + NVLink P2P), when the box has them: tools/peer_selftest.py checks Q1/Q9
+    against the oracle on every rank and exits non-zero on any mismatch."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29591",
+                        os.path.join(ROOT, "tools", "peer_selftest.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "peer selftest ok" in r.stdout
