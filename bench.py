@@ -60,6 +60,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def effective_cpus():
+    """CPUs this container may burn (cgroup quota aware) — the 128-thread box gives a container 16."""
+    try:
+        from lingodb_b200 import capi
+        return int(capi.lib().ldb_gpu_effective_cpus())
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def host_available_bytes():
     try:
         import psutil
@@ -128,12 +137,11 @@ def host_lineitem(sf, seed, cols, n_rows, gen_rows=1 << 23):
 
 
 def sweep_oracle_workers(o, run, cands=None):
-    """Give the CPU side the worker count it is fastest with: all hardware threads down to 1/8 of them (the scan is DRAM-bound
-    well before two hyper-threaded sockets are full).  Returns {workers: seconds}."""
-    ncpu = os.cpu_count() or 1
+    """Give the CPU side the worker count it is fastest with: a sweep around the CPUs the container may use.  Returns {workers: seconds}."""
+    ncpu = effective_cpus()
     env = os.environ.get("ORACLE_PARALLELISM")
-    if cands is None:
-        cands = [int(env)] if env else sorted({max(1, int(ncpu * f)) for f in (1, 0.75, 0.5, 0.375, 0.25, 0.125)}, reverse=True)
+    if cands is None:  # around the CPU quota: more threads than the quota only get throttled (measured: 128 workers 9x slower than 16)
+        cands = [int(env)] if env else sorted({max(1, int(ncpu * f)) for f in (2, 1.5, 1, 0.75, 0.5)}, reverse=True)
     seen = {}
     for w in cands:
         o.set_workers(w)
@@ -252,9 +260,9 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    ncpu = os.cpu_count() or 8
-    # one staging engine per rank: the ranks of a box share its cores
-    os.environ.setdefault("LDB_STAGING_THREADS", str(max(4, min(64, ncpu // 2) if world == 1 else (ncpu * 3 // 4) // world)))
+    ncpu = effective_cpus()
+    # one staging engine per rank: the ranks of a box share the container's CPU quota
+    os.environ.setdefault("LDB_STAGING_THREADS", str(max(2, ncpu - 2) if world == 1 else max(1, (ncpu - 2) // world)))
 
     from lingodb_b200 import datagen, devgen, parallel, runtime
 
@@ -320,7 +328,7 @@ def run_ours(args):
     oracle = None
     if have_host and not args.no_parity:
         from oracle import oracle as O
-        oracle = O.Oracle("auto", workers=max(2, min(32, ncpu // 2) // world))
+        oracle = O.Oracle("auto", workers=max(2, ncpu // world))
         oh_li = oracle.table(td_li)
         t0 = time.perf_counter()
         mine = q1_sums(oracle.q1(oh_li)[0])
@@ -420,12 +428,14 @@ def run_ours(args):
         barrier()
         ctx.synchronize()
         h2d0 = int(L.ldb_gpu_context_h2d_bytes(ctx.h))
+        raw0 = int(L.ldb_gpu_context_raw_staged_rows(ctx.h))
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             rows_h = step_e2e()
         ctx.synchronize()
         e2e_s = time.perf_counter() - t0
         h2d_step = (int(L.ldb_gpu_context_h2d_bytes(ctx.h)) - h2d0) // args.e2e_steps
+        raw_rows = (int(L.ldb_gpu_context_raw_staged_rows(ctx.h)) - raw0) // args.e2e_steps
         # column-cache hit: the staged table stays in HBM (LingoDBTable.cpp:294-305 ownership), the same call reads it again
         t0 = time.perf_counter()
         for _ in range(3):
@@ -445,8 +455,10 @@ def run_ours(args):
             dist.all_reduce(hsum)
         e2e = {"value": total_rows * args.e2e_steps / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": int(hsum.item()),
                "host_arrow_bytes_per_step": h2d * world,
-               "staging": f"compressed staging: {os.environ['LDB_STAGING_THREADS']} host threads/rank pack 64Ki-value frame-of-reference blocks (1/2/4/8 B per value; decimal128(12,2) → its low 8 bytes first) "
-                          "into pinned slots, one CUDA stream per thread copies them and a kernel unpacks into the staged layout (csrc/staging.cu)",
+               "staging": f"compressed staging: {os.environ['LDB_STAGING_THREADS']} host threads/rank (container CPU quota {ncpu}) pack 64Ki-value frame-of-reference blocks (1/2/4/8 B per value; "
+                          "decimal128(12,2) → its low 8 bytes first) into pinned slots, one CUDA stream per thread copies them and a kernel unpacks into the staged layout; "
+                          f"{os.environ.get('LDB_STAGING_RAW_THREADS', '2')} raw copiers fill idle link time with uncompressed Arrow cells (csrc/staging.cu)",
+               "rows_shipped_raw_per_step_rank0": raw_rows, "host_cpu_quota": ncpu,
                "d2h_bytes_per_step": (64 * 140 + 16) * world, "steps": args.e2e_steps, "ms_per_step": 1000 * e2e_s / args.e2e_steps,
                "batch_rows": args.e2e_batch_rows, "host_memory": "pinned", "cold": True,
                "cached_value": total_rows / cached_s, "cached_note": "same C-ABI call with the table already staged (column-cache hit): no H2D, result D2H only; wall clock"}
@@ -542,7 +554,7 @@ def side_queries(args, ctx, s, tabs, lineitem, td_li, oracle, peak, parity, note
             oh = {"lineitem": oracle.table(td_li)}
             for name in ("orders", "customer", "supplier", "nation", "region", "part", "partsupp"):
                 oh[name] = oracle.table(device_table_to_host(tabs[name])[0])
-            oracle.set_workers(min(32, max(2, (os.cpu_count() or 8) // 2)))
+            oracle.set_workers(max(2, effective_cpus()))
             gate["q6"] = lambda: oracle.q6(oh["lineitem"])[0]
             gate["q3"] = lambda: oracle.q3(oh["customer"], oh["orders"], oh["lineitem"])[0]
             gate["q5"] = lambda: oracle.q5(oh["customer"], oh["orders"], oh["lineitem"], oh["supplier"], oh["nation"], oh["region"])[0]

@@ -90,6 +90,11 @@ int ldb_gpu_table_clear(LdbTable* t, LdbError* err); /* drop all batches (stagin
  * the host to the 8 bytes per value the kernels read (the JIT truncates them to i64, LowerToStd.cpp:111-209), so they
  * cost 8 B/value of PCIe instead of 16; LDB_NARROW_STAGING=0 in the environment disables it. */
 int64_t ldb_gpu_context_h2d_bytes(LdbContext* ctx);
+/* Compressed staging (csrc/staging.cu): HOST batches of >= 65 536 rows are re-encoded by host threads (frame of reference,
+ * 1/2/4/8 bytes per value per 64 Ki-value block) and decoded on the GPU; idle PCIe time is filled by raw copiers that ship
+ * Arrow cells unchanged.  rows the raw copiers took so far / CPUs the process may use (cgroup quota aware): */
+int64_t ldb_gpu_context_raw_staged_rows(LdbContext* ctx);
+int32_t ldb_gpu_effective_cpus(void);
 int64_t ldb_gpu_table_num_rows(const LdbTable* t);
 void ldb_gpu_table_destroy(LdbTable* t);
 

@@ -98,7 +98,29 @@ struct LdbContext {
    std::shared_ptr<ldb::StagingEngine> staging;
    std::atomic<uint64_t> stagingGen{0};      // bumped by ldb_gpu_table_clear: workers order their next write after computeDone
    std::atomic<int64_t> stagingLaunches{0};  // unpack kernels launched by the staging workers
+   std::atomic<int64_t> rawStagedRows{0};    // rows the raw copiers shipped uncompressed (the rest was packed)
 
+   // Host waits SLEEP instead of spinning (cudaEventBlockingSync): the container's CPU quota is shared with the staging
+   // threads and, on a multi-GPU box, with the other ranks — a spinning waiter would burn a whole CPU of it.
+   // Short waits (a query's result read: the stream drains within a few hundred microseconds) poll, long ones sleep.
+   cudaEvent_t blockingEv = nullptr;
+   void syncStream(cudaStream_t s) {
+      if (!blockingEv) LDB_CUDA(cudaEventCreateWithFlags(&blockingEv, cudaEventBlockingSync | cudaEventDisableTiming));
+      LDB_CUDA(cudaEventRecord(blockingEv, s));
+      for (int spin = 0; spin < 20000; spin++) { // ~0.3 ms of polling
+         cudaError_t q = cudaEventQuery(blockingEv);
+         if (q == cudaSuccess) return;
+         if (q != cudaErrorNotReady) LDB_CUDA(q);
+      }
+      LDB_CUDA(cudaEventSynchronize(blockingEv));
+   }
+   // pinned scratch for small result reads: a copy into pageable memory would be staged by the driver and serialise with the host
+   void* pinnedScratch = nullptr;
+   static constexpr size_t kPinnedScratchBytes = 512u << 10;
+   void* scratch() {
+      if (!pinnedScratch) LDB_CUDA(cudaMallocHost(&pinnedScratch, kPinnedScratchBytes));
+      return pinnedScratch;
+   }
    void* stagingAlloc(size_t bytes);
    void stagingRelease(void* p);
    cudaEvent_t getEvent();

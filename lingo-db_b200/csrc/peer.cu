@@ -233,7 +233,7 @@ int ldb_gpu_comm_create(LdbContext* ctx, int32_t rank, int32_t world, int64_t us
       LDB_CUDA(cudaMemsetAsync(c->heap, 0, kUserOff, ctx->compute));
       c->error = (int32_t*) (c->heap + kUserOff + c->userBytes);
       LDB_CUDA(cudaMemsetAsync(c->error, 0, 256, ctx->compute));
-      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+      ctx->syncStream(ctx->compute);
       c->peerHeap[rank] = c->heap;
       if (const char* e = getenv("LDB_PEER_TIMEOUT_MS")) c->timeoutNs = (unsigned long long) std::max(1, atoi(e)) * 1000000ull;
       cudaIpcMemHandle_t h;
@@ -372,7 +372,7 @@ int ldb_gpu_comm_check(LdbComm* c, LdbError* err) {
       LDB_CUDA(cudaSetDevice(c->ctx->device));
       int32_t e = 0;
       LDB_CUDA(cudaMemcpyAsync(&e, c->error, 4, cudaMemcpyDeviceToHost, c->ctx->compute));
-      LDB_CUDA(cudaStreamSynchronize(c->ctx->compute));
+      c->ctx->syncStream(c->ctx->compute);
       if (e) failPeer(LDB_ERR_CUDA, "a peer did not arrive at a collective within the timeout (LDB_PEER_TIMEOUT_MS)");
    });
 }

@@ -252,6 +252,8 @@ void ldb_gpu_context_destroy(LdbContext* ctx) {
    cudaEventDestroy(ctx->timerStart);
    cudaEventDestroy(ctx->timerStop);
    cudaEventDestroy(ctx->computeDone);
+   if (ctx->blockingEv) cudaEventDestroy(ctx->blockingEv);
+   if (ctx->pinnedScratch) cudaFreeHost(ctx->pinnedScratch);
    cudaStreamDestroy(ctx->compute);
    cudaStreamDestroy(ctx->copy);
    delete ctx;
@@ -275,12 +277,14 @@ int ldb_gpu_device_info(LdbContext* ctx, LdbDeviceInfo* out, LdbError* err) {
 }
 int ldb_gpu_synchronize(LdbContext* ctx, LdbError* err) {
    return guarded(err, [&] {
-      LDB_CUDA(cudaStreamSynchronize(ctx->copy));
-      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+      ctx->syncStream(ctx->copy);
+      ctx->syncStream(ctx->compute);
    });
 }
 void* ldb_gpu_context_stream(LdbContext* ctx) { return ctx ? (void*) ctx->compute : nullptr; }
 int64_t ldb_gpu_context_h2d_bytes(LdbContext* ctx) { return ctx ? ctx->h2dBytes.load() : 0; }
+int64_t ldb_gpu_context_raw_staged_rows(LdbContext* ctx) { return ctx ? ctx->rawStagedRows.load() : 0; }
+int32_t ldb_gpu_effective_cpus(void) { return effectiveCpus(); }
 int64_t ldb_gpu_launch_count(LdbContext* ctx) { return ctx ? ctx->launches + ctx->stagingLaunches.load() : 0; }
 int ldb_gpu_timer_start(LdbContext* ctx, LdbError* err) {
    return guarded(err, [&] { LDB_CUDA(cudaEventRecord(ctx->timerStart, ctx->compute)); });
@@ -294,7 +298,7 @@ int ldb_gpu_timer_stop(LdbContext* ctx, float* ms, LdbError* err) {
 }
 int ldb_gpu_kernel_time_reset(LdbContext* ctx, int enable, LdbError* err) {
    return guarded(err, [&] {
-      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+      ctx->syncStream(ctx->compute);
       for (auto& kv : ctx->timers) {
          for (auto& pr : kv.second.pending) {
             ctx->eventPool.push_back(pr.first);
@@ -307,7 +311,7 @@ int ldb_gpu_kernel_time_reset(LdbContext* ctx, int enable, LdbError* err) {
 }
 int ldb_gpu_kernel_time(LdbContext* ctx, const char* family, float* ms, int64_t* launches, LdbError* err) {
    return guarded(err, [&] {
-      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+      ctx->syncStream(ctx->compute);
       auto it = ctx->timers.find(family);
       if (it == ctx->timers.end()) {
          *ms = 0;
@@ -361,10 +365,11 @@ int ldb_gpu_table_append_batch(LdbTable* t, int64_t n_rows, const LdbArrayView* 
       std::shared_ptr<PackedBatch> pk;
       if (packThis) {
          if (!ctx->staging) {
-            int hw = (int) std::thread::hardware_concurrency();
-            int nt = std::max(2, std::min(64, hw / 2));
+            // sized by the CPUs this process may burn (cgroup quota!), minus the caller's thread and the raw copiers
+            int nt = std::max(2, std::min(64, effectiveCpus() - 2)), nraw = 2;
             if (const char* e = getenv("LDB_STAGING_THREADS")) nt = std::max(1, std::min(256, atoi(e)));
-            ctx->staging = std::make_shared<StagingEngine>(ctx, nt);
+            if (const char* e = getenv("LDB_STAGING_RAW_THREADS")) nraw = std::max(0, std::min(8, atoi(e)));
+            ctx->staging = std::make_shared<StagingEngine>(ctx, nt, nraw);
          }
          pk = std::make_shared<PackedBatch>();
          pk->nRows = n_rows;
@@ -535,15 +540,15 @@ int ldb_gpu_groupby_create(LdbContext* ctx, int32_t n_keys, int32_t n_aggs, int3
 static void checkGroupError(LdbState* s) {
    int32_t e = 0;
    LDB_CUDA(cudaMemcpyAsync(&e, s->group.error, sizeof(e), cudaMemcpyDeviceToHost, s->ctx->compute));
-   LDB_CUDA(cudaStreamSynchronize(s->ctx->compute));
+   s->ctx->syncStream(s->ctx->compute);
    if (e) fail(LDB_ERR_CAPACITY, "group-by table overflow: more groups than the declared capacity");
 }
 int ldb_gpu_simple_state_read(LdbState* s, LdbI128* aggs, LdbError* err) {
    return guarded(err, [&] {
       if (!s || s->kind != LDB_STATE_SIMPLE) fail(LDB_ERR_INVALID, "not a simple state");
-      unsigned long long h[kMaxAggs * 2];
-      LDB_CUDA(cudaMemcpyAsync(h, s->group.acc, sizeof(h), cudaMemcpyDeviceToHost, s->ctx->compute));
-      LDB_CUDA(cudaStreamSynchronize(s->ctx->compute));
+      unsigned long long* h = (unsigned long long*) s->ctx->scratch();
+      LDB_CUDA(cudaMemcpyAsync(h, s->group.acc, sizeof(unsigned long long) * kMaxAggs * 2, cudaMemcpyDeviceToHost, s->ctx->compute));
+      s->ctx->syncStream(s->ctx->compute);
       for (int a = 0; a < s->nAggs; a++) aggs[a] = (s->is64Mask >> a) & 1u ? LdbI128{h[2 * a], (int64_t) h[2 * a] >> 63} : LdbI128{h[2 * a], (int64_t) h[2 * a + 1]};
    });
 }
@@ -553,13 +558,18 @@ int ldb_gpu_groupby_read(LdbState* s, LdbGroupRow* rows, int32_t max_rows, int32
       auto& g = s->group;
       // the table is one allocation (image + error word): one copy, one synchronisation
       const size_t image = groupImageBytes(g.capacity);
-      std::vector<uint8_t> host(image + 16);
-      LDB_CUDA(cudaMemcpyAsync(host.data(), g.state, image + 16, cudaMemcpyDeviceToHost, s->ctx->compute));
-      LDB_CUDA(cudaStreamSynchronize(s->ctx->compute));
-      if (*(const int32_t*) (host.data() + image)) fail(LDB_ERR_CAPACITY, "group-by table overflow: more groups than the declared capacity");
-      const int32_t* st = (const int32_t*) host.data();
-      const int32_t* keys = (const int32_t*) (host.data() + (size_t) g.capacity * 4);
-      const unsigned long long* acc = (const unsigned long long*) (host.data() + (size_t) g.capacity * 4 + (size_t) g.capacity * kMaxKeys * 4);
+      std::vector<uint8_t> pageable;
+      uint8_t* host = (uint8_t*) s->ctx->scratch(); // pinned: the copy is asynchronous, the only wait is the one below
+      if (image + 16 > LdbContext::kPinnedScratchBytes) {
+         pageable.resize(image + 16);
+         host = pageable.data();
+      }
+      LDB_CUDA(cudaMemcpyAsync(host, g.state, image + 16, cudaMemcpyDeviceToHost, s->ctx->compute));
+      s->ctx->syncStream(s->ctx->compute);
+      if (*(const int32_t*) (host + image)) fail(LDB_ERR_CAPACITY, "group-by table overflow: more groups than the declared capacity");
+      const int32_t* st = (const int32_t*) host;
+      const int32_t* keys = (const int32_t*) (host + (size_t) g.capacity * 4);
+      const unsigned long long* acc = (const unsigned long long*) (host + (size_t) g.capacity * 4 + (size_t) g.capacity * kMaxKeys * 4);
       int n = 0;
       for (int i = 0; i < g.capacity; i++) {
          if (st[i] != 2) continue;
@@ -597,7 +607,7 @@ int ldb_gpu_groupby_merge_rows(LdbState* s, const LdbGroupRow* rows, int32_t n_r
       LDB_CUDA(cudaMemcpyAsync(dk, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice, ctx->compute));
       LDB_CUDA(cudaMemcpyAsync(da, acc.data(), acc.size() * 8, cudaMemcpyHostToDevice, ctx->compute));
       ctx->launch("group_merge", [&] { launchGroupMergeRows(s->group, (const int32_t*) dk, (const unsigned long long*) da, n_rows, ctx->compute); });
-      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+      ctx->syncStream(ctx->compute);
       ctx->stagingRelease(dk);
       ctx->stagingRelease(da);
    });
@@ -720,7 +730,7 @@ int ldb_gpu_table_column_range(LdbTable* t, const char* column, int32_t* mn, int
          ctx->launch("column_range", [&] { launchColumnRange((const int32_t*) b.data[c], b.nRows, d, ctx->smCount, ctx->compute); });
       }
       LDB_CUDA(cudaMemcpyAsync(init, d, 8, cudaMemcpyDeviceToHost, ctx->compute));
-      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+      ctx->syncStream(ctx->compute);
       ctx->stagingRelease(d);
       *mn = init[0];
       *mx = init[1];
@@ -729,7 +739,7 @@ int ldb_gpu_table_column_range(LdbTable* t, const char* column, int32_t* mn, int
 static void checkJoinError(LdbState* s) {
    int32_t e = 0;
    LDB_CUDA(cudaMemcpyAsync(&e, s->join.error, sizeof(e), cudaMemcpyDeviceToHost, s->ctx->compute));
-   LDB_CUDA(cudaStreamSynchronize(s->ctx->compute));
+   s->ctx->syncStream(s->ctx->compute);
    if (e == 1) fail(LDB_ERR_CAPACITY, "join table full: more build rows than expected_rows allowed");
    if (e == 2) fail(LDB_ERR_INVALID, "duplicate key inserted into a join table declared unique");
    if (e == 3) fail(LDB_ERR_UNSUPPORTED, "the pair (key=-1, payload=-1) cannot be stored in a join table");
@@ -742,7 +752,7 @@ int ldb_gpu_join_table_count(LdbState* s, int64_t* n_entries, LdbError* err) {
       checkJoinError(s);
       unsigned long long c = 0;
       LDB_CUDA(cudaMemcpyAsync(&c, s->join.count, 8, cudaMemcpyDeviceToHost, s->ctx->compute));
-      LDB_CUDA(cudaStreamSynchronize(s->ctx->compute));
+      s->ctx->syncStream(s->ctx->compute);
       *n_entries = (int64_t) c;
    });
 }
@@ -765,7 +775,7 @@ int ldb_gpu_join_table_topk(LdbState* s, int32_t k, LdbTopKRow* rows, int32_t* n
       ctx->launch("join_topk", [&] { launchJoinTopK(s->join, k, (TopKRowDev*) d, &blocks, ctx->smCount, ctx->compute); });
       std::vector<TopKRowDev> h((size_t) blocks * k);
       LDB_CUDA(cudaMemcpyAsync(h.data(), d, bytes, cudaMemcpyDeviceToHost, ctx->compute));
-      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+      ctx->syncStream(ctx->compute);
       ctx->stagingRelease(d);
       std::vector<TopKRowDev> valid;
       for (auto& r : h)
@@ -1236,7 +1246,7 @@ int ldb_gpu_partition_tuples(LdbContext* ctx, const int32_t* keys, const void* c
       if (n_rows > 0) ctx->launch("partition", [&] { launchPartitionHistogram(keys, n_rows, n_parts, counts, ctx->smCount, ctx->compute); });
       unsigned long long h[64];
       LDB_CUDA(cudaMemcpyAsync(h, counts, 64 * 8, cudaMemcpyDeviceToHost, ctx->compute));
-      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+      ctx->syncStream(ctx->compute);
       unsigned long long cursor[64];
       int64_t off = 0;
       for (int p = 0; p < n_parts; p++) {
@@ -1247,7 +1257,7 @@ int ldb_gpu_partition_tuples(LdbContext* ctx, const int32_t* keys, const void* c
       out_part_offsets[n_parts] = off;
       LDB_CUDA(cudaMemcpyAsync(counts, cursor, 64 * 8, cudaMemcpyHostToDevice, ctx->compute));
       if (n_rows > 0) ctx->launch("partition", [&] { launchPartitionScatter(keys, payload_cols, payload_widths, n_payload_cols, n_rows, n_parts, counts, out_keys, out_payload_cols, ctx->smCount, ctx->compute); });
-      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+      ctx->syncStream(ctx->compute);
       ctx->stagingRelease(counts);
    });
 }
@@ -1270,7 +1280,7 @@ int ldb_gpu_hash_i64(LdbContext* ctx, const int64_t* a, const int64_t* b, int64_
       if (b) LDB_CUDA(cudaMemcpyAsync(db, b, n * 8, cudaMemcpyHostToDevice, ctx->compute));
       ctx->launch("hash", [&] { launchHashI64((const int64_t*) da, (const int64_t*) db, n, (uint64_t*) dout, ctx->compute); });
       LDB_CUDA(cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, ctx->compute));
-      LDB_CUDA(cudaStreamSynchronize(ctx->compute));
+      ctx->syncStream(ctx->compute);
       ctx->stagingRelease(da);
       if (db) ctx->stagingRelease(db);
       ctx->stagingRelease(dout);

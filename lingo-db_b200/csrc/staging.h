@@ -31,6 +31,10 @@ struct UnpackOuts {
    void* out[kMaxPackCols];        // decoded destination of each column for the task's FIRST row
    int32_t outBytes[kMaxPackCols]; // 4 (int32/date32/fsb4) or 8 (int64, narrowed decimal128)
 };
+// CPUs this process may actually burn: min(hardware threads, affinity mask, cgroup CPU quota).  Containers on the 128-thread
+// box run under `cpu.max 1600000 100000` = 16 CPUs: 64 packing threads there are throttled to a crawl (measured: 1.55 s per
+// SF100 pass vs 0.3 s with 14), so the engine sizes itself by the quota, not by hardware_concurrency().
+int effectiveCpus();
 void launchUnpack(const uint8_t* devSlot, int nCols, int nBlocks, int rows, const UnpackOuts& outs, cudaStream_t s);
 
 // one HOST batch being staged through the engine
@@ -58,18 +62,20 @@ class StagingEngine {
       int32_t rows;
    };
    LdbContext* ctx;
+   int nPack = 0, nRaw = 0; // workers [0, nPack) pack; workers [nPack, nPack + nRaw) ship raw Arrow cells (no CPU work per value)
    std::vector<std::thread> threads;
    std::mutex m;
    std::condition_variable cv;
    std::deque<Task> queue;
    bool stop = false;
    void workerMain(int w);
+   void rawMain(int w);
 
    public:
    // events[w] is re-recorded on worker w's stream after every task it issues: waiting for it covers every earlier task of
    // that (in-order) stream, in particular all tasks of a batch whose remaining count reached zero
    std::vector<cudaEvent_t> events;
-   StagingEngine(LdbContext* ctx, int nThreads);
+   StagingEngine(LdbContext* ctx, int nPackThreads, int nRawThreads);
    ~StagingEngine();
    int workers() const { return (int) threads.size(); }
    // splits the batch into tasks and returns at once; the batch is complete when remaining == 0

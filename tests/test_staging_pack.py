@@ -55,3 +55,23 @@ def test_int64_full_range_needs_8_bytes():
     packed, mn, w = _pack(v, 1, 4)
     assert w == 8 and mn == np.iinfo(np.int64).min
     assert np.array_equal(_unpack(packed, mn, w, 4), v)
+
+
+def test_speculative_single_pass_matches_two_pass_and_falls_back():
+    """ldb_pack_block_hinted: a hint that covers the block packs in one pass against a base <= min; a hint that does not is
+    detected and the block is re-packed exactly.  Either way the decoded values are the source values."""
+    L = capi.lib()
+    L.ldb_pack_block_hinted.restype = C.c_size_t
+    L.ldb_pack_block_hinted.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    rng = np.random.default_rng(7)
+    n = 65536
+    for lo, hi, hint, width in [(1000, 1200, (1010, 1190), 1), (1000, 1200, (5000, 5100), 1), (-50, 60000, (0, 50000), 2), (0, 10**7, (100, 9 * 10**6), 4),
+                                (5, 9, (2**40, 2**40 + 3), 1), (-2**62, 2**62, (0, 10), 8), (0, 100, (-2**63, -2**63 + 50), 1)]:
+        v = rng.integers(lo, hi + 1, n, dtype=np.int64)
+        v[0], v[1] = lo, hi
+        dst = np.zeros(n * 8, np.uint8)
+        mn, w, hl, hh = C.c_int64(), C.c_int32(), C.c_int64(hint[0]), C.c_int64(hint[1])
+        nbytes = L.ldb_pack_block_hinted(v.ctypes.data, 1, n, dst.ctypes.data, C.byref(mn), C.byref(w), C.byref(hl), C.byref(hh))
+        assert (hl.value, hh.value) == (lo, hi)  # the hint now describes this block
+        assert w.value == width and nbytes == n * width and mn.value <= lo
+        assert np.array_equal(_unpack(dst[:nbytes], mn.value, w.value, n), v), (lo, hi, hint)
