@@ -62,6 +62,18 @@ int ldb_gpu_timer_stop(LdbContext* ctx, float* milliseconds, LdbError* err);
 int ldb_gpu_kernel_time(LdbContext* ctx, const char* family, float* ms, int64_t* launches, LdbError* err);
 int ldb_gpu_kernel_time_reset(LdbContext* ctx, int enable, LdbError* err);
 
+/* ------------------------------------------------------------------------------------ captured queries
+ * "Compile once, run many" (the reference JIT-compiles a query's main() once, src/execution/LLVMBackends.cpp:795-867): between
+ * _begin and _end the context's compute stream is captured into a CUDA graph — state creation, pipelines over DEVICE-resident or
+ * already staged tables and peer collectives (ldb_gpu_groupby_allmerge, ldb_gpu_comm_barrier) are recorded instead of run; result
+ * reads and anything that synchronises stay outside.  ldb_gpu_graph_launch replays the whole sequence with one driver call;
+ * states created inside the capture are re-initialised by each replay and are read (ldb_gpu_groupby_read …) after it. */
+typedef struct LdbGraph LdbGraph;
+int ldb_gpu_graph_begin(LdbContext* ctx, LdbError* err);
+int ldb_gpu_graph_end(LdbContext* ctx, LdbGraph** out, LdbError* err);
+int ldb_gpu_graph_launch(LdbGraph* graph, LdbError* err);
+void ldb_gpu_graph_destroy(LdbGraph* graph);
+
 /* ------------------------------------------------------------------------------------ tables
  * Replaces: ArrayView/BatchView (include/lingodb/runtime/ArrowView.h:8-29), LingoDBTable::TableChunk
  * (src/runtime/storage/LingoDBTable.cpp:200-225) and DataSource::get (src/runtime/DataSourceIteration.cpp:57).
@@ -231,7 +243,14 @@ enum LdbPipelineKind {
    LDB_PIPE_SCAN_MATERIALIZE = 6,
    /* K9  scan → filters → probe 0 (composite key, int64 payload) → probe 1 → probe 2 → group by (payload 1, payload 2),
     *     SUM(aggs[0]) with aggs[0].expr = LDB_EXPR_MUL_1MINUS_MINUS_PAYMUL → GroupBy with 2 keys            (Q9) */
-   LDB_PIPE_SCAN_STAR_PROBE_GROUPBY = 7
+   LDB_PIPE_SCAN_STAR_PROBE_GROUPBY = 7,
+   /* K10 scan → filters → [probe | Bloom-only semi-join] → radix partition by h64(key) across the ranks of `comm` → tuples stored
+    *     straight into the DESTINATION rank's receive region over NVLink (fused partition + exchange; multi-GPU joins).
+    *     out_columns[0] = partition/join key (int32), out_columns[1] = second int32 column or "$payload", out_columns[2..3] =
+    *     decimal(p<19) columns shipped as their low 8 bytes.  Tuple = 1 + (n_out_cols - 2) eight-byte words.  The receive region of
+    *     every rank is heap[send_offset, + world * send_capacity * tuple bytes): sub-region s belongs to source rank s.
+    *     send_cursors_offset: heap offset of 16 uint64 (zeroed by the caller): [d] = tuples sent to rank d, [8] = overflow flag. */
+   LDB_PIPE_SCAN_PARTITION_SEND = 8
 };
 /* inline payload of a K3 build: the column's value, or extract(year from <date32 column>) (DateRuntime::extractYear) */
 enum LdbPayloadExpr { LDB_PAYLOAD_COLUMN = 0, LDB_PAYLOAD_YEAR = 1 };
@@ -274,6 +293,9 @@ typedef struct LdbPipelineDesc {
    int64_t out_capacity;
    uint64_t* out_count;
    int32_t probe_bloom_only;
+   /* K10 partition-send */
+   struct LdbComm* comm;
+   int64_t send_offset, send_capacity, send_cursors_offset;
 } LdbPipelineDesc;
 int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* desc, LdbError* err);
 
@@ -315,6 +337,19 @@ int ldb_gpu_comm_allgather_small(LdbComm* comm, const void* dev_src, int64_t byt
  * and folds the peers' images into its own table — ONE kernel instead of export + all-gather + merge.  Afterwards every
  * rank holds the full result.  SIMPLE and GROUPBY states (capacity <= 1024). */
 int ldb_gpu_groupby_allmerge(LdbState* s, LdbComm* comm, LdbError* err);
+/* zero / read back (synchronising) a range of this rank's user heap */
+int ldb_gpu_comm_heap_zero(LdbComm* comm, int64_t user_offset, int64_t bytes, LdbError* err);
+int ldb_gpu_comm_heap_read(LdbComm* comm, int64_t user_offset, int64_t bytes, void* host_dst, LdbError* err);
+/* ---- receive side of LDB_PIPE_SCAN_PARTITION_SEND (all offsets are user-heap offsets, identical on every rank)
+ * publish: copy this rank's cursors[d] into rank d's counts[rank] (heap[counts_offset + rank * 8]); follow with a barrier */
+int ldb_gpu_comm_publish_counts(LdbComm* comm, int64_t cursors_offset, int64_t counts_offset, LdbError* err);
+/* insert the {key:32 | payload:32} tuples received from every source (counts read on the device) into a join table */
+int ldb_gpu_join_table_insert_received(LdbState* table, LdbComm* comm, int64_t recv_offset, int64_t capacity, int64_t counts_offset, LdbError* err);
+/* received {keyA:32 | keyB:32, a, b} tuples → probe A, probe B, payloads equal → group by payload → SUM(a * (1 - b)) (decimal scale `scale`) */
+int ldb_gpu_probe_received_groupby(LdbState* table_a, LdbState* table_b, LdbState* groups, LdbComm* comm, int64_t recv_offset, int64_t capacity, int64_t counts_offset, int32_t scale, LdbError* err);
+/* a join table whose Bloom filter lives in the symmetric heap at bloom_offset (so the ranks can OR their partitions' filters
+ * together with ldb_gpu_comm_or_reduce); *bloom_bytes = size of the filter (call with out == NULL to query it for expected_rows) */
+int ldb_gpu_join_table_create_shared_bloom(LdbContext* ctx, int64_t expected_rows, int32_t unique_keys, LdbComm* comm, int64_t bloom_offset, int64_t* bloom_bytes, LdbState** out, LdbError* err);
 /* OR-all-reduce of heap[user_offset, +bytes) across the ranks (Bloom filters of hash partitions); barrier before and after */
 int ldb_gpu_comm_or_reduce(LdbComm* comm, int64_t user_offset, int64_t bytes, LdbError* err);
 /* synchronises and reports a collective that timed out on a dead peer (LDB_PEER_TIMEOUT_MS, default 20000) */

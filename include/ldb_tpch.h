@@ -63,6 +63,23 @@ int ldb_tpch_q9_partial(LdbContext* ctx, const LdbTpchTables* t, const char* nam
 int ldb_tpch_q9_finish(LdbState* group_state, LdbQ9Row* rows /* max_rows */, int32_t max_rows, int32_t* n_rows, LdbError* err);
 int ldb_tpch_q9(LdbContext* ctx, const LdbTpchTables* t, const char* name_contains, LdbQ9Row* rows /* max_rows */, int32_t max_rows, int32_t* n_rows, LdbError* err);
 
+/* Q5 with the orders ⋈ lineitem join radix-partitioned across the ranks of `comm` (BASELINE.json config 3; no reference
+ * counterpart, the reference is single-process).  `t` holds THIS rank's shard of orders and lineitem (any split) and full copies
+ * of customer/supplier/nation/region (small build sides are replicated).  Every data-path step is a kernel on the context's
+ * stream: qualifying orders are partitioned by h64(o_orderkey) and stored straight into the owning rank's receive region over
+ * NVLink (K10), each rank builds its hash partition, the partitions' Bloom filters are OR-ed through peer loads so that every
+ * rank pre-filters its lineitem shard before the second partition-send, probes + the 5-group aggregation run where the
+ * partition lives, and the group tables are merged by the peer all-merge kernel.  No NCCL call, no host synchronisation
+ * between the first send and the result read.  The comm's user heap must hold ldb_tpch_q5_repartitioned_heap_bytes(). */
+typedef struct LdbQ5ShuffleStats {
+   int64_t orders_tuples_sent, orders_tuples_received, lineitem_tuples_sent, lineitem_tuples_received;
+   int64_t shuffle_bytes_out; /* 8 B per orders tuple + 24 B per lineitem tuple, tuples that stay on this rank included */
+   int64_t heap_bytes;
+} LdbQ5ShuffleStats;
+int64_t ldb_tpch_q5_repartitioned_heap_bytes(int64_t n_orders_total, int64_t n_lineitem_total, int32_t world);
+int ldb_tpch_q5_repartitioned(LdbContext* ctx, const LdbTpchTables* t, struct LdbComm* comm, const char* region_name, const char* date_ge, const char* date_lt,
+                              int64_t n_orders_total, int64_t n_lineitem_total, LdbQ5Row* rows /* 25 */, int32_t* n_rows, LdbQ5ShuffleStats* stats, LdbError* err);
+
 #ifdef __cplusplus
 }
 #endif

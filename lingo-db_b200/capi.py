@@ -15,7 +15,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 OPS = {"=": 0, "!=": 1, "<": 2, "<=": 3, ">": 4, ">=": 5, "notnull": 6, "in": 7, "contains": 8}
 EXPR = {"col": 0, "mul": 1, "mul_1minus": 2, "mul_1minus_1plus": 3, "one": 4, "mul_1minus_minus_paymul": 5}
 PIPE = {"scan_reduce": 1, "scan_groupby": 2, "scan_build": 3, "scan_probe_agg": 4, "scan_probe2_groupby": 5, "scan_materialize": 6,
-        "scan_star_probe_groupby": 7}
+        "scan_star_probe_groupby": 7, "scan_partition_send": 8}
 PAYLOAD_EXPR = {"column": 0, "year": 1}
 MAX_AGGS, MAX_KEYS, MAX_SIDE = 8, 2, 2
 
@@ -80,7 +80,8 @@ class PipelineDesc(C.Structure):
                 ("build_payload_expr", C.c_int32), ("n_side", C.c_int32),
                 ("side_columns", C.c_char_p * MAX_SIDE), ("sink", C.c_void_p),
                 ("n_out_cols", C.c_int32), ("out_columns", C.c_char_p * 4), ("out_buffers", C.c_void_p * 4), ("out_capacity", C.c_int64),
-                ("out_count", C.c_void_p), ("probe_bloom_only", C.c_int32)]
+                ("out_count", C.c_void_p), ("probe_bloom_only", C.c_int32),
+                ("comm", C.c_void_p), ("send_offset", C.c_int64), ("send_capacity", C.c_int64), ("send_cursors_offset", C.c_int64)]
 
 
 class TpchTables(C.Structure):
@@ -99,6 +100,10 @@ class Q3Row(C.Structure):
 
 class Q5Row(C.Structure):
     _fields_ = [("n_nationkey", C.c_int32), ("pad", C.c_int32), ("revenue", I128)]
+
+
+class Q5ShuffleStats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("orders_tuples_sent", "orders_tuples_received", "lineitem_tuples_sent", "lineitem_tuples_received", "shuffle_bytes_out", "heap_bytes")]
 
 
 class Q9Row(C.Structure):
@@ -122,6 +127,10 @@ SIGNATURES = {
     "ldb_gpu_timer_stop": (C.c_int, [_P, C.POINTER(C.c_float), _E]),
     "ldb_gpu_kernel_time": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_int64), _E]),
     "ldb_gpu_kernel_time_reset": (C.c_int, [_P, C.c_int, _E]),
+    "ldb_gpu_graph_begin": (C.c_int, [_P, _E]),
+    "ldb_gpu_graph_end": (C.c_int, [_P, C.POINTER(_P), _E]),
+    "ldb_gpu_graph_launch": (C.c_int, [_P, _E]),
+    "ldb_gpu_graph_destroy": (None, [_P]),
     "ldb_gpu_table_create": (C.c_int, [_P, C.c_char_p, C.c_int32, C.POINTER(ColumnSchema), C.POINTER(_P), _E]),
     "ldb_gpu_table_append_batch": (C.c_int, [_P, C.c_int64, C.POINTER(ArrayView), C.POINTER(C.c_int64), C.c_int32, _E]),
     "ldb_gpu_table_clear": (C.c_int, [_P, _E]),
@@ -158,6 +167,12 @@ SIGNATURES = {
     "ldb_gpu_comm_barrier": (C.c_int, [_P, _E]),
     "ldb_gpu_comm_allgather_small": (C.c_int, [_P, _P, C.c_int64, C.POINTER(_P), _E]),
     "ldb_gpu_groupby_allmerge": (C.c_int, [_P, _P, _E]),
+    "ldb_gpu_comm_heap_zero": (C.c_int, [_P, C.c_int64, C.c_int64, _E]),
+    "ldb_gpu_comm_heap_read": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _E]),
+    "ldb_gpu_comm_publish_counts": (C.c_int, [_P, C.c_int64, C.c_int64, _E]),
+    "ldb_gpu_join_table_insert_received": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _E]),
+    "ldb_gpu_probe_received_groupby": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _E]),
+    "ldb_gpu_join_table_create_shared_bloom": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, C.POINTER(C.c_int64), C.POINTER(_P), _E]),
     "ldb_gpu_comm_or_reduce": (C.c_int, [_P, C.c_int64, C.c_int64, _E]),
     "ldb_gpu_comm_check": (C.c_int, [_P, _E]),
     "ldb_gpu_hash_i64": (C.c_int, [_P, _P, _P, C.c_int64, _P, _E]),
@@ -181,6 +196,9 @@ SIGNATURES = {
     "ldb_tpch_q1_finish": (C.c_int, [_P, C.POINTER(Q1Row), C.c_int32, C.POINTER(C.c_int32), _E]),
     "ldb_tpch_q3": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.c_char_p, C.POINTER(Q3Row), C.POINTER(C.c_int32), _E]),
     "ldb_tpch_q5": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(Q5Row), C.POINTER(C.c_int32), _E]),
+    "ldb_tpch_q5_repartitioned_heap_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int32]),
+    "ldb_tpch_q5_repartitioned": (C.c_int, [_P, C.POINTER(TpchTables), _P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, C.c_int64, C.POINTER(Q5Row), C.POINTER(C.c_int32),
+                                            C.POINTER(Q5ShuffleStats), _E]),
     "ldb_tpch_q9_partial": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.POINTER(_P), _E]),
     "ldb_tpch_q9_finish": (C.c_int, [_P, C.POINTER(Q9Row), C.c_int32, C.POINTER(C.c_int32), _E]),
     "ldb_tpch_q9": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.POINTER(Q9Row), C.c_int32, C.POINTER(C.c_int32), _E]),

@@ -71,7 +71,9 @@ struct PackedBatch;
 struct LdbState;
 struct LdbTable;
 
+struct LdbGraph;
 struct LdbContext {
+   LdbGraph* capturing = nullptr; // non-null between ldb_gpu_graph_begin and _end: launches are recorded, not run
    int device = 0;
    int smCount = 0;
    cudaDeviceProp prop{};
@@ -83,6 +85,7 @@ struct LdbContext {
    std::vector<cudaEvent_t> eventPool;
    std::vector<LdbState*> states;
    std::vector<LdbTable*> tables;
+   std::vector<LdbGraph*> graphs;
    // staging pool for HOST batches: size → free device buffers
    std::multimap<size_t, void*> stagingFree;
    std::map<void*, size_t> stagingSize;
@@ -121,12 +124,18 @@ struct LdbContext {
       if (!pinnedScratch) LDB_CUDA(cudaMallocHost(&pinnedScratch, kPinnedScratchBytes));
       return pinnedScratch;
    }
+   void launchCaptured(const char* family, const std::function<void()>& fn); // runtime.cpp
    void* stagingAlloc(size_t bytes);
    void stagingRelease(void* p);
    cudaEvent_t getEvent();
    // wrap one kernel launch: counts it and, when timing is on, brackets it with events on `compute`
    template <class Fn>
    void launch(const char* family, const Fn& fn) {
+      if (capturing) {
+         launchCaptured(family, [&] { fn(); });
+         LDB_CUDA(cudaGetLastError());
+         return;
+      }
       launches++;
       if (timing) {
          auto& t = timers[family];
@@ -168,6 +177,22 @@ struct LdbTable {
          if (columns[i].name == n) return (int) i;
       return -1;
    }
+};
+
+// A captured query (CUDA graph of everything enqueued on the compute stream between _begin and _end): one cudaGraphLaunch
+// replays memsets, pipeline kernels and peer collectives without per-launch host work.
+struct LdbGraph {
+   LdbContext* ctx = nullptr;
+   cudaGraph_t graph = nullptr;
+   cudaGraphExec_t exec = nullptr;
+   int64_t kernelsPerLaunch = 0;
+   struct Timer {
+      std::string family;
+      cudaEvent_t a, b; // recorded by the graph itself (external event-record nodes)
+   };
+   std::vector<Timer> timers;
+   bool pendingTimes = false; // the last launch's events were not harvested yet
+   std::vector<std::function<void()>> onLaunch; // host-side bookkeeping per replay (peer epoch mirrors)
 };
 
 struct LdbState {

@@ -1664,4 +1664,126 @@ void launchPartitionScatter(const int32_t* keys, const void* const* payloadCols,
    partitionScatterKernel<<<grid, kBlock, 0, s>>>(keys, cols, n, nParts, cursors, outKeys);
 }
 
+// =================================================================================== K10 fused scan → partition → peer store
+// (multi-GPU repartition step of a join: subop.materialize + the exchange the reference does not have)
+template <int DB>
+__global__ void __launch_bounds__(kBlock, 4) scanPartitionSendKernel(const __grid_constant__ SendParams p) {
+   constexpr bool IN = true;
+   __shared__ __align__(8) TileBarriers barsStorage;
+   __shared__ unsigned int sCnt[kMaxRanks];
+   __shared__ unsigned long long sBase[kMaxRanks];
+   TileBarriers* bars = &barsStorage;
+   if (threadIdx.x < kMaxRanks) sCnt[threadIdx.x] = 0;
+   __syncthreads();
+   const int words = 1 + p.nDec;
+   forEachTileUniform<kRowsPerThreadProbe, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+      bool emit[kRowsPerThreadProbe];
+      int lrs[kRowsPerThreadProbe], dest[kRowsPerThreadProbe];
+      int32_t key[kRowsPerThreadProbe], second[kRowsPerThreadProbe];
+      unsigned pos[kRowsPerThreadProbe];
+#pragma unroll
+      for (int j = 0; j < kRowsPerThreadProbe; j++) {
+         const int lr = j * kBlock + threadIdx.x;
+         const bool valid = lr < rows;
+         lrs[j] = valid ? lr : 0;
+         bool ok = valid && evalFilters<IN>(p.src.filters, tile, lrs[j], rowBase + lrs[j]);
+         key[j] = tile.i32(p.keyStage, lrs[j]);
+         second[j] = p.secondStage >= 0 ? tile.i32(p.secondStage, lrs[j]) : 0;
+         if (ok && p.hasProbe) {
+            const int32_t pk = tile.i32(p.probeKeyStage, lrs[j]);
+            if (p.bloomOnly) {
+               ok = bloomMayContain(p.probe, pk);
+            } else {
+               bool found = false;
+               joinProbe(p.probe, pk, [&](int64_t, int32_t pay) {
+                  found = true;
+                  if (p.secondStage < 0) second[j] = pay;
+               });
+               ok = found;
+            }
+         }
+         emit[j] = ok;
+         dest[j] = ok ? partOf(key[j], p.world) : 0;
+         pos[j] = ok ? atomicAdd(&sCnt[dest[j]], 1u) : 0u; // few percent of the rows get here: a shared atomic each is cheap
+      }
+      __syncthreads();
+      if (threadIdx.x < p.world) { // ONE global atomic per destination per tile claims the range of all its tuples
+         const unsigned n = sCnt[threadIdx.x];
+         sBase[threadIdx.x] = n ? atomicAdd(&p.cursors[threadIdx.x], (unsigned long long) n) : 0ull;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < kRowsPerThreadProbe; j++) {
+         if (!emit[j]) continue;
+         const unsigned long long at = sBase[dest[j]] + pos[j];
+         if (at >= (unsigned long long) p.capacity) {
+            atomicExch(p.error, 6);
+            continue;
+         }
+         unsigned long long* out = (unsigned long long*) p.dest[dest[j]] + at * words; // peer HBM over NVLink (or local for dest == rank)
+         out[0] = packSlot(key[j], second[j]);
+         for (int d = 0; d < p.nDec; d++) out[1 + d] = (unsigned long long) tile.lo64(p.decStage[d], lrs[j]);
+      }
+      if (threadIdx.x < kMaxRanks) sCnt[threadIdx.x] = 0;
+      __syncthreads();
+   });
+}
+void launchScanPartitionSend(const SendParams& p, int smCount, cudaStream_t s) {
+   size_t dyn;
+   if (p.src.cols.decBytes == 8) {
+      int grid = persistentGrid(scanPartitionSendKernel<8>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+      scanPartitionSendKernel<8><<<grid, kBlock, dyn, s>>>(p);
+   } else {
+      int grid = persistentGrid(scanPartitionSendKernel<16>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
+      scanPartitionSendKernel<16><<<grid, kBlock, dyn, s>>>(p);
+   }
+}
+// tuples received from `world` sources: sub-region s holds counts[s] tuples (count read from device memory: no host round trip)
+__global__ void __launch_bounds__(kBlock) insertReceivedKernel(JoinTableDev t, const uint8_t* recv, int world, int64_t capacity, const unsigned long long* counts) {
+   unsigned long long inserted = 0;
+   const int64_t total = (int64_t) world * capacity;
+   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t) gridDim.x * blockDim.x) {
+      const int src = (int) (i / capacity);
+      const int64_t idx = i - (int64_t) src * capacity;
+      if ((unsigned long long) idx >= counts[src]) continue;
+      const unsigned long long e = ((const unsigned long long*) recv)[i];
+      if (joinInsert(t, (int32_t) (uint32_t) e, (int32_t) (uint32_t) (e >> 32)) >= 0) inserted++;
+   }
+   flushInsertCount(t, inserted);
+}
+void launchInsertReceived(const JoinTableDev& t, const uint8_t* recv, int world, int64_t capacity, const unsigned long long* counts, int smCount, cudaStream_t s) {
+   const int64_t total = (int64_t) world * capacity;
+   int grid = (int) std::min<int64_t>(std::max<int64_t>((total + kBlock - 1) / kBlock, 1), (int64_t) smCount * 8);
+   insertReceivedKernel<<<grid, kBlock, 0, s>>>(t, recv, world, capacity, counts);
+}
+__global__ void __launch_bounds__(kBlock) probeReceivedGroupByKernel(JoinTableDev tableA, JoinTableDev tableB, GroupTableDev groupsOut, const uint8_t* recv, int world, int64_t capacity,
+                                                                     const unsigned long long* counts, int64_t one) {
+   __shared__ LocalGroups groups;
+   groups.init();
+   __syncthreads();
+   const int64_t total = (int64_t) world * capacity;
+   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t) gridDim.x * blockDim.x) {
+      const int src = (int) (i / capacity);
+      const int64_t idx = i - (int64_t) src * capacity;
+      if ((unsigned long long) idx >= counts[src]) continue;
+      const unsigned long long* tup = (const unsigned long long*) recv + i * 3;
+      const unsigned long long w0 = tup[0];
+      const int32_t keyA = (int32_t) (uint32_t) w0, keyB = (int32_t) (uint32_t) (w0 >> 32);
+      const int64_t a = (int64_t) tup[1], b = (int64_t) tup[2];
+      joinProbe(tableA, keyA, [&](int64_t, int32_t payA) {
+         joinProbe(tableB, keyB, [&](int64_t, int32_t payB) {
+            if (payA == payB) groups.add(groupsOut, payB, 0, mul64x64(a, one - b), false);
+         });
+      });
+   }
+   __syncthreads();
+   groups.flush(groupsOut, false);
+}
+void launchProbeReceivedGroupBy(const JoinTableDev& tableA, const JoinTableDev& tableB, const GroupTableDev& groups, const uint8_t* recv, int world, int64_t capacity,
+                                const unsigned long long* counts, int64_t one, int smCount, cudaStream_t s) {
+   const int64_t total = (int64_t) world * capacity;
+   int grid = (int) std::min<int64_t>(std::max<int64_t>((total + kBlock - 1) / kBlock, 1), (int64_t) smCount * 4);
+   probeReceivedGroupByKernel<<<grid, kBlock, 0, s>>>(tableA, tableB, groups, recv, world, capacity, counts, one);
+}
+
 } // namespace ldb

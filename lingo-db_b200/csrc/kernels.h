@@ -178,6 +178,34 @@ struct TopKRowDev {
    long long aggHi;
 };
 
+// ---- fused repartition (multi-GPU joins): scan → filters → [probe | Bloom semi-join] → radix partition by h64(key) → tuples
+// stored STRAIGHT into the destination rank's receive buffer over NVLink (peer-mapped heap, csrc/peer.cu) — no staging copy,
+// no collective call.  A tuple is 1..3 eight-byte words: {key:32 | second:32}, then up to two decimal(p<19) values (lo64).
+// Every (source, destination) pair owns a sub-region of `capacity` tuples in the destination's buffer, so the only atomics
+// are the source's local per-destination cursors (one per destination per tile).
+constexpr int kMaxRanks = 8;
+struct SendParams {
+   ScanSource src;
+   int32_t keyStage;
+   int32_t secondStage; // staged int32 column, or -1: the probe's payload
+   int32_t nDec;
+   int32_t decStage[2];
+   int32_t hasProbe, bloomOnly;
+   JoinTableDev probe;
+   int32_t probeKeyStage;
+   int32_t world;
+   uint8_t* dest[kMaxRanks]; // destination d's receive region, already offset to THIS source's sub-region
+   int64_t capacity;         // tuples per sub-region
+   unsigned long long* cursors; // [world], device-local, zeroed by the caller
+   int32_t* error;              // 6 = a sub-region overflowed
+};
+void launchScanPartitionSend(const SendParams& p, int smCount, cudaStream_t s);
+// received tuples of `world` sources (counts[src] tuples each, read from DEVICE memory) → join-table inserts
+void launchInsertReceived(const JoinTableDev& t, const uint8_t* recv, int world, int64_t capacity, const unsigned long long* counts, int smCount, cudaStream_t s);
+// received {key|keyB, a, b} tuples → probe A on key, probe B on keyB, payloads equal → group by payload → SUM(a * (one - b))
+void launchProbeReceivedGroupBy(const JoinTableDev& tableA, const JoinTableDev& tableB, const GroupTableDev& groups, const uint8_t* recv, int world, int64_t capacity,
+                                const unsigned long long* counts, int64_t one, int smCount, cudaStream_t s);
+
 // signature → instantiation registry for the group-by kernel; returns false when no compiled shape matches
 bool launchScanGroupBy(const GroupByParams& p, int smCount, cudaStream_t s, const char** why);
 void launchScanBuild(const BuildParams& p, int smCount, cudaStream_t s);

@@ -51,7 +51,16 @@ __device__ __forceinline__ bool waitFlag(const unsigned long long* flag, unsigne
 }
 
 // all-to-all "I am here": CTA p tells peer p and waits for peer p
-__global__ void peerBarrierKernel(PeerView v, unsigned long long epoch) {
+enum EpochKind { EPOCH_BARRIER = 0, EPOCH_GATHER = 1, EPOCH_MERGE = 2 };
+__device__ __forceinline__ unsigned long long nextEpoch(const PeerView& v, int kind) { return ((const volatile unsigned long long*) (v.heap[v.rank] + kEpochsOff))[kind] + 1; }
+// runs behind every collective kernel (stream order): the epoch a kernel reads is stable for all its CTAs
+__global__ void peerBumpKernel(PeerView v, int kindA, int kindB) {
+   unsigned long long* e = (unsigned long long*) (v.heap[v.rank] + kEpochsOff);
+   e[kindA]++;
+   if (kindB >= 0) e[kindB]++;
+}
+__global__ void peerBarrierKernel(PeerView v) {
+   const unsigned long long epoch = nextEpoch(v, EPOCH_BARRIER);
    const int p = blockIdx.x;
    if (p == v.rank || threadIdx.x != 0) return;
    __threadfence_system(); // everything this GPU wrote into peer memory before the barrier (earlier kernels of the stream included)
@@ -81,7 +90,8 @@ __device__ __forceinline__ bool waitBlock(const PeerView& v, int p, unsigned lon
    __syncthreads();
    return ok != 0;
 }
-__global__ void __launch_bounds__(256) peerAllGatherKernel(PeerView v, const uint8_t* src, size_t bytes, unsigned long long epoch) {
+__global__ void __launch_bounds__(256) peerAllGatherKernel(PeerView v, const uint8_t* src, size_t bytes) {
+   const unsigned long long epoch = nextEpoch(v, EPOCH_GATHER);
    const int p = blockIdx.x;
    pushBlock(v, p, src, bytes, epoch);
    waitBlock(v, p, epoch);
@@ -91,7 +101,9 @@ __global__ void __launch_bounds__(256) peerAllGatherKernel(PeerView v, const uin
 // the image: state | keys | acc) to peer p, waits for peer p's image and folds it into the local table with the same
 // lookup-or-insert + two-word atomic adds the single-GPU flush uses (rt::PreAggregationHashtable::merge semantics: sums per key).
 __device__ int peerGroupLookupOrInsert(const GroupTableDev& t, const int32_t* k); // kernels.cu twin, defined below
-__global__ void __launch_bounds__(256) peerGroupAllMergeKernel(PeerView v, GroupTableDev t, size_t imageBytes, unsigned long long epoch, unsigned long long localTarget) {
+__global__ void __launch_bounds__(256) peerGroupAllMergeKernel(PeerView v, GroupTableDev t, size_t imageBytes) {
+   const unsigned long long epoch = nextEpoch(v, EPOCH_GATHER);
+   const unsigned long long localTarget = nextEpoch(v, EPOCH_MERGE) * (unsigned long long) (v.world - 1);
    const int p = blockIdx.x;
    if (p == v.rank) return; // the own table is merged into, not from
    pushBlock(v, p, (const uint8_t*) t.state, imageBytes, epoch);
@@ -168,6 +180,13 @@ __global__ void __launch_bounds__(256) peerOrReduceKernel(PeerView v, size_t hea
       }
       own[i] = a;
    }
+}
+
+__global__ void peerPublishCountsKernel(PeerView v, size_t cursorsOff, size_t countsOff) {
+   const int d = threadIdx.x;
+   if (d >= v.world) return;
+   const unsigned long long n = *((const unsigned long long*) (v.heap[v.rank] + cursorsOff) + d);
+   *((unsigned long long*) (v.heap[d] + countsOff) + v.rank) = n; // plain store into the peer; the barrier that follows publishes it
 }
 
 } // namespace ldb
@@ -315,8 +334,10 @@ int ldb_gpu_comm_barrier(LdbComm* c, LdbError* err) {
       if (c->world == 1) return;
       LdbContext* ctx = c->ctx;
       LDB_CUDA(cudaSetDevice(ctx->device));
-      const unsigned long long epoch = ++c->barrierEpoch;
-      ctx->launch("peer_barrier", [&] { peerBarrierKernel<<<c->world, 32, 0, ctx->compute>>>(c->view(), epoch); });
+      ctx->launch("peer_barrier", [&] {
+         peerBarrierKernel<<<c->world, 32, 0, ctx->compute>>>(c->view());
+         peerBumpKernel<<<1, 1, 0, ctx->compute>>>(c->view(), EPOCH_BARRIER, -1);
+      });
    });
 }
 
@@ -329,8 +350,12 @@ int ldb_gpu_comm_allgather_small(LdbComm* c, const void* src, int64_t bytes, voi
       if (bytes <= 0 || bytes > (int64_t) kSlotBytes || bytes % 16) failPeer(LDB_ERR_INVALID, "all-gather blocks are 16..262144 bytes, multiples of 16");
       LdbContext* ctx = c->ctx;
       LDB_CUDA(cudaSetDevice(ctx->device));
-      const unsigned long long epoch = ++c->gatherEpoch;
-      ctx->launch("peer_allgather", [&] { peerAllGatherKernel<<<c->world, 256, 0, ctx->compute>>>(c->view(), (const uint8_t*) src, (size_t) bytes, epoch); });
+      if (ctx->capturing) failPeer(LDB_ERR_UNSUPPORTED, "the small all-gather returns a parity-dependent address and cannot be captured");
+      const unsigned long long epoch = ++c->gatherEpochHost; // mirror of the device counter (every rank issues the same collectives)
+      ctx->launch("peer_allgather", [&] {
+         peerAllGatherKernel<<<c->world, 256, 0, ctx->compute>>>(c->view(), (const uint8_t*) src, (size_t) bytes);
+         peerBumpKernel<<<1, 1, 0, ctx->compute>>>(c->view(), EPOCH_GATHER, -1);
+      });
       if (result) *result = c->heap + kMailboxOff + (size_t) (epoch & 1) * c->world * kSlotBytes;
    });
 }
@@ -345,10 +370,12 @@ int ldb_gpu_groupby_allmerge(LdbState* s, LdbComm* c, LdbError* err) {
       if (image > kSlotBytes) failPeer(LDB_ERR_UNSUPPORTED, "group table image larger than a mailbox slot (capacity <= 1024 groups)");
       LdbContext* ctx = c->ctx;
       LDB_CUDA(cudaSetDevice(ctx->device));
-      const unsigned long long epoch = ++c->gatherEpoch;
-      c->localSyncTarget += (unsigned long long) (c->world - 1);
-      const unsigned long long target = c->localSyncTarget;
-      ctx->launch("peer_group_allmerge", [&] { peerGroupAllMergeKernel<<<c->world, 256, 0, ctx->compute>>>(c->view(), s->group, image, epoch, target); });
+      ++c->gatherEpochHost;
+      if (ctx->capturing) ctx->capturing->onLaunch.push_back([c] { ++c->gatherEpochHost; }); // every replay bumps the device epoch once more
+      ctx->launch("peer_group_allmerge", [&] {
+         peerGroupAllMergeKernel<<<c->world, 256, 0, ctx->compute>>>(c->view(), s->group, image);
+         peerBumpKernel<<<1, 1, 0, ctx->compute>>>(c->view(), EPOCH_GATHER, EPOCH_MERGE);
+      });
    });
 }
 
@@ -362,6 +389,66 @@ int ldb_gpu_comm_or_reduce(LdbComm* c, int64_t user_offset, int64_t bytes, LdbEr
       const size_t n4 = (size_t) bytes / 16;
       const int grid = (int) std::min<size_t>((n4 + 255) / 256, (size_t) ctx->smCount * 8);
       ctx->launch("peer_or_reduce", [&] { peerOrReduceKernel<<<grid, 256, 0, ctx->compute>>>(c->view(), kUserOff + (size_t) user_offset, n4); });
+   });
+}
+
+int ldb_gpu_comm_heap_zero(LdbComm* c, int64_t user_offset, int64_t bytes, LdbError* err) {
+   return guardedPeer(err, [&] {
+      if (!c || user_offset < 0 || bytes < 0 || (size_t) (user_offset + bytes) > c->userBytes) failPeer(LDB_ERR_INVALID, "range outside the comm's user heap");
+      LDB_CUDA(cudaSetDevice(c->ctx->device));
+      LDB_CUDA(cudaMemsetAsync(c->heap + kUserOff + user_offset, 0, (size_t) bytes, c->ctx->compute));
+   });
+}
+int ldb_gpu_comm_heap_read(LdbComm* c, int64_t user_offset, int64_t bytes, void* host_dst, LdbError* err) {
+   return guardedPeer(err, [&] {
+      if (!c || !host_dst || user_offset < 0 || bytes < 0 || (size_t) (user_offset + bytes) > c->userBytes) failPeer(LDB_ERR_INVALID, "range outside the comm's user heap");
+      LDB_CUDA(cudaSetDevice(c->ctx->device));
+      LDB_CUDA(cudaMemcpyAsync(host_dst, c->heap + kUserOff + user_offset, (size_t) bytes, cudaMemcpyDeviceToHost, c->ctx->compute));
+      c->ctx->syncStream(c->ctx->compute);
+   });
+}
+static void wantRange(LdbComm* c, int64_t off, int64_t bytes, const char* what) {
+   if (off < 0 || bytes < 0 || off % 16 || (size_t) (off + bytes) > c->userBytes) failPeer(LDB_ERR_CAPACITY, std::string(what) + " outside the comm's user heap (create the comm with a larger heap)");
+}
+int ldb_gpu_comm_publish_counts(LdbComm* c, int64_t cursors_offset, int64_t counts_offset, LdbError* err) {
+   return guardedPeer(err, [&] {
+      wantConnected(c);
+      wantRange(c, cursors_offset, 16 * 8, "cursors");
+      wantRange(c, counts_offset, kMaxPeers * 8, "counts");
+      LdbContext* ctx = c->ctx;
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      ctx->launch("peer_publish_counts", [&] { peerPublishCountsKernel<<<1, 32, 0, ctx->compute>>>(c->view(), kUserOff + (size_t) cursors_offset, kUserOff + (size_t) counts_offset); });
+   });
+}
+int ldb_gpu_join_table_insert_received(LdbState* table, LdbComm* c, int64_t recv_offset, int64_t capacity, int64_t counts_offset, LdbError* err) {
+   return guardedPeer(err, [&] {
+      wantConnected(c);
+      if (!table || table->kind != LDB_STATE_JOIN_TABLE || table->join.stride != 8 || table->join.direct) failPeer(LDB_ERR_INVALID, "insert target must be a plain single-key join table");
+      wantRange(c, recv_offset, (int64_t) c->world * capacity * 8, "receive region");
+      wantRange(c, counts_offset, kMaxPeers * 8, "counts");
+      LdbContext* ctx = c->ctx;
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      uint8_t* user = c->heap + kUserOff;
+      ctx->launch("join_build", [&] { launchInsertReceived(table->join, user + recv_offset, c->world, capacity, (const unsigned long long*) (user + counts_offset), ctx->smCount, ctx->compute); });
+   });
+}
+int ldb_gpu_probe_received_groupby(LdbState* ta, LdbState* tb, LdbState* groups, LdbComm* c, int64_t recv_offset, int64_t capacity, int64_t counts_offset, int32_t scale, LdbError* err) {
+   return guardedPeer(err, [&] {
+      wantConnected(c);
+      for (LdbState* t : {ta, tb})
+         if (!t || t->kind != LDB_STATE_JOIN_TABLE || t->join.stride != 8 || t->join.direct) failPeer(LDB_ERR_INVALID, "probe tables must be plain single-key join tables");
+      if (!groups || groups->kind != LDB_STATE_GROUPBY || groups->group.nKeys != 1 || groups->group.nAggs != 1) failPeer(LDB_ERR_INVALID, "sink must be a group-by state with one key and one aggregate");
+      if (scale < 0 || scale > 18) failPeer(LDB_ERR_INVALID, "decimal scale out of range");
+      wantRange(c, recv_offset, (int64_t) c->world * capacity * 24, "receive region");
+      wantRange(c, counts_offset, kMaxPeers * 8, "counts");
+      int64_t one = 1;
+      for (int i = 0; i < scale; i++) one *= 10;
+      LdbContext* ctx = c->ctx;
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      uint8_t* user = c->heap + kUserOff;
+      ctx->launch("join_probe2_groupby", [&] {
+         launchProbeReceivedGroupBy(ta->join, tb->join, groups->group, user + recv_offset, c->world, capacity, (const unsigned long long*) (user + counts_offset), one, ctx->smCount, ctx->compute);
+      });
    });
 }
 

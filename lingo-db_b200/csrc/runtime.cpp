@@ -3,6 +3,7 @@
 // src/runtime surface for the three hot paths; there is NO CPU fallback: without a CUDA device
 // every entry point fails with LDB_ERR_NO_DEVICE.
 #include "context.h"
+#include "peer.h"
 #include "staging.h"
 
 #include <algorithm>
@@ -200,6 +201,20 @@ cudaEvent_t LdbContext::getEvent() {
    return e;
 }
 
+// a launch while the compute stream is being captured: bracket it with EXTERNAL event-record nodes so that every replay of the
+// graph times the kernel, like the eager path does (ldb_gpu_kernel_time harvests them)
+void LdbContext::launchCaptured(const char* family, const std::function<void()>& fn) {
+   LdbGraph* g = capturing;
+   g->kernelsPerLaunch++;
+   cudaEvent_t a = nullptr, b = nullptr;
+   LDB_CUDA(cudaEventCreate(&a));
+   LDB_CUDA(cudaEventCreate(&b));
+   g->timers.push_back({family, a, b});
+   LDB_CUDA(cudaEventRecordWithFlags(a, compute, cudaEventRecordExternal));
+   fn();
+   LDB_CUDA(cudaEventRecordWithFlags(b, compute, cudaEventRecordExternal));
+}
+
 extern "C" {
 
 int ldb_gpu_context_create(int device, LdbContext** out, LdbError* err) {
@@ -309,9 +324,11 @@ int ldb_gpu_kernel_time_reset(LdbContext* ctx, int enable, LdbError* err) {
       ctx->timing = enable != 0;
    });
 }
+static void harvestGraphTimes(LdbGraph* g);
 int ldb_gpu_kernel_time(LdbContext* ctx, const char* family, float* ms, int64_t* launches, LdbError* err) {
    return guarded(err, [&] {
       ctx->syncStream(ctx->compute);
+      for (LdbGraph* g : ctx->graphs) harvestGraphTimes(g);
       auto it = ctx->timers.find(family);
       if (it == ctx->timers.end()) {
          *ms = 0;
@@ -330,6 +347,84 @@ int ldb_gpu_kernel_time(LdbContext* ctx, const char* family, float* ms, int64_t*
       *ms = (float) t.totalMs;
       *launches = t.launches;
    });
+}
+
+// ------------------------------------------------------------------------------------------------ captured queries (CUDA graphs)
+// Replaces nothing in the reference by name: it is the GPU counterpart of "compile once, run many" (the reference JIT-compiles a
+// query's main() once, LLVMBackends.cpp:795-867).  Between _begin and _end the compute stream is in capture mode: pipelines over
+// DEVICE-resident (or already staged) tables, state creation and peer collectives are recorded; result reads and anything else that
+// synchronises must stay outside.  States created inside the capture are re-initialised by every launch and belong to the caller.
+static void harvestGraphTimes(LdbGraph* g) {
+   if (!g->pendingTimes) return;
+   for (auto& t : g->timers) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, t.a, t.b) != cudaSuccess) {
+         cudaGetLastError();
+         return; // not finished yet: the caller has not synchronised — keep them pending
+      }
+      auto& acc = g->ctx->timers[t.family];
+      acc.totalMs += ms;
+      acc.launches++;
+   }
+   g->pendingTimes = false;
+}
+int ldb_gpu_graph_begin(LdbContext* ctx, LdbError* err) {
+   return guarded(err, [&] {
+      if (!ctx) fail(LDB_ERR_INVALID, "null context");
+      if (ctx->capturing) fail(LDB_ERR_INVALID, "a capture is already in progress");
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      ctx->syncStream(ctx->compute);
+      auto* g = new LdbGraph;
+      g->ctx = ctx;
+      cudaError_t e = cudaStreamBeginCapture(ctx->compute, cudaStreamCaptureModeRelaxed);
+      if (e != cudaSuccess) {
+         delete g;
+         LDB_CUDA(e);
+      }
+      ctx->capturing = g;
+   });
+}
+int ldb_gpu_graph_end(LdbContext* ctx, LdbGraph** out, LdbError* err) {
+   return guarded(err, [&] {
+      if (!ctx || !out || !ctx->capturing) fail(LDB_ERR_INVALID, "no capture in progress");
+      LdbGraph* g = ctx->capturing;
+      ctx->capturing = nullptr;
+      cudaError_t e = cudaStreamEndCapture(ctx->compute, &g->graph);
+      if (e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+      if (e != cudaSuccess) {
+         if (g->graph) cudaGraphDestroy(g->graph);
+         delete g;
+         LDB_CUDA(e);
+      }
+      ctx->graphs.push_back(g);
+      *out = g;
+   });
+}
+int ldb_gpu_graph_launch(LdbGraph* g, LdbError* err) {
+   return guarded(err, [&] {
+      if (!g || !g->exec) fail(LDB_ERR_INVALID, "null graph");
+      LdbContext* ctx = g->ctx;
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      if (ctx->timing) harvestGraphTimes(g);
+      LDB_CUDA(cudaGraphLaunch(g->exec, ctx->compute));
+      ctx->launches += g->kernelsPerLaunch;
+      g->pendingTimes = ctx->timing && !g->timers.empty();
+      for (auto& f : g->onLaunch) f();
+   });
+}
+void ldb_gpu_graph_destroy(LdbGraph* g) {
+   if (!g) return;
+   cudaSetDevice(g->ctx->device);
+   cudaStreamSynchronize(g->ctx->compute);
+   for (auto& t : g->timers) {
+      cudaEventDestroy(t.a);
+      cudaEventDestroy(t.b);
+   }
+   auto& gs = g->ctx->graphs;
+   gs.erase(std::remove(gs.begin(), gs.end(), g), gs.end());
+   if (g->exec) cudaGraphExecDestroy(g->exec);
+   if (g->graph) cudaGraphDestroy(g->graph);
+   delete g;
 }
 
 // ------------------------------------------------------------------------------------------------ tables
@@ -662,6 +757,33 @@ int ldb_gpu_join_table_create(LdbContext* ctx, int64_t expected_rows, int32_t un
       }
       s->nSide = n_side;
       s->nAggs = n_aggs;
+      *out = s;
+   });
+}
+int ldb_gpu_join_table_create_shared_bloom(LdbContext* ctx, int64_t expected_rows, int32_t unique_keys, LdbComm* comm, int64_t bloom_offset, int64_t* bloom_bytes, LdbState** out, LdbError* err) {
+   return guarded(err, [&] {
+      const uint64_t cap = nextPow2((uint64_t) std::max<int64_t>(expected_rows, 2048) * 2); // >= 4096 slots: always has a filter
+      const uint64_t words = cap / 4;
+      if (bloom_bytes) *bloom_bytes = (int64_t) words * 4;
+      if (!out) return; // size query
+      if (!ctx || !comm) fail(LDB_ERR_INVALID, "null argument");
+      if (comm->ctx != ctx) fail(LDB_ERR_INVALID, "comm belongs to another context");
+      if (bloom_offset < 0 || bloom_offset % 16 || (size_t) bloom_offset + words * 4 > comm->userBytes) fail(LDB_ERR_CAPACITY, "Bloom filter outside the comm's user heap (create the comm with a larger heap)");
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      auto* s = new LdbState;
+      s->ctx = ctx;
+      s->kind = LDB_STATE_JOIN_TABLE;
+      ctx->states.push_back(s);
+      auto& j = s->join;
+      j.mask = cap - 1;
+      j.unique = unique_keys & LDB_JOIN_UNIQUE;
+      j.stride = 8;
+      j.base = (uint8_t*) devAlloc(s, cap * 8, 0xff);
+      j.count = (unsigned long long*) devAlloc(s, 8, 0);
+      j.error = (int32_t*) devAlloc(s, 4, 0);
+      j.bloom = (uint32_t*) (comm->heap + kUserOff + bloom_offset); // owned by the comm's heap, not by the state
+      j.bloomMask = (uint32_t) (words - 1);
+      LDB_CUDA(cudaMemsetAsync(j.bloom, 0, words * 4, ctx->compute));
       *out = s;
    });
 }
@@ -1224,6 +1346,52 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                p.groups = sink->group;
                waitBatch(ctx, b);
                ctx->launch("join_star_probe_groupby", [&] { launchScanStarProbeGroupBy(p, ctx->smCount, ctx->compute); });
+            }
+            break;
+         }
+         case LDB_PIPE_SCAN_PARTITION_SEND: {
+            LdbComm* c = d->comm;
+            if (!c || c->ctx != ctx) fail(LDB_ERR_INVALID, "partition-send needs a comm of this context");
+            if (!c->connected && c->world > 1) fail(LDB_ERR_INVALID, "comm is not connected to its peers yet");
+            if (d->n_out_cols < 2 || d->n_out_cols > 4) fail(LDB_ERR_INVALID, "partition-send ships {key, second[, decimal[, decimal]]}");
+            if (d->n_probes < 0 || d->n_probes > 1) fail(LDB_ERR_UNSUPPORTED, "partition-send pipelines take at most one probe");
+            LdbState* probe = d->n_probes ? wantSingleKeyTable(d->probe_states[0], "probe") : nullptr;
+            SendParams base{};
+            base.hasProbe = probe ? 1 : 0;
+            base.bloomOnly = d->probe_bloom_only ? 1 : 0;
+            if (probe) base.probeKeyStage = sp.add(t, R.col(d->probe_key_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key"));
+            base.keyStage = sp.add(t, R.col(d->out_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "partition key"));
+            if (d->out_columns[1] && std::string(d->out_columns[1]) == "$payload") {
+               if (!probe || d->probe_bloom_only) fail(LDB_ERR_INVALID, "$payload needs a full probe");
+               base.secondStage = -1;
+            } else {
+               base.secondStage = sp.add(t, R.col(d->out_columns[1], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "second tuple column"));
+            }
+            base.nDec = d->n_out_cols - 2;
+            for (int k = 0; k < base.nDec; k++) {
+               int col = R.col(d->out_columns[2 + k], {LDB_DECIMAL128}, "decimal tuple column");
+               if (t->columns[col].precision >= 19) fail(LDB_ERR_UNSUPPORTED, "shipped decimals must have precision < 19");
+               base.decStage[k] = sp.add(t, col);
+            }
+            const int64_t tupleBytes = 8 * (1 + base.nDec);
+            const int64_t region = (int64_t) c->world * d->send_capacity * tupleBytes;
+            if (d->send_capacity <= 0 || d->send_offset < 0 || d->send_offset % 16 || (size_t) (d->send_offset + region) > c->userBytes ||
+                d->send_cursors_offset < 0 || d->send_cursors_offset % 16 || (size_t) d->send_cursors_offset + 16 * 8 > c->userBytes)
+               fail(LDB_ERR_CAPACITY, "receive region / cursors outside the comm's user heap (create the comm with a larger heap)");
+            base.world = c->world;
+            for (int r = 0; r < c->world; r++) base.dest[r] = c->peerHeap[r] + kUserOff + d->send_offset + (int64_t) c->rank * d->send_capacity * tupleBytes;
+            base.capacity = d->send_capacity;
+            base.cursors = (unsigned long long*) (c->heap + kUserOff + d->send_cursors_offset);
+            base.error = (int32_t*) (base.cursors + 8);
+            for (auto& b : t->batches) {
+               if (b.nRows == 0) continue;
+               SendParams p = base;
+               p.src.nRows = b.nRows;
+               bindFilters(fp, b, p.src.filters);
+               sp.bind(t, b, p.src.cols, kRowsPerThreadProbe);
+               if (probe) p.probe = probe->join;
+               waitBatch(ctx, b);
+               ctx->launch("partition_send", [&] { launchScanPartitionSend(p, ctx->smCount, ctx->compute); });
             }
             break;
          }

@@ -371,6 +371,187 @@ int ldb_tpch_q5(LdbContext* ctx, const LdbTpchTables* t, const char* regionName,
    });
 }
 
+// ------------------------------------------------------------------------------------------------ Q5, repartitioned across GPUs
+namespace {
+struct Q5Layout {
+   int64_t capOrd, capLi, bloomBytes;
+   int64_t cursorsA, cursorsB, countsA, countsB, ordRecv, liRecv, bloom, total;
+   int64_t expectedOrders;
+};
+Q5Layout q5Layout(int64_t nOrdTotal, int64_t nLiTotal, int world) {
+   Q5Layout l{};
+   const int64_t w2 = (int64_t) world * world;
+   // qualifying orders ≈ 3 % of orders (one year of seven, one region of five), lineitem survivors of the Bloom semi-join ≈ 4-5 %:
+   // every (source, destination) sub-region gets twice its expected share
+   l.capOrd = nOrdTotal / 16 / w2 + 8192;
+   l.capLi = nLiTotal / 10 / w2 + 8192;
+   l.expectedOrders = nOrdTotal / 24 + 4096;
+   ldb_gpu_join_table_create_shared_bloom(nullptr, l.expectedOrders, LDB_JOIN_UNIQUE, nullptr, 0, &l.bloomBytes, nullptr, nullptr);
+   int64_t off = 0;
+   auto take = [&](int64_t bytes) {
+      int64_t at = off;
+      off = (off + bytes + 255) & ~int64_t(255);
+      return at;
+   };
+   l.cursorsA = take(16 * 8);
+   l.cursorsB = take(16 * 8);
+   l.countsA = take(8 * 8);
+   l.countsB = take(8 * 8);
+   l.ordRecv = take((int64_t) world * l.capOrd * 8);
+   l.liRecv = take((int64_t) world * l.capLi * 24);
+   l.bloom = take(l.bloomBytes);
+   l.total = off;
+   return l;
+}
+} // namespace
+int64_t ldb_tpch_q5_repartitioned_heap_bytes(int64_t n_orders_total, int64_t n_lineitem_total, int32_t world) { return q5Layout(n_orders_total, n_lineitem_total, world).total; }
+int ldb_tpch_q5_repartitioned(LdbContext* ctx, const LdbTpchTables* t, LdbComm* comm, const char* regionName, const char* dateGe, const char* dateLt, int64_t nOrdTotal, int64_t nLiTotal,
+                              LdbQ5Row* rows, int32_t* nRows, LdbQ5ShuffleStats* stats, LdbError* err) {
+   return guarded(err, [&] {
+      LdbError e;
+      StateGuard g;
+      if (!comm) throw std::runtime_error("repartitioned Q5 needs a comm");
+      const int world = ldb_gpu_comm_world(comm);
+      const Q5Layout L = q5Layout(nOrdTotal, nLiTotal, world);
+      int64_t heapBytes = 0;
+      ldb_gpu_comm_heap(comm, &heapBytes);
+      if (heapBytes < L.total) {
+         LdbError he{LDB_ERR_CAPACITY, ""};
+         snprintf(he.message, sizeof(he.message), "comm user heap holds %lld bytes, repartitioned Q5 needs %lld (ldb_tpch_q5_repartitioned_heap_bytes)", (long long) heapBytes, (long long) L.total);
+         throw PlanError(he);
+      }
+      int64_t nCust = ldb_gpu_table_num_rows(t->customer), nSupp = ldb_gpu_table_num_rows(t->supplier);
+      check(ldb_gpu_comm_heap_zero(comm, 0, L.ordRecv, &e), e); // cursors + counts
+      // replicated build sides (as in ldb_tpch_q5)
+      LdbFilterDesc fr[1] = {strFilter("r_name", LDB_EQ, regionName)};
+      LdbPipelineDesc dr{};
+      dr.kind = LDB_PIPE_SCAN_BUILD;
+      dr.source = t->region;
+      dr.n_filters = 1;
+      dr.filters = fr;
+      dr.build_key_column = "r_regionkey";
+      LdbState* region = buildJoin(ctx, g, dr, 16, 1, 0, 0);
+      LdbPipelineDesc dn{};
+      dn.kind = LDB_PIPE_SCAN_BUILD;
+      dn.source = t->nation;
+      dn.n_probes = 1;
+      dn.probe_states[0] = region;
+      dn.probe_key_columns[0] = "n_regionkey";
+      dn.build_key_column = "n_nationkey";
+      dn.build_payload_column = "n_nationkey";
+      LdbState* nation = buildJoin(ctx, g, dn, 64, 1, 0, 0);
+      LdbPipelineDesc dc{};
+      dc.kind = LDB_PIPE_SCAN_BUILD;
+      dc.source = t->customer;
+      dc.n_probes = 1;
+      dc.probe_states[0] = nation;
+      dc.probe_key_columns[0] = "c_nationkey";
+      dc.build_key_column = "c_custkey";
+      dc.build_payload_column = "c_nationkey";
+      LdbState* cust = buildJoin(ctx, g, dc, nCust / 4 + 1024, 1, 0, 0);
+      LdbPipelineDesc ds{};
+      ds.kind = LDB_PIPE_SCAN_BUILD;
+      ds.source = t->supplier;
+      ds.n_probes = 1;
+      ds.probe_states[0] = nation;
+      ds.probe_key_columns[0] = "s_nationkey";
+      ds.build_key_column = "s_suppkey";
+      ds.build_payload_column = "s_nationkey";
+      LdbState* supp = buildJoin(ctx, g, ds, nSupp / 4 + 1024, 1, 0, 0);
+      // this rank's hash partition of orders ⋈ customer, sized for the GLOBAL key set so that every rank's Bloom filter has the same
+      // geometry (their OR keeps the false-positive rate of a single-GPU build)
+      LdbState* ordp = nullptr;
+      check(ldb_gpu_join_table_create_shared_bloom(ctx, L.expectedOrders, LDB_JOIN_UNIQUE, comm, L.bloom, nullptr, &ordp, &e), e);
+      g.own(ordp);
+      check(ldb_gpu_comm_barrier(comm, &e), e); // every rank cleared its cursors, counts and filter
+      // ---- orders shard → {o_orderkey, c_nationkey} tuples → owner rank (K10: partition fused with the NVLink store)
+      LdbFilterDesc fo[2] = {strFilter("o_orderdate", LDB_GTE, dateGe), strFilter("o_orderdate", LDB_LT, dateLt)};
+      LdbPipelineDesc so{};
+      so.kind = LDB_PIPE_SCAN_PARTITION_SEND;
+      so.source = t->orders;
+      so.n_filters = 2;
+      so.filters = fo;
+      so.n_probes = 1;
+      so.probe_states[0] = cust;
+      so.probe_key_columns[0] = "o_custkey";
+      so.n_out_cols = 2;
+      so.out_columns[0] = "o_orderkey";
+      so.out_columns[1] = "$payload";
+      so.comm = comm;
+      so.send_offset = L.ordRecv;
+      so.send_capacity = L.capOrd;
+      so.send_cursors_offset = L.cursorsA;
+      check(ldb_gpu_run_pipeline(ctx, &so, &e), e);
+      check(ldb_gpu_comm_publish_counts(comm, L.cursorsA, L.countsA, &e), e);
+      check(ldb_gpu_comm_barrier(comm, &e), e); // all tuples and counts landed
+      check(ldb_gpu_join_table_insert_received(ordp, comm, L.ordRecv, L.capOrd, L.countsA, &e), e);
+      check(ldb_gpu_comm_barrier(comm, &e), e); // every partition built
+      check(ldb_gpu_comm_or_reduce(comm, L.bloom, L.bloomBytes, &e), e);
+      check(ldb_gpu_comm_barrier(comm, &e), e); // nobody still reads a filter that is about to be probed / reused
+      // ---- lineitem shard → Bloom semi-join → {l_orderkey, l_suppkey, l_extendedprice, l_discount} tuples → owner rank
+      LdbPipelineDesc sl{};
+      sl.kind = LDB_PIPE_SCAN_PARTITION_SEND;
+      sl.source = t->lineitem;
+      sl.n_probes = 1;
+      sl.probe_states[0] = ordp;
+      sl.probe_key_columns[0] = "l_orderkey";
+      sl.probe_bloom_only = 1;
+      sl.n_out_cols = 4;
+      sl.out_columns[0] = "l_orderkey";
+      sl.out_columns[1] = "l_suppkey";
+      sl.out_columns[2] = "l_extendedprice";
+      sl.out_columns[3] = "l_discount";
+      sl.comm = comm;
+      sl.send_offset = L.liRecv;
+      sl.send_capacity = L.capLi;
+      sl.send_cursors_offset = L.cursorsB;
+      check(ldb_gpu_run_pipeline(ctx, &sl, &e), e);
+      check(ldb_gpu_comm_publish_counts(comm, L.cursorsB, L.countsB, &e), e);
+      check(ldb_gpu_comm_barrier(comm, &e), e);
+      // ---- probes + aggregation where the partition lives, then the all-merge of the 5-group tables
+      LdbState* groups = nullptr;
+      check(ldb_gpu_groupby_create(ctx, 1, 1, 64, &groups, &e), e);
+      g.own(groups);
+      check(ldb_gpu_probe_received_groupby(ordp, supp, groups, comm, L.liRecv, L.capLi, L.countsB, 2, &e), e);
+      check(ldb_gpu_groupby_allmerge(groups, comm, &e), e);
+      // ---- the only host synchronisation of the data path: result + bookkeeping read-back
+      std::vector<LdbGroupRow> gr(64);
+      int32_t n = 0;
+      check(ldb_gpu_groupby_read(groups, gr.data(), 64, &n, &e), e);
+      uint64_t hdr[48]; // cursorsA[16] | cursorsB[16] | countsA[8] | countsB[8]
+      check(ldb_gpu_comm_heap_read(comm, L.cursorsA, 16 * 8, hdr, &e), e);
+      check(ldb_gpu_comm_heap_read(comm, L.cursorsB, 16 * 8, hdr + 16, &e), e);
+      check(ldb_gpu_comm_heap_read(comm, L.countsA, 8 * 8, hdr + 32, &e), e);
+      check(ldb_gpu_comm_heap_read(comm, L.countsB, 8 * 8, hdr + 40, &e), e);
+      check(ldb_gpu_comm_check(comm, &e), e);
+      if ((uint32_t) hdr[8] || (uint32_t) hdr[16 + 8]) {
+         LdbError ce{LDB_ERR_CAPACITY, "a repartition receive sub-region overflowed (skewed partitions): raise the comm heap / capacities"};
+         throw PlanError(ce);
+      }
+      int64_t cnt = 0;
+      check(ldb_gpu_join_table_count(ordp, &cnt, &e), e); // surfaces table-full / duplicate-key errors of the partition build
+      if (stats) {
+         *stats = LdbQ5ShuffleStats{};
+         for (int r = 0; r < world; r++) {
+            stats->orders_tuples_sent += (int64_t) hdr[r];
+            stats->lineitem_tuples_sent += (int64_t) hdr[16 + r];
+            stats->orders_tuples_received += (int64_t) hdr[32 + r];
+            stats->lineitem_tuples_received += (int64_t) hdr[40 + r];
+         }
+         stats->shuffle_bytes_out = stats->orders_tuples_sent * 8 + stats->lineitem_tuples_sent * 24;
+         stats->heap_bytes = L.total;
+      }
+      std::vector<LdbQ5Row> out;
+      for (int i = 0; i < n; i++) out.push_back(LdbQ5Row{gr[i].keys[0], 0, gr[i].aggs[0]});
+      std::sort(out.begin(), out.end(), [](const LdbQ5Row& a, const LdbQ5Row& b) {
+         i128 x = toI128(a.revenue), y = toI128(b.revenue);
+         return x != y ? x > y : a.n_nationkey < b.n_nationkey;
+      });
+      for (int i = 0; i < (int) out.size() && i < 25; i++) rows[i] = out[i];
+      *nRows = (int32_t) std::min<size_t>(out.size(), 25);
+   });
+}
+
 // ------------------------------------------------------------------------------------------------ Q9
 // part(p_name like '%X%') → partsupp ⋈ part keyed (ps_partkey, ps_suppkey) → supplier, orders(→ year) → lineitem star probe.
 // p_partkey = l_partkey follows from ps_partkey = l_partkey and p_partkey = ps_partkey (the partsupp table only holds

@@ -190,6 +190,22 @@ def q9_sharded(ctx, tpch, world: int, rank: int, bufs: dict, name_contains: str 
 
 
 # ------------------------------------------------------------------------------------------------ Q5 with repartition
+def q5_heap_bytes(ctx, n_orders_total: int, n_lineitem_total: int, world: int) -> int:
+    return int(ctx.L.ldb_tpch_q5_repartitioned_heap_bytes(int(n_orders_total), int(n_lineitem_total), world))
+
+
+def q5_repartitioned_peer(ctx, tpch, comm: "Comm", n_orders_total: int, n_lineitem_total: int, region_name="ASIA", date_ge="1994-01-01", date_lt="1995-01-01"):
+    """The C++ driver (include/ldb_tpch.h ldb_tpch_q5_repartitioned): fused partition + NVLink peer stores, device-side barriers,
+    Bloom OR through peer loads, peer all-merge — no NCCL, no host synchronisation inside the data path.  Returns (rows, stats)."""
+    from . import capi
+    rows, n, st, e = (capi.Q5Row * 25)(), C.c_int32(), capi.Q5ShuffleStats(), capi.Error()
+    capi.check(ctx.L.ldb_tpch_q5_repartitioned(ctx.h, C.byref(tpch.t), comm.h, region_name.encode(), date_ge.encode(), date_lt.encode(), int(n_orders_total), int(n_lineitem_total),
+                                               rows, C.byref(n), C.byref(st), C.byref(e)), e)
+    out = [{"n_name": tpch.nation_names[r.n_nationkey], "revenue": r.revenue.value()} for r in rows[: n.value]]
+    out.sort(key=lambda r: (-r["revenue"], r["n_name"]))
+    return out, {k: int(getattr(st, k)) for k, _ in capi.Q5ShuffleStats._fields_}
+
+
 def _all_to_all(cols, send_offsets, world, dev):
     """Exchange per-destination contiguous blocks (K6 output) of several columns; returns received columns + row count."""
     import torch

@@ -66,6 +66,16 @@ class Context:
         check(self.L.ldb_gpu_kernel_time(self.h, family.encode(), C.byref(ms), C.byref(n), C.byref(e)), e)
         return ms.value, n.value
 
+    # ------------------------------------------------------------------ captured queries (CUDA graphs)
+    def graph_begin(self):
+        e = Error()
+        check(self.L.ldb_gpu_graph_begin(self.h, C.byref(e)), e)
+
+    def graph_end(self) -> "Graph":
+        g, e = C.c_void_p(), Error()
+        check(self.L.ldb_gpu_graph_end(self.h, C.byref(g), C.byref(e)), e)
+        return Graph(self, g)
+
     # ------------------------------------------------------------------ tables
     def table(self, name: str, columns: List[datagen.ColumnSpec]) -> "Table":
         return Table(self, name, columns)
@@ -87,6 +97,22 @@ class Context:
         e = Error()
         check(self.L.ldb_gpu_hash_i64(self.h, a.ctypes.data, bp, a.shape[0], out.ctypes.data, C.byref(e)), e)
         return out
+
+
+class Graph:
+    """A captured query: launch() replays every kernel / memset / peer collective recorded between graph_begin and graph_end."""
+
+    def __init__(self, ctx: Context, h):
+        self.ctx, self.h = ctx, h
+
+    def launch(self):
+        e = Error()
+        check(self.ctx.L.ldb_gpu_graph_launch(self.h, C.byref(e)), e)
+
+    def destroy(self):
+        if self.h:
+            self.ctx.L.ldb_gpu_graph_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 class Table:

@@ -167,6 +167,114 @@ def test_peer_allmerge_protocol_on_one_device(oracle):
             c.close()
 
 
+def test_captured_query_replays_bit_identically(gpu_ctx, oracle):
+    """ldb_gpu_graph_*: Q1 captured once (state init + pipeline) and replayed; every replay re-initialises the state and gives
+    the oracle's rows; the per-kernel timers keep working through the graph's external event nodes."""
+    from lingodb_b200 import devgen, runtime
+    s = datagen.scale(0.05, seed=23)
+    cols = ["l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus", "l_shipdate"]
+    want = oracle.q1(oracle.table(datagen.lineitem(s, cols)))[0]
+    tp = runtime.Tpch(gpu_ctx, {"lineitem": devgen.lineitem(gpu_ctx, s, cols)})
+    assert tp.q1() == want  # eager first (warms the allocation pool)
+    gpu_ctx.graph_begin()
+    st = tp.q1_partial()
+    g = gpu_ctx.graph_end()
+    gpu_ctx.kernel_time_reset(True)
+    for _ in range(3):
+        g.launch()
+        assert tp.q1_finish(st) == want
+    ms, n = gpu_ctx.kernel_time("scan_groupby")
+    gpu_ctx.kernel_time_reset(False)
+    assert n == 3 and ms > 0
+    g.destroy()
+    runtime.state_destroy(gpu_ctx, st)
+
+
+def test_captured_query_with_peer_allmerge(oracle):
+    """The all-merge kernel reads its epoch from device memory, so a captured (scan + all-merge) query replays correctly on
+    every rank: 2 ranks = 2 contexts of this process on device 0."""
+    from lingodb_b200 import parallel, runtime
+    world = 2
+    s = datagen.scale(0.05, seed=29)
+    cols = ["l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus", "l_shipdate"]
+    want = oracle.q1(oracle.table(datagen.lineitem(s, cols)))[0]
+    ctxs = [runtime.Context(0) for _ in range(world)]
+    try:
+        comms = parallel.Comm.local_group(ctxs)
+        tps = [runtime.Tpch(c, _shard_tables(c, s, cols, r, world)) for r, c in enumerate(ctxs)]
+        graphs, states = [], []
+        for c, cm, tp in zip(ctxs, comms, tps):
+            tp.q1()  # warm the pools before capturing
+            c.graph_begin()
+            st = tp.q1_partial()
+            cm.allmerge(st)
+            graphs.append(c.graph_end())
+            states.append(st)
+        for _ in range(3):
+            for g in graphs:
+                g.launch()
+            for tp, st in zip(tps, states):
+                assert tp.q1_finish(st) == want
+        for cm in comms:
+            cm.barrier()  # eager collectives still line up with the replayed ones
+        for cm in comms:
+            cm.check()
+        for g, c, st in zip(graphs, ctxs, states):
+            g.destroy()
+            runtime.state_destroy(c, st)
+        for cm in comms:
+            cm.close()
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_q5_repartitioned_peer_stores_match_the_oracle(oracle, world):
+    """ldb_tpch_q5_repartitioned: fused partition + peer store, device barriers, Bloom OR by peer loads, all-merge — `world` ranks
+    as contexts of this process on device 0, one host thread per rank (the drivers block on their peers)."""
+    import threading
+    from lingodb_b200 import devgen, parallel, runtime
+    s = datagen.scale(0.2, seed=31)
+    host = datagen.tpch(0.2, seed=31)
+    oh = {k: oracle.table(v) for k, v in host.items()}
+    want = oracle.q5(oh["customer"], oh["orders"], oh["lineitem"], oh["supplier"], oh["nation"], oh["region"])[0]
+    cols = ["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount"]
+    ctxs = [runtime.Context(0) for _ in range(world)]
+    try:
+        heap = parallel.q5_heap_bytes(ctxs[0], s.n_orders, s.n_lineitem, world)
+        comms = parallel.Comm.local_group(ctxs, user_bytes=heap)
+        tps = []
+        for r, c in enumerate(ctxs):
+            o_lo, o_hi, r_lo, r_hi = parallel.order_range(s, r, world)
+            # lineitem rows of OTHER orders than this rank's order shard: the join is not co-partitioned, the shuffle has to do it
+            rr = (r + 1) % world
+            _, _, l_lo, l_hi = parallel.order_range(s, rr, world)
+            tps.append(runtime.Tpch(c, {"lineitem": devgen.lineitem(c, s, cols, row_begin=l_lo, n_rows=l_hi - l_lo), "orders": devgen.orders(c, s, row_begin=o_lo, n_rows=o_hi - o_lo),
+                                        "customer": devgen.customer(c, s), "supplier": devgen.supplier(c, s), **devgen.small_tables(c)}))
+        for it in range(2):
+            res, errs = [None] * world, []
+
+            def run(r):
+                try:
+                    res[r] = parallel.q5_repartitioned_peer(ctxs[r], tps[r], comms[r], s.n_orders, s.n_lineitem)
+                except Exception as ex:  # noqa: BLE001
+                    errs.append((r, ex))
+            ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+            [t.start() for t in ts]
+            [t.join() for t in ts]
+            assert not errs, errs
+            for r in range(world):
+                assert res[r][0] == want, f"rank {r} iteration {it}"
+            assert sum(res[r][1]["orders_tuples_sent"] for r in range(world)) == sum(res[r][1]["orders_tuples_received"] for r in range(world)) > 0
+            assert sum(res[r][1]["lineitem_tuples_sent"] for r in range(world)) == sum(res[r][1]["lineitem_tuples_received"] for r in range(world)) > 0
+        for cm in comms:
+            cm.close()
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def test_peer_collectives_across_processes_and_gpus():
     """world = 2 processes on 2 GPUs (CUDA IPC + NVLink P2P), when the box has them: tools/peer_selftest.py checks Q1/Q9
     against the oracle on every rank and exits non-zero on any mismatch."""
