@@ -255,6 +255,16 @@ int ldb_gpu_comm_create(LdbContext* ctx, int32_t rank, int32_t world, int64_t us
       ctx->syncStream(ctx->compute);
       c->peerHeap[rank] = c->heap;
       if (const char* e = getenv("LDB_PEER_TIMEOUT_MS")) c->timeoutNs = (unsigned long long) std::max(1, atoi(e)) * 1000000ull;
+      // CUDA loads kernels lazily, and loading one may have to wait for running kernels: a collective kernel that spins on a peer
+      // while the next launch (of this or another rank in the same process) is still being loaded would stall until the
+      // timeout — so every collective kernel is loaded now
+      cudaFuncAttributes fa;
+      LDB_CUDA(cudaFuncGetAttributes(&fa, peerBarrierKernel));
+      LDB_CUDA(cudaFuncGetAttributes(&fa, peerBumpKernel));
+      LDB_CUDA(cudaFuncGetAttributes(&fa, peerAllGatherKernel));
+      LDB_CUDA(cudaFuncGetAttributes(&fa, peerGroupAllMergeKernel));
+      LDB_CUDA(cudaFuncGetAttributes(&fa, peerOrReduceKernel));
+      LDB_CUDA(cudaFuncGetAttributes(&fa, peerPublishCountsKernel));
       cudaIpcMemHandle_t h;
       LDB_CUDA(cudaIpcGetMemHandle(&h, c->heap));
       static_assert(sizeof(h) == LDB_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
@@ -366,7 +376,7 @@ int ldb_gpu_groupby_allmerge(LdbState* s, LdbComm* c, LdbError* err) {
       wantConnected(c);
       if (s->ctx != c->ctx) failPeer(LDB_ERR_INVALID, "state and comm belong to different contexts");
       if (c->world == 1) return;
-      const size_t image = groupImageBytes(s->group.capacity);
+      const size_t image = (groupImageBytes(s->group.capacity) + 15) & ~size_t(15); // the table allocation carries 16 spare bytes (error word)
       if (image > kSlotBytes) failPeer(LDB_ERR_UNSUPPORTED, "group table image larger than a mailbox slot (capacity <= 1024 groups)");
       LdbContext* ctx = c->ctx;
       LDB_CUDA(cudaSetDevice(ctx->device));

@@ -206,6 +206,14 @@ cudaEvent_t LdbContext::getEvent() {
 void LdbContext::launchCaptured(const char* family, const std::function<void()>& fn) {
    LdbGraph* g = capturing;
    g->kernelsPerLaunch++;
+   static const bool timers = [] {
+      const char* e = getenv("LDB_GRAPH_TIMERS");
+      return !(e && e[0] == '0');
+   }();
+   if (!timers) { // replay-latency experiments: no per-kernel event nodes in the graph
+      fn();
+      return;
+   }
    cudaEvent_t a = nullptr, b = nullptr;
    LDB_CUDA(cudaEventCreate(&a));
    LDB_CUDA(cudaEventCreate(&b));

@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# a dead peer in a collective test should fail the test in seconds, not after the production timeout
+os.environ.setdefault("LDB_PEER_TIMEOUT_MS", "5000")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

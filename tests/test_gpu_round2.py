@@ -242,6 +242,8 @@ def test_q5_repartitioned_peer_stores_match_the_oracle(oracle, world):
     cols = ["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount"]
     ctxs = [runtime.Context(0) for _ in range(world)]
     try:
+        # (ranks of one process share the CUDA context: the world=1 case, which runs first, has loaded every kernel of the flow —
+        #  with lazy loading one rank's first launch of a kernel would wait for another rank's spinning barrier kernel)
         heap = parallel.q5_heap_bytes(ctxs[0], s.n_orders, s.n_lineitem, world)
         comms = parallel.Comm.local_group(ctxs, user_bytes=heap)
         tps = []
@@ -259,11 +261,11 @@ def test_q5_repartitioned_peer_stores_match_the_oracle(oracle, world):
                 try:
                     res[r] = parallel.q5_repartitioned_peer(ctxs[r], tps[r], comms[r], s.n_orders, s.n_lineitem)
                 except Exception as ex:  # noqa: BLE001
-                    errs.append((r, ex))
+                    errs.append((r, str(ex)))
             ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
             [t.start() for t in ts]
             [t.join() for t in ts]
-            assert not errs, errs
+            assert not errs, "\n".join(f"rank {r}: {m}" for r, m in errs)
             for r in range(world):
                 assert res[r][0] == want, f"rank {r} iteration {it}"
             assert sum(res[r][1]["orders_tuples_sent"] for r in range(world)) == sum(res[r][1]["orders_tuples_received"] for r in range(world)) > 0
