@@ -84,7 +84,9 @@ typedef struct LdbArrayView {
    const void** buffers; /* [0] validity (may be NULL), [1] values or utf8 offsets, [2] utf8 bytes */
    const struct LdbArrayView** children;
 } LdbArrayView;
-enum LdbPhysType { LDB_INT32 = 0, LDB_INT64 = 1, LDB_DATE32 = 2, LDB_DECIMAL128 = 3, LDB_FSB4 = 4, LDB_UTF8 = 5 };
+enum LdbPhysType { LDB_INT32 = 0, LDB_INT64 = 1, LDB_DATE32 = 2, LDB_DECIMAL128 = 3, LDB_FSB4 = 4, LDB_UTF8 = 5,
+                   /* read by the program pipeline (ldb_gpu_run_program) only */
+                   LDB_INT8 = 6, LDB_INT16 = 7, LDB_FLOAT32 = 8, LDB_FLOAT64 = 9 };
 typedef struct LdbColumnSchema {
    const char* name;
    int32_t type; /* LdbPhysType: physical Arrow type as in LingoDBTable.cpp:122-195 */
@@ -120,7 +122,7 @@ void ldb_gpu_table_destroy(LdbTable* t);
  *                         lanes it is the group-join map of SubOpToControlFlow.cpp:2730-2839.
  * The memory image differs from the CPU objects (open addressing, 32-bit payloads, no tagged
  * pointers): the contract is the same MULTISET of results, not the same bytes. */
-enum LdbStateKind { LDB_STATE_SIMPLE = 1, LDB_STATE_GROUPBY = 2, LDB_STATE_JOIN_TABLE = 3 };
+enum LdbStateKind { LDB_STATE_SIMPLE = 1, LDB_STATE_GROUPBY = 2, LDB_STATE_JOIN_TABLE = 3, LDB_STATE_HASHAGG = 4 };
 typedef struct LdbState LdbState;
 typedef struct LdbI128 {
    uint64_t lo;
@@ -298,6 +300,96 @@ typedef struct LdbPipelineDesc {
    int64_t send_offset, send_capacity, send_cursors_offset;
 } LdbPipelineDesc;
 int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* desc, LdbError* err);
+
+/* ------------------------------------------------------------------------------------ program pipelines (generic)
+ * The hand-specialised pipelines above cover the TPC-H hot shapes at HBM speed.  Everything else a scan pipeline of the
+ * sub-operator dialect can contain runs through ONE kernel that interprets a register program per row (csrc/program.cu):
+ *   expressions   db.add/sub/mul/div/cmp/and/or/not/between/case over int8..int64, date32, char(1), decimal(38), float/double
+ *                 (LowerToStd.cpp:612-700,851-910; decimal scales are the program writer's job, exactly as the lowering rescales)
+ *   nulls         every LOAD tests the column's validity bit (Restrictions.cpp:67-162, LowerToStd.cpp:111-209); SQL three-valued logic
+ *   strings       =, <>, <, <=, >, >= against constants, LIKE 'x%' / '%x' / '%x%' (VarLen32Filter, Restrictions.cpp:234-325)
+ *   joins         PROBE: key → payload of a join table, NULL when absent → semi / anti / mark / left-outer joins
+ *                 (RelAlgToSubOp.cpp:1129-1206,1340-1588) as a filter or a value
+ *   sinks         hash aggregation with up to 4 (nullable) int64 keys and SUM/COUNT/MIN/MAX/ANY over ANY number of groups
+ *                 (rt::PreAggregationHashtable::merge, PreAggregationHashtable.cpp:76-170; rt::Hashtable, Hashtable.cpp:10-150;
+ *                 subop.reduce, SubOpToControlFlow.cpp:3540-3769), a join-table build, or compacted output columns.
+ * It is slower than the specialised kernels (one thread per row, registers in local memory) — it is the catch-all. */
+enum LdbOp {
+   LDB_OP_LOAD = 1,    /* dst = columns[arg]                                  (NULL from the validity bit) */
+   LDB_OP_CONST = 2,   /* dst = consts[arg] */
+   LDB_OP_ADD = 3, LDB_OP_SUB = 4, LDB_OP_MUL = 5, /* wrapping i128 */
+   LDB_OP_DIV = 6,     /* truncating signed division; x / 0 = NULL */
+   LDB_OP_NEG = 7,
+   LDB_OP_CMP = 8,     /* dst = a <arg: LDB_EQ..LDB_GTE> b                    (integers, decimals at equal scale, dates, char(1)) */
+   LDB_OP_AND = 9, LDB_OP_OR = 10, LDB_OP_NOT = 11, /* three-valued */
+   LDB_OP_ISNULL = 12,
+   LDB_OP_SELECT = 13, /* dst = regs[arg] is true ? a : b                     (CASE WHEN) */
+   LDB_OP_I2F = 14, LDB_OP_FADD = 15, LDB_OP_FSUB = 16, LDB_OP_FMUL = 17, LDB_OP_FDIV = 18,
+   LDB_OP_FCMP = 19,   /* like CMP on doubles */
+   LDB_OP_STRCMP = 20, /* dst = columns[a] <b: LDB_EQ..LDB_GTE> strings[arg] */
+   LDB_OP_STRLIKE = 21,/* dst = columns[a] LIKE strings[arg]; b = 0 'x%', 1 '%x', 2 '%x%' */
+   LDB_OP_YEAR = 22,   /* dst = extract(year from date32 a) */
+   LDB_OP_PROBE = 23,  /* dst = payload of int32 key a in tables[arg]; NULL when absent */
+   LDB_OP_STRKEY8 = 24 /* dst = first 8 bytes of columns[a], zero padded, big-endian (an order-preserving int64 group / sort key for short
+                          strings: char(n<=8), flags, codes; longer strings need a dictionary and are not keys here) */
+};
+enum LdbAggKind { LDB_AGG_SUM = 1, LDB_AGG_SUM_F64 = 2, LDB_AGG_COUNT = 3, LDB_AGG_COUNT_STAR = 4, LDB_AGG_MIN = 5, LDB_AGG_MAX = 6 /* 64-bit signed */,
+                  LDB_AGG_MIN_F64 = 7, LDB_AGG_MAX_F64 = 8, LDB_AGG_ANY = 9 };
+typedef struct LdbInstr {
+   uint8_t op, dst, a, b;
+   int32_t arg;
+} LdbInstr;
+#define LDB_PROG_MAX_KEYS 4
+typedef struct LdbProgAgg {
+   int32_t kind; /* LdbAggKind */
+   int32_t reg;
+} LdbProgAgg;
+enum LdbProgramSink { LDB_SINK_HASHAGG = 1, LDB_SINK_JOIN_BUILD = 2, LDB_SINK_MATERIALIZE = 3 };
+typedef struct LdbProgramDesc {
+   LdbTable* source;
+   int32_t n_columns;            /* <= 12 */
+   const char* const* columns;
+   int32_t n_instr;              /* <= 96, registers 0..23 */
+   const LdbInstr* instr;
+   int32_t n_consts;             /* <= 24 */
+   const LdbI128* consts;
+   int32_t n_strings;            /* <= 12, each <= 32 bytes */
+   const char* const* strings;
+   int32_t n_tables;             /* <= 4 join tables (single int32 key or direct-address) for LDB_OP_PROBE */
+   LdbState* const* tables;
+   int32_t filter_reg;           /* the row is kept when this register is TRUE (NULL is not true); -1 = keep all */
+   int32_t sink_kind;            /* LdbProgramSink */
+   LdbState* sink;               /* HASHAGG state | JOIN_TABLE; NULL for MATERIALIZE */
+   int32_t n_keys;
+   int32_t key_regs[LDB_PROG_MAX_KEYS];
+   int32_t n_aggs;
+   LdbProgAgg aggs[LDB_MAX_AGGS];
+   int32_t build_key_reg, build_payload_reg; /* JOIN_BUILD: payload_reg -1 = 0 */
+   /* MATERIALIZE: out_regs → a new DEVICE table (columns "c0".."cN": decimal128(38,0) cells = the raw i128 / double bits in the
+    * low 8 bytes, each with a validity byte); capacity = source rows */
+   int32_t n_out;
+   int32_t out_regs[LDB_MAX_AGGS];
+   LdbTable** out_table;
+} LdbProgramDesc;
+int ldb_gpu_run_program(LdbContext* ctx, const LdbProgramDesc* desc, LdbError* err);
+/* hash aggregation state sized for `expected_groups` (the directory holds 2x that; LDB_ERR_CAPACITY when it overflows) */
+int ldb_gpu_hashagg_create(LdbContext* ctx, int32_t n_keys, int32_t n_aggs, const LdbProgAgg* aggs, int64_t expected_groups, LdbState** out, LdbError* err);
+int ldb_gpu_hashagg_count(LdbState* s, int64_t* n_groups, LdbError* err);
+typedef struct LdbHashAggRow {
+   int64_t keys[LDB_PROG_MAX_KEYS];
+   uint32_t key_null_mask, agg_valid_mask; /* bit k: key k IS NULL / bit a: aggregate a is not NULL */
+   LdbI128 aggs[LDB_MAX_AGGS];             /* doubles: bits in .lo */
+} LdbHashAggRow;
+int ldb_gpu_hashagg_read(LdbState* s, LdbHashAggRow* rows, int64_t max_rows, int64_t* n_rows, LdbError* err);
+/* the groups as a DEVICE table for the next pipeline (HAVING, joins, top-k): columns k0..k3 (int64, nullable) and a0..a7
+ * (decimal128(38,0) raw i128 | float64, nullable) — the scan over the hash table that starts the reference's next pipeline */
+int ldb_gpu_hashagg_to_table(LdbState* s, const char* name, LdbTable** out, LdbError* err);
+/* ORDER BY <column> [DESC] LIMIT k over a DEVICE/staged table (GrowingBuffer::sort + Heap, GrowingBuffer.cpp:54-78): an LSD radix
+ * sort of (order-preserving 64-bit key, row id) on the device; returns the first `limit` row ids (ties keep row order: stable).
+ * column types: int32/date32/fsb4/int64/decimal(p<19). */
+int ldb_gpu_table_order_by(LdbTable* t, const char* column, int32_t descending, int64_t limit, int64_t* row_ids, int64_t* n_out, LdbError* err);
+/* read back `n` cells of a fixed-width column at the given row ids (result materialisation of small outputs) */
+int ldb_gpu_table_gather(LdbTable* t, const char* column, const int64_t* row_ids, int64_t n, void* host_dst /* n * cell bytes */, uint8_t* host_valid /* n, may be NULL */, LdbError* err);
 
 /* ------------------------------------------------------------------------------------ repartition (K6)
  * No reference counterpart (the reference is single-process; SURVEY §2 "Parallelism strategies").

@@ -10,7 +10,7 @@ from . import build as _build
 from .datagen import CustomerCols, GenScale, LineitemCols, OrdersCols, PartCols, PartsuppCols, SupplierCols
 
 LDB_OK, LDB_ERR_CUDA, LDB_ERR_UNSUPPORTED, LDB_ERR_INVALID, LDB_ERR_CAPACITY, LDB_ERR_NO_DEVICE = range(6)
-PHYS = {"int32": 0, "int64": 1, "date32": 2, "decimal128": 3, "fsb4": 4, "utf8": 5}
+PHYS = {"int32": 0, "int64": 1, "date32": 2, "decimal128": 3, "fsb4": 4, "utf8": 5, "int8": 6, "int16": 7, "float32": 8, "float64": 9}
 MEM_HOST, MEM_DEVICE = 0, 1
 OPS = {"=": 0, "!=": 1, "<": 2, "<=": 3, ">": 4, ">=": 5, "notnull": 6, "in": 7, "contains": 8}
 EXPR = {"col": 0, "mul": 1, "mul_1minus": 2, "mul_1minus_1plus": 3, "one": 4, "mul_1minus_minus_paymul": 5}
@@ -102,6 +102,27 @@ class Q5Row(C.Structure):
     _fields_ = [("n_nationkey", C.c_int32), ("pad", C.c_int32), ("revenue", I128)]
 
 
+class Instr(C.Structure):
+    _fields_ = [("op", C.c_uint8), ("dst", C.c_uint8), ("a", C.c_uint8), ("b", C.c_uint8), ("arg", C.c_int32)]
+
+
+class ProgAgg(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reg", C.c_int32)]
+
+
+class ProgramDesc(C.Structure):
+    _fields_ = [("source", C.c_void_p), ("n_columns", C.c_int32), ("columns", C.POINTER(C.c_char_p)), ("n_instr", C.c_int32), ("instr", C.POINTER(Instr)),
+                ("n_consts", C.c_int32), ("consts", C.POINTER(I128)), ("n_strings", C.c_int32), ("strings", C.POINTER(C.c_char_p)),
+                ("n_tables", C.c_int32), ("tables", C.POINTER(C.c_void_p)), ("filter_reg", C.c_int32), ("sink_kind", C.c_int32), ("sink", C.c_void_p),
+                ("n_keys", C.c_int32), ("key_regs", C.c_int32 * 4), ("n_aggs", C.c_int32), ("aggs", ProgAgg * MAX_AGGS),
+                ("build_key_reg", C.c_int32), ("build_payload_reg", C.c_int32), ("n_out", C.c_int32), ("out_regs", C.c_int32 * MAX_AGGS),
+                ("out_table", C.POINTER(C.c_void_p))]
+
+
+class HashAggRow(C.Structure):
+    _fields_ = [("keys", C.c_int64 * 4), ("key_null_mask", C.c_uint32), ("agg_valid_mask", C.c_uint32), ("aggs", I128 * MAX_AGGS)]
+
+
 class Q5ShuffleStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("orders_tuples_sent", "orders_tuples_received", "lineitem_tuples_sent", "lineitem_tuples_received", "shuffle_bytes_out", "heap_bytes")]
 
@@ -153,6 +174,13 @@ SIGNATURES = {
     "ldb_gpu_join_table_bloom": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64), _E]),
     "ldb_gpu_join_table_topk": (C.c_int, [_P, C.c_int32, C.POINTER(TopKRow), C.POINTER(C.c_int32), _E]),
     "ldb_gpu_run_pipeline": (C.c_int, [_P, C.POINTER(PipelineDesc), _E]),
+    "ldb_gpu_run_program": (C.c_int, [_P, C.POINTER(ProgramDesc), _E]),
+    "ldb_gpu_hashagg_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(ProgAgg), C.c_int64, C.POINTER(_P), _E]),
+    "ldb_gpu_hashagg_count": (C.c_int, [_P, C.POINTER(C.c_int64), _E]),
+    "ldb_gpu_hashagg_read": (C.c_int, [_P, C.POINTER(HashAggRow), C.c_int64, C.POINTER(C.c_int64), _E]),
+    "ldb_gpu_hashagg_to_table": (C.c_int, [_P, C.c_char_p, C.POINTER(_P), _E]),
+    "ldb_gpu_table_order_by": (C.c_int, [_P, C.c_char_p, C.c_int32, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _E]),
+    "ldb_gpu_table_gather": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64), C.c_int64, _P, _P, _E]),
     "ldb_gpu_partition_tuples": (C.c_int, [_P, _P, C.POINTER(_P), C.POINTER(C.c_int32), C.c_int32, C.c_int64, C.c_int32, _P, C.POINTER(_P), C.POINTER(C.c_int64), _E]),
     "ldb_gpu_join_table_insert": (C.c_int, [_P, _P, _P, _P, C.POINTER(_P), C.c_int64, _E]),
     "ldb_gpu_comm_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, C.POINTER(_P), _P, _E]),

@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/ldb_gpu.h"
 #include "kernels.h"
+#include "program.h"
 
 #include <cuda_runtime.h>
 #include <atomic>
@@ -157,6 +158,9 @@ struct LdbBatch {
    std::vector<const void*> data;  // per column: values / utf8 offsets (device)
    std::vector<const void*> bytes; // per column: utf8 bytes (device) or null
    std::vector<int32_t> elemBytes; // per column: bytes per value as staged (decimal128: 16, or 8 when narrowed)
+   std::vector<const void*> validity;      // per column: Arrow validity bitmap on the device (null = no nulls in this batch)
+   std::vector<int64_t> validityBitOffset; // bit index of row 0 inside the bitmap
+   std::vector<uint8_t*> validBytes;       // per column: one validity byte per row (tables this library produced), else empty / null
    std::vector<void*> owned;       // staging buffers to give back on clear
    cudaEvent_t ready = nullptr;    // H2D of this batch finished (null for borrowed device batches)
    std::shared_ptr<ldb::PackedBatch> packed; // columns staged through the compressed staging engine (host wait + worker events)
@@ -195,11 +199,16 @@ struct LdbGraph {
    std::vector<std::function<void()>> onLaunch; // host-side bookkeeping per replay (peer epoch mirrors)
 };
 
+// order the compute stream after the staging of one batch (runtime.cpp)
+void ldb_gpu_wait_batch_internal(LdbContext* ctx, const struct LdbBatch* b);
+
 struct LdbState {
    LdbContext* ctx;
    int32_t kind;
    ldb::GroupTableDev group{}; // SIMPLE / GROUPBY
    ldb::JoinTableDev join{};   // JOIN_TABLE
+   ldb::HashAggDev hashagg{};  // HASHAGG
+   int32_t aggKinds[ldb::kProgMaxAggs] = {};
    int32_t nSide = 0, nAggs = 0;
    uint32_t is64Mask = 0; // aggregates that are 64-bit sums (COL / ONE): normalised to a sign-extended i64 on read
    std::vector<void*> allocations;

@@ -56,8 +56,12 @@ size_t elemWidth(int type) {
       case LDB_DATE32:
       case LDB_FSB4:
       case LDB_UTF8: return 4; // utf8: offsets
-      case LDB_INT64: return 8;
+      case LDB_INT64:
+      case LDB_FLOAT64: return 8;
       case LDB_DECIMAL128: return 16;
+      case LDB_INT8: return 1;
+      case LDB_INT16: return 2;
+      case LDB_FLOAT32: return 4;
    }
    fail(LDB_ERR_INVALID, "unknown physical type");
 }
@@ -122,6 +126,8 @@ void waitBatch(LdbContext* ctx, const LdbBatch& b) {
    }
 }
 }
+
+void ldb_gpu_wait_batch_internal(LdbContext* ctx, const LdbBatch* b) { waitBatch(ctx, *b); }
 
 // ------------------------------------------------------------------------------------------------ host pool
 namespace ldb {
@@ -461,6 +467,8 @@ int ldb_gpu_table_append_batch(LdbTable* t, int64_t n_rows, const LdbArrayView* 
       b.data.resize(nc);
       b.bytes.assign(nc, nullptr);
       b.elemBytes.assign(nc, 0);
+      b.validity.assign(nc, nullptr);
+      b.validityBitOffset.assign(nc, 0);
       // compressed staging (staging.h): fixed-width HOST columns of batches that span at least one block are re-encoded by
       // the staging engine's independent pipelines (pack on a host thread → H2D on its stream → decode kernel) and this call
       // returns at once; the Arrow buffers must stay valid until the table is cleared (they belong to the table storage)
@@ -479,15 +487,29 @@ int ldb_gpu_table_append_batch(LdbTable* t, int64_t n_rows, const LdbArrayView* 
       }
       for (size_t c = 0; c < nc; c++) {
          const LdbArrayView& av = columns[c];
-         if (av.null_count != 0) fail(LDB_ERR_UNSUPPORTED, "nullable batches are not supported on the GPU path yet");
          if (av.length < n_rows) fail(LDB_ERR_INVALID, "column shorter than the batch");
+         // nullable column: keep its validity bitmap (Arrow: bit i of buffers[0], LSB first, ArrayView.offset applies).  Only the
+         // program pipeline reads it; the specialised pipelines refuse batches whose touched columns carry one (StagePlan::bind).
+         if (av.null_count != 0 && av.buffers[0] && n_rows > 0) {
+            const int64_t firstByte = av.offset / 8, nBytes = (av.offset % 8 + n_rows + 7) / 8;
+            if (location == LDB_MEM_DEVICE) {
+               b.validity[c] = (const uint8_t*) av.buffers[0] + firstByte;
+            } else {
+               void* dv = ctx->stagingAlloc((size_t) nBytes);
+               b.owned.push_back(dv);
+               LDB_CUDA(cudaMemcpyAsync(dv, (const uint8_t*) av.buffers[0] + firstByte, (size_t) nBytes, cudaMemcpyHostToDevice, ctx->copy));
+               ctx->h2dBytes.fetch_add(nBytes);
+               b.validity[c] = dv;
+            }
+            b.validityBitOffset[c] = av.offset % 8;
+         }
          size_t w = elemWidth(t->columns[c].type);
          bool utf8 = t->columns[c].type == LDB_UTF8;
          const uint8_t* src = (const uint8_t*) av.buffers[1] + (size_t) av.offset * w;
          size_t bytes = (size_t) (n_rows + (utf8 ? 1 : 0)) * w;
          b.elemBytes[c] = (int32_t) w;
          const int ty = t->columns[c].type;
-         const bool packable = packThis && !utf8 && (ty != LDB_DECIMAL128 || t->columns[c].precision < 19) && pk->cols.size() < (size_t) kMaxPackCols;
+         const bool packable = packThis && (ty == LDB_INT32 || ty == LDB_DATE32 || ty == LDB_FSB4 || ty == LDB_INT64 || (ty == LDB_DECIMAL128 && t->columns[c].precision < 19)) && pk->cols.size() < (size_t) kMaxPackCols;
          if (location == LDB_MEM_DEVICE) {
             b.data[c] = src;
             if (utf8) b.bytes[c] = av.buffers[2];
@@ -959,6 +981,8 @@ struct StagePlan {
       int off = 0;
       bool aligned = true;
       for (int i = 0; i < n; i++) {
+         if ((colIdx[i] < (int) b.validity.size() && b.validity[colIdx[i]]) || (colIdx[i] < (int) b.validBytes.size() && b.validBytes[colIdx[i]]))
+            fail(LDB_ERR_UNSUPPORTED, "column " + t->columns[colIdx[i]].name + " has NULLs in this batch: the specialised pipelines read non-nullable columns — use the program pipeline (ldb_gpu_run_program)");
          out.base[i] = (const uint8_t*) b.data[colIdx[i]];
          out.elemBytes[i] = b.elemBytes[colIdx[i]]; // as staged: decimal128 is 16, or 8 when the HOST batch was narrowed
          out.smemOffset[i] = off;
@@ -1066,6 +1090,7 @@ void bindFilters(const FilterPlan& p, const LdbBatch& b, FilterSet& out) {
    out = p.set;
    for (int i = 0; i < out.n; i++) {
       if (out.c[i].kind != COL_UTF8_EQ && out.c[i].kind != COL_UTF8_CONTAINS) continue; // fixed-width filter columns are read from the staged tile
+      if (p.colIdx[i] < (int) b.validity.size() && b.validity[p.colIdx[i]]) fail(LDB_ERR_UNSUPPORTED, "string filter column has NULLs in this batch: use the program pipeline (ldb_gpu_run_program)");
       out.c[i].base = b.data[p.colIdx[i]];
       out.c[i].bytes = (const uint8_t*) b.bytes[p.colIdx[i]];
    }

@@ -128,8 +128,8 @@ class Table:
         self._keep = []
         ctx._tables.append(self)
 
-    def _append(self, n_rows: int, bufs: Dict[str, object], location: int, utf8_sizes: Dict[str, int]):
-        """bufs: column → address (int) or (offsets_addr, bytes_addr) for utf8."""
+    def _append(self, n_rows: int, bufs: Dict[str, object], location: int, utf8_sizes: Dict[str, int], valids: Optional[Dict[str, int]] = None):
+        """bufs: column → address (int) or (offsets_addr, bytes_addr) for utf8; valids: column → address of an Arrow validity bitmap."""
         nc = len(self.columns)
         views = (capi.ArrayView * nc)()
         sizes = (C.c_int64 * nc)()
@@ -142,16 +142,24 @@ class Table:
                 sizes[i] = utf8_sizes[c.name]
             else:
                 arr[1] = v
+            nulls = 0
+            if valids and valids.get(c.name):
+                arr[0] = valids[c.name]
+                nulls = -1  # "unknown, look at the bitmap" (Arrow's convention)
             keep.append(arr)
-            views[i] = capi.ArrayView(n_rows, 0, 0, 3 if c.phys == "utf8" else 2, 0, C.cast(arr, C.POINTER(C.c_void_p)), None)
+            views[i] = capi.ArrayView(n_rows, nulls, 0, 3 if c.phys == "utf8" else 2, 0, C.cast(arr, C.POINTER(C.c_void_p)), None)
         e = Error()
         check(self.ctx.L.ldb_gpu_table_append_batch(self.h, n_rows, views, sizes, location, C.byref(e)), e)
         self._keep.append((keep, views))
 
     def append_host(self, chunk: Dict[str, object], n_rows: int):
-        bufs, sizes = {}, {}
+        """chunk: column → numpy buffer ((offsets, bytes) for utf8); an optional entry "<column>$valid" holds the column's Arrow
+        validity bitmap (numpy uint8, LSB first, bit i = row i is NOT NULL)."""
+        bufs, sizes, valids = {}, {}, {}
         for c in self.columns:
             v = chunk[c.name]
+            if c.name + "$valid" in chunk:
+                valids[c.name] = chunk[c.name + "$valid"].ctypes.data
             if c.phys == "utf8":
                 offs, data = v
                 bufs[c.name] = (offs.ctypes.data, data.ctypes.data)
@@ -159,7 +167,7 @@ class Table:
             else:
                 bufs[c.name] = v.ctypes.data
         self._keep.append(chunk)
-        self._append(n_rows, bufs, capi.MEM_HOST, sizes)
+        self._append(n_rows, bufs, capi.MEM_HOST, sizes, valids)
 
     def append_device(self, tensors: Dict[str, object], n_rows: int):
         """tensors: column → torch CUDA tensor (or (offsets, bytes) pair for utf8); borrowed."""

@@ -144,3 +144,55 @@ def test_gpu_reproduces_the_references_sf1_answers(sf1, gpu_ctx):
 
     g = runtime.Tpch(gpu_ctx, {k: gpu_ctx.table_from_host(base(v)) for k, v in sf1.items()})
     check_all(g.q1(), g.q6(), g.q3(), g.q5(), g.q9())
+
+
+@pytest.mark.gpu
+def test_gpu_program_pipelines_reproduce_q4_q12_q18(sf1, gpu_ctx):
+    """f4 on the GPU, pinned by the reference's own answers: Q4 (EXISTS → semi join with a col-vs-col filter on the build side), Q12
+    (string IN-list, join, conditional counts) and Q18 (1.5 M-group aggregation, HAVING, semi join, ORDER BY … LIMIT 100) as register
+    programs of the generic pipeline (csrc/program.cu) over the dbgen-faithful SF1 tables."""
+    import ctypes as C
+    from lingodb_b200 import program as P, runtime
+    col, const = (lambda n: ("col", n)), (lambda v: ("const", v))
+    d = lambda s: (datetime.date.fromisoformat(s) - datetime.date(1970, 1, 1)).days
+    li, od = gpu_ctx.table_from_host(sf1["lineitem"]), gpu_ctx.table_from_host(sf1["orders"])
+    # ---- Q4 (tpchSf1.test:20455-20459): orders ⋉ lineitem(l_commitdate < l_receiptdate), group by o_orderpriority
+    late = runtime.join_table(gpu_ctx, 1_600_000, unique=True)
+    P.build_join(gpu_ctx, li, late, col("l_orderkey"), where=("cmp", "<", col("l_commitdate"), col("l_receiptdate")))
+    where = ("and", ("and", ("cmp", ">=", col("o_orderdate"), const(d("1993-07-01"))), ("cmp", "<", col("o_orderdate"), const(d("1993-10-01")))),
+             ("not", ("isnull", ("probe", late, col("o_orderkey")))))
+    st = P.group_by(gpu_ctx, od, [("strkey8", "o_orderpriority")], [("count_star", None)], where=where, expected_groups=16)
+    got = P.decode_groups(P.read_groups(gpu_ctx, st, 16), 1, 1)
+    key8 = lambda s_: int.from_bytes(s_.encode()[:8].ljust(8, b"\0"), "big")
+    assert [[p, str(got[(key8(p),)][0])] for p in dbgen.ORDER_PRIORITIES] == GOLD["q4_rows"]
+    gpu_ctx.L.ldb_gpu_state_destroy(st)
+    # ---- Q12 (:1197-1198): lineitem(shipmode IN, date predicates) ⋈ orders, sum(case priority high / low)
+    prio = runtime.join_table(gpu_ctx, 1_600_000, unique=True)
+    high = ("or", ("strcmp", "=", "o_orderpriority", "1-URGENT"), ("strcmp", "=", "o_orderpriority", "2-HIGH"))
+    P.build_join(gpu_ctx, od, prio, col("o_orderkey"), payload=("case", high, const(1), const(0)))
+    pr = ("probe", prio, col("l_orderkey"))
+    where = ("and", ("and", ("or", ("strcmp", "=", "l_shipmode", "MAIL"), ("strcmp", "=", "l_shipmode", "SHIP")),
+                     ("and", ("cmp", "<", col("l_commitdate"), col("l_receiptdate")), ("cmp", "<", col("l_shipdate"), col("l_commitdate")))),
+             ("and", ("and", ("cmp", ">=", col("l_receiptdate"), const(d("1994-01-01"))), ("cmp", "<", col("l_receiptdate"), const(d("1995-01-01")))), ("not", ("isnull", pr))))
+    aggs = [("sum", ("case", ("cmp", "=", pr, const(1)), const(1), const(0))), ("sum", ("case", ("cmp", "=", pr, const(0)), const(1), const(0)))]
+    st = P.group_by(gpu_ctx, li, [("strkey8", "l_shipmode")], aggs, where=where, expected_groups=16)
+    got = P.decode_groups(P.read_groups(gpu_ctx, st, 16), 1, 2)
+    assert [[m, str(got[(key8(m),)][0]), str(got[(key8(m),)][1])] for m in ("MAIL", "SHIP")] == GOLD["q12_rows"]
+    gpu_ctx.L.ldb_gpu_state_destroy(st)
+    # ---- Q18 (:19726-19782): group by l_orderkey (1.5 M groups) having sum(l_quantity) > 300 → semi join orders → top 100
+    st = P.group_by(gpu_ctx, li, [col("l_orderkey")], [("sum", col("l_quantity"))], expected_groups=1_600_000)
+    groups = P.groups_table(gpu_ctx, st)
+    assert groups.num_rows == 1_500_000
+    big = runtime.join_table(gpu_ctx, 4096, unique=True)
+    P.build_join(gpu_ctx, groups, big, col("k0"), payload=col("a0"), where=("cmp", ">", col("a0"), const(30000)))
+    pb = ("probe", big, col("o_orderkey"))
+    mt = P.RawTable(gpu_ctx, P.materialize(gpu_ctx, od, [col("o_custkey"), col("o_orderkey"), col("o_orderdate"), col("o_totalprice"), pb], where=("not", ("isnull", pb))))
+    ids = mt.order_by("c3", descending=True)  # o_totalprice desc on the device; the date tie-break over <= 100 rows below
+    rows = list(zip(*[mt.gather(f"c{i}", ids) for i in range(5)]))
+    rows.sort(key=lambda r: (-r[3], r[2]))
+    got18 = [["Customer#%09d" % r[0], str(r[0]), str(r[1]), day(r[2]), dec(r[3], 2), dec(r[4], 2)] for r in rows[:100]]
+    assert got18 == GOLD["q18_rows"]
+    for t in (mt, groups):
+        t.destroy()
+    for s_ in (st, late, prio, big):
+        gpu_ctx.L.ldb_gpu_state_destroy(s_)
