@@ -349,7 +349,7 @@ typedef struct LdbProgramDesc {
    LdbTable* source;
    int32_t n_columns;            /* <= 12 */
    const char* const* columns;
-   int32_t n_instr;              /* <= 96, registers 0..23 */
+   int32_t n_instr;              /* <= 96, registers 0..47 */
    const LdbInstr* instr;
    int32_t n_consts;             /* <= 24 */
    const LdbI128* consts;

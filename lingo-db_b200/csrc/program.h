@@ -12,7 +12,7 @@
 namespace ldb {
 
 constexpr int kProgMaxInstr = 96;
-constexpr int kProgMaxRegs = 24;
+constexpr int kProgMaxRegs = 48;
 constexpr int kProgMaxCols = 12;
 constexpr int kProgMaxConsts = 24;
 constexpr int kProgMaxStrings = 12;

@@ -34,8 +34,8 @@ class Builder:
     def _reg(self):
         r = self._next
         self._next += 1
-        if r >= 24:
-            raise ValueError("program needs more than 24 registers")
+        if r >= 48:
+            raise ValueError("program needs more than 48 registers")
         return r
 
     def _col(self, name):
