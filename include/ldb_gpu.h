@@ -109,6 +109,10 @@ int64_t ldb_gpu_context_h2d_bytes(LdbContext* ctx);
  * Arrow cells unchanged.  rows the raw copiers took so far / CPUs the process may use (cgroup quota aware): */
 int64_t ldb_gpu_context_raw_staged_rows(LdbContext* ctx);
 int32_t ldb_gpu_effective_cpus(void);
+/* experiment hook: depth of the TMA tile pipeline (2..4 stages) of the join-build / probe-aggregate / probe-probe-group / star-probe
+ * kernels and the rows per thread of a build tile (1, 2, 4); defaults = measured best (profiles/r2_stage_sweep.md), also settable
+ * through LDB_STAGES_BUILD / _PROBE_AGG / _PROBE2 / _STAR and LDB_RPT_BUILD */
+void ldb_gpu_set_tuning(int32_t stages_build, int32_t stages_probe_agg, int32_t stages_probe2, int32_t stages_star, int32_t rows_per_thread_build);
 int64_t ldb_gpu_table_num_rows(const LdbTable* t);
 void ldb_gpu_table_destroy(LdbTable* t);
 

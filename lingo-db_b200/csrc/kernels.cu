@@ -72,10 +72,10 @@ __device__ __forceinline__ void issueTile(const StagedCols& sc, uint8_t* smem, u
 constexpr int kWarps = kBlock / 32;
 constexpr int kThreads = kBlock + 32;
 struct TileBarriers {
-   uint64_t full[kStages];
-   uint64_t empty[kStages];
+   uint64_t full[kMaxStages];
+   uint64_t empty[kMaxStages];
 };
-template <int kRowsPerThread, int DB, class Fn>
+template <int kRowsPerThread, int DB, int kStages = ldb::kStages, class Fn>
 __device__ __forceinline__ void forEachTile(const StagedCols& sc, int64_t n, uint8_t* smem, TileBarriers* bars, const Fn& fnTile) {
    constexpr int kTileRows = kRowsPerThread * kBlock; // == sc.tileRows (host binds the same constant)
    const int64_t nFull = n / kTileRows;
@@ -126,7 +126,7 @@ __device__ __forceinline__ void forEachTile(const StagedCols& sc, int64_t n, uin
 // Non-specialised variant for the arithmetic-bound group-by kernel (K1/K2): every row costs the same, so the CTA-wide
 // barrier is cheap (stall_barrier 0.1 per issue) and a 9th warp would only cost registers (2 CTAs x 288 threads
 // cap the kernel at 112 registers → spills).  One elected thread issues the copies, __syncthreads() recycles a stage.
-template <int kRowsPerThread, int DB, class Fn>
+template <int kRowsPerThread, int DB, int kStages = ldb::kStages, class Fn>
 __device__ __forceinline__ void forEachTileUniform(const StagedCols& sc, int64_t n, uint8_t* smem, TileBarriers* bars, const Fn& fnTile) {
    constexpr int kTileRows = kRowsPerThread * kBlock;
    const int64_t nFull = n / kTileRows;
@@ -189,6 +189,9 @@ __device__ __forceinline__ void forEachRow(const StagedCols& sc, int64_t n, uint
       }
    });
 }
+
+// late-materialised operand: low 8 bytes of the cell of `row` (decimal(p<19) computes from them, LowerToStd.cpp:111-209)
+__device__ __forceinline__ int64_t lazyLo64(const LazyCols& lc, int c, int64_t row) { return ldStream64((const int64_t*) (lc.base[c] + (size_t) row * lc.elemBytes[c])); }
 
 // =================================================================================== filters
 // Conjunction of column-vs-constant predicates (Restrictions::applyFilters, Restrictions.cpp:365-390):
@@ -612,6 +615,42 @@ struct Aggs {
    }
 };
 
+static int envInt(const char* name, int dflt, int lo, int hi) {
+   const char* e = getenv(name);
+   if (!e) return dflt;
+   int v = atoi(e);
+   return v < lo ? lo : (v > hi ? hi : v);
+}
+static Tuning& tuningStorage() {
+   static Tuning t = [] {
+      Tuning x;
+      // measured at SF100 (profiles/r2_stage_sweep.md): deeper pipelines cost resident CTAs and the probe kernels lose more from that
+      // than they gain (K9 9.5 / 10.8 / 12.5 ms at 2 / 3 / 4 stages); only the build kernel likes 3 stages with 2 rows per thread
+      x.stagesBuild = envInt("LDB_STAGES_BUILD", 3, 2, kMaxStages);
+      x.stagesProbeAgg = envInt("LDB_STAGES_PROBE_AGG", 2, 2, kMaxStages);
+      x.stagesProbe2 = envInt("LDB_STAGES_PROBE2", 2, 2, kMaxStages);
+      x.stagesStar = envInt("LDB_STAGES_STAR", 2, 2, kMaxStages);
+      x.rptBuild = envInt("LDB_RPT_BUILD", 2, 1, 4);
+      x.rptStar = envInt("LDB_RPT_STAR", 4, 1, 4);
+      if (x.rptStar == 3) x.rptStar = 2;
+      if (x.rptBuild == 3) x.rptBuild = 2;
+      return x;
+   }();
+   return t;
+}
+const Tuning& tuning() { return tuningStorage(); }
+void setTuning(const Tuning& t) {
+   Tuning x = t;
+   auto clampStages = [](int v) { return v < 2 ? 2 : (v > kMaxStages ? kMaxStages : v); };
+   x.stagesBuild = clampStages(x.stagesBuild);
+   x.stagesProbeAgg = clampStages(x.stagesProbeAgg);
+   x.stagesProbe2 = clampStages(x.stagesProbe2);
+   x.stagesStar = clampStages(x.stagesStar);
+   x.rptBuild = x.rptBuild >= 4 ? 4 : (x.rptBuild >= 2 ? 2 : 1);
+   x.rptStar = x.rptStar >= 4 ? 4 : (x.rptStar >= 2 ? 2 : 1);
+   tuningStorage() = x;
+}
+
 extern __shared__ __align__(128) uint8_t dynSmem[];
 
 // =================================================================================== K1 / K2
@@ -772,8 +811,8 @@ static std::string signature(const GroupByParams& p) {
 }
 // persistent grid: SMs x resident CTAs of this instantiation (occupancy API), never more than the tiles
 template <class K>
-static int persistentGrid(K kernel, const StagedCols& sc, int64_t nRows, int smCount, size_t* dynBytes, int threads = kThreads) {
-   *dynBytes = sc.useTma ? (size_t) kStages * sc.stageBytes : 0;
+static int persistentGrid(K kernel, const StagedCols& sc, int64_t nRows, int smCount, size_t* dynBytes, int threads = kThreads, int stages = kStages) {
+   *dynBytes = sc.useTma ? (size_t) stages * sc.stageBytes : 0;
    // static + dynamic shared memory beyond 48 KB needs the opt-in (K9 carries 12 KB of static group slots), so always ask
    if (*dynBytes > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) *dynBytes);
    int perSm = 1;
@@ -844,9 +883,9 @@ bool launchScanGroupBy(const GroupByParams& p, int smCount, cudaStream_t s, cons
 // i128 arithmetic, atomics) and holds the tile's stage until the slowest chain is done (profiles/r1_q9.md: 9.4 ms for a
 // 1.7 ms scan).  Instead the scan COPIES each survivor's operands (NW 32-bit words) into a CTA-wide queue in shared memory;
 // whenever the queue holds a CTA's worth, every thread takes one entry: kBlock independent chains in flight, all lanes busy.
-template <int NW>
+template <int NW, int RPT = kRowsPerThreadStar>
 struct SurvivorQueue {
-   static constexpr int kCap = kBlock + kRowsPerThreadStar * kBlock; // a drain leaves < kBlock entries; one tile adds <= its rows
+   static constexpr int kCap = kBlock + RPT * kBlock; // a drain leaves < kBlock entries; one tile adds <= its rows
    int32_t w[NW][kCap];
    int count;
    __device__ __forceinline__ int claim() { return atomicAdd(&count, 1); }
@@ -858,9 +897,9 @@ struct SurvivorQueue {
 };
 // Called by every thread of the CTA after a barrier that published the pushes.  Processes entries kBlock at a time until
 // fewer than kBlock are left (all == false) or none (all == true, at the end of the kernel).
-template <int NW, class Fn>
-__device__ __forceinline__ void drainQueue(SurvivorQueue<NW>& q, bool all, const Fn& process) {
-   int count = q.count;
+template <class Q, class Fn>
+__device__ __forceinline__ void drainQueue(Q& q, bool all, const Fn& process) {
+   int count = q.count < Q::kCap ? q.count : Q::kCap; // claims beyond the capacity were handled in place by their owners
    if (!(count >= kBlock || (all && count > 0))) return;
    while (count >= kBlock || (all && count > 0)) {
       const int n = count < kBlock ? count : kBlock;
@@ -930,11 +969,11 @@ __device__ __forceinline__ void flushInsertCount(const JoinTableDev& t, unsigned
 // scan → filters → [probe parent table] → insert {key, payload, side…}
 // (subop.materialize + rt::GrowingBuffer::insert + rt::HashIndexedView::build; for the group-join
 //  the lookup_or_insert of the left input, RelAlgToSubOp.cpp:2682-2950)
-template <int DB>
+template <int DB, int RPT, int NS>
 __global__ void __launch_bounds__(kBlock, 4) scanBuildKernel(const __grid_constant__ BuildParams p) {
    constexpr bool IN = true; // latency-bound kernels keep the IN path in
    __shared__ __align__(8) TileBarriers barsStorage;
-   __shared__ SurvivorQueue<5> queue; // {probe key, build key, own payload, side0, side1}
+   __shared__ SurvivorQueue<5, RPT> queue; // {probe key, build key, own payload, side0, side1}
    TileBarriers* bars = &barsStorage;
    if (threadIdx.x == 0) queue.count = 0;
    __syncthreads();
@@ -958,9 +997,9 @@ __global__ void __launch_bounds__(kBlock, 4) scanBuildKernel(const __grid_consta
          insert(queue.w[1][q], p.payloadStage >= 0 ? queue.w[2][q] : (int32_t) (parentPayload & (p.probe.stride == 32 ? 0x7fffffff : -1)), queue.w[3][q], queue.w[4][q]);
       });
    };
-   forEachTileUniform<kRowsPerThreadStar, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+   forEachTileUniform<RPT, DB, NS>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
 #pragma unroll
-      for (int j = 0; j < kRowsPerThreadStar; j++) {
+      for (int j = 0; j < RPT; j++) {
          const int lrRaw = j * kBlock + threadIdx.x;
          const bool valid = lrRaw < rows;
          const int lr = valid ? lrRaw : 0;
@@ -1027,13 +1066,22 @@ void launchScanBuild(const BuildParams& p, int smCount, cudaStream_t s) {
       }
       return;
    }
-   if (p.src.cols.decBytes == 8) {
-      int grid = persistentGrid(scanBuildKernel<8>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
-      scanBuildKernel<8><<<grid, kBlock, dyn, s>>>(p);
-   } else {
-      int grid = persistentGrid(scanBuildKernel<16>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
-      scanBuildKernel<16><<<grid, kBlock, dyn, s>>>(p);
+   // (RPT, NS) from tuning(): the host bound the tiles with the same rows-per-thread (runtime.cpp)
+   const int rpt = tuning().rptBuild, ns = tuning().stagesBuild;
+#define LDB_BUILD_CASE(DBV, RPTV, NSV)                                                                                          \
+   if (rpt == RPTV && ns == NSV) {                                                                                              \
+      int grid = persistentGrid(scanBuildKernel<DBV, RPTV, NSV>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock, NSV);          \
+      scanBuildKernel<DBV, RPTV, NSV><<<grid, kBlock, dyn, s>>>(p);                                                             \
+      return;                                                                                                                   \
    }
+   if (p.src.cols.decBytes == 8) {
+      LDB_BUILD_CASE(8, 1, 2) LDB_BUILD_CASE(8, 2, 2) LDB_BUILD_CASE(8, 4, 2) LDB_BUILD_CASE(8, 1, 3) LDB_BUILD_CASE(8, 2, 3) LDB_BUILD_CASE(8, 4, 3)
+      LDB_BUILD_CASE(8, 1, 4) LDB_BUILD_CASE(8, 2, 4) LDB_BUILD_CASE(8, 4, 4)
+   } else {
+      LDB_BUILD_CASE(16, 1, 2) LDB_BUILD_CASE(16, 2, 2) LDB_BUILD_CASE(16, 4, 2) LDB_BUILD_CASE(16, 1, 3) LDB_BUILD_CASE(16, 2, 3) LDB_BUILD_CASE(16, 4, 3)
+      LDB_BUILD_CASE(16, 1, 4) LDB_BUILD_CASE(16, 2, 4) LDB_BUILD_CASE(16, 4, 4)
+   }
+#undef LDB_BUILD_CASE
 }
 
 // =================================================================================== K8 materialize
@@ -1159,13 +1207,13 @@ void launchScanMaterialize(const MaterializeParams& p, int smCount, cudaStream_t
 // scan → filters → pure lookup in the group-join map → SUM into the shared entry.  The reference
 // takes a per-entry spin lock (SubOpToControlFlow.cpp:4218-4251, EntryLock.cpp:9-25) or an
 // atomic_rmw; here the i128 SUM is two 64-bit atomics with carry (exact, order independent).
-template <int NV, int DB>
+template <int NV, int DB, int NS>
 __global__ void __launch_bounds__(kThreads, 4) scanProbeAggKernel(const __grid_constant__ ProbeAggParams p) {
    constexpr bool IN = true;
    __shared__ __align__(8) TileBarriers barsStorage;
    TileBarriers* bars = &barsStorage;
    const int64_t one = 100;
-   forEachTile<kRowsPerThreadProbe, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+   forEachTile<kRowsPerThreadProbe, DB, NS>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
       int32_t key[kRowsPerThreadProbe];
       int lrs[kRowsPerThreadProbe];
       BloomProbe bp[kRowsPerThreadProbe];
@@ -1186,7 +1234,7 @@ __global__ void __launch_bounds__(kThreads, 4) scanProbeAggKernel(const __grid_c
          joinProbeSlots<true>(p.table, key[j], bp[j].h, [&](int64_t slot, int32_t payloadWord) {
             int64_t vals[NV];
 #pragma unroll
-            for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lrs[j]);
+            for (int c = 0; c < NV; c++) vals[c] = lazyLo64(p.values, c, rowBase + lrs[j]);
             i128 v = evalAggDyn(p.agg, vals, one);
             uint8_t* entry = p.table.base + (uint64_t) slot * 32;
             atomicAdd128((unsigned long long*) (entry + 16), (unsigned long long*) (entry + 24), v);
@@ -1202,44 +1250,31 @@ bool launchScanProbeAgg(const ProbeAggParams& p, int smCount, cudaStream_t s, co
       return false;
    }
    size_t dyn;
-   if (nv == 1) {
-      if (p.src.cols.decBytes == 8) {
-         int grid = persistentGrid(scanProbeAggKernel<1, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbeAggKernel<1, 8><<<grid, kThreads, dyn, s>>>(p);
-      } else {
-         int grid = persistentGrid(scanProbeAggKernel<1, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbeAggKernel<1, 16><<<grid, kThreads, dyn, s>>>(p);
-      }
-   } else if (nv == 2) {
-      if (p.src.cols.decBytes == 8) {
-         int grid = persistentGrid(scanProbeAggKernel<2, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbeAggKernel<2, 8><<<grid, kThreads, dyn, s>>>(p);
-      } else {
-         int grid = persistentGrid(scanProbeAggKernel<2, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbeAggKernel<2, 16><<<grid, kThreads, dyn, s>>>(p);
-      }
-   } else {
-      if (p.src.cols.decBytes == 8) {
-         int grid = persistentGrid(scanProbeAggKernel<3, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbeAggKernel<3, 8><<<grid, kThreads, dyn, s>>>(p);
-      } else {
-         int grid = persistentGrid(scanProbeAggKernel<3, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbeAggKernel<3, 16><<<grid, kThreads, dyn, s>>>(p);
-      }
+   const int ns = tuning().stagesProbeAgg;
+#define LDB_PA_CASE(NVV, DBV, NSV)                                                                                   \
+   if (nv == NVV && p.src.cols.decBytes == DBV && ns == NSV) {                                                       \
+      int grid = persistentGrid(scanProbeAggKernel<NVV, DBV, NSV>, p.src.cols, p.src.nRows, smCount, &dyn, kThreads, NSV); \
+      scanProbeAggKernel<NVV, DBV, NSV><<<grid, kThreads, dyn, s>>>(p);                                              \
+      return true;                                                                                                   \
    }
-   return true;
+#define LDB_PA_ALL(NVV, DBV) LDB_PA_CASE(NVV, DBV, 2) LDB_PA_CASE(NVV, DBV, 3) LDB_PA_CASE(NVV, DBV, 4)
+   LDB_PA_ALL(1, 8) LDB_PA_ALL(1, 16) LDB_PA_ALL(2, 8) LDB_PA_ALL(2, 16) LDB_PA_ALL(3, 8) LDB_PA_ALL(3, 16)
+#undef LDB_PA_ALL
+#undef LDB_PA_CASE
+   *why = "no probe-aggregate instantiation for this shape";
+   return false;
 }
 
 // =================================================================================== K4 probe, probe, group
 // scan → probe A on keyA → probe B on keyB → keep rows whose payloads agree (the composite join key
 // (l_suppkey, c_nationkey) = (s_suppkey, s_nationkey) of Q5) → group by that payload → SUM.
-template <int NV, int DB>
+template <int NV, int DB, int NS>
 __global__ void __launch_bounds__(kThreads, 4) scanProbe2GroupByKernel(const __grid_constant__ Probe2GroupByParams p) {
    constexpr bool IN = true;
    __shared__ __align__(8) TileBarriers barsStorage;
    TileBarriers* bars = &barsStorage;
    const int64_t one = 100;
-   forEachTile<kRowsPerThreadProbe, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+   forEachTile<kRowsPerThreadProbe, DB, NS>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
       int32_t key[kRowsPerThreadProbe];
       int lrs[kRowsPerThreadProbe];
       BloomProbe bp[kRowsPerThreadProbe];
@@ -1267,7 +1302,7 @@ __global__ void __launch_bounds__(kThreads, 4) scanProbe2GroupByKernel(const __g
                if (((payA ^ payB) & (p.tableA.stride == 32 || p.tableB.stride == 32 ? 0x7fffffff : -1)) != 0) return;
                int64_t vals[NV];
 #pragma unroll
-               for (int c = 0; c < NV; c++) vals[c] = tile.lo64(p.valueStage[c], lrs[j]);
+               for (int c = 0; c < NV; c++) vals[c] = lazyLo64(p.values, c, rowBase + lrs[j]);
                int32_t kk[2] = {p.tableB.stride == 32 ? (payB & 0x7fffffff) : payB, 0}; // bit 31 of a wide entry is the group-join marker, not payload
                int slot = groupLookupOrInsert(p.groups, kk);
                if (slot >= 0) groupAtomicAdd(p.groups, slot, 0, evalAggDyn(p.agg, vals, one), p.agg.expr == LDB_EXPR_COL || p.agg.expr == LDB_EXPR_ONE);
@@ -1283,32 +1318,19 @@ bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStre
       return false;
    }
    size_t dyn;
-   if (nv == 1) {
-      if (p.src.cols.decBytes == 8) {
-         int grid = persistentGrid(scanProbe2GroupByKernel<1, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbe2GroupByKernel<1, 8><<<grid, kThreads, dyn, s>>>(p);
-      } else {
-         int grid = persistentGrid(scanProbe2GroupByKernel<1, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbe2GroupByKernel<1, 16><<<grid, kThreads, dyn, s>>>(p);
-      }
-   } else if (nv == 2) {
-      if (p.src.cols.decBytes == 8) {
-         int grid = persistentGrid(scanProbe2GroupByKernel<2, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbe2GroupByKernel<2, 8><<<grid, kThreads, dyn, s>>>(p);
-      } else {
-         int grid = persistentGrid(scanProbe2GroupByKernel<2, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbe2GroupByKernel<2, 16><<<grid, kThreads, dyn, s>>>(p);
-      }
-   } else {
-      if (p.src.cols.decBytes == 8) {
-         int grid = persistentGrid(scanProbe2GroupByKernel<3, 8>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbe2GroupByKernel<3, 8><<<grid, kThreads, dyn, s>>>(p);
-      } else {
-         int grid = persistentGrid(scanProbe2GroupByKernel<3, 16>, p.src.cols, p.src.nRows, smCount, &dyn);
-         scanProbe2GroupByKernel<3, 16><<<grid, kThreads, dyn, s>>>(p);
-      }
+   const int ns = tuning().stagesProbe2;
+#define LDB_P2_CASE(NVV, DBV, NSV)                                                                                        \
+   if (nv == NVV && p.src.cols.decBytes == DBV && ns == NSV) {                                                            \
+      int grid = persistentGrid(scanProbe2GroupByKernel<NVV, DBV, NSV>, p.src.cols, p.src.nRows, smCount, &dyn, kThreads, NSV); \
+      scanProbe2GroupByKernel<NVV, DBV, NSV><<<grid, kThreads, dyn, s>>>(p);                                              \
+      return true;                                                                                                        \
    }
-   return true;
+#define LDB_P2_ALL(NVV, DBV) LDB_P2_CASE(NVV, DBV, 2) LDB_P2_CASE(NVV, DBV, 3) LDB_P2_CASE(NVV, DBV, 4)
+   LDB_P2_ALL(1, 8) LDB_P2_ALL(1, 16) LDB_P2_ALL(2, 8) LDB_P2_ALL(2, 16) LDB_P2_ALL(3, 8) LDB_P2_ALL(3, 16)
+#undef LDB_P2_ALL
+#undef LDB_P2_CASE
+   *why = "no probe-probe-group instantiation for this shape";
+   return false;
 }
 
 // =================================================================================== K9 star probe, group
@@ -1316,48 +1338,69 @@ bool launchScanProbe2GroupBy(const Probe2GroupByParams& p, int smCount, cudaStre
 // int32 payloads → SUM(a * (1 - b) - c * d), c = P's int64 payload.  The reference's per-worker pre-aggregation
 // cache (PreAggregationHashtable.cpp:46-60) becomes a per-CTA shared-memory table flushed once per CTA: ~10^8 matched
 // rows over 175 groups would otherwise serialise on 175 HBM addresses.
-template <int DB>
+// Survivor queue of bounded size: a claim beyond the capacity is handled in place by its owner (only non-selective inputs get
+// there), so the queue — and with it the CTA's shared memory — stays small and more CTAs are resident.
+struct StarQueue {
+   static constexpr int kCap = 3 * kBlock;
+   int32_t w[6][kCap]; // k0, k1, kS, kO, row lo, row hi
+   int count;
+};
+template <int DB, int RPT, int NS>
 __global__ void __launch_bounds__(kBlock, 4) scanStarProbeGroupByKernel(const __grid_constant__ StarProbeParams p) {
    constexpr bool IN = true;
    __shared__ __align__(8) TileBarriers barsStorage;
-   __shared__ SurvivorQueue<10> queue; // {k0, k1, kS, kO, a, b, d}
+   __shared__ StarQueue queue;
    __shared__ LocalGroups groups;
    TileBarriers* bars = &barsStorage;
    groups.init();
    if (threadIdx.x == 0) queue.count = 0;
    __syncthreads();
    const int64_t one = 100;
-   // the three probes of a row are independent of each other: their first slots are loaded together (S and O are
-   // foreign-key probes that always hit, so their Bloom filters are not consulted)
-   auto process = [&](int q) {
-      const int32_t k0 = queue.w[0][q], k1 = queue.w[1][q], kS = queue.w[2][q], kO = queue.w[3][q];
+   // the three probes of a row and its three operand loads are independent of each other: all first loads are issued together
+   // (S and O are foreign-key probes that always hit, so their Bloom filters are not consulted)
+   auto handle = [&](int32_t k0, int32_t k1, int32_t kS, int32_t kO, int64_t row) {
       const uint64_t hP = hashPair(k0, k1), hS = p.tableS.direct ? 0 : hashI32(kS), hO = p.tableO.direct ? 0 : hashI32(kO);
       const ulonglong2 eP = __ldg((const ulonglong2*) slotPtr(p.tableP, hP & p.tableP.mask));
       const unsigned long long eS = fkFirstSlot(p.tableS, kS, hS), eO = fkFirstSlot(p.tableO, kO, hO);
-      const int64_t a = queue.get64(4, q), b = queue.get64(6, q), d = queue.get64(8, q);
+      const int64_t a = lazyLo64(p.values, 0, row), b = lazyLo64(p.values, 1, row), d = lazyLo64(p.values, 2, row);
       pairProbeFrom(p.tableP, k0, k1, hP, eP, [&](int64_t c) {
          fkProbeFrom(p.tableS, kS, hS, eS, [&](int32_t g0) {
             fkProbeFrom(p.tableO, kO, hO, eO, [&](int32_t g1) { groups.add(p.groups, g0, g1, sub128(mul64x64(a, one - b), mul64x64(c, d)), false); });
          });
       });
    };
-   forEachTileUniform<kRowsPerThreadStar, DB>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+   auto process = [&](int q) {
+      handle(queue.w[0][q], queue.w[1][q], queue.w[2][q], queue.w[3][q], (int64_t) (((uint64_t) (uint32_t) queue.w[5][q] << 32) | (uint32_t) queue.w[4][q]));
+   };
+   forEachTileUniform<RPT, DB, NS>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+      int32_t k0[RPT], k1[RPT];
+      int lrs[RPT];
+      BloomProbe bp[RPT];
 #pragma unroll
-      for (int j = 0; j < kRowsPerThreadStar; j++) { // filters + P's Bloom word; survivors join the queue
+      for (int j = 0; j < RPT; j++) { // filters + P's Bloom word of every row of this thread: RPT loads in flight per thread
          const int lrRaw = j * kBlock + threadIdx.x;
          const bool valid = lrRaw < rows;
-         const int lr = valid ? lrRaw : 0;
-         const bool ok = valid && evalFilters<IN>(p.src.filters, tile, lr, rowBase + lr);
-         const int32_t k0 = tile.i32(p.keyStageP0, lr), k1 = tile.i32(p.keyStageP1, lr);
-         if (pairBloomPrefetch(p.tableP, k0, k1, ok).mayContain()) {
-            const int q = queue.claim();
-            queue.w[0][q] = k0;
-            queue.w[1][q] = k1;
-            queue.w[2][q] = tile.i32(p.keyStageS, lr);
-            queue.w[3][q] = tile.i32(p.keyStageO, lr);
-            queue.put64(4, q, tile.lo64(p.valueStage[0], lr));
-            queue.put64(6, q, tile.lo64(p.valueStage[1], lr));
-            queue.put64(8, q, tile.lo64(p.valueStage[2], lr));
+         lrs[j] = valid ? lrRaw : 0;
+         const bool ok = valid && evalFilters<IN>(p.src.filters, tile, lrs[j], rowBase + lrs[j]);
+         k0[j] = tile.i32(p.keyStageP0, lrs[j]);
+         k1[j] = tile.i32(p.keyStageP1, lrs[j]);
+         bp[j] = pairBloomPrefetch(p.tableP, k0[j], k1[j], ok);
+      }
+#pragma unroll
+      for (int j = 0; j < RPT; j++) { // survivors join the queue (or, if it is full, are handled in place)
+         if (!bp[j].mayContain()) continue;
+         const int32_t kS = tile.i32(p.keyStageS, lrs[j]), kO = tile.i32(p.keyStageO, lrs[j]);
+         const int64_t row = rowBase + lrs[j];
+         const int q = atomicAdd(&queue.count, 1);
+         if (q < StarQueue::kCap) {
+            queue.w[0][q] = k0[j];
+            queue.w[1][q] = k1[j];
+            queue.w[2][q] = kS;
+            queue.w[3][q] = kO;
+            queue.w[4][q] = (int32_t) (uint32_t) (uint64_t) row;
+            queue.w[5][q] = (int32_t) (uint32_t) ((uint64_t) row >> 32);
+         } else {
+            handle(k0[j], k1[j], kS, kO, row);
          }
       }
       __syncthreads();
@@ -1370,13 +1413,17 @@ __global__ void __launch_bounds__(kBlock, 4) scanStarProbeGroupByKernel(const __
 }
 void launchScanStarProbeGroupBy(const StarProbeParams& p, int smCount, cudaStream_t s) {
    size_t dyn;
-   if (p.src.cols.decBytes == 8) {
-      int grid = persistentGrid(scanStarProbeGroupByKernel<8>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
-      scanStarProbeGroupByKernel<8><<<grid, kBlock, dyn, s>>>(p);
-   } else {
-      int grid = persistentGrid(scanStarProbeGroupByKernel<16>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock);
-      scanStarProbeGroupByKernel<16><<<grid, kBlock, dyn, s>>>(p);
+   const int ns = tuning().stagesStar, rpt = tuning().rptStar;
+#define LDB_STAR_CASE(DBV, RPTV, NSV)                                                                                          \
+   if (p.src.cols.decBytes == DBV && rpt == RPTV && ns == NSV) {                                                               \
+      int grid = persistentGrid(scanStarProbeGroupByKernel<DBV, RPTV, NSV>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock, NSV); \
+      scanStarProbeGroupByKernel<DBV, RPTV, NSV><<<grid, kBlock, dyn, s>>>(p);                                                 \
+      return;                                                                                                                  \
    }
+   // the staged columns of a star probe are int32 keys only (the operands are late-materialised): decBytes stays at its default
+   LDB_STAR_CASE(16, 1, 2) LDB_STAR_CASE(16, 2, 2) LDB_STAR_CASE(16, 4, 2) LDB_STAR_CASE(16, 1, 3) LDB_STAR_CASE(16, 2, 3) LDB_STAR_CASE(16, 4, 3)
+   LDB_STAR_CASE(8, 1, 2) LDB_STAR_CASE(8, 2, 2) LDB_STAR_CASE(8, 4, 2) LDB_STAR_CASE(8, 1, 3) LDB_STAR_CASE(8, 2, 3) LDB_STAR_CASE(8, 4, 3)
+#undef LDB_STAR_CASE
 }
 
 // =================================================================================== top-k over the group-join map
@@ -1722,7 +1769,7 @@ __global__ void __launch_bounds__(kBlock, 4) scanPartitionSendKernel(const __gri
          }
          unsigned long long* out = (unsigned long long*) p.dest[dest[j]] + at * words; // peer HBM over NVLink (or local for dest == rank)
          out[0] = packSlot(key[j], second[j]);
-         for (int d = 0; d < p.nDec; d++) out[1 + d] = (unsigned long long) tile.lo64(p.decStage[d], lrs[j]);
+         for (int d = 0; d < p.nDec; d++) out[1 + d] = (unsigned long long) lazyLo64(p.dec, d, rowBase + lrs[j]);
       }
       if (threadIdx.x < kMaxRanks) sCnt[threadIdx.x] = 0;
       __syncthreads();

@@ -83,7 +83,16 @@ constexpr int kBlockThreads = 256;
 constexpr int kRowsPerThreadScan = 2;  // K1/K2: arithmetic-heavy, fewer/larger tiles
 constexpr int kRowsPerThreadProbe = 2; // K4/K5/K8 (1 row/thread with 2x the CTAs measured slower there: 11.8 vs 11.4 ms on Q3)
 constexpr int kRowsPerThreadStar = 1;  // K3/K9 (survivor-queue kernels): small tiles → >= 4 CTAs/SM; they are latency-bound between tiles, not arithmetic-bound
-constexpr int kStages = 2;
+constexpr int kStages = 2;    // default depth of the tile pipeline
+constexpr int kMaxStages = 4; // the probe / build kernels are tile-LATENCY bound with 2 (one copy in flight per CTA): they take 3-4
+// Tuning knobs read once from the environment (experiments; the defaults are the measured best, profiles/r2_stage_sweep.md)
+struct Tuning {
+   int stagesBuild, stagesProbeAgg, stagesProbe2, stagesStar; // TMA pipeline depth of K3 / K5 / K4 / K9
+   int rptBuild;                                              // rows per thread of a K3 tile (1, 2 or 4)
+   int rptStar;                                               // rows per thread of a K9 tile (1, 2 or 4)
+};
+const Tuning& tuning();
+void setTuning(const Tuning& t);
 struct StagedCols {
    int32_t n;
    int32_t tileRows;   // rows per tile = kBlockThreads * rows-per-thread of the kernel
@@ -93,6 +102,16 @@ struct StagedCols {
    const uint8_t* base[kMaxStagedCols];
    int32_t elemBytes[kMaxStagedCols];  // 4 (int32/date32/fsb4) or 16 (decimal128)
    int32_t smemOffset[kMaxStagedCols]; // offset of the column inside a stage
+};
+// LATE-MATERIALISED value columns: a selective probe pipeline (Bloom filter in front, a few percent of the rows survive) streams
+// only its key / filter columns through the TMA tiles; the operands of the aggregate are fetched from HBM by the SURVIVORS
+// (one 32-byte sector per cell) — Q9's lineitem pipeline then moves 16 B/row + 5 % x 3 sectors instead of 60 B/row.  When every
+// row survives the per-warp loads are contiguous, so the traffic is never worse than streaming (only un-prefetched).
+constexpr int kMaxLazyCols = 4;
+struct LazyCols {
+   int32_t n;
+   int32_t elemBytes[kMaxLazyCols]; // 16, or 8 when the HOST batch was narrowed
+   const uint8_t* base[kMaxLazyCols];
 };
 struct ScanSource {
    int64_t nRows;
@@ -136,7 +155,7 @@ struct ProbeAggParams {
    int32_t probeKeyStage;
    JoinTableDev table;
    AggSpec agg;
-   int32_t valueStage[kMaxValueCols];
+   LazyCols values; // operands of the aggregate, in expression order
 };
 
 struct Probe2GroupByParams {
@@ -144,7 +163,7 @@ struct Probe2GroupByParams {
    int32_t keyStageA, keyStageB;
    JoinTableDev tableA, tableB;
    AggSpec agg;
-   int32_t valueStage[kMaxValueCols];
+   LazyCols values;
    GroupTableDev groups; // keyed by the matched payload
 };
 
@@ -154,7 +173,7 @@ struct StarProbeParams {
    ScanSource src;
    int32_t keyStageP0, keyStageP1, keyStageS, keyStageO;
    JoinTableDev tableP, tableS, tableO;
-   int32_t valueStage[3]; // a, b, d
+   LazyCols values;       // a, b, d
    GroupTableDev groups;  // 2 keys, 1 aggregate
 };
 
@@ -189,7 +208,7 @@ struct SendParams {
    int32_t keyStage;
    int32_t secondStage; // staged int32 column, or -1: the probe's payload
    int32_t nDec;
-   int32_t decStage[2];
+   LazyCols dec; // the shipped decimal columns (fetched for the rows that are sent)
    int32_t hasProbe, bloomOnly;
    JoinTableDev probe;
    int32_t probeKeyStage;

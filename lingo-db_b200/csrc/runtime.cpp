@@ -314,6 +314,15 @@ void* ldb_gpu_context_stream(LdbContext* ctx) { return ctx ? (void*) ctx->comput
 int64_t ldb_gpu_context_h2d_bytes(LdbContext* ctx) { return ctx ? ctx->h2dBytes.load() : 0; }
 int64_t ldb_gpu_context_raw_staged_rows(LdbContext* ctx) { return ctx ? ctx->rawStagedRows.load() : 0; }
 int32_t ldb_gpu_effective_cpus(void) { return effectiveCpus(); }
+void ldb_gpu_set_tuning(int32_t stages_build, int32_t stages_probe_agg, int32_t stages_probe2, int32_t stages_star, int32_t rows_per_thread_build) {
+   Tuning t = tuning();
+   t.stagesBuild = stages_build;
+   t.stagesProbeAgg = stages_probe_agg;
+   t.stagesProbe2 = stages_probe2;
+   t.stagesStar = stages_star;
+   t.rptBuild = rows_per_thread_build;
+   setTuning(t);
+}
 int64_t ldb_gpu_launch_count(LdbContext* ctx) { return ctx ? ctx->launches + ctx->stagingLaunches.load() : 0; }
 int ldb_gpu_timer_start(LdbContext* ctx, LdbError* err) {
    return guarded(err, [&] { LDB_CUDA(cudaEventRecord(ctx->timerStart, ctx->compute)); });
@@ -1128,6 +1137,16 @@ AggPlan planAggs(const Resolved& R, const LdbAggDesc* a, int n) {
    p.nAggs = n;
    return p;
 }
+// late-materialised operand columns of a probe pipeline (kernels.h LazyCols): bound per batch, never staged through the tiles
+void bindLazy(LdbTable* t, const LdbBatch& b, const int* cols, int n, LazyCols& out) {
+   out.n = n;
+   for (int i = 0; i < n; i++) {
+      if ((cols[i] < (int) b.validity.size() && b.validity[cols[i]]) || (cols[i] < (int) b.validBytes.size() && b.validBytes[cols[i]]))
+         fail(LDB_ERR_UNSUPPORTED, "column " + t->columns[cols[i]].name + " has NULLs in this batch: use the program pipeline (ldb_gpu_run_program)");
+      out.base[i] = (const uint8_t*) b.data[cols[i]];
+      out.elemBytes[i] = b.elemBytes[cols[i]];
+   }
+}
 LdbState* wantState(LdbState* s, int kind, const char* role) {
    if (!s || s->kind != kind) fail(LDB_ERR_INVALID, std::string("wrong or missing state for ") + role);
    return s;
@@ -1229,7 +1248,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                BuildParams p{};
                p.src.nRows = b.nRows;
                bindFilters(fp, b, p.src.filters);
-               sp.bind(t, b, p.src.cols, kRowsPerThreadStar);
+               sp.bind(t, b, p.src.cols, sink->join.stride == 16 ? kRowsPerThreadStar : tuning().rptBuild); // the pair build keeps 1 row/thread
                p.keyStage = keyStage;
                p.keyStage2 = key2Stage;
                p.payloadStage = payStage;
@@ -1253,8 +1272,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
             if (d->n_probes != 1 || d->probe_states[0] != table) fail(LDB_ERR_INVALID, "probe-aggregate pipelines probe their own sink");
             AggPlan ap = planAggs(R, d->aggs, 1);
             int probeCol = R.col(d->probe_key_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key");
-            int probeStage = sp.add(t, probeCol), valueStage[kMaxValueCols] = {0, 0, 0, 0};
-            for (int v = 0; v < ap.nValueCols; v++) valueStage[v] = sp.add(t, ap.valueCol[v]);
+            int probeStage = sp.add(t, probeCol);
             for (auto& b : t->batches) {
                if (b.nRows == 0) continue;
                ProbeAggParams p{};
@@ -1264,7 +1282,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                p.probeKeyStage = probeStage;
                p.table = table->join;
                p.agg = ap.aggs[0];
-               for (int v = 0; v < ap.nValueCols; v++) p.valueStage[v] = valueStage[v];
+               bindLazy(t, b, ap.valueCol, ap.nValueCols, p.values);
                waitBatch(ctx, b);
                bool ok = true;
                ctx->launch("join_probe_agg", [&] { ok = launchScanProbeAgg(p, ctx->smCount, ctx->compute, &why); });
@@ -1281,8 +1299,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
             AggPlan ap = planAggs(R, d->aggs, 1);
             int ca = R.col(d->probe_key_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key A");
             int cb = R.col(d->probe_key_columns[1], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key B");
-            int stageA = sp.add(t, ca), stageB = sp.add(t, cb), valueStage[kMaxValueCols] = {0, 0, 0, 0};
-            for (int v = 0; v < ap.nValueCols; v++) valueStage[v] = sp.add(t, ap.valueCol[v]);
+            int stageA = sp.add(t, ca), stageB = sp.add(t, cb);
             for (auto& b : t->batches) {
                if (b.nRows == 0) continue;
                Probe2GroupByParams p{};
@@ -1294,7 +1311,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                p.tableA = ta->join;
                p.tableB = tb->join;
                p.agg = ap.aggs[0];
-               for (int v = 0; v < ap.nValueCols; v++) p.valueStage[v] = valueStage[v];
+               bindLazy(t, b, ap.valueCol, ap.nValueCols, p.values);
                p.groups = sink->group;
                if (p.agg.expr == LDB_EXPR_COL || p.agg.expr == LDB_EXPR_ONE) sink->is64Mask |= 1u;
                waitBatch(ctx, b);
@@ -1362,17 +1379,19 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
             base.keyStageP1 = sp.add(t, R.col(d->probe_key2_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key 0 (second)"));
             base.keyStageS = sp.add(t, R.col(d->probe_key_columns[1], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key 1"));
             base.keyStageO = sp.add(t, R.col(d->probe_key_columns[2], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key 2"));
+            int starValueCols[3];
             for (int k = 0; k < 3; k++) {
                int c = R.col(d->aggs[0].columns[k], {LDB_DECIMAL128}, "aggregate operand");
                if (t->columns[c].precision >= 19 || t->columns[c].scale != 2) fail(LDB_ERR_UNSUPPORTED, "aggregate operands must be decimal(p<19, 2) on the GPU path");
-               base.valueStage[k] = sp.add(t, c);
+               starValueCols[k] = c;
             }
             for (auto& b : t->batches) {
                if (b.nRows == 0) continue;
                StarProbeParams p = base;
                p.src.nRows = b.nRows;
                bindFilters(fp, b, p.src.filters);
-               sp.bind(t, b, p.src.cols, kRowsPerThreadStar);
+               sp.bind(t, b, p.src.cols, tuning().rptStar);
+               bindLazy(t, b, starValueCols, 3, p.values);
                p.tableP = tp->join;
                p.tableS = ts->join;
                p.tableO = to->join;
@@ -1401,10 +1420,11 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                base.secondStage = sp.add(t, R.col(d->out_columns[1], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "second tuple column"));
             }
             base.nDec = d->n_out_cols - 2;
+            int sendDecCols[2] = {0, 0};
             for (int k = 0; k < base.nDec; k++) {
                int col = R.col(d->out_columns[2 + k], {LDB_DECIMAL128}, "decimal tuple column");
                if (t->columns[col].precision >= 19) fail(LDB_ERR_UNSUPPORTED, "shipped decimals must have precision < 19");
-               base.decStage[k] = sp.add(t, col);
+               sendDecCols[k] = col;
             }
             const int64_t tupleBytes = 8 * (1 + base.nDec);
             const int64_t region = (int64_t) c->world * d->send_capacity * tupleBytes;
@@ -1422,6 +1442,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                p.src.nRows = b.nRows;
                bindFilters(fp, b, p.src.filters);
                sp.bind(t, b, p.src.cols, kRowsPerThreadProbe);
+               bindLazy(t, b, sendDecCols, base.nDec, p.dec);
                if (probe) p.probe = probe->join;
                waitBatch(ctx, b);
                ctx->launch("partition_send", [&] { launchScanPartitionSend(p, ctx->smCount, ctx->compute); });
