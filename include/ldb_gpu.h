@@ -305,6 +305,21 @@ typedef struct LdbPipelineDesc {
 } LdbPipelineDesc;
 int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* desc, LdbError* err);
 
+/* ------------------------------------------------------------------------------------ serialised steps
+ * One execution step as a DOCUMENT: what a compiler hook (GPUPatternList / handleExecutionStepGPU, SURVEY §8 f1;
+ * SubOpToControlFlow.cpp:4254-4394) emits for a scan pipeline and what rt::GPUPipeline::run(VarLen32 descr) receives, like the
+ * hex-serialised description DataSource::get receives today (DataSourceIteration.cpp:57-88).  JSON:
+ *   {"kind": "scan_groupby", "source": "<table name>", "filters": [{"column", "op", "value" | "values"}], "keys": [...],
+ *    "aggs": [{"expr", "columns"}], "probes": [{"state", "key", "key2"}], "build": {"key", "key2", "payload", "payload_expr", "side"},
+ *    "sink": {"name", "create": {"type": "simple|groupby|join|join_pair|join_direct", ...}}}
+ * Tables are resolved by the name given to ldb_gpu_table_create, states by the names steps gave them (or ldb_gpu_register_state).
+ * tests/golden/plans/*.json hold the five TPC-H plans in this form. */
+int ldb_gpu_step_validate(const char* json, LdbError* err); /* structure only; needs no device */
+int ldb_gpu_run_step(LdbContext* ctx, const char* json, LdbError* err);
+int ldb_gpu_run_step_hex(LdbContext* ctx, const char* hex_json, LdbError* err);
+int ldb_gpu_register_state(LdbContext* ctx, const char* name, LdbState* s, LdbError* err);
+LdbState* ldb_gpu_find_state(LdbContext* ctx, const char* name);
+
 /* ------------------------------------------------------------------------------------ program pipelines (generic)
  * The hand-specialised pipelines above cover the TPC-H hot shapes at HBM speed.  Everything else a scan pipeline of the
  * sub-operator dialect can contain runs through ONE kernel that interprets a register program per row (csrc/program.cu):

@@ -175,6 +175,11 @@ SIGNATURES = {
     "ldb_gpu_join_table_bloom": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64), _E]),
     "ldb_gpu_join_table_topk": (C.c_int, [_P, C.c_int32, C.POINTER(TopKRow), C.POINTER(C.c_int32), _E]),
     "ldb_gpu_run_pipeline": (C.c_int, [_P, C.POINTER(PipelineDesc), _E]),
+    "ldb_gpu_step_validate": (C.c_int, [C.c_char_p, _E]),
+    "ldb_gpu_run_step": (C.c_int, [_P, C.c_char_p, _E]),
+    "ldb_gpu_run_step_hex": (C.c_int, [_P, C.c_char_p, _E]),
+    "ldb_gpu_register_state": (C.c_int, [_P, C.c_char_p, _P, _E]),
+    "ldb_gpu_find_state": (C.c_void_p, [_P, C.c_char_p]),
     "ldb_gpu_run_program": (C.c_int, [_P, C.POINTER(ProgramDesc), _E]),
     "ldb_gpu_hashagg_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(ProgAgg), C.c_int64, C.POINTER(_P), _E]),
     "ldb_gpu_hashagg_count": (C.c_int, [_P, C.POINTER(C.c_int64), _E]),

@@ -87,6 +87,7 @@ struct LdbContext {
    std::vector<LdbState*> states;
    std::vector<LdbTable*> tables;
    std::vector<LdbGraph*> graphs;
+   std::map<std::string, LdbState*> namedStates; // states created / registered through serialised steps (step_json.cpp)
    // staging pool for HOST batches: size → free device buffers
    std::multimap<size_t, void*> stagingFree;
    std::map<void*, size_t> stagingSize;

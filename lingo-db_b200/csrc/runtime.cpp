@@ -660,6 +660,7 @@ void ldb_gpu_state_destroy(LdbState* s) {
    cudaSetDevice(ctx->device);
    cudaStreamSynchronize(ctx->compute);
    ctx->states.erase(std::remove(ctx->states.begin(), ctx->states.end(), s), ctx->states.end());
+   for (auto it = ctx->namedStates.begin(); it != ctx->namedStates.end();) it = it->second == s ? ctx->namedStates.erase(it) : std::next(it);
    destroyState(s);
 }
 int ldb_gpu_simple_state_create(LdbContext* ctx, int32_t n_aggs, LdbState** out, LdbError* err) {
