@@ -102,3 +102,67 @@ def write_ipc(path: str, t: TableData):
         with pa.ipc.new_file(sink, schema) as w:
             for b in batches:
                 w.write_batch(b)
+
+
+# ---- the C++ path (libldb_arrow_io.so, include/ldb_arrow_io.h): file → backend table without Python touching the buffers
+_arrow_lib = None
+
+
+def _lib():
+    import ctypes as C
+
+    from . import build, capi
+    global _arrow_lib
+    if _arrow_lib is None:
+        L = C.CDLL(build.build_arrow_io())
+        P, E = C.c_void_p, C.POINTER(capi.Error)
+        L.ldb_arrow_file_open.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int32, C.POINTER(P), E]
+        L.ldb_arrow_file_num_columns.argtypes = [P]
+        L.ldb_arrow_file_schema.restype = C.POINTER(capi.ColumnSchema)
+        L.ldb_arrow_file_schema.argtypes = [P]
+        L.ldb_arrow_file_num_batches.argtypes = [P]
+        L.ldb_arrow_file_load.argtypes = [P, P, P, C.c_int64, C.POINTER(C.c_int64), E]
+        L.ldb_arrow_file_close.argtypes = [P]
+        _arrow_lib = L
+    return _arrow_lib
+
+
+class ArrowFile:
+    """An open `<table>.arrow` (memory-mapped by Arrow C++).  schema() works without a GPU; load() stages the file into a backend
+    table — the column cache: later pipelines read it from HBM, the file only has to stay open until the table is cleared."""
+
+    def __init__(self, path: str, columns: Optional[List[str]] = None):
+        import ctypes as C
+
+        from . import capi
+        self.L, self.h = _lib(), C.c_void_p()
+        e = capi.Error()
+        arr = (C.c_char_p * max(1, len(columns or [])))(*[c.encode() for c in (columns or [])])
+        capi.check(self.L.ldb_arrow_file_open(path.encode(), arr, len(columns or []), C.byref(self.h), C.byref(e)), e)
+
+    def schema(self) -> List[ColumnSpec]:
+        from . import capi
+        inv = {v: k for k, v in capi.PHYS.items()}
+        s = self.L.ldb_arrow_file_schema(self.h)
+        return [ColumnSpec(s[i].name.decode(), inv[s[i].type], s[i].precision, s[i].scale) for i in range(self.L.ldb_arrow_file_num_columns(self.h))]
+
+    @property
+    def num_batches(self) -> int:
+        return int(self.L.ldb_arrow_file_num_batches(self.h))
+
+    def load(self, ctx, name: str, max_rows_per_batch: int = 1 << 24):
+        """→ runtime.Table staged from the mapped file (ldb_arrow_file_load → ldb_gpu_table_append_batch)."""
+        import ctypes as C
+
+        from . import capi, runtime
+        tab = runtime.Table(ctx, name, self.schema())
+        n, e = C.c_int64(), capi.Error()
+        fn = C.cast(ctx.L.ldb_gpu_table_append_batch, C.c_void_p)
+        capi.check(self.L.ldb_arrow_file_load(self.h, tab.h, fn, max_rows_per_batch, C.byref(n), C.byref(e)), e)
+        tab._keep.append(self)  # the views point into the mapping
+        return tab
+
+    def close(self):
+        if self.h:
+            self.L.ldb_arrow_file_close(self.h)
+            self.h = None

@@ -21,6 +21,7 @@ CXX = os.environ.get("LDB_CXX", "/usr/bin/g++")  # not $CXX: the image exports a
 
 GPU_LIB = os.path.join(HERE, "libldb_gpu.so")
 GEN_LIB = os.path.join(HERE, "libldb_datagen_host.so")
+ARROW_LIB = os.path.join(HERE, "libldb_arrow_io.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -141,8 +142,25 @@ def _build_gpu(verbose=False, force=False, ptxas_verbose=False):
     return GPU_LIB
 
 
+def build_arrow_io(verbose=False, force=False):
+    """libldb_arrow_io.so: Arrow IPC file → backend table (csrc_arrow/), linked against the Arrow C++ that ships inside pyarrow."""
+    with _Lock():
+        import pyarrow
+        pa_dir = os.path.dirname(pyarrow.__file__)
+        src = os.path.join(HERE, "csrc_arrow", "arrow_table_io.cpp")
+        deps = [src, os.path.join(INCLUDE, "ldb_arrow_io.h"), os.path.join(INCLUDE, "ldb_gpu.h")]
+        stamp = _stamp(deps, pyarrow.__version__)
+        if not force and _up_to_date(ARROW_LIB, stamp):
+            return ARROW_LIB
+        libs = [f for f in os.listdir(pa_dir) if f.startswith("libarrow.so.") and f.count(".") == 2]
+        _run([CXX, "-std=c++20", "-O2", "-fPIC", "-shared", "-Wall", "-I", INCLUDE, "-I", os.path.join(pa_dir, "include"), "-o", ARROW_LIB, src,
+              "-L", pa_dir, "-l:" + sorted(libs)[0], "-Wl,-rpath," + pa_dir], verbose)
+        open(ARROW_LIB + ".stamp", "w").write(stamp)
+        return ARROW_LIB
+
+
 def build_all(verbose=False, force=False):
-    return build_datagen_host(verbose, force), build_gpu(verbose, force)
+    return build_datagen_host(verbose, force), build_gpu(verbose, force), build_arrow_io(verbose, force)
 
 
 if __name__ == "__main__":

@@ -81,3 +81,62 @@ def test_gpu_queries_on_arrow_files(tmp_path, gpu_ctx, oracle):
     assert g.q1() == oracle.q1(oh["lineitem"])[0]
     assert g.q3() == oracle.q3(oh["customer"], oh["orders"], oh["lineitem"])[0]
     assert g.q9() == oracle.q9(oh["part"], oh["supplier"], oh["lineitem"], oh["partsupp"], oh["orders"], oh["nation"])[0]
+
+
+def test_cpp_reader_opens_the_references_file_format(tmp_path):
+    """libldb_arrow_io.so (Arrow C++ RecordBatchFileReader over a memory map, like LingoDBTable::loadTable): schema and batch count
+    without a device; nullable and float columns are accepted (the program pipeline reads them)."""
+    td = datagen.lineitem(datagen.scale(0.01, seed=3), chunk_rows=20_000)
+    path = str(tmp_path / "lineitem.arrow")
+    arrow_io.write_ipc(path, td)
+    f = arrow_io.ArrowFile(path, ["l_orderkey", "l_quantity", "l_shipdate", "l_returnflag"])
+    assert [(c.name, c.phys, c.precision, c.scale) for c in f.schema()] == [("l_orderkey", "int32", 0, 0), ("l_quantity", "decimal128", 12, 2), ("l_returnflag", "fsb4", 0, 0), ("l_shipdate", "date32", 0, 0)]
+    assert f.num_batches == len(td.chunks)
+    f.close()
+    b = pa.RecordBatch.from_arrays([pa.array([1, None, 3], pa.int32()), pa.array([0.5, 1.5, None], pa.float64()), pa.array(["a", None, "c"])], names=["x", "y", "s"])
+    p2 = str(tmp_path / "n.arrow")
+    with pa.OSFile(p2, "wb") as sink, pa.ipc.new_file(sink, b.schema) as w:
+        w.write_batch(b)
+    f = arrow_io.ArrowFile(p2)
+    assert [(c.name, c.phys) for c in f.schema()] == [("x", "int32"), ("y", "float64"), ("s", "utf8")]
+    f.close()
+    from lingodb_b200 import capi
+    with pytest.raises(capi.LdbRuntimeError):
+        arrow_io.ArrowFile(str(tmp_path / "missing.arrow"))
+
+
+@pytest.mark.gpu
+def test_cpp_reader_stages_files_and_the_table_is_the_column_cache(tmp_path, gpu_ctx, oracle):
+    """File → ldb_arrow_file_load → compressed staging → Q1/Q6 == oracle; a second query reads the staged table (no new H2D);
+    a file with NULLs goes through the program pipeline."""
+    from lingodb_b200 import program as P, runtime
+    t = datagen.tpch(0.05, seed=8, chunk_rows=100_000)
+    path = str(tmp_path / "lineitem.arrow")
+    arrow_io.write_ipc(path, t["lineitem"])
+    f = arrow_io.ArrowFile(path)
+    tab = f.load(gpu_ctx, "lineitem")
+    oh = oracle.table(t["lineitem"])
+    tp = runtime.Tpch(gpu_ctx, {"lineitem": tab})
+    assert tp.q1() == oracle.q1(oh)[0]
+    h2d = int(gpu_ctx.L.ldb_gpu_context_h2d_bytes(gpu_ctx.h))
+    assert tp.q6() == oracle.q6(oh)[0]
+    assert int(gpu_ctx.L.ldb_gpu_context_h2d_bytes(gpu_ctx.h)) == h2d  # column-cache hit: nothing crossed the link again
+    tab.clear()
+    f.close()
+    x = np.arange(100_000, dtype=np.int32)
+    arr = pa.array(x, mask=(x % 7 == 0))
+    b = pa.RecordBatch.from_arrays([arr, pa.array((x % 5).astype(np.int32))], names=["x", "g"])
+    p2 = str(tmp_path / "n.arrow")
+    with pa.OSFile(p2, "wb") as sink, pa.ipc.new_file(sink, b.schema) as w:
+        w.write_batch(b.slice(0, 60_001))
+        w.write_batch(b.slice(60_001))
+    f = arrow_io.ArrowFile(p2)
+    tn = f.load(gpu_ctx, "n")
+    st = P.group_by(gpu_ctx, tn, [("col", "g")], [("sum", ("col", "x")), ("count", ("col", "x")), ("count_star", None)], expected_groups=16)
+    got = P.decode_groups(P.read_groups(gpu_ctx, st, 16), 1, 3)
+    for g in range(5):
+        m = (x % 5 == g) & (x % 7 != 0)
+        assert got[(g,)] == [int(x[m].sum()), int(m.sum()), int((x % 5 == g).sum())]
+    gpu_ctx.L.ldb_gpu_state_destroy(st)
+    tn.clear()
+    f.close()
