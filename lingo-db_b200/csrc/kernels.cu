@@ -368,6 +368,9 @@ __device__ __forceinline__ int32_t directLoad(const JoinTableDev& t, int32_t key
 }
 // probe (SubOpToControlFlow.cpp:2558-2586 + chain walk :2254-2313): visit every entry with the key.
 // Split in two so a thread can put the Bloom loads of ALL its rows in flight before it consumes the first one.
+// Bloom words are read through the read-only path with the default L1 policy: an experiment with L1::no_allocate for large filters
+// (to protect small ones in L1) cost 15-45 % on every probe kernel (profiles/r2_stage_sweep.md) — the words of hot blocks do get reused.
+__device__ __forceinline__ uint32_t ldBloom(const JoinTableDev& t, uint32_t idx) { return __ldg(t.bloom + idx); }
 struct BloomProbe {
    uint64_t h;
    uint32_t word, bits;
@@ -377,7 +380,7 @@ __device__ __forceinline__ BloomProbe bloomPrefetch(const JoinTableDev& t, int32
    BloomProbe b;
    b.h = hashI32(key);
    b.bits = t.bloom ? bloomBits(b.h) : 0u;
-   b.word = (t.bloom && wanted) ? __ldg(&t.bloom[(uint32_t) (b.h >> 32) & t.bloomMask]) : (wanted ? ~0u : 0u);
+   b.word = (t.bloom && wanted) ? ldBloom(t, (uint32_t) (b.h >> 32) & t.bloomMask) : (wanted ? ~0u : 0u);
    if (!wanted) b.bits = 1u; // word == 0 → mayContain() false
    return b;
 }
@@ -402,7 +405,7 @@ __device__ __forceinline__ void joinProbe(const JoinTableDev& t, int32_t key, co
    const uint64_t h = hashI32(key);
    if (t.bloom) {
       const uint32_t bits = bloomBits(h);
-      if ((__ldg(&t.bloom[(uint32_t) (h >> 32) & t.bloomMask]) & bits) != bits) return;
+      if ((ldBloom(t, (uint32_t) (h >> 32) & t.bloomMask) & bits) != bits) return;
    }
    uint64_t s = h & t.mask;
    const uint64_t limit = t.mask < kMaxProbe ? t.mask + 1 : kMaxProbe;
@@ -462,7 +465,7 @@ __device__ __forceinline__ BloomProbe pairBloomPrefetch(const JoinTableDev& t, i
    BloomProbe b;
    b.h = hashPair(k0, k1);
    b.bits = t.bloom ? bloomBits(b.h) : 0u;
-   b.word = (t.bloom && wanted) ? __ldg(&t.bloom[(uint32_t) (b.h >> 32) & t.bloomMask]) : (wanted ? ~0u : 0u);
+   b.word = (t.bloom && wanted) ? ldBloom(t, (uint32_t) (b.h >> 32) & t.bloomMask) : (wanted ? ~0u : 0u);
    if (!wanted) b.bits = 1u;
    return b;
 }
@@ -624,14 +627,15 @@ static int envInt(const char* name, int dflt, int lo, int hi) {
 static Tuning& tuningStorage() {
    static Tuning t = [] {
       Tuning x;
-      // measured at SF100 (profiles/r2_stage_sweep.md): deeper pipelines cost resident CTAs and the probe kernels lose more from that
-      // than they gain (K9 9.5 / 10.8 / 12.5 ms at 2 / 3 / 4 stages); only the build kernel likes 3 stages with 2 rows per thread
+      // measured at SF100 (profiles/r2_stage_sweep.md).  With every operand staged (60 B/row tiles) deeper pipelines cost resident CTAs
+      // and lost (K9 9.5 / 10.8 / 12.5 ms at 2 / 3 / 4 stages); with late-materialised operands the tiles are 8-16 B/row and K4 / K5
+      // gain from a third stage (5.0 -> 4.3 ms, 4.2 -> 3.7 ms); K9 is best with 2 rows per thread and 2 stages (5.7 ms; 9.8 with 4 rows)
       x.stagesBuild = envInt("LDB_STAGES_BUILD", 3, 2, kMaxStages);
-      x.stagesProbeAgg = envInt("LDB_STAGES_PROBE_AGG", 2, 2, kMaxStages);
-      x.stagesProbe2 = envInt("LDB_STAGES_PROBE2", 2, 2, kMaxStages);
+      x.stagesProbeAgg = envInt("LDB_STAGES_PROBE_AGG", 3, 2, kMaxStages);
+      x.stagesProbe2 = envInt("LDB_STAGES_PROBE2", 3, 2, kMaxStages);
       x.stagesStar = envInt("LDB_STAGES_STAR", 2, 2, kMaxStages);
       x.rptBuild = envInt("LDB_RPT_BUILD", 2, 1, 4);
-      x.rptStar = envInt("LDB_RPT_STAR", 4, 1, 4);
+      x.rptStar = envInt("LDB_RPT_STAR", 2, 1, 4);
       if (x.rptStar == 3) x.rptStar = 2;
       if (x.rptBuild == 3) x.rptBuild = 2;
       return x;
@@ -1092,7 +1096,7 @@ __device__ __forceinline__ bool bloomMayContain(const JoinTableDev& t, int32_t k
    if (!t.bloom) return true;
    const uint64_t h = hashI32(key);
    const uint32_t bits = bloomBits(h);
-   return (__ldg(&t.bloom[(uint32_t) (h >> 32) & t.bloomMask]) & bits) == bits;
+   return (ldBloom(t, (uint32_t) (h >> 32) & t.bloomMask) & bits) == bits;
 }
 // Two instantiations: MULTI = false (no probe, Bloom-only semi-join, or a unique-key probe: at most one output per row) claims
 // the output range of a whole TILE with one global atomic (CTA-wide prefix sum of the emit flags) — with a single counter,

@@ -19,7 +19,7 @@ def main():
     tp = runtime.Tpch(ctx, tabs)
     fams = ["join_build", "join_probe_agg", "join_probe2_groupby", "join_star_probe_groupby", "join_topk", "table_init", "column_range"]
     base = {}
-    configs = [(2, 2, 2, 2, 1), (3, 3, 3, 3, 4), (4, 4, 4, 4, 4), (3, 3, 3, 3, 2), (2, 2, 2, 2, 4), (3, 2, 2, 2, 1), (4, 3, 3, 4, 2)]
+    configs = [(3, 3, 3, 2, 2), (2, 2, 2, 2, 1), (3, 2, 2, 2, 2), (3, 4, 4, 3, 2)]
     if len(sys.argv) > 2:
         configs = [tuple(int(x) for x in c.split(":")) for c in sys.argv[2].split(",")]
     for cfg in configs:
