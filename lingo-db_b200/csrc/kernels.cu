@@ -19,6 +19,8 @@
 #include "kernels.h"
 #include "../../include/ldb_gpu.h"
 
+#include <map>
+#include <mutex>
 #include <string>
 
 namespace ldb {
@@ -676,6 +678,14 @@ __global__ void __launch_bounds__(kBlock, 2) scanGroupByKernel(const __grid_cons
    __shared__ __align__(8) TileBarriers barsStorage;
    TileBarriers* bars = &barsStorage;
 
+   // self-timing (two words behind the table's error word): max(~start), max(end) of %globaltimer over the CTAs — the kernel's
+   // duration without event nodes, so that a captured query (CUDA graph) still reports its kernel time (runtime.cpp groupby_read)
+   unsigned long long* const selfTime = (unsigned long long*) (p.table.error) + 1;
+   if (threadIdx.x == 0) {
+      unsigned long long t0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      atomicMax(selfTime, ~t0);
+   }
    for (int i = threadIdx.x; i < LG * N * 2; i += kBlock) (&sAcc[0][0][0])[i] = 0;
    if (threadIdx.x == 0) {
       sCount = NK == 0 ? 1 : 0;
@@ -800,6 +810,12 @@ __global__ void __launch_bounds__(kBlock, 2) scanGroupByKernel(const __grid_cons
          atomicAdd128(dst, dst + 1, s); // 64-bit aggregates keep hi == 0 and are read back as i64
       }
    }
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      atomicMax(selfTime + 1, t1);
+   }
 }
 
 // ---- signature registry
@@ -817,8 +833,19 @@ static std::string signature(const GroupByParams& p) {
 template <class K>
 static int persistentGrid(K kernel, const StagedCols& sc, int64_t nRows, int smCount, size_t* dynBytes, int threads = kThreads, int stages = kStages) {
    *dynBytes = sc.useTma ? (size_t) stages * sc.stageBytes : 0;
-   // static + dynamic shared memory beyond 48 KB needs the opt-in (K9 carries 12 KB of static group slots), so always ask
-   if (*dynBytes > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) *dynBytes);
+   // static + dynamic shared memory beyond 48 KB needs the opt-in (K9 carries 12 KB of static group slots), so always ask — but only
+   // ever RAISE a kernel's limit: several contexts of one process (threads) launch the same kernel with different tile sizes, and
+   // lowering the attribute between another thread's query and its launch made that launch fail with "invalid argument"
+   if (*dynBytes > 0) {
+      static std::mutex m;
+      static std::map<const void*, size_t> granted;
+      std::lock_guard<std::mutex> lock(m);
+      size_t& g = granted[(const void*) kernel];
+      if (*dynBytes > g) {
+         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) *dynBytes);
+         g = *dynBytes;
+      }
+   }
    int perSm = 1;
    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, threads, *dynBytes);
    if (perSm < 1) perSm = 1;

@@ -214,10 +214,10 @@ void LdbContext::launchCaptured(const char* family, const std::function<void()>&
    g->kernelsPerLaunch++;
    static const bool timers = [] {
       const char* e = getenv("LDB_GRAPH_TIMERS");
-      return !(e && e[0] == '0');
+      return e && e[0] == '1';
    }();
-   if (!timers) { // replay-latency experiments: no per-kernel event nodes in the graph
-      fn();
+   if (!timers) { // default: no event-record nodes in the graph (each costs ~10-20 us of replay latency); the group-by scan kernel
+      fn();       // times itself through %globaltimer instead (LDB_GRAPH_TIMERS=1 brings the event nodes back for every kernel)
       return;
    }
    cudaEvent_t a = nullptr, b = nullptr;
@@ -645,8 +645,10 @@ static LdbState* newGroupState(LdbContext* ctx, int kind, int nKeys, int nAggs, 
    g.nKeys = nKeys;
    g.nAggs = nAggs;
    // one allocation, one memset: the exchange image (state | keys | acc) followed by the error word
+   // … then {error word, pad, self-timing words max(~start), max(end)} — kernels.cu scanGroupByKernel
    const size_t image = groupImageBytes(g.capacity);
-   uint8_t* base = (uint8_t*) devAlloc(s, image + 16, 0);
+   uint8_t* base = (uint8_t*) devAlloc(s, image + 32, 0);
+   s->selfTimed = ctx->capturing != nullptr; // a state created inside a captured query reports its kernel time through the table
    g.state = (int32_t*) base;
    g.keys = (int32_t*) (base + (size_t) g.capacity * 4);
    g.acc = (unsigned long long*) (base + (size_t) g.capacity * 4 + (size_t) g.capacity * kMaxKeys * 4);
@@ -695,12 +697,20 @@ int ldb_gpu_groupby_read(LdbState* s, LdbGroupRow* rows, int32_t max_rows, int32
       const size_t image = groupImageBytes(g.capacity);
       std::vector<uint8_t> pageable;
       uint8_t* host = (uint8_t*) s->ctx->scratch(); // pinned: the copy is asynchronous, the only wait is the one below
-      if (image + 16 > LdbContext::kPinnedScratchBytes) {
-         pageable.resize(image + 16);
+      if (image + 32 > LdbContext::kPinnedScratchBytes) {
+         pageable.resize(image + 32);
          host = pageable.data();
       }
-      LDB_CUDA(cudaMemcpyAsync(host, g.state, image + 16, cudaMemcpyDeviceToHost, s->ctx->compute));
+      LDB_CUDA(cudaMemcpyAsync(host, g.state, image + 32, cudaMemcpyDeviceToHost, s->ctx->compute));
       s->ctx->syncStream(s->ctx->compute);
+      if (s->ctx->timing && s->selfTimed) { // captured queries carry no event nodes: the scan kernel timed itself (%globaltimer)
+         const unsigned long long inv = *(const unsigned long long*) (host + image + 8), end = *(const unsigned long long*) (host + image + 16);
+         if (inv && end > ~inv) {
+            auto& acc = s->ctx->timers["scan_groupby"];
+            acc.totalMs += (double) (end - ~inv) / 1e6;
+            acc.launches++;
+         }
+      }
       if (*(const int32_t*) (host + image)) fail(LDB_ERR_CAPACITY, "group-by table overflow: more groups than the declared capacity");
       const int32_t* st = (const int32_t*) host;
       const int32_t* keys = (const int32_t*) (host + (size_t) g.capacity * 4);
