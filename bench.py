@@ -316,7 +316,7 @@ def run_ours(args):
                     comm.allmerge(prepared["state"])
                 prepared["graph"] = ctx.graph_end()
             prepared["graph"].launch()
-            return tp.q1_finish(prepared["state"])
+            return tp.q1_finish(prepared["state"], lazy=True)  # C rows in host memory; python dicts are built when they are compared
         st = tp.q1_partial()
         if world > 1:
             if args.merge == "peer":
@@ -352,7 +352,7 @@ def run_ours(args):
             for k, v in part.items():
                 cur = merged.get(k, (0, 0, 0, 0, 0))
                 merged[k] = tuple(a + b for a, b in zip(cur, v))
-        got_rows = step_resident()
+        got_rows = list(step_resident())
         if q1_sums(got_rows) != merged:
             raise SystemExit(f"PARITY FAILURE (Q1 resident, rank {rank}): CUDA {q1_sums(got_rows)} != oracle {merged}")
         for r in got_rows:  # avg = (sum * 10^19) sdiv count, recomputed from the merged exact sums
