@@ -313,7 +313,7 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* desc, LdbError*
  *    "aggs": [{"expr", "columns"}], "probes": [{"state", "key", "key2"}], "build": {"key", "key2", "payload", "payload_expr", "side"},
  *    "sink": {"name", "create": {"type": "simple|groupby|join|join_pair|join_direct", ...}}}
  * Tables are resolved by the name given to ldb_gpu_table_create, states by the names steps gave them (or ldb_gpu_register_state).
- * tests/golden/plans/*.json hold the five TPC-H plans in this form. */
+ * tests/golden/plans/ holds the five TPC-H plans in this form (q1.json … q9.json). */
 int ldb_gpu_step_validate(const char* json, LdbError* err); /* structure only; needs no device */
 int ldb_gpu_run_step(LdbContext* ctx, const char* json, LdbError* err);
 int ldb_gpu_run_step_hex(LdbContext* ctx, const char* hex_json, LdbError* err);
@@ -478,6 +478,8 @@ struct LdbGenLineitemCols;
 struct LdbGenOrdersCols;
 struct LdbGenCustomerCols;
 struct LdbGenSupplierCols;
+struct LdbGenPartCols;
+struct LdbGenPartsuppCols;
 int ldb_gpu_datagen_lineitem(LdbContext* ctx, const struct LdbGenScale* g, int64_t row_begin, int64_t n_rows, const struct LdbGenLineitemCols* dev_cols, LdbError* err);
 int ldb_gpu_datagen_orders(LdbContext* ctx, const struct LdbGenScale* g, int64_t row_begin, int64_t n_rows, const struct LdbGenOrdersCols* dev_cols, LdbError* err);
 int ldb_gpu_datagen_customer_fixed(LdbContext* ctx, const struct LdbGenScale* g, int64_t row_begin, int64_t n_rows, const struct LdbGenCustomerCols* dev_cols, int32_t* dev_seg_lengths, LdbError* err);

@@ -97,3 +97,17 @@ def test_q9_shaped_group_images_merge_on_the_host():
     for k, v in r0 + r1:
         want[k] = (want.get(k, 0) + v[0]) % (1 << 128)
     assert {k: v[0] % (1 << 128) for k, v in merged.items()} == want
+
+
+def test_repartitioned_q5_heap_layout_is_a_pure_function_of_the_cardinalities():
+    """ldb_tpch_q5_repartitioned_heap_bytes (csrc/tpch_plans.cpp q5Layout): every rank derives the same symmetric-heap layout from
+    (orders, lineitem, world) alone — no device needed; the receive sub-regions shrink with world^2, the Bloom filter does not."""
+    from lingodb_b200 import capi
+    L = capi.lib()
+    n_o, n_l = 150_000_000, 600_000_004
+    sizes = {w: int(L.ldb_tpch_q5_repartitioned_heap_bytes(n_o, n_l, w)) for w in (1, 2, 4, 8)}
+    assert all(v % 256 == 0 and v > 0 for v in sizes.values())
+    assert sizes[1] > sizes[2] > sizes[4] > sizes[8] > 16 << 20  # the 16 MiB Bloom filter of the global orders key set stays
+    per_rank_lineitem_region = lambda w: w * (n_l // 10 // (w * w) + 8192) * 24
+    assert abs((sizes[1] - sizes[8]) - (per_rank_lineitem_region(1) - per_rank_lineitem_region(8))) < 64 << 20
+    assert int(L.ldb_tpch_q5_repartitioned_heap_bytes(1500, 6000, 2)) < 4 << 20
