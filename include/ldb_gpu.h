@@ -252,11 +252,17 @@ enum LdbPipelineKind {
    LDB_PIPE_SCAN_STAR_PROBE_GROUPBY = 7,
    /* K10 scan → filters → [probe | Bloom-only semi-join] → radix partition by h64(key) across the ranks of `comm` → tuples stored
     *     straight into the DESTINATION rank's receive region over NVLink (fused partition + exchange; multi-GPU joins).
-    *     out_columns[0] = partition/join key (int32), out_columns[1] = second int32 column or "$payload", out_columns[2..3] =
+    *     out_columns[0] = partition/join key (int32), out_columns[1] = second int32 column or "$payload" (build_payload_expr =
+    *     LDB_PAYLOAD_YEAR ships extract(year from that date32 column) instead), out_columns[2..3] =
     *     decimal(p<19) columns shipped as their low 8 bytes.  Tuple = 1 + (n_out_cols - 2) eight-byte words.  The receive region of
     *     every rank is heap[send_offset, + world * send_capacity * tuple bytes): sub-region s belongs to source rank s.
     *     send_cursors_offset: heap offset of 16 uint64 (zeroed by the caller): [d] = tuples sent to rank d, [8] = overflow flag. */
-   LDB_PIPE_SCAN_PARTITION_SEND = 8
+   LDB_PIPE_SCAN_PARTITION_SEND = 8,
+   /* K11 scan → filters → probe 0 (composite key, int64 payload c; Bloom first) → probe 1 (foreign key → int32 payload g) → the row's
+    *     a * (1 - b) - c * d (aggs[0] = LDB_EXPR_MUL_1MINUS_MINUS_PAYMUL) is shipped as {out_columns[0] : 32 | g : 32, lo, hi} (24 bytes)
+    *     to the rank that owns h64(out_columns[0]) — the probe side of a star join whose LAST build side is hash-partitioned across
+    *     the ranks (Q9's orders).  comm / send_* as for K10; the receiver runs ldb_gpu_probe_received_groupby2. */
+   LDB_PIPE_SCAN_STAR_PROBE_SEND = 9
 };
 /* inline payload of a K3 build: the column's value, or extract(year from <date32 column>) (DateRuntime::extractYear) */
 enum LdbPayloadExpr { LDB_PAYLOAD_COLUMN = 0, LDB_PAYLOAD_YEAR = 1 };
@@ -458,6 +464,8 @@ int ldb_gpu_comm_publish_counts(LdbComm* comm, int64_t cursors_offset, int64_t c
 int ldb_gpu_join_table_insert_received(LdbState* table, LdbComm* comm, int64_t recv_offset, int64_t capacity, int64_t counts_offset, LdbError* err);
 /* received {keyA:32 | keyB:32, a, b} tuples → probe A, probe B, payloads equal → group by payload → SUM(a * (1 - b)) (decimal scale `scale`) */
 int ldb_gpu_probe_received_groupby(LdbState* table_a, LdbState* table_b, LdbState* groups, LdbComm* comm, int64_t recv_offset, int64_t capacity, int64_t counts_offset, int32_t scale, LdbError* err);
+/* received {key:32 | g0:32, lo, hi} tuples (K11) → probe `table` on key (payload = g1) → group by (g0, g1) → SUM of the shipped i128 */
+int ldb_gpu_probe_received_groupby2(LdbState* table, LdbState* groups, LdbComm* comm, int64_t recv_offset, int64_t capacity, int64_t counts_offset, LdbError* err);
 /* a join table whose Bloom filter lives in the symmetric heap at bloom_offset (so the ranks can OR their partitions' filters
  * together with ldb_gpu_comm_or_reduce); *bloom_bytes = size of the filter (call with out == NULL to query it for expected_rows) */
 int ldb_gpu_join_table_create_shared_bloom(LdbContext* ctx, int64_t expected_rows, int32_t unique_keys, LdbComm* comm, int64_t bloom_offset, int64_t* bloom_bytes, LdbState** out, LdbError* err);

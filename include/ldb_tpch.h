@@ -80,6 +80,16 @@ int64_t ldb_tpch_q5_repartitioned_heap_bytes(int64_t n_orders_total, int64_t n_l
 int ldb_tpch_q5_repartitioned(LdbContext* ctx, const LdbTpchTables* t, struct LdbComm* comm, const char* region_name, const char* date_ge, const char* date_lt,
                               int64_t n_orders_total, int64_t n_lineitem_total, LdbQ5Row* rows /* 25 */, int32_t* n_rows, LdbQ5ShuffleStats* stats, LdbError* err);
 
+/* Q9 with orders HASH-PARTITIONED across the ranks of `comm` (BASELINE.json config 4: "large build side … NVLink shuffle"): `t` holds
+ * this rank's shard of orders and of lineitem (ANY split — the join is not assumed co-partitioned) and full copies of part, partsupp,
+ * supplier (the composite-key and the supplier tables are built on every rank).  {o_orderkey, year(o_orderdate)} tuples go to the
+ * owner of h64(o_orderkey) (K10), every rank builds its orders partition; lineitem rows that survive the partsupp probe ship their
+ * contribution {l_orderkey | nation, amount} to the same owner (K11), which probes its partition for the year and aggregates; the
+ * 175-group tables are all-merged.  stats: orders_* = orders tuples, lineitem_* = lineitem tuples (24 B each). */
+int64_t ldb_tpch_q9_repartitioned_heap_bytes(int64_t n_orders_total, int64_t n_lineitem_total, int32_t world);
+int ldb_tpch_q9_repartitioned(LdbContext* ctx, const LdbTpchTables* t, struct LdbComm* comm, const char* name_contains, int64_t n_orders_total, int64_t n_lineitem_total,
+                              LdbQ9Row* rows /* max_rows */, int32_t max_rows, int32_t* n_rows, LdbQ5ShuffleStats* stats, LdbError* err);
+
 #ifdef __cplusplus
 }
 #endif

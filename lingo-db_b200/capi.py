@@ -15,7 +15,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 OPS = {"=": 0, "!=": 1, "<": 2, "<=": 3, ">": 4, ">=": 5, "notnull": 6, "in": 7, "contains": 8}
 EXPR = {"col": 0, "mul": 1, "mul_1minus": 2, "mul_1minus_1plus": 3, "one": 4, "mul_1minus_minus_paymul": 5}
 PIPE = {"scan_reduce": 1, "scan_groupby": 2, "scan_build": 3, "scan_probe_agg": 4, "scan_probe2_groupby": 5, "scan_materialize": 6,
-        "scan_star_probe_groupby": 7, "scan_partition_send": 8}
+        "scan_star_probe_groupby": 7, "scan_partition_send": 8, "scan_star_probe_send": 9}
 PAYLOAD_EXPR = {"column": 0, "year": 1}
 MAX_AGGS, MAX_KEYS, MAX_SIDE = 8, 2, 2
 
@@ -206,6 +206,7 @@ SIGNATURES = {
     "ldb_gpu_comm_publish_counts": (C.c_int, [_P, C.c_int64, C.c_int64, _E]),
     "ldb_gpu_join_table_insert_received": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _E]),
     "ldb_gpu_probe_received_groupby": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _E]),
+    "ldb_gpu_probe_received_groupby2": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _E]),
     "ldb_gpu_join_table_create_shared_bloom": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, C.POINTER(C.c_int64), C.POINTER(_P), _E]),
     "ldb_gpu_comm_or_reduce": (C.c_int, [_P, C.c_int64, C.c_int64, _E]),
     "ldb_gpu_comm_check": (C.c_int, [_P, _E]),
@@ -232,6 +233,9 @@ SIGNATURES = {
     "ldb_tpch_q5": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(Q5Row), C.POINTER(C.c_int32), _E]),
     "ldb_tpch_q5_repartitioned_heap_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int32]),
     "ldb_tpch_q5_repartitioned": (C.c_int, [_P, C.POINTER(TpchTables), _P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, C.c_int64, C.POINTER(Q5Row), C.POINTER(C.c_int32),
+                                            C.POINTER(Q5ShuffleStats), _E]),
+    "ldb_tpch_q9_repartitioned_heap_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int32]),
+    "ldb_tpch_q9_repartitioned": (C.c_int, [_P, C.POINTER(TpchTables), _P, C.c_char_p, C.c_int64, C.c_int64, C.POINTER(Q9Row), C.c_int32, C.POINTER(C.c_int32),
                                             C.POINTER(Q5ShuffleStats), _E]),
     "ldb_tpch_q9_partial": (C.c_int, [_P, C.POINTER(TpchTables), C.c_char_p, C.POINTER(_P), _E]),
     "ldb_tpch_q9_finish": (C.c_int, [_P, C.POINTER(Q9Row), C.c_int32, C.POINTER(C.c_int32), _E]),

@@ -1767,6 +1767,7 @@ __global__ void __launch_bounds__(kBlock, 4) scanPartitionSendKernel(const __gri
          bool ok = valid && evalFilters<IN>(p.src.filters, tile, lrs[j], rowBase + lrs[j]);
          key[j] = tile.i32(p.keyStage, lrs[j]);
          second[j] = p.secondStage >= 0 ? tile.i32(p.secondStage, lrs[j]) : 0;
+         if (p.secondYear) second[j] = yearOfDays(second[j]);
          if (ok && p.hasProbe) {
             const int32_t pk = tile.i32(p.probeKeyStage, lrs[j]);
             if (p.bloomOnly) {
@@ -1816,6 +1817,116 @@ void launchScanPartitionSend(const SendParams& p, int smCount, cudaStream_t s) {
       scanPartitionSendKernel<16><<<grid, kBlock, dyn, s>>>(p);
    }
 }
+// =================================================================================== K11 star probe → peer store
+template <int DB, int RPT>
+__global__ void __launch_bounds__(kBlock, 4) scanStarProbeSendKernel(const __grid_constant__ StarSendParams p) {
+   constexpr bool IN = true;
+   __shared__ __align__(8) TileBarriers barsStorage;
+   __shared__ StarQueue queue;
+   TileBarriers* bars = &barsStorage;
+   if (threadIdx.x == 0) queue.count = 0;
+   __syncthreads();
+   const int64_t one = 100;
+   auto handle = [&](int32_t k0, int32_t k1, int32_t kS, int32_t kO, int64_t row) {
+      const uint64_t hP = hashPair(k0, k1), hS = p.tableS.direct ? 0 : hashI32(kS);
+      const ulonglong2 eP = __ldg((const ulonglong2*) slotPtr(p.tableP, hP & p.tableP.mask));
+      const unsigned long long eS = fkFirstSlot(p.tableS, kS, hS);
+      const int64_t a = lazyLo64(p.values, 0, row), b = lazyLo64(p.values, 1, row), d = lazyLo64(p.values, 2, row);
+      const int dest = partOf(kO, p.world);
+      pairProbeFrom(p.tableP, k0, k1, hP, eP, [&](int64_t c) {
+         fkProbeFrom(p.tableS, kS, hS, eS, [&](int32_t g0) {
+            const i128 v = sub128(mul64x64(a, one - b), mul64x64(c, d));
+            // lanes of the warp that ship to the same rank share one claim of the (device-local) cursor
+            const unsigned peers = __match_any_sync(__activemask(), dest);
+            const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+            unsigned long long at = 0;
+            if (lane == leader) at = atomicAdd(&p.cursors[dest], (unsigned long long) __popc(peers));
+            at = __shfl_sync(peers, at, leader) + __popc(peers & ((1u << lane) - 1));
+            if (at >= (unsigned long long) p.capacity) {
+               atomicExch(p.error, 6);
+               return;
+            }
+            unsigned long long* out = (unsigned long long*) p.dest[dest] + at * 3;
+            out[0] = packSlot(kO, g0);
+            out[1] = (unsigned long long) v.lo;
+            out[2] = (unsigned long long) v.hi;
+         });
+      });
+   };
+   auto process = [&](int q) {
+      handle(queue.w[0][q], queue.w[1][q], queue.w[2][q], queue.w[3][q], (int64_t) (((uint64_t) (uint32_t) queue.w[5][q] << 32) | (uint32_t) queue.w[4][q]));
+   };
+   forEachTileUniform<RPT, DB, 2>(p.src.cols, p.src.nRows, dynSmem, bars, [&](const auto& tile, int64_t rowBase, int rows) {
+      int32_t k0[RPT], k1[RPT];
+      int lrs[RPT];
+      BloomProbe bp[RPT];
+#pragma unroll
+      for (int j = 0; j < RPT; j++) {
+         const int lrRaw = j * kBlock + threadIdx.x;
+         const bool valid = lrRaw < rows;
+         lrs[j] = valid ? lrRaw : 0;
+         const bool ok = valid && evalFilters<IN>(p.src.filters, tile, lrs[j], rowBase + lrs[j]);
+         k0[j] = tile.i32(p.keyStageP0, lrs[j]);
+         k1[j] = tile.i32(p.keyStageP1, lrs[j]);
+         bp[j] = pairBloomPrefetch(p.tableP, k0[j], k1[j], ok);
+      }
+#pragma unroll
+      for (int j = 0; j < RPT; j++) {
+         if (!bp[j].mayContain()) continue;
+         const int32_t kS = tile.i32(p.keyStageS, lrs[j]), kO = tile.i32(p.keyStageO, lrs[j]);
+         const int64_t row = rowBase + lrs[j];
+         const int q = atomicAdd(&queue.count, 1);
+         if (q < StarQueue::kCap) {
+            queue.w[0][q] = k0[j];
+            queue.w[1][q] = k1[j];
+            queue.w[2][q] = kS;
+            queue.w[3][q] = kO;
+            queue.w[4][q] = (int32_t) (uint32_t) (uint64_t) row;
+            queue.w[5][q] = (int32_t) (uint32_t) ((uint64_t) row >> 32);
+         } else {
+            handle(k0[j], k1[j], kS, kO, row);
+         }
+      }
+      __syncthreads();
+      drainQueue(queue, false, process);
+   });
+   __syncthreads();
+   drainQueue(queue, true, process);
+}
+void launchScanStarProbeSend(const StarSendParams& p, int smCount, cudaStream_t s) {
+   size_t dyn;
+   if (p.src.cols.decBytes == 8) {
+      int grid = persistentGrid(scanStarProbeSendKernel<8, 2>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock, 2);
+      scanStarProbeSendKernel<8, 2><<<grid, kBlock, dyn, s>>>(p);
+   } else {
+      int grid = persistentGrid(scanStarProbeSendKernel<16, 2>, p.src.cols, p.src.nRows, smCount, &dyn, kBlock, 2);
+      scanStarProbeSendKernel<16, 2><<<grid, kBlock, dyn, s>>>(p);
+   }
+}
+__global__ void __launch_bounds__(kBlock) probeReceivedGroupBy2Kernel(JoinTableDev table, GroupTableDev groupsOut, const uint8_t* recv, int world, int64_t capacity, const unsigned long long* counts) {
+   __shared__ LocalGroups groups;
+   groups.init();
+   __syncthreads();
+   const int64_t total = (int64_t) world * capacity;
+   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t) gridDim.x * blockDim.x) {
+      const int src = (int) (i / capacity);
+      const int64_t idx = i - (int64_t) src * capacity;
+      if ((unsigned long long) idx >= counts[src]) continue;
+      const unsigned long long* tup = (const unsigned long long*) recv + i * 3;
+      const unsigned long long w0 = tup[0];
+      const int32_t key = (int32_t) (uint32_t) w0, g0 = (int32_t) (uint32_t) (w0 >> 32);
+      const i128 v{tup[1], (int64_t) tup[2]};
+      joinProbe(table, key, [&](int64_t, int32_t g1) { groups.add(groupsOut, g0, g1, v, false); });
+   }
+   __syncthreads();
+   groups.flush(groupsOut, false);
+}
+void launchProbeReceivedGroupBy2(const JoinTableDev& table, const GroupTableDev& groups, const uint8_t* recv, int world, int64_t capacity, const unsigned long long* counts, int smCount, cudaStream_t s) {
+   const int64_t total = (int64_t) world * capacity;
+   int grid = (int) std::min<int64_t>(std::max<int64_t>((total + kBlock - 1) / kBlock, 1), (int64_t) smCount * 4);
+   probeReceivedGroupBy2Kernel<<<grid, kBlock, 0, s>>>(table, groups, recv, world, capacity, counts);
+}
+
 // tuples received from `world` sources: sub-region s holds counts[s] tuples (count read from device memory: no host round trip)
 __global__ void __launch_bounds__(kBlock) insertReceivedKernel(JoinTableDev t, const uint8_t* recv, int world, int64_t capacity, const unsigned long long* counts) {
    unsigned long long inserted = 0;

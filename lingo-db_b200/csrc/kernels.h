@@ -207,6 +207,7 @@ struct SendParams {
    ScanSource src;
    int32_t keyStage;
    int32_t secondStage; // staged int32 column, or -1: the probe's payload
+   int32_t secondYear;  // ship extract(year from <date32 second column>) instead of the column's value (DateRuntime::extractYear)
    int32_t nDec;
    LazyCols dec; // the shipped decimal columns (fetched for the rows that are sent)
    int32_t hasProbe, bloomOnly;
@@ -219,6 +220,23 @@ struct SendParams {
    int32_t* error;              // 6 = a sub-region overflowed
 };
 void launchScanPartitionSend(const SendParams& p, int smCount, cudaStream_t s);
+// K11 star probe + send: scan → composite-key probe P (Bloom first) → foreign-key probe S → the row's contribution
+// a * (1 - b) - c * d (c = P's payload) is shipped as {partition key : 32 | S payload : 32, lo, hi} to the rank that owns the
+// partition key — the lineitem side of a Q9-shaped join whose third build side (orders) is hash-partitioned across the ranks
+struct StarSendParams {
+   ScanSource src;
+   int32_t keyStageP0, keyStageP1, keyStageS, keyStageO;
+   JoinTableDev tableP, tableS;
+   LazyCols values; // a, b, d
+   int32_t world;
+   uint8_t* dest[kMaxRanks];
+   int64_t capacity;
+   unsigned long long* cursors;
+   int32_t* error;
+};
+void launchScanStarProbeSend(const StarSendParams& p, int smCount, cudaStream_t s);
+// received {key | g0, lo, hi} tuples → probe `table` on key (payload = g1) → group by (g0, g1) → SUM of the shipped i128 value
+void launchProbeReceivedGroupBy2(const JoinTableDev& table, const GroupTableDev& groups, const uint8_t* recv, int world, int64_t capacity, const unsigned long long* counts, int smCount, cudaStream_t s);
 // received tuples of `world` sources (counts[src] tuples each, read from DEVICE memory) → join-table inserts
 void launchInsertReceived(const JoinTableDev& t, const uint8_t* recv, int world, int64_t capacity, const unsigned long long* counts, int smCount, cudaStream_t s);
 // received {key|keyB, a, b} tuples → probe A on key, probe B on keyB, payloads equal → group by payload → SUM(a * (one - b))

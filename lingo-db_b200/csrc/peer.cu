@@ -462,6 +462,22 @@ int ldb_gpu_probe_received_groupby(LdbState* ta, LdbState* tb, LdbState* groups,
    });
 }
 
+int ldb_gpu_probe_received_groupby2(LdbState* table, LdbState* groups, LdbComm* c, int64_t recv_offset, int64_t capacity, int64_t counts_offset, LdbError* err) {
+   return guardedPeer(err, [&] {
+      wantConnected(c);
+      if (!table || table->kind != LDB_STATE_JOIN_TABLE || table->join.stride != 8 || table->join.direct) failPeer(LDB_ERR_INVALID, "probe table must be a plain single-key join table");
+      if (!groups || groups->kind != LDB_STATE_GROUPBY || groups->group.nKeys != 2 || groups->group.nAggs != 1) failPeer(LDB_ERR_INVALID, "sink must be a group-by state with two keys and one aggregate");
+      wantRange(c, recv_offset, (int64_t) c->world * capacity * 24, "receive region");
+      wantRange(c, counts_offset, kMaxPeers * 8, "counts");
+      LdbContext* ctx = c->ctx;
+      LDB_CUDA(cudaSetDevice(ctx->device));
+      uint8_t* user = c->heap + kUserOff;
+      ctx->launch("join_probe_received_groupby", [&] {
+         launchProbeReceivedGroupBy2(table->join, groups->group, user + recv_offset, c->world, capacity, (const unsigned long long*) (user + counts_offset), ctx->smCount, ctx->compute);
+      });
+   });
+}
+
 // surfaces a timed-out wait (dead or stuck peer); synchronises the compute stream
 int ldb_gpu_comm_check(LdbComm* c, LdbError* err) {
    return guardedPeer(err, [&] {

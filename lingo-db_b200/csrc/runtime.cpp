@@ -1430,6 +1430,8 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
             } else {
                base.secondStage = sp.add(t, R.col(d->out_columns[1], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "second tuple column"));
             }
+            base.secondYear = d->build_payload_expr == LDB_PAYLOAD_YEAR ? 1 : 0;
+            if (base.secondYear && base.secondStage < 0) fail(LDB_ERR_INVALID, "the year expression applies to a shipped date32 column, not to a probe payload");
             base.nDec = d->n_out_cols - 2;
             int sendDecCols[2] = {0, 0};
             for (int k = 0; k < base.nDec; k++) {
@@ -1457,6 +1459,50 @@ int ldb_gpu_run_pipeline(LdbContext* ctx, const LdbPipelineDesc* d, LdbError* er
                if (probe) p.probe = probe->join;
                waitBatch(ctx, b);
                ctx->launch("partition_send", [&] { launchScanPartitionSend(p, ctx->smCount, ctx->compute); });
+            }
+            break;
+         }
+         case LDB_PIPE_SCAN_STAR_PROBE_SEND: {
+            LdbComm* c = d->comm;
+            if (!c || c->ctx != ctx) fail(LDB_ERR_INVALID, "star-probe-send needs a comm of this context");
+            if (!c->connected && c->world > 1) fail(LDB_ERR_INVALID, "comm is not connected to its peers yet");
+            if (d->n_probes != 2) fail(LDB_ERR_INVALID, "star-probe-send pipelines take two probes (composite-key table, foreign-key table)");
+            if (d->n_aggs != 1 || d->aggs[0].expr != LDB_EXPR_MUL_1MINUS_MINUS_PAYMUL) fail(LDB_ERR_UNSUPPORTED, "star-probe-send pipelines ship a * (1 - b) - $payload0 * c");
+            if (d->n_out_cols != 1 || !d->out_columns[0]) fail(LDB_ERR_INVALID, "star-probe-send: out_columns[0] names the partition key");
+            LdbState* tp = wantState(d->probe_states[0], LDB_STATE_JOIN_TABLE, "probe 0");
+            LdbState* ts = wantState(d->probe_states[1], LDB_STATE_JOIN_TABLE, "probe 1");
+            if (tp->join.stride != 16 || !d->probe_key2_columns[0]) fail(LDB_ERR_INVALID, "probe 0 of a star-probe-send pipeline is a composite-key table");
+            if (ts->join.stride == 16) fail(LDB_ERR_INVALID, "probe 1 of a star-probe-send pipeline is a single-key table");
+            StarSendParams base{};
+            base.keyStageP0 = sp.add(t, R.col(d->probe_key_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key 0"));
+            base.keyStageP1 = sp.add(t, R.col(d->probe_key2_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key 0 (second)"));
+            base.keyStageS = sp.add(t, R.col(d->probe_key_columns[1], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "probe key 1"));
+            base.keyStageO = sp.add(t, R.col(d->out_columns[0], {LDB_INT32, LDB_DATE32, LDB_FSB4}, "partition key"));
+            int valueCols[3];
+            for (int k = 0; k < 3; k++) {
+               valueCols[k] = R.col(d->aggs[0].columns[k], {LDB_DECIMAL128}, "aggregate operand");
+               if (t->columns[valueCols[k]].precision >= 19 || t->columns[valueCols[k]].scale != 2) fail(LDB_ERR_UNSUPPORTED, "aggregate operands must be decimal(p<19, 2) on the GPU path");
+            }
+            const int64_t region = (int64_t) c->world * d->send_capacity * 24;
+            if (d->send_capacity <= 0 || d->send_offset < 0 || d->send_offset % 16 || (size_t) (d->send_offset + region) > c->userBytes ||
+                d->send_cursors_offset < 0 || d->send_cursors_offset % 16 || (size_t) d->send_cursors_offset + 16 * 8 > c->userBytes)
+               fail(LDB_ERR_CAPACITY, "receive region / cursors outside the comm's user heap (create the comm with a larger heap)");
+            base.world = c->world;
+            for (int r = 0; r < c->world; r++) base.dest[r] = c->peerHeap[r] + kUserOff + d->send_offset + (int64_t) c->rank * d->send_capacity * 24;
+            base.capacity = d->send_capacity;
+            base.cursors = (unsigned long long*) (c->heap + kUserOff + d->send_cursors_offset);
+            base.error = (int32_t*) (base.cursors + 8);
+            for (auto& b : t->batches) {
+               if (b.nRows == 0) continue;
+               StarSendParams p = base;
+               p.src.nRows = b.nRows;
+               bindFilters(fp, b, p.src.filters);
+               sp.bind(t, b, p.src.cols, 2);
+               bindLazy(t, b, valueCols, 3, p.values);
+               p.tableP = tp->join;
+               p.tableS = ts->join;
+               waitBatch(ctx, b);
+               ctx->launch("star_probe_send", [&] { launchScanStarProbeSend(p, ctx->smCount, ctx->compute); });
             }
             break;
          }

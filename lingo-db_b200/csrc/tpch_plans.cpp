@@ -628,6 +628,154 @@ int ldb_tpch_q9_partial(LdbContext* ctx, const LdbTpchTables* t, const char* nam
       *state = groups; // the join tables die here (StateGuard); the caller owns the group state
    });
 }
+// ------------------------------------------------------------------------------------------------ Q9, orders hash-partitioned across GPUs
+namespace {
+struct Q9Layout {
+   int64_t capOrd, capLi, cursorsA, cursorsB, countsA, countsB, ordRecv, liRecv, total;
+};
+Q9Layout q9Layout(int64_t nOrdTotal, int64_t nLiTotal, int world) {
+   Q9Layout l{};
+   const int64_t w2 = (int64_t) world * world;
+   l.capOrd = nOrdTotal / w2 + nOrdTotal / w2 / 4 + 8192; // every order is shipped: expected share + 25 %
+   l.capLi = nLiTotal / 10 / w2 + 8192;                   // ~5.4 % of lineitem survives the partsupp probe: twice the expected share
+   int64_t off = 0;
+   auto take = [&](int64_t bytes) {
+      int64_t at = off;
+      off = (off + bytes + 255) & ~int64_t(255);
+      return at;
+   };
+   l.cursorsA = take(16 * 8);
+   l.cursorsB = take(16 * 8);
+   l.countsA = take(8 * 8);
+   l.countsB = take(8 * 8);
+   l.ordRecv = take((int64_t) world * l.capOrd * 8);
+   l.liRecv = take((int64_t) world * l.capLi * 24);
+   l.total = off;
+   return l;
+}
+} // namespace
+int64_t ldb_tpch_q9_repartitioned_heap_bytes(int64_t n_orders_total, int64_t n_lineitem_total, int32_t world) { return q9Layout(n_orders_total, n_lineitem_total, world).total; }
+int ldb_tpch_q9_repartitioned(LdbContext* ctx, const LdbTpchTables* t, LdbComm* comm, const char* nameContains, int64_t nOrdTotal, int64_t nLiTotal, LdbQ9Row* rows, int32_t maxRows,
+                              int32_t* nRows, LdbQ5ShuffleStats* stats, LdbError* err) {
+   return guarded(err, [&] {
+      LdbError e;
+      StateGuard g;
+      if (!comm) throw std::runtime_error("repartitioned Q9 needs a comm");
+      if (!t->part || !t->partsupp) throw std::runtime_error("Q9 needs the part and partsupp tables");
+      const int world = ldb_gpu_comm_world(comm);
+      const Q9Layout L = q9Layout(nOrdTotal, nLiTotal, world);
+      int64_t heapBytes = 0;
+      ldb_gpu_comm_heap(comm, &heapBytes);
+      if (heapBytes < L.total) {
+         LdbError he{LDB_ERR_CAPACITY, ""};
+         snprintf(he.message, sizeof(he.message), "comm user heap holds %lld bytes, repartitioned Q9 needs %lld (ldb_tpch_q9_repartitioned_heap_bytes)", (long long) heapBytes, (long long) L.total);
+         throw PlanError(he);
+      }
+      check(ldb_gpu_comm_heap_zero(comm, 0, L.ordRecv, &e), e);
+      int64_t nPart = ldb_gpu_table_num_rows(t->part), nPs = ldb_gpu_table_num_rows(t->partsupp);
+      // replicated build sides, as in ldb_tpch_q9_partial
+      LdbFilterDesc fp[1] = {strFilter("p_name", LDB_CONTAINS, nameContains)};
+      LdbPipelineDesc dp{};
+      dp.kind = LDB_PIPE_SCAN_BUILD;
+      dp.source = t->part;
+      dp.n_filters = 1;
+      dp.filters = fp;
+      dp.build_key_column = "p_partkey";
+      LdbState* part = buildJoin(ctx, g, dp, nPart / 12 + 1024, 1, 0, 0);
+      LdbPipelineDesc dps{};
+      dps.kind = LDB_PIPE_SCAN_BUILD;
+      dps.source = t->partsupp;
+      dps.n_probes = 1;
+      dps.probe_states[0] = part;
+      dps.probe_key_columns[0] = "ps_partkey";
+      dps.build_key_column = "ps_partkey";
+      dps.build_key2_column = "ps_suppkey";
+      dps.build_payload_column = "ps_supplycost";
+      LdbState* ps = nullptr;
+      try {
+         ps = buildJoin(ctx, g, dps, nPs / 12 + 1024, LDB_JOIN_UNIQUE, 0, 0, true);
+      } catch (const PlanError& pe) {
+         if (pe.e.code != LDB_ERR_INVALID) throw;
+         ps = buildJoin(ctx, g, dps, nPs / 12 + 1024, 0, 0, 0, true);
+      }
+      LdbPipelineDesc ds{};
+      ds.kind = LDB_PIPE_SCAN_BUILD;
+      ds.source = t->supplier;
+      ds.build_key_column = "s_suppkey";
+      ds.build_payload_column = "s_nationkey";
+      LdbState* supp = buildForeignKeyTable(ctx, g, ds, t->supplier, "s_suppkey");
+      // this rank's hash partition of orders: o_orderkey → year (foreign-key probes always hit: no Bloom filter)
+      LdbState* ordp = nullptr;
+      check(ldb_gpu_join_table_create(ctx, nOrdTotal / world + nOrdTotal / world / 4 + 4096, LDB_JOIN_UNIQUE | LDB_JOIN_NO_BLOOM, 0, 0, &ordp, &e), e);
+      g.own(ordp);
+      check(ldb_gpu_comm_barrier(comm, &e), e); // every rank cleared its cursors and counts
+      LdbPipelineDesc so{};
+      so.kind = LDB_PIPE_SCAN_PARTITION_SEND;
+      so.source = t->orders;
+      so.n_out_cols = 2;
+      so.out_columns[0] = "o_orderkey";
+      so.out_columns[1] = "o_orderdate";
+      so.build_payload_expr = LDB_PAYLOAD_YEAR;
+      so.comm = comm;
+      so.send_offset = L.ordRecv;
+      so.send_capacity = L.capOrd;
+      so.send_cursors_offset = L.cursorsA;
+      check(ldb_gpu_run_pipeline(ctx, &so, &e), e);
+      check(ldb_gpu_comm_publish_counts(comm, L.cursorsA, L.countsA, &e), e);
+      // the lineitem side does not depend on the orders partition: its send kernel runs before the barrier that publishes the orders
+      LdbPipelineDesc sl{};
+      sl.kind = LDB_PIPE_SCAN_STAR_PROBE_SEND;
+      sl.source = t->lineitem;
+      sl.n_probes = 2;
+      sl.probe_states[0] = ps;
+      sl.probe_key_columns[0] = "l_partkey";
+      sl.probe_key2_columns[0] = "l_suppkey";
+      sl.probe_states[1] = supp;
+      sl.probe_key_columns[1] = "l_suppkey";
+      sl.n_aggs = 1;
+      sl.aggs[0] = agg(LDB_EXPR_MUL_1MINUS_MINUS_PAYMUL, "l_extendedprice", "l_discount", "l_quantity");
+      sl.n_out_cols = 1;
+      sl.out_columns[0] = "l_orderkey";
+      sl.comm = comm;
+      sl.send_offset = L.liRecv;
+      sl.send_capacity = L.capLi;
+      sl.send_cursors_offset = L.cursorsB;
+      check(ldb_gpu_run_pipeline(ctx, &sl, &e), e);
+      check(ldb_gpu_comm_publish_counts(comm, L.cursorsB, L.countsB, &e), e);
+      check(ldb_gpu_comm_barrier(comm, &e), e); // all tuples and counts of both shuffles landed
+      check(ldb_gpu_join_table_insert_received(ordp, comm, L.ordRecv, L.capOrd, L.countsA, &e), e);
+      LdbState* groups = nullptr;
+      check(ldb_gpu_groupby_create(ctx, 2, 1, 1024, &groups, &e), e);
+      g.own(groups);
+      check(ldb_gpu_probe_received_groupby2(ordp, groups, comm, L.liRecv, L.capLi, L.countsB, &e), e);
+      check(ldb_gpu_groupby_allmerge(groups, comm, &e), e);
+      check(ldb_tpch_q9_finish(groups, rows, maxRows, nRows, &e), e);
+      uint64_t hdr[48];
+      check(ldb_gpu_comm_heap_read(comm, L.cursorsA, 16 * 8, hdr, &e), e);
+      check(ldb_gpu_comm_heap_read(comm, L.cursorsB, 16 * 8, hdr + 16, &e), e);
+      check(ldb_gpu_comm_heap_read(comm, L.countsA, 8 * 8, hdr + 32, &e), e);
+      check(ldb_gpu_comm_heap_read(comm, L.countsB, 8 * 8, hdr + 40, &e), e);
+      check(ldb_gpu_comm_check(comm, &e), e);
+      if ((uint32_t) hdr[8] || (uint32_t) hdr[16 + 8]) {
+         LdbError ce{LDB_ERR_CAPACITY, "a repartition receive sub-region overflowed (skewed partitions): raise the comm heap / capacities"};
+         throw PlanError(ce);
+      }
+      int64_t cnt = 0;
+      check(ldb_gpu_join_table_count(ordp, &cnt, &e), e);
+      if (stats) {
+         *stats = LdbQ5ShuffleStats{};
+         for (int r = 0; r < world; r++) {
+            stats->orders_tuples_sent += (int64_t) hdr[r];
+            stats->lineitem_tuples_sent += (int64_t) hdr[16 + r];
+            stats->orders_tuples_received += (int64_t) hdr[32 + r];
+            stats->lineitem_tuples_received += (int64_t) hdr[40 + r];
+         }
+         stats->shuffle_bytes_out = stats->orders_tuples_sent * 8 + stats->lineitem_tuples_sent * 24;
+         stats->heap_bytes = L.total;
+      }
+   });
+}
+
 int ldb_tpch_q9_finish(LdbState* groups, LdbQ9Row* rows, int32_t maxRows, int32_t* nRows, LdbError* err) {
    return guarded(err, [&] {
       LdbError e;

@@ -206,6 +206,20 @@ def q5_repartitioned_peer(ctx, tpch, comm: "Comm", n_orders_total: int, n_lineit
     return out, {k: int(getattr(st, k)) for k, _ in capi.Q5ShuffleStats._fields_}
 
 
+def q9_heap_bytes(ctx, n_orders_total: int, n_lineitem_total: int, world: int) -> int:
+    return int(ctx.L.ldb_tpch_q9_repartitioned_heap_bytes(int(n_orders_total), int(n_lineitem_total), world))
+
+
+def q9_repartitioned_peer(ctx, tpch, comm: "Comm", n_orders_total: int, n_lineitem_total: int, name_contains: str = "green"):
+    """ldb_tpch_q9_repartitioned: orders hash-partitioned across the ranks, lineitem contributions shipped to the owner of their order
+    (K10 + K11 peer stores, device barriers, peer all-merge).  Returns (rows, stats)."""
+    from . import capi
+    rows, n, st, e = (capi.Q9Row * 1024)(), C.c_int32(), capi.Q5ShuffleStats(), capi.Error()
+    capi.check(ctx.L.ldb_tpch_q9_repartitioned(ctx.h, C.byref(tpch.t), comm.h, name_contains.encode(), int(n_orders_total), int(n_lineitem_total), rows, 1024, C.byref(n),
+                                               C.byref(st), C.byref(e)), e)
+    return tpch._q9_rows(rows, n.value), {k: int(getattr(st, k)) for k, _ in capi.Q5ShuffleStats._fields_}
+
+
 def _all_to_all(cols, send_offsets, world, dev):
     """Exchange per-destination contiguous blocks (K6 output) of several columns; returns received columns + row count."""
     import torch

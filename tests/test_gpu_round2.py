@@ -277,6 +277,50 @@ def test_q5_repartitioned_peer_stores_match_the_oracle(oracle, world):
             c.close()
 
 
+@pytest.mark.parametrize("world", [1, 3])
+def test_q9_repartitioned_orders_hash_partitioned_match_the_oracle(oracle, world):
+    """ldb_tpch_q9_repartitioned: {o_orderkey, year} tuples to the owner of h64(o_orderkey) (K10 with the year expression), lineitem
+    contributions {l_orderkey | nation, i128 amount} shipped after the partsupp / supplier probes (K11), probe of the received tuples
+    against the orders partition, all-merge — ranks as contexts of this process, lineitem shards deliberately NOT co-partitioned."""
+    import threading
+    from lingodb_b200 import devgen, parallel, runtime
+    s = datagen.scale(0.1, seed=37)
+    cols = ["l_orderkey", "l_partkey", "l_suppkey", "l_quantity", "l_extendedprice", "l_discount"]
+    host = datagen.tpch(0.1, seed=37, lineitem_columns=cols, with_parts=True)
+    oh = {k: oracle.table(v) for k, v in host.items()}
+    want = oracle.q9(oh["part"], oh["supplier"], oh["lineitem"], oh["partsupp"], oh["orders"], oh["nation"])[0]
+    ctxs = [runtime.Context(0) for _ in range(world)]
+    try:
+        comms = parallel.Comm.local_group(ctxs, user_bytes=parallel.q9_heap_bytes(ctxs[0], s.n_orders, s.n_lineitem, world))
+        tps = []
+        for r, c in enumerate(ctxs):
+            o_lo, o_hi, _, _ = parallel.order_range(s, r, world)
+            _, _, l_lo, l_hi = parallel.order_range(s, (r + 1) % world, world)
+            tps.append(runtime.Tpch(c, {"lineitem": devgen.lineitem(c, s, cols, row_begin=l_lo, n_rows=l_hi - l_lo), "orders": devgen.orders(c, s, row_begin=o_lo, n_rows=o_hi - o_lo),
+                                        "supplier": devgen.supplier(c, s), "part": devgen.part(c, s), "partsupp": devgen.partsupp(c, s), **devgen.small_tables(c)}))
+        for it in range(2):
+            res, errs = [None] * world, []
+
+            def run(r):
+                try:
+                    res[r] = parallel.q9_repartitioned_peer(ctxs[r], tps[r], comms[r], s.n_orders, s.n_lineitem)
+                except Exception as ex:  # noqa: BLE001
+                    errs.append((r, str(ex)))
+            ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+            [t.start() for t in ts]
+            [t.join() for t in ts]
+            assert not errs, "\n".join(f"rank {r}: {m}" for r, m in errs)
+            for r in range(world):
+                assert res[r][0] == want, f"rank {r} iteration {it}"
+            assert sum(res[r][1]["orders_tuples_sent"] for r in range(world)) == s.n_orders  # every order is shipped to its owner
+            assert sum(res[r][1]["lineitem_tuples_sent"] for r in range(world)) == sum(res[r][1]["lineitem_tuples_received"] for r in range(world)) > 0
+        for cm in comms:
+            cm.close()
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def test_peer_collectives_across_processes_and_gpus():
     """world = 2 processes on 2 GPUs (CUDA IPC + NVLink P2P), when the box has them: tools/peer_selftest.py checks Q1/Q9
     against the oracle on every rank and exits non-zero on any mismatch."""

@@ -22,7 +22,7 @@ def main():
     s = datagen.scale(sf, seed=17)
     cols = ["l_orderkey", "l_partkey", "l_suppkey", "l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus", "l_shipdate"]
     ctx = runtime.Context(local)
-    comm = parallel.Comm(ctx, rank, world, user_bytes=parallel.q5_heap_bytes(ctx, s.n_orders, s.n_lineitem, world))
+    comm = parallel.Comm(ctx, rank, world, user_bytes=max(parallel.q5_heap_bytes(ctx, s.n_orders, s.n_lineitem, world), parallel.q9_heap_bytes(ctx, s.n_orders, s.n_lineitem, world)))
     o_lo, o_hi, r_lo, r_hi = parallel.order_range(s, rank, world)
     tabs = {"lineitem": devgen.lineitem(ctx, s, cols, row_begin=r_lo, n_rows=r_hi - r_lo), "orders": devgen.orders(ctx, s, row_begin=o_lo, n_rows=o_hi - o_lo),
             "supplier": devgen.supplier(ctx, s), "part": devgen.part(ctx, s), "partsupp": devgen.partsupp(ctx, s), "customer": devgen.customer(ctx, s), **devgen.small_tables(ctx)}
@@ -43,6 +43,8 @@ def main():
         assert got9 == want_q9, f"rank {rank} iteration {it}: Q9 differs"
         got5, st5 = parallel.q5_repartitioned_peer(ctx, tp, comm, s.n_orders, s.n_lineitem)
         assert got5 == want_q5, f"rank {rank} iteration {it}: repartitioned Q5 differs"
+        got9r, st9 = parallel.q9_repartitioned_peer(ctx, tp, comm, s.n_orders, s.n_lineitem)
+        assert got9r == want_q9, f"rank {rank} iteration {it}: repartitioned Q9 differs"
     comm.barrier()
     comm.check()
     dist.barrier()
