@@ -277,7 +277,7 @@ def run_ours(args):
     ctx = runtime.Context(local)
     L = ctx.L
     s = datagen.scale(args.sf, args.seed)
-    comm = parallel.Comm(ctx, rank, world, user_bytes=parallel.q5_heap_bytes(ctx, s.n_orders, s.n_lineitem, world) if not args.no_extra else 0) if world > 1 else None
+    comm = parallel.Comm(ctx, rank, world, user_bytes=max(parallel.q5_heap_bytes(ctx, s.n_orders, s.n_lineitem, world), parallel.q9_heap_bytes(ctx, s.n_orders, s.n_lineitem, world)) if not args.no_extra else 0) if world > 1 else None
     # strong scaling: SF-sized lineitem split by order range
     o_lo, o_hi, r_lo, r_hi = parallel.order_range(s, rank, world)
     my_rows = r_hi - r_lo
@@ -644,6 +644,26 @@ def side_queries_multi(args, ctx, comm, s, tabs, rank, world, o_lo, o_hi, dev, n
     queries["q9_sharded"] = {"ms": float(t.item()), "rows_per_s": scanned / (float(t.item()) / 1000), "rows_scanned": scanned, "groups": len(res),
                              "checksum_sum_profit": sum(r["sum_profit"] for r in res),
                              "plan": "lineitem and orders sharded by the same order range (co-partitioned join), part/partsupp/supplier replicated, peer-mapped all-merge of the 175-group tables"}
+    comm.check()
+    # ---- Q9 with orders HASH-partitioned (config 4): K10 + K11 peer stores; must give the co-partitioned plan's rows
+    rows9, st9 = parallel.q9_repartitioned_peer(ctx, tpx, comm, s.n_orders, s.n_lineitem)
+    if rows9 != res:
+        raise SystemExit(f"PARITY FAILURE (repartitioned Q9, rank {rank}): differs from the co-partitioned plan")
+    secs = []
+    for _ in range(3):
+        dist.barrier()
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        rows9, st9 = parallel.q9_repartitioned_peer(ctx, tpx, comm, s.n_orders, s.n_lineitem)
+        secs.append(time.perf_counter() - t0)
+    t9 = torch.tensor([min(secs[1:])], dtype=torch.float64, device=dev)
+    dist.all_reduce(t9, op=dist.ReduceOp.MAX)
+    st = torch.tensor([st9["orders_tuples_sent"], st9["lineitem_tuples_sent"], st9["shuffle_bytes_out"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(st)
+    queries["q9_repartitioned"] = {"ms": 1000 * float(t9.item()), "rows_per_s": scanned / float(t9.item()), "rows_scanned": scanned, "orders_tuples_shuffled": int(st[0].item()),
+                                   "lineitem_tuples_shuffled": int(st[1].item()), "shuffle_bytes_all_ranks": int(st[2].item()),
+                                   "parity": "rows == the co-partitioned plan's (whose single-GPU twin is oracle-gated at SF100)",
+                                   "plan": "orders hash-partitioned across the ranks (K10), lineitem contributions shipped to the owner of their order (K11), peer all-merge"}
     comm.check()
     # ---- Q5 with the orders ⋈ lineitem join REPARTITIONED across the ranks (BASELINE.json config 3): fused partition + NVLink peer
     # stores, device-side barriers, Bloom OR by peer loads, peer all-merge — C++ driver ldb_tpch_q5_repartitioned, no NCCL
