@@ -189,7 +189,9 @@ def q9_sharded(ctx, tpch, world: int, rank: int, bufs: dict, name_contains: str 
     return rows
 
 
-# ------------------------------------------------------------------------------------------------ Q5 with repartition
+# ------------------------------------------------------------------------------------------------ repartitioned joins (C++ drivers)
+# (round 1 orchestrated this plan from Python with NCCL all-to-alls and host synchronisations between the phases; it is now
+#  csrc/tpch_plans.cpp + csrc/peer.cu: fused partition → NVLink peer stores, device-side barriers, no host round trip)
 def q5_heap_bytes(ctx, n_orders_total: int, n_lineitem_total: int, world: int) -> int:
     return int(ctx.L.ldb_tpch_q5_repartitioned_heap_bytes(int(n_orders_total), int(n_lineitem_total), world))
 
@@ -220,30 +222,8 @@ def q9_repartitioned_peer(ctx, tpch, comm: "Comm", n_orders_total: int, n_lineit
     return tpch._q9_rows(rows, n.value), {k: int(getattr(st, k)) for k, _ in capi.Q5ShuffleStats._fields_}
 
 
-def _all_to_all(cols, send_offsets, world, dev):
-    """Exchange per-destination contiguous blocks (K6 output) of several columns; returns received columns + row count."""
-    import torch
-    import torch.distributed as dist
-    send_counts = [send_offsets[i + 1] - send_offsets[i] for i in range(world)]
-    if world == 1:
-        return cols, send_counts[0]
-    sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
-    rc = torch.empty_like(sc)
-    dist.all_to_all_single(rc, sc)  # row counts first, so receive buffers are exact
-    recv_counts = [int(x) for x in rc.tolist()]
-    n_recv = sum(recv_counts)
-    out = []
-    for c in cols:
-        width = c.shape[1] if c.dim() == 2 else 1
-        flat = c.reshape(-1)
-        recv = torch.empty(n_recv * width, dtype=c.dtype, device=dev)
-        dist.all_to_all_single(recv, flat[: send_offsets[world] * width], [n * width for n in recv_counts], [n * width for n in send_counts])
-        out.append(recv.reshape(-1, width) if c.dim() == 2 else recv)
-    return out, n_recv
-
-
 def _materialize(ctx, table, out_columns, widths, capacity, dev, **kw):
-    """Run a K8 pipeline into fresh device buffers; regrow once if the estimate was too small."""
+    """Run a K8 (scan → filters → [probe] → compacted columns) pipeline into fresh device buffers; regrow if the estimate was too small."""
     import torch
 
     from . import runtime
@@ -258,110 +238,6 @@ def _materialize(ctx, table, out_columns, widths, capacity, dev, **kw):
         if n <= capacity:
             return bufs, n
         capacity = int(n * 1.1) + 1024
-
-
-def _partition(ctx, keys, payload, widths, n, world, dev):
-    import torch
-
-    from . import capi
-    out_keys = torch.empty_like(keys)
-    outs = [torch.empty_like(p) for p in payload]
-    offs = (C.c_int64 * (world + 1))()
-    cols = (C.c_void_p * max(1, len(payload)))(*[p.data_ptr() for p in payload])
-    ocols = (C.c_void_p * max(1, len(payload)))(*[p.data_ptr() for p in outs])
-    w = (C.c_int32 * max(1, len(payload)))(*widths)
-    torch.cuda.synchronize(dev)
-    e = capi.Error()
-    capi.check(ctx.L.ldb_gpu_partition_tuples(ctx.h, C.c_void_p(keys.data_ptr()), cols, w, len(payload), n, world, C.c_void_p(out_keys.data_ptr()), ocols, offs, C.byref(e)), e)
-    return out_keys, outs, list(offs)
-
-
-def q5_repartitioned(ctx, tables, world: int, rank: int, n_orders_total: int, region_name="ASIA", date_ge="1994-01-01", date_lt="1995-01-01"):
-    """TPC-H Q5 with the orders⋈lineitem join radix-partitioned across `world` GPUs (BASELINE.json config 3).
-
-    tables: this rank's shares of lineitem/orders (any split) + full customer/supplier/nation/region (small build
-    sides are replicated = broadcast).  Steps: local K8 materialise of qualifying orders tuples → K6 radix
-    partition by h64(o_orderkey) → NCCL all-to-all → each rank builds its hash partition; the partitions' Bloom
-    filters are OR-all-reduced so every rank pre-filters its lineitem share (semi-join reduction, ≈3 % survive)
-    before the second partition + all-to-all; probes and the 5-group aggregation run where the partition lives;
-    the partial group tables are all-gathered and merged (K7).  Returns the same rows as Tpch.q5()."""
-    import torch
-    import torch.distributed as dist
-
-    from . import capi, runtime
-    dev = torch.device("cuda", ctx.device)
-    L = ctx.L
-    states = []
-
-    def own(s):
-        states.append(s)
-        return s
-
-    try:
-        n_cust, n_supp = tables["customer"].num_rows, tables["supplier"].num_rows
-        region = own(runtime.join_table(ctx, 16))
-        runtime.run_pipeline(ctx, "scan_build", tables["region"], filters=[("r_name", "=", region_name)], build_key="r_regionkey", sink=region)
-        nation = own(runtime.join_table(ctx, 64))
-        runtime.run_pipeline(ctx, "scan_build", tables["nation"], probes=[(region, "n_regionkey")], build_key="n_nationkey", build_payload="n_nationkey", sink=nation)
-        cust = own(runtime.join_table(ctx, n_cust // 4 + 1024))
-        runtime.run_pipeline(ctx, "scan_build", tables["customer"], probes=[(nation, "c_nationkey")], build_key="c_custkey", build_payload="c_nationkey", sink=cust)
-        supp = own(runtime.join_table(ctx, n_supp // 4 + 1024))
-        runtime.run_pipeline(ctx, "scan_build", tables["supplier"], probes=[(nation, "s_nationkey")], build_key="s_suppkey", build_payload="s_nationkey", sink=supp)
-        # orders share → (o_orderkey, c_nationkey) tuples → radix partition → all-to-all → this rank's hash partition
-        n_ord_local = tables["orders"].num_rows
-        (ok, on), n_t = _materialize(ctx, tables["orders"], ["o_orderkey", "$payload"], [4, 4], n_ord_local // 16 + 4096, dev,
-                                     filters=[("o_orderdate", ">=", date_ge), ("o_orderdate", "<", date_lt)], probes=[(cust, "o_custkey")])
-        pk, (pn,), offs = _partition(ctx, ok, [on], [4], n_t, world, dev)
-        (rk, rn), n_r = _all_to_all([pk, pn], offs, world, dev)
-        # sized for the GLOBAL key set on every rank: identical Bloom geometry everywhere, and the OR of all partitions'
-        # filters keeps the false-positive rate of a single-GPU build (a 1/world-sized filter let 8 % through at N=4)
-        ordp = own(runtime.join_table(ctx, n_orders_total // 24 + 4096))
-        e = capi.Error()
-        torch.cuda.synchronize(dev)
-        capi.check(L.ldb_gpu_join_table_insert(ctx.h, ordp, C.c_void_p(rk.data_ptr()), C.c_void_p(rn.data_ptr()), None, n_r, C.byref(e)), e)
-        runtime.join_count(ctx, ordp)  # surfaces capacity / duplicate errors
-        if world > 1:
-            bp, nb = C.c_void_p(), C.c_int64()
-            capi.check(L.ldb_gpu_join_table_bloom(ordp, C.byref(bp), C.byref(nb), C.byref(e)), e)
-            if nb.value:
-                bloom = _device_view(bp.value, nb.value // 4, dev)  # zero-copy view of the table's own filter
-                ctx.synchronize()
-                gathered = torch.empty(world * bloom.numel(), dtype=torch.int32, device=dev)
-                dist.all_gather_into_tensor(gathered, bloom)  # NCCL has no bitwise-OR reduction: gather, then OR
-                gathered = gathered.view(world, -1)
-                acc = gathered[0]
-                for i in range(1, world):
-                    acc = acc | gathered[i]
-                bloom.copy_(acc)
-                torch.cuda.synchronize(dev)
-        # lineitem share → Bloom semi-join → tuples → radix partition → all-to-all
-        n_li = tables["lineitem"].num_rows
-        (lk, ls, le, ld), n_l = _materialize(ctx, tables["lineitem"], ["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount"], [4, 4, 16, 16],
-                                             n_li // 16 + 4096, dev, probes=[(ordp, "l_orderkey")], bloom_only=True)
-        plk, (pls, ple, pld), offs = _partition(ctx, lk, [ls, le, ld], [4, 16, 16], n_l, world, dev)
-        (rlk, rls, rle, rld), n_rl = _all_to_all([plk, pls, ple, pld], offs, world, dev)
-        from . import datagen
-        shuffled = runtime.Table(ctx, "lineitem_repartitioned", [c for c in datagen.LINEITEM_SCHEMA if c.name in ("l_orderkey", "l_suppkey", "l_extendedprice", "l_discount")])
-        groups = own(runtime.groupby_state(ctx, 1, 1, 64))
-        if n_rl > 0:
-            shuffled.append_device({"l_orderkey": rlk, "l_suppkey": rls, "l_extendedprice": rle, "l_discount": rld}, n_rl)
-            torch.cuda.synchronize(dev)
-            runtime.run_pipeline(ctx, "scan_probe2_groupby", shuffled, probes=[(ordp, "l_orderkey"), (supp, "l_suppkey")],
-                                 aggs=[("mul_1minus", ["l_extendedprice", "l_discount"])], sink=groups)
-        ctx.synchronize()
-        if world > 1:
-            allgather_merge_state(ctx, groups, world, rank, {})
-        rows, n = runtime.groupby_read(ctx, groups)
-        names = [nm for nm, _ in datagen.NATIONS]
-        out = [{"n_name": names[rows[i].keys[0]], "revenue": rows[i].aggs[0].value()} for i in range(n)]
-        out.sort(key=lambda r: (-r["revenue"], r["n_name"]))
-        stats = {"orders_tuples_sent": n_t, "orders_tuples_received": n_r, "lineitem_tuples_sent": n_l, "lineitem_tuples_received": n_rl,
-                 "lineitem_rows_scanned": n_li, "shuffle_bytes_out": n_t * 8 + n_l * 40}
-        return out, stats
-    finally:
-        ctx.synchronize()
-        for s in states:
-            L.ldb_gpu_state_destroy(s)
 
 
 class _CudaArray:

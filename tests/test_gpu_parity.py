@@ -203,18 +203,6 @@ def test_radix_partition_and_tuple_insert(gpu_ctx, oracle):
     L.ldb_gpu_state_destroy(st)
 
 
-def test_q5_repartitioned_world1_matches_oracle(gpu_ctx, oracle):
-    """The multi-GPU Q5 plan (K8 materialise → K6 partition → exchange → partition-local probes) run with world = 1."""
-    from lingodb_b200 import parallel
-    t = datagen.tpch(0.05, seed=21, chunk_rows=1 << 20)
-    tabs = {k: gpu_ctx.table_from_host(v) for k, v in t.items()}
-    oh = {k: oracle.table(v) for k, v in t.items()}
-    want, _ = oracle.q5(oh["customer"], oh["orders"], oh["lineitem"], oh["supplier"], oh["nation"], oh["region"])
-    got, stats = parallel.q5_repartitioned(gpu_ctx, tabs, 1, 0, t["orders"].num_rows)
-    assert got == want
-    assert 0 < stats["lineitem_tuples_sent"] < 0.1 * stats["lineitem_rows_scanned"]  # the Bloom semi-join did its job
-
-
 def test_materialize_pipeline_exact_rows(gpu_ctx):
     import torch
     from lingodb_b200 import parallel
