@@ -118,11 +118,19 @@ uint32_t opMask(int op) {
 namespace {
 // order the compute stream after the staging of one batch
 void waitBatch(LdbContext* ctx, const LdbBatch& b) {
-   if (b.ready) LDB_CUDA(cudaStreamWaitEvent(ctx->compute, b.ready, 0));
+   // inside a captured query the staging must be COMPLETE (a captured stream cannot depend on uncaptured copy streams): wait on the host
+   const bool capturing = ctx->capturing != nullptr;
+   if (b.ready) {
+      if (capturing) LDB_CUDA(cudaEventSynchronize(b.ready));
+      else LDB_CUDA(cudaStreamWaitEvent(ctx->compute, b.ready, 0));
+   }
    if (b.packed) { // compressed staging: every task of the batch issued (host), then order the scan after the workers' streams
       StagingEngine::wait(*b.packed);
-      for (size_t w = 0; w < b.packed->used.size(); w++)
-         if (b.packed->used[w]) LDB_CUDA(cudaStreamWaitEvent(ctx->compute, ctx->staging->events[w], 0));
+      for (size_t w = 0; w < b.packed->used.size(); w++) {
+         if (!b.packed->used[w]) continue;
+         if (capturing) LDB_CUDA(cudaEventSynchronize(ctx->staging->events[w]));
+         else LDB_CUDA(cudaStreamWaitEvent(ctx->compute, ctx->staging->events[w], 0));
+      }
    }
 }
 }

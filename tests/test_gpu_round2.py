@@ -188,6 +188,16 @@ def test_captured_query_replays_bit_identically(gpu_ctx, oracle):
     assert n == 3 and ms > 0
     g.destroy()
     runtime.state_destroy(gpu_ctx, st)
+    # a HOST-staged table can be captured too: the capture waits for its staging on the host instead of on the stream
+    tph = runtime.Tpch(gpu_ctx, {"lineitem": gpu_ctx.table_from_host(datagen.lineitem(s, cols, chunk_rows=70_000))})
+    gpu_ctx.graph_begin()
+    st = tph.q1_partial()
+    g = gpu_ctx.graph_end()
+    for _ in range(2):
+        g.launch()
+        assert tph.q1_finish(st) == want
+    g.destroy()
+    runtime.state_destroy(gpu_ctx, st)
 
 
 def test_captured_query_with_peer_allmerge(oracle):
