@@ -108,6 +108,8 @@ class Oracle:
         L.oracle_q4.argtypes = [C.c_void_p] * 2 + [C.c_char_p] * 2 + [C.POINTER(CountRow), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.oracle_q12.argtypes = [C.c_void_p] * 2 + [C.c_char_p] * 4 + [C.POINTER(CountRow), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.oracle_q18.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.POINTER(Q18Row), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.oracle_scan_count_sum.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_char_p), C.POINTER(C.c_int64),
+                                            C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.oracle_extract_year.restype = C.c_int64
         L.oracle_extract_year.argtypes = [C.c_int64]
         L.oracle_const_like_contains.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p]
@@ -138,6 +140,8 @@ class Oracle:
                 else:
                     assert v.flags["C_CONTIGUOUS"]
                     ptrs[3 * i + 1] = v.ctypes.data
+                if c.name + "$valid" in chunk:  # Arrow validity bitmap of a nullable column
+                    ptrs[3 * i] = chunk[c.name + "$valid"].ctypes.data
             L.oracle_table_add_chunk(h, n, ptrs)
             self._keep.append((chunk, ptrs))
         return h
@@ -150,6 +154,21 @@ class Oracle:
             raise RuntimeError(self.lib.oracle_last_error().decode())
 
     # ---- queries: python-int results + pipeline seconds
+    OPS = {"=": 0, "!=": 1, "<": 2, "<=": 3, ">": 4, ">=": 5, "notnull": 6}
+
+    def scan_count_sum(self, table, filters, sum_column=None):
+        """count(*) and sum(sum_column) of the rows the reference's pushed-down filters keep; filters: (column, op, value | None);
+        nullable columns carry "<col>$valid" bitmaps in their chunks (NOTNULL consults them, Restrictions.cpp:67-162)."""
+        n = len(filters)
+        cols = (C.c_char_p * max(1, n))(*[f[0].encode() for f in filters])
+        ops = (C.c_int * max(1, n))(*[self.OPS[f[1]] for f in filters])
+        is_int = (C.c_int * max(1, n))(*[int(isinstance(f[2], int)) for f in filters])
+        strs = (C.c_char_p * max(1, n))(*[(f[2].encode() if isinstance(f[2], str) else None) for f in filters])
+        ints = (C.c_int64 * max(1, n))(*[(f[2] if isinstance(f[2], int) else 0) for f in filters])
+        cnt, lo, hi = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self.lib.oracle_scan_count_sum(table, n, cols, ops, is_int, strs, ints, sum_column.encode() if sum_column else None, C.byref(cnt), C.byref(lo), C.byref(hi)))
+        return cnt.value, i128((lo.value, hi.value))
+
     def q6(self, lineitem, date_ge="1994-01-01", date_lt="1995-01-01", disc_ge="0.05", disc_le="0.07", qty_lt=24):
         lo, hi, sec = C.c_int64(), C.c_int64(), C.c_double()
         self._check(self.lib.oracle_q6(lineitem, date_ge.encode(), date_lt.encode(), disc_ge.encode(), disc_le.encode(), qty_lt,

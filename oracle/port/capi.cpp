@@ -2,9 +2,12 @@
 // (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference legs).
 #include "pipelines.h"
 #include "rt_select.h"
+#include "scan.h"
 #include "scheduler.h"
 
+#include <atomic>
 #include <cstring>
+#include <mutex>
 
 using namespace oracle;
 
@@ -104,6 +107,58 @@ void oracle_avg_dec12_2(int64_t sum, int64_t count, int64_t* lo, int64_t* hi) { 
 void oracle_mul_i128(int64_t alo, int64_t ahi, int64_t blo, int64_t bhi, int64_t* lo, int64_t* hi) {
    i128 a = (i128) (((u128) (uint64_t) ahi << 64) | (uint64_t) alo), b = (i128) (((u128) (uint64_t) bhi << 64) | (uint64_t) blo);
    split(wrapMul(a, b), lo, hi);
+}
+
+// ---- a scan with pushed-down filters over (possibly nullable) columns: count(*) and sum(<int32 | decimal(p<19) column>) of the rows the
+// reference's Restrictions::applyFilters lets through (NOTNULL filters consult the validity bitmap, Restrictions.cpp:67-162); NULL cells of
+// the summed column are skipped like the JIT'd aggregate skips them.  ops: FilterOp order (EQ, NEQ, LT, LTE, GT, GTE, NOTNULL).
+int oracle_scan_count_sum(void* table, int nFilters, const char* const* columns, const int* ops, const int* isInt, const char* const* strValues, const int64_t* intValues,
+                          const char* sumColumn, int64_t* count, int64_t* sumLo, int64_t* sumHi) {
+   return guarded([&] {
+      HostTable& t = *(HostTable*) table;
+      std::vector<FilterDescription> fds;
+      std::vector<std::string> cols;
+      for (int i = 0; i < nFilters; i++) {
+         FilterDescription fd;
+         fd.columnName = columns[i];
+         int id = t.colIndex(columns[i]);
+         if (id < 0) throw std::runtime_error("unknown filter column");
+         fd.columnId = (size_t) id;
+         fd.op = (FilterOp) ops[i];
+         if (isInt[i]) fd.value = intValues[i];
+         else fd.value = std::string(strValues[i] ? strValues[i] : "");
+         fds.push_back(fd);
+      }
+      int sumId = sumColumn ? t.colIndex(sumColumn) : -1;
+      if (sumColumn && sumId < 0) throw std::runtime_error("unknown sum column");
+      if (sumColumn) cols.push_back(sumColumn);
+      else cols.push_back(t.schema[0].name);
+      rt::QueryContextScope scope;
+      std::atomic<int64_t> n{0};
+      std::mutex m;
+      i128 total = 0;
+      const bool dec = sumId >= 0 && t.schema[sumId].type == PhysType::DECIMAL128;
+      scanTable(t, cols, fds, [&](rt::BatchView* b) {
+         int64_t localN = 0;
+         i128 local = 0;
+         ColReader r(b, 0);
+         const rt::ArrayView* av = b->arrays[0];
+         const uint8_t* valid = av->nullCount ? (const uint8_t*) av->buffers[0] : nullptr;
+         for (size_t i = 0; i < b->length; i++) {
+            const int64_t idx = b->selectionVector[i];
+            localN++;
+            if (sumId < 0) continue;
+            const int64_t abs = av->offset + b->offset + idx;
+            if (valid && !((valid[abs / 8] >> (abs % 8)) & 1)) continue;
+            local += dec ? (i128) r.dec64(idx) : (i128) r.i32(idx);
+         }
+         n += localN;
+         std::lock_guard<std::mutex> l(m);
+         total += local;
+      });
+      *count = n.load();
+      split(total, sumLo, sumHi);
+   });
 }
 
 // ---- queries; *seconds = wall time of the pipelines only (tables resident), like the reference's

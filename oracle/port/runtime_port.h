@@ -543,6 +543,24 @@ class VarLen32Filter : public Filter { // Restrictions.cpp:279-325: utf8 offsets
       return w - next;
    }
 };
+class NotNullFilter : public Filter { // Restrictions.cpp:67-162: keep the positions whose validity bit is set; a column without nulls passes through
+   public:
+   size_t filter(size_t len, const uint16_t* cur, uint16_t* next, const ArrayView* av, size_t offset) override {
+      if (av->nullCount == 0) {
+         memcpy(next, cur, len * sizeof(uint16_t));
+         return len;
+      }
+      const uint8_t* bits = reinterpret_cast<const uint8_t*>(av->buffers[0]);
+      const size_t first = offset + av->offset;
+      uint16_t* w = next;
+      for (size_t i = 0; i < len; i++) {
+         const size_t bit = first + cur[i];
+         *w = cur[i];
+         w += (bits[bit >> 3] >> (bit & 7)) & 1;
+      }
+      return w - next;
+   }
+};
 class Restrictions {
    std::vector<std::pair<std::unique_ptr<Filter>, size_t>> filters;
 
@@ -556,6 +574,10 @@ class Restrictions {
             if (schema[i].name == d.columnName) colId = i;
          if (colId == (size_t) -1) throw std::runtime_error("unknown column in filter");
          auto& col = schema[colId];
+         if (d.op == FilterOp::NOTNULL) { // Restrictions.cpp:399-405 (value unused)
+            r->filters.push_back({std::make_unique<NotNullFilter>(), colId});
+            continue;
+         }
          switch (col.type) {
             case PhysType::FSB4: { // char(1): compare the 4-byte cell as int32 (Restrictions.cpp:411-424)
                std::string s = std::get<std::string>(d.value);

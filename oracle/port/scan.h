@@ -32,7 +32,7 @@ struct ChunkViews {
       for (size_t col = 0; col < t.schema.size(); col++) {
          rt::ArrayView v{};
          v.length = c.numRows;
-         v.nullCount = 0;
+         v.nullCount = c.buffers[3 * col] ? 1 : 0; // a caller-provided validity bitmap: "has nulls" (the filters test nullCount != 0, Restrictions.cpp:70,112)
          v.offset = 0;
          v.nBuffers = t.schema[col].type == PhysType::STRING ? 3 : 2;
          v.nChildren = 0;

@@ -1,7 +1,8 @@
 """The generic program pipeline (csrc/program.cu) through the C-ABI: arbitrary expressions, nullable columns, strings, float/int64
 operands, SUM/COUNT/MIN/MAX/ANY with SQL null semantics over ANY number of groups, semi joins and ORDER BY — against the CPU
-oracle where it has the query, against an independent numpy evaluation where it does not (nullable inputs: "parity unpinned"
-beyond the three-valued-logic rules of the SQL standard that numpy restates)."""
+oracle where it has the query (nullable scans: the reference's own Restrictions with the NOTNULL filters its pushdown adds,
+test_nullable_scans_match_the_reference_filters), against an independent numpy evaluation for the rest (NULL handling inside
+aggregates and boolean connectives: the three-valued-logic rules of the SQL standard, restated in numpy)."""
 import ctypes as C
 
 import numpy as np
@@ -119,6 +120,29 @@ def test_nullable_columns_types_and_every_aggregate(gpu_ctx):
         gpu_ctx.L.ldb_gpu_state_destroy(st)
         wk = np.array([{"<": w < k.encode(), "=": w == k.encode(), ">=": w >= k.encode(), "!=": w != k.encode()}[op] for w in words])[sidx]
         assert cnt == int((wk & valid["s"]).sum()), (op, k)
+
+
+def test_nullable_scans_match_the_reference_filters(gpu_ctx, oracle):
+    """WHERE predicates over nullable generator columns, evaluated by the program pipeline with SQL three-valued logic, keep exactly
+    the rows the reference's scan keeps with the filter lists its pushdown writes for nullable columns ([NOTNULL, cmp…],
+    Pushdown.cpp:346-372 → Restrictions.cpp:67-162), and SUM skips the same NULL cells: count and sum bit-exact against the oracle
+    (the reference-compiled Restrictions when oracle/_ref is built)."""
+    from lingodb_b200 import program as P
+    from _nullable import cases, nullable_lineitem
+    li, _ = nullable_lineitem()
+    tab = gpu_ctx.table_from_host(li)
+    oh = oracle.table(li)
+    date = lambda s: oracle.lib.oracle_parse_date(s.encode())
+    for filters, where, sum_column in cases(date):
+        aggs = [("count_star", None)] + ([("sum", col(sum_column))] if sum_column else [])
+        st = P.group_by(gpu_ctx, tab, [], aggs, where=where)
+        got = P.decode_groups(P.read_groups(gpu_ctx, st, 4), 0, len(aggs))[()]
+        gpu_ctx.L.ldb_gpu_state_destroy(st)
+        want_n, want_sum = oracle.scan_count_sum(oh, filters, sum_column)
+        assert got[0] == want_n, filters
+        if sum_column:
+            assert got[1] == want_sum, filters
+    oracle.free(oh)
 
 
 def test_large_domain_group_by_having_and_order_by(gpu_ctx):
