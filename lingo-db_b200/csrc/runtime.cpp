@@ -1019,9 +1019,14 @@ struct StagePlan {
       }
       out.stageBytes = off;
       out.useTma = aligned && n > 0 ? 1 : 0;
-      out.decBytes = 16;
-      for (int i = 0; i < n; i++)
-         if (t->columns[colIdx[i]].type == LDB_DECIMAL128) out.decBytes = out.elemBytes[i]; // uniform per batch (all or none narrowed)
+      out.decBytes = 0; // the kernels are instantiated for ONE decimal cell width per batch
+      for (int i = 0; i < n; i++) {
+         if (t->columns[colIdx[i]].type != LDB_DECIMAL128) continue;
+         if (out.decBytes && out.decBytes != out.elemBytes[i])
+            fail(LDB_ERR_UNSUPPORTED, "batch stages decimal columns of different cell widths (a narrowed decimal(p<19) next to a 16-byte decimal(p>=19)): use the program pipeline (ldb_gpu_run_program)");
+         out.decBytes = out.elemBytes[i];
+      }
+      if (!out.decBytes) out.decBytes = 16;
    }
 };
 struct FilterPlan {
