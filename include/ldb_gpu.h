@@ -113,6 +113,13 @@ int32_t ldb_gpu_effective_cpus(void);
  * kernels and the rows per thread of a build tile (1, 2, 4); defaults = measured best (profiles/r2_stage_sweep.md), also settable
  * through LDB_STAGES_BUILD / _PROBE_AGG / _PROBE2 / _STAR and LDB_RPT_BUILD */
 void ldb_gpu_set_tuning(int32_t stages_build, int32_t stages_probe_agg, int32_t stages_probe2, int32_t stages_star, int32_t rows_per_thread_build);
+/* experiment hook: 1 (default) = the join pipelines (build, probe-aggregate, probe-probe-group, star probe) run the instantiation compiled for
+ * their filter SHAPE (none / one int32 compare / one int32 range — what the reference's JIT would emit for the same pushed-down predicate);
+ * 0 = always the descriptor-driven form.  Results are identical; also settable through LDB_SPECIALISE. */
+void ldb_gpu_set_filter_specialisation(int32_t on);
+/* experiment hook: nanoseconds the producer lane / the consumer warps of the warp-specialised tile driver pause between two polls of
+ * a tile barrier (0 = poll back to back; also LDB_PRODUCER_SLEEP_NS / LDB_CONSUMER_SLEEP_NS) */
+void ldb_gpu_set_poll_pause(int32_t producer_ns, int32_t consumer_ns);
 int64_t ldb_gpu_table_num_rows(const LdbTable* t);
 void ldb_gpu_table_destroy(LdbTable* t);
 

@@ -176,6 +176,13 @@ struct LdbTable {
    std::vector<LdbColumn> columns;
    std::vector<LdbBatch> batches;
    int64_t numRows = 0;
+   // column statistics (min, max) of int32/date32 columns, computed on first use and valid while the table has `rows` rows: the planner
+   // asks for them on every query (direct-address join tables), the table does not change between two queries
+   struct ColumnRange {
+      int64_t rows;
+      int32_t lo, hi;
+   };
+   std::map<int, ColumnRange> ranges;
    int colIndex(const char* n) const {
       if (!n) return -1;
       for (size_t i = 0; i < columns.size(); i++)

@@ -112,6 +112,24 @@ __device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// the same wait with a pause between polls: a thread that is expected to wait long (the producer lane behind the slowest consumer
+// warp) otherwise spends issue slots on try_wait/branch that the compute warps of the SM need (profiles/r2_ncu_stall_sites.txt: 13-22 % of
+// the issued instructions of K4/K5 were poll loops).  sleepNs == 0: plain polling.
+__device__ __forceinline__ void mbarWaitPaused(uint64_t* bar, uint32_t parity, uint32_t sleepNs) {
+   const uint32_t addr = smemAddr(bar);
+   while (true) {
+      uint32_t done;
+      asm volatile(
+         "{\n\t.reg .pred p;\n\t"
+         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+         "selp.u32 %0, 1, 0, p;\n\t}"
+         : "=r"(done)
+         : "r"(addr), "r"(parity)
+         : "memory");
+      if (done) return;
+      if (sleepNs) __nanosleep(sleepNs);
+   }
+}
 // global → shared bulk copy, completion counted in bytes on `bar`; src/dst 16-B aligned, bytes % 16 == 0
 // Column data is read exactly once: L2 evict_first keeps the 126 MB L2 for the hash-table directories and bloom filters.
 __device__ __forceinline__ uint64_t evictFirstPolicy() {
@@ -133,6 +151,15 @@ __device__ __forceinline__ int64_t ldShared64(uint32_t addr) {
    int64_t v;
    asm volatile("ld.shared.s64 %0, [%1];" : "=l"(v) : "r"(addr));
    return v;
+}
+
+// ---------------------------------------------------------------- blocked Bloom filter of the join tables
+// Three bit positions inside the 32-bit filter word that (h >> 32) selects, from a second multiply of the hash.  (Deriving them from the
+// low hash word with one 32-bit multiply saves four instructions per probe but raised the false-positive rate enough to cost K9
+// 0.14 ms at SF100 and gained nothing on K4/K5, which wait on the filter word, not on the ALU: profiles/r2_join_kernels_round2b.md.)
+__device__ __forceinline__ uint32_t bloomBits(uint64_t h) {
+   const uint64_t g = h * 0xD6E8FEB86659FD93ull;
+   return (1u << (g >> 59)) | (1u << ((g >> 54) & 31)) | (1u << ((g >> 49) & 31));
 }
 
 // ---------------------------------------------------------------- filters

@@ -90,6 +90,8 @@ struct Tuning {
    int stagesBuild, stagesProbeAgg, stagesProbe2, stagesStar; // TMA pipeline depth of K3 / K5 / K4 / K9
    int rptBuild;                                              // rows per thread of a K3 tile (1, 2 or 4)
    int rptStar;                                               // rows per thread of a K9 tile (1, 2 or 4)
+   int producerSleepNs, consumerSleepNs;                      // pause between mbarrier polls in the warp-specialised tile driver (0 = poll)
+   int specialise;                                            // 1: join pipelines run the filter-shape instantiations (kernels.cu FilterShape), 0: descriptor-driven only
 };
 const Tuning& tuning();
 void setTuning(const Tuning& t);
@@ -99,6 +101,7 @@ struct StagedCols {
    int32_t stageBytes; // bytes of one stage = sum(elemBytes) * tileRows
    int32_t useTma;     // 0 when a column base is not 16-byte aligned: tiles are then read with plain loads
    int32_t decBytes;   // bytes per decimal128 cell as staged: 16 (Arrow layout) or 8 (HOST batch narrowed); selects the kernel instantiation
+   int32_t producerSleepNs, consumerSleepNs; // pause between mbarrier polls of the producer lane / the consumer warps (0 = plain polling)
    const uint8_t* base[kMaxStagedCols];
    int32_t elemBytes[kMaxStagedCols];  // 4 (int32/date32/fsb4) or 16 (decimal128)
    int32_t smemOffset[kMaxStagedCols]; // offset of the column inside a stage

@@ -26,10 +26,7 @@ __device__ bool joinInsertProg(const JoinTableDev& t, int32_t key, int32_t paylo
    for (uint64_t probes = 0; probes < limit; probes++) {
       const unsigned long long old = atomicCAS((unsigned long long*) (t.base + s * t.stride), ~0ull, packed);
       if (old == ~0ull) {
-         if (t.bloom) {
-            const uint64_t g = h * 0xD6E8FEB86659FD93ull;
-            atomicOr(&t.bloom[(uint32_t) (h >> 32) & t.bloomMask], (1u << (g >> 59)) | (1u << ((g >> 54) & 31)) | (1u << ((g >> 49) & 31)));
-         }
+         if (t.bloom) atomicOr(&t.bloom[(uint32_t) (h >> 32) & t.bloomMask], bloomBits(h));
          return true;
       }
       if ((int32_t) (uint32_t) old == key && t.unique) { // a set of keys (semi-join build side): duplicates are dropped, not an error
@@ -325,8 +322,7 @@ __global__ void __launch_bounds__(256) programKernel(const __grid_constant__ Pro
                         const uint64_t h = hashI32(key);
                         bool maybe = true;
                         if (t.bloom) {
-                           uint64_t g = h * 0xD6E8FEB86659FD93ull;
-                           const uint32_t bits = (1u << (g >> 59)) | (1u << ((g >> 54) & 31)) | (1u << ((g >> 49) & 31));
+                           const uint32_t bits = bloomBits(h);
                            maybe = (__ldg(&t.bloom[(uint32_t) (h >> 32) & t.bloomMask]) & bits) == bits;
                         }
                         uint64_t s = h & t.mask;

@@ -331,6 +331,17 @@ void ldb_gpu_set_tuning(int32_t stages_build, int32_t stages_probe_agg, int32_t 
    t.rptBuild = rows_per_thread_build;
    setTuning(t);
 }
+void ldb_gpu_set_filter_specialisation(int32_t on) {
+   Tuning t = tuning();
+   t.specialise = on ? 1 : 0;
+   setTuning(t);
+}
+void ldb_gpu_set_poll_pause(int32_t producer_ns, int32_t consumer_ns) {
+   Tuning t = tuning();
+   t.producerSleepNs = producer_ns;
+   t.consumerSleepNs = consumer_ns;
+   setTuning(t);
+}
 int64_t ldb_gpu_launch_count(LdbContext* ctx) { return ctx ? ctx->launches + ctx->stagingLaunches.load() : 0; }
 int ldb_gpu_timer_start(LdbContext* ctx, LdbError* err) {
    return guarded(err, [&] { LDB_CUDA(cudaEventRecord(ctx->timerStart, ctx->compute)); });
@@ -594,6 +605,7 @@ int ldb_gpu_table_append_batch(LdbTable* t, int64_t n_rows, const LdbArrayView* 
          ctx->staging->submit(pk);
       }
       t->numRows += n_rows;
+      t->ranges.clear();
       t->batches.push_back(std::move(b));
    });
 }
@@ -620,6 +632,7 @@ int ldb_gpu_table_clear(LdbTable* t, LdbError* err) {
       }
       t->batches.clear();
       t->numRows = 0;
+      t->ranges.clear();
    });
 }
 int64_t ldb_gpu_table_num_rows(const LdbTable* t) { return t ? t->numRows : 0; }
@@ -900,6 +913,11 @@ int ldb_gpu_table_column_range(LdbTable* t, const char* column, int32_t* mn, int
       int c = t->colIndex(column);
       if (c < 0) fail(LDB_ERR_INVALID, "unknown column");
       if (t->columns[c].type != LDB_INT32 && t->columns[c].type != LDB_DATE32) fail(LDB_ERR_UNSUPPORTED, "column range needs an int32/date32 column");
+      if (auto it = t->ranges.find(c); it != t->ranges.end() && it->second.rows == t->numRows && !ctx->capturing) {
+         *mn = it->second.lo;
+         *mx = it->second.hi;
+         return;
+      }
       LDB_CUDA(cudaSetDevice(ctx->device));
       int32_t init[2] = {INT32_MAX, INT32_MIN};
       int32_t* d = (int32_t*) ctx->stagingAlloc(8);
@@ -914,6 +932,7 @@ int ldb_gpu_table_column_range(LdbTable* t, const char* column, int32_t* mn, int
       ctx->stagingRelease(d);
       *mn = init[0];
       *mx = init[1];
+      t->ranges[c] = LdbTable::ColumnRange{t->numRows, init[0], init[1]};
    });
 }
 static void checkJoinError(LdbState* s) {
@@ -1019,6 +1038,8 @@ struct StagePlan {
       }
       out.stageBytes = off;
       out.useTma = aligned && n > 0 ? 1 : 0;
+      out.producerSleepNs = tuning().producerSleepNs;
+      out.consumerSleepNs = tuning().consumerSleepNs;
       out.decBytes = 0; // the kernels are instantiated for ONE decimal cell width per batch
       for (int i = 0; i < n; i++) {
          if (t->columns[colIdx[i]].type != LDB_DECIMAL128) continue;

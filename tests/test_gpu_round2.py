@@ -341,3 +341,23 @@ def test_peer_collectives_across_processes_and_gpus():
                         os.path.join(ROOT, "tools", "peer_selftest.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "peer selftest ok" in r.stdout
+
+
+def test_filter_shape_instantiations_agree_with_the_descriptor_driven_kernels(gpu_ctx, oracle):
+    """The join pipelines run an instantiation compiled for their filter shape (none / one int32 compare / one int32 range —
+    kernels.cu FilterShape) by default; the descriptor-driven form must give the same rows, and both the oracle's."""
+    from lingodb_b200 import runtime
+    t = datagen.tpch(0.05, seed=11, chunk_rows=40_003, with_parts=True)
+    g = runtime.Tpch(gpu_ctx, {k: gpu_ctx.table_from_host(v) for k, v in t.items()})
+    oh = {k: oracle.table(v) for k, v in t.items()}
+    res = {}
+    try:
+        for on in (0, 1):
+            gpu_ctx.L.ldb_gpu_set_filter_specialisation(on)
+            res[on] = (g.q3(), g.q3("MACHINERY", "1996-01-01"), g.q5(), g.q5("EUROPE", "1996-01-01", "1997-01-01"), g.q9("green"))
+    finally:
+        gpu_ctx.L.ldb_gpu_set_filter_specialisation(1)
+    assert res[0] == res[1]
+    assert res[1][0] == oracle.q3(oh["customer"], oh["orders"], oh["lineitem"])[0]
+    assert res[1][2] == oracle.q5(oh["customer"], oh["orders"], oh["lineitem"], oh["supplier"], oh["nation"], oh["region"])[0]
+    assert res[1][4] == oracle.q9(oh["part"], oh["supplier"], oh["lineitem"], oh["partsupp"], oh["orders"], oh["nation"], "green")[0]
