@@ -196,3 +196,124 @@ def test_gpu_program_pipelines_reproduce_q4_q12_q18(sf1, gpu_ctx):
         t.destroy()
     for s_ in (st, late, prio, big):
         gpu_ctx.L.ldb_gpu_state_destroy(s_)
+
+
+def test_data_also_reproduces_q10_and_q15(sf1):
+    """Two more answers evaluated in numpy on the same tables: Q10 (join + 38 k-group aggregation + top 20 by revenue, tpchSf1.test:66-85:
+    c_custkey, c_name, revenue and n_name of every row) and Q15 (the top supplier of a quarter, :1317: s_suppkey, s_name, total_revenue)."""
+    from lingodb_b200 import datagen
+    cat = lambda t, k: np.concatenate([c[k] for c in sf1[t].chunks])
+    lo = lambda a: a[:, :8].copy().view(np.int64).reshape(-1)
+    d = lambda s: (datetime.date.fromisoformat(s) - datetime.date(1970, 1, 1)).days
+    lkey, lsupp, lship, lflag = (cat("lineitem", k) for k in ("l_orderkey", "l_suppkey", "l_shipdate", "l_returnflag"))
+    rev = lo(cat("lineitem", "l_extendedprice")) * (100 - lo(cat("lineitem", "l_discount")))
+    okey, ocust, odate = (cat("orders", k) for k in ("o_orderkey", "o_custkey", "o_orderdate"))
+    cnat = cat("customer", "c_nationkey")
+    names = [n for n, _ in datagen.NATIONS]
+    # ---- Q10
+    cust_of = np.zeros(int(okey.max()) + 1, np.int64)
+    in_range = (odate >= d("1993-10-01")) & (odate < d("1994-01-01"))
+    cust_of[okey[in_range]] = ocust[in_range]
+    m = ((lflag & 0xFF) == ord("R")) & (cust_of[lkey] > 0)
+    total = np.zeros(len(cnat) + 1, np.int64)
+    np.add.at(total, cust_of[lkey[m]], rev[m])
+    top = sorted(np.flatnonzero(total).tolist(), key=lambda c: (-int(total[c]), c))[:20]
+    got = [[str(c), "Customer#%09d" % c, dec(int(total[c]), 4), names[cnat[c - 1]]] for c in top]
+    assert got == [[r[0], r[1], r[2], r[4]] for r in GOLD["q10_rows"]]
+    # ---- Q15
+    m = (lship >= d("1996-01-01")) & (lship < d("1996-04-01"))
+    per = np.zeros(int(lsupp.max()) + 1, np.int64)
+    np.add.at(per, lsupp[m], rev[m])
+    best = np.flatnonzero(per == per.max())
+    assert [[str(s_), "Supplier#%09d" % s_, dec(int(per[s_]), 4)] for s_ in best.tolist()] == [[r[0], r[1].strip(), r[4]] for r in GOLD["q15_rows"]]
+
+
+@pytest.mark.gpu
+def test_gpu_program_pipelines_reproduce_q7_q10_q15_q21(sf1, gpu_ctx):
+    """Four more of the 22 queries as register programs over the dbgen-faithful SF1 tables, against the reference's own answers:
+    Q7 (a probe whose key is another probe's payload: lineitem → orders → customer; OR of two nation pairs; group by two payloads and
+    extract(year)), Q10 (join + 38 k-group aggregation, a program over the exported groups, ORDER BY … LIMIT 20 on the device), Q15
+    (aggregate, then the rows equal to the maximum) and Q21 (EXISTS / NOT EXISTS over the same table rewritten as per-order MIN / MAX
+    aggregates with HAVING, 1.5 M groups, two semi joins)."""
+    from lingodb_b200 import datagen, program as P, runtime
+    col, const = (lambda n: ("col", n)), (lambda v: ("const", v))
+    d = lambda s: (datetime.date.fromisoformat(s) - datetime.date(1970, 1, 1)).days
+    names = [n for n, _ in datagen.NATIONS]
+    L = gpu_ctx.L
+    li, od = gpu_ctx.table_from_host(sf1["lineitem"]), gpu_ctx.table_from_host(sf1["orders"])
+    cu, su = gpu_ctx.table_from_host(sf1["customer"]), gpu_ctx.table_from_host(sf1["supplier"])
+    revenue = ("mul", col("l_extendedprice"), ("sub", const(100), col("l_discount")))
+    states, tables = [], []
+
+    def table(expected, unique=True):
+        states.append(runtime.join_table(gpu_ctx, expected, unique=unique))
+        return states[-1]
+
+    # ---- Q7 (tpchSf1.test:20550-20553)
+    fr, ge = names.index("FRANCE"), names.index("GERMANY")
+    either = lambda c: ("or", ("cmp", "=", col(c), const(fr)), ("cmp", "=", col(c), const(ge)))
+    supp_n, cust_n, ord_c = table(4096), table(40_000), table(1_600_000)
+    P.build_join(gpu_ctx, su, supp_n, col("s_suppkey"), payload=col("s_nationkey"), where=either("s_nationkey"))
+    P.build_join(gpu_ctx, cu, cust_n, col("c_custkey"), payload=col("c_nationkey"), where=either("c_nationkey"))
+    P.build_join(gpu_ctx, od, ord_c, col("o_orderkey"), payload=col("o_custkey"))
+    sn = ("probe", supp_n, col("l_suppkey"))
+    cn = ("probe", cust_n, ("probe", ord_c, col("l_orderkey")))
+    pair = lambda a, b: ("and", ("cmp", "=", sn, const(a)), ("cmp", "=", cn, const(b)))
+    where = ("and", ("between", col("l_shipdate"), const(d("1995-01-01")), const(d("1996-12-31"))), ("or", pair(fr, ge), pair(ge, fr)))
+    st = P.group_by(gpu_ctx, li, [sn, cn, ("year", col("l_shipdate"))], [("sum", revenue)], where=where, expected_groups=64)
+    got = P.decode_groups(P.read_groups(gpu_ctx, st, 64), 3, 1)
+    L.ldb_gpu_state_destroy(st)
+    assert sorted([names[a], names[b], str(y), dec(v[0], 4)] for (a, b, y), v in got.items()) == GOLD["q7_rows"]
+    # ---- Q10 (:66-85): c_custkey, c_name, revenue, n_name of the 20 customers with the largest returned-item revenue of a quarter
+    ord_q = table(200_000)
+    P.build_join(gpu_ctx, od, ord_q, col("o_orderkey"), payload=col("o_custkey"),
+                 where=("and", ("cmp", ">=", col("o_orderdate"), const(d("1993-10-01"))), ("cmp", "<", col("o_orderdate"), const(d("1994-01-01")))))
+    ck = ("probe", ord_q, col("l_orderkey"))
+    st = P.group_by(gpu_ctx, li, [ck], [("sum", revenue)], where=("and", ("cmp", "=", col("l_returnflag"), const(ord("R"))), ("not", ("isnull", ck))), expected_groups=100_000)
+    groups = P.groups_table(gpu_ctx, st)
+    tables.append(groups)
+    states.append(st)
+    cust_all = table(160_000)
+    P.build_join(gpu_ctx, cu, cust_all, col("c_custkey"), payload=col("c_nationkey"))
+    mt = P.RawTable(gpu_ctx, P.materialize(gpu_ctx, groups, [col("k0"), col("a0"), ("probe", cust_all, col("k0"))]))
+    tables.append(mt)
+    ids = mt.order_by("c1", descending=True, limit=20)
+    rows = list(zip(*[mt.gather(f"c{i}", ids) for i in range(3)]))
+    assert [[str(c), "Customer#%09d" % c, dec(r, 4), names[n]] for c, r, n in rows] == [[g[0], g[1], g[2], g[4]] for g in GOLD["q10_rows"]]
+    # ---- Q15 (:1317): the supplier(s) with the largest revenue of a quarter
+    st = P.group_by(gpu_ctx, li, [col("l_suppkey")], [("sum", revenue)],
+                    where=("and", ("cmp", ">=", col("l_shipdate"), const(d("1996-01-01"))), ("cmp", "<", col("l_shipdate"), const(d("1996-04-01")))), expected_groups=20_000)
+    per = P.groups_table(gpu_ctx, st)
+    tables.append(per)
+    states.append(st)
+    ids = per.order_by("a0", descending=True, limit=8)
+    top = list(zip(per.gather("k0", ids, cell_bytes=8), per.gather("a0", ids)))  # exported keys are int64 cells, aggregates 16-byte cells
+    best = sorted((k, v) for k, v in top if v == top[0][1])
+    assert [[str(k), "Supplier#%09d" % k, dec(v, 4)] for k, v in best] == [[g[0], g[1].strip(), g[4]] for g in GOLD["q15_rows"]]
+    # ---- Q21 (:20244-20343).  Per order: MIN / MAX supplier over all lines and over the late lines (receipt after commit), and the number of lines
+    # whose status is not 'F' (o_orderstatus = 'F' iff there is none — dbgen derives the column that way).  An order qualifies when it is 'F', has two
+    # different suppliers (EXISTS l2) and exactly one late supplier (NOT EXISTS l3); its late lines are then l1's rows.
+    late = ("cmp", ">", col("l_receiptdate"), col("l_commitdate"))
+    big = 1 << 30
+    aggs = [("min", col("l_suppkey")), ("max", col("l_suppkey")), ("min", ("case", late, col("l_suppkey"), const(big))), ("max", ("case", late, col("l_suppkey"), const(-1))),
+            ("sum", ("case", ("cmp", "!=", col("l_linestatus"), const(ord("F"))), const(1), const(0)))]
+    st = P.group_by(gpu_ctx, li, [col("l_orderkey")], aggs, expected_groups=1_600_000)
+    per_order = P.groups_table(gpu_ctx, st)
+    tables.append(per_order)
+    states.append(st)
+    assert per_order.num_rows == 1_500_000
+    qual = table(200_000)
+    having = ("and", ("and", ("cmp", "=", col("a4"), const(0)), ("cmp", "!=", col("a0"), col("a1"))), ("cmp", "=", col("a2"), col("a3")))
+    P.build_join(gpu_ctx, per_order, qual, col("k0"), payload=col("a2"), where=having)
+    saudi = table(4096)
+    P.build_join(gpu_ctx, su, saudi, col("s_suppkey"), where=("cmp", "=", col("s_nationkey"), const(names.index("SAUDI ARABIA"))))
+    where = ("and", late, ("and", ("not", ("isnull", ("probe", qual, col("l_orderkey")))), ("not", ("isnull", ("probe", saudi, col("l_suppkey"))))))
+    st = P.group_by(gpu_ctx, li, [col("l_suppkey")], [("count_star", None)], where=where, expected_groups=4096)
+    waits = P.decode_groups(P.read_groups(gpu_ctx, st, 4096), 1, 1)
+    L.ldb_gpu_state_destroy(st)
+    top = sorted((("Supplier#%09d" % k, v[0]) for (k,), v in waits.items()), key=lambda kv: (-kv[1], kv[0]))[:100]
+    assert [[n, str(v)] for n, v in top] == GOLD["q21_rows"]
+    for t in tables:
+        t.destroy()
+    for s_ in states:
+        L.ldb_gpu_state_destroy(s_)
