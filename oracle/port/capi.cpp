@@ -144,7 +144,7 @@ int oracle_scan_count_sum(void* table, int nFilters, const char* const* columns,
          ColReader r(b, 0);
          const rt::ArrayView* av = b->arrays[0];
          const uint8_t* valid = av->nullCount ? (const uint8_t*) av->buffers[0] : nullptr;
-         for (size_t i = 0; i < b->length; i++) {
+         for (size_t i = 0; i < (size_t) b->length; i++) {
             const int64_t idx = b->selectionVector[i];
             localN++;
             if (sumId < 0) continue;
