@@ -510,7 +510,13 @@ def run_ours(args):
     if extra and world == 1:
         queries, metrics = side_queries(args, ctx, s, tabs, lineitem, td_li, oracle, peak, parity, notes)
     elif extra and world > 1:
-        queries = side_queries_multi(args, ctx, comm, s, tabs, rank, world, o_lo, o_hi, dev, notes)
+        # The Q9 / Q5 multi-GPU plans ride along: a failure there (their own parity gates raise) must not take the gated Q1 line with it —
+        # the plan is then reported as failed, without a number.  (Every rank sees the same merged rows, so a parity failure is rank-consistent.)
+        try:
+            queries = side_queries_multi(args, ctx, comm, s, tabs, rank, world, o_lo, o_hi, dev, notes)
+        except (Exception, SystemExit) as ex:  # noqa: BLE001
+            queries = {"error": f"{type(ex).__name__}: {ex}"[:600]}
+            notes.append("side queries failed and are not reported: " + queries["error"])
 
     if rank == 0:
         line = {
