@@ -210,7 +210,31 @@ def extra_columns(sf: float, line_counts: np.ndarray) -> Dict[str, np.ndarray]:
     n_o = int(1500000 * sf)
     valid = np.arange(7)[None, :] < line_counts[:, None]
     return {"o_orderpriority": unif(stream(SEED["o_orderpriority"], n_o), 0, 4).astype(np.int32),
-            "l_shipmode": unif(stream(SEED["l_shipmode"], 7 * n_o), 0, 6).reshape(n_o, 7)[valid].astype(np.int32)}
+            "l_shipmode": unif(stream(SEED["l_shipmode"], 7 * n_o), 0, 6).reshape(n_o, 7)[valid].astype(np.int32),
+            "l_shipinstruct": unif(stream(SEED["l_shipinstruct"], 7 * n_o), 0, 3).reshape(n_o, 7)[valid].astype(np.int32)}
+
+
+# part attributes and l_shipinstruct: the streams and distributions behind Q14 / Q17 / Q19 (pinned by tpchSf1.test's answers to those queries,
+# tests/test_reference_answers_sf1.py); one draw per part row each, pick_str index = UnifInt(1, count) - 1 over dists.dss' lists
+SEED.update({"p_mfgr": 1, "p_brand": 46831694, "p_type": 1841581359, "p_size": 1193163244, "p_container": 727633698, "l_shipinstruct": 1371272478})
+TYPE_SYLLABLES = (["STANDARD", "SMALL", "MEDIUM", "LARGE", "ECONOMY", "PROMO"], ["ANODIZED", "BURNISHED", "PLATED", "POLISHED", "BRUSHED"], ["TIN", "NICKEL", "BRASS", "STEEL", "COPPER"])
+CONTAINER_SYLLABLES = (["SM", "LG", "MED", "JUMBO", "WRAP"], ["CASE", "BOX", "BAG", "JAR", "PKG", "PACK", "CAN", "DRUM"])
+SHIP_INSTRUCTIONS = ["DELIVER IN PERSON", "COLLECT COD", "NONE", "TAKE BACK RETURN"]  # position of DELIVER IN PERSON pinned by Q19
+
+
+def part_attributes(sf: float) -> Dict[str, np.ndarray]:
+    """Per part (row p_partkey - 1): p_brand as the two-digit number of 'Brand#MN', p_type as an index into the 150 three-syllable types
+    (first syllable = index // 25 — the level Q14's LIKE 'PROMO%' pins; the order of the inner syllables follows the TPC-H specification's
+    lists), p_size, p_container as index // 8 = first and index % 8 = second syllable of CONTAINER_SYLLABLES."""
+    n_p = int(200000 * sf)
+    mfgr = unif(stream(SEED["p_mfgr"], n_p), 1, 5)
+    return {"p_brand": (mfgr * 10 + unif(stream(SEED["p_brand"], n_p), 1, 5)).astype(np.int32), "p_type": (unif(stream(SEED["p_type"], n_p), 1, 150) - 1).astype(np.int32),
+            "p_size": unif(stream(SEED["p_size"], n_p), 1, 50).astype(np.int32), "p_container": (unif(stream(SEED["p_container"], n_p), 1, 40) - 1).astype(np.int32)}
+
+
+def container_index(name: str) -> int:
+    a, b = name.split()
+    return CONTAINER_SYLLABLES[0].index(a) * 8 + CONTAINER_SYLLABLES[1].index(b)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

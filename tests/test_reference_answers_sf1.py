@@ -317,3 +317,43 @@ def test_gpu_program_pipelines_reproduce_q7_q10_q15_q21(sf1, gpu_ctx):
         t.destroy()
     for s_ in states:
         L.ldb_gpu_state_destroy(s_)
+
+
+def test_data_also_reproduces_q14_q17_q19(sf1):
+    """Part attributes (p_brand, p_type, p_size, p_container) and l_shipinstruct of the dbgen twin, evaluated in numpy: Q14 (join + CASE on
+    LIKE 'PROMO%', a ratio of two sums, tpchSf1.test:1282), Q17 (a correlated 0.2 * avg(l_quantity) per part, :19687) and Q19 (three OR-ed
+    conjunctions over brand / container / size / quantity / ship mode / ship instruction, :19822).  The reference prints the quotients
+    truncated to six decimals."""
+    from fractions import Fraction
+    cat = lambda t, k: np.concatenate([c[k] for c in sf1[t].chunks])
+    lo = lambda a: a[:, :8].copy().view(np.int64).reshape(-1)
+    d = lambda s: (datetime.date.fromisoformat(s) - datetime.date(1970, 1, 1)).days
+    trunc6 = lambda f: dec(int(f * 10**6), 6)
+    lkey, lpart, lship = (cat("lineitem", k) for k in ("l_orderkey", "l_partkey", "l_shipdate"))
+    ext, disc, qty = (lo(cat("lineitem", k)) for k in ("l_extendedprice", "l_discount", "l_quantity"))
+    rev = ext * (100 - disc)
+    pa = dbgen.part_attributes(1.0)
+    brand, ptype, size, cntr = (pa[k][lpart - 1] for k in ("p_brand", "p_type", "p_size", "p_container"))
+    # ---- Q14
+    m = (lship >= d("1995-09-01")) & (lship < d("1995-10-01"))
+    promo = ptype // 25 == dbgen.TYPE_SYLLABLES[0].index("PROMO")
+    assert [[trunc6(Fraction(100 * int(rev[m & promo].sum()), int(rev[m].sum())))]] == GOLD["q14_rows"]
+    # ---- Q17: l_quantity < 0.2 * avg(l_quantity) of the part  <=>  5 * l_quantity * count < sum
+    m = (brand == 23) & (cntr == dbgen.container_index("MED BOX"))
+    n_p = len(pa["p_brand"])
+    sum_q, cnt = np.zeros(n_p + 1, np.int64), np.zeros(n_p + 1, np.int64)
+    np.add.at(sum_q, lpart[m], qty[m])
+    np.add.at(cnt, lpart[m], 1)
+    small = m & (5 * qty * cnt[lpart] < sum_q[lpart])
+    assert [[trunc6(Fraction(int(ext[small].sum()), 700))]] == GOLD["q17_rows"]
+    # ---- Q19 ('AIR REG' is no ship mode: only 'AIR' qualifies)
+    counts = np.diff(np.r_[0, np.flatnonzero(np.r_[np.diff(lkey) != 0, True]) + 1])
+    x = dbgen.extra_columns(1.0, counts)
+    base = (x["l_shipmode"] == dbgen.SHIP_MODES.index("AIR")) & (x["l_shipinstruct"] == dbgen.SHIP_INSTRUCTIONS.index("DELIVER IN PERSON"))
+
+    def branch(b, containers, q_lo, size_max):
+        return (brand == b) & np.isin(cntr, [dbgen.container_index(c) for c in containers]) & (qty >= 100 * q_lo) & (qty <= 100 * (q_lo + 10)) & (size >= 1) & (size <= size_max)
+
+    m = base & (branch(12, ("SM CASE", "SM BOX", "SM PACK", "SM PKG"), 1, 5) | branch(23, ("MED BAG", "MED BOX", "MED PKG", "MED PACK"), 10, 10)
+                | branch(34, ("LG CASE", "LG BOX", "LG PACK", "LG PKG"), 20, 15))
+    assert [[dec(int(rev[m].sum()), 4)]] == GOLD["q19_rows"]
