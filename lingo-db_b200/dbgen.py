@@ -232,6 +232,17 @@ def part_attributes(sf: float) -> Dict[str, np.ndarray]:
             "p_size": unif(stream(SEED["p_size"], n_p), 1, 50).astype(np.int32), "p_container": (unif(stream(SEED["p_container"], n_p), 1, 40) - 1).astype(np.int32)}
 
 
+# account balances and available quantities (UnifInt in cents / units, one draw per row; 4 per part for partsupp): pinned by Q2 / Q11 / Q20 / Q22.
+# The country code of c_phone is 10 + c_nationkey (dbgen gen_phone), so Q22's substring(c_phone, 1, 2) needs no further stream.
+SEED.update({"ps_availqty": 1671059989, "c_acctbal": 298370230, "s_acctbal": 962338209})
+
+
+def balances_and_quantities(sf: float) -> Dict[str, np.ndarray]:
+    n_c, n_s, n_p = int(150000 * sf), int(10000 * sf), int(200000 * sf)
+    return {"c_acctbal": unif(stream(SEED["c_acctbal"], n_c), -99999, 999999), "s_acctbal": unif(stream(SEED["s_acctbal"], n_s), -99999, 999999),
+            "ps_availqty": unif(stream(SEED["ps_availqty"], 4 * n_p), 1, 9999)}
+
+
 def container_index(name: str) -> int:
     a, b = name.split()
     return CONTAINER_SYLLABLES[0].index(a) * 8 + CONTAINER_SYLLABLES[1].index(b)
