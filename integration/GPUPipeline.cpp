@@ -71,6 +71,32 @@ void GPUPipeline::run(const LdbPipelineDesc& desc) {
    LdbError e;
    check(ldb_gpu_run_pipeline(context(), &desc, &e), e);
 }
+LdbState* GPUPipeline::createHashAggregation(int32_t nKeys, int32_t nAggs, const LdbProgAgg* aggs, int64_t expectedGroups) {
+   LdbState* s = nullptr;
+   LdbError e;
+   check(ldb_gpu_hashagg_create(context(), nKeys, nAggs, aggs, expectedGroups, &s, &e), e);
+   return own(s);
+}
+void GPUPipeline::run(VarLen32 description) {
+   const std::string step = description.str();
+   LdbError e;
+   // plain JSON starts with '{'; anything else is the hex form utility::serializeToHexString produces for DataSource descriptions
+   if (!step.empty() && step.front() == '{') check(ldb_gpu_run_step(context(), step.c_str(), &e), e);
+   else check(ldb_gpu_run_step_hex(context(), step.c_str(), &e), e);
+}
+void GPUPipeline::run(const LdbProgramDesc& program) {
+   LdbError e;
+   check(ldb_gpu_run_program(context(), &program, &e), e);
+}
+void GPUPipeline::registerState(VarLen32 name, LdbState* state) {
+   LdbError e;
+   check(ldb_gpu_register_state(context(), name.str().c_str(), state, &e), e);
+}
+LdbState* GPUPipeline::findState(VarLen32 name) {
+   LdbState* s = ldb_gpu_find_state(context(), name.str().c_str());
+   if (!s) throw std::runtime_error("no GPU state named " + name.str());
+   return s;
+}
 void GPUPipeline::appendChunk(LdbTable* table, int64_t numRows, const ArrayView* const* columns, size_t nColumns, const int64_t* utf8Bytes) {
    std::vector<LdbArrayView> views(nColumns);
    for (size_t c = 0; c < nColumns; c++) views[c] = *reinterpret_cast<const LdbArrayView*>(columns[c]);
