@@ -243,6 +243,22 @@ def balances_and_quantities(sf: float) -> Dict[str, np.ndarray]:
             "ps_availqty": unif(stream(SEED["ps_availqty"], 4 * n_p), 1, 9999)}
 
 
+# suppliers whose comment carries "Customer … Complaints" (dbgen mk_supp: one supplier in a thousand gets a Better-Business-Bureau remark,
+# half of them complaints): drawn from two streams of their own, so Q16's NOT IN needs no generated text
+SEED.update({"s_bbb_comment": 202794285, "s_bbb_type": 753643799})
+
+
+def complaint_suppliers(sf: float) -> np.ndarray:
+    n_s = int(10000 * sf)
+    bad_press, kind = unif(stream(SEED["s_bbb_comment"], n_s), 1, 10000), unif(stream(SEED["s_bbb_type"], n_s), 0, 100)
+    return (np.flatnonzero((bad_press <= 10) & (kind < 50)) + 1).astype(np.int32)
+
+
+def type_name(index: int) -> str:
+    a, b, c = TYPE_SYLLABLES
+    return f"{a[index // 25]} {b[index // 5 % 5]} {c[index % 5]}"
+
+
 def container_index(name: str) -> int:
     a, b = name.split()
     return CONTAINER_SYLLABLES[0].index(a) * 8 + CONTAINER_SYLLABLES[1].index(b)

@@ -364,7 +364,7 @@ def test_data_also_reproduces_q2_q8_q11_q20_q22(sf1):
     (minimum-cost supplier per part, ORDER BY balance: s_acctbal / s_name / n_name / p_partkey / p_mfgr of the 100 rows, tpchSf1.test:19872-19971),
     Q8 (p_type = 'ECONOMY ANODIZED STEEL', market share per year, :20596-20597), Q11 (1048 rows, :113-1160), Q20 (p_name LIKE 'forest%',
     a correlated 0.5 * sum per (part, supplier): the 186 supplier names, :20012-20197) and Q22 (country code = 10 + nation, NOT EXISTS, :20387-20393).
-    With these, 20 of the 22 answers are reproduced on the generator (Q13 and Q16 read generated comment text)."""
+    (Q16 follows below; Q13 reads generated comment text.)"""
     from fractions import Fraction
     from lingodb_b200 import datagen
     cat = lambda t, k: np.concatenate([c[k] for c in sf1[t].chunks])
@@ -428,3 +428,26 @@ def test_data_also_reproduces_q2_q8_q11_q20_q22(sf1):
     has_order[ocust] = True
     sel = listed & (bal * int(positive.sum()) > int(bal[positive].sum())) & ~has_order[1:]
     assert [[str(c), str(int((sel & (code == c)).sum())), dec(int(bal[sel & (code == c)].sum()), 2)] for c in (13, 17, 18, 23, 29, 30, 31)] == GOLD["q22_rows"]
+
+
+def test_data_also_reproduces_q16(sf1):
+    """Q16 (tpchSf1.test:1352-19665, 18 314 rows): count(distinct ps_suppkey) per (brand, type, size) with an anti join against the suppliers
+    whose comment holds 'Customer … Complaints' — dbgen marks those with two streams of their own, so no comment text is needed; the rows
+    carry the full three-syllable type names.  21 of the 22 answers are then reproduced on the generator (Q13 reads o_comment text)."""
+    import hashlib
+    cat = lambda t, k: np.concatenate([c[k] for c in sf1[t].chunks])
+    pspart, pssupp = cat("partsupp", "ps_partkey"), cat("partsupp", "ps_suppkey")
+    pa = dbgen.part_attributes(1.0)
+    t1, t2, _ = dbgen.TYPE_SYLLABLES
+    brand, ptype, size = pa["p_brand"], pa["p_type"], pa["p_size"]
+    medium_polished = (ptype // 25 == t1.index("MEDIUM")) & (ptype // 5 % 5 == t2.index("POLISHED"))
+    part_ok = (brand != 45) & ~medium_polished & np.isin(size, [49, 14, 23, 45, 19, 3, 36, 9])
+    m = part_ok[pspart - 1] & ~np.isin(pssupp, dbgen.complaint_suppliers(1.0))
+    groups = {}
+    for p, s_ in zip(pspart[m].tolist(), pssupp[m].tolist()):
+        groups.setdefault((int(brand[p - 1]), int(ptype[p - 1]), int(size[p - 1])), set()).add(s_)
+    rows = sorted((-len(v), "Brand#%d" % b, dbgen.type_name(t), sz) for (b, t, sz), v in groups.items())
+    got = [[b, t, str(sz), str(-n)] for n, b, t, sz in rows]
+    want = GOLD["q16"]
+    assert len(got) == want["rows"] and got[:3] == want["first"] and got[-3:] == want["last"]
+    assert hashlib.sha256("\n".join("\t".join(r) for r in got).encode()).hexdigest() == want["sha256"]
